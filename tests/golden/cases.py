@@ -1,0 +1,134 @@
+"""Seeded synthetic inputs shared by the golden-vector generator (which feeds them to the real
+reference) and the tests (which feed them to the oracle and to the CUDA path).
+
+Every case returns a dict: samples (N,P) f64 C-order  | list of per-chain arrays,
+weights (N,) f64 | list | None, names, ranges {name: (lo|None, hi|None)}, settings {},
+pairs [(jx, jy), ...] 2D densities to evaluate, kwargs_1d / kwargs_2d: list of per-call overrides.
+"""
+
+import hashlib
+
+import numpy as np
+
+
+def _ar1_chol(P, rho):
+    R = rho ** np.abs(np.subtract.outer(np.arange(P), np.arange(P)))
+    return np.linalg.cholesky(R)
+
+
+def case_mix3():
+    """C1-like: bimodal x0, correlated (x1,x2) at 0.5 (shear branch), Exponential weights."""
+    rng = np.random.default_rng(10)
+    N = 60000
+    comp = rng.random(N) < 0.5
+    x0 = np.where(comp, rng.normal(-1.0, 2.0 / 3, N), rng.normal(1.0, 2.0 / 3, N))
+    z = rng.normal(size=(N, 2))
+    x1 = 3.0 + 0.5 * z[:, 0]
+    x2 = -20.0 + 4.0 * (0.5 * z[:, 0] + np.sqrt(0.75) * z[:, 1])
+    X = np.ascontiguousarray(np.stack([x0, x1, x2], axis=1))
+    w = np.random.default_rng(11).exponential(1.0, N)
+    return dict(samples=X, weights=w, names=["a", "b", "c"], ranges={}, settings={},
+                pairs=[(0, 1), (0, 2), (1, 2), (2, 1)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+def case_unit5():
+    """Unit weights, five nearly independent parameters on very different scales/offsets
+    (plain branch with the TNC step; fp32-hazard offsets mean/sigma ~ 150)."""
+    rng = np.random.default_rng(21)
+    N = 40000
+    Z = rng.normal(size=(N, 5)).dot(_ar1_chol(5, 0.15).T)
+    sig = np.array([1e-4, 3.0, 50.0, 0.02, 1.0])
+    mu = sig * np.array([150.0, -40.0, 0.0, 77.0, 3.0])
+    X = np.ascontiguousarray(mu + sig * Z)
+    return dict(samples=X, weights=None, names=["p%d" % i for i in range(5)], ranges={}, settings={},
+                pairs=[(0, 1), (1, 2), (0, 4), (3, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+def case_bounded():
+    """C3-like: hard priors (lower / upper / both / far-away bound that gets dropped)."""
+    rng = np.random.default_rng(2025)
+    N = 50000
+    P = 5
+    L = _ar1_chol(P, 0.5)
+    lo = np.array([-0.5, -np.inf, -1.5, -np.inf, -30.0])
+    hi = np.array([np.inf, 1.0, 1.5, np.inf, np.inf])
+    out = np.empty((0, P))
+    while out.shape[0] < N:
+        Z = rng.normal(size=(N, P)).dot(L.T)
+        ok = np.all((Z > lo) & (Z < hi), axis=1)
+        out = np.vstack([out, Z[ok]])
+    X = np.ascontiguousarray(out[:N] * np.array([1.0, 2.0, 0.5, 1.0, 1.0]) + np.array([0, 0, 0, 5.0, 0]))
+    w = np.random.default_rng(2026).exponential(1.0, N)
+    ranges = {"q0": (-0.5, None), "q1": (None, 2.0), "q2": (-0.75, 0.75), "q4": (-30.0, None)}
+    return dict(samples=X, weights=w, names=["q%d" % i for i in range(P)], ranges=ranges, settings={},
+                pairs=[(0, 1), (0, 2), (1, 3), (2, 0), (3, 4), (0, 3)],
+                kwargs_1d=[{}, {"boundary_correction_order": 0}, {"boundary_correction_order": 2},
+                           {"mult_bias_correction_order": 0}, {"mult_bias_correction_order": 2},
+                           {"smooth_scale_1D": 0.3}, {"smooth_scale_1D": 2.0}, {"fine_bins": 512}],
+                kwargs_2d=[{}, {"boundary_correction_order": 0, "fine_bins_2D": 128},
+                           {"mult_bias_correction_order": 0, "fine_bins_2D": 128},
+                           {"smooth_scale_2D": 0.3, "fine_bins_2D": 128},
+                           {"smooth_scale_2D": 1.5, "fine_bins_2D": 128},
+                           {"mult_bias_correction_order": 2, "fine_bins_2D": 100}])
+
+
+def case_highcorr():
+    """Strong correlations: 0.93 (scaled 512^2 grid, shear), -0.995 (> max_corr_2D, rule of thumb),
+    and -0.93."""
+    rng = np.random.default_rng(77)
+    N = 50000
+    z = rng.normal(size=(N, 4))
+    x0 = z[:, 0]
+    x1 = 0.93 * z[:, 0] + np.sqrt(1 - 0.93**2) * z[:, 1]
+    x2 = -0.995 * z[:, 0] + np.sqrt(1 - 0.995**2) * z[:, 2]
+    x3 = -0.93 * z[:, 0] + np.sqrt(1 - 0.93**2) * z[:, 3]
+    X = np.ascontiguousarray(np.stack([x0, 10 + 3 * x1, x2 * 0.1, x3], axis=1))
+    w = 1.0 + np.random.default_rng(78).poisson(2.0, N).astype(np.float64)
+    return dict(samples=X, weights=w, names=["h0", "h1", "h2", "h3"], ranges={}, settings={},
+                pairs=[(0, 1), (0, 2), (0, 3), (1, 3)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+def case_chains():
+    """C4-like: 4 chains, integer weights, mean-shifted chains -> Gelman-Rubin + cov."""
+    rng = np.random.default_rng(777)
+    P = 6
+    L = _ar1_chol(P, 0.7)
+    chains, weights, loglikes = [], [], []
+    for c in range(4):
+        n = 9000 + 500 * c
+        Z = rng.normal(size=(n, P)).dot(L.T) + 0.05 * rng.normal(size=P)
+        chains.append(np.ascontiguousarray(Z * np.array([1, 10, 0.1, 1, 1, 3.0]) + np.array([0, 100, 0, -5, 0, 0])))
+        weights.append(1.0 + rng.poisson(2.0, n).astype(np.float64))
+        loglikes.append(0.5 * np.sum(Z**2, axis=1))  # the reference's getSeparateChains needs loglikes
+    return dict(samples=chains, weights=weights, loglikes=loglikes, names=["g%d" % i for i in range(P)], ranges={}, settings={},
+                pairs=[(0, 1), (2, 5)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+CASES = {
+    "mix3": case_mix3,
+    "unit5": case_unit5,
+    "bounded": case_bounded,
+    "highcorr": case_highcorr,
+    "chains": case_chains,
+}
+
+
+def input_digest(case):
+    h = hashlib.sha256()
+    s = case["samples"]
+    for a in (s if isinstance(s, list) else [s]):
+        h.update(np.ascontiguousarray(a).tobytes())
+    w = case["weights"]
+    if w is not None:
+        for a in (w if isinstance(w, list) else [w]):
+            h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def grid_stride(size):
+    """Golden 2D grids larger than 256^2 are stored on a strided subsample to keep fixtures small."""
+    return 1 if size <= 256 else max(1, size // 128)
+
+
+def kw_tag(kw):
+    return "default" if not kw else ",".join("%s=%s" % (k, kw[k]) for k in sorted(kw))

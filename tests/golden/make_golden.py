@@ -1,0 +1,92 @@
+"""Generate golden vectors by running the UNMODIFIED reference (getdist imported from
+/root/reference) on the seeded cases in cases.py.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Outputs tests/golden/<case>.npz.  The reference's private bandwidth helpers are wrapped (not
+modified) so that the bandwidths they return can be recorded next to the density grids.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, "/root/reference")
+
+import getdist  # noqa: E402
+from getdist import MCSamples  # noqa: E402
+
+from cases import CASES, grid_stride, input_digest, kw_tag  # noqa: E402
+
+
+def run_case(name):
+    case = CASES[name]()
+    out = {"digest": np.array(input_digest(case)), "getdist_version": np.array(getdist.__version__)}
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"],
+                   ranges=case["ranges"] or None, sampler="uncorrelated", loglikes=case.get("loglikes"), settings=case["settings"] or None)
+    rec = {}
+    orig1d = mc.getAutoBandwidth1D
+    orig2d = mc.getAutoBandwidth2D
+
+    def wrap1d(*a, **k):
+        r = orig1d(*a, **k)
+        rec["h1d"] = r
+        return r
+
+    def wrap2d(*a, **k):
+        r = orig2d(*a, **k)
+        rec["h2d"] = r
+        return r
+
+    mc.getAutoBandwidth1D = wrap1d
+    mc.getAutoBandwidth2D = wrap2d
+
+    out["means"] = mc.getMeans()
+    out["vars"] = mc.getVars()
+    out["cov"] = mc.getCov()
+    out["corr"] = mc.getCorrelationMatrix()
+    out["norm"] = np.array(mc.norm)
+    out["max_mult"] = np.array(mc.max_mult)
+    out["mean_mult"] = np.array(mc.mean_mult)
+    if mc.chain_offsets is not None:
+        out["chain_offsets"] = np.asarray(mc.chain_offsets)
+        out["gelman_rubin"] = np.array(mc.getGelmanRubin())
+        out["gelman_rubin_eig"] = mc.getGelmanRubinEigenvalues()
+        out["gelman_rubin_3"] = np.array(mc.getGelmanRubin(nparam=3))
+    P = len(case["names"])
+    # quantiles used by _initParam, straight from confidence()
+    fr = np.array([0.001, 0.999] + list(np.linspace(0.1, 0.9, 9)))
+    out["quantile_fracs"] = fr
+    out["quantiles"] = np.array([mc.confidence(j, fr) for j in range(P)])
+    for kw in case["kwargs_1d"]:
+        tag = kw_tag(kw)
+        for j in range(P):
+            rec.clear()
+            d = mc.get1DDensityGridData(j, **kw)
+            par = mc.paramNames.names[j]
+            out["d1/%s/%d/P" % (tag, j)] = d.P
+            out["d1/%s/%d/x" % (tag, j)] = np.array([d.x[0], d.x[-1], d.x.size])
+            out["d1/%s/%d/par" % (tag, j)] = np.array(
+                [par.range_min, par.range_max, par.sigma_range, par.param_min, par.param_max, par.err, par.mean,
+                 float(par.has_limits_bot), float(par.has_limits_top),
+                 par.kde_h if getattr(par, "kde_h", None) is not None else np.nan,
+                 rec.get("h1d", np.nan)])
+    for kw in case["kwargs_2d"]:
+        tag = kw_tag(kw)
+        for (jx, jy) in case["pairs"]:
+            rec.clear()
+            d = mc.get2DDensity(jx, jy, **kw)
+            st = grid_stride(d.P.shape[0])
+            out["d2/%s/%d_%d/P" % (tag, jx, jy)] = d.P[::st, ::st]
+            out["d2/%s/%d_%d/xy" % (tag, jx, jy)] = np.array([d.x[0], d.x[-1], d.x.size, d.y[0], d.y[-1], d.y.size])
+            out["d2/%s/%d_%d/h" % (tag, jx, jy)] = np.array(rec.get("h2d", (np.nan, np.nan, np.nan)), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or list(CASES)):
+        run_case(nm)
