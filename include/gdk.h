@@ -1,0 +1,203 @@
+/*
+ * gdk.h -- C-ABI of the B200-native GetDist density kernel library (libgdk.so).
+ *
+ * The reference (cmbant/getdist 1.7.7) is pure Python and has NO FFI for this path:
+ * the boundary it offers is the Python method surface of MCSamples / Chains / WeightedSamples.
+ * Each entry point below names the reference methods (file:line under /root/reference/getdist/)
+ * whose N-sized / grid-sized arithmetic it replaces.  The host-side mirror of those methods
+ * (getdist_b200/mcsamples.py) is the only caller; it binds these symbols with ctypes
+ * (getdist_b200/_abi.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int32: 0 = OK, negative = error (text via gdk_last_error()).
+ *   - per-density soft failures (bandwidth optimiser failed -> reference fallback applied) are
+ *     reported in the result structs' `status` bit mask, never as a function error.
+ *   - plain pointers and sizes only; all host pointers are BORROWED for the duration of the call.
+ *   - output buffers are caller-allocated.  `P_out` may be a host pointer or a device pointer
+ *     (flag GDK_OUT_DEVICE) so that a caller holding a torch tensor can all-gather it with NCCL.
+ *   - calls on one context must be serialised by the caller (the reference is single-threaded).
+ *   - all arithmetic on the path is float64 (+ exact 64-bit fixed-point weight accumulation).
+ */
+#ifndef GDK_H
+#define GDK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gdk_ctx gdk_ctx;
+
+#define GDK_ABI_VERSION 1
+
+/* error codes */
+#define GDK_OK 0
+#define GDK_ERR_CUDA (-1)
+#define GDK_ERR_ARG (-2)
+#define GDK_ERR_STATE (-3)
+#define GDK_ERR_NOMEM (-4)
+#define GDK_ERR_UNSUPPORTED (-5)
+
+/* flags for the batch calls */
+#define GDK_OUT_DEVICE 1u /* P_out is a device pointer */
+
+/* per-density status bits (result structs) */
+#define GDK_ST_BW_FALLBACK 1u    /* 1D: ISJ root failed or too small -> rule-of-thumb (mcsamples.py:1258-1268)   */
+                                 /* 2D: optimiser failed -> fallback widths (mcsamples.py:1336-1345)            */
+#define GDK_ST_BW_FAILED_NONE 2u /* 1D: gaussian_kde_bandwidth_binned returned None (kde_bandwidth.py:133-135)   */
+#define GDK_ST_USED_BRENT 4u     /* 1D: second-root guard replaced the fsolve root (kde_bandwidth.py:124-131)    */
+#define GDK_ST_SMALL_SMOOTH 8u   /* smoothing scale < 2 bins: host logs the reference's warning (:1579, :1860)   */
+#define GDK_ST_ZERO_MAX 16u      /* max(P)==0: host raises DensitiesError (densities.py:85-86)                   */
+#define GDK_ST_FALLBACK_T 32u    /* 2D: fallback_t replaced t* (kde_bandwidth.py:163-173)                        */
+#define GDK_ST_AMISE_CORR 64u    /* 2D: fixed-correlation AMISE minimum accepted (kde_bandwidth.py:275-288)      */
+#define GDK_ST_AMISE_FULL 128u   /* 2D: 3-parameter AMISE minimum accepted (kde_bandwidth.py:292-304)            */
+#define GDK_ST_BIAS_NEG 256u     /* 2D: AMISE bias term negative at the closed-form h (reference raises)         */
+#define GDK_ST_NONFINITE 512u    /* a non-finite intermediate was met; treated as optimiser failure              */
+
+/* 2D bandwidth branch (mcsamples.py:1347-1409) */
+#define GDK_BW2D_FIXED 0 /* smooth_scale_2D >= 0: rx, ry given in bins by the host       */
+#define GDK_BW2D_PLAIN 1 /* KernelOptimizer2D on the pair's own histogram                */
+#define GDK_BW2D_SHEAR 2 /* shear branch: re-bin (p1, r0*xi + r1*xj), optimise, de-rotate */
+#define GDK_BW2D_RULE 3  /* rule of thumb: sigma_range / N_eff^(1/6)                     */
+
+/* ---------------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------------- */
+int32_t gdk_abi_version(void);
+int32_t gdk_create(int32_t device, gdk_ctx** out);
+void gdk_destroy(gdk_ctx* ctx);
+const char* gdk_last_error(gdk_ctx* ctx);
+/* pinned host staging buffers for callers that want full-rate H2D (bench e2e path) */
+int32_t gdk_alloc_pinned(uint64_t bytes, void** out);
+int32_t gdk_free_pinned(void* p);
+/* number of kernel launches issued by this context since creation (bench `gpu_launches`) */
+int64_t gdk_launch_count(gdk_ctx* ctx);
+/* CUDA-event time (ms) of the tagged phase of the most recent batch call:
+ * 0 = 1D histogram sweep, 1 = 1D grid stage, 2 = 2D histogram pass, 3 = 2D shear re-bin,
+ * 4 = 2D transforms, 5 = 2D bandwidth, 6 = 2D convolution stage, 7 = moments, 8 = quantiles, 9 = upload */
+double gdk_phase_ms(gdk_ctx* ctx, int32_t phase);
+
+/* ---------------------------------------------------------------------------------------------
+ * data residency -- replaces WeightedSamples.setSamples / Chains.makeSingle state
+ * (chains.py:262-308, 1488-1503) as far as the device copy is concerned.
+ *   X: N x P float64, element (n, j) at X[n*row_stride + j*col_stride] (strides in elements);
+ *      stored on the device column-major (one contiguous N-vector per parameter).
+ *   w: N weights or NULL (unit weights).  Must be >= 0.
+ *   chain_offsets: nchains+1 row offsets (chains.py:1497) or NULL (single chain).
+ * ------------------------------------------------------------------------------------------- */
+int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
+                        int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains);
+
+/* ---------------------------------------------------------------------------------------------
+ * weighted moments -- replaces setMeans/getMeans (chains.py:373-398), getVars (:400-412),
+ * cov/_setCov/getCov (:709-733, 339-361), the w statistics of updateBaseStatistics
+ * (:1340-1352, mcsamples.py:552-562), and the per-chain means/covs of
+ * getGelmanRubinEigenvalues (:1446-1474).  All outputs optional (NULL to skip).
+ *   scalars[8]: sum w, sum w^2, max w, #outliers(w > mult_max), N, min w, 0, 0
+ *   chain_covs: nchains x P x P, centred on the CHAIN mean, normalised by the chain's sum w.
+ * ------------------------------------------------------------------------------------------- */
+int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double* cov, double* scalars, double* xmin,
+                    double* xmax, double* chain_means, double* chain_covs, double* chain_norms);
+
+/* ---------------------------------------------------------------------------------------------
+ * exact weighted order statistics -- replaces initParamConfidenceData + confidence
+ * (chains.py:793-838): value of the first sample, in sorted order, whose inclusive cumulative
+ * weight reaches frac * sum(w); clamped to the last sample.  out[np * nf].
+ * ------------------------------------------------------------------------------------------- */
+int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs,
+                               int32_t nf, double* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * 1D densities -- replaces the body of get1DDensityGridData (mcsamples.py:1517-1686) after
+ * _initParam: _binSamples + bincount (:1486-1498, 1554), getAutoBandwidth1D (:1237-1283) with
+ * gaussian_kde_bandwidth_binned (kde_bandwidth.py:102-135), Kernel1D (:129-135), convolve1D
+ * (convolve.py:196-202), boundary (:1600-1647) and multiplicative bias correction (:1649-1666),
+ * normalize('max') (densities.py:71-92).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gdk_spec1d {
+    int32_t param;                     /* column index                                            */
+    int32_t fine_bins;                 /* F                                                       */
+    double binmin, binmax;             /* grid geometry from _binSamples                          */
+    double range_min, range_max;       /* par.range_min/max after _initParam                      */
+    double param_min, param_max;       /* sample min/max                                          */
+    double sigma_range, err;           /* par.sigma_range, par.err (std dev)                      */
+    double neff;                       /* N_eff (par.N_eff_kde)                                   */
+    double smooth_scale_1D;            /* <=0 auto, <1 in units of err, else in units of width    */
+    double width;                      /* paramrange/(num_bins-1)                                 */
+    int32_t boundary_correction_order; /* -1 off, 0, 1, 2                                         */
+    int32_t mult_bias_correction_order;
+    int32_t has_limits_bot, has_limits_top;
+} gdk_spec1d;
+
+typedef struct gdk_result1d {
+    double kde_h;     /* par.kde_h (fraction of bin range, after the small-h fallback)            */
+    double h_raw;     /* ISJ root before the fallback test (NaN if None)                          */
+    double smooth_1D; /* kernel std dev in bins, after clipping                                   */
+    int32_t winw;
+    uint32_t status;
+    int32_t n_feval; /* fixed-point evaluations used by the root finder                           */
+    int32_t pad;
+} gdk_result1d;
+
+/* P_out: n x max(fine_bins) doubles, density i at P_out + i * stride (stride in doubles). */
+int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, int64_t stride,
+                            gdk_result1d* res, uint32_t flags);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2D densities -- replaces the body of get2DDensityGridData (mcsamples.py:1748-1990) after
+ * _initParamRanges: _binSamples x2 + _make2Dhist (:1821-1827, 1724-1728), getAutoBandwidth2D
+ * (:1285-1419) with KernelOptimizer2D (kde_bandwidth.py:146-309) and kde.bin_samples (:76-87),
+ * the kernel build (:1857-1867), convolve2D (convolve.py:205-212, 405-436), boundary and bias
+ * corrections (:1905-1976, masks :1688-1712), normalize('max').
+ * Grids are stored [y][x] (mcsamples.py:1725).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gdk_spec2d {
+    int32_t px, py;                    /* column indices of the x and y parameters                */
+    int32_t fine_bins;                 /* G for this pair (may be scaled up, :1812-1819)          */
+    int32_t base_fine_bins;            /* G used for the shear re-binning (:1373-1375)            */
+    double xbinmin, xbinmax, ybinmin, ybinmax;
+    double x_sigma_range, y_sigma_range;
+    double x_err, y_err;
+    double neff;
+    double corr;                       /* actual correlation handed to getAutoBandwidth2D          */
+    double kernel_corr;                /* correlation used for the kernel when bw_mode == FIXED    */
+    double max_corr_2D;
+    double rx_fixed, ry_fixed;         /* bw_mode FIXED: smoothing in bins                        */
+    double smooth_scale_2D;            /* multiplies the auto bandwidth (abs value), :1848         */
+    int32_t bw_mode;                   /* GDK_BW2D_*                                              */
+    int32_t boundary_correction_order; /* -1 off, 0, 1                                            */
+    int32_t mult_bias_correction_order;
+    int32_t x_has_bot, x_has_top, y_has_bot, y_has_top;
+    /* shear branch (host computes the 2x2 Cholesky algebra, :1364-1369) */
+    int32_t shear_i, shear_j;          /* p1 = X[:, i];  p2 = r0*X[:, i] + r1*X[:, j]             */
+    int32_t shear_swapped;             /* pary.has_limits: (i, j) = (py, px) and hx<->hy at the end */
+    double r0, r1;
+    double S00, S10, S11;              /* S * ichol[0,0], lower triangular                        */
+    double p1_min, p1_max;             /* range of p1 (imin/imax or sample min/max +- 10%)        */
+} gdk_spec2d;
+
+typedef struct gdk_result2d {
+    double hx, hy, c;   /* bandwidth matrix in parameter units as returned by getAutoBandwidth2D  */
+    double rx, ry;      /* smoothing in bins                                                      */
+    double t_star;      /* fixed point (NaN if not run)                                           */
+    int32_t winw;
+    uint32_t status;
+    int32_t n_brent;    /* fixed-point evaluations used by Brent                                  */
+    int32_t pad;
+} gdk_result2d;
+
+/* P_out: densities packed back to back; density i (G_i x G_i doubles, [y][x]) at P_out + offsets[i]. */
+int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out,
+                            const int64_t* offsets, gdk_result2d* res, uint32_t flags);
+
+/* raw histograms (test hooks; also the unit the `hist HBM GB/s` roofline figure is measured on):
+ * weighted fine-grid histograms exactly as _binSamples + bincount build them.                   */
+int32_t gdk_hist1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* bins_out, int64_t stride);
+int32_t gdk_hist2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* bins_out,
+                         const int64_t* offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDK_H */

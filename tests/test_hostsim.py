@@ -1,0 +1,147 @@
+"""CPU tests of the grid-stage DEVICE arithmetic: the .cuh headers the CUDA kernels are built from
+are compiled for the host (tests/hostsim, one-thread cooperative group) and compared with numpy/scipy
+and with the oracle.  Checks the math, not the CUDA execution (that is what the -m gpu tests do)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import fftpack
+from scipy.optimize import brentq, fsolve
+
+from cases import kw_tag
+from helpers import load_case, make_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="session")
+def hs():
+    src = os.path.join(HERE, "hostsim", "hostsim.cpp")
+    out = os.path.join(HERE, "hostsim", "libhostsim.so")
+    deps = [src] + [os.path.join(ROOT, "getdist_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "getdist_b200", "csrc"))
+                    if f.endswith((".cuh", ".h"))] + [os.path.join(ROOT, "include", "gdk.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
+    return C.CDLL(out)
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 100, 384, 7])
+def test_fft_dct(hs, n):
+    rng = np.random.default_rng(n)
+    nl = 3
+    x = rng.normal(size=(nl, n)) + 1j * rng.normal(size=(nl, n))
+    re, im = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    ore, oim = np.empty_like(re), np.empty_like(im)
+    hs.hs_fft(dptr(re), dptr(im), n, nl, dptr(ore), dptr(oim))
+    ref = np.fft.fft(x, axis=1)
+    assert np.max(np.abs(ore + 1j * oim - ref)) < 1e-13 * n * np.max(np.abs(ref))
+    r = np.ascontiguousarray(rng.random((nl, n)))
+    out = np.empty_like(r)
+    hs.hs_dct2(dptr(r), n, nl, dptr(out))
+    ref = fftpack.dct(r, axis=1)
+    assert np.max(np.abs(out - ref)) < 2e-15 * n * np.max(np.abs(ref))
+
+
+CUBICS = [(1.0, 0.5, 0.3), (5.0, 0.01, 0.02), (-2.0, -1.0, 0.7), (100.0, 3.0, 0.0123), (0.3, 2.0, 0.11)]
+
+
+@pytest.mark.parametrize("a,b,r", CUBICS)
+def test_brentq_port_matches_scipy(hs, a, b, r):
+    pts = []
+
+    def f(x):
+        pts.append(x)
+        d = x - r
+        return a * d * d * d + b * d
+
+    for (xa, xb, xtol) in [(0.0, 1.0, 1e-6), (r - 0.4, r + 0.9, 1e-3), (0.0, 0.1 + r, 1e-12)]:
+        pts.clear()
+        ref = brentq(f, xa, xb, xtol=xtol)
+        xs = np.zeros(512)
+        xo = C.c_double()
+        nf = C.c_int()
+        st = hs.hs_brentq(C.c_double(a), C.c_double(b), C.c_double(r), C.c_double(xa), C.c_double(xb),
+                          C.c_double(xtol), C.byref(xo), dptr(xs), C.byref(nf))
+        assert st == 0
+        assert xo.value == ref
+        assert nf.value == len(pts)
+        assert np.array_equal(xs[: nf.value], np.array(pts))
+
+
+@pytest.mark.parametrize("a,b,r", CUBICS)
+def test_hybrd_port_matches_fsolve(hs, a, b, r):
+    pts = []
+
+    def f(x):
+        pts.append(float(x[0]))
+        d = x[0] - r
+        return [a * d * d * d + b * d]
+
+    for x0 in [0.53 * r + 0.01, 1.7 * r + 0.05, 0.2]:
+        pts.clear()
+        ref = fsolve(f, x0, xtol=x0 / 20, factor=1)[0]
+        xs = np.zeros(512)
+        xo = C.c_double()
+        nf = C.c_int()
+        hs.hs_hybrd1(C.c_double(a), C.c_double(b), C.c_double(r), C.c_double(x0), C.c_double(x0 / 20),
+                     C.c_double(1.0), C.byref(xo), dptr(xs), C.byref(nf))
+        # scipy makes extra bookkeeping evaluations at x0 (shape check etc.): compare the iterates
+        # away from x0 (x0 itself and the forward-difference point x0*(1+1.5e-8) are dropped)
+        ours = xs[: nf.value]
+        theirs = np.array(pts)
+        ours = ours[np.abs(ours - x0) > 1e-6 * abs(x0)]
+        theirs = theirs[np.abs(theirs - x0) > 1e-6 * abs(x0)]
+        assert len(ours) == len(theirs), (ours, theirs)
+        np.testing.assert_allclose(ours, theirs, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(xo.value, ref, rtol=1e-12)
+
+
+class Spec1D(C.Structure):
+    _fields_ = [("param", C.c_int32), ("fine_bins", C.c_int32), ("binmin", C.c_double), ("binmax", C.c_double),
+                ("range_min", C.c_double), ("range_max", C.c_double), ("param_min", C.c_double),
+                ("param_max", C.c_double), ("sigma_range", C.c_double), ("err", C.c_double), ("neff", C.c_double),
+                ("smooth_scale_1D", C.c_double), ("width", C.c_double), ("boundary_correction_order", C.c_int32),
+                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32)]
+
+
+class Res1D(C.Structure):
+    _fields_ = [("kde_h", C.c_double), ("h_raw", C.c_double), ("smooth_1D", C.c_double), ("winw", C.c_int32),
+                ("status", C.c_uint32), ("n_feval", C.c_int32), ("pad", C.c_int32)]
+
+
+@pytest.mark.parametrize("name", ["mix3", "unit5", "bounded", "highcorr", "chains"])
+def test_kde1d_core_vs_oracle_and_golden(hs, name):
+    from oracle.getdist_oracle import bin_geometry, bin_indices
+
+    case, g = load_case(name)
+    o = make_oracle(case)
+    for kw in case["kwargs_1d"]:
+        tag = kw_tag(kw)
+        for j in range(o.n):
+            d = o.density_1d(j, **kw)
+            par = o.pars[j]
+            s = dict(o.settings)
+            s.update(kw)
+            F = s["fine_bins"]
+            binmin, binmax, fw = bin_geometry(par, F)
+            bins = np.bincount(bin_indices(o.samples[:, j], binmin, fw), weights=o.weights, minlength=F)
+            sp = Spec1D(j, F, binmin, binmax, par.range_min, par.range_max, par.param_min, par.param_max,
+                        par.sigma_range, par.err, o._neff(par), s["smooth_scale_1D"],
+                        (par.range_max - par.range_min) / (s["num_bins"] - 1), s["boundary_correction_order"],
+                        s["mult_bias_correction_order"], int(par.has_limits_bot), int(par.has_limits_top))
+            P = np.empty(F)
+            res = Res1D()
+            hs.hs_kde1d(C.byref(sp), dptr(bins), dptr(P), C.byref(res))
+            assert res.winw == d.winw, (name, tag, j)
+            if s["smooth_scale_1D"] <= 0:
+                np.testing.assert_allclose(res.kde_h, d.h, rtol=2e-6)
+            err = np.max(np.abs(P - d.P))
+            gerr = np.max(np.abs(P - g["d1/%s/%d/P" % (tag, j)]))
+            assert err < 1e-7 and gerr < 1e-7, (name, tag, j, err, gerr)
