@@ -1,0 +1,252 @@
+"""ctypes binding of libgdk.so (include/gdk.h).  The library is hand-written CUDA for sm_100a; there is no
+CPU fallback: if the shared library is missing or no CUDA device is present, construction fails loudly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgdk.so")
+
+GDK_OUT_DEVICE = 1
+
+ST_BW_FALLBACK = 1
+ST_BW_FAILED_NONE = 2
+ST_USED_BRENT = 4
+ST_SMALL_SMOOTH = 8
+ST_ZERO_MAX = 16
+ST_FALLBACK_T = 32
+ST_AMISE_CORR = 64
+ST_AMISE_FULL = 128
+ST_BIAS_NEG = 256
+ST_NONFINITE = 512
+
+BW2D_FIXED, BW2D_PLAIN, BW2D_SHEAR, BW2D_RULE = 0, 1, 2, 3
+
+PHASES = ["hist1d", "kde1d", "hist2d", "shear", "xform2d", "bw2d", "conv2d", "moments", "quantiles", "upload"]
+
+
+class Spec1D(C.Structure):
+    _fields_ = [("param", C.c_int32), ("fine_bins", C.c_int32), ("binmin", C.c_double), ("binmax", C.c_double),
+                ("range_min", C.c_double), ("range_max", C.c_double), ("param_min", C.c_double),
+                ("param_max", C.c_double), ("sigma_range", C.c_double), ("err", C.c_double), ("neff", C.c_double),
+                ("smooth_scale_1D", C.c_double), ("width", C.c_double), ("boundary_correction_order", C.c_int32),
+                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32)]
+
+
+class Result1D(C.Structure):
+    _fields_ = [("kde_h", C.c_double), ("h_raw", C.c_double), ("smooth_1D", C.c_double), ("winw", C.c_int32),
+                ("status", C.c_uint32), ("n_feval", C.c_int32), ("pad", C.c_int32)]
+
+
+class Spec2D(C.Structure):
+    _fields_ = [("px", C.c_int32), ("py", C.c_int32), ("fine_bins", C.c_int32), ("base_fine_bins", C.c_int32),
+                ("xbinmin", C.c_double), ("xbinmax", C.c_double), ("ybinmin", C.c_double), ("ybinmax", C.c_double),
+                ("x_sigma_range", C.c_double), ("y_sigma_range", C.c_double), ("x_err", C.c_double), ("y_err", C.c_double),
+                ("neff", C.c_double), ("corr", C.c_double), ("kernel_corr", C.c_double), ("max_corr_2D", C.c_double),
+                ("rx_fixed", C.c_double), ("ry_fixed", C.c_double), ("smooth_scale_2D", C.c_double),
+                ("bw_mode", C.c_int32), ("boundary_correction_order", C.c_int32),
+                ("mult_bias_correction_order", C.c_int32),
+                ("x_has_bot", C.c_int32), ("x_has_top", C.c_int32), ("y_has_bot", C.c_int32), ("y_has_top", C.c_int32),
+                ("shear_i", C.c_int32), ("shear_j", C.c_int32), ("shear_swapped", C.c_int32),
+                ("r0", C.c_double), ("r1", C.c_double), ("S00", C.c_double), ("S10", C.c_double), ("S11", C.c_double),
+                ("p1_min", C.c_double), ("p1_max", C.c_double)]
+
+
+class Result2D(C.Structure):
+    _fields_ = [("hx", C.c_double), ("hy", C.c_double), ("c", C.c_double), ("rx", C.c_double), ("ry", C.c_double),
+                ("t_star", C.c_double), ("winw", C.c_int32), ("status", C.c_uint32), ("n_brent", C.c_int32),
+                ("pad", C.c_int32)]
+
+
+class GdkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libgdk.so (once).  Raises GdkError if it was not built -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GdkError("libgdk.so not found at %s -- build it with `python -m getdist_b200.build` "
+                       "(needs nvcc; there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+    pd = C.POINTER(C.c_double)
+    lib.gdk_abi_version.restype = i32
+    lib.gdk_create.argtypes = [i32, C.POINTER(vp)]
+    lib.gdk_create.restype = i32
+    lib.gdk_destroy.argtypes = [vp]
+    lib.gdk_destroy.restype = None
+    lib.gdk_last_error.argtypes = [vp]
+    lib.gdk_last_error.restype = C.c_char_p
+    lib.gdk_alloc_pinned.argtypes = [u64, C.POINTER(vp)]
+    lib.gdk_alloc_pinned.restype = i32
+    lib.gdk_free_pinned.argtypes = [vp]
+    lib.gdk_free_pinned.restype = i32
+    lib.gdk_launch_count.argtypes = [vp]
+    lib.gdk_launch_count.restype = i64
+    lib.gdk_phase_ms.argtypes = [vp, i32]
+    lib.gdk_phase_ms.restype = dbl
+    lib.gdk_set_samples.argtypes = [vp, vp, i64, i32, i64, i64, vp, vp, i32]
+    lib.gdk_set_samples.restype = i32
+    lib.gdk_moments.argtypes = [vp] + [vp] * 9
+    lib.gdk_moments.restype = i32
+    lib.gdk_weighted_quantiles.argtypes = [vp, vp, i32, vp, i32, vp]
+    lib.gdk_weighted_quantiles.restype = i32
+    lib.gdk_density1d_batch.argtypes = [vp, i32, vp, vp, i64, vp, u32]
+    lib.gdk_density1d_batch.restype = i32
+    lib.gdk_density2d_batch.argtypes = [vp, i32, vp, vp, vp, vp, u32]
+    lib.gdk_density2d_batch.restype = i32
+    lib.gdk_hist1d_batch.argtypes = [vp, i32, vp, vp, i64]
+    lib.gdk_hist1d_batch.restype = i32
+    lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
+    lib.gdk_hist2d_batch.restype = i32
+    if lib.gdk_abi_version() != 1:
+        raise GdkError("libgdk.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One library context = one device + one resident sample store."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.gdk_create(int(device), C.byref(h))
+        if rc != 0:
+            raise GdkError("gdk_create(device=%d) failed (code %d): no usable CUDA device -- this package has no CPU "
+                           "fallback" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gdk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise GdkError("%s failed (code %d): %s" % (what, rc, self.lib.gdk_last_error(self.h).decode()))
+
+    def set_samples(self, X, w=None, chain_offsets=None):
+        X = np.asarray(X)
+        if X.dtype != np.float64 or X.ndim != 2:
+            raise GdkError("samples must be a 2D float64 array")
+        N, P = X.shape
+        rs, cs = X.strides[0] // 8, X.strides[1] // 8
+        if not ((cs == 1 and rs >= P) or (rs == 1 and cs >= N)):
+            X = np.ascontiguousarray(X)
+            rs, cs = P, 1
+        if w is not None:
+            w = np.ascontiguousarray(w, dtype=np.float64)
+        co = None
+        nch = 0
+        if chain_offsets is not None:
+            co = np.ascontiguousarray(chain_offsets, dtype=np.int64)
+            nch = co.size - 1
+        self._keep = (X, w, co)
+        self._ck(self.lib.gdk_set_samples(self.h, _ptr(X), N, P, rs, cs, _ptr(w), _ptr(co), nch), "gdk_set_samples")
+        self.N, self.P, self.nchains = N, P, max(nch, 1)
+
+    def moments(self):
+        P, nch = self.P, self.nchains
+        out = dict(means=np.empty(P), vars=np.empty(P), cov=np.empty((P, P)), scalars=np.empty(8), xmin=np.empty(P),
+                   xmax=np.empty(P), chain_means=np.empty((nch, P)), chain_covs=np.empty((nch, P, P)),
+                   chain_norms=np.empty(nch))
+        self._ck(self.lib.gdk_moments(self.h, *[_ptr(out[k]) for k in
+                                                ("means", "vars", "cov", "scalars", "xmin", "xmax", "chain_means",
+                                                 "chain_covs", "chain_norms")]), "gdk_moments")
+        return out
+
+    def weighted_quantiles(self, params, fracs):
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        fracs = np.ascontiguousarray(fracs, dtype=np.float64)
+        out = np.empty((params.size, fracs.size))
+        self._ck(self.lib.gdk_weighted_quantiles(self.h, _ptr(params), params.size, _ptr(fracs), fracs.size, _ptr(out)),
+                 "gdk_weighted_quantiles")
+        return out
+
+    def density1d_batch(self, specs):
+        n = len(specs)
+        arr = (Spec1D * n)(*specs)
+        stride = max(s.fine_bins for s in specs)
+        P = np.empty((n, stride))
+        res = (Result1D * n)()
+        self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(P), stride, C.cast(res, C.c_void_p), 0),
+                 "gdk_density1d_batch")
+        return P, list(res)
+
+    def hist1d_batch(self, specs):
+        n = len(specs)
+        arr = (Spec1D * n)(*specs)
+        stride = max(s.fine_bins for s in specs)
+        out = np.empty((n, stride))
+        self._ck(self.lib.gdk_hist1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), stride), "gdk_hist1d_batch")
+        return out
+
+    def density2d_batch(self, specs, out=None, device_ptr=None):
+        n = len(specs)
+        arr = (Spec2D * n)(*specs)
+        sizes = np.array([s.fine_bins * s.fine_bins for s in specs], dtype=np.int64)
+        offsets = np.zeros(n, dtype=np.int64)
+        offsets[1:] = np.cumsum(sizes)[:-1]
+        total = int(sizes.sum())
+        res = (Result2D * n)()
+        if device_ptr is not None:
+            self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), _ptr(offsets),
+                                                  C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density2d_batch")
+            return None, offsets, list(res)
+        if out is None:
+            out = np.empty(total)
+        self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets),
+                                              C.cast(res, C.c_void_p), 0), "gdk_density2d_batch")
+        return out, offsets, list(res)
+
+    def hist2d_batch(self, specs):
+        n = len(specs)
+        arr = (Spec2D * n)(*specs)
+        sizes = np.array([s.fine_bins * s.fine_bins for s in specs], dtype=np.int64)
+        offsets = np.zeros(n, dtype=np.int64)
+        offsets[1:] = np.cumsum(sizes)[:-1]
+        out = np.empty(int(sizes.sum()))
+        self._ck(self.lib.gdk_hist2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets)), "gdk_hist2d_batch")
+        return out, offsets
+
+    def phase_ms(self):
+        return {nm: self.lib.gdk_phase_ms(self.h, i) for i, nm in enumerate(PHASES)}
+
+    def launch_count(self):
+        return int(self.lib.gdk_launch_count(self.h))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (full-rate H2D for the e2e bench path)."""
+    lib = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    if lib.gdk_alloc_pinned(n, C.byref(p)) != 0:
+        raise GdkError("pinned allocation of %d bytes failed" % n)
+    buf = (C.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    arr._gdk_pinned = p  # noqa  (keep-alive; freed explicitly by free_pinned)
+    return arr, p
+
+
+def free_pinned(p):
+    load().gdk_free_pinned(p)

@@ -1,0 +1,628 @@
+// gdk.cu -- host side of libgdk.so: context, resident sample store, and the C-ABI entry points declared in
+// include/gdk.h.  No torch types, no Python: plain CUDA runtime.  All arithmetic runs in the kernels of
+// kernels_*.cuh / kde*_core.cuh; the host code only plans launches and does O(P^2) bookkeeping.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gdk.h"
+#include "host_tables.h"
+#include "kernels_1d.cuh"
+#include "kernels_quant.cuh"
+#include "kernels_stats.cuh"
+#include "gdk_ctx.h"
+#include "gdk_2d.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// helpers
+// -------------------------------------------------------------------------------------------------
+int gdk_fail(gdk_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return gdk_fail(ctx, GDK_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                            cudaGetErrorString(e_));                                                     \
+    } while (0)
+
+std::vector<Seg> gdk_make_segments(const gdk_ctx* c, int64_t seglen) {
+    std::vector<Seg> v;
+    seglen = std::max<int64_t>(2, seglen & ~int64_t(1));
+    for (int ch = 0; ch < c->nchains; ch++) {
+        const int64_t a = c->chain_off[ch], b = c->chain_off[ch + 1];
+        // interior cuts on even rows so that 16-byte vector loads stay aligned
+        int64_t r = a;
+        while (r < b) {
+            int64_t e = std::min(b, ((r + seglen) & ~int64_t(1)));
+            if (e <= r) e = b;
+            v.push_back(Seg{r, e, ch, 0});
+            r = e;
+        }
+    }
+    return v;
+}
+
+int gdk_upload_segs(gdk_ctx* ctx, const std::vector<Seg>& v, DevBuf<Seg>& buf) {
+    int rc = buf.ensure(v.size());
+    if (rc) return gdk_fail(ctx, GDK_ERR_NOMEM, "segment buffer");
+    CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+const Kde1dTablesHost* gdk_tables_for(gdk_ctx* ctx, int n) {
+    auto it = ctx->tables.find(n);
+    if (it != ctx->tables.end()) return &it->second;
+    Kde1dTablesHost t{};
+    if (is_pow2(n) && n >= 2) {
+        std::vector<cplx> tw(n), tw4(n);
+        gdk_fill_roots(tw.data(), n, n);
+        gdk_fill_roots(tw4.data(), 4 * n, n);
+        if (cudaMalloc(&t.tw, n * sizeof(cplx)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&t.tw4, n * sizeof(cplx)) != cudaSuccess) return nullptr;
+        cudaMemcpy(t.tw, tw.data(), n * sizeof(cplx), cudaMemcpyHostToDevice);
+        cudaMemcpy(t.tw4, tw4.data(), n * sizeof(cplx), cudaMemcpyHostToDevice);
+    } else {
+        std::vector<double> c4(4 * (size_t)n);
+        gdk_fill_cos(c4.data(), 4 * n);
+        std::vector<cplx> tw(n);
+        gdk_fill_roots(tw.data(), n, n);
+        if (cudaMalloc(&t.cos4, 4 * (size_t)n * sizeof(double)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&t.twn, n * sizeof(cplx)) != cudaSuccess) return nullptr;
+        cudaMemcpy(t.cos4, c4.data(), 4 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(t.twn, tw.data(), n * sizeof(cplx), cudaMemcpyHostToDevice);
+    }
+    auto r = ctx->tables.emplace(n, t);
+    return &r.first->second;
+}
+
+void PhaseTimer::begin(gdk_ctx* c, int ph) {
+    ctx = c;
+    phase = ph;
+    cudaEventRecord(c->ev0[ph], c->stream);
+}
+void PhaseTimer::end() {
+    cudaEventRecord(ctx->ev1[phase], ctx->stream);
+    ctx->phase_valid[phase] = 1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t gdk_abi_version(void) { return GDK_ABI_VERSION; }
+
+extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
+    if (!out) return GDK_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GDK_ERR_CUDA;
+    if (device < 0 || device >= ndev) return GDK_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return GDK_ERR_CUDA;
+    gdk_ctx* ctx = new gdk_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GDK_ERR_CUDA;
+    }
+    for (int i = 0; i < GDK_NPHASE; i++) {
+        cudaEventCreate(&ctx->ev0[i]);
+        cudaEventCreate(&ctx->ev1[i]);
+        ctx->phase_valid[i] = 0;
+    }
+    gdk_fill_isj_consts(&ctx->isj);
+    *out = ctx;
+    return GDK_OK;
+}
+
+extern "C" void gdk_destroy(gdk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    for (auto& kv : ctx->tables) {
+        cudaFree(kv.second.tw);
+        cudaFree(kv.second.tw4);
+        cudaFree(kv.second.cos4);
+        cudaFree(kv.second.twn);
+    }
+    for (int i = 0; i < GDK_NPHASE; i++) {
+        cudaEventDestroy(ctx->ev0[i]);
+        cudaEventDestroy(ctx->ev1[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
+    delete ctx;  // DevBuf destructors free device memory
+}
+
+extern "C" const char* gdk_last_error(gdk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int32_t gdk_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return GDK_ERR_ARG;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? GDK_OK : GDK_ERR_NOMEM;
+}
+extern "C" int32_t gdk_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? GDK_OK : GDK_ERR_CUDA; }
+extern "C" int64_t gdk_launch_count(gdk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double gdk_phase_ms(gdk_ctx* ctx, int32_t phase) {
+    if (!ctx || phase < 0 || phase >= GDK_NPHASE || !ctx->phase_valid[phase]) return -1.0;
+    float ms = 0;
+    if (cudaEventSynchronize(ctx->ev1[phase]) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0[phase], ctx->ev1[phase]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+// -------------------------------------------------------------------------------------------------
+// data residency
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
+                                   int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (!X || N <= 0 || P <= 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_set_samples: bad shape N=%lld P=%d", (long long)N, P);
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_moments = false;
+    ctx->N = N;
+    ctx->P = P;
+    ctx->ld = (N + 63) & ~int64_t(63);
+    ctx->chain_off.clear();
+    if (chain_offsets && nchains > 0) {
+        if (chain_offsets[0] != 0 || chain_offsets[nchains] != N) return gdk_fail(ctx, GDK_ERR_ARG, "chain_offsets must span [0, N]");
+        for (int i = 0; i <= nchains; i++) {
+            if (i && chain_offsets[i] <= chain_offsets[i - 1]) return gdk_fail(ctx, GDK_ERR_ARG, "empty chain");
+            ctx->chain_off.push_back(chain_offsets[i]);
+        }
+        ctx->nchains = nchains;
+    } else {
+        ctx->chain_off = {0, N};
+        ctx->nchains = 1;
+    }
+    if (ctx->dX.ensure((size_t)ctx->ld * P) || ctx->dW.ensure((size_t)ctx->ld) || ctx->dWq.ensure((size_t)ctx->ld))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "sample store (%lld x %d)", (long long)N, P);
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_UPLOAD);
+    if (col_stride == 1 && row_stride >= P) {
+        // C-ordered rows: chunked H2D into a row-major staging buffer, transposed on the device while the
+        // next chunk is copied (two staging buffers, two streams)
+        int64_t chunk = std::max<int64_t>(1024, (int64_t)(128ll << 20) / ((int64_t)P * 8));
+        chunk = std::min(chunk, N);
+        if (ctx->stage[0].ensure((size_t)chunk * P) || ctx->stage[1].ensure((size_t)chunk * P))
+            return gdk_fail(ctx, GDK_ERR_NOMEM, "staging buffers");
+        cudaEvent_t done[2];
+        CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+        cudaStream_t st[2] = {ctx->stream, ctx->stream2};
+        // stream2 must not start before earlier work on stream (event chain)
+        CK(cudaEventRecord(done[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, done[0], 0));
+        int k = 0;
+        for (int64_t r0 = 0; r0 < N; r0 += chunk, k ^= 1) {
+            const int64_t rows = std::min(chunk, N - r0);
+            if (row_stride == P)
+                CK(cudaMemcpyAsync(ctx->stage[k].p, X + r0 * row_stride, (size_t)rows * P * 8, cudaMemcpyHostToDevice, st[k]));
+            else
+                CK(cudaMemcpy2DAsync(ctx->stage[k].p, (size_t)P * 8, X + r0 * row_stride, (size_t)row_stride * 8, (size_t)P * 8,
+                                     (size_t)rows, cudaMemcpyHostToDevice, st[k]));
+            dim3 g((unsigned)((rows + 31) / 32), (unsigned)((P + 31) / 32));
+            k_transpose_in<<<g, 256, 0, st[k]>>>(ctx->stage[k].p, rows, P, ctx->dX.p, ctx->ld, r0);
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(done[1], ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, done[1], 0));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaEventDestroy(done[0]);
+        cudaEventDestroy(done[1]);
+    } else if (row_stride == 1 && col_stride >= N) {
+        for (int j = 0; j < P; j++)
+            CK(cudaMemcpyAsync(ctx->dX.p + (int64_t)j * ctx->ld, X + (int64_t)j * col_stride, (size_t)N * 8, cudaMemcpyHostToDevice,
+                               ctx->stream));
+    } else {
+        return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "samples must be C- or F-contiguous along one axis (strides %lld, %lld)",
+                        (long long)row_stride, (long long)col_stride);
+    }
+    // weights
+    ctx->unit_weights = (w == nullptr);
+    if (w) {
+        CK(cudaMemcpyAsync(ctx->dW.p, w, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->dW.p, N, 1.0);
+        ctx->launches++;
+    }
+    // weight statistics and fixed-point weights
+    const int nb = ctx->num_sms * 4;
+    if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+    k_wstats<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, N, ctx->scratch.p);
+    ctx->launches++;
+    std::vector<double> part((size_t)nb * 4);
+    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sw = 0, sw2 = 0, mx = -INFINITY, mn = INFINITY;
+    for (int i = 0; i < nb; i++) {
+        sw += part[i * 4 + 0];
+        sw2 += part[i * 4 + 1];
+        mx = std::max(mx, part[i * 4 + 2]);
+        mn = std::min(mn, part[i * 4 + 3]);
+    }
+    if (!(mn >= 0) || !(sw > 0) || !std::isfinite(sw))
+        return gdk_fail(ctx, GDK_ERR_ARG, "weights must be finite, >= 0 and not all zero (min %g, sum %g)", mn, sw);
+    ctx->sum_w = sw;
+    ctx->sum_w2 = sw2;
+    ctx->max_w = mx;
+    ctx->min_w = mn;
+    // scale 2^k with sum(w)*2^k < 2^61 (headroom for rounding of N terms)
+    int e = 0;
+    frexp(sw, &e);  // sw = m * 2^e, m in [0.5, 1)
+    ctx->wshift = 61 - e;
+    ctx->wscale = ldexp(1.0, ctx->wshift);
+    const double mean_mult = sw / (double)N;
+    const double mult_max = (mean_mult * (double)N) / (double)std::min<int64_t>(N / 2, 500);  // mcsamples.py:559
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
+    CK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+    k_make_wq<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, N, ctx->wscale, mult_max, ctx->dWq.p, acc);
+    ctx->launches++;
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    pt.end();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->wq_total = h[0];
+    ctx->n_outliers = (double)h[1];
+    return GDK_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// moments
+// -------------------------------------------------------------------------------------------------
+static int compute_moments(gdk_ctx* ctx) {
+    if (ctx->have_moments) return 0;
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK(cudaSetDevice(ctx->device));
+    const int P = ctx->P, nch = ctx->nchains;
+    const int64_t N = ctx->N;
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_MOMENTS);
+    // pass 1: per-chain sums
+    {
+        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, P));
+        const int64_t seglen = std::max<int64_t>(1 << 14, (N + want - 1) / want);
+        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+        int rc = gdk_upload_segs(ctx, segs, ctx->segs);
+        if (rc) return rc;
+        const size_t np = segs.size() * (size_t)P * 4;
+        if (ctx->scratch.ensure(np)) return gdk_fail(ctx, GDK_ERR_NOMEM, "moment partials");
+        dim3 g((unsigned)segs.size(), (unsigned)P);
+        k_col_sums<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, ctx->scratch.p);
+        ctx->launches++;
+        std::vector<double> part(np);
+        CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->chain_means.assign((size_t)nch * P, 0.0);
+        ctx->chain_norm.assign(nch, 0.0);
+        ctx->xmin.assign(P, INFINITY);
+        ctx->xmax.assign(P, -INFINITY);
+        std::vector<double> swx((size_t)nch * P, 0.0);
+        for (size_t s = 0; s < segs.size(); s++) {
+            const int ch = segs[s].chain;
+            for (int j = 0; j < P; j++) {
+                const double* o = &part[(s * P + j) * 4];
+                swx[(size_t)ch * P + j] += o[0];
+                if (j == 0) ctx->chain_norm[ch] += o[1];
+                ctx->xmin[j] = std::min(ctx->xmin[j], o[2]);
+                ctx->xmax[j] = std::max(ctx->xmax[j], o[3]);
+            }
+        }
+        ctx->means.assign(P, 0.0);
+        double norm = 0;
+        for (int ch = 0; ch < nch; ch++) norm += ctx->chain_norm[ch];
+        ctx->norm = norm;
+        for (int j = 0; j < P; j++) {
+            double t = 0;
+            for (int ch = 0; ch < nch; ch++) {
+                t += swx[(size_t)ch * P + j];
+                ctx->chain_means[(size_t)ch * P + j] = swx[(size_t)ch * P + j] / ctx->chain_norm[ch];
+            }
+            ctx->means[j] = t / norm;
+        }
+    }
+    // pass 2: centred second moments per chain
+    {
+        const int T = (P + COV_T - 1) / COV_T;
+        std::vector<int2> tiles;
+        for (int a = 0; a < T; a++)
+            for (int b = a; b < T; b++) tiles.push_back(int2{a, b});
+        const int nt = (int)tiles.size();
+        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 4 / nt);
+        const int64_t seglen = std::max<int64_t>(1 << 12, (N + want - 1) / want);
+        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+        int rc = gdk_upload_segs(ctx, segs, ctx->segs);
+        if (rc) return rc;
+        const size_t np = segs.size() * (size_t)nt * COV_T * COV_T;
+        if (ctx->scratch.ensure(np) || ctx->dS.ensure((size_t)nch * P * P) || ctx->dmeans.ensure((size_t)nch * P) ||
+            ctx->dtiles.ensure(tiles.size()))
+            return gdk_fail(ctx, GDK_ERR_NOMEM, "covariance partials");
+        CK(cudaMemcpyAsync(ctx->dmeans.p, ctx->chain_means.data(), (size_t)nch * P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        dim3 g((unsigned)segs.size(), (unsigned)nt);
+        k_cov_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, nt, ctx->dtiles.p, ctx->dmeans.p,
+                                                ctx->scratch.p);
+        dim3 g2((unsigned)nt, (unsigned)nch);
+        k_cov_reduce<<<g2, 256, 0, ctx->stream>>>(ctx->scratch.p, ctx->segs.p, (int)segs.size(), nt, ctx->dtiles.p, P, ctx->dS.p);
+        ctx->launches += 2;
+        ctx->chain_S.resize((size_t)nch * P * P);
+        CK(cudaMemcpyAsync(ctx->chain_S.data(), ctx->dS.p, ctx->chain_S.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        pt.end();
+        CK(cudaStreamSynchronize(ctx->stream));
+        // global covariance: sum_c (S_c + W_c d_c d_c^T) / W with d_c = m_c - m  (no cancellation)
+        ctx->cov.assign((size_t)P * P, 0.0);
+        for (int i = 0; i < P; i++)
+            for (int j = i; j < P; j++) {
+                double t = 0;
+                for (int ch = 0; ch < nch; ch++) {
+                    const double di = ctx->chain_means[(size_t)ch * P + i] - ctx->means[i];
+                    const double dj = ctx->chain_means[(size_t)ch * P + j] - ctx->means[j];
+                    t += ctx->chain_S[((size_t)ch * P + i) * P + j] + ctx->chain_norm[ch] * di * dj;
+                }
+                ctx->cov[(size_t)i * P + j] = ctx->cov[(size_t)j * P + i] = t / ctx->norm;
+            }
+    }
+    ctx->have_moments = true;
+    return 0;
+}
+
+extern "C" int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double* cov, double* scalars, double* xmin,
+                               double* xmax, double* chain_means, double* chain_covs, double* chain_norms) {
+    if (!ctx) return GDK_ERR_ARG;
+    int rc = compute_moments(ctx);
+    if (rc) return rc;
+    const int P = ctx->P, nch = ctx->nchains;
+    if (means) memcpy(means, ctx->means.data(), P * 8);
+    if (vars)
+        for (int j = 0; j < P; j++) vars[j] = ctx->cov[(size_t)j * P + j];
+    if (cov) memcpy(cov, ctx->cov.data(), (size_t)P * P * 8);
+    if (scalars) {
+        scalars[0] = ctx->norm;
+        scalars[1] = ctx->sum_w2;
+        scalars[2] = ctx->max_w;
+        scalars[3] = ctx->n_outliers;
+        scalars[4] = (double)ctx->N;
+        scalars[5] = ctx->min_w;
+        scalars[6] = 0;
+        scalars[7] = 0;
+    }
+    if (xmin) memcpy(xmin, ctx->xmin.data(), P * 8);
+    if (xmax) memcpy(xmax, ctx->xmax.data(), P * 8);
+    if (chain_means) memcpy(chain_means, ctx->chain_means.data(), (size_t)nch * P * 8);
+    if (chain_norms) memcpy(chain_norms, ctx->chain_norm.data(), nch * 8);
+    if (chain_covs)
+        for (int ch = 0; ch < nch; ch++)
+            for (size_t e = 0; e < (size_t)P * P; e++)
+                chain_covs[(size_t)ch * P * P + e] = ctx->chain_S[(size_t)ch * P * P + e] / ctx->chain_norm[ch];
+    return GDK_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// weighted quantiles
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf,
+                                          double* out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (!params || !fracs || !out || np <= 0 || nf <= 0 || nf > QMAXF)
+        return gdk_fail(ctx, GDK_ERR_ARG, "gdk_weighted_quantiles: need 1 <= nf <= %d", QMAXF);
+    int rc = compute_moments(ctx);  // column min / max
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int P = ctx->P;
+    for (int i = 0; i < np; i++)
+        if (params[i] < 0 || params[i] >= P) return gdk_fail(ctx, GDK_ERR_ARG, "parameter index %d out of range", params[i]);
+    const int B1_LOG2 = 13, B2_LOG2 = 10;
+    const int B1 = 1 << B1_LOG2, B2 = 1 << B2_LOG2;
+    std::vector<QSlot> slots((size_t)np * QMAXF);
+    memset(slots.data(), 0, slots.size() * sizeof(QSlot));
+    for (int i = 0; i < np; i++) {
+        const unsigned long long klo = f64_to_key(ctx->xmin[params[i]]), khi = f64_to_key(ctx->xmax[params[i]]);
+        for (int s = 0; s < QMAXF; s++) {
+            QSlot& q = slots[(size_t)i * QMAXF + s];
+            q.klo = klo;
+            q.khi = khi;
+            q.below = 0;
+            q.state = 1;  // unused slots stay "resolved"
+            q.value = 0;
+            if (s < nf) {
+                double t = ceil(fracs[s] * (double)ctx->wq_total);
+                if (!(t >= 1.0)) t = 1.0;
+                if (t > (double)ctx->wq_total) t = (double)ctx->wq_total;
+                q.target = (unsigned long long)t;
+                if (q.target > ctx->wq_total) q.target = ctx->wq_total;
+                if (klo == khi) {
+                    q.value = key_to_f64(klo);
+                } else {
+                    q.state = 0;
+                    q.shift = q_shift_for(khi - klo, B1_LOG2);
+                }
+            }
+        }
+    }
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_QUANT);
+    const size_t nslots = slots.size();
+    if (ctx->qslots.ensure(nslots) || ctx->qparams.ensure(np) || ctx->qhist.ensure(nslots * (size_t)std::max(B1 / QMAXF + 1, B2)) ||
+        ctx->qhist.ensure((size_t)np * QMAXF * B2) || ctx->qcand.ensure(nslots * QCAP) || ctx->iscratch.ensure(4))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "quantile buffers");
+    // pass-1 histogram lives at ghist[(p*QMAXF + 0) * B1 ...]; make sure the buffer covers it
+    if (ctx->qhist.ensure((size_t)np * QMAXF * std::max(B1, B2))) return gdk_fail(ctx, GDK_ERR_NOMEM, "quantile histograms");
+    CK(cudaMemcpyAsync(ctx->qslots.p, slots.data(), nslots * sizeof(QSlot), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->qparams.p, params, np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 6 / np);
+    const int64_t seglen = std::max<int64_t>(1 << 15, (ctx->N + want - 1) / want);
+    std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+    rc = gdk_upload_segs(ctx, segs, ctx->segs);
+    if (rc) return rc;
+    dim3 g((unsigned)segs.size(), (unsigned)np);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QMAXF * B2 * 4));
+        CK(cudaFuncSetAttribute(k_qselect, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QCAP * 8));
+        attr_set = true;
+    }
+    // pass 1: shared histogram per parameter
+    CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B1 * 8, ctx->stream));
+    k_qhist<<<g, 256, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
+                                                 ctx->qhist.p);
+    k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B1, 1, 0, B2_LOG2, ctx->qhist.p);
+    ctx->launches += 2;
+    int next_state = 2;
+    for (int iter = 0; iter < 12; iter++) {
+        // refinement pass: one histogram of B2 bins per refining slot
+        CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B2 * 8, ctx->stream));
+        k_qhist<<<g, 256, 2 * nf * B2 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf,
+                                                          B2, 0, ctx->qhist.p);
+        k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B2, 0, next_state, B2_LOG2, ctx->qhist.p);
+        CK(cudaMemsetAsync(ctx->iscratch.p, 0, sizeof(int), ctx->stream));
+        k_qgather<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, ctx->qcand.p);
+        k_qselect<<<(unsigned)nslots, 512, 2 * QCAP * 8, ctx->stream>>>(ctx->qslots.p, nf, ctx->qcand.p, B2_LOG2, ctx->iscratch.p);
+        ctx->launches += 4;
+        int nover = 0;
+        CK(cudaMemcpyAsync(&nover, ctx->iscratch.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (nover == 0) break;
+    }
+    CK(cudaMemcpyAsync(slots.data(), ctx->qslots.p, nslots * sizeof(QSlot), cudaMemcpyDeviceToHost, ctx->stream));
+    pt.end();
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < np; i++)
+        for (int s = 0; s < nf; s++) {
+            const QSlot& q = slots[(size_t)i * QMAXF + s];
+            if (q.state != 1) return gdk_fail(ctx, GDK_ERR_STATE, "quantile selection did not converge (param %d, frac %g)", params[i], fracs[s]);
+            out[(size_t)i * nf + s] = q.value;
+        }
+    return GDK_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// 1D densities
+// -------------------------------------------------------------------------------------------------
+static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gstride_out) {
+    int maxF = 0;
+    std::vector<Hist1dJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        const gdk_spec1d& s = specs[i];
+        if (s.param < 0 || s.param >= ctx->P) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: parameter %d out of range", i, s.param);
+        if (s.fine_bins < 8 || s.fine_bins > (1 << 16)) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: fine_bins %d unsupported", i, s.fine_bins);
+        if (!(s.binmax > s.binmin)) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: empty bin range", i);
+        maxF = std::max(maxF, s.fine_bins);
+        const double fw = (s.binmax - s.binmin) / (s.fine_bins - 1);
+        jobs[i] = Hist1dJob{s.param, s.fine_bins, s.binmin, fw, 1.0 / fw};
+    }
+    const int64_t gstride = (maxF + 15) & ~15;
+    *gstride_out = gstride;
+    if (ctx->gbins.ensure((size_t)n * gstride) || ctx->jobs1d.ensure(n)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D histogram buffers");
+    if (maxF * 8 > ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "fine_bins %d exceeds shared memory", maxF);
+    CK(cudaMemsetAsync(ctx->gbins.p, 0, (size_t)n * gstride * 8, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->jobs1d.p, jobs.data(), n * sizeof(Hist1dJob), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 16 / n);
+    const int64_t seglen = std::max<int64_t>(1 << 15, (ctx->N + want - 1) / want);
+    std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+    int rc = gdk_upload_segs(ctx, segs, ctx->segs);
+    if (rc) return rc;
+    static int smem_set = 0;
+    if (maxF * 8 > smem_set) {
+        CK(cudaFuncSetAttribute(k_hist1d, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(maxF * 8, 48 * 1024)));
+        smem_set = std::max(maxF * 8, 48 * 1024);
+    }
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_HIST1D);
+    dim3 g((unsigned)segs.size(), (unsigned)n);
+    k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->jobs1d.p, ctx->gbins.p, gstride);
+    ctx->launches++;
+    pt.end();
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t gdk_hist1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* bins_out, int64_t stride) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (n <= 0 || !specs || !bins_out) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_hist1d_batch: bad arguments");
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK(cudaSetDevice(ctx->device));
+    int64_t gstride = 0;
+    int rc = run_hist1d(ctx, n, specs, &gstride);
+    if (rc) return rc;
+    if (ctx->fbuf.ensure((size_t)n * gstride)) return gdk_fail(ctx, GDK_ERR_NOMEM, "histogram output");
+    k_bins_to_f64<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->gbins.p, ctx->fbuf.p, (int64_t)n * gstride, 1.0 / ctx->wscale);
+    ctx->launches++;
+    for (int i = 0; i < n; i++)
+        CK(cudaMemcpyAsync(bins_out + (int64_t)i * stride, ctx->fbuf.p + (int64_t)i * gstride, (size_t)specs[i].fine_bins * 8,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, int64_t stride,
+                                       gdk_result1d* res, uint32_t flags) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (n <= 0 || !specs || !P_out || !res) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_density1d_batch: bad arguments");
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        const gdk_spec1d& s = specs[i];
+        if (s.boundary_correction_order > 2) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: boundary_correction_order must be <= 2", i);
+        if (s.smooth_scale_1D <= 0 && !(s.neff > 0)) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: N_eff must be > 0", i);
+        if (stride < s.fine_bins) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: output stride too small", i);
+    }
+    int64_t gstride = 0;
+    int rc = run_hist1d(ctx, n, specs, &gstride);
+    if (rc) return rc;
+    // twiddle / cosine tables per density
+    std::vector<Kde1dTables> tabs(n);
+    int maxF = 0;
+    for (int i = 0; i < n; i++) {
+        const Kde1dTablesHost* t = gdk_tables_for(ctx, specs[i].fine_bins);
+        if (!t) return gdk_fail(ctx, GDK_ERR_NOMEM, "transform tables");
+        tabs[i] = Kde1dTables{t->tw, t->tw4, t->cos4};
+        maxF = std::max(maxF, specs[i].fine_bins);
+    }
+    const size_t smem_need = (size_t)9 * maxF * 8;
+    const int use_smem = smem_need <= (size_t)ctx->max_smem - 1024;
+    if (ctx->specs1d.ensure(n) || ctx->res1d.ensure(n) || ctx->tabs1d.ensure(n) || ctx->fbuf.ensure((size_t)n * gstride))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "1D density buffers");
+    if (!use_smem && ctx->gwork.ensure((size_t)n * 9 * maxF)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D workspace");
+    CK(cudaMemcpyAsync(ctx->specs1d.p, specs, n * sizeof(gdk_spec1d), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tabs1d.p, tabs.data(), n * sizeof(Kde1dTables), cudaMemcpyHostToDevice, ctx->stream));
+    static size_t smem_set = 0;
+    if (use_smem && smem_need > smem_set) {
+        CK(cudaFuncSetAttribute(k_kde1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_need, 48 * 1024)));
+        smem_set = std::max<size_t>(smem_need, 48 * 1024);
+    }
+    const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
+    double* dP = dev_out ? P_out : ctx->fbuf.p;
+    const int64_t pstride = dev_out ? stride : gstride;
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_KDE1D);
+    k_kde1d<<<n, 256, use_smem ? smem_need : 0, ctx->stream>>>(ctx->specs1d.p, ctx->gbins.p, gstride, 1.0 / ctx->wscale, ctx->isj,
+                                                               ctx->tabs1d.p, dP, pstride, ctx->res1d.p, ctx->gwork.p, use_smem);
+    ctx->launches++;
+    pt.end();
+    CK(cudaGetLastError());
+    if (!dev_out)
+        for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(P_out + (int64_t)i * stride, ctx->fbuf.p + (int64_t)i * gstride, (size_t)specs[i].fine_bins * 8,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(res, ctx->res1d.p, n * sizeof(gdk_result1d), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GDK_OK;
+}

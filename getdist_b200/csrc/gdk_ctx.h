@@ -1,0 +1,109 @@
+// gdk_ctx.h -- the library context: resident sample store, cached statistics, grow-only device buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kde1d_core.cuh"
+#include "kernels_1d.cuh"
+#include "kernels_quant.cuh"
+#include "kernels_stats.cuh"
+
+#define GDK_NPHASE 10
+enum {
+    GDK_PH_HIST1D = 0,
+    GDK_PH_KDE1D = 1,
+    GDK_PH_HIST2D = 2,
+    GDK_PH_SHEAR = 3,
+    GDK_PH_XFORM2D = 4,
+    GDK_PH_BW2D = 5,
+    GDK_PH_CONV2D = 6,
+    GDK_PH_MOMENTS = 7,
+    GDK_PH_QUANT = 8,
+    GDK_PH_UPLOAD = 9
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        cap = n;
+        return 0;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+struct Kde1dTablesHost {
+    cplx* tw = nullptr;      // n-th roots (pow2 sizes)
+    cplx* tw4 = nullptr;     // first n of the 4n-th roots (pow2 sizes)
+    double* cos4 = nullptr;  // cos(2 pi j / 4n), j < 4n (other sizes)
+    cplx* twn = nullptr;     // n-th roots (other sizes, direct DFT)
+};
+
+struct gdk_ctx {
+    int device = 0, num_sms = 148, max_smem = 48 * 1024;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0[GDK_NPHASE], ev1[GDK_NPHASE];
+    int phase_valid[GDK_NPHASE];
+    std::string err;
+    int64_t launches = 0;
+    // sample store
+    int64_t N = 0, ld = 0;
+    int P = 0, nchains = 1;
+    std::vector<int64_t> chain_off;
+    bool unit_weights = true;
+    DevBuf<double> dX, dW, stage[2];
+    DevBuf<unsigned long long> dWq;
+    int wshift = 0;
+    double wscale = 1.0;
+    unsigned long long wq_total = 0;
+    double sum_w = 0, sum_w2 = 0, max_w = 0, min_w = 0, n_outliers = 0;
+    // cached moments
+    bool have_moments = false;
+    double norm = 0;
+    std::vector<double> means, cov, xmin, xmax, chain_means, chain_norm, chain_S;
+    // constants / tables
+    IsjConsts isj;
+    std::map<int, Kde1dTablesHost> tables;
+    // grow-only work buffers
+    DevBuf<Seg> segs;
+    DevBuf<double> scratch, dS, dmeans, fbuf, gwork, f2, a2buf, affbuf, work2d;
+    DevBuf<int2> dtiles;
+    DevBuf<int> iscratch, qparams;
+    DevBuf<QSlot> qslots;
+    DevBuf<unsigned long long> qhist, gbins, gbins2, gbins_rot;
+    DevBuf<QCand> qcand;
+    DevBuf<Hist1dJob> jobs1d;
+    DevBuf<gdk_spec1d> specs1d;
+    DevBuf<gdk_result1d> res1d;
+    DevBuf<Kde1dTables> tabs1d;
+    DevBuf<unsigned char> bytes2d, bytes2d_b;
+    DevBuf<cplx> cwork2d;
+};
+
+struct PhaseTimer {
+    gdk_ctx* ctx = nullptr;
+    int phase = 0;
+    void begin(gdk_ctx* c, int ph);
+    void end();
+};
+
+int gdk_fail(gdk_ctx* c, int code, const char* fmt, ...);
+std::vector<Seg> gdk_make_segments(const gdk_ctx* c, int64_t seglen);
+int gdk_upload_segs(gdk_ctx* ctx, const std::vector<Seg>& v, DevBuf<Seg>& buf);
+const Kde1dTablesHost* gdk_tables_for(gdk_ctx* ctx, int n);

@@ -1,0 +1,166 @@
+// kernels_1d.cuh -- the 1D density path on the device.
+//   k_hist1d : weighted fine-grid histograms of all requested parameters in one sweep of the column-major
+//              sample store (_binSamples + np.bincount, mcsamples.py:1486-1498, 1554)
+//   k_kde1d  : one CTA per density: TMA bulk load of the fine grid into shared memory, then
+//              kde1d_core (bandwidth, kernel, convolution, corrections, normalisation)
+#pragma once
+#include "kde1d_core.cuh"
+#include "kernels_quant.cuh"
+
+// Exact restatement of ((x - binmin) / fine_width + 0.5).astype(int): the same three correctly rounded
+// IEEE operations numpy performs, then truncation.  `inv` = 1/fine_width is only used to decide whether
+// the cheap product (x - binmin) * inv can round differently from the true quotient: the two differ by at
+// most a few ulp, so unless the value sits within 1e-9 of an integer the truncation is identical.
+__device__ __forceinline__ int bin_index_round(double x, double binmin, double fine_width, double inv) {
+    const double d = __dsub_rn(x, binmin);
+    const double q = __dadd_rn(__dmul_rn(d, inv), 0.5);
+    const double fr = q - floor(q);
+    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (int)q;
+    return (int)__dadd_rn(__ddiv_rn(d, fine_width), 0.5);
+}
+// kde.bin_samples (kde_bandwidth.py:85-87): truncating ((x - range_min) / dx).astype(int)
+__device__ __forceinline__ int bin_index_trunc(double x, double rmin, double dx, double inv) {
+    const double d = __dsub_rn(x, rmin);
+    const double q = __dmul_rn(d, inv);
+    const double fr = q - floor(q);
+    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (int)q;
+    return (int)__ddiv_rn(d, dx);
+}
+
+struct Hist1dJob {
+    int param, F;
+    double binmin, fine_width, inv_width;
+};
+
+// grid (nseg, njobs), 256 threads, dynamic smem = 2 * F * 4 bytes (two 32-bit limbs per bin).
+// Privatised shared-memory bins with native 32-bit integer atomics on 64-bit fixed-point weights;
+// flushed with u64 global atomics (integer: the result is independent of the order of accumulation).
+__global__ void __launch_bounds__(256) k_hist1d(const double* __restrict__ dX, int64_t ld,
+                                                const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                const Hist1dJob* __restrict__ jobs, unsigned long long* __restrict__ gbins,
+                                                int64_t gstride) {
+    extern __shared__ unsigned hsm[];
+    const Hist1dJob jb = jobs[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const int F = jb.F;
+    unsigned* hlo = hsm;
+    unsigned* hhi = hsm + F;
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) hsm[i] = 0;
+    __syncthreads();
+    const double* x = dX + (int64_t)jb.param * ld;
+    int64_t r = sg.r0;
+    if ((r & 1) && r < sg.r1) {
+        if (threadIdx.x == 0) {
+            const int b = bin_index_round(x[r], jb.binmin, jb.fine_width, jb.inv_width);
+            if (b >= 0 && b < F) smem_add_u64(hlo + b, hhi + b, dWq[r]);
+        }
+        r++;
+    }
+    const int64_t npair = (sg.r1 - r) >> 1;
+    for (int64_t i = threadIdx.x; i < npair; i += blockDim.x) {
+        const double2 xv = ldg_stream2(x + r + 2 * i);
+        const ulonglong2 wv = ldg_stream2_u64(dWq + r + 2 * i);
+        const int b0 = bin_index_round(xv.x, jb.binmin, jb.fine_width, jb.inv_width);
+        const int b1 = bin_index_round(xv.y, jb.binmin, jb.fine_width, jb.inv_width);
+        if (b0 >= 0 && b0 < F) smem_add_u64(hlo + b0, hhi + b0, wv.x);
+        if (b1 >= 0 && b1 < F) smem_add_u64(hlo + b1, hhi + b1, wv.y);
+    }
+    if (((sg.r1 - r) & 1) && threadIdx.x == 0) {
+        const int b = bin_index_round(x[sg.r1 - 1], jb.binmin, jb.fine_width, jb.inv_width);
+        if (b >= 0 && b < F) smem_add_u64(hlo + b, hhi + b, dWq[sg.r1 - 1]);
+    }
+    __syncthreads();
+    unsigned long long* g = gbins + (int64_t)blockIdx.y * gstride;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        const unsigned long long v = ((unsigned long long)hhi[i] << 32) | hlo[i];
+        if (v) atomicAdd(g + i, v);
+    }
+}
+
+// fixed point -> float64 bins
+__global__ void k_bins_to_f64(const unsigned long long* __restrict__ g, double* __restrict__ out, int64_t n, double inv_scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)g[i] * inv_scale;
+}
+
+// ---- TMA (bulk async copy) helpers: global -> shared with an mbarrier ------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+struct Kde1dTables {
+    const cplx* tw;
+    const cplx* tw4;
+    const double* cos4;
+};
+
+// grid (n), 256 threads.  Work arrays: 9*F doubles, in dynamic shared memory when use_smem != 0, otherwise in
+// the per-density global workspace gwork + i*9*F.
+__global__ void __launch_bounds__(256) k_kde1d(const gdk_spec1d* __restrict__ specs, const unsigned long long* __restrict__ gbins,
+                                               int64_t gstride, double inv_scale, IsjConsts K, const Kde1dTables* __restrict__ tabs,
+                                               double* __restrict__ P_out, int64_t pstride, gdk_result1d* __restrict__ res,
+                                               double* __restrict__ gwork, int use_smem) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ double red[32];
+    __shared__ __align__(8) unsigned long long bar;
+    const int i = blockIdx.x;
+    const gdk_spec1d sp = specs[i];
+    const int F = sp.fine_bins;
+    double* base = use_smem ? reinterpret_cast<double*>(dsm) : gwork + (int64_t)i * 9 * F;
+    Kde1dWork W;
+    W.bins = base;
+    W.a2 = base + F;
+    W.logI = base + 2 * F;
+    W.aux = base + 3 * F;
+    W.aux2 = base + 4 * F;
+    W.ca = reinterpret_cast<cplx*>(base + 5 * F);
+    W.cb = reinterpret_cast<cplx*>(base + 7 * F);
+    W.P = base + 5 * F;    // aliases ca (free after the DCT)
+    W.win = base + 7 * F;  // aliases cb
+    W.tw = tabs[i].tw;
+    W.tw4 = tabs[i].tw4;
+    W.cos4 = tabs[i].cos4;
+    const unsigned long long* g = gbins + (int64_t)i * gstride;
+    if (use_smem && ((F * 8) % 16 == 0)) {
+        // TMA staging of the fine grid: one bulk copy of the raw fixed-point bins, completion on an mbarrier
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (unsigned)(F * 8));
+            bulk_g2s(W.aux, g, (unsigned)(F * 8), &bar);
+        }
+        mbar_wait(&bar, 0);
+        const unsigned long long* raw = reinterpret_cast<const unsigned long long*>(W.aux);
+        for (int k = threadIdx.x; k < F; k += blockDim.x) W.bins[k] = (double)raw[k] * inv_scale;
+    } else {
+        for (int k = threadIdx.x; k < F; k += blockDim.x) W.bins[k] = (double)g[k] * inv_scale;
+    }
+    __syncthreads();
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    kde1d_core(co, sp, K, W, P_out + (int64_t)i * pstride, res + i);
+}

@@ -1,0 +1,314 @@
+// kernels_quant.cuh -- exact weighted order statistics by multi-pass radix selection.
+//
+// Replaces initParamConfidenceData + confidence (chains.py:793-838): the reference argsorts all N
+// samples for every density; here all (parameter, fraction) targets are resolved together in a few
+// streaming sweeps over the column-major store:
+//   keys   : the IEEE-754 bits of x mapped to an order-preserving uint64
+//   weights: 64-bit fixed point (exact integer sums -> the selected sample does not depend on the
+//            summation order, unlike a float64 prefix sum)
+//   pass   : every slot (param, target) keeps a key interval [klo, khi] known to contain the answer and
+//            the cumulative weight below it; the keys inside the interval are histogrammed by their
+//            leading bits (shared-memory privatised, native 32-bit integer atomics on two limbs),
+//            scanned, and the interval is narrowed.  In the first pass all slots of a parameter share
+//            the interval [key(min), key(max)] and therefore one histogram.
+//   finish : an interval that collapses to one key is the answer; otherwise its candidates are gathered
+//            (<= QCAP), bitonic-sorted in shared memory and scanned.  An interval with more candidates
+//            than QCAP (heavy duplicates / clusters) is refined again.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "kernels_stats.cuh"
+
+#define QMAXF 16   // max target fractions per parameter
+#define QCAP 4096  // max candidates gathered per slot
+
+struct QSlot {
+    unsigned long long klo, khi;  // inclusive key interval
+    unsigned long long below;     // fixed-point weight strictly below klo
+    unsigned long long target;    // answer = first sample with inclusive cumulative weight >= target
+    int shift;                    // digit = (key - klo) >> shift
+    int state;                    // 0 = refining, 1 = resolved (value valid), 2 = ready to gather
+    int ncand;                    // candidates gathered
+    int pad;
+    double value;
+};
+
+struct QCand {
+    unsigned long long key, wq;
+};
+
+__host__ __device__ __forceinline__ unsigned long long f64_to_key(double x) {
+    unsigned long long b;
+#if defined(__CUDA_ARCH__)
+    b = (unsigned long long)__double_as_longlong(x);
+#else
+    memcpy(&b, &x, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double key_to_f64(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+
+__host__ __device__ __forceinline__ int q_shift_for(unsigned long long width, int log2bins) {
+    int bits = 0;
+    while (bits < 64 && (width >> bits)) bits++;  // bits needed to represent width
+    const int sh = bits - log2bins;
+    return sh > 0 ? sh : 0;
+}
+
+// 64-bit add into two 32-bit shared-memory limbs with native ATOMS.ADD (shared f64/u64 atomics compile to
+// CAS spin loops on sm_100a; 32-bit integer adds are native)
+__device__ __forceinline__ void smem_add_u64(unsigned* lo, unsigned* hi, unsigned long long v) {
+    const unsigned vlo = (unsigned)v, vhi = (unsigned)(v >> 32);
+    const unsigned old = atomicAdd(lo, vlo);
+    const unsigned carry = (old + vlo < old) ? 1u : 0u;
+    if (vhi | carry) atomicAdd(hi, vhi + carry);
+}
+
+// One histogram pass.  grid (nseg, nparams).
+//   shared_first != 0: one histogram per parameter over slot 0's interval (first pass).
+//   else             : each refining slot s owns bins [s*nbins, (s+1)*nbins).
+// ghist[(p*QMAXF + s) * nbins + d] accumulates with u64 atomics (integer: order independent).
+__global__ void __launch_bounds__(256) k_qhist(const double* __restrict__ dX, int64_t ld,
+                                               const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                               const int* __restrict__ params, const QSlot* __restrict__ slots, int ns,
+                                               int nbins, int shared_first, unsigned long long* __restrict__ ghist) {
+    extern __shared__ unsigned qsm[];  // lo limbs [nh][nbins] then hi limbs [nh][nbins]
+    __shared__ unsigned long long s_lo[QMAXF], s_w[QMAXF];
+    __shared__ int s_shift[QMAXF], s_slot[QMAXF];
+    __shared__ int n_act;
+    const int p = blockIdx.y;
+    const Seg sg = segs[blockIdx.x];
+    const double* x = dX + (int64_t)params[p] * ld;
+    const int nh = shared_first ? 1 : ns;
+    unsigned* hlo = qsm;
+    unsigned* hhi = qsm + nh * nbins;
+    if (threadIdx.x == 0) {
+        int na = 0;
+        for (int s = 0; s < nh; s++) {
+            const QSlot q = slots[p * QMAXF + s];
+            bool act = q.state == 0;
+            if (shared_first) {  // active if any slot of the parameter still refines
+                act = false;
+                for (int t = 0; t < ns; t++) act |= slots[p * QMAXF + t].state == 0;
+            }
+            if (act) {
+                s_lo[na] = q.klo;
+                s_w[na] = q.khi - q.klo;
+                s_shift[na] = q.shift;
+                s_slot[na] = s;
+                na++;
+            }
+        }
+        n_act = na;
+    }
+    for (int i = threadIdx.x; i < 2 * nh * nbins; i += blockDim.x) qsm[i] = 0;
+    __syncthreads();
+    const int na = n_act;
+    if (na == 0) return;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const unsigned long long key = f64_to_key(ldg_stream(x + r));
+        for (int t = 0; t < na; t++) {
+            const unsigned long long d = key - s_lo[t];
+            if (d <= s_w[t]) {
+                const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
+                smem_add_u64(hlo + bin, hhi + bin, dWq[r]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = 0; t < na; t++) {
+        const int s = s_slot[t];
+        for (int d = threadIdx.x; d < nbins; d += blockDim.x) {
+            const unsigned long long v = ((unsigned long long)hhi[s * nbins + d] << 32) | hlo[s * nbins + d];
+            if (v) atomicAdd(&ghist[((int64_t)(p * QMAXF + s)) * nbins + d], v);
+        }
+    }
+}
+
+// Scan: grid (nparams), one warp per slot.  Find the digit where the inclusive cumulative weight first
+// reaches the target, narrow the interval.  next_state: 0 -> refine again with 2^next_log2bins bins,
+// 2 -> gather candidates next.
+__global__ void k_qscan(QSlot* __restrict__ slots, int ns, int nbins, int shared_first, int next_state,
+                        int next_log2bins, const unsigned long long* __restrict__ ghist) {
+    const int p = blockIdx.x;
+    const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (s >= ns) return;
+    QSlot q = slots[p * QMAXF + s];
+    if (q.state != 0) return;
+    const unsigned long long* h = ghist + ((int64_t)(p * QMAXF + (shared_first ? 0 : s))) * nbins;
+    unsigned long long run = q.below;  // cumulative weight before the current chunk
+    int found = -1;
+    unsigned long long below_found = 0;
+    int last_nz = -1;
+    unsigned long long below_last = 0;
+    for (int base = 0; base < nbins && found < 0; base += 32) {
+        const int d = base + lane;
+        const unsigned long long v = d < nbins ? h[d] : 0ull;
+        unsigned long long inc = v;  // inclusive prefix within the chunk
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const bool hit = (v != 0) && (run + inc >= q.target);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const unsigned nz = __ballot_sync(0xffffffffu, v != 0);
+        if (nz) {
+            const int l = 31 - __clz(nz);
+            last_nz = base + l;
+            below_last = run + __shfl_sync(0xffffffffu, inc - v, l);
+        }
+        if (m) {
+            const int l = __ffs(m) - 1;
+            found = base + l;
+            below_found = run + __shfl_sync(0xffffffffu, inc - v, l);
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (found < 0) {  // target beyond the total (rounding): clamp to the last occupied digit
+        found = last_nz;
+        below_found = below_last;
+    }
+    if (lane == 0) {
+        if (found < 0) {  // empty interval: cannot happen for consistent inputs; resolve to klo
+            q.state = 1;
+            q.value = key_to_f64(q.klo);
+        } else {
+            const unsigned long long lo = q.klo + ((unsigned long long)found << q.shift);
+            unsigned long long hi = (q.shift >= 64) ? q.khi : lo + ((1ull << q.shift) - 1ull);
+            if (hi > q.khi || hi < lo) hi = q.khi;
+            q.klo = lo;
+            q.khi = hi;
+            q.below = below_found;
+            if (lo == hi) {
+                q.state = 1;
+                q.value = key_to_f64(lo);
+            } else {
+                q.state = next_state;
+                q.shift = q_shift_for(hi - lo, next_log2bins);
+                q.ncand = 0;
+            }
+        }
+        slots[p * QMAXF + s] = q;
+    }
+}
+
+// Gather candidates of the slots in state 2.  grid (nseg, nparams).
+__global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, int64_t ld,
+                                                 const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                 const int* __restrict__ params, QSlot* __restrict__ slots, int ns,
+                                                 QCand* __restrict__ cand) {
+    __shared__ unsigned long long s_lo[QMAXF], s_w[QMAXF];
+    __shared__ int s_slot[QMAXF];
+    __shared__ int n_act;
+    const int p = blockIdx.y;
+    const Seg sg = segs[blockIdx.x];
+    const double* x = dX + (int64_t)params[p] * ld;
+    if (threadIdx.x == 0) {
+        int na = 0;
+        for (int s = 0; s < ns; s++) {
+            const QSlot q = slots[p * QMAXF + s];
+            if (q.state == 2) {
+                s_lo[na] = q.klo;
+                s_w[na] = q.khi - q.klo;
+                s_slot[na] = s;
+                na++;
+            }
+        }
+        n_act = na;
+    }
+    __syncthreads();
+    const int na = n_act;
+    if (na == 0) return;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const unsigned long long key = f64_to_key(ldg_stream(x + r));
+        for (int t = 0; t < na; t++) {
+            if (key - s_lo[t] <= s_w[t]) {
+                const int gs = p * QMAXF + s_slot[t];
+                const int idx = atomicAdd(&slots[gs].ncand, 1);
+                if (idx < QCAP) cand[(int64_t)gs * QCAP + idx] = QCand{key, dWq[r]};
+            }
+        }
+    }
+}
+
+// Select: grid (nparams * QMAXF), 512 threads, 64 KB dynamic shared memory.  Sort the gathered
+// candidates by key, walk the inclusive cumulative weight to the target.  Overflowing slots go back to
+// refinement (state 0) and are counted in *n_overflow.
+__global__ void __launch_bounds__(512) k_qselect(QSlot* __restrict__ slots, int ns, const QCand* __restrict__ cand,
+                                                 int log2bins, int* __restrict__ n_overflow) {
+    extern __shared__ unsigned long long ssm[];  // keys[QCAP] then wq[QCAP]
+    const int gs = blockIdx.x;
+    if ((gs % QMAXF) >= ns) return;
+    QSlot q = slots[gs];
+    if (q.state != 2) return;
+    const int n = q.ncand;
+    if (n > QCAP) {
+        if (threadIdx.x == 0) {
+            q.state = 0;
+            q.ncand = 0;
+            q.shift = q_shift_for(q.khi - q.klo, log2bins);
+            slots[gs] = q;
+            atomicAdd(n_overflow, 1);
+        }
+        return;
+    }
+    int m = 1;
+    while (m < n) m <<= 1;
+    unsigned long long* keys = ssm;
+    unsigned long long* wqs = ssm + QCAP;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (i < n) {
+            const QCand c = cand[(int64_t)gs * QCAP + i];
+            keys[i] = c.key;
+            wqs[i] = c.wq;
+        } else {
+            keys[i] = ~0ull;
+            wqs[i] = 0;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = keys[i], b = keys[l];
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[l] = a;
+                        const unsigned long long t = wqs[i];
+                        wqs[i] = wqs[l];
+                        wqs[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long cum = q.below;
+        unsigned long long ans = n > 0 ? keys[n - 1] : q.klo;  // clamp to the last candidate
+        for (int i = 0; i < n; i++) {
+            cum += wqs[i];
+            if (cum >= q.target) {
+                ans = keys[i];
+                break;
+            }
+        }
+        q.state = 1;
+        q.value = key_to_f64(ans);
+        slots[gs] = q;
+    }
+}

@@ -1,0 +1,138 @@
+"""Return types of the density calls -- host float64 grids with the attributes getdist.plots reads
+(`.x/.y/.P/.contours/.likes/.mask/.view_ranges/.bounds()`), mirroring getdist.densities
+(densities.py:59-280 of the reference) so that plotting code receives the same kind of object."""
+import numpy as np
+
+
+class DensitiesError(Exception):
+    pass
+
+
+def getContourLevels(inbins, contours=(0.68, 0.95), missing_norm=0, half_edge=True):
+    """Density levels enclosing the given probability fractions (reference densities.py:19-56).
+    Host-side numpy on the returned grid; SURVEY s8f-2 lists a device version as a later row."""
+    contours = np.atleast_1d(contours)
+    levels = np.zeros(len(contours))
+    if half_edge:
+        a = inbins.copy()
+        for ax in range(a.ndim):
+            sl = [slice(None)] * a.ndim
+            sl[ax] = 0
+            a[tuple(sl)] /= 2
+            sl[ax] = -1
+            a[tuple(sl)] /= 2
+    else:
+        a = inbins
+    norm = np.sum(a)
+    targets = (1 - np.array(contours)) * norm - missing_norm
+    flat = a.reshape(-1)
+    order = inbins.reshape(-1).argsort()
+    sortgrid = flat[order]
+    cumsum = np.cumsum(sortgrid)
+    ixs = np.searchsorted(cumsum, targets)
+    for i, ix in enumerate(ixs):
+        if ix == 0:
+            raise DensitiesError("Contour level outside plotted ranges")
+        h = cumsum[ix] - cumsum[ix - 1]
+        d = (cumsum[ix] - targets[i]) / h
+        levels[i] = sortgrid[ix] * (1 - d) + d * sortgrid[ix - 1]
+    return levels
+
+
+class GridDensity:
+    def normalize(self, by="integral", in_place=False):
+        if by == "integral":
+            norm = self.norm_integral()
+        elif by == "max":
+            norm = np.max(self.P)
+            if norm == 0:
+                raise DensitiesError("no samples in bin")
+        else:
+            raise DensitiesError("Density: unknown normalization")
+        if in_place:
+            self.P /= norm
+        else:
+            self.setP(self.P / norm)
+        self.spl = None
+        return self
+
+    def setP(self, P=None):
+        if P is not None:
+            for size, ax in zip(P.shape, self.axes):
+                if size != ax.size:
+                    raise DensitiesError("Array size mismatch in Density arrays: P %s, axis %s" % (size, ax.size))
+            self.P = P
+        else:
+            self.P = np.zeros([ax.size for ax in self.axes])
+        self.spl = None
+
+    def bounds(self):
+        if self.view_ranges is not None:
+            return self.view_ranges
+        return [(ax[0], ax[-1]) for ax in self.axes]
+
+    def getContourLevels(self, contours=(0.68, 0.95)):
+        return getContourLevels(self.P, contours)
+
+
+class Density1D(GridDensity):
+    def __init__(self, x, P=None, view_ranges=None):
+        self.n = x.size
+        self.axes = [x]
+        self.x = x
+        self.view_ranges = view_ranges
+        self.spacing = x[1] - x[0]
+        self.likes = None
+        self.setP(P)
+
+    def bounds(self):
+        if self.view_ranges is not None:
+            return self.view_ranges
+        return self.x[0], self.x[-1]
+
+    def integrate(self, P):
+        return ((P[0] + P[-1]) / 2 + np.sum(P[1:-1])) * self.spacing
+
+    def norm_integral(self):
+        return self.integrate(self.P)
+
+    def Prob(self, x, derivative=0):
+        from scipy.interpolate import splev, splrep
+
+        if self.spl is None:
+            self.spl = splrep(self.x, self.P, s=0)
+        if isinstance(x, (np.ndarray, list, tuple)):
+            return splev(x, self.spl, derivative, ext=1)
+        return splev([x], self.spl, derivative, ext=1)[0]
+
+    __call__ = Prob
+
+
+class Density2D(GridDensity):
+    def __init__(self, x, y, P=None, view_ranges=None, mask=None):
+        self.x = x
+        self.y = y
+        self.axes = [y, x]
+        self.view_ranges = view_ranges
+        self.mask = mask
+        self.spacing = (self.x[1] - self.x[0]) * (self.y[1] - self.y[0])
+        self.likes = None
+        self.contours = None
+        self.setP(P)
+
+    def integrate(self, P):
+        norm = (np.sum(P[1:-1, 1:-1]) + (P[0, 0] + P[0, -1] + P[-1, 0] + P[-1, -1]) / 4.0
+                + (np.sum(P[1:-1, 0]) + np.sum(P[0, 1:-1]) + np.sum(P[1:-1, -1]) + np.sum(P[-1, 1:-1])) / 2.0)
+        return norm * self.spacing
+
+    def norm_integral(self):
+        return self.integrate(self.P)
+
+    def Prob(self, x, y, grid=False):
+        from scipy.interpolate import RectBivariateSpline
+
+        if self.spl is None:
+            self.spl = RectBivariateSpline(self.x, self.y, self.P.T, s=0)
+        return self.spl.ev(x, y) if not grid else self.spl(x, y)
+
+    __call__ = Prob

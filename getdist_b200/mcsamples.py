@@ -1,0 +1,704 @@
+"""Host-side mirror of the GetDist ``MCSamples`` hot-path surface, backed by libgdk.so (CUDA, sm_100a).
+
+Mirrors, with the same names, argument meaning and error behaviour (reference paths under
+``/root/reference/getdist/``):
+
+    MCSamples.get1DDensity / get1DDensityGridData      mcsamples.py:1500, 1517
+    MCSamples.get2DDensity / get2DDensityGridData      mcsamples.py:1730, 1748
+    getMeans / getVars / getCov / getCorrelationMatrix chains.py:386, 400, 339, 363
+    getGelmanRubin / getGelmanRubinEigenvalues         chains.py:1476, 1446
+    confidence / twoTailLimits                         chains.py:814, 782
+    updateBaseStatistics / updateSettings              mcsamples.py:552, 472
+
+Everything N-sized or grid-sized runs on the device through the C-ABI (getdist_b200/_abi.py); this module
+keeps only the scalar per-parameter logic (``_initParam`` limit tests, grid geometry, 2D branch selection and
+2x2 Cholesky algebra), settings handling, caching and error/warning behaviour.  There is no CPU fallback:
+options of the reference that the device path does not implement yet raise ``NotImplementedError``
+(meanlikes, mask_function, periodic parameters, sampler='mcmc' N_eff -- SURVEY.md s8f).
+
+``prefetch_triangle`` computes all 1D and 2D densities of a parameter list in batched launches and fills the
+caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by getdist.plots) then hit.
+"""
+import logging
+import math
+from collections.abc import Mapping
+
+import numpy as np
+
+from . import _abi
+from .densities import DensitiesError, Density1D, Density2D  # noqa: F401
+
+log = logging.getLogger("getdist_b200")
+
+
+class WeightedSampleError(Exception):
+    pass
+
+
+class MCSamplesError(WeightedSampleError):
+    pass
+
+
+class SettingError(MCSamplesError):
+    pass
+
+
+class BandwidthError(MCSamplesError):
+    pass
+
+
+class ParamError(MCSamplesError):
+    pass
+
+
+# analysis_defaults.ini of the reference (these override the class attribute defaults)
+ANALYSIS_DEFAULTS = dict(
+    ignore_rows=0, min_weight_ratio=1e-30, contours=(0.68, 0.95, 0.99), credible_interval_threshold=0.05,
+    range_ND_contour=-1, range_confidence=0.001, converge_test_limit=0.95, fine_bins=1024, smooth_scale_1D=-1.0,
+    boundary_correction_order=1, mult_bias_correction_order=1, smooth_scale_2D=-1.0, max_corr_2D=0.99,
+    fine_bins_2D=256, use_effective_samples_2D=False, max_scatter_points=2000, num_bins=100, num_bins_2D=40,
+)
+
+_QFRACS_TAIL = list(np.linspace(0.1, 0.9, 9))
+
+
+class ParamInfo:
+    """Per-parameter state (paramnames.py:69 of the reference; only what the hot path reads/writes)."""
+
+    def __init__(self, name, label=None):
+        self.name = name
+        self.label = label or name
+        self.isDerived = False
+        self.limmin = None
+        self.limmax = None
+        self.has_limits_bot = False
+        self.has_limits_top = False
+        self.has_limits = False
+        self.periodic = False
+        self.N_eff_kde = None
+        self.kde_h = None
+        self._ranges_ready = False
+
+    def __repr__(self):
+        return "ParamInfo(%s)" % self.name
+
+
+class ParamNames:
+    def __init__(self, names, labels=None):
+        self.names = [ParamInfo(n, labels[i] if labels else None) for i, n in enumerate(names)]
+
+    def list(self):
+        return [p.name for p in self.names]
+
+    def numNonDerived(self):
+        return len([p for p in self.names if not p.isDerived])
+
+    def numberOfName(self, name):
+        for i, p in enumerate(self.names):
+            if p.name == name:
+                return i
+        return -1
+
+
+class ParamBounds:
+    """Hard prior ranges (parampriors.py:6 of the reference): name -> (lower|None, upper|None)."""
+
+    def __init__(self, ranges=None):
+        self.lower, self.upper, self.periodic = {}, {}, set()
+        for name, r in (ranges or {}).items():
+            self.setRange(name, r)
+
+    def setRange(self, name, r):
+        lo, hi = r[0], r[1]
+        if lo is not None and not (isinstance(lo, str) and lo == "N"):
+            self.lower[name] = float(lo)
+        if hi is not None and not (isinstance(hi, str) and hi == "N"):
+            self.upper[name] = float(hi)
+        if len(r) > 2 and r[2]:
+            self.periodic.add(name)
+
+    def getLower(self, name):
+        return self.lower.get(name)
+
+    def getUpper(self, name):
+        return self.upper.get(name)
+
+
+class ParamConfidenceData:
+    """Handle standing in for chains.ParamConfidenceData: the device resolves order statistics directly, so
+    the handle only remembers which column it refers to."""
+
+    def __init__(self, index):
+        self.index = index
+
+
+class MCSamples:
+    def __init__(self, samples=None, weights=None, loglikes=None, names=None, labels=None, ranges=None, sampler=None,
+                 settings=None, label=None, device=0, name_tag=None, **kwargs):
+        if samples is None:
+            raise MCSamplesError("getdist_b200.MCSamples needs in-memory samples (file loading stays in the reference)")
+        self.chain_offsets = None
+        if isinstance(samples, (list, tuple)) and len(samples) and np.ndim(samples[0]) == 2:
+            # chains.py:1488-1503 (makeSingle)
+            self.chain_offsets = np.cumsum(np.array([0] + [s.shape[0] for s in samples]))
+            if weights is not None:
+                weights = np.hstack([np.asarray(w, dtype=np.float64) for w in weights])
+            if loglikes is not None:
+                loglikes = np.hstack(list(loglikes))
+            samples = np.vstack([np.asarray(s, dtype=np.float64) for s in samples])
+        samples = np.asarray(samples, dtype=np.float64)
+        if samples.ndim == 1:
+            samples = samples.reshape(-1, 1)
+        self.samples = samples
+        self.numrows, self.n = samples.shape
+        self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
+        self.loglikes = loglikes
+        self.label = label
+        self.name_tag = name_tag
+        if names is None:
+            names = ["param%d" % (i + 1) for i in range(self.n)]
+        if len(names) != self.n:
+            raise MCSamplesError("names do not match the number of sample columns")
+        self.paramNames = ParamNames(list(names), labels)
+        self.index = {p.name: i for i, p in enumerate(self.paramNames.names)}
+        self.ranges = ranges if isinstance(ranges, ParamBounds) else ParamBounds(ranges)
+        self.sampler = "mcmc" if not isinstance(sampler, str) else sampler.lower()
+        if self.sampler not in ("mcmc", "nested", "uncorrelated"):
+            self.sampler = "mcmc"
+        self.raise_on_bandwidth_errors = False
+        self.no_warning_params = []
+        self.no_warning_chi2_params = True
+        self.likeStats = None
+        for k, v in ANALYSIS_DEFAULTS.items():
+            setattr(self, k, v)
+        self.contours = np.array(self.contours)
+        self._ctx = _abi.Context(device)  # raises if there is no CUDA device / library: no fallback
+        self._device_valid = False
+        self.density1D = {}
+        self._density2D = {}
+        self.needs_update = True
+        self.updateSettings(settings=settings, doUpdate=False)
+        if self.weights is None:
+            self.norm = np.float64(self.numrows)
+        else:
+            self.norm = None
+        self.updateBaseStatistics()
+
+    # ------------------------------------------------------------------ settings
+    def updateSettings(self, settings=None, ini=None, doUpdate=True):
+        """mcsamples.py:472-499 (dictionary form; .ini files stay with the reference's IniFile)."""
+        assert settings is None or isinstance(settings, Mapping)
+        if ini is not None:
+            raise NotImplementedError("ini files are handled by the reference's IniFile; pass settings as a dict")
+        for k, v in (settings or {}).items():
+            if k == "contours":
+                v = np.array(v if not isinstance(v, str) else [float(x) for x in v.split()])
+            elif k in ANALYSIS_DEFAULTS and not isinstance(ANALYSIS_DEFAULTS[k], tuple):
+                v = type(ANALYSIS_DEFAULTS[k])(v)  # typed by the existing attribute, inifile.py:216-226
+            setattr(self, k, v)
+        if doUpdate and self.samples is not None:
+            self.updateBaseStatistics()
+
+    # ------------------------------------------------------------------ data residency / statistics
+    def _upload(self):
+        if not self._device_valid:
+            self._ctx.set_samples(self.samples, self.weights, self.chain_offsets)
+            self._device_valid = True
+
+    def _weightsChanged(self):
+        """chains.py:310-323: invalidate everything derived from the samples (and the device copy)."""
+        self._device_valid = False
+        self.means = None
+        self.fullcov = None
+        self.correlationMatrix = None
+        self.vars = None
+        self.sddev = None
+        self.needs_update = True
+
+    def setSamples(self, samples, weights=None, loglikes=None):
+        self.samples = np.asarray(samples, dtype=np.float64)
+        self.numrows, self.n = self.samples.shape
+        self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
+        self.loglikes = loglikes
+        self._weightsChanged()
+
+    def updateBaseStatistics(self):
+        """chains.py:1340-1352 + mcsamples.py:552-576: one fused device reduction for means, variances,
+        covariance (per chain and total), weight statistics, min/max."""
+        self._upload()
+        m = self._ctx.moments()
+        self._mom = m
+        self.means = m["means"]
+        self.vars = m["vars"]
+        self.sddev = np.sqrt(self.vars)
+        self.fullcov = m["cov"]
+        self.correlationMatrix = None
+        self.norm = m["scalars"][0]
+        self.mean_mult = self.norm / self.numrows
+        self.max_mult = m["scalars"][2]
+        outliers = m["scalars"][3]
+        if outliers != 0:
+            log.warning("outlier fraction %s ", float(outliers) / self.numrows)
+        self._sum_w2 = m["scalars"][1]
+        self._xmin, self._xmax = m["xmin"], m["xmax"]
+        self.density1D = {}
+        self._density2D = {}
+        self._initLimits()
+        for par in self.paramNames.names:
+            par.N_eff_kde = None
+            par._ranges_ready = False
+        self._quantile_cache = {}
+        self.needs_update = False
+        return self
+
+    def _initLimits(self):
+        """mcsamples.py:442-470 (ranges only)."""
+        for par in self.paramNames.names:
+            par.limmin = self.ranges.getLower(par.name)
+            par.limmax = self.ranges.getUpper(par.name)
+            par.has_limits_bot = par.limmin is not None
+            par.has_limits_top = par.limmax is not None
+            par.periodic = par.name in self.ranges.periodic
+
+    def _parAndNumber(self, name):
+        """chains.py:1235-1250: name | index | ParamInfo -> (index, ParamInfo); unknown -> (None, None)."""
+        if isinstance(name, ParamInfo):
+            name = name.name
+        if isinstance(name, str):
+            ix = self.index.get(name)
+            if ix is None:
+                return None, None
+            return ix, self.paramNames.names[ix]
+        ix = int(name)
+        if ix < 0 or ix >= self.n:
+            return None, None
+        return ix, self.paramNames.names[ix]
+
+    def get_norm(self):
+        return self.norm
+
+    def getMeans(self, pars=None):
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if pars is None:
+            return self.means
+        return np.array([self.means[i] for i in pars])
+
+    def getVars(self):
+        if self.needs_update:
+            self.updateBaseStatistics()
+        return self.vars
+
+    def getCov(self, nparam=None, pars=None):
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if pars is not None:
+            return self.fullcov[np.ix_(pars, pars)]
+        return self.fullcov[:nparam, :nparam]
+
+    def getCorrelationMatrix(self):
+        """chains.py:363-371 with covToCorr :155-169."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if self.correlationMatrix is None:
+            c = self.fullcov.copy()
+            for i, di in enumerate(np.sqrt(self.fullcov.diagonal())):
+                if di:
+                    c[i, :] /= di
+                    c[:, i] /= di
+            self.correlationMatrix = c
+        return self.correlationMatrix
+
+    def getGelmanRubinEigenvalues(self, nparam=None, chainlist=None):
+        """chains.py:1446-1474; the per-chain means/covariances come from the fused device reduction, the
+        P x P LAPACK work stays on the host."""
+        if chainlist is not None:
+            raise NotImplementedError("explicit chainlist: use the reference")
+        if self.chain_offsets is None:
+            raise WeightedSampleError("Samples were not combined from separate chains")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        nparam = nparam or self.paramNames.numNonDerived()
+        m = self._mom
+        nch = m["chain_means"].shape[0]
+        means = self.means[:nparam]
+        meanscov = np.zeros((nparam, nparam))
+        meancov = np.zeros((nparam, nparam))
+        for c in range(nch):
+            diff = m["chain_means"][c, :nparam] - means
+            meanscov += np.outer(diff, diff)
+            meancov += m["chain_covs"][c, :nparam, :nparam]
+        meanscov /= nch - 1
+        meancov /= nch
+        w, U = np.linalg.eigh(meancov)
+        if np.min(w) > 0:
+            U /= np.sqrt(w)
+            return np.linalg.eigvalsh(np.dot(U.T, meanscov).dot(U))
+        return None
+
+    def getGelmanRubin(self, nparam=None, chainlist=None):
+        return np.max(self.getGelmanRubinEigenvalues(nparam, chainlist))
+
+    # ------------------------------------------------------------------ order statistics
+    def initParamConfidenceData(self, paramVec, start=0, end=None, weights=None):
+        if not isinstance(paramVec, (int, np.integer)) or start != 0 or end is not None or weights is not None:
+            raise NotImplementedError("device order statistics work on stored columns with the stored weights")
+        return ParamConfidenceData(int(paramVec))
+
+    def confidence(self, paramVec, limfrac, upper=False, start=0, end=None, weights=None):
+        """chains.py:814-838 on a stored column (index, name or ParamConfidenceData)."""
+        if isinstance(paramVec, ParamConfidenceData):
+            j = paramVec.index
+        else:
+            j, _ = self._parAndNumber(paramVec)
+            if j is None or start != 0 or end is not None or weights is not None:
+                raise NotImplementedError("device order statistics work on stored columns with the stored weights")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        fr = np.atleast_1d(np.asarray(limfrac, dtype=np.float64))
+        if upper:
+            fr = 1 - fr
+        out = np.concatenate([self._ctx.weighted_quantiles([j], fr[i:i + 16])[0] for i in range(0, fr.size, 16)])
+        return out if np.ndim(limfrac) else out[0]
+
+    def twoTailLimits(self, paramVec, confidence):
+        limits = np.array([(1 - confidence) / 2, 1 - (1 - confidence) / 2])
+        return self.confidence(paramVec, limits)
+
+    # ------------------------------------------------------------------ N_eff
+    def getEffectiveSamplesGaussianKDE(self, paramVec, h=0.2, scale=None, maxoff=None, min_corr=0.05):
+        """chains.py:477-574.  Uncorrelated/nested samplers: (sum w)^2 / sum w^2 (:500-501)."""
+        if self.sampler in ("nested", "uncorrelated"):
+            return self.norm ** 2 / self._sum_w2
+        raise NotImplementedError(
+            "sampler='mcmc' needs the autocorrelation-based N_eff (chains.py:423-574), which is not on the device "
+            "path yet (SURVEY.md s8f-1); construct with sampler='uncorrelated' or 'nested'")
+
+    def _get1DNeff(self, par, param):
+        if par.N_eff_kde is None:
+            par.N_eff_kde = self.getEffectiveSamplesGaussianKDE(param, scale=par.sigma_range)
+        return par.N_eff_kde
+
+    # ------------------------------------------------------------------ parameter ranges
+    def _ensure_param_ranges(self, indices):
+        """_initParam (mcsamples.py:1427-1484) for a set of parameters: one batched exact-quantile call for
+        those not done yet, then the scalar range / limit logic per parameter."""
+        todo = [j for j in dict.fromkeys(indices) if not self.paramNames.names[j]._ranges_ready]
+        if not todo:
+            return
+        fr = np.array([self.range_confidence, 1 - self.range_confidence] + _QFRACS_TAIL)
+        q = self._ctx.weighted_quantiles(todo, fr)
+        for row, j in zip(q, todo):
+            self._finish_param(self.paramNames.names[j], j, row)
+
+    def _finish_param(self, par, j, confids):
+        par.err = self.sddev[j]
+        par.mean = self.means[j]
+        par.param_min = self._xmin[j]
+        par.param_max = self._xmax[j]
+        confids = np.array(confids, dtype=np.float64)
+        par.range_min, par.range_max = confids[0:2]
+        confids[1:-1] = confids[2:]
+        confids[0] = par.param_min
+        confids[-1] = par.param_max
+        diffs = confids[4:] - confids[:-4]
+        scale = np.min(diffs) / 1.049
+        if np.all(diffs > par.err * 1.049) and np.all(diffs < scale * 1.5):
+            par.sigma_range = scale
+        else:
+            par.sigma_range = min(par.err, scale)
+        if self.range_ND_contour >= 0 and self.likeStats:
+            raise NotImplementedError("range_ND_contour needs likeStats (mcsamples.py:1455-1459): use the reference")
+        smooth_1D = par.sigma_range * 0.4
+        par.has_limits_bot = par.limmin is not None
+        par.has_limits_top = par.limmax is not None
+        if par.has_limits_bot:
+            if par.range_min - par.limmin > 2 * smooth_1D and par.param_min - par.limmin > smooth_1D:
+                par.has_limits_bot = False
+            else:
+                par.range_min = par.limmin
+        if par.has_limits_top:
+            if par.limmax - par.range_max > 2 * smooth_1D and par.limmax - par.param_max > smooth_1D:
+                par.has_limits_top = False
+            else:
+                par.range_max = par.limmax
+        if not par.has_limits_bot:
+            par.range_min -= smooth_1D * 2
+        if not par.has_limits_top:
+            par.range_max += smooth_1D * 2
+        par.has_limits = par.has_limits_top or par.has_limits_bot
+        par._ranges_ready = True
+
+    def _initParamRanges(self, j, paramConfid=None):
+        j, par = self._parAndNumber(j)
+        self._ensure_param_ranges([j])
+        return par
+
+    @staticmethod
+    def _bin_geometry(par, num_fine_bins, borderfrac=0.1):
+        """mcsamples.py:1486-1496."""
+        border = (par.range_max - par.range_min) * borderfrac
+        binmin = min(par.param_min, par.range_min)
+        if not par.has_limits_bot:
+            binmin -= border
+        binmax = max(par.param_max, par.range_max)
+        if not par.has_limits_top:
+            binmax += border
+        return binmin, binmax
+
+    # ------------------------------------------------------------------ 1D densities
+    def get1DDensity(self, name, **kwargs):
+        """mcsamples.py:1500-1514."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if not kwargs:
+            j, par = self._parAndNumber(name)
+            if par is not None:
+                density = self.density1D.get(par.name)
+                if density is not None:
+                    return density
+        return self.get1DDensityGridData(name, **kwargs)
+
+    def get1DDensityGridData(self, j, paramConfid=None, meanlikes=False, **kwargs):
+        """mcsamples.py:1517-1686."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        j = self._parAndNumber(j)[0]
+        if j is None:
+            return None
+        return self._densities_1d([j], meanlikes=meanlikes, **kwargs)[0]
+
+    def _spec_1d(self, j, kwargs):
+        par = self.paramNames.names[j]
+        if par.periodic:
+            raise NotImplementedError("periodic parameters are not on the device path yet (SURVEY.md s8f-3)")
+        num_bins = kwargs.get("num_bins", self.num_bins)
+        smooth_scale_1D = kwargs.get("smooth_scale_1D", self.smooth_scale_1D)
+        bco = kwargs.get("boundary_correction_order", self.boundary_correction_order)
+        mbc = kwargs.get("mult_bias_correction_order", self.mult_bias_correction_order)
+        fine_bins = int(kwargs.get("fine_bins", self.fine_bins))
+        paramrange = par.range_max - par.range_min
+        if paramrange <= 0:
+            raise MCSamplesError("Parameter range is <= 0: " + par.name)
+        if par.has_limits and bco > 2:
+            raise SettingError("Unknown boundary_correction_order (expected 0, 1, 2)")
+        width = paramrange / (num_bins - 1)
+        binmin, binmax = self._bin_geometry(par, fine_bins)
+        neff = self._get1DNeff(par, j) if smooth_scale_1D <= 0 else 1.0
+        return _abi.Spec1D(j, fine_bins, binmin, binmax, par.range_min, par.range_max, par.param_min, par.param_max,
+                           par.sigma_range, par.err, neff, float(smooth_scale_1D), width, int(bco), int(mbc),
+                           int(par.has_limits_bot), int(par.has_limits_top))
+
+    def _densities_1d(self, indices, meanlikes=False, **kwargs):
+        if meanlikes:
+            raise NotImplementedError("meanlikes is not on the device path yet (SURVEY.md s8f-3)")
+        self._ensure_param_ranges(indices)
+        specs = [self._spec_1d(j, kwargs) for j in indices]
+        P, res = self._ctx.density1d_batch(specs)
+        out = []
+        for j, sp, row, r in zip(indices, specs, P, res):
+            par = self.paramNames.names[j]
+            if sp.smooth_scale_1D <= 0:
+                if r.status & _abi.ST_BW_FALLBACK:
+                    # mcsamples.py:1258-1268
+                    if par.name not in self.no_warning_params and (
+                            not self.no_warning_chi2_params or "chi2_" not in par.name and "minuslog" not in par.name):
+                        h = None if (r.status & _abi.ST_BW_FAILED_NONE) else r.h_raw
+                        msg = "auto bandwidth for %s very small or failed (h=%s,N_eff=%s). Using fallback (h=%s)" % (
+                            par.name, h, sp.neff, r.kde_h)
+                        if self.raise_on_bandwidth_errors:
+                            raise BandwidthError(msg)
+                        log.warning(msg)
+                par.kde_h = r.kde_h
+            if r.status & _abi.ST_SMALL_SMOOTH:
+                log.warning("fine_bins not large enough to well sample smoothing scale - " + par.name)
+            if r.status & _abi.ST_ZERO_MAX:
+                raise DensitiesError("no samples in bin")
+            x = np.linspace(sp.binmin, sp.binmax, sp.fine_bins)
+            d = Density1D(x, P=np.array(row[: sp.fine_bins]), view_ranges=[par.range_min, par.range_max])
+            d.likes = None
+            d._gdk = dict(kde_h=r.kde_h, smooth_1D=r.smooth_1D, winw=r.winw, status=r.status, n_feval=r.n_feval)
+            if not kwargs:
+                self.density1D[par.name] = d
+            out.append(d)
+        return out
+
+    # ------------------------------------------------------------------ 2D densities
+    def get2DDensity(self, x, y, normalized=False, **kwargs):
+        """mcsamples.py:1730-1745."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        density = self.get2DDensityGridData(x, y, get_density=True, **kwargs)
+        if normalized:
+            density.normalize(in_place=True)
+        return density
+
+    def get2DDensityGridData(self, j, j2, num_plot_contours=None, get_density=False, meanlikes=False,
+                             mask_function=None, **kwargs):
+        """mcsamples.py:1748-2010."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if meanlikes or mask_function is not None:
+            raise NotImplementedError("meanlikes / mask_function are not on the device path yet (SURVEY.md s8f-3)")
+        j, parx = self._parAndNumber(j)
+        j2, pary = self._parAndNumber(j2)
+        if j is None or j2 is None:
+            return None
+        density = None
+        if not kwargs:
+            cached = self._density2D.get((j, j2))
+            if cached is not None:
+                # a fresh object per call, as the reference returns (callers normalise in place)
+                density = Density2D(cached.x, cached.y, cached.P.copy(), view_ranges=cached.view_ranges)
+                density._gdk = cached._gdk
+        if density is None:
+            density = self._densities_2d([(j, j2)], **kwargs)[0]
+        if get_density:
+            return density
+        ncontours = len(self.contours)
+        if num_plot_contours:
+            ncontours = min(num_plot_contours, ncontours)
+        density.contours = density.getContourLevels(self.contours[:ncontours])
+        density.likes = None
+        return density
+
+    def _spec_2d(self, j, j2, kwargs):
+        parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
+        if parx.periodic or pary.periodic:
+            raise NotImplementedError("periodic parameters are not on the device path yet (SURVEY.md s8f-3)")
+        base_fine_bins_2D = int(kwargs.get("fine_bins_2D", self.fine_bins_2D))
+        bco = kwargs.get("boundary_correction_order", self.boundary_correction_order)
+        mbc = kwargs.get("mult_bias_correction_order", self.mult_bias_correction_order)
+        smooth_scale_2D = float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D))
+        has_prior = parx.has_limits or pary.has_limits
+        corr = self.getCorrelationMatrix()[j2][j]
+        actual_corr = corr
+        if abs(abs(corr) - 1.0) <= 1e-8:
+            log.warning("Parameters are 100%% correlated: %s, %s", parx.name, pary.name)
+            corr = np.sign(corr) * self.max_corr_2D
+        if abs(self.max_corr_2D) > 1:
+            raise SettingError("max_corr_2D cannot be >=1")
+        if abs(corr) < 0.1:
+            corr = 0.0
+        if has_prior and bco > 1:
+            raise SettingError("unknown boundary_correction_order (expected 0 or 1)")
+        angle_scale = max(0.2, np.sqrt(1 - min(self.max_corr_2D, abs(corr)) ** 2))
+        nbin2D = int(round(self.num_bins_2D / angle_scale))
+        fine_bins_2D = base_fine_bins_2D
+        if corr:
+            scaled = 192 * int(3 / angle_scale) // 3
+            if base_fine_bins_2D < scaled and int(1 / angle_scale) > 1:
+                fine_bins_2D = scaled
+        xbinmin, xbinmax = self._bin_geometry(parx, fine_bins_2D)
+        ybinmin, ybinmax = self._bin_geometry(pary, fine_bins_2D)
+        finewidthx = (xbinmax - xbinmin) / (fine_bins_2D - 1)
+        finewidthy = (ybinmax - ybinmin) / (fine_bins_2D - 1)
+        sp = _abi.Spec2D()
+        sp.px, sp.py = j, j2
+        sp.fine_bins, sp.base_fine_bins = fine_bins_2D, base_fine_bins_2D
+        sp.xbinmin, sp.xbinmax, sp.ybinmin, sp.ybinmax = xbinmin, xbinmax, ybinmin, ybinmax
+        sp.x_sigma_range, sp.y_sigma_range = parx.sigma_range, pary.sigma_range
+        sp.x_err, sp.y_err = parx.err, pary.err
+        sp.corr = actual_corr
+        sp.kernel_corr = corr
+        sp.max_corr_2D = self.max_corr_2D
+        sp.smooth_scale_2D = smooth_scale_2D
+        sp.boundary_correction_order = int(bco)
+        sp.mult_bias_correction_order = int(mbc)
+        sp.x_has_bot, sp.x_has_top = int(parx.has_limits_bot), int(parx.has_limits_top)
+        sp.y_has_bot, sp.y_has_top = int(pary.has_limits_bot), int(pary.has_limits_top)
+        sp.neff = 1.0
+        if smooth_scale_2D < 0:
+            # branch selection of getAutoBandwidth2D, mcsamples.py:1325-1409
+            if self.use_effective_samples_2D and abs(actual_corr) < 0.999:
+                raise NotImplementedError("use_effective_samples_2D needs the 2D autocorrelation N_eff: use the reference")
+            sp.neff = min(self._get1DNeff(parx, j), self._get1DNeff(pary, j2))
+            do_correlated = not parx.has_limits or not pary.has_limits
+            min_corr = 0.2
+            if min_corr < abs(actual_corr) <= self.max_corr_2D and do_correlated:
+                sp.bw_mode = _abi.BW2D_SHEAR
+                i, k = j, j2
+                imax, imin = None, None
+                if parx.has_limits_bot:
+                    imin = parx.range_min
+                if parx.has_limits_top:
+                    imax = parx.range_max
+                swapped = 0
+                if pary.has_limits:
+                    i, k = k, i
+                    swapped = 1
+                    if pary.has_limits_bot:
+                        imin = pary.range_min
+                    if pary.has_limits_top:
+                        imax = pary.range_max
+                cov = self.getCov(pars=[i, k])
+                S = np.linalg.cholesky(cov)
+                ichol = np.linalg.inv(S)
+                S = S * ichol[0, 0]
+                r = ichol[1, :] / ichol[0, 0]
+                sp.shear_i, sp.shear_j, sp.shear_swapped = i, k, swapped
+                sp.r0, sp.r1 = r[0], r[1]
+                sp.S00, sp.S10, sp.S11 = S[0, 0], S[1, 0], S[1, 1]
+                # kde.bin_samples range of p1 (kde_bandwidth.py:77-84)
+                mn, mx = self._xmin[i], self._xmax[i]
+                delta = mx - mn
+                sp.p1_min = imin if imin is not None else mn - delta * 0.1
+                sp.p1_max = imax if imax is not None else mx + delta * 0.1
+            elif abs(actual_corr) > self.max_corr_2D or not do_correlated and actual_corr > 0.8:
+                sp.bw_mode = _abi.BW2D_RULE
+            else:
+                sp.bw_mode = _abi.BW2D_PLAIN
+        else:
+            sp.bw_mode = _abi.BW2D_FIXED
+            if smooth_scale_2D < 1.0:
+                sp.rx_fixed = smooth_scale_2D * parx.err / finewidthx
+                sp.ry_fixed = smooth_scale_2D * pary.err / finewidthy
+            else:
+                sp.rx_fixed = smooth_scale_2D * fine_bins_2D / nbin2D
+                sp.ry_fixed = smooth_scale_2D * fine_bins_2D / nbin2D
+        return sp
+
+    def _densities_2d(self, pairs, **kwargs):
+        self._ensure_param_ranges([p for pr in pairs for p in pr])
+        specs = [self._spec_2d(j, j2, kwargs) for (j, j2) in pairs]
+        buf, offsets, res = self._ctx.density2d_batch(specs)
+        out = []
+        for (j, j2), sp, off, r in zip(pairs, specs, offsets, res):
+            parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
+            if r.status & _abi.ST_BIAS_NEG:
+                raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
+            if r.status & _abi.ST_BW_FALLBACK:
+                msg = "2D kernel density bandwidth optimizer failed for %s, %s. Using fallback width" % (parx.name, pary.name)
+                if self.raise_on_bandwidth_errors:
+                    raise BandwidthError(msg)
+                log.warning(msg)
+            if r.status & _abi.ST_SMALL_SMOOTH:
+                log.warning("fine_bins_2D not large enough for optimal density: %s, %s", parx.name, pary.name)
+            if r.status & _abi.ST_ZERO_MAX:
+                raise DensitiesError("no samples in bin")
+            G = sp.fine_bins
+            x = np.linspace(sp.xbinmin, sp.xbinmax, G)
+            y = np.linspace(sp.ybinmin, sp.ybinmax, G)
+            d = Density2D(x, y, np.array(buf[off: off + G * G]).reshape(G, G),
+                          view_ranges=[(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
+            d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
+                          n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G)
+            if not kwargs:
+                self._density2D[(j, j2)] = d
+            out.append(d)
+        return out
+
+    # ------------------------------------------------------------------ batched driver
+    def prefetch_triangle(self, params=None, do_1d=True, do_2d=True):
+        """Compute every 1D and (lower-triangle) 2D density of a triangle plot in batched launches and seed
+        the caches that get1DDensity / get2DDensity consult.  Pair (x, y) = (params[i], params[k]) for i < k,
+        as getdist.plots.triangle_plot requests them (x = column parameter, y = row parameter)."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]
+        if any(i is None for i in idx):
+            raise ParamError("unknown parameter in prefetch_triangle")
+        d1 = self._densities_1d(idx) if do_1d else []
+        pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))]
+        d2 = self._densities_2d(pairs) if (do_2d and pairs) else []
+        return d1, d2
