@@ -48,7 +48,7 @@ def test_gelman_rubin(gpu_objs):
     case, g, mc = gpu_objs("chains")
     np.testing.assert_allclose(mc.getGelmanRubin(), float(g["gelman_rubin"]), rtol=1e-9)
     np.testing.assert_allclose(mc.getGelmanRubin(3), float(g["gelman_rubin_3"]), rtol=1e-9)
-    np.testing.assert_allclose(mc.getGelmanRubinEigenvalues(), g["gelman_rubin_eig"], rtol=1e-8)
+    np.testing.assert_allclose(mc.getGelmanRubinEigenvalues(), g["gelman_rubin_eig"], rtol=1e-8, atol=1e-13)
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -102,7 +102,11 @@ def test_hist1d_matches_bincount(gpu_objs, name):
     for j in range(mc.n):
         par = o.init_param_ranges(j)
         binmin, binmax, fw = bin_geometry(par, 1024)
-        assert specs[j].binmin == binmin and specs[j].binmax == binmax
+        # geometry agrees to rounding (it inherits the last-ulp difference of the device std dev) ...
+        np.testing.assert_allclose([specs[j].binmin, specs[j].binmax], [binmin, binmax], rtol=1e-13)
+        # ... and the histogram is compared on exactly the geometry the device was given
+        binmin, binmax = specs[j].binmin, specs[j].binmax
+        fw = (binmax - binmin) / (1024 - 1)
         ref = np.bincount(bin_indices(o.samples[:, j], binmin, fw), weights=o.weights, minlength=1024)
         assert np.all((ref == 0) == (bins[j] == 0))
         assert np.max(np.abs(bins[j] - ref)) <= 1e-11 * np.max(ref)
