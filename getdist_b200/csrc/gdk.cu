@@ -129,6 +129,7 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->phase_valid[i] = 0;
     }
     gdk_fill_isj_consts(&ctx->isj);
+    gdk_fill_kde2d_consts(&ctx->k2d);
     *out = ctx;
     return GDK_OK;
 }

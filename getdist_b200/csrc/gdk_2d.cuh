@@ -1,9 +1,518 @@
-// placeholder until the 2D path lands
+// gdk_2d.cuh -- host orchestration of the 2D density path (gdk_density2d_batch / gdk_hist2d_batch).
+// Included by gdk.cu.  Per chunk of pairs: histograms (tiled global reductions) -> sheared re-binning ->
+// transforms -> bandwidth -> window/mask maps/convolutions/corrections -> max-normalised output.
 #pragma once
+#include <algorithm>
+#include <map>
+#include <set>
+#include <vector>
+
 #include "gdk_ctx.h"
-extern "C" int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t, const gdk_spec2d*, double*, const int64_t*, gdk_result2d*, uint32_t) {
-    return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "2D path not built yet");
+#include "host_tables.h"
+#include "kernels_2d.cuh"
+
+#define CK2(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return gdk_fail(ctx, GDK_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                            cudaGetErrorString(e_));                                                       \
+    } while (0)
+
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+    void* take(size_t bytes) {
+        const size_t a = (used + 255) & ~size_t(255);
+        if (a + bytes > cap) return nullptr;
+        used = a + bytes;
+        return base + a;
+    }
+};
+
+static size_t bytes_per_pair_estimate(const gdk_spec2d& s) {
+    const size_t g = (size_t)s.fine_bins * s.fine_bins * 8, gb = (size_t)s.base_fine_bins * s.base_fine_bins * 8;
+    const size_t w = 256;  // generous window half-width guess for the T scratch
+    return g * 12 + gb * 6 + (2 * w + 1) * (size_t)s.fine_bins * 4 * 8 + (2 * w + 1) * (2 * w + 1) * 8;
 }
-extern "C" int32_t gdk_hist2d_batch(gdk_ctx* ctx, int32_t, const gdk_spec2d*, double*, const int64_t*) {
-    return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "2D path not built yet");
+
+template <class T>
+static int upload_vec(gdk_ctx* ctx, const std::vector<T>& v, DevBuf<unsigned char>& buf, T** out) {
+    if (buf.ensure(std::max<size_t>(v.size() * sizeof(T), 256))) return gdk_fail(ctx, GDK_ERR_NOMEM, "job table");
+    if (!v.empty()) CK2(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = reinterpret_cast<T*>(buf.p);
+    return 0;
+}
+
+static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
+                           gdk_result2d* res, uint32_t flags, bool hist_only) {
+    const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
+    // ---------------- layout of the pair grids ----------------
+    std::vector<long long> goff(n);
+    size_t gtot = 0;
+    for (int i = 0; i < n; i++) {
+        goff[i] = (long long)gtot;
+        gtot += (size_t)specs[i].fine_bins * specs[i].fine_bins;
+    }
+    std::vector<int> shear_of(n, -1);
+    std::vector<ShearJob> sjobs;
+    size_t rtot = 0;
+    if (!hist_only)
+        for (int i = 0; i < n; i++)
+            if (specs[i].bw_mode == GDK_BW2D_SHEAR) {
+                const gdk_spec2d& s = specs[i];
+                ShearJob j{};
+                j.pi = s.shear_i;
+                j.pj = s.shear_j;
+                j.Gb = s.base_fine_bins;
+                j.r0 = s.r0;
+                j.r1 = s.r1;
+                j.p1_min = s.p1_min;
+                j.dx1 = (s.p1_max - s.p1_min) / (s.base_fine_bins - 1);
+                j.inv1 = 1.0 / j.dx1;
+                j.off = (long long)rtot;
+                rtot += (size_t)j.Gb * j.Gb;
+                shear_of[i] = (int)sjobs.size();
+                sjobs.push_back(j);
+            }
+    if (ctx->gbins2.ensure(gtot) || ctx->gbins_rot.ensure(std::max<size_t>(rtot, 1)))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "2D histogram grids (%zu MB)", (gtot + rtot) * 8 >> 20);
+    CK2(cudaMemsetAsync(ctx->gbins2.p, 0, gtot * 8, ctx->stream));
+    if (rtot) CK2(cudaMemsetAsync(ctx->gbins_rot.p, 0, rtot * 8, ctx->stream));
+
+    // ---------------- histogram tiles, grouped by grid size ----------------
+    std::vector<Tile2d> tiles;
+    {
+        std::map<int, std::vector<int>> byG;
+        for (int i = 0; i < n; i++) byG[specs[i].fine_bins].push_back(i);
+        for (auto& kv : byG) {
+            const int G = kv.first;
+            std::vector<int> A, B;
+            for (int i : kv.second) {
+                A.push_back(specs[i].px);
+                B.push_back(specs[i].py);
+            }
+            std::sort(A.begin(), A.end());
+            A.erase(std::unique(A.begin(), A.end()), A.end());
+            std::sort(B.begin(), B.end());
+            B.erase(std::unique(B.begin(), B.end()), B.end());
+            std::map<int, int> ia, ib;
+            for (size_t k = 0; k < A.size(); k++) ia[A[k]] = (int)k;
+            for (size_t k = 0; k < B.size(); k++) ib[B[k]] = (int)k;
+            std::map<std::pair<int, int>, int> tix;
+            for (int i : kv.second) {
+                const gdk_spec2d& s = specs[i];
+                const int a = ia[s.px], b = ib[s.py];
+                const std::pair<int, int> key(a / HT, b / HT);
+                auto it = tix.find(key);
+                if (it == tix.end()) {
+                    Tile2d t{};
+                    t.G = G;
+                    for (int x = 0; x < HT; x++)
+                        for (int y = 0; y < HT; y++) t.off[x][y] = -1;
+                    it = tix.emplace(key, (int)tiles.size()).first;
+                    tiles.push_back(t);
+                }
+                Tile2d& t = tiles[it->second];
+                const int la = a % HT, lb = b % HT;
+                if (t.off[la][lb] >= 0) {
+                    // the same (px, py, G) requested twice in one batch: give it its own 1x1 tile
+                    Tile2d d{};
+                    d.G = G;
+                    for (int x = 0; x < HT; x++)
+                        for (int y = 0; y < HT; y++) d.off[x][y] = -1;
+                    d.na = d.nb = 1;
+                    d.pa[0] = s.px;
+                    d.pb[0] = s.py;
+                    d.amin[0] = s.xbinmin;
+                    d.afw[0] = (s.xbinmax - s.xbinmin) / (G - 1);
+                    d.ainv[0] = 1.0 / d.afw[0];
+                    d.bmin[0] = s.ybinmin;
+                    d.bfw[0] = (s.ybinmax - s.ybinmin) / (G - 1);
+                    d.binv[0] = 1.0 / d.bfw[0];
+                    d.off[0][0] = goff[i];
+                    tiles.push_back(d);
+                    continue;
+                }
+                t.na = std::max(t.na, la + 1);
+                t.nb = std::max(t.nb, lb + 1);
+                t.pa[la] = s.px;
+                t.amin[la] = s.xbinmin;
+                t.afw[la] = (s.xbinmax - s.xbinmin) / (G - 1);
+                t.ainv[la] = 1.0 / t.afw[la];
+                t.pb[lb] = s.py;
+                t.bmin[lb] = s.ybinmin;
+                t.bfw[lb] = (s.ybinmax - s.ybinmin) / (G - 1);
+                t.binv[lb] = 1.0 / t.bfw[lb];
+                t.off[la][lb] = goff[i];
+            }
+        }
+        // slots of a tile that were never assigned keep pa/pb = 0 with all offsets -1: harmless loads
+        for (Tile2d& t : tiles) {
+            for (int k = 0; k < t.na; k++)
+                if (t.afw[k] == 0) {
+                    t.afw[k] = t.ainv[k] = 1;
+                }
+            for (int k = 0; k < t.nb; k++)
+                if (t.bfw[k] == 0) {
+                    t.bfw[k] = t.binv[k] = 1;
+                }
+        }
+    }
+    Tile2d* dtiles = nullptr;
+    int rc = upload_vec(ctx, tiles, ctx->bytes2d, &dtiles);
+    if (rc) return rc;
+    const int ntiles = (int)tiles.size();
+    {
+        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, ntiles) + 1);
+        const int64_t seglen = std::max<int64_t>(1 << 13, (ctx->N + want - 1) / want);
+        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+        rc = gdk_upload_segs(ctx, segs, ctx->segs);
+        if (rc) return rc;
+        PhaseTimer pt;
+        pt.begin(ctx, GDK_PH_HIST2D);
+        dim3 g((unsigned)segs.size(), (unsigned)ntiles);
+        k_hist2d_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dtiles, ctx->gbins2.p);
+        ctx->launches++;
+        pt.end();
+        CK2(cudaGetLastError());
+    }
+    // ---------------- sheared re-binning ----------------
+    ShearJob* dsj = nullptr;
+    ShearGeom* dgeom = nullptr;
+    const int nshear = (int)sjobs.size();
+    if (nshear) {
+        rc = upload_vec(ctx, sjobs, ctx->bytes2d_b, &dsj);
+        if (rc) return rc;
+        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / nshear + 1);
+        const int64_t seglen = std::max<int64_t>(1 << 14, (ctx->N + want - 1) / want);
+        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+        rc = gdk_upload_segs(ctx, segs, ctx->segs);
+        if (rc) return rc;
+        const int nseg = (int)segs.size();
+        if (ctx->scratch.ensure((size_t)nshear * nseg * 2 + (size_t)nshear * 4 + 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "shear scratch");
+        double* part = ctx->scratch.p;
+        dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
+        PhaseTimer pt;
+        pt.begin(ctx, GDK_PH_SHEAR);
+        dim3 g((unsigned)nseg, (unsigned)nshear);
+        k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsj, part);
+        k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
+        k_shear_hist<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsj, dgeom, ctx->gbins_rot.p);
+        ctx->launches += 3;
+        pt.end();
+        CK2(cudaGetLastError());
+    }
+    // fixed point -> float64, in place
+    k_u64_to_f64_inplace<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gbins2.p, (int64_t)gtot, 1.0 / ctx->wscale);
+    if (rtot) k_u64_to_f64_inplace<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gbins_rot.p, (int64_t)rtot, 1.0 / ctx->wscale);
+    ctx->launches += rtot ? 2 : 1;
+    const double* H = reinterpret_cast<const double*>(ctx->gbins2.p);
+    const double* Hrot = reinterpret_cast<const double*>(ctx->gbins_rot.p);
+    if (hist_only) {
+        for (int i = 0; i < n; i++)
+            CK2(cudaMemcpyAsync(P_out + offsets[i], H + goff[i], (size_t)specs[i].fine_bins * specs[i].fine_bins * 8,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        CK2(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+
+    // ---------------- arena for everything grid-sized below ----------------
+    size_t need = 0;
+    for (int i = 0; i < n; i++) need += bytes_per_pair_estimate(specs[i]);
+    need += (size_t)64 << 20;
+    if (ctx->bytes_arena.ensure(need)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D work arena (%zu MB)", need >> 20);
+    Arena ar{ctx->bytes_arena.p, ctx->bytes_arena.cap, 0};
+    auto take_d = [&](size_t cnt) { return reinterpret_cast<double*>(ar.take(cnt * 8)); };
+
+    // ---------------- transforms ----------------
+    std::vector<XformJob> xjobs;
+    std::vector<Bw2dJob> bjobs(n);
+    int Gmax_opt = 0;
+    for (int i = 0; i < n; i++) {
+        const gdk_spec2d& s = specs[i];
+        bjobs[i] = Bw2dJob{nullptr, nullptr, 0, -1};
+        if (s.bw_mode != GDK_BW2D_PLAIN && s.bw_mode != GDK_BW2D_SHEAR) continue;
+        const bool shear = s.bw_mode == GDK_BW2D_SHEAR;
+        const int G = shear ? s.base_fine_bins : s.fine_bins;
+        const bool has_limits = s.x_has_bot || s.x_has_top || s.y_has_bot || s.y_has_top;
+        const Kde1dTablesHost* t = gdk_tables_for(ctx, G);
+        if (!t) return gdk_fail(ctx, GDK_ERR_NOMEM, "transform tables");
+        XformJob x{};
+        x.src = shear ? Hrot + sjobs[shear_of[i]].off : H + goff[i];
+        x.G = G;
+        x.a2 = take_d((size_t)G * G);
+        x.aFFT = has_limits ? nullptr : take_d((size_t)G * G);
+        x.tw = t->tw;
+        x.tw4 = t->tw4;
+        x.cos4 = t->cos4;
+        x.twn = t->twn;
+        if (!x.a2 || (!has_limits && !x.aFFT)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (a2)");
+        bjobs[i] = Bw2dJob{x.a2, x.aFFT, G, shear ? shear_of[i] : -1};
+        Gmax_opt = std::max(Gmax_opt, G);
+        xjobs.push_back(x);
+    }
+    const size_t mark = ar.used;
+    if (!xjobs.empty()) {
+        // scratch that is only alive during the transforms (released afterwards)
+        for (XformJob& x : xjobs) {
+            x.tmpD = take_d((size_t)x.G * x.G);
+            x.tmpC = x.aFFT ? reinterpret_cast<cplx*>(ar.take((size_t)x.G * x.G * 16)) : nullptr;
+            if (!x.tmpD || (x.aFFT && !x.tmpC)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (transform scratch)");
+        }
+        // launches are per grid size (shared-memory footprint and grid shape depend on G)
+        std::sort(xjobs.begin(), xjobs.end(), [](const XformJob& a, const XformJob& b) { return a.G < b.G; });
+        XformJob* dx = nullptr;
+        rc = upload_vec(ctx, xjobs, ctx->bytes2d_c, &dx);
+        if (rc) return rc;
+        PhaseTimer pt;
+        pt.begin(ctx, GDK_PH_XFORM2D);
+        k_grid_totals<<<(unsigned)xjobs.size(), 256, 0, ctx->stream>>>(dx);
+        ctx->launches++;
+        size_t b = 0;
+        while (b < xjobs.size()) {
+            size_t e = b;
+            while (e < xjobs.size() && xjobs[e].G == xjobs[b].G) e++;
+            const int G = xjobs[b].G;
+            const int lines = std::max(1, std::min(8, (int)((size_t)(ctx->max_smem - 2048) / ((size_t)G * 48))));
+            const size_t smem_r = (size_t)lines * G * 40, smem_c = (size_t)lines * G * 48;
+            if (smem_c > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "grid size %d too large for the transform kernels", G);
+            CK2(cudaFuncSetAttribute(k_xform_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_r, 48 << 10)));
+            CK2(cudaFuncSetAttribute(k_xform_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_c, 48 << 10)));
+            dim3 g((unsigned)((G + lines - 1) / lines), (unsigned)(e - b));
+            k_xform_rows<<<g, 256, smem_r, ctx->stream>>>(dx + b, lines);
+            k_xform_cols<<<g, 256, smem_c, ctx->stream>>>(dx + b, lines);
+            ctx->launches += 2;
+            b = e;
+        }
+        pt.end();
+        CK2(cudaGetLastError());
+    }
+    // ---------------- bandwidth ----------------
+    gdk_spec2d* dspecs = nullptr;
+    Bw2dJob* dbj = nullptr;
+    {
+        std::vector<gdk_spec2d> sv(specs, specs + n);
+        rc = upload_vec(ctx, sv, ctx->bytes2d_d, &dspecs);
+        if (rc) return rc;
+        rc = upload_vec(ctx, bjobs, ctx->bytes2d_e, &dbj);
+        if (rc) return rc;
+    }
+    if (ctx->bytes2d_res.ensure((size_t)n * sizeof(gdk_result2d))) return gdk_fail(ctx, GDK_ERR_NOMEM, "result buffer");
+    gdk_result2d* dres = reinterpret_cast<gdk_result2d*>(ctx->bytes2d_res.p);
+    {
+        const size_t smem = std::max<size_t>((size_t)2 * PSI_MAXE * std::max(Gmax_opt, 8) * 8, 1024);
+        if (smem > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "optimiser grid too large");
+        CK2(cudaFuncSetAttribute(k_bw2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
+        PhaseTimer pt;
+        pt.begin(ctx, GDK_PH_BW2D);
+        k_bw2d<<<n, 512, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
+        ctx->launches++;
+        pt.end();
+        CK2(cudaGetLastError());
+    }
+    CK2(cudaMemcpyAsync(res, dres, (size_t)n * sizeof(gdk_result2d), cudaMemcpyDeviceToHost, ctx->stream));
+    CK2(cudaStreamSynchronize(ctx->stream));
+
+    // ---------------- convolution stage ----------------
+    ar.used = mark;  // transform scratch is dead
+    std::vector<ConvJob> cj(n);
+    int wmax_all = 0;
+    if (ctx->bytes2d_mx.ensure((size_t)n * 8 * 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "max buffer");
+    CK2(cudaMemsetAsync(ctx->bytes2d_mx.p, 0, (size_t)n * 64, ctx->stream));
+    int max_mbc = 0;
+    for (int i = 0; i < n; i++) {
+        const gdk_spec2d& s = specs[i];
+        const int G = s.fine_bins, w = res[i].winw, K = 2 * w + 1;
+        if (w > 384) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "pair %d: kernel half-width %d exceeds the supported 384 bins", i, w);
+        if (s.mult_bias_correction_order > 6) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "mult_bias_correction_order > 6");
+        const bool has_prior = s.x_has_bot || s.x_has_top || s.y_has_bot || s.y_has_top;
+        ConvJob& c = cj[i];
+        c = ConvJob{};
+        c.hist = H + goff[i];
+        c.G = G;
+        c.w = w;
+        c.rx = res[i].rx;
+        c.ry = res[i].ry;
+        c.c = res[i].c;
+        if (s.bw_mode == GDK_BW2D_FIXED) c.c = s.kernel_corr;
+        c.bounded = (has_prior && s.boundary_correction_order >= 0) ? 1 : 0;
+        c.bco = s.boundary_correction_order;
+        c.mbc = s.mult_bias_correction_order;
+        c.xb = s.x_has_bot;
+        c.xt = s.x_has_top;
+        c.yb = s.y_has_bot;
+        c.yt = s.y_has_top;
+        c.Wk = take_d((size_t)K * K);
+        c.P = take_d((size_t)G * G);
+        c.Pn = c.mbc ? take_d((size_t)G * G) : c.P;
+        c.a00b = c.mbc ? take_d((size_t)G * G) : nullptr;
+        c.T = (c.mbc || c.bounded) ? take_d((size_t)K * G * 4) : nullptr;
+        if (c.bounded) {
+            c.maps = take_d((size_t)G * G * 6);
+            if (c.bco == 1) {
+                c.xP = take_d((size_t)G * G);
+                c.yP = take_d((size_t)G * G);
+            }
+        }
+        c.mx = reinterpret_cast<unsigned long long*>(ctx->bytes2d_mx.p) + (size_t)i * 8;
+        if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || !c.T)) || (c.bounded && (!c.maps || !c.T || (c.bco == 1 && (!c.xP || !c.yP)))))
+            return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (convolution stage, pair %d)", i);
+        wmax_all = std::max(wmax_all, w);
+        max_mbc = std::max(max_mbc, c.mbc);
+    }
+    // sort jobs by window size so that each launch group uses a tight shared-memory footprint
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cj[a].w < cj[b].w; });
+    std::vector<ConvJob> cjs(n);
+    std::vector<long long> offs_sorted(n);
+    for (int k = 0; k < n; k++) {
+        cjs[k] = cj[order[k]];
+        offs_sorted[k] = offsets[order[k]];
+    }
+    ConvJob* dcj = nullptr;
+    rc = upload_vec(ctx, cjs, ctx->bytes2d_c, &dcj);
+    if (rc) return rc;
+    long long* doffs = nullptr;
+    rc = upload_vec(ctx, offs_sorted, ctx->bytes2d_e, &doffs);
+    if (rc) return rc;
+    // result structs in sorted order for the finalize kernel's status bit
+    std::vector<gdk_result2d> res_sorted(n);
+    for (int k = 0; k < n; k++) res_sorted[k] = res[order[k]];
+    CK2(cudaMemcpyAsync(dres, res_sorted.data(), (size_t)n * sizeof(gdk_result2d), cudaMemcpyHostToDevice, ctx->stream));
+
+    PhaseTimer pt;
+    pt.begin(ctx, GDK_PH_CONV2D);
+    k_build_kernel2d<<<n, 256, 0, ctx->stream>>>(dcj);
+    ctx->launches++;
+    // groups of jobs with similar window size
+    struct Grp {
+        int b, e, wmax, Gmax;
+    };
+    std::vector<Grp> groups;
+    {
+        int b = 0;
+        while (b < n) {
+            int lim = 32;
+            while (lim < cjs[b].w) lim *= 2;
+            int e = b, gm = 0, wm = 0;
+            while (e < n && cjs[e].w <= lim) {
+                gm = std::max(gm, cjs[e].G);
+                wm = std::max(wm, cjs[e].w);
+                e++;
+            }
+            groups.push_back(Grp{b, e, wm, gm});
+            b = e;
+        }
+    }
+    auto conv_smem = [](int wmax) { return ((size_t)(CV_TY + CV_KC - 1) * (CV_TX + 2 * wmax + 4) + (size_t)CV_KC * (2 * wmax + 5)) * 8; };
+    const size_t smem_max = conv_smem(wmax_all);
+    if (smem_max > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "window too large for the convolution kernel");
+    CK2(cudaFuncSetAttribute(k_conv2d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+    CK2(cudaFuncSetAttribute(k_conv2d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+    for (const Grp& g : groups) {
+        const int nj = g.e - g.b;
+        const int K = 2 * g.wmax + 1;
+        // mask tables / maps (jobs without bias correction and without boundary correction skip internally)
+        dim3 gt((unsigned)K, (unsigned)nj);
+        k_mask_T<<<gt, 256, 0, ctx->stream>>>(dcj + g.b);
+        dim3 gm((unsigned)((g.Gmax + 7) / 8), (unsigned)nj);
+        k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
+        const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
+        dim3 gc((unsigned)tiles, (unsigned)nj);
+        k_conv2d<0><<<gc, 256, conv_smem(g.wmax), ctx->stream>>>(dcj + g.b, 0, g.wmax);
+        dim3 gb(64, (unsigned)nj);
+        k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+        ctx->launches += 4;
+        for (int it = 0; it < max_mbc; it++) {
+            k_conv2d<1><<<gc, 256, conv_smem(g.wmax), ctx->stream>>>(dcj + g.b, it, g.wmax);
+            ctx->launches++;
+        }
+    }
+    // output
+    double* dout = nullptr;
+    if (dev_out) {
+        dout = P_out;
+    } else {
+        size_t otot = 0;
+        for (int i = 0; i < n; i++) otot = std::max(otot, (size_t)(offsets[i] - offsets[0]) + (size_t)specs[i].fine_bins * specs[i].fine_bins);
+        if (ctx->f2.ensure(otot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D output buffer");
+        dout = ctx->f2.p - offsets[0];  // offsets are relative to P_out; the chunk's first density sits at f2[0]
+    }
+    {
+        dim3 gf(64, (unsigned)n);
+        k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dout, doffs, dres);
+        ctx->launches++;
+    }
+    pt.end();
+    CK2(cudaGetLastError());
+    CK2(cudaMemcpyAsync(res_sorted.data(), dres, (size_t)n * sizeof(gdk_result2d), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_out) {
+        // the chunk's densities are contiguous in P_out when offsets are packed back to back; copy per density
+        // otherwise
+        bool packed = true;
+        for (int i = 0; i + 1 < n; i++)
+            if (offsets[i + 1] != offsets[i] + (int64_t)specs[i].fine_bins * specs[i].fine_bins) packed = false;
+        if (packed) {
+            size_t cnt = (size_t)(offsets[n - 1] - offsets[0]) + (size_t)specs[n - 1].fine_bins * specs[n - 1].fine_bins;
+            CK2(cudaMemcpyAsync(P_out + offsets[0], ctx->f2.p, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            for (int i = 0; i < n; i++)
+                CK2(cudaMemcpyAsync(P_out + offsets[i], ctx->f2.p + (offsets[i] - offsets[0]),
+                                    (size_t)specs[i].fine_bins * specs[i].fine_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CK2(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n; k++) res[order[k]].status = res_sorted[k].status;
+    return 0;
+}
+
+static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
+                          gdk_result2d* res, uint32_t flags, bool hist_only) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (n <= 0 || !specs || !P_out || !offsets || (!hist_only && !res)) return gdk_fail(ctx, GDK_ERR_ARG, "2D batch: bad arguments");
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK2(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        const gdk_spec2d& s = specs[i];
+        if (s.px < 0 || s.px >= ctx->P || s.py < 0 || s.py >= ctx->P) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: parameter out of range", i);
+        if (s.fine_bins < 8 || s.fine_bins > 4096 || s.base_fine_bins < 8 || s.base_fine_bins > 4096)
+            return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: fine_bins_2D %d unsupported", i, s.fine_bins);
+        if (!(s.xbinmax > s.xbinmin) || !(s.ybinmax > s.ybinmin)) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: empty bin range", i);
+        if (hist_only) continue;
+        if (s.bw_mode < 0 || s.bw_mode > 3) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: bad bw_mode", i);
+        if (s.bw_mode != GDK_BW2D_FIXED && !(s.neff > 0)) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: N_eff must be > 0", i);
+        if (s.boundary_correction_order > 1) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: boundary_correction_order must be <= 1", i);
+        if (s.bw_mode == GDK_BW2D_SHEAR && (s.shear_i < 0 || s.shear_i >= ctx->P || s.shear_j < 0 || s.shear_j >= ctx->P))
+            return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: bad shear parameters", i);
+    }
+    // chunks bounded by a memory budget
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)32 << 30, (freeb + ctx->bytes_arena.cap) / 2));
+    int b = 0;
+    while (b < n) {
+        size_t acc = 0;
+        int e = b;
+        while (e < n) {
+            const size_t add = bytes_per_pair_estimate(specs[e]);
+            if (e > b && acc + add > budget) break;
+            acc += add;
+            e++;
+        }
+        int rc = density2d_chunk(ctx, e - b, specs + b, P_out, offsets + b, hist_only ? nullptr : res + b, flags, hist_only);
+        if (rc) return rc;
+        b = e;
+    }
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
+                                       gdk_result2d* res, uint32_t flags) {
+    return density2d_impl(ctx, n, specs, P_out, offsets, res, flags, false);
+}
+
+extern "C" int32_t gdk_hist2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* bins_out, const int64_t* offsets) {
+    return density2d_impl(ctx, n, specs, bins_out, offsets, nullptr, 0, true);
 }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kde1d_core.cuh"
+#include "kde2d_core.cuh"
 #include "kernels_1d.cuh"
 #include "kernels_quant.cuh"
 #include "kernels_stats.cuh"
@@ -92,7 +93,8 @@ struct gdk_ctx {
     DevBuf<gdk_spec1d> specs1d;
     DevBuf<gdk_result1d> res1d;
     DevBuf<Kde1dTables> tabs1d;
-    DevBuf<unsigned char> bytes2d, bytes2d_b;
+    DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena;
+    Kde2dConsts k2d;
     DevBuf<cplx> cwork2d;
 };
 

@@ -69,3 +69,25 @@ static inline void gdk_fill_isj_consts(IsjConsts* K) {
         K->cj[j] = (1 + pow(0.5, j + 0.5)) / 3 * prod / (rootpi / sqrt(2.0));
     }
 }
+
+#include "kde2d_core.cuh"
+// kde_bandwidth.py:140-143 and the powers of pi the psi functionals use
+static inline void gdk_fill_kde2d_consts(Kde2dConsts* K) {
+    K->pi2 = M_PI * M_PI;
+    K->K[0] = 1 / sqrt(2 * M_PI);
+    for (int j = 1; j < 5; j++) {
+        double prod = 1;
+        for (int o = 1; o < 2 * j; o += 2) prod *= o;
+        K->K[j] = ((j & 1) ? -1.0 : 1.0) * prod / sqrt(2 * M_PI);
+    }
+    K->Kodd[0] = 1;
+    for (int j = 1; j < 9; j++) {
+        double prod = 1;
+        for (int o = 1; o < 2 * j; o += 2) prod *= o;
+        K->Kodd[j] = prod / pow(2.0, j + 1) / sqrt(M_PI);
+    }
+    for (int k = 0; k < 12; k++) {
+        K->pipow[k] = pow(M_PI, 2 * k);
+        K->twopipow[k] = pow(2 * M_PI, k);
+    }
+}

@@ -1,0 +1,456 @@
+// kde2d_core.cuh -- grid-sized bandwidth selection for one 2D density, executed by one cooperating group.
+//
+// Restates KernelOptimizer2D (kde_bandwidth.py:146-309): psi functionals as bilinear forms on the squared
+// 2D-DCT (even orders) and on |FFT2|^2 (odd orders), the func2d / func2d_odd plug-in recursions, the
+// Brent fixed point for t*, the closed-form h_x, h_y, and the AMISE minimisation with its accept rules;
+// and the tail of getAutoBandwidth2D (mcsamples.py:1376-1419): rescaling to parameter units, de-rotation of
+// the sheared kernel, bias-order rescale, fallback widths.
+//
+// Differences from the reference, both documented in DESIGN.md:
+//   * the recursion is memoised per (s, level) and all psi of one level are accumulated in ONE sweep over
+//     a2 (identical arithmetic per node, 4 sweeps per fixed-point evaluation instead of 45 bilinear forms);
+//   * the final 2-3 variable AMISE minimisation uses a safeguarded Newton iteration with analytic
+//     derivatives, converged tightly, instead of scipy's TNC with finite-difference gradients (whose stopping
+//     point scatters by ~1e-4 in h under ulp-level input changes, see tests/test_oracle_golden.py notes).
+#pragma once
+#include "../../include/gdk.h"
+#include "coop.cuh"
+#include "solvers.cuh"
+
+#define PSI_MAXE 6  // max psi entries per level
+
+struct Kde2dConsts {
+    double K[5];     // kde_bandwidth.py:140-142
+    double Kodd[9];  // kde_bandwidth.py:143
+    double pi2;
+    double pipow[12];     // pi^(2k), k = 0..11   (np.pi ** (2 * sum(s)))
+    double twopipow[12];  // (2 pi)^k, k = 0..11
+};
+
+struct Kde2dWork {
+    const double* a2;    // squared dct2d of the normalised histogram, G x G row-major [ky][kx]; row/col 0 unused
+    const double* aFFT;  // |fft2|^2, G x G, or NULL when do_correlation is off
+    int G;
+    double* wx;  // [PSI_MAXE][G] scratch (shared memory on the device)
+    double* wy;  // [PSI_MAXE][G]
+};
+
+struct PsiEntry {
+    int s0, s1;
+    double time;
+};
+
+// psi(s, time) for up to PSI_MAXE entries in one sweep over a2 (kde_bandwidth.py:182-186)
+template <class C>
+GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W, const PsiEntry* e, int n, double* out) {
+    const int G = W.G;
+    for (int it = co.tid; it < n * (G - 1); it += co.nt) {
+        const int k = it / (G - 1), i = it - k * (G - 1) + 1;  // i = 1..G-1
+        const double I = (double)i * (double)i;
+        const double logI = log(I);
+        const double w = -I * (K.pi2 * e[k].time);
+        W.wx[k * G + i] = exp(w + logI * e[k].s0);
+        W.wy[k * G + i] = exp(w + logI * e[k].s1);
+    }
+    co.sync();
+    double part[PSI_MAXE];
+    for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
+    const int tot = (G - 1) * (G - 1);
+    for (int it = co.tid; it < tot; it += co.nt) {
+        const int y = it / (G - 1) + 1, x = it - (y - 1) * (G - 1) + 1;
+        const double v = W.a2[(size_t)y * G + x];
+        for (int k = 0; k < n; k++) part[k] += (W.wy[k * G + y] * v) * W.wx[k * G + x];
+    }
+    for (int k = 0; k < n; k++) {
+        const double s = co.sum(part[k]);
+        const int ss = e[k].s0 + e[k].s1;
+        out[k] = ((ss & 1) ? -1.0 : 1.0) * s * K.pipow[ss] / 4;
+    }
+    co.sync();
+}
+
+// psi_odd(s, time) (kde_bandwidth.py:209-214): frequencies f = fftfreq(G) * G
+template <class C>
+GDK_HD void psi_odd_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W, const PsiEntry* e, int n, double* out) {
+    const int G = W.G;
+    for (int it = co.tid; it < n * G; it += co.nt) {
+        const int k = it / G, i = it - k * G;
+        const double f = (i < (G + 1) / 2) ? (double)i : (double)(i - G);
+        const double w = exp(-(f * f) * (4 * K.pi2 * e[k].time));
+        W.wx[k * G + i] = w * pow(f, (double)e[k].s0);
+        W.wy[k * G + i] = w * pow(f, (double)e[k].s1);
+    }
+    co.sync();
+    double part[PSI_MAXE];
+    for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
+    const int tot = G * G;
+    for (int it = co.tid; it < tot; it += co.nt) {
+        const int y = it / G, x = it - y * G;
+        const double v = W.aFFT[it];
+        for (int k = 0; k < n; k++) part[k] += (W.wy[k * G + y] * v) * W.wx[k * G + x];
+    }
+    for (int k = 0; k < n; k++) {
+        const double s = co.sum(part[k]);
+        out[k] = s * K.twopipow[e[k].s0 + e[k].s1];
+    }
+    co.sync();
+}
+
+// func2d for every s with min_sum <= |s| <= 5 (kde_bandwidth.py:188-196), level by level from |s| = 5 down.
+// tab[s0][s1]; returns 0 on success, 1 if a non-finite value appeared.
+template <class C>
+GDK_HD int func2d_table(const C& co, const Kde2dConsts& K, const Kde2dWork& W, double N, double t, int min_sum,
+                        double tab[6][6]) {
+    int bad = 0;
+    for (int ssum = 5; ssum >= min_sum; ssum--) {
+        PsiEntry e[PSI_MAXE];
+        double out[PSI_MAXE];
+        const int n = ssum + 1;
+        for (int s0 = 0; s0 <= ssum; s0++) {
+            const int s1 = ssum - s0;
+            double time = t;
+            if (ssum <= 4) {
+                const double sum_func = tab[s0 + 1][s1] + tab[s0][s1 + 1];
+                const double cst = (1 + pow(0.5, (double)(ssum + 1))) / 3;
+                time = pow(-2 * cst * K.K[s0] * K.K[s1] / N / sum_func, 1.0 / (2 + ssum));
+            }
+            e[s0] = PsiEntry{s0, s1, time};
+            if (!(time == time)) bad = 1;
+        }
+        psi_even_level(co, K, W, e, n, out);
+        for (int s0 = 0; s0 <= ssum; s0++) {
+            tab[s0][ssum - s0] = out[s0];
+            if (!(out[s0] == out[s0]) || isinf(out[s0])) bad = 1;
+        }
+    }
+    return bad;
+}
+
+template <class C>
+struct FixedPoint2D {
+    const C& co;
+    const Kde2dConsts& K;
+    const Kde2dWork& W;
+    double N;
+    // kde_bandwidth.py:177-180
+    GDK_HD double operator()(double t, int& fail) const {
+        double tab[6][6];
+        const int bad = func2d_table(co, K, W, N, t, 2, tab);
+        const double sum_func = tab[0][2] + tab[2][0] + 2 * tab[1][1];
+        const double time = pow(2 * M_PI * N * sum_func, -1.0 / 3);
+        const double r = (t - time) / time;
+        if (bad || !(r == r)) fail = 1;
+        return r;
+    }
+};
+
+struct Amise {
+    double p40, p04, p22, p31, p13, N;
+    // kde_bandwidth.py:216-232; returns +inf where the reference raises ("bias not positive definite")
+    GDK_HD double operator()(double hx, double hy, double c) const {
+        const double var = 1.0 / (4 * M_PI * hx * hy * sqrt(1 - c * c) * N);
+        const double bias = 0.25 * (hx * hx * hx * hx * p40 + hy * hy * hy * hy * p04 + 2 * hx * hx * hy * hy * p22 * (2 * c * c + 1) +
+                                    4 * c * hx * hy * (hx * hx * p31 + hy * hy * p13));
+        if (bias < 0 || !(bias == bias)) return INFINITY;
+        return var + bias;
+    }
+    // gradient g[3] and Hessian H[3][3] with respect to (hx, hy, c)
+    GDK_HD void derivs(double hx, double hy, double c, double* g, double (*H)[3]) const {
+        const double V = 1.0 / (4 * M_PI * N);
+        const double s2 = 1 - c * c, s = sqrt(s2), s3 = s * s2, s5 = s3 * s2;
+        const double A = p40, B = p04, D = p22, E = p31, F = p13;
+        const double q = 2 * c * c + 1;
+        g[0] = -V / (hx * hx * hy * s) + 0.25 * (4 * A * hx * hx * hx + 4 * D * hx * hy * hy * q + 4 * c * hy * (3 * E * hx * hx + F * hy * hy));
+        g[1] = -V / (hx * hy * hy * s) + 0.25 * (4 * B * hy * hy * hy + 4 * D * hx * hx * hy * q + 4 * c * hx * (E * hx * hx + 3 * F * hy * hy));
+        g[2] = V * c / (hx * hy * s3) + 0.25 * (8 * D * hx * hx * hy * hy * c + 4 * hx * hy * (E * hx * hx + F * hy * hy));
+        H[0][0] = 2 * V / (hx * hx * hx * hy * s) + 0.25 * (12 * A * hx * hx + 4 * D * hy * hy * q + 24 * c * E * hx * hy);
+        H[1][1] = 2 * V / (hx * hy * hy * hy * s) + 0.25 * (12 * B * hy * hy + 4 * D * hx * hx * q + 24 * c * F * hx * hy);
+        H[0][1] = H[1][0] = V / (hx * hx * hy * hy * s) + 0.25 * (8 * D * hx * hy * q + 4 * c * (3 * E * hx * hx + 3 * F * hy * hy));
+        H[0][2] = H[2][0] = -V * c / (hx * hx * hy * s3) + 0.25 * (16 * D * hx * hy * hy * c + 4 * hy * (3 * E * hx * hx + F * hy * hy));
+        H[1][2] = H[2][1] = -V * c / (hx * hy * hy * s3) + 0.25 * (16 * D * hx * hx * hy * c + 4 * hx * (E * hx * hx + 3 * F * hy * hy));
+        H[2][2] = V * (1 + 2 * c * c) / (hx * hy * s5) + 0.25 * (8 * D * hx * hx * hy * hy);
+    }
+};
+
+// Safeguarded Newton minimisation of the AMISE over a box (nv = 2: c fixed; nv = 3: c free).
+// Variables at a bound whose gradient points outwards are frozen (active set); the Hessian of the free
+// block is shifted until positive definite; steps are backtracked on the function value.
+// Returns 1 on convergence (the analogue of res.success), 0 otherwise.  Scalar code: every thread of a
+// group executes it identically.
+GDK_HD int amise_minimise(const Amise& f, int nv, double* x, const double* lo, const double* hi) {
+    double fx = f(x[0], x[1], x[2]);
+    if (!(fx < INFINITY)) return 0;
+    for (int iter = 0; iter < 200; iter++) {
+        double g[3], H[3][3];
+        f.derivs(x[0], x[1], x[2], g, H);
+        bool freev[3];
+        int nfree = 0;
+        for (int i = 0; i < 3; i++) {
+            freev[i] = i < nv;
+            if (freev[i] && ((x[i] <= lo[i] && g[i] > 0) || (x[i] >= hi[i] && g[i] < 0))) freev[i] = false;
+            if (freev[i]) nfree++;
+        }
+        // scaled projected-gradient test
+        double gn = 0;
+        for (int i = 0; i < 3; i++)
+            if (freev[i]) gn = fmax(gn, fabs(g[i] * x[i] == 0 ? g[i] : g[i] * fmax(fabs(x[i]), 1e-3)));
+        if (nfree == 0 || gn <= 1e-14 * fmax(fabs(fx), 1e-300)) return 1;
+        // solve (H_ff + lam I) d = -g_f by Cholesky with increasing shift
+        double d[3] = {0, 0, 0};
+        double lam = 0;
+        bool ok = false;
+        for (int tries = 0; tries < 60 && !ok; tries++) {
+            int idx[3], m = 0;
+            for (int i = 0; i < 3; i++)
+                if (freev[i]) idx[m++] = i;
+            double L[3][3];
+            ok = true;
+            for (int a = 0; a < m && ok; a++)
+                for (int b = 0; b <= a; b++) {
+                    double sacc = H[idx[a]][idx[b]] + (a == b ? lam : 0.0);
+                    for (int k = 0; k < b; k++) sacc -= L[a][k] * L[b][k];
+                    if (a == b) {
+                        if (!(sacc > 0)) {
+                            ok = false;
+                            break;
+                        }
+                        L[a][a] = sqrt(sacc);
+                    } else {
+                        L[a][b] = sacc / L[b][b];
+                    }
+                }
+            if (ok) {
+                double y[3];
+                for (int a = 0; a < m; a++) {
+                    double sacc = -g[idx[a]];
+                    for (int k = 0; k < a; k++) sacc -= L[a][k] * y[k];
+                    y[a] = sacc / L[a][a];
+                }
+                for (int a = m - 1; a >= 0; a--) {
+                    double sacc = y[a];
+                    for (int k = a + 1; k < m; k++) sacc -= L[k][a] * d[idx[k]];
+                    d[idx[a]] = sacc / L[a][a];
+                }
+            } else {
+                double diagmax = 0;
+                for (int i = 0; i < 3; i++)
+                    if (freev[i]) diagmax = fmax(diagmax, fabs(H[i][i]));
+                lam = (lam == 0) ? 1e-6 * fmax(diagmax, 1e-300) : lam * 10;
+            }
+        }
+        if (!ok) return 0;
+        // backtracking line search with projection onto the box
+        double step = 1.0;
+        bool moved = false;
+        double xn[3];
+        for (int ls = 0; ls < 60; ls++) {
+            for (int i = 0; i < 3; i++) {
+                xn[i] = x[i] + step * d[i];
+                if (i < nv) xn[i] = fmin(fmax(xn[i], lo[i]), hi[i]);
+            }
+            const double fn = f(xn[0], xn[1], xn[2]);
+            if (fn < fx) {
+                moved = true;
+                double rel = 0;
+                for (int i = 0; i < nv; i++) rel = fmax(rel, fabs(xn[i] - x[i]) / fmax(fabs(x[i]), 1e-3));
+                const double dec = fx - fn;
+                for (int i = 0; i < 3; i++) x[i] = xn[i];
+                fx = fn;
+                if (rel < 1e-13 || dec <= 1e-16 * fabs(fx)) return 1;
+                break;
+            }
+            step *= 0.5;
+        }
+        if (!moved) return 1;  // no descent possible at working precision: at the minimum
+    }
+    return 0;
+}
+
+struct Bw2dOut {
+    double hx, hy, c;  // what KernelOptimizer2D.get_h returns (grid-fraction units)
+    double t_star;
+    uint32_t status;
+    int n_brent;
+    int failed;  // ValueError-equivalent: caller applies fallback widths
+};
+
+// KernelOptimizer2D(data, N, corr, do_correlation, fallback_t).get_h()
+template <class C>
+GDK_HD Bw2dOut kernel_optimizer_2d(const C& co, const Kde2dConsts& K, const Kde2dWork& W, double N, double corr,
+                                   int do_correlation, int have_fallback_t, double fallback_t) {
+    Bw2dOut o{0, 0, 0, NAN, 0u, 0, 0};
+    FixedPoint2D<C> fp{co, K, W, N};
+    RootResult rr = brentq_port(fp, 0.0, 0.1, 0.001 * 0.001, 4 * GDK_DBL_EPS, 100);
+    o.n_brent = rr.nfev;
+    double t_star = rr.x;
+    if (rr.status == 0) {
+        if (have_fallback_t && fallback_t != 0 && t_star > 0.01 && t_star > 2 * fallback_t) {
+            t_star = fallback_t;
+            o.status |= GDK_ST_FALLBACK_T;
+        }
+    } else {
+        if (rr.status == 1) o.status |= GDK_ST_NONFINITE;
+        if (have_fallback_t) {
+            t_star = fallback_t;
+            o.status |= GDK_ST_FALLBACK_T;
+        } else {
+            o.failed = 1;
+            return o;
+        }
+    }
+    o.t_star = t_star;
+    double tab[6][6];
+    const int bad = func2d_table(co, K, W, N, t_star, do_correlation ? 0 : 2, tab);
+    const double p_02 = tab[0][2], p_20 = tab[2][0], p_11 = tab[1][1];
+    double h_x = pow(pow(p_02, 0.75) / (4 * M_PI * N * pow(p_20, 0.75) * (p_11 + sqrt(p_20 * p_02))), 1.0 / 6);
+    double h_y = pow(pow(p_20, 0.75) / (4 * M_PI * N * pow(p_02, 0.75) * (p_11 + sqrt(p_20 * p_02))), 1.0 / 6);
+    if (bad || !(h_x == h_x) || !(h_y == h_y)) {
+        o.status |= GDK_ST_NONFINITE;
+        o.failed = 1;
+        return o;
+    }
+    double c = 0;
+    o.hx = h_x;
+    o.hy = h_y;
+    o.c = 0;
+    if (!do_correlation) return o;
+    // odd functionals under [1,3] and [3,1] (kde_bandwidth.py:198-207)
+    const double p00 = tab[0][0];
+    double otab[10][10];
+    for (int ssum = 10; ssum >= 4; ssum -= 2) {
+        PsiEntry e[PSI_MAXE];
+        double out[PSI_MAXE];
+        int n = 0;
+        for (int s0 = 1; s0 < ssum; s0 += 2) {
+            const int s1 = ssum - s0;
+            double time = t_star;
+            if (ssum <= 8) {
+                const double sum_func = otab[s0 + 2][s1] + otab[s0][s1 + 2];
+                const double cst = 8 * (1 - pow(2.0, (double)(-ssum - 1))) / 3.0;
+                time = pow(cst * p00 * K.Kodd[s0] * K.Kodd[s1] / (N * N) / (sum_func * sum_func), 1.0 / (3 + ssum));
+            }
+            e[n++] = PsiEntry{s0, s1, time};
+        }
+        psi_odd_level(co, K, W, e, n, out);
+        for (int k = 0; k < n; k++) otab[e[k].s0][e[k].s1] = out[k];
+    }
+    Amise am{p_20, p_02, p_11, otab[3][1], otab[1][3], N};
+    double AM = am(h_x, h_y, 0.0);
+    if (!(AM < INFINITY)) {
+        o.status |= GDK_ST_BIAS_NEG;  // the reference raises here (outside any try)
+        o.failed = 1;
+        return o;
+    }
+    const double lo[3] = {0.001, 0.001, -0.99}, hi[3] = {0.3, 0.3, 0.99};
+    if (corr != 0) {
+        const double sc = sqrt(1 - fabs(corr));
+        double x[3] = {h_x / sc, h_y / sc, corr};
+        x[0] = fmin(fmax(x[0], lo[0]), hi[0]);  // TNC clips the start into the box
+        x[1] = fmin(fmax(x[1], lo[1]), hi[1]);
+        if (amise_minimise(am, 2, x, lo, hi)) {
+            const double A2 = am(x[0], x[1], corr);
+            if (A2 < AM) {
+                h_x = x[0];
+                h_y = x[1];
+                c = corr;
+                AM = A2;
+                o.status |= GDK_ST_AMISE_CORR;
+            }
+        }
+    }
+    {
+        double x[3] = {h_x, h_y, corr};
+        for (int i = 0; i < 3; i++) x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+        if (amise_minimise(am, 3, x, lo, hi)) {
+            const double A3 = am(x[0], x[1], x[2]);
+            if (A3 < AM * 0.9) {
+                h_x = x[0];
+                h_y = x[1];
+                c = x[2];
+                o.status |= GDK_ST_AMISE_FULL;
+            }
+        }
+    }
+    o.hx = h_x;
+    o.hy = h_y;
+    o.c = c;
+    return o;
+}
+
+// Tail of getAutoBandwidth2D + the smoothing-width logic of get2DDensityGridData (mcsamples.py:1336-1345,
+// 1376-1419, 1848-1863): from the optimiser output (or the rule of thumb / fallback) to (hx, hy, c) in
+// parameter units, (rx, ry) in bins and the kernel half width.
+GDK_HD void finish_bandwidth_2d(const gdk_spec2d& sp, const Bw2dOut* opt, double r2_shear, gdk_result2d* res) {
+    const double N_eff = sp.neff;
+    const double rangex = sp.xbinmax - sp.xbinmin, rangey = sp.ybinmax - sp.ybinmin;
+    const double fwx = rangex / (sp.fine_bins - 1), fwy = rangey / (sp.fine_bins - 1);
+    double hx = 0, hy = 0, c = sp.kernel_corr, rx, ry;
+    uint32_t status = 0;
+    double t_star = NAN;
+    int n_brent = 0;
+    if (sp.bw_mode == GDK_BW2D_FIXED) {
+        rx = sp.rx_fixed;
+        ry = sp.ry_fixed;
+    } else {
+        bool fallback = false;
+        if (sp.bw_mode == GDK_BW2D_RULE) {
+            fallback = true;  // same formula as fallback_widths, without the warning
+        } else {
+            status = opt->status;
+            t_star = opt->t_star;
+            n_brent = opt->n_brent;
+            if (opt->failed) {
+                fallback = true;
+                if (!(status & GDK_ST_BIAS_NEG)) status |= GDK_ST_BW_FALLBACK;
+            } else if (sp.bw_mode == GDK_BW2D_SHEAR) {
+                const double r1 = sp.p1_max - sp.p1_min;
+                double ex = opt->hx * r1, ey = opt->hy * r2_shear, ec = opt->c;
+                // kernelC = S [[hx^2, hx hy c],[hx hy c, hy^2]] S^T with S lower triangular
+                const double m00 = ex * ex, m01 = ex * ey * ec, m11 = ey * ey;
+                const double t00 = sp.S00 * m00, t01 = sp.S00 * m01;                    // (S M) row 0
+                const double t10 = sp.S10 * m00 + sp.S11 * m01, t11 = sp.S10 * m01 + sp.S11 * m11;  // row 1
+                const double k00 = t00 * sp.S00;
+                const double k01 = t00 * sp.S10 + t01 * sp.S11;
+                const double k11 = t10 * sp.S10 + t11 * sp.S11;
+                hx = sqrt(k00);
+                hy = sqrt(k11);
+                c = k01 / sqrt(k00 * k11);
+                if (sp.shear_swapped) {
+                    const double t = hx;
+                    hx = hy;
+                    hy = t;
+                }
+            } else {
+                hx = opt->hx * rangex;
+                hy = opt->hy * rangey;
+                c = opt->c;
+            }
+        }
+        if (fallback) {
+            hx = sp.x_sigma_range / pow(N_eff, 1.0 / 6);
+            hy = sp.y_sigma_range / pow(N_eff, 1.0 / 6);
+            c = fmax(fmin(sp.corr, sp.max_corr_2D), -sp.max_corr_2D);
+        }
+        if (sp.mult_bias_correction_order) {
+            const double scale = 1.1 * pow(N_eff, 1.0 / 6 - 1.0 / (2 + 4 * (1 + sp.mult_bias_correction_order)));
+            hx *= scale;
+            hy *= scale;
+        }
+        rx = hx * fabs(sp.smooth_scale_2D) / fwx;
+        ry = hy * fabs(sp.smooth_scale_2D) / fwy;
+    }
+    const double smooth_scale = fmax(rx, ry);
+    if (smooth_scale < 2) status |= GDK_ST_SMALL_SMOOTH;
+    int winw = (int)rint(2.5 * smooth_scale);
+    if (winw < 1) winw = 1;
+    res->hx = hx;
+    res->hy = hy;
+    res->c = c;
+    res->rx = rx;
+    res->ry = ry;
+    res->t_star = t_star;
+    res->winw = winw;
+    res->status = status;
+    res->n_brent = n_brent;
+    res->pad = 0;
+}

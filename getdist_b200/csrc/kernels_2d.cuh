@@ -1,0 +1,634 @@
+// kernels_2d.cuh -- the 2D density path on the device.
+//   k_hist2d_tiles   weighted 2D fine-grid histograms (_binSamples x2 + _make2Dhist, mcsamples.py:1821-1827,
+//                    1724-1728) for tiles of up to 8 x 8 parameter pairs per CTA: every sample row is read
+//                    once per tile, its 16 bin indices computed once, then up to 64 grid updates issued as
+//                    native 64-bit integer global reductions (REDG.ADD.64) into L2-resident grids
+//   k_shear_*        the sheared re-binning of getAutoBandwidth2D (mcsamples.py:1370-1375, kde.bin_samples)
+//   k_xform_*        dct2d and |fft2|^2 of the normalised histogram (kde_bandwidth.py:151-157) with the
+//                    shared-memory Stockham FFT, rows then columns
+//   k_bw2d           one CTA per pair: KernelOptimizer2D + the tail of getAutoBandwidth2D (kde2d_core.cuh)
+//   k_build_kernel2d the correlated Gaussian window (mcsamples.py:1863-1867)
+//   k_conv2d         direct 2D convolution, register-tiled (convolve2D 'same', convolve.py:205-212)
+//   k_mask_*         the 'valid' convolutions of the prior mask with the moment kernels (mcsamples.py:
+//                    1926-1951, 1967) evaluated separably: mask = my (x) mx is piecewise constant
+//   k_boundary2d     linear boundary correction (mcsamples.py:1927-1959)
+//   k_finalize2d     normalize('max') (densities.py:71-92)
+#pragma once
+#include "kde2d_core.cuh"
+#include "kernels_1d.cuh"
+
+// ----------------------------------------------------------------------------------------------------
+// histograms
+// ----------------------------------------------------------------------------------------------------
+#define HT 8  // tile edge (parameters per side)
+
+struct Tile2d {
+    int na, nb, G, pad;
+    int pa[HT], pb[HT];
+    double amin[HT], afw[HT], ainv[HT];
+    double bmin[HT], bfw[HT], binv[HT];
+    long long off[HT][HT];  // grid offset (elements) of pair (a, b) or -1
+};
+
+// grid (nseg, ntiles), 256 threads
+__global__ void __launch_bounds__(256) k_hist2d_tiles(const double* __restrict__ dX, int64_t ld,
+                                                      const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                      const Tile2d* __restrict__ tiles, unsigned long long* __restrict__ grids) {
+    __shared__ Tile2d T;
+    {
+        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tile2d) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const Seg sg = segs[blockIdx.x];
+    const int G = T.G, na = T.na, nb = T.nb;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const unsigned long long w = dWq[r];
+        int ia[HT], ib[HT];
+#pragma unroll
+        for (int k = 0; k < HT; k++) {
+            ia[k] = -1;
+            if (k < na) {
+                const int b = bin_index_round(ldg_stream(dX + (int64_t)T.pa[k] * ld + r), T.amin[k], T.afw[k], T.ainv[k]);
+                ia[k] = (b >= 0 && b < G) ? b : -1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HT; k++) {
+            ib[k] = -1;
+            if (k < nb) {
+                const int b = bin_index_round(ldg_stream(dX + (int64_t)T.pb[k] * ld + r), T.bmin[k], T.bfw[k], T.binv[k]);
+                ib[k] = (b >= 0 && b < G) ? b : -1;
+            }
+        }
+        if (w == 0) continue;
+#pragma unroll
+        for (int a = 0; a < HT; a++) {
+            if (a >= na || ia[a] < 0) continue;
+#pragma unroll
+            for (int b = 0; b < HT; b++) {
+                if (b >= nb || ib[b] < 0) continue;
+                const long long off = T.off[a][b];
+                if (off >= 0) atomicAdd(grids + off + (long long)ib[b] * G + ia[a], w);
+            }
+        }
+    }
+}
+
+// in-place fixed point -> float64 (same storage)
+__global__ void k_u64_to_f64_inplace(unsigned long long* __restrict__ g, int64_t n, double inv_scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)g[i] * inv_scale;
+        reinterpret_cast<double*>(g)[i] = v;
+    }
+}
+
+struct ShearJob {
+    int pi, pj, Gb, pad;
+    double r0, r1;
+    double p1_min, dx1, inv1;  // kde.bin_samples geometry of p1 (host)
+    long long off;             // rot grid offset (elements)
+};
+struct ShearGeom {
+    double rmin, dx, inv, R;
+};
+
+__device__ __forceinline__ double shear_p2(double xi, double xj, double r0, double r1) {
+    return __dadd_rn(__dmul_rn(r0, xi), __dmul_rn(r1, xj));  // r[0]*xi + r[1]*xj, no FMA contraction
+}
+
+// grid (nseg, nshear): partial min/max of p2 -> part[(job*nseg + seg)*2]
+__global__ void __launch_bounds__(256) k_shear_minmax(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
+                                                      int nseg, const ShearJob* __restrict__ jobs, double* __restrict__ part) {
+    const ShearJob jb = jobs[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const double* xi = dX + (int64_t)jb.pi * ld;
+    const double* xj = dX + (int64_t)jb.pj * ld;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const double p2 = shear_p2(ldg_stream(xi + r), ldg_stream(xj + r), jb.r0, jb.r1);
+        mn = fmin(mn, p2);
+        mx = fmax(mx, p2);
+    }
+    __shared__ double sh[2][8];
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = mn;
+        sh[1][threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) {
+            mn = fmin(mn, sh[0][i]);
+            mx = fmax(mx, sh[1][i]);
+        }
+        mn = fmin(mn, sh[0][0]);
+        mx = fmax(mx, sh[1][0]);
+        part[((int64_t)blockIdx.y * nseg + blockIdx.x) * 2 + 0] = mn;
+        part[((int64_t)blockIdx.y * nseg + blockIdx.x) * 2 + 1] = mx;
+    }
+}
+
+// kde.bin_samples range of p2 (kde_bandwidth.py:77-86): one thread per job
+__global__ void k_shear_geom(const double* __restrict__ part, int nseg, int njobs, const ShearJob* __restrict__ jobs,
+                             ShearGeom* __restrict__ geom) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int s = 0; s < nseg; s++) {
+        mn = fmin(mn, part[((int64_t)j * nseg + s) * 2]);
+        mx = fmax(mx, part[((int64_t)j * nseg + s) * 2 + 1]);
+    }
+    const double delta = __dsub_rn(mx, mn);
+    const double rmin = __dsub_rn(mn, __dmul_rn(delta, 0.1));
+    const double rmax = __dadd_rn(mx, __dmul_rn(delta, 0.1));
+    const double R = __dsub_rn(rmax, rmin);
+    const double dx = __ddiv_rn(R, (double)(jobs[j].Gb - 1));
+    geom[j] = ShearGeom{rmin, dx, 1.0 / dx, R};
+}
+
+// grid (nseg, nshear)
+__global__ void __launch_bounds__(256) k_shear_hist(const double* __restrict__ dX, int64_t ld,
+                                                    const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                    const ShearJob* __restrict__ jobs, const ShearGeom* __restrict__ geom,
+                                                    unsigned long long* __restrict__ grids) {
+    const ShearJob jb = jobs[blockIdx.y];
+    const ShearGeom gm = geom[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const double* xi = dX + (int64_t)jb.pi * ld;
+    const double* xj = dX + (int64_t)jb.pj * ld;
+    const int G = jb.Gb;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const double a = ldg_stream(xi + r), b = ldg_stream(xj + r);
+        const int b1 = bin_index_trunc(a, jb.p1_min, jb.dx1, jb.inv1);
+        const int b2 = bin_index_trunc(shear_p2(a, b, jb.r0, jb.r1), gm.rmin, gm.dx, gm.inv);
+        const unsigned long long w = dWq[r];
+        if (w && b1 >= 0 && b1 < G && b2 >= 0 && b2 < G) atomicAdd(grids + jb.off + (long long)b2 * G + b1, w);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// transforms
+// ----------------------------------------------------------------------------------------------------
+struct XformJob {
+    const double* src;  // G x G histogram (float64)
+    double* a2;         // G x G
+    double* aFFT;       // G x G or NULL
+    double* tmpD;       // G x G real scratch
+    cplx* tmpC;         // G x G complex scratch (NULL when aFFT is NULL)
+    const cplx* tw;     // tables for G (pow2) ...
+    const cplx* tw4;
+    const double* cos4;  // ... or direct tables
+    const cplx* twn;
+    int G, pad;
+    double total;  // filled by k_grid_totals
+};
+
+// one CTA per job
+__global__ void __launch_bounds__(256) k_grid_totals(XformJob* __restrict__ jobs) {
+    __shared__ double red[32];
+    XformJob& jb = jobs[blockIdx.x];
+    const int64_t n = (int64_t)jb.G * jb.G;
+    double s = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += jb.src[i];
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    const double t = co.sum(s);
+    if (threadIdx.x == 0) jb.total = t;
+}
+
+// rows: grid (ceil(G/rb), njobs), 256 threads, dynamic smem = rb*G*(8 + 16 + 16) bytes
+__global__ void __launch_bounds__(256) k_xform_rows(const XformJob* __restrict__ jobs, int rb) {
+    extern __shared__ __align__(16) unsigned char xsm[];
+    __shared__ double red[32];
+    const XformJob jb = jobs[blockIdx.y];
+    const int G = jb.G;
+    const int y0 = blockIdx.x * rb;
+    if (y0 >= G) return;
+    const int nl = min(rb, G - y0);
+    double* in = reinterpret_cast<double*>(xsm);
+    cplx* a = reinterpret_cast<cplx*>(xsm + (size_t)rb * G * 8);
+    cplx* b = a + (size_t)rb * G;
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    for (int it = threadIdx.x; it < nl * G; it += blockDim.x) in[it] = jb.src[(size_t)y0 * G + it] / jb.total;
+    __syncthreads();
+    double* outD = jb.tmpD + (size_t)y0 * G;
+    if (jb.tw) {
+        dct2_lines_pow2(co, in, outD, a, b, G, nl, jb.tw, jb.tw4);
+    } else {
+        dct2_lines_direct(co, in, outD, G, nl, jb.cos4);
+    }
+    if (jb.aFFT) {
+        cplx* outC = jb.tmpC + (size_t)y0 * G;
+        if (jb.tw) {
+            for (int it = threadIdx.x; it < nl * G; it += blockDim.x) a[it] = cplx{in[it], 0.0};
+            __syncthreads();
+            const cplx* r = fft_lines(co, a, b, G, nl, jb.tw);
+            for (int it = threadIdx.x; it < nl * G; it += blockDim.x) outC[it] = r[it];
+        } else {
+            for (int it = threadIdx.x; it < nl * G; it += blockDim.x) a[it] = cplx{in[it], 0.0};
+            __syncthreads();
+            dft_lines_direct(co, a, outC, G, nl, jb.twn);
+        }
+    }
+}
+
+// columns: grid (ceil(G/cb), njobs), 256 threads, dynamic smem = cb*G*(8 + 8 + 16 + 16) bytes
+__global__ void __launch_bounds__(256) k_xform_cols(const XformJob* __restrict__ jobs, int cb) {
+    extern __shared__ __align__(16) unsigned char xsm[];
+    __shared__ double red[32];
+    const XformJob jb = jobs[blockIdx.y];
+    const int G = jb.G;
+    const int x0 = blockIdx.x * cb;
+    if (x0 >= G) return;
+    const int nl = min(cb, G - x0);
+    double* in = reinterpret_cast<double*>(xsm);
+    double* out = in + (size_t)cb * G;
+    cplx* a = reinterpret_cast<cplx*>(xsm + (size_t)cb * G * 16);
+    cplx* b = a + (size_t)cb * G;
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    // line l = column x0 + l, element y
+    for (int it = threadIdx.x; it < nl * G; it += blockDim.x) {
+        const int y = it / nl, l = it - y * nl;
+        in[(size_t)l * G + y] = jb.tmpD[(size_t)y * G + x0 + l];
+    }
+    __syncthreads();
+    if (jb.tw)
+        dct2_lines_pow2(co, in, out, a, b, G, nl, jb.tw, jb.tw4);
+    else
+        dct2_lines_direct(co, in, out, G, nl, jb.cos4);
+    for (int it = threadIdx.x; it < nl * G; it += blockDim.x) {
+        const int y = it / nl, l = it - y * nl;
+        const double v = out[(size_t)l * G + y];
+        jb.a2[(size_t)y * G + x0 + l] = v * v;
+    }
+    if (jb.aFFT) {
+        __syncthreads();
+        for (int it = threadIdx.x; it < nl * G; it += blockDim.x) {
+            const int y = it / nl, l = it - y * nl;
+            a[(size_t)l * G + y] = jb.tmpC[(size_t)y * G + x0 + l];
+        }
+        __syncthreads();
+        const cplx* r;
+        if (jb.tw) {
+            r = fft_lines(co, a, b, G, nl, jb.tw);
+        } else {
+            dft_lines_direct(co, a, b, G, nl, jb.twn);
+            r = b;
+        }
+        for (int it = threadIdx.x; it < nl * G; it += blockDim.x) {
+            const int y = it / nl, l = it - y * nl;
+            const cplx v = r[(size_t)l * G + y];
+            jb.aFFT[(size_t)y * G + x0 + l] = v.x * v.x + v.y * v.y;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// bandwidth
+// ----------------------------------------------------------------------------------------------------
+struct Bw2dJob {
+    const double* a2;
+    const double* aFFT;
+    int G;        // size of the optimiser grid (pair grid or base grid for the shear branch)
+    int shear;    // index into ShearGeom or -1
+};
+
+// grid (npairs), 512 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
+__global__ void __launch_bounds__(512) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
+                                              const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    __shared__ double red[32];
+    const gdk_spec2d sp = specs[blockIdx.x];
+    const Bw2dJob jb = jobs[blockIdx.x];
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    Bw2dOut o{0, 0, 0, NAN, 0u, 0, 0};
+    double r2 = 0;
+    if (sp.bw_mode == GDK_BW2D_PLAIN || sp.bw_mode == GDK_BW2D_SHEAR) {
+        const int G = jb.G;
+        double* wx = reinterpret_cast<double*>(bsm);
+        double* wy = wx + (size_t)PSI_MAXE * G;
+        const bool has_limits = sp.x_has_bot || sp.x_has_top || sp.y_has_bot || sp.y_has_top;
+        const int do_corr = has_limits ? 0 : 1;
+        Kde2dWork W{jb.a2, do_corr ? jb.aFFT : nullptr, G, wx, wy};
+        if (sp.bw_mode == GDK_BW2D_PLAIN) {
+            const double rangex = sp.xbinmax - sp.xbinmin, rangey = sp.ybinmax - sp.ybinmin;
+            const double q = fmin(sp.y_sigma_range / rangey, sp.x_sigma_range / rangex) / pow(sp.neff, 1.0 / 6);
+            o = kernel_optimizer_2d(co, K, W, sp.neff, sp.corr, do_corr, 1, q * q);
+        } else {
+            o = kernel_optimizer_2d(co, K, W, sp.neff, 0.0, do_corr, 0, 0.0);
+            r2 = geom[jb.shear].R;
+        }
+    }
+    if (threadIdx.x == 0) finish_bandwidth_2d(sp, &o, r2, res + blockIdx.x);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// convolution stage
+// ----------------------------------------------------------------------------------------------------
+struct ConvJob {
+    const double* hist;  // G x G
+    double* Wk;          // K x K window, [u + w][v + w]
+    double* P;           // current density
+    double* Pn;          // next density (bias iterations)
+    double* xP;          // bounded, order 1
+    double* yP;
+    double* maps;        // bounded: 6 maps a00,a10,a01,a20,a02,a11 (G*G each)
+    double* a00b;        // bias-correction normaliser map
+    double* T;           // scratch K x G x 3
+    unsigned long long* mx;  // [8] running maxima (bit patterns of non-negative doubles):
+                             // 0 = hist*W, 1 = after boundary correction, 2 + it = after bias iteration it
+    double rx, ry, c;
+    int G, w;
+    int bounded;  // boundary correction active (has_prior && order >= 0)
+    int bco, mbc;
+    int xb, xt, yb, yt;
+};
+
+// window: one CTA per job
+__global__ void __launch_bounds__(256) k_build_kernel2d(const ConvJob* __restrict__ jobs) {
+    __shared__ double red[32];
+    const ConvJob jb = jobs[blockIdx.x];
+    const int w = jb.w, K = 2 * w + 1;
+    // Cinv = inv([[ry^2, rx ry c], [rx ry c, rx^2]])  (mcsamples.py:1864)
+    const double m00 = jb.ry * jb.ry, m01 = jb.rx * jb.ry * jb.c, m11 = jb.rx * jb.rx;
+    const double det = m00 * m11 - m01 * m01;
+    const double C00 = m11 / det, C11 = m00 / det, C10 = -m01 / det;
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    double part = 0;
+    for (int it = threadIdx.x; it < K * K; it += blockDim.x) {
+        const int i1 = it / K - w, i2 = it % K - w;
+        const double v = exp(-((double)(i1 * i1) * C00 + (double)(i2 * i2) * C11 + 2 * C10 * (double)i1 * (double)i2) / 2);
+        jb.Wk[it] = v;
+        part += v;
+    }
+    const double s = co.sum(part);
+    for (int it = threadIdx.x; it < K * K; it += blockDim.x) jb.Wk[it] = jb.Wk[it] / s;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* p, double v) {
+    if (v > 0) atomicMax(p, (unsigned long long)__double_as_longlong(v));
+}
+
+#define CV_TY 16
+#define CV_TX 64
+#define CV_KC 8
+// Direct 'same' convolution out[y][x] = sum_{u,v} W(u,v) in[y-u][x-v], zero padded.
+// MODE 0: in = hist                      -> P (and xP, yP when bounded with order 1); running max -> mx[0]
+// MODE 1: in = box = hist / P where P > thr (thr = mx[src]*1e-8) else hist
+//                                         -> Pn = P * conv / a00b; running max -> mx[dst]
+// grid (tiles, njobs), 256 threads (16 x 16), 4 consecutive outputs per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs, int iter, int wmax) {
+    extern __shared__ __align__(16) double csm[];
+    const ConvJob jb = jobs[blockIdx.y];
+    if (MODE == 1 && iter >= jb.mbc) return;
+    const int G = jb.G, w = jb.w, K = 2 * w + 1;
+    const int tilesx = (G + CV_TX - 1) / CV_TX;
+    const int tyi = blockIdx.x / tilesx, txi = blockIdx.x % tilesx;
+    const int oy0 = tyi * CV_TY, ox0 = txi * CV_TX;
+    if (oy0 >= G) return;
+    const int inw = CV_TX + 2 * wmax + 4;  // row pitch of the input tile
+    const int kp = 2 * wmax + 1 + 4;       // row pitch of the kernel chunk
+    double* in_s = csm;
+    double* wk_s = csm + (size_t)(CV_TY + CV_KC - 1) * inw;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const double* P = (MODE == 1) ? ((iter & 1) ? jb.Pn : jb.P) : nullptr;
+    double* Pout = (MODE == 1) ? ((iter & 1) ? jb.P : jb.Pn) : jb.P;
+    double thr = 0;
+    if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
+    const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
+    double acc[4] = {0, 0, 0, 0}, accx[4] = {0, 0, 0, 0}, accy[4] = {0, 0, 0, 0};
+    for (int k0 = 0; k0 < K; k0 += CV_KC) {
+        const int kc = min(CV_KC, K - k0);
+        __syncthreads();
+        // kernel chunk, columns reversed: wk_s[kk][kr] = W[k0+kk][2w - kr]
+        for (int it = threadIdx.x; it < kc * K; it += blockDim.x) {
+            const int kk = it / K, kr = it - kk * K;
+            wk_s[kk * kp + kr] = jb.Wk[(size_t)(k0 + kk) * K + (2 * w - kr)];
+        }
+        // input rows a = abase + r, r < CV_TY + kc - 1; columns b = ox0 - w + c, c < CV_TX + 2w
+        const int abase = oy0 - (k0 + kc - 1) + w;
+        const int nrow = CV_TY + kc - 1, ncol = CV_TX + 2 * w;
+        for (int it = threadIdx.x; it < nrow * ncol; it += blockDim.x) {
+            const int r = it / ncol, c = it - r * ncol;
+            const int a = abase + r, b = ox0 - w + c;
+            double v = 0;
+            if (a >= 0 && a < G && b >= 0 && b < G) {
+                v = jb.hist[(size_t)a * G + b];
+                if (MODE == 1) {
+                    const double p = P[(size_t)a * G + b];
+                    if (p > thr) v = v / p;
+                }
+            }
+            in_s[r * inw + c] = v;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kc; kk++) {
+            const int r = ty + (kc - 1 - kk);
+            const double* irow = in_s + r * inw + tx * 4;
+            const double* wr = wk_s + kk * kp;
+            const double u = (double)(k0 + kk - w);
+            double c0 = irow[0], c1 = irow[1], c2 = irow[2], c3 = irow[3];
+            if (!moments) {
+                for (int t = 0; t < K; t++) {
+                    const double wv = wr[t];
+                    acc[0] = fma(wv, c0, acc[0]);
+                    acc[1] = fma(wv, c1, acc[1]);
+                    acc[2] = fma(wv, c2, acc[2]);
+                    acc[3] = fma(wv, c3, acc[3]);
+                    c0 = c1;
+                    c1 = c2;
+                    c2 = c3;
+                    c3 = irow[t + 4];
+                }
+            } else {
+                for (int t = 0; t < K; t++) {
+                    const double wv = wr[t];
+                    const double wvx = wv * (double)(w - t);  // Win * indexes (column offset v = w - t)
+                    const double wvy = wv * u;                // Win * y       (row offset u)
+                    acc[0] = fma(wv, c0, acc[0]);
+                    acc[1] = fma(wv, c1, acc[1]);
+                    acc[2] = fma(wv, c2, acc[2]);
+                    acc[3] = fma(wv, c3, acc[3]);
+                    accx[0] = fma(wvx, c0, accx[0]);
+                    accx[1] = fma(wvx, c1, accx[1]);
+                    accx[2] = fma(wvx, c2, accx[2]);
+                    accx[3] = fma(wvx, c3, accx[3]);
+                    accy[0] = fma(wvy, c0, accy[0]);
+                    accy[1] = fma(wvy, c1, accy[1]);
+                    accy[2] = fma(wvy, c2, accy[2]);
+                    accy[3] = fma(wvy, c3, accy[3]);
+                    c0 = c1;
+                    c1 = c2;
+                    c2 = c3;
+                    c3 = irow[t + 4];
+                }
+            }
+        }
+    }
+    const int oy = oy0 + ty;
+    double tmax = 0;
+    if (oy < G) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int ox = ox0 + tx * 4 + m;
+            if (ox >= G) continue;
+            const size_t o = (size_t)oy * G + ox;
+            if (MODE == 0) {
+                jb.P[o] = acc[m];
+                if (moments) {
+                    jb.xP[o] = accx[m];
+                    jb.yP[o] = accy[m];
+                }
+                tmax = fmax(tmax, acc[m]);
+            } else {
+                const double v = P[o] * acc[m] / jb.a00b[o];
+                Pout[o] = v;
+                tmax = fmax(tmax, v);
+            }
+        }
+    }
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
+}
+
+// prior-mask factors along one axis (mcsamples.py:1688-1712): index s relative to the unpadded grid
+__device__ __forceinline__ double mask1d(int s, int G, int bot, int top) {
+    if (s < 0) return bot ? 0.0 : 1.0;
+    if (s > G - 1) return top ? 0.0 : 1.0;
+    double m = 1.0;
+    if (s == 0 && bot) m *= 0.5;
+    if (s == G - 1 && top) m *= 0.5;
+    return m;
+}
+
+// T[s][ku][x] = sum_v v^s W(u,v) mx(x - v)   for s = 0,1,2 (edge mask) and, at s = 3, the all-edge mask with
+// s = 0.  grid (K, njobs), 256 threads.
+__global__ void __launch_bounds__(256) k_mask_T(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    const int G = jb.G, w = jb.w, K = 2 * w + 1;
+    const int ku = blockIdx.x;
+    if (ku >= K || !jb.T) return;
+    const double* wrow = jb.Wk + (size_t)ku * K;
+    const int eb = jb.bounded ? jb.xb : 0, et = jb.bounded ? jb.xt : 0;
+    for (int x = threadIdx.x; x < G; x += blockDim.x) {
+        double t0 = 0, t1 = 0, t2 = 0, tb = 0;
+        for (int kv = 0; kv < K; kv++) {
+            const int v = kv - w;
+            const int s = x - v;
+            const double wv = wrow[kv];
+            const double m = mask1d(s, G, eb, et);
+            const double wx = wv * (double)v;
+            t0 += wv * m;
+            t1 += wx * m;
+            t2 += (wx * (double)v) * m;
+            const double mb = (s < 0 || s > G - 1) ? 0.0 : m;
+            tb += wv * mb;
+        }
+        const size_t base = ((size_t)ku) * G + x;
+        const size_t plane = (size_t)K * G;
+        jb.T[base] = t0;
+        jb.T[plane + base] = t1;
+        jb.T[2 * plane + base] = t2;
+        jb.T[3 * plane + base] = tb;
+    }
+}
+
+// maps: a_rs[y][x] = sum_u u^r my(y - u) T_s[u][x].  grid (ceil(G/8), njobs), 256 threads.
+__global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    const int G = jb.G, w = jb.w, K = 2 * w + 1;
+    const size_t plane = (size_t)K * G, gg = (size_t)G * G;
+    if (!jb.T) return;
+    const int eb = jb.bounded ? jb.yb : 0, et = jb.bounded ? jb.yt : 0;
+    for (int yy = 0; yy < 8; yy++) {
+        const int y = blockIdx.x * 8 + yy;
+        if (y >= G) break;
+        for (int x = threadIdx.x; x < G; x += blockDim.x) {
+            double a00 = 0, a10 = 0, a01 = 0, a20 = 0, a02 = 0, a11 = 0, ab = 0;
+            for (int ku = 0; ku < K; ku++) {
+                const int u = ku - w;
+                const int s = y - u;
+                const double m = mask1d(s, G, eb, et);
+                const double mb = (s < 0 || s > G - 1) ? 0.0 : m;
+                const size_t base = (size_t)ku * G + x;
+                const double t0 = jb.T[base];
+                ab += mb * jb.T[3 * plane + base];
+                if (jb.bounded) {
+                    const double t1 = jb.T[plane + base], t2 = jb.T[2 * plane + base];
+                    const double du = (double)u;
+                    a00 += m * t0;
+                    a10 += m * t1;
+                    a20 += m * t2;
+                    a01 += (m * du) * t0;
+                    a02 += (m * du * du) * t0;
+                    a11 += (m * du) * t1;
+                }
+            }
+            const size_t o = (size_t)y * G + x;
+            if (jb.a00b) jb.a00b[o] = ab;
+            if (jb.bounded) {
+                jb.maps[o] = a00;
+                jb.maps[gg + o] = a10;
+                jb.maps[2 * gg + o] = a01;
+                jb.maps[3 * gg + o] = a20;
+                jb.maps[4 * gg + o] = a02;
+                jb.maps[5 * gg + o] = a11;
+            }
+        }
+    }
+}
+
+// boundary correction (mcsamples.py:1927-1959); running max of the corrected density -> mx[1]
+__global__ void __launch_bounds__(256) k_boundary2d(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    const int G = jb.G;
+    const size_t gg = (size_t)G * G;
+    const double mx0 = __longlong_as_double((long long)jb.mx[0]);
+    double tmax = 0;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < gg; o += (size_t)gridDim.x * blockDim.x) {
+        double p = jb.P[o];
+        if (jb.bounded) {
+            const double a00 = jb.maps[o];
+            if (a00 * p > mx0 * 1e-8) {
+                const double normed = p / a00;
+                if (jb.bco == 0) {
+                    p = normed;
+                } else {
+                    const double a10 = jb.maps[gg + o], a01 = jb.maps[2 * gg + o], a20 = jb.maps[3 * gg + o];
+                    const double a02 = jb.maps[4 * gg + o], a11 = jb.maps[5 * gg + o];
+                    const double xP = jb.xP[o], yP = jb.yP[o];
+                    const double denom = a20 * a01 * a01 + a10 * a10 * a02 - a00 * a02 * a20 + a11 * a11 * a00 - 2 * a01 * a10 * a11;
+                    const double A = a11 * a11 - a02 * a20;
+                    const double Ax = a10 * a02 - a01 * a11;
+                    const double Ay = a01 * a20 - a10 * a11;
+                    const double corrected = (p * A + xP * Ax + yP * Ay) / denom;
+                    p = normed * exp(fmin(corrected / normed, 4.0) - 1);
+                }
+                jb.P[o] = p;
+            }
+        }
+        tmax = fmax(tmax, p);
+    }
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + 1, tmax);
+}
+
+// normalize('max') into the output; status ZERO_MAX if the maximum is 0
+__global__ void __launch_bounds__(256) k_finalize2d(const ConvJob* __restrict__ jobs, double* __restrict__ out,
+                                                    const long long* __restrict__ offs, gdk_result2d* __restrict__ res) {
+    const ConvJob jb = jobs[blockIdx.y];
+    const int G = jb.G;
+    const size_t gg = (size_t)G * G;
+    // final density buffer and its max slot: after mbc bias iterations
+    const int it = jb.mbc;
+    const double* P = (it & 1) ? jb.Pn : jb.P;
+    const int slot = 1 + it;
+    const double mx = __longlong_as_double((long long)jb.mx[slot]);
+    double* o = out + offs[blockIdx.y];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < gg; i += (size_t)gridDim.x * blockDim.x)
+        o[i] = (mx != 0) ? P[i] / mx : P[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !(mx != 0)) res[blockIdx.y].status |= GDK_ST_ZERO_MAX;
+}

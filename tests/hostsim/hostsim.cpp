@@ -9,6 +9,7 @@
 
 #include "../../getdist_b200/csrc/host_tables.h"
 #include "../../getdist_b200/csrc/kde1d_core.cuh"
+#include "../../getdist_b200/csrc/kde2d_core.cuh"
 
 extern "C" {
 
@@ -109,6 +110,59 @@ int hs_kde1d(const gdk_spec1d* sp, const double* bins, double* P_out, gdk_result
         W.cos4 = c4.data();
     }
     kde1d_core(co, *sp, K, W, P_out, res);
+    return 0;
+}
+
+// squared 2D DCT-II and |FFT2|^2 of hist/sum(hist), G x G, with the same line transforms the kernels use
+int hs_xform2d(const double* hist, int G, double* a2, double* aFFT) {
+    CoopHost co;
+    const size_t n2 = (size_t)G * G;
+    double total = 0;
+    for (size_t i = 0; i < n2; i++) total += hist[i];
+    std::vector<double> p(n2), t1(n2), t2(n2);
+    for (size_t i = 0; i < n2; i++) p[i] = hist[i] / total;
+    std::vector<cplx> a(n2), b(n2), tw(G), tw4(G), c1(n2), c2(n2);
+    std::vector<double> c4(4 * (size_t)G);
+    gdk_fill_roots(tw.data(), G, G);
+    gdk_fill_roots(tw4.data(), 4 * G, G);
+    gdk_fill_cos(c4.data(), 4 * G);
+    const bool p2 = is_pow2(G);
+    // dct2d = dct along axis 0 then axis 1 (convolve.py:565-566); the two commute up to rounding
+    if (p2) dct2_lines_pow2(co, p.data(), t1.data(), a.data(), b.data(), G, G, tw.data(), tw4.data());
+    else dct2_lines_direct(co, p.data(), t1.data(), G, G, c4.data());
+    for (int y = 0; y < G; y++) for (int x = 0; x < G; x++) t2[(size_t)x * G + y] = t1[(size_t)y * G + x];
+    if (p2) dct2_lines_pow2(co, t2.data(), t1.data(), a.data(), b.data(), G, G, tw.data(), tw4.data());
+    else dct2_lines_direct(co, t2.data(), t1.data(), G, G, c4.data());
+    for (int y = 0; y < G; y++) for (int x = 0; x < G; x++) { double v = t1[(size_t)x * G + y]; a2[(size_t)y * G + x] = v * v; }
+    // fft2
+    for (size_t i = 0; i < n2; i++) a[i] = cplx{p[i], 0};
+    cplx* r;
+    if (p2) r = fft_lines(co, a.data(), b.data(), G, G, tw.data());
+    else { dft_lines_direct(co, a.data(), b.data(), G, G, tw.data()); r = b.data(); }
+    for (int y = 0; y < G; y++) for (int x = 0; x < G; x++) c1[(size_t)x * G + y] = r[(size_t)y * G + x];
+    if (p2) r = fft_lines(co, c1.data(), c2.data(), G, G, tw.data());
+    else { dft_lines_direct(co, c1.data(), c2.data(), G, G, tw.data()); r = c2.data(); }
+    for (int y = 0; y < G; y++) for (int x = 0; x < G; x++) { cplx v = r[(size_t)x * G + y]; aFFT[(size_t)y * G + x] = v.x * v.x + v.y * v.y; }
+    return 0;
+}
+
+// KernelOptimizer2D(...).get_h() on precomputed a2 / aFFT
+int hs_bw2d(const double* a2, const double* aFFT, int G, double N, double corr, int do_corr, int have_ft, double ft,
+            double* out /*hx, hy, c, t_star*/, int* iout /*status, n_brent, failed*/) {
+    CoopHost co;
+    Kde2dConsts K;
+    gdk_fill_kde2d_consts(&K);
+    std::vector<double> wx((size_t)PSI_MAXE * G), wy((size_t)PSI_MAXE * G);
+    Kde2dWork W{a2, do_corr ? aFFT : nullptr, G, wx.data(), wy.data()};
+    Bw2dOut o = kernel_optimizer_2d(co, K, W, N, corr, do_corr, have_ft, ft);
+    out[0] = o.hx; out[1] = o.hy; out[2] = o.c; out[3] = o.t_star;
+    iout[0] = (int)o.status; iout[1] = o.n_brent; iout[2] = o.failed;
+    return 0;
+}
+
+int hs_finish_bw2d(const gdk_spec2d* sp, const double* optv /*hx,hy,c,t_star*/, const int* opti, double r2, gdk_result2d* res) {
+    Bw2dOut o{optv[0], optv[1], optv[2], optv[3], (uint32_t)opti[0], opti[1], opti[2]};
+    finish_bandwidth_2d(*sp, &o, r2, res);
     return 0;
 }
 }

@@ -1,0 +1,112 @@
+"""GPU parity tests for the 2D path (through the C-ABI / MCSamples mirror): 2D histograms, sheared re-binning +
+bandwidths, and the final 2D densities against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+
+from cases import CASES, grid_stride, kw_tag
+from helpers import load_case, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+ALL = list(CASES)
+AMISE_BITS = 64 | 128  # GDK_ST_AMISE_CORR | GDK_ST_AMISE_FULL
+
+
+def make_gpu(case):
+    from getdist_b200 import MCSamples
+
+    return MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"],
+                     sampler="uncorrelated", settings=case["settings"] or None)
+
+
+@pytest.fixture(scope="module")
+def gpu_objs():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            case, g = load_case(name)
+            cache[name] = (case, g, make_gpu(case))
+        return cache[name]
+
+    return get
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_hist2d_matches_bincount(gpu_objs, name):
+    from oracle.getdist_oracle import bin_indices
+
+    case, g, mc = gpu_objs(name)
+    o = make_oracle(case)
+    pairs = case["pairs"]
+    mc._ensure_param_ranges([p for pr in pairs for p in pr])
+    specs = [mc._spec_2d(j, j2, {}) for (j, j2) in pairs]
+    buf, offs = mc._ctx.hist2d_batch(specs)
+    for sp, off in zip(specs, offs):
+        G = sp.fine_bins
+        fwx = (sp.xbinmax - sp.xbinmin) / (G - 1)
+        fwy = (sp.ybinmax - sp.ybinmin) / (G - 1)
+        ix = bin_indices(o.samples[:, sp.px], sp.xbinmin, fwx)
+        iy = bin_indices(o.samples[:, sp.py], sp.ybinmin, fwy)
+        ref = np.bincount(ix + iy * G, weights=o.weights, minlength=G * G)
+        got = buf[off: off + G * G]
+        assert np.all((ref == 0) == (got == 0))
+        assert np.max(np.abs(got - ref)) <= 1e-11 * np.max(ref)
+        np.testing.assert_allclose(got.sum(), o.weights.sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_density_2d(gpu_objs, name):
+    case, g, mc = gpu_objs(name)
+    worst = 0
+    for kw in case["kwargs_2d"]:
+        tag = kw_tag(kw)
+        for (jx, jy) in case["pairs"]:
+            d = mc.get2DDensity(jx, jy, **kw)
+            xy = g["d2/%s/%d_%d/xy" % (tag, jx, jy)]
+            assert d.x.size == int(xy[2]) and d.y.size == int(xy[5])
+            np.testing.assert_allclose([d.x[0], d.x[-1], d.y[0], d.y[-1]], xy[[0, 1, 3, 4]], rtol=1e-12)
+            st = grid_stride(d.P.shape[0])
+            ref = g["d2/%s/%d_%d/P" % (tag, jx, jy)]
+            err = np.max(np.abs(d.P[::st, ::st] - ref))
+            h = g["d2/%s/%d_%d/h" % (tag, jx, jy)]
+            info = d._gdk
+            amise = bool(info["status"] & AMISE_BITS)
+            if not np.isnan(h[0]):
+                # bandwidths handed back by getAutoBandwidth2D: SURVEY s8c staged tolerance 5e-5, except where the
+                # reference's TNC step decided the value (chaotic at ~1e-4, DESIGN.md "TNC")
+                rtol = 3e-4 if amise else 5e-5
+                np.testing.assert_allclose([info["hx"], info["hy"]], h[:2], rtol=rtol, err_msg=str((name, tag, jx, jy)))
+                np.testing.assert_allclose(info["c"], h[2], rtol=rtol, atol=1e-12)
+            tol = 1e-5 if amise else 1e-6
+            assert err < tol, (name, tag, jx, jy, err, info)
+            worst = max(worst, err)
+    print(name, "worst 2D |dP|", worst)
+
+
+def test_prefetch_triangle_matches_single_calls(gpu_objs):
+    case, g, mc = gpu_objs("bounded")
+    names = case["names"]
+    d1, d2 = mc.prefetch_triangle(names)
+    k = 0
+    for i in range(len(names)):
+        assert mc.get1DDensity(names[i]) is d1[i]
+        for j in range(i + 1, len(names)):
+            single = mc._densities_2d([(i, j)], fine_bins_2D=256)[0]  # kwargs -> not cached, separate launch
+            assert np.max(np.abs(single.P - d2[k].P)) < 1e-12
+            got = mc.get2DDensity(names[i], names[j])  # served from the prefetch cache
+            assert np.array_equal(got.P, d2[k].P)
+            k += 1
+    # get2DDensityGridData adds contour levels (densities.py:19-56)
+    dd = mc.get2DDensityGridData(names[0], names[1])
+    assert dd.contours is not None and len(dd.contours) == 3 and np.all(np.diff(dd.contours) < 0)
+    assert mc.get2DDensity("nope", names[0]) is None
+
+
+def test_repeatable(gpu_objs):
+    """integer accumulation of fixed-point weights: histograms and densities are bit-reproducible"""
+    case, g, mc = gpu_objs("mix3")
+    a = mc._densities_2d([(0, 1), (1, 2)], fine_bins_2D=256)
+    b = mc._densities_2d([(0, 1), (1, 2)], fine_bins_2D=256)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.P, y.P)
