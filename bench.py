@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: 1D+2D densities/sec for the full triangle of N=1e7 weighted samples x P=64
+parameters (BASELINE.json configs[1], "C2": correlated Gaussian, fine_bins=2048 / 256^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N --p P (debug sizes)]
+
+A "step" is one pass of the hot path over the resident sample store: exact weighted quantiles for all P
+parameters, P 1D densities and P(P-1)/2 2D densities (histograms, bandwidths, convolutions, corrections,
+normalisation).  Means/covariance are computed at upload (as the reference does at construction) and are part of
+the end-to-end figure only.
+
+  value : densities/s, samples resident in HBM, results left on the device; CUDA events on the library stream.
+  e2e   : densities/s through the public API (MCSamples(samples=...) + prefetch_triangle()) from PINNED HOST
+          buffers: H2D upload, moments, quantiles, densities, D2H of every grid inside the timed region.
+  roofline    : the dominant kernel by CUDA-event time (2D histogram pass), algorithmic bytes N*24 B per pair
+                 over its event duration, against MEASURED_PEAKS.json hbm_gbs.
+  hist1d      : the north-star "histogram-pass HBM GB/s": N*(P+1)*8 B over the 1D sweep's event duration.
+  cpu_baseline: the oracle (numpy/scipy restatement of the reference, pinned to it by goldens) timed on the host
+                on a bounded sample of the same workload; also used as a parity check of the GPU result.
+
+--impl reference times that same CPU path alone (rank 0 only) and prints the reference-arm line.
+Multi-GPU (torchrun): every rank holds the full sample store, the list of densities is partitioned across ranks,
+result grids are all-gathered with NCCL (torch.distributed); total work is fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "1D+2D densities/sec (full triangle, N=1e7 x P=64, fine_bins=2048 / 256^2)"
+UNIT = "densities/s"
+SETTINGS = {"fine_bins": 2048, "fine_bins_2D": 256}
+CPU_SAMPLE_PARAMS = [0, 1, 2, 40]  # oracle subset: 1D of 0,1 ; 2D of (0,1) shear and (2,40) plain
+
+
+def gen_c2(N, P, out_X=None, out_w=None, rho=0.85, seed=1234):
+    """AR(1) correlated Gaussian, scales 10^U(-4,2), offsets sigma*U(-150,150), Exp(1) weights."""
+    rng = np.random.default_rng(seed)
+    R = rho ** np.abs(np.subtract.outer(np.arange(P), np.arange(P)))
+    L = np.linalg.cholesky(R)
+    sig = 10.0 ** rng.uniform(-4, 2, P)
+    mu = sig * rng.uniform(-150, 150, P)
+    X = np.empty((N, P)) if out_X is None else out_X
+    chunk = 1 << 19
+    for r0 in range(0, N, chunk):
+        r1 = min(N, r0 + chunk)
+        Z = rng.standard_normal((r1 - r0, P))
+        np.multiply(Z.dot(L.T), sig, out=X[r0:r1])
+        X[r0:r1] += mu
+    w = np.empty(N) if out_w is None else out_w
+    w[:] = np.random.default_rng(seed + 1).exponential(1.0, N)
+    return X, w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(X, w, steps=1):
+    """Oracle on a bounded sample of the workload: columns CPU_SAMPLE_PARAMS at full N; per step two 1D and two 2D
+    densities.  Returns (densities/s, seconds, results for the parity check)."""
+    from oracle.getdist_oracle import OracleSamples
+
+    cols = CPU_SAMPLE_PARAMS
+    orc = OracleSamples(np.ascontiguousarray(X[:, cols]), w, names=["p%d" % c for c in cols], sampler="uncorrelated",
+                        settings=SETTINGS)
+    results = {}
+    t0 = time.perf_counter()
+    nd = 0
+    for _ in range(steps):
+        results[("1d", cols[0])] = orc.density_1d(0)
+        results[("1d", cols[1])] = orc.density_1d(1)
+        results[("2d", cols[0], cols[1])] = orc.density_2d(0, 1)
+        results[("2d", cols[2], cols[3])] = orc.density_2d(2, 3)
+        nd += 4
+    dt = time.perf_counter() - t0
+    return nd / dt, dt, results
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, P = args.n, args.p
+    X, w = gen_c2(N, P)
+    from oracle.getdist_oracle import OracleSamples
+
+    cols = CPU_SAMPLE_PARAMS if P > max(CPU_SAMPLE_PARAMS) else list(range(min(P, 4)))
+    orc = OracleSamples(np.ascontiguousarray(X[:, cols]), w, names=["p%d" % c for c in cols], sampler="uncorrelated",
+                        settings=SETTINGS)
+
+    def step():
+        orc.density_1d(0)
+        orc.density_2d(0, 1)
+        return 2
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    nd = 0
+    for _ in range(args.steps):
+        nd += step()
+    dt = time.perf_counter() - t0
+    val = nd / dt
+    sample = "per step: 1 x get1DDensity + 1 x get2DDensity (shear branch) at full N=%d, fine_bins 2048/256^2" % N
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 correlated Gaussian N=%d P=%d full triangle (bounded CPU sample per step)" % (N, P)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    dev = local if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    from getdist_b200 import MCSamples, _abi
+
+    N, P = args.n, args.p
+    # pinned host inputs (e2e path copies from here every step)
+    X, xh = _abi.pinned_empty((N, P))
+    w, wh = _abi.pinned_empty((N,))
+    t0 = time.perf_counter()
+    gen_c2(N, P, X, w)
+    t_gen = time.perf_counter() - t0
+    names = ["p%d" % i for i in range(P)]
+
+    mc = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
+    idx, pairs = mc.triangle_pairs()
+    my1d = idx[rank::world]
+    # contiguous blocks of pairs keep the 8x8 histogram tiles dense
+    per = (len(pairs) + world - 1) // world
+    my2d = pairs[rank * per: (rank + 1) * per]
+    F, G = SETTINGS["fine_bins"], SETTINGS["fine_bins_2D"]
+    max1d = (len(idx) + world - 1) // world
+    d1 = torch.zeros((max1d, F), dtype=torch.float64, device="cuda")
+    d2 = torch.zeros((per, G * G), dtype=torch.float64, device="cuda")
+    g1 = torch.empty((world * max1d, F), dtype=torch.float64, device="cuda") if world > 1 else None
+    g2 = torch.empty((world * per, G * G), dtype=torch.float64, device="cuda") if world > 1 else None
+    ndens_total = len(idx) + len(pairs)
+
+    phases = {}
+
+    def step_resident():
+        mc.invalidate_density_caches()
+        mc._ctx.timer_start()
+        if my1d:
+            mc._densities_1d(my1d, _device_ptr=d1.data_ptr())
+            ph = mc._ctx.phase_ms()
+            phases["hist1d"], phases["kde1d"], phases["quantiles"] = ph["hist1d"], ph["kde1d"], ph["quantiles"]
+        if my2d:
+            # every 2D grid of the C2 workload is G x G; a scaled-up grid would not fit the packed tensor
+            specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr())
+            assert all(s.fine_bins == G for s in specs)
+            ph = mc._ctx.phase_ms()
+            for k in ("hist2d", "shear", "xform2d", "bw2d", "conv2d"):
+                phases[k] = ph[k]
+            if "quantiles" not in phases:
+                phases["quantiles"] = ph["quantiles"]
+        ms = mc._ctx.timer_stop_ms()
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(g1, d1)
+            dist.all_gather_into_tensor(g2, d2)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    l0 = mc._ctx.launch_count()
+    clocks = ClockSampler(dev)
+    if rank == 0:
+        clocks.start()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        total_ms += step_resident()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = mc._ctx.launch_count() - l0
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = ndens_total / (ms_per_step * 1e-3)
+
+    # ---------------- end to end through the public API, pinned host -> host results ----------------
+    out1, o1h = _abi.pinned_empty((len(my1d) or 1, F))
+    out2, o2h = _abi.pinned_empty((max(len(my2d), 1) * G * G,))
+    e2e_steps = max(1, min(args.steps, 3))
+    checksum = 0.0
+
+    def step_e2e():
+        m = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
+        a = m._densities_1d(my1d, _out=out1) if my1d else []
+        b = m._densities_2d(my2d, _out=out2) if my2d else []
+        s = float(out1[0, F // 2]) + float(out2[G * G // 2])
+        m._ctx.close()
+        return s, len(a) + len(b)
+
+    del mc  # free the resident copy before timing fresh uploads
+    import gc
+
+    gc.collect()
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        step_e2e()  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            s, _nd = step_e2e()
+            checksum += s
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_val = ndens_total / e2e_s
+    h2d = N * P * 8 + N * 8
+    d2h = (len(my1d) * F + len(my2d) * G * G) * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel + the 1D histogram sweep ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(("hist2d", "conv2d", "xform2d", "bw2d", "shear", "hist1d", "kde1d", "quantiles"),
+              key=lambda k: phases.get(k, 0) or 0)
+    algo_bytes = {"hist2d": N * 24.0 * len(my2d), "hist1d": N * (len(my1d) + 1) * 8.0}
+    roof = None
+    if phases.get("hist2d", 0) > 0:
+        ach = algo_bytes["hist2d"] / (phases["hist2d"] * 1e-3) / 1e9
+        roof = {"kernel": "k_hist2d_tiles", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "algorithmic_bytes": algo_bytes["hist2d"], "kernel_ms": phases["hist2d"],
+                "peak_source": peak_src, "dominant_phase_by_time": dom,
+                "note": "algorithmic bytes = N*24 B per pair (standalone per-pair sweep, SURVEY s8d); the tiled kernel "
+                        "reads far less from DRAM and is bound by L2 atomic throughput: updates/s = %.3e"
+                        % (N * len(my2d) / (phases["hist2d"] * 1e-3))}
+    hist1d = None
+    if phases.get("hist1d", 0) > 0:
+        a1 = algo_bytes["hist1d"] / (phases["hist1d"] * 1e-3) / 1e9
+        hist1d = {"kernel": "k_hist1d", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak,
+                  "algorithmic_bytes": algo_bytes["hist1d"], "kernel_ms": phases["hist1d"]}
+
+    # ---------------- CPU baseline on a bounded sample + parity check against it ----------------
+    cpu = None
+    parity = None
+    if not args.no_cpu and P > max(CPU_SAMPLE_PARAMS):
+        mc2 = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
+        cols = CPU_SAMPLE_PARAMS
+        g_1d = mc2._densities_1d(cols[:2])
+        g_2d = mc2._densities_2d([(cols[0], cols[1]), (cols[2], cols[3])])
+        val, dt, results = cpu_sample(X, w)
+        e1 = max(float(np.max(np.abs(g_1d[i].P - results[("1d", cols[i])].P))) for i in range(2))
+        e2a = float(np.max(np.abs(g_2d[0].P - results[("2d", cols[0], cols[1])].P)))
+        e2b = float(np.max(np.abs(g_2d[1].P - results[("2d", cols[2], cols[3])].P)))
+        parity = {"max_abs_dP_1d": e1, "max_abs_dP_2d_shear": e2a, "max_abs_dP_2d_plain": e2b,
+                  "plain_pair_amise_accepted": bool(g_2d[1]._gdk["status"] & (64 | 128)), "tolerance": 1e-6}
+        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "oracle (numpy/scipy restatement pinned to the reference) on columns %s at full N=%d: 2 x 1D + "
+                         "2 x 2D densities in %.1f s; host has %d cores, path is single-threaded" % (cols, N, dt, os.cpu_count())}
+        mc2._ctx.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2 correlated Gaussian (AR1 rho=0.85) N=%d P=%d, Exp(1) weights, fine_bins=%d, fine_bins_2D=%d, "
+                               "full triangle: %d 1D + %d 2D densities" % (N, P, F, G, len(idx), len(pairs)),
+                   "partition": "densities split across %d rank(s); every rank holds the full sample store; NCCL all-gather of grids" % world,
+                   "l2": "inputs (%.1f GB) are larger than L2; no flush needed between steps" % ((N * P * 8 + N * 8) / 1e9),
+                   "datagen_s": t_gen},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "s_per_step": e2e_s, "checksum": checksum,
+                "path": "MCSamples(samples=pinned host) [H2D + moments] -> quantiles -> 1D + 2D batches -> pinned host grids"},
+        "gpu_launches": int(launches), "phases_ms": phases, "clocks": clk, "roofline": roof, "hist1d": hist1d,
+        "cpu_baseline": cpu, "parity_check": parity,
+    }
+    print(json.dumps(line))
+    _abi.free_pinned(xh)
+    _abi.free_pinned(wh)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--p", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

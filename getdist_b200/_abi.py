@@ -90,6 +90,10 @@ def load():
     lib.gdk_free_pinned.restype = i32
     lib.gdk_launch_count.argtypes = [vp]
     lib.gdk_launch_count.restype = i64
+    lib.gdk_timer_start.argtypes = [vp]
+    lib.gdk_timer_start.restype = i32
+    lib.gdk_timer_stop_ms.argtypes = [vp]
+    lib.gdk_timer_stop_ms.restype = dbl
     lib.gdk_phase_ms.argtypes = [vp, i32]
     lib.gdk_phase_ms.restype = dbl
     lib.gdk_set_samples.argtypes = [vp, vp, i64, i32, i64, i64, vp, vp, i32]
@@ -182,12 +186,16 @@ class Context:
                  "gdk_weighted_quantiles")
         return out
 
-    def density1d_batch(self, specs):
+    def density1d_batch(self, specs, out=None, device_ptr=None):
         n = len(specs)
         arr = (Spec1D * n)(*specs)
         stride = max(s.fine_bins for s in specs)
-        P = np.empty((n, stride))
         res = (Result1D * n)()
+        if device_ptr is not None:
+            self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), stride,
+                                                  C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density1d_batch")
+            return None, list(res)
+        P = np.empty((n, stride)) if out is None else out
         self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(P), stride, C.cast(res, C.c_void_p), 0),
                  "gdk_density1d_batch")
         return P, list(res)
@@ -228,6 +236,12 @@ class Context:
         self._ck(self.lib.gdk_hist2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets)), "gdk_hist2d_batch")
         return out, offsets
 
+    def timer_start(self):
+        self._ck(self.lib.gdk_timer_start(self.h), "gdk_timer_start")
+
+    def timer_stop_ms(self):
+        return float(self.lib.gdk_timer_stop_ms(self.h))
+
     def phase_ms(self):
         return {nm: self.lib.gdk_phase_ms(self.h, i) for i, nm in enumerate(PHASES)}
 
@@ -244,7 +258,6 @@ def pinned_empty(shape, dtype=np.float64):
         raise GdkError("pinned allocation of %d bytes failed" % n)
     buf = (C.c_char * n).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    arr._gdk_pinned = p  # noqa  (keep-alive; freed explicitly by free_pinned)
     return arr, p
 
 

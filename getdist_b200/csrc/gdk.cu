@@ -162,6 +162,23 @@ extern "C" int32_t gdk_alloc_pinned(uint64_t bytes, void** out) {
 }
 extern "C" int32_t gdk_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? GDK_OK : GDK_ERR_CUDA; }
 extern "C" int64_t gdk_launch_count(gdk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int32_t gdk_timer_start(gdk_ctx* ctx) {
+    if (!ctx) return GDK_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->tm0) {
+        cudaEventCreate(&ctx->tm0);
+        cudaEventCreate(&ctx->tm1);
+    }
+    return cudaEventRecord(ctx->tm0, ctx->stream) == cudaSuccess ? GDK_OK : GDK_ERR_CUDA;
+}
+extern "C" double gdk_timer_stop_ms(gdk_ctx* ctx) {
+    if (!ctx || !ctx->tm0) return -1.0;
+    float ms = 0;
+    if (cudaEventRecord(ctx->tm1, ctx->stream) != cudaSuccess || cudaEventSynchronize(ctx->tm1) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, ctx->tm0, ctx->tm1) != cudaSuccess)
+        return -1.0;
+    return (double)ms;
+}
 extern "C" double gdk_phase_ms(gdk_ctx* ctx, int32_t phase) {
     if (!ctx || phase < 0 || phase >= GDK_NPHASE || !ctx->phase_valid[phase]) return -1.0;
     float ms = 0;

@@ -59,7 +59,8 @@ struct Kde1dTablesHost {
 struct gdk_ctx {
     int device = 0, num_sms = 148, max_smem = 48 * 1024;
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev0[GDK_NPHASE], ev1[GDK_NPHASE];
+    cudaEvent_t ev0[GDK_NPHASE], ev1[GDK_NPHASE], tm0 = nullptr, tm1 = nullptr;
+    double phase_acc[GDK_NPHASE];
     int phase_valid[GDK_NPHASE];
     std::string err;
     int64_t launches = 0;

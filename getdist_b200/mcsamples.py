@@ -489,12 +489,14 @@ class MCSamples:
                            par.sigma_range, par.err, neff, float(smooth_scale_1D), width, int(bco), int(mbc),
                            int(par.has_limits_bot), int(par.has_limits_top))
 
-    def _densities_1d(self, indices, meanlikes=False, **kwargs):
+    def _densities_1d(self, indices, meanlikes=False, _out=None, _device_ptr=None, **kwargs):
         if meanlikes:
             raise NotImplementedError("meanlikes is not on the device path yet (SURVEY.md s8f-3)")
         self._ensure_param_ranges(indices)
         specs = [self._spec_1d(j, kwargs) for j in indices]
-        P, res = self._ctx.density1d_batch(specs)
+        P, res = self._ctx.density1d_batch(specs, out=_out, device_ptr=_device_ptr)
+        if _device_ptr is not None:
+            return specs, res  # grids stay on the device (row i at device_ptr + i * max(fine_bins))
         out = []
         for j, sp, row, r in zip(indices, specs, P, res):
             par = self.paramNames.names[j]
@@ -515,7 +517,7 @@ class MCSamples:
             if r.status & _abi.ST_ZERO_MAX:
                 raise DensitiesError("no samples in bin")
             x = np.linspace(sp.binmin, sp.binmax, sp.fine_bins)
-            d = Density1D(x, P=np.array(row[: sp.fine_bins]), view_ranges=[par.range_min, par.range_max])
+            d = Density1D(x, P=row[: sp.fine_bins], view_ranges=[par.range_min, par.range_max])
             d.likes = None
             d._gdk = dict(kde_h=r.kde_h, smooth_1D=r.smooth_1D, winw=r.winw, status=r.status, n_feval=r.n_feval)
             if not kwargs:
@@ -658,10 +660,12 @@ class MCSamples:
                 sp.ry_fixed = smooth_scale_2D * fine_bins_2D / nbin2D
         return sp
 
-    def _densities_2d(self, pairs, **kwargs):
+    def _densities_2d(self, pairs, _out=None, _device_ptr=None, **kwargs):
         self._ensure_param_ranges([p for pr in pairs for p in pr])
         specs = [self._spec_2d(j, j2, kwargs) for (j, j2) in pairs]
-        buf, offsets, res = self._ctx.density2d_batch(specs)
+        buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
+        if _device_ptr is not None:
+            return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
         out = []
         for (j, j2), sp, off, r in zip(pairs, specs, offsets, res):
             parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
@@ -679,7 +683,7 @@ class MCSamples:
             G = sp.fine_bins
             x = np.linspace(sp.xbinmin, sp.xbinmax, G)
             y = np.linspace(sp.ybinmin, sp.ybinmax, G)
-            d = Density2D(x, y, np.array(buf[off: off + G * G]).reshape(G, G),
+            d = Density2D(x, y, buf[off: off + G * G].reshape(G, G),
                           view_ranges=[(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
             d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
                           n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G)
@@ -689,6 +693,22 @@ class MCSamples:
         return out
 
     # ------------------------------------------------------------------ batched driver
+    def triangle_pairs(self, params=None):
+        idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]
+        if any(i is None for i in idx):
+            raise ParamError("unknown parameter")
+        return idx, [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))]
+
+    def invalidate_density_caches(self):
+        """Forget per-parameter ranges and cached densities (as updateBaseStatistics does) without touching the
+        resident samples or the moments: the next density call recomputes quantiles, ranges and grids."""
+        self.density1D = {}
+        self._density2D = {}
+        for par in self.paramNames.names:
+            par._ranges_ready = False
+            par.N_eff_kde = None
+        self._initLimits()
+
     def prefetch_triangle(self, params=None, do_1d=True, do_2d=True):
         """Compute every 1D and (lower-triangle) 2D density of a triangle plot in batched launches and seed
         the caches that get1DDensity / get2DDensity consult.  Pair (x, y) = (params[i], params[k]) for i < k,

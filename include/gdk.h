@@ -73,6 +73,10 @@ int32_t gdk_alloc_pinned(uint64_t bytes, void** out);
 int32_t gdk_free_pinned(void* p);
 /* number of kernel launches issued by this context since creation (bench `gpu_launches`) */
 int64_t gdk_launch_count(gdk_ctx* ctx);
+/* CUDA-event stopwatch on the library's stream: start records an event, stop records another, waits for it
+ * and returns the elapsed milliseconds (host gaps between the enclosed calls included).                   */
+int32_t gdk_timer_start(gdk_ctx* ctx);
+double gdk_timer_stop_ms(gdk_ctx* ctx);
 /* CUDA-event time (ms) of the tagged phase of the most recent batch call:
  * 0 = 1D histogram sweep, 1 = 1D grid stage, 2 = 2D histogram pass, 3 = 2D shear re-bin,
  * 4 = 2D transforms, 5 = 2D bandwidth, 6 = 2D convolution stage, 7 = moments, 8 = quantiles, 9 = upload */
