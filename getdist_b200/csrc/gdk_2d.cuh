@@ -164,8 +164,12 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (rc) return rc;
     const int ntiles = (int)tiles.size();
     {
-        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, ntiles) + 1);
-        const int64_t seglen = std::max<int64_t>(1 << 13, (ctx->N + want - 1) / want);
+        // Row segments are the FAST grid index: all CTAs resident at one time (~5 per SM) then work on one or
+        // two tiles, whose <= 64 grids (32 MB at 256^2) stay L2-resident for the reductions.  With few segments
+        // per tile the resident CTAs span many tiles and every REDG misses L2 (profiles/r1a: 437 GB of DRAM
+        // traffic for 2e10 updates).
+        const int64_t want = (int64_t)ctx->num_sms * 6;
+        const int64_t seglen = std::max<int64_t>(1 << 12, (ctx->N + want - 1) / want);
         std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
         rc = gdk_upload_segs(ctx, segs, ctx->segs);
         if (rc) return rc;
@@ -184,8 +188,50 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (nshear) {
         rc = upload_vec(ctx, sjobs, ctx->bytes2d_b, &dsj);
         if (rc) return rc;
-        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / nshear + 1);
-        const int64_t seglen = std::max<int64_t>(1 << 14, (ctx->N + want - 1) / want);
+        // groups of jobs sharing (p1 column, p1 geometry, grid size): x_i is read once per row for the group
+        std::vector<int> ord(nshear);
+        for (int i = 0; i < nshear; i++) ord[i] = i;
+        auto keyless = [&](int a, int b) {
+            const ShearJob &A = sjobs[a], &B = sjobs[b];
+            if (A.pi != B.pi) return A.pi < B.pi;
+            if (A.Gb != B.Gb) return A.Gb < B.Gb;
+            if (A.p1_min != B.p1_min) return A.p1_min < B.p1_min;
+            if (A.dx1 != B.dx1) return A.dx1 < B.dx1;
+            return A.pj < B.pj;
+        };
+        std::sort(ord.begin(), ord.end(), keyless);
+        std::vector<ShearGroup> sgroups;
+        for (int k = 0; k < nshear; k++) {
+            const ShearJob& j = sjobs[ord[k]];
+            bool fresh = sgroups.empty();
+            if (!fresh) {
+                const ShearGroup& g = sgroups.back();
+                fresh = g.nj == SG || g.pi != j.pi || g.Gb != j.Gb || g.p1_min != j.p1_min || g.dx1 != j.dx1;
+            }
+            if (fresh) {
+                ShearGroup g{};
+                g.pi = j.pi;
+                g.Gb = j.Gb;
+                g.p1_min = j.p1_min;
+                g.dx1 = j.dx1;
+                g.inv1 = j.inv1;
+                sgroups.push_back(g);
+            }
+            ShearGroup& g = sgroups.back();
+            g.pj[g.nj] = j.pj;
+            g.job[g.nj] = ord[k];
+            g.r0[g.nj] = j.r0;
+            g.r1[g.nj] = j.r1;
+            g.off[g.nj] = j.off;
+            g.nj++;
+        }
+        ShearGroup* dsg = nullptr;
+        rc = upload_vec(ctx, sgroups, ctx->bytes2d_c, &dsg);
+        if (rc) return rc;
+        const int ngroups = (int)sgroups.size();
+        // fine segments (fast grid index) keep the <= 8 grids of a group L2-resident for the reductions
+        const int64_t want = std::max<int64_t>((int64_t)ctx->num_sms * 8 / ngroups + 1, std::min<int64_t>((int64_t)ctx->num_sms * 6, 64));
+        const int64_t seglen = std::max<int64_t>(1 << 13, (ctx->N + want - 1) / want);
         std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
         rc = gdk_upload_segs(ctx, segs, ctx->segs);
         if (rc) return rc;
@@ -195,10 +241,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_SHEAR);
-        dim3 g((unsigned)nseg, (unsigned)nshear);
-        k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsj, part);
+        dim3 g((unsigned)nseg, (unsigned)ngroups);
+        k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsg, part);
         k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
-        k_shear_hist<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsj, dgeom, ctx->gbins_rot.p);
+        k_shear_hist<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
         ctx->launches += 3;
         pt.end();
         CK2(cudaGetLastError());

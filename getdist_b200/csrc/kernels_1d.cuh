@@ -57,13 +57,28 @@ __global__ void __launch_bounds__(256) k_hist1d(const double* __restrict__ dX, i
         r++;
     }
     const int64_t npair = (sg.r1 - r) >> 1;
-    for (int64_t i = threadIdx.x; i < npair; i += blockDim.x) {
-        const double2 xv = ldg_stream2(x + r + 2 * i);
-        const ulonglong2 wv = ldg_stream2_u64(dWq + r + 2 * i);
-        const int b0 = bin_index_round(xv.x, jb.binmin, jb.fine_width, jb.inv_width);
-        const int b1 = bin_index_round(xv.y, jb.binmin, jb.fine_width, jb.inv_width);
-        if (b0 >= 0 && b0 < F) smem_add_u64(hlo + b0, hhi + b0, wv.x);
-        if (b1 >= 0 && b1 < F) smem_add_u64(hlo + b1, hhi + b1, wv.y);
+    // four independent 16-byte loads of x and of w in flight per thread before any dependent work
+    for (int64_t i0 = threadIdx.x; i0 < npair; i0 += 4 * (int64_t)blockDim.x) {
+        double2 xv[4];
+        ulonglong2 wv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t i = i0 + (int64_t)k * blockDim.x;
+            if (i < npair) {
+                xv[k] = ldg_stream2(x + r + 2 * i);
+                wv[k] = ldg_stream2_u64(dWq + r + 2 * i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t i = i0 + (int64_t)k * blockDim.x;
+            if (i < npair) {
+                const int b0 = bin_index_round(xv[k].x, jb.binmin, jb.fine_width, jb.inv_width);
+                const int b1 = bin_index_round(xv[k].y, jb.binmin, jb.fine_width, jb.inv_width);
+                if (b0 >= 0 && b0 < F) smem_add_u64(hlo + b0, hhi + b0, wv[k].x);
+                if (b1 >= 0 && b1 < F) smem_add_u64(hlo + b1, hhi + b1, wv[k].y);
+            }
+        }
     }
     if (((sg.r1 - r) & 1) && threadIdx.x == 0) {
         const int b = bin_index_round(x[sg.r1 - 1], jb.binmin, jb.fine_width, jb.inv_width);

@@ -98,36 +98,69 @@ __device__ __forceinline__ double shear_p2(double xi, double xj, double r0, doub
     return __dadd_rn(__dmul_rn(r0, xi), __dmul_rn(r1, xj));  // r[0]*xi + r[1]*xj, no FMA contraction
 }
 
-// grid (nseg, nshear): partial min/max of p2 -> part[(job*nseg + seg)*2]
+// Jobs that share their p1 column are processed together: x_i is read once per row for up to SG jobs.
+#define SG 8
+struct ShearGroup {
+    int pi, nj, Gb, pad;
+    int pj[SG], job[SG];
+    double r0[SG], r1[SG];
+    double p1_min, dx1, inv1;
+    long long off[SG];
+};
+
+// grid (nseg, ngroups): partial min/max of p2 per job -> part[(job*nseg + seg)*2]
 __global__ void __launch_bounds__(256) k_shear_minmax(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
-                                                      int nseg, const ShearJob* __restrict__ jobs, double* __restrict__ part) {
-    const ShearJob jb = jobs[blockIdx.y];
-    const Seg sg = segs[blockIdx.x];
-    const double* xi = dX + (int64_t)jb.pi * ld;
-    const double* xj = dX + (int64_t)jb.pj * ld;
-    double mn = INFINITY, mx = -INFINITY;
-    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const double p2 = shear_p2(ldg_stream(xi + r), ldg_stream(xj + r), jb.r0, jb.r1);
-        mn = fmin(mn, p2);
-        mx = fmax(mx, p2);
-    }
-    __shared__ double sh[2][8];
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) {
-        sh[0][threadIdx.x >> 5] = mn;
-        sh[1][threadIdx.x >> 5] = mx;
+                                                      int nseg, const ShearGroup* __restrict__ groups, double* __restrict__ part) {
+    __shared__ ShearGroup g;
+    __shared__ double sh[2][SG][8];
+    {
+        const int* src = reinterpret_cast<const int*>(groups + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShearGroup) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; i++) {
-            mn = fmin(mn, sh[0][i]);
-            mx = fmax(mx, sh[1][i]);
+    const Seg sg = segs[blockIdx.x];
+    const double* xi = dX + (int64_t)g.pi * ld;
+    const int nj = g.nj;
+    double mn[SG], mx[SG];
+#pragma unroll
+    for (int k = 0; k < SG; k++) {
+        mn[k] = INFINITY;
+        mx[k] = -INFINITY;
+    }
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const double a = ldg_stream(xi + r);
+        double b[SG];
+#pragma unroll
+        for (int k = 0; k < SG; k++)
+            if (k < nj) b[k] = ldg_stream(dX + (int64_t)g.pj[k] * ld + r);
+#pragma unroll
+        for (int k = 0; k < SG; k++)
+            if (k < nj) {
+                const double p2 = shear_p2(a, b[k], g.r0[k], g.r1[k]);
+                mn[k] = fmin(mn[k], p2);
+                mx[k] = fmax(mx[k], p2);
+            }
+    }
+    const int wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < SG; k++) {
+        const double a = warp_min(mn[k]), b = warp_max(mx[k]);
+        if ((threadIdx.x & 31) == 0) {
+            sh[0][k][wid] = a;
+            sh[1][k][wid] = b;
         }
-        mn = fmin(mn, sh[0][0]);
-        mx = fmax(mx, sh[1][0]);
-        part[((int64_t)blockIdx.y * nseg + blockIdx.x) * 2 + 0] = mn;
-        part[((int64_t)blockIdx.y * nseg + blockIdx.x) * 2 + 1] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x < nj) {
+        const int k = threadIdx.x;
+        double a = sh[0][k][0], b = sh[1][k][0];
+        for (int i = 1; i < 8; i++) {
+            a = fmin(a, sh[0][k][i]);
+            b = fmax(b, sh[1][k][i]);
+        }
+        part[((int64_t)g.job[k] * nseg + blockIdx.x) * 2 + 0] = a;
+        part[((int64_t)g.job[k] * nseg + blockIdx.x) * 2 + 1] = b;
     }
 }
 
@@ -149,23 +182,39 @@ __global__ void k_shear_geom(const double* __restrict__ part, int nseg, int njob
     geom[j] = ShearGeom{rmin, dx, 1.0 / dx, R};
 }
 
-// grid (nseg, nshear)
+// grid (nseg, ngroups)
 __global__ void __launch_bounds__(256) k_shear_hist(const double* __restrict__ dX, int64_t ld,
                                                     const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
-                                                    const ShearJob* __restrict__ jobs, const ShearGeom* __restrict__ geom,
+                                                    const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
                                                     unsigned long long* __restrict__ grids) {
-    const ShearJob jb = jobs[blockIdx.y];
-    const ShearGeom gm = geom[blockIdx.y];
+    __shared__ ShearGroup g;
+    __shared__ ShearGeom gm[SG];
+    {
+        const int* src = reinterpret_cast<const int*>(groups + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&g);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShearGroup) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < g.nj) gm[threadIdx.x] = geom[g.job[threadIdx.x]];
+    __syncthreads();
     const Seg sg = segs[blockIdx.x];
-    const double* xi = dX + (int64_t)jb.pi * ld;
-    const double* xj = dX + (int64_t)jb.pj * ld;
-    const int G = jb.Gb;
+    const double* xi = dX + (int64_t)g.pi * ld;
+    const int G = g.Gb, nj = g.nj;
     for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const double a = ldg_stream(xi + r), b = ldg_stream(xj + r);
-        const int b1 = bin_index_trunc(a, jb.p1_min, jb.dx1, jb.inv1);
-        const int b2 = bin_index_trunc(shear_p2(a, b, jb.r0, jb.r1), gm.rmin, gm.dx, gm.inv);
+        const double a = ldg_stream(xi + r);
         const unsigned long long w = dWq[r];
-        if (w && b1 >= 0 && b1 < G && b2 >= 0 && b2 < G) atomicAdd(grids + jb.off + (long long)b2 * G + b1, w);
+        double b[SG];
+#pragma unroll
+        for (int k = 0; k < SG; k++)
+            if (k < nj) b[k] = ldg_stream(dX + (int64_t)g.pj[k] * ld + r);
+        const int b1 = bin_index_trunc(a, g.p1_min, g.dx1, g.inv1);
+        if (w == 0 || b1 < 0 || b1 >= G) continue;
+#pragma unroll
+        for (int k = 0; k < SG; k++)
+            if (k < nj) {
+                const int b2 = bin_index_trunc(shear_p2(a, b[k], g.r0[k], g.r1[k]), gm[k].rmin, gm[k].dx, gm[k].inv);
+                if (b2 >= 0 && b2 < G) atomicAdd(grids + g.off[k] + (long long)b2 * G + b1, w);
+            }
     }
 }
 

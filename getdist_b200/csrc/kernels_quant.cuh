@@ -115,13 +115,28 @@ __global__ void __launch_bounds__(256) k_qhist(const double* __restrict__ dX, in
     __syncthreads();
     const int na = n_act;
     if (na == 0) return;
-    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const unsigned long long key = f64_to_key(ldg_stream(x + r));
-        for (int t = 0; t < na; t++) {
-            const unsigned long long d = key - s_lo[t];
-            if (d <= s_w[t]) {
-                const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
-                smem_add_u64(hlo + bin, hhi + bin, dWq[r]);
+    for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
+        unsigned long long key[4], wq[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            key[k] = 0;
+            wq[k] = 0;
+            if (r < sg.r1) {
+                key[k] = f64_to_key(ldg_stream(x + r));
+                if (shared_first) wq[k] = dWq[r];  // first pass: every sample lands in the histogram
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            if (r >= sg.r1) continue;
+            for (int t = 0; t < na; t++) {
+                const unsigned long long d = key[k] - s_lo[t];
+                if (d <= s_w[t]) {
+                    const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
+                    smem_add_u64(hlo + bin, hhi + bin, shared_first ? wq[k] : dWq[r]);
+                }
             }
         }
     }
@@ -230,13 +245,23 @@ __global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, 
     __syncthreads();
     const int na = n_act;
     if (na == 0) return;
-    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const unsigned long long key = f64_to_key(ldg_stream(x + r));
-        for (int t = 0; t < na; t++) {
-            if (key - s_lo[t] <= s_w[t]) {
-                const int gs = p * QMAXF + s_slot[t];
-                const int idx = atomicAdd(&slots[gs].ncand, 1);
-                if (idx < QCAP) cand[(int64_t)gs * QCAP + idx] = QCand{key, dWq[r]};
+    for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
+        unsigned long long key[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            key[k] = (r < sg.r1) ? f64_to_key(ldg_stream(x + r)) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            if (r >= sg.r1) continue;
+            for (int t = 0; t < na; t++) {
+                if (key[k] - s_lo[t] <= s_w[t]) {
+                    const int gs = p * QMAXF + s_slot[t];
+                    const int idx = atomicAdd(&slots[gs].ncand, 1);
+                    if (idx < QCAP) cand[(int64_t)gs * QCAP + idx] = QCand{key[k], dWq[r]};
+                }
             }
         }
     }
