@@ -197,13 +197,11 @@ def run_ours(args):
     names = ["p%d" % i for i in range(P)]
 
     mc = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
+    from getdist_b200.parallel import partition_triangle
+
     idx, pairs = mc.triangle_pairs()
-    my1d = idx[rank::world]
-    # contiguous blocks of pairs keep the 8x8 histogram tiles dense
-    per = (len(pairs) + world - 1) // world
-    my2d = pairs[rank * per: (rank + 1) * per]
+    my1d, my2d, max1d, per = partition_triangle(idx, pairs, rank, world)
     F, G = SETTINGS["fine_bins"], SETTINGS["fine_bins_2D"]
-    max1d = (len(idx) + world - 1) // world
     d1 = torch.zeros((max1d, F), dtype=torch.float64, device="cuda")
     d2 = torch.zeros((per, G * G), dtype=torch.float64, device="cuda")
     g1 = torch.empty((world * max1d, F), dtype=torch.float64, device="cuda") if world > 1 else None

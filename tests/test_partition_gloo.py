@@ -1,0 +1,73 @@
+"""N>1 host logic on CPU: a world_size-2 gloo group runs the density partition + all-gather with a stand-in
+compute step and checks that every rank ends up with every density exactly once, in the caller's order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from getdist_b200.parallel import all_gather_grids, gather_order, partition_triangle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_density_1d(j, F):
+    return torch.full((F,), float(j) + 0.5, dtype=torch.float64)
+
+
+def _fake_density_2d(pr, G2):
+    return torch.full((G2,), 1000.0 * pr[0] + pr[1], dtype=torch.float64)
+
+
+def _worker(rank, world, port, P, F, G2, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = list(range(P))
+    pairs = [(idx[i], idx[k]) for i in range(P) for k in range(i + 1, P)]
+    my1d, my2d, max1d, per = partition_triangle(idx, pairs, rank, world)
+    d1 = torch.zeros((max1d, F), dtype=torch.float64)
+    d2 = torch.zeros((per, G2), dtype=torch.float64)
+    for k, j in enumerate(my1d):
+        d1[k] = _fake_density_1d(j, F)
+    for k, pr in enumerate(my2d):
+        d2[k] = _fake_density_2d(pr, G2)
+    g1 = all_gather_grids(d1, world, dist)
+    g2 = all_gather_grids(d2, world, dist)
+    o1, o2 = gather_order(idx, pairs, world)
+    ok = all(torch.equal(g1[o1[i]], _fake_density_1d(j, F)) for i, j in enumerate(idx))
+    ok = ok and all(torch.equal(g2[o2[i]], _fake_density_2d(pr, G2)) for i, pr in enumerate(pairs))
+    ret[rank] = bool(ok) and len(set(o1)) == len(idx) and len(set(o2)) == len(pairs)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [5, 8])
+def test_partition_and_allgather_world2(P):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), P, 16, 9, ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_partition_covers_everything_once():
+    for world in (1, 2, 3, 4, 8):
+        for P in (1, 2, 7, 64):
+            idx = list(range(P))
+            pairs = [(i, k) for i in range(P) for k in range(i + 1, P)]
+            seen1, seen2 = [], []
+            for r in range(world):
+                a, b, m1, per = partition_triangle(idx, pairs, r, world)
+                assert len(a) <= m1 and len(b) <= per
+                seen1 += a
+                seen2 += b
+            assert sorted(seen1) == idx and sorted(seen2) == sorted(pairs)
