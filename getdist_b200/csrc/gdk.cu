@@ -450,9 +450,11 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     const int B1_LOG2 = 13, B2_LOG2 = 10;
     const int B1 = 1 << B1_LOG2, B2 = 1 << B2_LOG2;
     std::vector<QSlot> slots((size_t)np * QMAXF);
+    std::vector<QBase> qbase(np);
     memset(slots.data(), 0, slots.size() * sizeof(QSlot));
     for (int i = 0; i < np; i++) {
         const unsigned long long klo = f64_to_key(ctx->xmin[params[i]]), khi = f64_to_key(ctx->xmax[params[i]]);
+        qbase[i] = QBase{klo, q_shift_for(khi - klo, B1_LOG2), B1};
         for (int s = 0; s < QMAXF; s++) {
             QSlot& q = slots[(size_t)i * QMAXF + s];
             q.klo = klo;
@@ -485,6 +487,9 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     if (ctx->qhist.ensure((size_t)np * QMAXF * std::max(B1, B2))) return gdk_fail(ctx, GDK_ERR_NOMEM, "quantile histograms");
     CK(cudaMemcpyAsync(ctx->qslots.p, slots.data(), nslots * sizeof(QSlot), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->qparams.p, params, np * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->qbase.ensure((size_t)np * sizeof(QBase))) return gdk_fail(ctx, GDK_ERR_NOMEM, "quantile buffers");
+    QBase* dqbase = reinterpret_cast<QBase*>(ctx->qbase.p);
+    CK(cudaMemcpyAsync(dqbase, qbase.data(), (size_t)np * sizeof(QBase), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 6 / np);
     const int64_t seglen = std::max<int64_t>(1 << 15, (ctx->N + want - 1) / want);
     std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
@@ -493,25 +498,26 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     dim3 g((unsigned)segs.size(), (unsigned)np);
     static bool attr_set = false;
     if (!attr_set) {
-        CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QMAXF * B2 * 4));
+        CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QMAXF * B2 * 4 + B1 * 4));
         CK(cudaFuncSetAttribute(k_qselect, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QCAP * 8));
         attr_set = true;
     }
     // pass 1: shared histogram per parameter
     CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B1 * 8, ctx->stream));
     k_qhist<<<g, 256, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
-                                                 ctx->qhist.p);
+                                                 ctx->qhist.p, dqbase);
     k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B1, 1, 0, B2_LOG2, ctx->qhist.p);
     ctx->launches += 2;
     int next_state = 2;
     for (int iter = 0; iter < 12; iter++) {
         // refinement pass: one histogram of B2 bins per refining slot
         CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B2 * 8, ctx->stream));
-        k_qhist<<<g, 256, 2 * nf * B2 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf,
-                                                          B2, 0, ctx->qhist.p);
+        k_qhist<<<g, 1024, 2 * nf * B2 * 4 + B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p,
+                                                                   ctx->qslots.p, nf, B2, 0, ctx->qhist.p, dqbase);
         k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B2, 0, next_state, B2_LOG2, ctx->qhist.p);
         CK(cudaMemsetAsync(ctx->iscratch.p, 0, sizeof(int), ctx->stream));
-        k_qgather<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, ctx->qcand.p);
+        k_qgather<<<g, 256, B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, ctx->qcand.p,
+                                                   dqbase);
         k_qselect<<<(unsigned)nslots, 512, 2 * QCAP * 8, ctx->stream>>>(ctx->qslots.p, nf, ctx->qcand.p, B2_LOG2, ctx->iscratch.p);
         ctx->launches += 4;
         int nover = 0;

@@ -452,7 +452,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             b = e;
         }
     }
-    auto conv_smem = [](int wmax) { return ((size_t)(CV_TY + CV_KC - 1) * (CV_TX + 2 * wmax + 4) + (size_t)CV_KC * (2 * wmax + 5)) * 8; };
+    auto conv_smem = [](int wmax) { return ((size_t)(CV_TY + CV_KC - 1) * 8 * cv_q(wmax) + (size_t)CV_KC * cv_kp(wmax)) * 8; };
     const size_t smem_max = conv_smem(wmax_all);
     if (smem_max > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "window too large for the convolution kernel");
     CK2(cudaFuncSetAttribute(k_conv2d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
@@ -463,7 +463,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         // mask tables / maps (jobs without bias correction and without boundary correction skip internally)
         dim3 gt((unsigned)K, (unsigned)nj);
         k_mask_T<<<gt, 256, 0, ctx->stream>>>(dcj + g.b);
-        dim3 gm((unsigned)((g.Gmax + 7) / 8), (unsigned)nj);
+        dim3 gm((unsigned)((g.Gmax + 255) / 256), (unsigned)nj);
         k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
         const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
         dim3 gc((unsigned)tiles, (unsigned)nj);

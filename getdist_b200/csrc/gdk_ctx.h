@@ -94,7 +94,7 @@ struct gdk_ctx {
     DevBuf<gdk_spec1d> specs1d;
     DevBuf<gdk_result1d> res1d;
     DevBuf<Kde1dTables> tabs1d;
-    DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena;
+    DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena, qbase;
     Kde2dConsts k2d;
     DevBuf<cplx> cwork2d;
 };

@@ -55,11 +55,28 @@ GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W
     co.sync();
     double part[PSI_MAXE];
     for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
-    const int tot = (G - 1) * (G - 1);
-    for (int it = co.tid; it < tot; it += co.nt) {
-        const int y = it / (G - 1) + 1, x = it - (y - 1) * (G - 1) + 1;
-        const double v = W.a2[(size_t)y * G + x];
-        for (int k = 0; k < n; k++) part[k] += (W.wy[k * G + y] * v) * W.wx[k * G + x];
+    // rows are dealt to groups of L threads (a warp on the device); within a row the L threads stride over x with
+    // coalesced loads of a2.  The row weights wy_k[y] are uniform over the group and hoisted out of the x loop.
+    const int L = co.nt >= 32 ? 32 : co.nt;
+    const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
+    for (int y = 1 + grp; y < G; y += ngrp) {
+        double wyk[PSI_MAXE];
+        for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
+        const double* row = W.a2 + (size_t)y * G;
+        for (int x0 = 1 + lane; x0 < G; x0 += 4 * L) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j * L;
+                v[j] = x < G ? row[x] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j * L;
+                if (x < G)
+                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + x];
+            }
+        }
     }
     for (int k = 0; k < n; k++) {
         const double s = co.sum(part[k]);
@@ -83,11 +100,26 @@ GDK_HD void psi_odd_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W,
     co.sync();
     double part[PSI_MAXE];
     for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
-    const int tot = G * G;
-    for (int it = co.tid; it < tot; it += co.nt) {
-        const int y = it / G, x = it - y * G;
-        const double v = W.aFFT[it];
-        for (int k = 0; k < n; k++) part[k] += (W.wy[k * G + y] * v) * W.wx[k * G + x];
+    const int L = co.nt >= 32 ? 32 : co.nt;
+    const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
+    for (int y = grp; y < G; y += ngrp) {
+        double wyk[PSI_MAXE];
+        for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
+        const double* row = W.aFFT + (size_t)y * G;
+        for (int x0 = lane; x0 < G; x0 += 4 * L) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j * L;
+                v[j] = x < G ? row[x] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j * L;
+                if (x < G)
+                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + x];
+            }
+        }
     }
     for (int k = 0; k < n; k++) {
         const double s = co.sum(part[k]);

@@ -13,17 +13,19 @@
 // most a few ulp, so unless the value sits within 1e-9 of an integer the truncation is identical.
 __device__ __forceinline__ int bin_index_round(double x, double binmin, double fine_width, double inv) {
     const double d = __dsub_rn(x, binmin);
-    const double q = __dadd_rn(__dmul_rn(d, inv), 0.5);
-    const double fr = q - floor(q);
-    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (int)q;
+    const double q = fma(d, inv, 0.5);  // approximate quotient + 0.5; only its distance to an integer matters
+    const int i = __double2int_rd(q);
+    const double fr = q - (double)i;
+    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (q < 0 && fr != 0) ? i + 1 : i;  // astype(int) truncates toward zero
     return (int)__dadd_rn(__ddiv_rn(d, fine_width), 0.5);
 }
 // kde.bin_samples (kde_bandwidth.py:85-87): truncating ((x - range_min) / dx).astype(int)
 __device__ __forceinline__ int bin_index_trunc(double x, double rmin, double dx, double inv) {
     const double d = __dsub_rn(x, rmin);
     const double q = __dmul_rn(d, inv);
-    const double fr = q - floor(q);
-    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (int)q;
+    const int i = __double2int_rd(q);
+    const double fr = q - (double)i;
+    if (fr > 1e-9 && fr < 1.0 - 1e-9) return (q < 0 && fr != 0) ? i + 1 : i;
     return (int)__ddiv_rn(d, dx);
 }
 

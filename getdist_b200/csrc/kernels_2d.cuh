@@ -421,99 +421,106 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long* p, double 
 }
 
 #define CV_TY 16
-#define CV_TX 64
+#define CV_TX 128
+#define CV_MX 8
 #define CV_KC 8
+// geometry of the shared-memory tiles for a launch whose largest half width is wmax
+__host__ __device__ __forceinline__ int cv_kp(int wmax) { return ((2 * wmax + 1 + 7) & ~7) + 8; }  // padded kernel row
+__host__ __device__ __forceinline__ int cv_q(int wmax) {
+    int q = (CV_TX + ((2 * wmax + 1 + 7) & ~7)) / 8 + 2;
+    while ((q & 3) != 2) q++;  // q = 2 (mod 4): the interleaved fill below is then bank-conflict free
+    return q;
+}
 // Direct 'same' convolution out[y][x] = sum_{u,v} W(u,v) in[y-u][x-v], zero padded.
 // MODE 0: in = hist                      -> P (and xP, yP when bounded with order 1); running max -> mx[0]
-// MODE 1: in = box = hist / P where P > thr (thr = mx[src]*1e-8) else hist
-//                                         -> Pn = P * conv / a00b; running max -> mx[dst]
-// grid (tiles, njobs), 256 threads (16 x 16), 4 consecutive outputs per thread.
+// MODE 1: in = box = hist / P where P > thr (thr = mx[1+iter]*1e-8) else hist
+//                                         -> next P = P * conv / a00b; running max -> mx[2+iter]
+// grid (tiles, njobs), 256 threads = 16 (x) x 16 (y); every thread produces 8 consecutive outputs of one row.
+// Shared-memory input tile: row r, column c stored at r*8q + (c&7)*q + (c>>3) ("8-way column interleave"): the
+// sliding-window loads of the 16 threads of a row then hit 16 consecutive words (conflict free), and so do the
+// coalesced fills.  Kernel rows are stored reversed and zero padded to a multiple of 8 taps; the window lives
+// in 16 registers that rotate through a fully unrolled block of 8 taps (one 8-byte load per tap per thread).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs, int iter, int wmax) {
     extern __shared__ __align__(16) double csm[];
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
+    const int Kp = (K + 7) & ~7;
     const int tilesx = (G + CV_TX - 1) / CV_TX;
     const int tyi = blockIdx.x / tilesx, txi = blockIdx.x % tilesx;
     const int oy0 = tyi * CV_TY, ox0 = txi * CV_TX;
     if (oy0 >= G) return;
-    const int inw = CV_TX + 2 * wmax + 4;  // row pitch of the input tile
-    const int kp = 2 * wmax + 1 + 4;       // row pitch of the kernel chunk
+    const int q = cv_q(wmax), pitch = 8 * q, kp = cv_kp(wmax);
     double* in_s = csm;
-    double* wk_s = csm + (size_t)(CV_TY + CV_KC - 1) * inw;
+    double* wk_s = csm + (size_t)(CV_TY + CV_KC - 1) * pitch;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double* P = (MODE == 1) ? ((iter & 1) ? jb.Pn : jb.P) : nullptr;
     double* Pout = (MODE == 1) ? ((iter & 1) ? jb.P : jb.Pn) : jb.P;
     double thr = 0;
     if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
     const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
-    double acc[4] = {0, 0, 0, 0}, accx[4] = {0, 0, 0, 0}, accy[4] = {0, 0, 0, 0};
+    double acc[CV_MX], accx[CV_MX], accy[CV_MX];
+#pragma unroll
+    for (int m = 0; m < CV_MX; m++) acc[m] = accx[m] = accy[m] = 0;
+    const int ncol = CV_TX + Kp;  // columns b = ox0 - w + c, c < ncol (zero beyond the grid / beyond 2w)
     for (int k0 = 0; k0 < K; k0 += CV_KC) {
         const int kc = min(CV_KC, K - k0);
         __syncthreads();
-        // kernel chunk, columns reversed: wk_s[kk][kr] = W[k0+kk][2w - kr]
-        for (int it = threadIdx.x; it < kc * K; it += blockDim.x) {
-            const int kk = it / K, kr = it - kk * K;
-            wk_s[kk * kp + kr] = jb.Wk[(size_t)(k0 + kk) * K + (2 * w - kr)];
+        // kernel chunk, columns reversed and zero padded: wk_s[kk][kr] = W[k0+kk][2w - kr] for kr < K, else 0
+        for (int it = threadIdx.x; it < kc * kp; it += blockDim.x) {
+            const int kk = it / kp, kr = it - kk * kp;
+            wk_s[it] = (kr < K) ? jb.Wk[(size_t)(k0 + kk) * K + (2 * w - kr)] : 0.0;
         }
-        // input rows a = abase + r, r < CV_TY + kc - 1; columns b = ox0 - w + c, c < CV_TX + 2w
+        // input rows a = abase + r, r < CV_TY + kc - 1
         const int abase = oy0 - (k0 + kc - 1) + w;
-        const int nrow = CV_TY + kc - 1, ncol = CV_TX + 2 * w;
-        for (int it = threadIdx.x; it < nrow * ncol; it += blockDim.x) {
-            const int r = it / ncol, c = it - r * ncol;
+        const int nrow = CV_TY + kc - 1;
+        for (int it = threadIdx.x; it < nrow * pitch; it += blockDim.x) {
+            const int r = it / pitch, c = it - r * pitch;  // c < 8q covers every stored position
             const int a = abase + r, b = ox0 - w + c;
             double v = 0;
-            if (a >= 0 && a < G && b >= 0 && b < G) {
+            if (c < ncol + 8 && a >= 0 && a < G && b >= 0 && b < G) {
                 v = jb.hist[(size_t)a * G + b];
                 if (MODE == 1) {
                     const double p = P[(size_t)a * G + b];
                     if (p > thr) v = v / p;
                 }
             }
-            in_s[r * inw + c] = v;
+            in_s[r * pitch + (c & 7) * q + (c >> 3)] = v;
         }
         __syncthreads();
         for (int kk = 0; kk < kc; kk++) {
-            const int r = ty + (kc - 1 - kk);
-            const double* irow = in_s + r * inw + tx * 4;
+            const double* irow = in_s + (ty + (kc - 1 - kk)) * pitch + tx;
             const double* wr = wk_s + kk * kp;
             const double u = (double)(k0 + kk - w);
-            double c0 = irow[0], c1 = irow[1], c2 = irow[2], c3 = irow[3];
-            if (!moments) {
-                for (int t = 0; t < K; t++) {
-                    const double wv = wr[t];
-                    acc[0] = fma(wv, c0, acc[0]);
-                    acc[1] = fma(wv, c1, acc[1]);
-                    acc[2] = fma(wv, c2, acc[2]);
-                    acc[3] = fma(wv, c3, acc[3]);
-                    c0 = c1;
-                    c1 = c2;
-                    c2 = c3;
-                    c3 = irow[t + 4];
+            double v[CV_MX], nx[CV_MX];
+#pragma unroll
+            for (int m = 0; m < CV_MX; m++) v[m] = irow[m * q];  // columns tx*8 + m
+            for (int tb = 0; tb < Kp; tb += 8) {
+                const int qi = 1 + (tb >> 3);
+#pragma unroll
+                for (int j = 0; j < 8; j++) nx[j] = irow[j * q + qi];  // columns tx*8 + tb + 8 + j
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double wv = wr[tb + j];
+                    // window of tap tb+j: columns tx*8 + tb + j + m, m = 0..7  ->  v[j+m] for j+m < 8, else nx[j+m-8]
+                    if (!moments) {
+#pragma unroll
+                        for (int m = 0; m < CV_MX; m++) acc[m] = fma(wv, (j + m < 8) ? v[j + m] : nx[j + m - 8], acc[m]);
+                    } else {
+                        const double wvx = wv * (double)(w - (tb + j));  // Win * indexes (column offset)
+                        const double wvy = wv * u;                        // Win * y       (row offset)
+#pragma unroll
+                        for (int m = 0; m < CV_MX; m++) {
+                            const double c = (j + m < 8) ? v[j + m] : nx[j + m - 8];
+                            acc[m] = fma(wv, c, acc[m]);
+                            accx[m] = fma(wvx, c, accx[m]);
+                            accy[m] = fma(wvy, c, accy[m]);
+                        }
+                    }
                 }
-            } else {
-                for (int t = 0; t < K; t++) {
-                    const double wv = wr[t];
-                    const double wvx = wv * (double)(w - t);  // Win * indexes (column offset v = w - t)
-                    const double wvy = wv * u;                // Win * y       (row offset u)
-                    acc[0] = fma(wv, c0, acc[0]);
-                    acc[1] = fma(wv, c1, acc[1]);
-                    acc[2] = fma(wv, c2, acc[2]);
-                    acc[3] = fma(wv, c3, acc[3]);
-                    accx[0] = fma(wvx, c0, accx[0]);
-                    accx[1] = fma(wvx, c1, accx[1]);
-                    accx[2] = fma(wvx, c2, accx[2]);
-                    accx[3] = fma(wvx, c3, accx[3]);
-                    accy[0] = fma(wvy, c0, accy[0]);
-                    accy[1] = fma(wvy, c1, accy[1]);
-                    accy[2] = fma(wvy, c2, accy[2]);
-                    accy[3] = fma(wvy, c3, accy[3]);
-                    c0 = c1;
-                    c1 = c2;
-                    c2 = c3;
-                    c3 = irow[t + 4];
-                }
+#pragma unroll
+                for (int m = 0; m < CV_MX; m++) v[m] = nx[m];
             }
         }
     }
@@ -521,8 +528,8 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     double tmax = 0;
     if (oy < G) {
 #pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const int ox = ox0 + tx * 4 + m;
+        for (int m = 0; m < CV_MX; m++) {
+            const int ox = ox0 + tx * CV_MX + m;
             if (ox >= G) continue;
             const size_t o = (size_t)oy * G + ox;
             if (MODE == 0) {
@@ -533,9 +540,9 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
                 }
                 tmax = fmax(tmax, acc[m]);
             } else {
-                const double v = P[o] * acc[m] / jb.a00b[o];
-                Pout[o] = v;
-                tmax = fmax(tmax, v);
+                const double vv = P[o] * acc[m] / jb.a00b[o];
+                Pout[o] = vv;
+                tmax = fmax(tmax, vv);
             }
         }
     }
@@ -585,47 +592,77 @@ __global__ void __launch_bounds__(256) k_mask_T(const ConvJob* __restrict__ jobs
     }
 }
 
-// maps: a_rs[y][x] = sum_u u^r my(y - u) T_s[u][x].  grid (ceil(G/8), njobs), 256 threads.
+// maps: a_rs[y][x] = sum_u u^r my(y - u) T_s[u][x].  grid (ceil(G/256), njobs), one thread per column x.
+// Interior rows (w <= y <= G-1-w) see my == 1 for every tap, so each map equals the column's FULL sum there; only
+// the <= 2w boundary rows need corrections, and only for the taps that reach the edge: O(K + w^2) work per column
+// instead of O(G K).
 __global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ jobs) {
     const ConvJob jb = jobs[blockIdx.y];
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const size_t plane = (size_t)K * G, gg = (size_t)G * G;
     if (!jb.T) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= G) return;
     const int eb = jb.bounded ? jb.yb : 0, et = jb.bounded ? jb.yt : 0;
-    for (int yy = 0; yy < 8; yy++) {
-        const int y = blockIdx.x * 8 + yy;
-        if (y >= G) break;
-        for (int x = threadIdx.x; x < G; x += blockDim.x) {
-            double a00 = 0, a10 = 0, a01 = 0, a20 = 0, a02 = 0, a11 = 0, ab = 0;
-            for (int ku = 0; ku < K; ku++) {
-                const int u = ku - w;
-                const int s = y - u;
-                const double m = mask1d(s, G, eb, et);
-                const double mb = (s < 0 || s > G - 1) ? 0.0 : m;
-                const size_t base = (size_t)ku * G + x;
-                const double t0 = jb.T[base];
-                ab += mb * jb.T[3 * plane + base];
-                if (jb.bounded) {
-                    const double t1 = jb.T[plane + base], t2 = jb.T[2 * plane + base];
-                    const double du = (double)u;
-                    a00 += m * t0;
-                    a10 += m * t1;
-                    a20 += m * t2;
-                    a01 += (m * du) * t0;
-                    a02 += (m * du * du) * t0;
-                    a11 += (m * du) * t1;
+    const double* T0 = jb.T + x;
+    const double* T1 = jb.T + plane + x;
+    const double* T2 = jb.T + 2 * plane + x;
+    const double* T3 = jb.T + 3 * plane + x;
+    double F00 = 0, F10 = 0, F01 = 0, F20 = 0, F02 = 0, F11 = 0, FB = 0;
+    for (int ku = 0; ku < K; ku++) {
+        const double du = (double)(ku - w);
+        const size_t o = (size_t)ku * G;
+        FB += T3[o];
+        if (jb.bounded) {
+            const double t0 = T0[o], t1 = T1[o];
+            F00 += t0;
+            F10 += t1;
+            F20 += T2[o];
+            F01 += du * t0;
+            F02 += (du * du) * t0;
+            F11 += du * t1;
+        }
+    }
+    for (int y = 0; y < G; y++) {
+        double a00 = F00, a10 = F10, a01 = F01, a20 = F20, a02 = F02, a11 = F11, ab = FB;
+        // taps reaching the lower edge (s = y - u <= 0) and the upper edge (s >= G-1)
+        for (int pass = 0; pass < 2; pass++) {
+            int ulo, uhi;
+            if (pass == 0) {
+                ulo = y > -w ? y : -w;
+                uhi = w;
+            } else {
+                ulo = -w;
+                uhi = (y - (G - 1)) < w ? (y - (G - 1)) : w;
+                if (uhi >= y && y <= w) uhi = y - 1;  // never double count (only possible when K > G)
+            }
+            for (int u = ulo; u <= uhi; u++) {
+                const int sidx = y - u;
+                const double m = mask1d(sidx, G, eb, et);
+                const double mb = (sidx < 0 || sidx > G - 1) ? 0.0 : m;
+                const size_t o = (size_t)(u + w) * G;
+                ab += (mb - 1.0) * T3[o];
+                if (jb.bounded && m != 1.0) {
+                    const double d = m - 1.0, du = (double)u;
+                    const double t0 = T0[o], t1 = T1[o];
+                    a00 += d * t0;
+                    a10 += d * t1;
+                    a20 += d * T2[o];
+                    a01 += (d * du) * t0;
+                    a02 += (d * du * du) * t0;
+                    a11 += (d * du) * t1;
                 }
             }
-            const size_t o = (size_t)y * G + x;
-            if (jb.a00b) jb.a00b[o] = ab;
-            if (jb.bounded) {
-                jb.maps[o] = a00;
-                jb.maps[gg + o] = a10;
-                jb.maps[2 * gg + o] = a01;
-                jb.maps[3 * gg + o] = a20;
-                jb.maps[4 * gg + o] = a02;
-                jb.maps[5 * gg + o] = a11;
-            }
+        }
+        const size_t o = (size_t)y * G + x;
+        if (jb.a00b) jb.a00b[o] = ab;
+        if (jb.bounded) {
+            jb.maps[o] = a00;
+            jb.maps[gg + o] = a10;
+            jb.maps[2 * gg + o] = a01;
+            jb.maps[3 * gg + o] = a20;
+            jb.maps[4 * gg + o] = a02;
+            jb.maps[5 * gg + o] = a11;
         }
     }
 }

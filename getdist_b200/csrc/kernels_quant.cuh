@@ -38,6 +38,13 @@ struct QCand {
     unsigned long long key, wq;
 };
 
+// first-pass geometry of a parameter: after pass 1 every slot interval lies inside ONE first-pass digit, so a
+// table indexed by that digit (bit mask of slots) replaces the per-element scan over all slot intervals
+struct QBase {
+    unsigned long long klo0;
+    int shift0, nb0;
+};
+
 __host__ __device__ __forceinline__ unsigned long long f64_to_key(double x) {
     unsigned long long b;
 #if defined(__CUDA_ARCH__)
@@ -78,11 +85,12 @@ __device__ __forceinline__ void smem_add_u64(unsigned* lo, unsigned* hi, unsigne
 //   shared_first != 0: one histogram per parameter over slot 0's interval (first pass).
 //   else             : each refining slot s owns bins [s*nbins, (s+1)*nbins).
 // ghist[(p*QMAXF + s) * nbins + d] accumulates with u64 atomics (integer: order independent).
-__global__ void __launch_bounds__(256) k_qhist(const double* __restrict__ dX, int64_t ld,
+__global__ void __launch_bounds__(1024) k_qhist(const double* __restrict__ dX, int64_t ld,
                                                const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
                                                const int* __restrict__ params, const QSlot* __restrict__ slots, int ns,
-                                               int nbins, int shared_first, unsigned long long* __restrict__ ghist) {
-    extern __shared__ unsigned qsm[];  // lo limbs [nh][nbins] then hi limbs [nh][nbins]
+                                               int nbins, int shared_first, unsigned long long* __restrict__ ghist,
+                                               const QBase* __restrict__ qbase) {
+    extern __shared__ unsigned qsm[];  // lo limbs [nh][nbins], hi limbs [nh][nbins], then the prefilter table
     __shared__ unsigned long long s_lo[QMAXF], s_w[QMAXF];
     __shared__ int s_shift[QMAXF], s_slot[QMAXF];
     __shared__ int n_act;
@@ -111,10 +119,17 @@ __global__ void __launch_bounds__(256) k_qhist(const double* __restrict__ dX, in
         }
         n_act = na;
     }
-    for (int i = threadIdx.x; i < 2 * nh * nbins; i += blockDim.x) qsm[i] = 0;
+    const QBase qb = qbase[p];
+    unsigned* tbl = qsm + 2 * nh * nbins;
+    const int ntbl = shared_first ? 0 : qb.nb0;
+    for (int i = threadIdx.x; i < 2 * nh * nbins + ntbl; i += blockDim.x) qsm[i] = 0;
     __syncthreads();
     const int na = n_act;
     if (na == 0) return;
+    if (!shared_first) {
+        if (threadIdx.x < na) atomicOr(&tbl[(int)((s_lo[threadIdx.x] - qb.klo0) >> qb.shift0)], 1u << threadIdx.x);
+        __syncthreads();
+    }
     for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
         unsigned long long key[4], wq[4];
 #pragma unroll
@@ -131,11 +146,22 @@ __global__ void __launch_bounds__(256) k_qhist(const double* __restrict__ dX, in
         for (int k = 0; k < 4; k++) {
             const int64_t r = r0 + (int64_t)k * blockDim.x;
             if (r >= sg.r1) continue;
-            for (int t = 0; t < na; t++) {
-                const unsigned long long d = key[k] - s_lo[t];
-                if (d <= s_w[t]) {
-                    const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
-                    smem_add_u64(hlo + bin, hhi + bin, shared_first ? wq[k] : dWq[r]);
+            if (shared_first) {
+                const unsigned long long d = key[k] - s_lo[0];
+                if (d <= s_w[0]) {
+                    const int bin = (int)(d >> s_shift[0]);
+                    smem_add_u64(hlo + bin, hhi + bin, wq[k]);
+                }
+            } else {
+                unsigned m = tbl[(int)((key[k] - qb.klo0) >> qb.shift0)];
+                while (m) {
+                    const int t = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long d = key[k] - s_lo[t];
+                    if (d <= s_w[t]) {
+                        const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
+                        smem_add_u64(hlo + bin, hhi + bin, dWq[r]);
+                    }
                 }
             }
         }
@@ -222,7 +248,8 @@ __global__ void k_qscan(QSlot* __restrict__ slots, int ns, int nbins, int shared
 __global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, int64_t ld,
                                                  const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
                                                  const int* __restrict__ params, QSlot* __restrict__ slots, int ns,
-                                                 QCand* __restrict__ cand) {
+                                                 QCand* __restrict__ cand, const QBase* __restrict__ qbase) {
+    extern __shared__ unsigned gtbl[];  // prefilter table, nb0 entries
     __shared__ unsigned long long s_lo[QMAXF], s_w[QMAXF];
     __shared__ int s_slot[QMAXF];
     __shared__ int n_act;
@@ -242,9 +269,13 @@ __global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, 
         }
         n_act = na;
     }
+    const QBase qb = qbase[p];
+    for (int i = threadIdx.x; i < qb.nb0; i += blockDim.x) gtbl[i] = 0;
     __syncthreads();
     const int na = n_act;
     if (na == 0) return;
+    if (threadIdx.x < na) atomicOr(&gtbl[(int)((s_lo[threadIdx.x] - qb.klo0) >> qb.shift0)], 1u << threadIdx.x);
+    __syncthreads();
     for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
         unsigned long long key[4];
 #pragma unroll
@@ -256,7 +287,10 @@ __global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, 
         for (int k = 0; k < 4; k++) {
             const int64_t r = r0 + (int64_t)k * blockDim.x;
             if (r >= sg.r1) continue;
-            for (int t = 0; t < na; t++) {
+            unsigned m = gtbl[(int)((key[k] - qb.klo0) >> qb.shift0)];
+            while (m) {
+                const int t = __ffs(m) - 1;
+                m &= m - 1;
                 if (key[k] - s_lo[t] <= s_w[t]) {
                     const int gs = p * QMAXF + s_slot[t];
                     const int idx = atomicAdd(&slots[gs].ncand, 1);
