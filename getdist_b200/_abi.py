@@ -59,6 +59,11 @@ class Result2D(C.Structure):
                 ("pad", C.c_int32)]
 
 
+class LagJob(C.Structure):
+    _fields_ = [("param", C.c_int32), ("mode", C.c_int32), ("k0", C.c_int64), ("nk", C.c_int32), ("pad", C.c_int32),
+                ("mean", C.c_double), ("inv4s2", C.c_double)]
+
+
 class GdkError(RuntimeError):
     pass
 
@@ -106,6 +111,8 @@ def load():
     lib.gdk_density1d_batch.restype = i32
     lib.gdk_density2d_batch.argtypes = [vp, i32, vp, vp, vp, vp, u32]
     lib.gdk_density2d_batch.restype = i32
+    lib.gdk_lag_sums.argtypes = [vp, i32, vp, vp]
+    lib.gdk_lag_sums.restype = i32
     lib.gdk_hist1d_batch.argtypes = [vp, i32, vp, vp, i64]
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
@@ -235,6 +242,19 @@ class Context:
         out = np.empty(int(sizes.sum()))
         self._ck(self.lib.gdk_hist2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets)), "gdk_hist2d_batch")
         return out, offsets
+
+    def lag_sums(self, jobs):
+        """jobs: list of (param, mode, k0, nk, mean, inv4s2) -> list of arrays (one per job, nk values)"""
+        n = len(jobs)
+        arr = (LagJob * n)(*[LagJob(int(p), int(m), int(k0), int(nk), 0, float(mean), float(i4)) for (p, m, k0, nk, mean, i4) in jobs])
+        tot = sum(int(j[3]) for j in jobs)
+        out = np.empty(tot)
+        self._ck(self.lib.gdk_lag_sums(self.h, n, C.cast(arr, C.c_void_p), _ptr(out)), "gdk_lag_sums")
+        res, o = [], 0
+        for j in jobs:
+            res.append(out[o: o + int(j[3])])
+            o += int(j[3])
+        return res
 
     def timer_start(self):
         self._ck(self.lib.gdk_timer_start(self.h), "gdk_timer_start")

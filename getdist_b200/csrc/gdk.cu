@@ -563,15 +563,40 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
     std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
     int rc = gdk_upload_segs(ctx, segs, ctx->segs);
     if (rc) return rc;
-    static int smem_set = 0;
-    if (maxF * 8 > smem_set) {
-        CK(cudaFuncSetAttribute(k_hist1d, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(maxF * 8, 48 * 1024)));
-        smem_set = std::max(maxF * 8, 48 * 1024);
-    }
+    // TMA-pipelined kernel when every segment starts on an even row (16-byte aligned bulk copies) and the bins fit
+    bool aligned = true;
+    for (const Seg& sgm : segs) aligned = aligned && ((sgm.r0 & 1) == 0);
+    const size_t smem_tma = (size_t)2 * H1_STAGES * H1_CHUNK * 8 + (size_t)maxF * 8;
+    const bool use_tma = aligned && maxF <= 32768 && smem_tma <= (size_t)ctx->max_smem - 2048;
     PhaseTimer pt;
-    pt.begin(ctx, GDK_PH_HIST1D);
     dim3 g((unsigned)segs.size(), (unsigned)n);
-    k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->jobs1d.p, ctx->gbins.p, gstride);
+    if (use_tma) {
+        std::vector<Hist1dJobT> jt(n);
+        for (int i = 0; i < n; i++) {
+            int bits = 0;
+            while ((1 << bits) < specs[i].fine_bins + 2) bits++;
+            const int sh = 31 - bits;
+            jt[i] = Hist1dJobT{jobs[i].param, jobs[i].F, sh, 0, jobs[i].binmin, jobs[i].fine_width, jobs[i].inv_width, ldexp(1.0, sh)};
+        }
+        if (ctx->bytes2d.ensure((size_t)n * sizeof(Hist1dJobT))) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D job table");
+        Hist1dJobT* djt = reinterpret_cast<Hist1dJobT*>(ctx->bytes2d.p);
+        CK(cudaMemcpyAsync(djt, jt.data(), (size_t)n * sizeof(Hist1dJobT), cudaMemcpyHostToDevice, ctx->stream));
+        static size_t tma_set = 0;
+        if (smem_tma > tma_set) {
+            CK(cudaFuncSetAttribute(k_hist1d_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tma, 48 * 1024)));
+            tma_set = std::max<size_t>(smem_tma, 48 * 1024);
+        }
+        pt.begin(ctx, GDK_PH_HIST1D);
+        k_hist1d_tma<<<g, 256, smem_tma, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, djt, ctx->gbins.p, gstride);
+    } else {
+        static int smem_set = 0;
+        if (maxF * 8 > smem_set) {
+            CK(cudaFuncSetAttribute(k_hist1d, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(maxF * 8, 48 * 1024)));
+            smem_set = std::max(maxF * 8, 48 * 1024);
+        }
+        pt.begin(ctx, GDK_PH_HIST1D);
+        k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->jobs1d.p, ctx->gbins.p, gstride);
+    }
     ctx->launches++;
     pt.end();
     CK(cudaGetLastError());
@@ -648,5 +673,43 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
                                cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(res, ctx->res1d.p, n * sizeof(gdk_result1d), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return GDK_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// lagged sums
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t gdk_lag_sums(gdk_ctx* ctx, int32_t njobs, const gdk_lagjob* jobs, double* out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (njobs <= 0 || !jobs || !out) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_lag_sums: bad arguments");
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<LagJob> lj(njobs);
+    for (int i = 0; i < njobs; i++) {
+        const gdk_lagjob& j = jobs[i];
+        if (j.param < 0 || j.param >= ctx->P || j.nk < 1 || j.nk > LAG_MAXK || j.k0 < 0 || (j.mode != 0 && j.mode != 1))
+            return gdk_fail(ctx, GDK_ERR_ARG, "gdk_lag_sums: bad job %d", i);
+        lj[i] = LagJob{j.param, j.mode, (long long)j.k0, j.nk, 0, j.mean, j.inv4s2};
+    }
+    const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>((ctx->N + 8191) / 8192, (int64_t)ctx->num_sms * 8 / njobs + 1));
+    const int64_t chunk = (ctx->N + nchunk - 1) / nchunk;
+    if (ctx->bytes2d.ensure((size_t)njobs * sizeof(LagJob)) || ctx->scratch.ensure((size_t)njobs * nchunk * LAG_MAXK))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "lag-sum buffers");
+    LagJob* dj = reinterpret_cast<LagJob*>(ctx->bytes2d.p);
+    CK(cudaMemcpyAsync(dj, lj.data(), (size_t)njobs * sizeof(LagJob), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 g((unsigned)nchunk, (unsigned)njobs);
+    k_lag_sums<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->N, chunk, dj, ctx->scratch.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<double> part((size_t)njobs * nchunk * LAG_MAXK);
+    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t o = 0;
+    for (int i = 0; i < njobs; i++)
+        for (int k = 0; k < jobs[i].nk; k++) {
+            double t = 0;
+            for (int c = 0; c < nchunk; c++) t += part[((size_t)i * nchunk + c) * LAG_MAXK + k];
+            out[o++] = t;
+        }
     return GDK_OK;
 }

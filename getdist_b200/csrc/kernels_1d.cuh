@@ -29,6 +29,37 @@ __device__ __forceinline__ int bin_index_trunc(double x, double rmin, double dx,
     return (int)__ddiv_rn(d, dx);
 }
 
+// ---- TMA (bulk async copy) helpers: global -> shared with an mbarrier ------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 struct Hist1dJob {
     int param, F;
     double binmin, fine_width, inv_width;
@@ -94,37 +125,112 @@ __global__ void __launch_bounds__(256) k_hist1d(const double* __restrict__ dX, i
     }
 }
 
+// ---- TMA-pipelined variant of the 1D sweep ------------------------------------------------------------------
+// The sample and weight streams are staged through a ring of H1_STAGES shared-memory buffers by bulk async
+// copies (cp.async.bulk -> UBLKCP) with full/empty mbarriers: no load latency on the consumers' critical path
+// and no registers tied up by loads in flight.  Consumers copy their elements to registers, release the stage,
+// then do the index arithmetic and the shared-memory atomics.  Bin index: q = (x - binmin)/fw + 0.5 is evaluated
+// in fixed point (one DFMA + F2I); the low `sh` bits are the fractional part, and only when it lies within
+// 2^-(sh-4) of an integer is the exact IEEE sequence (sub, div, add) executed.
+#define H1_STAGES 3
+#define H1_CHUNK 1024
+struct Hist1dJobT {
+    int param, F, sh, pad;
+    double binmin, fine_width, inv_width, scale;  // scale = 2^sh
+};
+
+__global__ void __launch_bounds__(256) k_hist1d_tma(const double* __restrict__ dX, int64_t ld,
+                                                    const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                    const Hist1dJobT* __restrict__ jobs, unsigned long long* __restrict__ gbins,
+                                                    int64_t gstride) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    __shared__ __align__(8) unsigned long long full[H1_STAGES], empty[H1_STAGES];
+    const Hist1dJobT jb = jobs[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const int F = jb.F;
+    double* xs = reinterpret_cast<double*>(tsm);                                                   // [stages][chunk]
+    unsigned long long* ws = reinterpret_cast<unsigned long long*>(tsm + (size_t)H1_STAGES * H1_CHUNK * 8);
+    unsigned* hlo = reinterpret_cast<unsigned*>(tsm + (size_t)2 * H1_STAGES * H1_CHUNK * 8);
+    unsigned* hhi = hlo + F;
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) hlo[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < H1_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], blockDim.x);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double* x = dX + (int64_t)jb.param * ld + sg.r0;  // r0 even -> 16-byte aligned
+    const unsigned long long* wq = dWq + sg.r0;
+    const int64_t n = sg.r1 - sg.r0;
+    const int nchunks = (int)((n + H1_CHUNK - 1) / H1_CHUNK);
+    auto issue = [&](int c) {
+        const int s = c % H1_STAGES;
+        const int64_t off = (int64_t)c * H1_CHUNK;
+        const int cnt = (int)min((int64_t)H1_CHUNK, n - off);
+        const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);  // columns are padded: one element past is readable
+        mbar_expect_tx(&full[s], 2 * bytes);
+        bulk_g2s(xs + (size_t)s * H1_CHUNK, x + off, bytes, &full[s]);
+        bulk_g2s(ws + (size_t)s * H1_CHUNK, wq + off, bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int c = 0; c < H1_STAGES && c < nchunks; c++) issue(c);
+    const unsigned fmask = (1u << jb.sh) - 1u;
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c % H1_STAGES;
+        const unsigned ph = (unsigned)((c / H1_STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        const int cnt = (int)min((int64_t)H1_CHUNK, n - (int64_t)c * H1_CHUNK);
+        const double2* xp = reinterpret_cast<const double2*>(xs + (size_t)s * H1_CHUNK);
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(ws + (size_t)s * H1_CHUNK);
+        double2 xv[2];
+        ulonglong2 wv[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {  // 256 threads x 2 x (2 elements) = one chunk
+            const int i = threadIdx.x + k * 256;
+            xv[k] = xp[i];
+            wv[k] = wp[i];
+        }
+        mbar_arrive(&empty[s]);  // stage may be refilled
+        if (threadIdx.x == 0 && c + H1_STAGES < nchunks) {
+            mbar_wait(&empty[s], ph);
+            issue(c + H1_STAGES);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i2 = (threadIdx.x + k * 256) * 2;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                if (i2 + e >= cnt) continue;
+                const double xe = e ? xv[k].y : xv[k].x;
+                const unsigned long long we = e ? wv[k].y : wv[k].x;
+                const double d = __dsub_rn(xe, jb.binmin);
+                const double t = fma(d, jb.inv_width * jb.scale, 0.5 * jb.scale);
+                unsigned b;
+                const unsigned I = __double2uint_rd(t);
+                const unsigned fr = I & fmask;
+                if (t >= 0.0 && t < 4294967040.0 && (fr - 8u) < (fmask - 15u)) {
+                    b = I >> jb.sh;
+                } else {
+                    b = (unsigned)(int)__dadd_rn(__ddiv_rn(d, jb.fine_width), 0.5);
+                }
+                if (b < (unsigned)F) smem_add_u64(hlo + b, hhi + b, we);
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long* g = gbins + (int64_t)blockIdx.y * gstride;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        const unsigned long long v = ((unsigned long long)hhi[i] << 32) | hlo[i];
+        if (v) atomicAdd(g + i, v);
+    }
+}
+
 // fixed point -> float64 bins
 __global__ void k_bins_to_f64(const unsigned long long* __restrict__ g, double* __restrict__ out, int64_t n, double inv_scale) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (double)g[i] * inv_scale;
-}
-
-// ---- TMA (bulk async copy) helpers: global -> shared with an mbarrier ------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-        "r"(phase)
-        : "memory");
 }
 
 struct Kde1dTables {

@@ -283,3 +283,57 @@ __global__ void k_cov_reduce(const double* __restrict__ part, const Seg* __restr
         }
     }
 }
+
+// ---- lagged sums (MCMC effective-sample estimate) ----------------------------------------------------------
+#define LAG_MAXK 16
+struct LagJob {
+    int param, mode;
+    long long k0;
+    int nk, pad;
+    double mean, inv4s2;
+};
+// grid (nchunk, njobs), 256 threads; part[(job*nchunk + chunk)*LAG_MAXK + k].  Rows are NOT cut at chain
+// boundaries: the reference neglects edge effects between concatenated chains (chains.py:427-428).
+__global__ void __launch_bounds__(256) k_lag_sums(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
+                                                  int64_t N, int64_t chunk, const LagJob* __restrict__ jobs,
+                                                  double* __restrict__ part) {
+    const LagJob jb = jobs[blockIdx.y];
+    const double* x = dX + (int64_t)jb.param * ld;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(N, r0 + chunk);
+    double acc[LAG_MAXK];
+#pragma unroll
+    for (int k = 0; k < LAG_MAXK; k++) acc[k] = 0;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        const double xi = x[i], wi = dW[i];
+        if (jb.mode == 0) {
+            const double di = (xi - jb.mean) * wi;
+#pragma unroll
+            for (int k = 0; k < LAG_MAXK; k++) {
+                const int64_t j = i + jb.k0 + k;
+                if (k < jb.nk && j < N) acc[k] += di * ((x[j] - jb.mean) * dW[j]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < LAG_MAXK; k++) {
+                const int64_t j = i + jb.k0 + k;
+                if (k < jb.nk && j < N) {
+                    const double d = xi - x[j];
+                    acc[k] += (exp(-(d * d) * jb.inv4s2) * wi) * dW[j];
+                }
+            }
+        }
+    }
+    __shared__ double sh[LAG_MAXK][8];
+    const int wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < LAG_MAXK; k++) {
+        const double v = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) sh[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < LAG_MAXK) {
+        double t = 0;
+        for (int i = 0; i < 8; i++) t += sh[threadIdx.x][i];
+        part[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * LAG_MAXK + threadIdx.x] = t;
+    }
+}

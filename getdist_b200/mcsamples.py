@@ -14,7 +14,7 @@ Everything N-sized or grid-sized runs on the device through the C-ABI (getdist_b
 keeps only the scalar per-parameter logic (``_initParam`` limit tests, grid geometry, 2D branch selection and
 2x2 Cholesky algebra), settings handling, caching and error/warning behaviour.  There is no CPU fallback:
 options of the reference that the device path does not implement yet raise ``NotImplementedError``
-(meanlikes, mask_function, periodic parameters, sampler='mcmc' N_eff -- SURVEY.md s8f).
+(meanlikes, mask_function, periodic parameters -- SURVEY.md s8f).
 
 ``prefetch_triangle`` computes all 1D and 2D densities of a parameter list in batched launches and fills the
 caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by getdist.plots) then hit.
@@ -367,17 +367,140 @@ class MCSamples:
 
     # ------------------------------------------------------------------ N_eff
     def getEffectiveSamplesGaussianKDE(self, paramVec, h=0.2, scale=None, maxoff=None, min_corr=0.05):
-        """chains.py:477-574.  Uncorrelated/nested samplers: (sum w)^2 / sum w^2 (:500-501)."""
+        """chains.py:477-574.  Uncorrelated/nested samplers: (sum w)^2 / sum w^2 (:500-501); mcmc: the
+        autocorrelation-length / lagged-kernel estimate with every N-sized sum evaluated on the device."""
         if self.sampler in ("nested", "uncorrelated"):
             return self.norm ** 2 / self._sum_w2
-        raise NotImplementedError(
-            "sampler='mcmc' needs the autocorrelation-based N_eff (chains.py:423-574), which is not on the device "
-            "path yet (SURVEY.md s8f-1); construct with sampler='uncorrelated' or 'nested'")
+        j, _ = self._parAndNumber(paramVec)
+        if j is None:
+            raise NotImplementedError("device N_eff works on stored columns")
+        return self._neff_mcmc_batch([j], [scale], h=h, maxoff=maxoff, min_corr=min_corr)[0]
+
+    def _lag_rounds(self, gens):
+        """Drive per-parameter generators in lockstep: each yields a lag-sum request
+        (param, mode, k0, nk, mean, inv4s2) and is sent the nk sums; one batched device call per round."""
+        out = [None] * len(gens)
+        reqs = {}
+        for i, g in enumerate(gens):
+            try:
+                reqs[i] = next(g)
+            except StopIteration as e:
+                out[i] = e.value
+        while reqs:
+            order = list(reqs)
+            res = self._ctx.lag_sums([reqs[i] for i in order])
+            nxt = {}
+            for i, r in zip(order, res):
+                try:
+                    nxt[i] = gens[i].send(r)
+                except StopIteration as e:
+                    out[i] = e.value
+            reqs = nxt
+        return out
+
+    def _corr_length_gen(self, j, min_corr=0.05):
+        """getCorrelationLength(d, weight_units=False) (chains.py:448-466) with getAutocorrelation (:423-446):
+        corr[k] = sum_i d_i d_{i+k} / (N - k) / var, d = (x - mean) w, for k up to N//10; the reference gets all lags
+        from one size-2N FFT (autoConvolve), here lags are produced 16 at a time until the first one that is
+        <= min_corr * corr[0]."""
+        n = self.numrows
+        max_off = n // 10
+        mean, var = self.means[j], self.vars[j]
+        corr = []
+        k0 = 0
+        ix = None
+        while k0 <= max_off and ix is None:
+            nk = min(16, max_off + 1 - k0)
+            sums = yield (j, 0, k0, nk, mean, 0.0)
+            for t in range(nk):
+                k = k0 + t
+                corr.append(sums[t] / (n - k) / var)
+                if not corr[k] > min_corr * corr[0]:
+                    ix = k
+                    break
+            k0 += nk
+        if ix is None:
+            ix = 0  # np.argmin over an all-True array
+        return corr[0] + 2 * sum(corr[1:ix])
+
+    def _neff_gen(self, j, scale, h, maxoff, min_corr):
+        """getEffectiveSamplesGaussianKDE, mcmc branch (chains.py:502-574)."""
+        n = self.numrows
+        kernel_std = (scale or self.sddev[j]) * h
+        inv4 = 1.0 / (4 * kernel_std ** 2)
+        if maxoff is None:
+            clen = yield from self._corr_length_gen(j)
+            maxoff = int(clen * 1.5) + 4
+        maxoff = min(maxoff, n // 10)
+        uncorr_len = n // 2
+        sums = yield (j, 1, uncorr_len, 5, 0.0, inv4)
+        nav = sum(n - k for k in range(uncorr_len, uncorr_len + 5))
+        uncorr_term = float(np.sum(sums)) / nav
+        corr0 = self._sum_w2
+        nn = float(n)
+
+        def corr_k(k):
+            s = yield (j, 1, k, 1, 0.0, inv4)
+            return s[0] - (nn - k) * uncorr_term
+
+        threshold = min_corr * corr0
+        c1 = yield from corr_k(1)
+        if c1 < threshold:
+            N = corr0
+        else:
+            c2 = yield from corr_k(2)
+            if c2 > threshold:
+                max_k = maxoff
+                while max_k > 10:
+                    test_val = yield from corr_k(max_k // 3)
+                    if test_val >= threshold:
+                        break
+                    max_k //= 3
+                step_size = 1 if max_k < 20 else max_k // 10
+                cum_sum = c1 + c2
+                for k in range(3, maxoff + 1, step_size):
+                    test_val = yield from corr_k(k)
+                    if test_val < threshold:
+                        break
+                    if k > 3:
+                        cum_sum += test_val * step_size
+                    else:
+                        cum_sum += (test_val * step_size) / 2
+                N = corr0 + 2 * cum_sum
+            else:
+                N = corr0 + 2 * c1
+        return self.norm ** 2 / N
+
+    def _neff_mcmc_batch(self, indices, scales, h=0.2, maxoff=None, min_corr=0.05):
+        if self.needs_update:
+            self.updateBaseStatistics()
+        gens = [self._neff_gen(j, sc, h, maxoff, min_corr) for j, sc in zip(indices, scales)]
+        return self._lag_rounds(gens)
+
+    def getCorrelationLength(self, j, weight_units=True, min_corr=0.05, corr=None):
+        """chains.py:448-466 (row units only: weight_units=False)."""
+        if weight_units or corr is not None:
+            raise NotImplementedError("only weight_units=False is on the device path")
+        j, _ = self._parAndNumber(j)
+        return self._lag_rounds([self._corr_length_gen(j, min_corr)])[0]
 
     def _get1DNeff(self, par, param):
         if par.N_eff_kde is None:
             par.N_eff_kde = self.getEffectiveSamplesGaussianKDE(param, scale=par.sigma_range)
         return par.N_eff_kde
+
+    def _ensure_neff(self, indices):
+        """N_eff for every listed parameter that does not have one yet; mcmc sampler: batched rounds."""
+        todo = [j for j in dict.fromkeys(indices) if self.paramNames.names[j].N_eff_kde is None]
+        if not todo:
+            return
+        if self.sampler in ("nested", "uncorrelated"):
+            for j in todo:
+                self.paramNames.names[j].N_eff_kde = self.norm ** 2 / self._sum_w2
+        else:
+            vals = self._neff_mcmc_batch(todo, [self.paramNames.names[j].sigma_range for j in todo])
+            for j, v in zip(todo, vals):
+                self.paramNames.names[j].N_eff_kde = v
 
     # ------------------------------------------------------------------ parameter ranges
     def _ensure_param_ranges(self, indices):
@@ -493,6 +616,8 @@ class MCSamples:
         if meanlikes:
             raise NotImplementedError("meanlikes is not on the device path yet (SURVEY.md s8f-3)")
         self._ensure_param_ranges(indices)
+        if kwargs.get("smooth_scale_1D", self.smooth_scale_1D) <= 0:
+            self._ensure_neff(indices)
         specs = [self._spec_1d(j, kwargs) for j in indices]
         P, res = self._ctx.density1d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
@@ -662,6 +787,8 @@ class MCSamples:
 
     def _densities_2d(self, pairs, _out=None, _device_ptr=None, **kwargs):
         self._ensure_param_ranges([p for pr in pairs for p in pr])
+        if float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D)) < 0:
+            self._ensure_neff([p for pr in pairs for p in pr])
         specs = [self._spec_2d(j, j2, kwargs) for (j, j2) in pairs]
         buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:

@@ -195,6 +195,23 @@ typedef struct gdk_result2d {
 int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out,
                             const int64_t* offsets, gdk_result2d* res, uint32_t flags);
 
+/* ---------------------------------------------------------------------------------------------
+ * lagged sums over the stored rows -- the N-sized arithmetic of the MCMC effective-sample estimate
+ * getEffectiveSamplesGaussianKDE / getCorrelationLength / getAutocorrelation (chains.py:423-466,
+ * 477-574; autoConvolve convolve.py:458-478, evaluated as direct lag products instead of a size-2N FFT):
+ *   mode 0: out[k] = sum_{i < N-k} d_i d_{i+k},  d = (x - mean) * w                (auto-covariance)
+ *   mode 1: out[k] = sum_{i < N-k} exp(-(x_i - x_{i+k})^2 * inv4s2) w_i w_{i+k}    (kernel-weighted pairs)
+ * for the consecutive lags k = k0 .. k0+nk-1 (nk <= 16) of one stored column.  out is packed job after job.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct gdk_lagjob {
+    int32_t param, mode;
+    int64_t k0;
+    int32_t nk, pad;
+    double mean;   /* mode 0 */
+    double inv4s2; /* mode 1: 1 / (4 kernel_std^2) */
+} gdk_lagjob;
+int32_t gdk_lag_sums(gdk_ctx* ctx, int32_t njobs, const gdk_lagjob* jobs, double* out);
+
 /* raw histograms (test hooks; also the unit the `hist HBM GB/s` roofline figure is measured on):
  * weighted fine-grid histograms exactly as _binSamples + bincount build them.                   */
 int32_t gdk_hist1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* bins_out, int64_t stride);

@@ -223,6 +223,80 @@ def neff_uncorrelated(w):
     return np.sum(w) ** 2 / np.dot(w, w)
 
 
+def auto_convolve(x, n=None, normalize=True):
+    """convolve.py:458-478 (``autoConvolve``): result[k] = sum_i x_i x_{i+k} (/ number of terms), evaluated with
+    a zero-padded real FFT (the reference packs the same transform through fftpack.rfft + a type-1 DCT)."""
+    size = 1
+    while size < 2 * x.size:
+        size *= 2
+    xt = np.fft.rfft(x, size)
+    res = np.fft.irfft(xt * np.conj(xt), size)[: (n or x.size)]
+    if normalize:
+        res = res / np.arange(x.size, x.size - (n or x.size), -1)
+    return res
+
+
+def correlation_length_rows(x, w, mean, var, min_corr=0.05):
+    """chains.py:423-466 with weight_units=False: auto-correlation of (x - mean) w up to N//10 lags, summed up to
+    the first lag whose value is <= min_corr * corr[0]."""
+    d = (x - mean) * w
+    corr = auto_convolve(d, n=x.size // 10 + 1, normalize=True) / var
+    ix = np.argmin(corr > min_corr * corr[0])
+    return corr[0] + 2 * np.sum(corr[1:ix])
+
+
+def neff_mcmc(x, w, scale, h=0.2, maxoff=None, min_corr=0.05):
+    """chains.py:477-574 (``getEffectiveSamplesGaussianKDE``), mcmc branch."""
+    norm = np.sum(w)
+    mean = w.dot(x) / norm
+    var = w.dot((x - mean) ** 2) / norm
+    n = x.size
+    kernel_std = (scale or np.sqrt(var)) * h
+    if maxoff is None:
+        maxoff = int(correlation_length_rows(x, w, mean, var) * 1.5) + 4
+    maxoff = min(maxoff, n // 10)
+    uncorr_len = n // 2
+    uncorr_term = 0
+    nav = 0
+    for k in range(uncorr_len, uncorr_len + 5):
+        nav += n - k
+        diff2 = (x[:-k] - x[k:]) ** 2 / kernel_std**2
+        uncorr_term += np.dot(np.exp(-diff2 / 4) * w[:-k], w[k:])
+    uncorr_term /= nav
+    corr0 = np.dot(w, w)
+    nn = float(n)
+
+    def corr_k(k):
+        return np.dot(np.exp(-((x[:-k] - x[k:]) ** 2) / (4 * kernel_std**2)) * w[:-k], w[k:]) - (nn - k) * uncorr_term
+
+    threshold = min_corr * corr0
+    c1 = corr_k(1)
+    if c1 < threshold:
+        N = corr0
+    else:
+        c2 = corr_k(2)
+        if c2 > threshold:
+            max_k = maxoff
+            while max_k > 10:
+                if corr_k(max_k // 3) >= threshold:
+                    break
+                max_k //= 3
+            step_size = 1 if max_k < 20 else max_k // 10
+            cum_sum = c1 + c2
+            for k in range(3, maxoff + 1, step_size):
+                test_val = corr_k(k)
+                if test_val < threshold:
+                    break
+                if k > 3:
+                    cum_sum += test_val * step_size
+                else:
+                    cum_sum += (test_val * step_size) / 2
+            N = corr0 + 2 * cum_sum
+        else:
+            N = corr0 + 2 * c1
+    return norm**2 / N
+
+
 # --------------------------------------------------------------------------------------
 # parameter ranges (host-trivial scalar logic once quantiles/min/max exist)
 # --------------------------------------------------------------------------------------
@@ -566,8 +640,8 @@ class OracleSamples:
         self.names = list(names) if names is not None else ["param%d" % (i + 1) for i in range(self.n)]
         self.index = {n: i for i, n in enumerate(self.names)}
         self.sampler = sampler
-        if sampler not in ("uncorrelated", "nested"):
-            raise OracleError("oracle implements sampler='uncorrelated'/'nested' N_eff only (SURVEY s8f-1)")
+        if sampler not in ("uncorrelated", "nested", "mcmc"):
+            raise OracleError("unknown sampler")
         self.settings = dict(DEFAULT_SETTINGS)
         if settings:
             self.settings.update(settings)
@@ -631,7 +705,11 @@ class OracleSamples:
     def _neff(self, par):
         """mcsamples.py:1230-1235 with chains.py:500-501."""
         if par.N_eff_kde is None:
-            par.N_eff_kde = neff_uncorrelated(self.weights)
+            if self.sampler == "mcmc":
+                j = self.index[par.name]
+                par.N_eff_kde = neff_mcmc(self.samples[:, j], self.weights, par.sigma_range)
+            else:
+                par.N_eff_kde = neff_uncorrelated(self.weights)
         return par.N_eff_kde
 
     # ---- 1D ---------------------------------------------------------------------------

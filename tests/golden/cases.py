@@ -104,12 +104,30 @@ def case_chains():
                 pairs=[(0, 1), (2, 5)], kwargs_1d=[{}], kwargs_2d=[{}])
 
 
+def case_mcmc():
+    """Metropolis-like chain: AR(1) proposals with rejections folded into integer multiplicities, three
+    parameters with short / long / no autocorrelation -> the default sampler="mcmc" N_eff path."""
+    rng = np.random.default_rng(4242)
+    n = 30000
+    x = np.empty((n, 3))
+    e = rng.normal(size=(n, 3))
+    x[0] = e[0]
+    phi = np.array([0.6, 0.97, 0.0])
+    for i in range(1, n):
+        x[i] = phi * x[i - 1] + np.sqrt(1 - phi**2) * e[i]
+    w = 1.0 + rng.geometric(0.4, n).astype(np.float64)
+    X = np.ascontiguousarray(x * np.array([1.0, 5.0, 0.2]) + np.array([0.0, 50.0, 1.0]))
+    return dict(samples=X, weights=w, names=["m0", "m1", "m2"], ranges={}, settings={}, sampler="mcmc",
+                pairs=[(0, 1), (0, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
 CASES = {
     "mix3": case_mix3,
     "unit5": case_unit5,
     "bounded": case_bounded,
     "highcorr": case_highcorr,
     "chains": case_chains,
+    "mcmc": case_mcmc,
 }
 
 

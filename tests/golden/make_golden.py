@@ -26,7 +26,7 @@ def run_case(name):
     case = CASES[name]()
     out = {"digest": np.array(input_digest(case)), "getdist_version": np.array(getdist.__version__)}
     mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"],
-                   ranges=case["ranges"] or None, sampler="uncorrelated", loglikes=case.get("loglikes"), settings=case["settings"] or None)
+                   ranges=case["ranges"] or None, sampler=case.get("sampler", "uncorrelated"), loglikes=case.get("loglikes"), settings=case["settings"] or None)
     rec = {}
     orig1d = mc.getAutoBandwidth1D
     orig2d = mc.getAutoBandwidth2D
@@ -73,7 +73,7 @@ def run_case(name):
                 [par.range_min, par.range_max, par.sigma_range, par.param_min, par.param_max, par.err, par.mean,
                  float(par.has_limits_bot), float(par.has_limits_top),
                  par.kde_h if getattr(par, "kde_h", None) is not None else np.nan,
-                 rec.get("h1d", np.nan)])
+                 rec.get("h1d", np.nan), par.N_eff_kde if getattr(par, "N_eff_kde", None) is not None else np.nan])
     for kw in case["kwargs_2d"]:
         tag = kw_tag(kw)
         for (jx, jy) in case["pairs"]:

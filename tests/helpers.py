@@ -24,4 +24,4 @@ def make_oracle(case):
     from oracle.getdist_oracle import OracleSamples
 
     return OracleSamples(case["samples"], case["weights"], names=case["names"], ranges=case["ranges"],
-                         sampler="uncorrelated", settings=case["settings"])
+                         sampler=case.get("sampler", "uncorrelated"), settings=case["settings"])

@@ -16,7 +16,7 @@ def make_gpu(case):
     from getdist_b200 import MCSamples
 
     return MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"],
-                     sampler="uncorrelated", settings=case["settings"] or None)
+                     sampler=case.get("sampler", "uncorrelated"), settings=case["settings"] or None)
 
 
 @pytest.fixture(scope="module")
