@@ -219,7 +219,7 @@ def run_ours(args):
             phases["hist1d"], phases["kde1d"], phases["quantiles"] = ph["hist1d"], ph["kde1d"], ph["quantiles"]
         if my2d:
             # every 2D grid of the C2 workload is G x G; a scaled-up grid would not fit the packed tensor
-            specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr())
+            specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr(), _contours=[])
             assert all(s.fine_bins == G for s in specs)
             ph = mc._ctx.phase_ms()
             for k in ("hist2d", "shear", "xform2d", "bw2d", "conv2d"):
@@ -272,7 +272,7 @@ def run_ours(args):
     def step_e2e():
         m = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
         a = m._densities_1d(my1d, _out=out1) if my1d else []
-        b = m._densities_2d(my2d, _out=out2) if my2d else []
+        b = m._densities_2d(my2d, _out=out2, _contours=[]) if my2d else []
         s = float(out1[0, F // 2]) + float(out2[G * G // 2])
         m._ctx.close()
         return s, len(a) + len(b)
@@ -337,7 +337,7 @@ def run_ours(args):
         mc2 = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
         cols = CPU_SAMPLE_PARAMS
         g_1d = mc2._densities_1d(cols[:2])
-        g_2d = mc2._densities_2d([(cols[0], cols[1]), (cols[2], cols[3])])
+        g_2d = mc2._densities_2d([(cols[0], cols[1]), (cols[2], cols[3])], _contours=[])
         val, dt, results = cpu_sample(X, w)
         e1 = max(float(np.max(np.abs(g_1d[i].P - results[("1d", cols[i])].P))) for i in range(2))
         e2a = float(np.max(np.abs(g_2d[0].P - results[("2d", cols[0], cols[1])].P)))

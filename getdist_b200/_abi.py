@@ -20,6 +20,7 @@ ST_AMISE_CORR = 64
 ST_AMISE_FULL = 128
 ST_BIAS_NEG = 256
 ST_NONFINITE = 512
+ST_CONTOUR_RANGE = 1024
 
 BW2D_FIXED, BW2D_PLAIN, BW2D_SHEAR, BW2D_RULE = 0, 1, 2, 3
 
@@ -50,13 +51,14 @@ class Spec2D(C.Structure):
                 ("x_has_bot", C.c_int32), ("x_has_top", C.c_int32), ("y_has_bot", C.c_int32), ("y_has_top", C.c_int32),
                 ("shear_i", C.c_int32), ("shear_j", C.c_int32), ("shear_swapped", C.c_int32),
                 ("r0", C.c_double), ("r1", C.c_double), ("S00", C.c_double), ("S10", C.c_double), ("S11", C.c_double),
-                ("p1_min", C.c_double), ("p1_max", C.c_double)]
+                ("p1_min", C.c_double), ("p1_max", C.c_double),
+                ("n_contours", C.c_int32), ("pad2", C.c_int32), ("contours", C.c_double * 4)]
 
 
 class Result2D(C.Structure):
     _fields_ = [("hx", C.c_double), ("hy", C.c_double), ("c", C.c_double), ("rx", C.c_double), ("ry", C.c_double),
                 ("t_star", C.c_double), ("winw", C.c_int32), ("status", C.c_uint32), ("n_brent", C.c_int32),
-                ("pad", C.c_int32)]
+                ("pad", C.c_int32), ("levels", C.c_double * 4)]
 
 
 class LagJob(C.Structure):
@@ -117,7 +119,7 @@ def load():
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
     lib.gdk_hist2d_batch.restype = i32
-    if lib.gdk_abi_version() != 1:
+    if lib.gdk_abi_version() != 2:
         raise GdkError("libgdk.so ABI version mismatch")
     _lib = lib
     return lib

@@ -385,6 +385,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         c.bounded = (has_prior && s.boundary_correction_order >= 0) ? 1 : 0;
         c.bco = s.boundary_correction_order;
         c.mbc = s.mult_bias_correction_order;
+        c.nc = std::max(0, std::min(4, s.n_contours));
+        for (int k = 0; k < 4; k++) c.contours[k] = s.contours[k];
         c.xb = s.x_has_bot;
         c.xt = s.x_has_top;
         c.yb = s.y_has_bot;
@@ -490,6 +492,12 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         dim3 gf(64, (unsigned)n);
         k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dout, doffs, dres);
         ctx->launches++;
+        bool any_contours = false;
+        for (int i = 0; i < n; i++) any_contours = any_contours || specs[i].n_contours > 0;
+        if (any_contours) {
+            k_contours2d<<<n, 1024, 0, ctx->stream>>>(dcj, dout, doffs, dres);
+            ctx->launches++;
+        }
     }
     pt.end();
     CK2(cudaGetLastError());
@@ -510,7 +518,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         }
     }
     CK2(cudaStreamSynchronize(ctx->stream));
-    for (int k = 0; k < n; k++) res[order[k]].status = res_sorted[k].status;
+    for (int k = 0; k < n; k++) {
+        res[order[k]].status = res_sorted[k].status;
+        for (int c = 0; c < 4; c++) res[order[k]].levels[c] = res_sorted[k].levels[c];
+    }
     return 0;
 }
 

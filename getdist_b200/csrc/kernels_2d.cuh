@@ -393,6 +393,8 @@ struct ConvJob {
     int bounded;  // boundary correction active (has_prior && order >= 0)
     int bco, mbc;
     int xb, xt, yb, yt;
+    int nc, pad;
+    double contours[4];
 };
 
 // window: one CTA per job
@@ -717,4 +719,19 @@ __global__ void __launch_bounds__(256) k_finalize2d(const ConvJob* __restrict__ 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < gg; i += (size_t)gridDim.x * blockDim.x)
         o[i] = (mx != 0) ? P[i] / mx : P[i];
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(mx != 0)) res[blockIdx.y].status |= GDK_ST_ZERO_MAX;
+}
+
+// contour levels of the normalised output grids (densities.py:19-56).  grid (njobs), 1024 threads.
+__global__ void __launch_bounds__(1024) k_contours2d(const ConvJob* __restrict__ jobs, const double* __restrict__ out,
+                                                     const long long* __restrict__ offs, gdk_result2d* __restrict__ res) {
+    __shared__ double red[32];
+    const ConvJob jb = jobs[blockIdx.x];
+    if (jb.nc <= 0) return;
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    double lv[4] = {0, 0, 0, 0};
+    const unsigned outside = contour_levels_core(co, out + offs[blockIdx.x], jb.G, jb.contours, jb.nc, lv);
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 4; c++) res[blockIdx.x].levels[c] = lv[c];
+        if (outside) res[blockIdx.x].status |= GDK_ST_CONTOUR_RANGE;
+    }
 }

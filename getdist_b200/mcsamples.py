@@ -671,6 +671,10 @@ class MCSamples:
         j2, pary = self._parAndNumber(j2)
         if j is None or j2 is None:
             return None
+        ncontours = len(self.contours)
+        if num_plot_contours:
+            ncontours = min(num_plot_contours, ncontours)
+        want = [] if get_density else list(self.contours[:ncontours])
         density = None
         if not kwargs:
             cached = self._density2D.get((j, j2))
@@ -679,13 +683,16 @@ class MCSamples:
                 density = Density2D(cached.x, cached.y, cached.P.copy(), view_ranges=cached.view_ranges)
                 density._gdk = cached._gdk
         if density is None:
-            density = self._densities_2d([(j, j2)], **kwargs)[0]
+            density = self._densities_2d([(j, j2)], _contours=want, **kwargs)[0]
         if get_density:
             return density
-        ncontours = len(self.contours)
-        if num_plot_contours:
-            ncontours = min(num_plot_contours, ncontours)
-        density.contours = density.getContourLevels(self.contours[:ncontours])
+        dev = density._gdk.get("levels")
+        if dev is not None and len(dev[0]) >= len(want) and list(dev[0][:len(want)]) == want:
+            if density._gdk["status"] & _abi.ST_CONTOUR_RANGE:
+                raise DensitiesError("Contour level outside plotted ranges")
+            density.contours = np.array(dev[1][:len(want)])
+        else:
+            density.contours = density.getContourLevels(want)  # more than 4 contours: host numpy
         density.likes = None
         return density
 
@@ -785,11 +792,18 @@ class MCSamples:
                 sp.ry_fixed = smooth_scale_2D * fine_bins_2D / nbin2D
         return sp
 
-    def _densities_2d(self, pairs, _out=None, _device_ptr=None, **kwargs):
+    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, **kwargs):
         self._ensure_param_ranges([p for pr in pairs for p in pr])
         if float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D)) < 0:
             self._ensure_neff([p for pr in pairs for p in pr])
         specs = [self._spec_2d(j, j2, kwargs) for (j, j2) in pairs]
+        if _contours is None:
+            _contours = list(self.contours[:4])  # batched prefetch: the analysis-settings contours
+        conts = [float(c) for c in _contours[:4]] if len(_contours) <= 4 else []
+        for sp in specs:
+            sp.n_contours = len(conts)
+            for k, c in enumerate(conts):
+                sp.contours[k] = c
         buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
@@ -813,7 +827,8 @@ class MCSamples:
             d = Density2D(x, y, buf[off: off + G * G].reshape(G, G),
                           view_ranges=[(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
             d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
-                          n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G)
+                          n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G,
+                          levels=(conts, [r.levels[k] for k in range(len(conts))]) if conts else None)
             if not kwargs:
                 self._density2D[(j, j2)] = d
             out.append(d)

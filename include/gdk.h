@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct gdk_ctx gdk_ctx;
 
-#define GDK_ABI_VERSION 1
+#define GDK_ABI_VERSION 2
 
 /* error codes */
 #define GDK_OK 0
@@ -54,6 +54,7 @@ typedef struct gdk_ctx gdk_ctx;
 #define GDK_ST_AMISE_FULL 128u   /* 2D: 3-parameter AMISE minimum accepted (kde_bandwidth.py:292-304)            */
 #define GDK_ST_BIAS_NEG 256u     /* 2D: AMISE bias term negative at the closed-form h (reference raises)         */
 #define GDK_ST_NONFINITE 512u    /* a non-finite intermediate was met; treated as optimiser failure              */
+#define GDK_ST_CONTOUR_RANGE 1024u /* 2D: a contour level lies outside the plotted range (densities.py:50-51)     */
 
 /* 2D bandwidth branch (mcsamples.py:1347-1409) */
 #define GDK_BW2D_FIXED 0 /* smooth_scale_2D >= 0: rx, ry given in bins by the host       */
@@ -179,6 +180,10 @@ typedef struct gdk_spec2d {
     double r0, r1;
     double S00, S10, S11;              /* S * ichol[0,0], lower triangular                        */
     double p1_min, p1_max;             /* range of p1 (imin/imax or sample min/max +- 10%)        */
+    /* contour levels of the normalised grid (getContourLevels, densities.py:19-56; requested by
+     * get2DDensityGridData(get_density=False), mcsamples.py:1994-2002): probability fractions, 0..4 of them */
+    int32_t n_contours, pad2;
+    double contours[4];
 } gdk_spec2d;
 
 typedef struct gdk_result2d {
@@ -189,6 +194,7 @@ typedef struct gdk_result2d {
     uint32_t status;
     int32_t n_brent;    /* fixed-point evaluations used by Brent                                  */
     int32_t pad;
+    double levels[4];   /* density levels enclosing spec.contours[] of the probability            */
 } gdk_result2d;
 
 /* P_out: densities packed back to back; density i (G_i x G_i doubles, [y][x]) at P_out + offsets[i]. */

@@ -83,6 +83,9 @@ def run_case(name):
             out["d2/%s/%d_%d/P" % (tag, jx, jy)] = d.P[::st, ::st]
             out["d2/%s/%d_%d/xy" % (tag, jx, jy)] = np.array([d.x[0], d.x[-1], d.x.size, d.y[0], d.y[-1], d.y.size])
             out["d2/%s/%d_%d/h" % (tag, jx, jy)] = np.array(rec.get("h2d", (np.nan, np.nan, np.nan)), dtype=np.float64)
+            if not kw:
+                dc = mc.get2DDensityGridData(jx, jy, num_plot_contours=3)
+                out["d2/%s/%d_%d/contours" % (tag, jx, jy)] = np.asarray(dc.contours)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "ok", len(out), "arrays")
 

@@ -165,4 +165,9 @@ int hs_finish_bw2d(const gdk_spec2d* sp, const double* optv /*hx,hy,c,t_star*/, 
     finish_bandwidth_2d(*sp, &o, r2, res);
     return 0;
 }
+
+int hs_contours(const double* P, int G, const double* contours, int nc, double* levels) {
+    CoopHost co;
+    return (int)contour_levels_core(co, P, G, contours, nc, levels);
+}
 }

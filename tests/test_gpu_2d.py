@@ -103,6 +103,49 @@ def test_prefetch_triangle_matches_single_calls(gpu_objs):
     assert mc.get2DDensity("nope", names[0]) is None
 
 
+@pytest.mark.parametrize("name", ALL)
+def test_contour_levels(gpu_objs, name):
+    """get2DDensityGridData(get_density=False): density.contours from the device vs the reference's sorted-grid
+    interpolation (goldens), and vs the host implementation on the same grid"""
+    from getdist_b200.densities import getContourLevels
+
+    case, g, mc = gpu_objs(name)
+    for (jx, jy) in case["pairs"]:
+        d = mc.get2DDensityGridData(jx, jy, num_plot_contours=3)
+        ref = g["d2/default/%d_%d/contours" % (jx, jy)]
+        amise = bool(d._gdk["status"] & AMISE_BITS)
+        np.testing.assert_allclose(d.contours, ref, rtol=1e-4 if amise else 1e-7, atol=1e-12)
+        np.testing.assert_allclose(d.contours, getContourLevels(d.P, mc.contours[:3]), rtol=1e-9, atol=1e-14)
+        assert d.likes is None
+
+
+def test_edge_cases():
+    """tiny N, single parameter, zero weights, ragged chains, constant column, unknown names"""
+    from getdist_b200 import MCSamples, MCSamplesError
+    from oracle.getdist_oracle import OracleSamples
+
+    rng = np.random.default_rng(8)
+    # N = 200, P = 1
+    x = rng.normal(size=(200, 1))
+    mc = MCSamples(samples=x, names=["x"], sampler="uncorrelated")
+    o = OracleSamples(x, None, names=["x"])
+    assert np.max(np.abs(mc.get1DDensity("x").P - o.density_1d(0).P)) < 1e-9
+    # weights with zeros, ragged list of chains
+    chains = [rng.normal(size=(n, 2)) * [1.0, 3.0] for n in (301, 150, 777)]
+    ws = [rng.integers(0, 3, c.shape[0]).astype(float) for c in chains]
+    mc = MCSamples(samples=chains, weights=ws, names=["u", "v"], sampler="uncorrelated")
+    o = OracleSamples(chains, ws, names=["u", "v"])
+    np.testing.assert_allclose(mc.getMeans(), o.get_means(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(mc.getGelmanRubin(), o.get_gelman_rubin(), rtol=1e-9)
+    assert np.max(np.abs(mc.get2DDensity("u", "v").P - o.density_2d(0, 1).P)) < 1e-6
+    # constant column: "Parameter range is <= 0" (mcsamples.py:1549-1550)
+    y = np.stack([rng.normal(size=500), np.full(500, 2.5)], axis=1)
+    mc = MCSamples(samples=y, names=["a", "k"], sampler="uncorrelated")
+    with pytest.raises(MCSamplesError):
+        mc.get1DDensity("k")
+    assert mc.get1DDensity("missing") is None
+
+
 def test_repeatable(gpu_objs):
     """integer accumulation of fixed-point weights: histograms and densities are bit-reproducible"""
     case, g, mc = gpu_objs("mix3")

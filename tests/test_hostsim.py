@@ -190,3 +190,21 @@ def test_bw2d_core_vs_oracle(hs, name, jx, jy, G):
     rtol = 3e-4 if tnc else 1e-9
     np.testing.assert_allclose(out[:2], [hx, hy], rtol=rtol)
     np.testing.assert_allclose(out[2], c, rtol=1e-12, atol=1e-15)
+
+
+def test_contour_levels_core(hs):
+    """device contour-level bisection vs the sort-based getContourLevels of the reference (golden 2D grids)"""
+    from getdist_b200.densities import getContourLevels
+
+    conts = np.array([0.68, 0.95, 0.99])
+    for name in ["mix3", "bounded", "chains"]:
+        case, g = load_case(name)
+        for (jx, jy) in case["pairs"]:
+            P = np.ascontiguousarray(g["d2/default/%d_%d/P" % (jx, jy)])
+            if P.shape[0] != 256:
+                continue
+            ref = getContourLevels(P, conts)
+            lv = np.zeros(4)
+            out = hs.hs_contours(dptr(P), P.shape[0], dptr(conts), 3, dptr(lv))
+            assert out == 0
+            np.testing.assert_allclose(lv[:3], ref, rtol=1e-9, atol=1e-14)
