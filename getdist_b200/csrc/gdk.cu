@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -118,6 +119,13 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem = (int)prop.sharedMemPerBlockOptin;
+    {
+        int cl = 0;
+        cudaDeviceGetAttribute(&cl, cudaDevAttrClusterLaunch, device);
+        ctx->cluster_ok = cl != 0 && prop.major >= 9;
+        const char* eb = getenv("GDK_BANDS");
+        ctx->use_bands = eb && eb[0] == '1';
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -504,7 +512,7 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     }
     // pass 1: shared histogram per parameter
     CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B1 * 8, ctx->stream));
-    k_qhist<<<g, 256, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
+    k_qhist<<<g, 1024, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
                                                  ctx->qhist.p, dqbase);
     k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B1, 1, 0, B2_LOG2, ctx->qhist.p);
     ctx->launches += 2;

@@ -2,6 +2,8 @@
 // Included by gdk.cu.  Per chunk of pairs: histograms (tiled global reductions) -> sheared re-binning ->
 // transforms -> bandwidth -> window/mask maps/convolutions/corrections -> max-normalised output.
 #pragma once
+#include <stdlib.h>
+
 #include <algorithm>
 #include <map>
 #include <set>
@@ -80,11 +82,27 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     CK2(cudaMemsetAsync(ctx->gbins2.p, 0, gtot * 8, ctx->stream));
     if (rtot) CK2(cudaMemsetAsync(ctx->gbins_rot.p, 0, rtot * 8, ctx->stream));
 
+    // ---------------- shared-memory privatised path for the 256 x 256 grids ----------------
+    std::vector<char> in_bands(n, 0);
+    std::vector<int> band_pairs;
+    {
+        // Opt-in (GDK_BANDS=1 at context creation).  Measured on B200 at C2 (profiles/README.md, r1h): 218 ms vs
+        // 103 ms for the tiled REDG kernel -- with 128 KB of exact 64-bit bins per CTA the multicast ring is only
+        // 80 KB deep, so the stream is bound by the issue->consume->remote-arrive round trip, not by atomics.
+        const size_t band_smem = (size_t)2 * 64 * 256 * 4 + (size_t)HB_STAGES * HB_CHUNK * 10;
+        if (ctx->use_bands && ctx->cluster_ok && ctx->N >= (1 << 17) && band_smem + 1024 <= (size_t)ctx->max_smem)
+            for (int i = 0; i < n; i++)
+                if (specs[i].fine_bins == 256) {
+                    in_bands[i] = 1;
+                    band_pairs.push_back(i);
+                }
+    }
     // ---------------- histogram tiles, grouped by grid size ----------------
     std::vector<Tile2d> tiles;
     {
         std::map<int, std::vector<int>> byG;
-        for (int i = 0; i < n; i++) byG[specs[i].fine_bins].push_back(i);
+        for (int i = 0; i < n; i++)
+            if (!in_bands[i]) byG[specs[i].fine_bins].push_back(i);
         for (auto& kv : byG) {
             const int G = kv.first;
             std::vector<int> A, B;
@@ -164,20 +182,71 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (rc) return rc;
     const int ntiles = (int)tiles.size();
     {
-        // Row segments are the FAST grid index: all CTAs resident at one time (~5 per SM) then work on one or
-        // two tiles, whose <= 64 grids (32 MB at 256^2) stay L2-resident for the reductions.  With few segments
-        // per tile the resident CTAs span many tiles and every REDG misses L2 (profiles/r1a: 437 GB of DRAM
-        // traffic for 2e10 updates).
-        const int64_t want = (int64_t)ctx->num_sms * 6;
-        const int64_t seglen = std::max<int64_t>(1 << 12, (ctx->N + want - 1) / want);
-        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
-        rc = gdk_upload_segs(ctx, segs, ctx->segs);
-        if (rc) return rc;
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_HIST2D);
-        dim3 g((unsigned)segs.size(), (unsigned)ntiles);
-        k_hist2d_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dtiles, ctx->gbins2.p);
-        ctx->launches++;
+        if (!band_pairs.empty()) {
+            // byte bin indices per parameter (geometry of a parameter is the same in every 256^2 pair)
+            std::map<int, int> slot;
+            std::vector<Bin8Job> bj;
+            auto add = [&](int p, double lo, double hi) {
+                if (slot.count(p)) return;
+                const double fw = (hi - lo) / 255.0;
+                slot[p] = (int)bj.size();
+                bj.push_back(Bin8Job{p, 0, lo, fw, 1.0 / fw});
+            };
+            for (int i : band_pairs) {
+                add(specs[i].px, specs[i].xbinmin, specs[i].xbinmax);
+                add(specs[i].py, specs[i].ybinmin, specs[i].ybinmax);
+            }
+            // a parameter must have ONE geometry across the batch; otherwise route the odd pairs through the tiles
+            bool consistent = true;
+            for (int i : band_pairs) {
+                const Bin8Job& a = bj[slot[specs[i].px]];
+                const Bin8Job& b = bj[slot[specs[i].py]];
+                if (a.binmin != specs[i].xbinmin || a.fw != (specs[i].xbinmax - specs[i].xbinmin) / 255.0 ||
+                    b.binmin != specs[i].ybinmin || b.fw != (specs[i].ybinmax - specs[i].ybinmin) / 255.0)
+                    consistent = false;
+            }
+            if (!consistent) return gdk_fail(ctx, GDK_ERR_ARG, "inconsistent grid geometry for one parameter within a batch");
+            const int np8 = (int)bj.size();
+            if (ctx->ix8.ensure((size_t)np8 * ctx->ld)) return gdk_fail(ctx, GDK_ERR_NOMEM, "byte bin indices");
+            Bin8Job* dbj = nullptr;
+            rc = upload_vec(ctx, bj, ctx->bytes2d_b, &dbj);
+            if (rc) return rc;
+            const int64_t want8 = std::max<int64_t>(1, (int64_t)ctx->num_sms * 16 / np8);
+            std::vector<Seg> segs8 = gdk_make_segments(ctx, std::max<int64_t>(1 << 14, (ctx->N + want8 - 1) / want8));
+            rc = gdk_upload_segs(ctx, segs8, ctx->segs);
+            if (rc) return rc;
+            dim3 g8((unsigned)segs8.size(), (unsigned)np8);
+            k_bin8<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld);
+            std::vector<BandJob> jobs(band_pairs.size());
+            for (size_t k = 0; k < band_pairs.size(); k++) {
+                const int i = band_pairs[k];
+                jobs[k] = BandJob{ctx->ix8.p + (size_t)slot[specs[i].px] * ctx->ld, ctx->ix8.p + (size_t)slot[specs[i].py] * ctx->ld,
+                                  ctx->gbins2.p + goff[i]};
+            }
+            BandJob* dband = nullptr;
+            rc = upload_vec(ctx, jobs, ctx->bytes2d_d, &dband);
+            if (rc) return rc;
+            const size_t band_smem = (size_t)2 * 64 * 256 * 4 + (size_t)HB_STAGES * HB_CHUNK * 10;
+            CK2(cudaFuncSetAttribute(k_hist2d_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem));
+            k_hist2d_bands<<<(unsigned)(4 * jobs.size()), HB_THREADS, band_smem, ctx->stream>>>(dband, ctx->dWq.p, ctx->N);
+            ctx->launches += 2;
+        }
+        if (ntiles) {
+            // Row segments are the FAST grid index: all CTAs resident at one time (~5 per SM) then work on one or
+            // two tiles, whose <= 64 grids (32 MB at 256^2) stay L2-resident for the reductions.  With few segments
+            // per tile the resident CTAs span many tiles and every REDG misses L2 (profiles/r1a: 437 GB of DRAM
+            // traffic for 2e10 updates).
+            const int64_t want = (int64_t)ctx->num_sms * 6;
+            const int64_t seglen = std::max<int64_t>(1 << 12, (ctx->N + want - 1) / want);
+            std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+            rc = gdk_upload_segs(ctx, segs, ctx->segs);
+            if (rc) return rc;
+            dim3 g((unsigned)segs.size(), (unsigned)ntiles);
+            k_hist2d_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dtiles, ctx->gbins2.p);
+            ctx->launches++;
+        }
         pt.end();
         CK2(cudaGetLastError());
     }

@@ -96,6 +96,8 @@ struct gdk_ctx {
     DevBuf<Kde1dTables> tabs1d;
     DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena, qbase;
     Kde2dConsts k2d;
+    DevBuf<unsigned char> ix8;
+    bool cluster_ok = false, use_bands = false;
     DevBuf<cplx> cwork2d;
 };
 

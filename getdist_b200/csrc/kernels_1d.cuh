@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) k_hist1d_tma(const double* __restrict__ d
     if (threadIdx.x == 0)
         for (int c = 0; c < H1_STAGES && c < nchunks; c++) issue(c);
     const unsigned fmask = (1u << jb.sh) - 1u;
+    const double kscale = jb.inv_width * jb.scale, khalf = 0.5 * jb.scale;
     for (int c = 0; c < nchunks; c++) {
         const int s = c % H1_STAGES;
         const unsigned ph = (unsigned)((c / H1_STAGES) & 1);
@@ -206,15 +207,13 @@ __global__ void __launch_bounds__(256) k_hist1d_tma(const double* __restrict__ d
                 const double xe = e ? xv[k].y : xv[k].x;
                 const unsigned long long we = e ? wv[k].y : wv[k].x;
                 const double d = __dsub_rn(xe, jb.binmin);
-                const double t = fma(d, jb.inv_width * jb.scale, 0.5 * jb.scale);
-                unsigned b;
+                const double t = fma(d, kscale, khalf);
+                // the conversion saturates: t < 0 -> 0 (fraction 0) and t >= 2^32 -> 0xffffffff (fraction all ones);
+                // both fail the fraction test below and take the exact path, so no separate range test is needed
                 const unsigned I = __double2uint_rd(t);
                 const unsigned fr = I & fmask;
-                if (t >= 0.0 && t < 4294967040.0 && (fr - 8u) < (fmask - 15u)) {
-                    b = I >> jb.sh;
-                } else {
-                    b = (unsigned)(int)__dadd_rn(__ddiv_rn(d, jb.fine_width), 0.5);
-                }
+                unsigned b = I >> jb.sh;
+                if ((fr - 8u) >= (fmask - 15u)) b = (unsigned)(int)__dadd_rn(__ddiv_rn(d, jb.fine_width), 0.5);
                 if (b < (unsigned)F) smem_add_u64(hlo + b, hhi + b, we);
             }
         }

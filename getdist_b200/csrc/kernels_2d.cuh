@@ -735,3 +735,160 @@ __global__ void __launch_bounds__(1024) k_contours2d(const ConvJob* __restrict__
         if (outside) res[blockIdx.x].status |= GDK_ST_CONTOUR_RANGE;
     }
 }
+
+// ----------------------------------------------------------------------------------------------------
+// shared-memory privatised 2D histograms for the common 256 x 256 grids
+// ----------------------------------------------------------------------------------------------------
+// k_bin8: per-parameter bin indices as bytes (the 2D grid geometry of a parameter does not depend on its
+// partner, mcsamples.py:1821-1822), so the pair sweeps below read 1 byte per coordinate instead of 8.
+// grid (nseg, nparams), 256 threads.
+struct Bin8Job {
+    int param, pad;
+    double binmin, fw, inv;
+};
+__global__ void __launch_bounds__(256) k_bin8(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
+                                              const Bin8Job* __restrict__ jobs, unsigned char* __restrict__ out, int64_t old) {
+    const Bin8Job jb = jobs[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const double* x = dX + (int64_t)jb.param * ld;
+    unsigned char* o = out + (int64_t)blockIdx.y * old;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const int b = bin_index_round(ldg_stream(x + r), jb.binmin, jb.fw, jb.inv);
+        o[r] = (unsigned char)(b < 0 ? 0 : (b > 255 ? 255 : b));
+    }
+}
+
+// k_hist2d_bands: one CLUSTER of 4 CTAs per parameter pair.  CTA `rank` owns the rows y with (y & 3) == rank of
+// the 256 x 256 grid: 64 x 256 bins x two 32-bit limbs = 128 KB of shared memory, updated with native ATOMS.ADD
+// (no L2 atomics: profiles/r1g shows the tiled REDG kernel at 81 % of L2 throughput).  The pre-binned sample
+// stream (x byte, y byte, 64-bit fixed-point weight) is fetched ONCE per cluster: the leader CTA issues TMA bulk
+// copies with .multicast::cluster into a 2-stage ring at the same shared-memory offsets of all four CTAs, each
+// CTA's own `full` mbarrier receives the transaction bytes; when a CTA has consumed a stage it arrives (remote,
+// release.cluster) on the leader's `empty` barrier.  Every CTA tests all samples of the stream (cheap byte test)
+// and accumulates the quarter that falls in its rows; at the end it writes its rows of the grid with plain
+// stores -- it is their only writer.
+#define HB_CHUNK 4096
+#define HB_STAGES 2
+#define HB_THREADS 512
+struct BandJob {
+    const unsigned char* ia;   // x bins, N bytes
+    const unsigned char* ib;   // y bins
+    unsigned long long* grid;  // 256 x 256, [y][x], fixed point
+};
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar,
+                                               unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long* local_bar, unsigned target_rank) {
+    unsigned raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"((unsigned)__cvta_generic_to_shared(local_bar)), "r"(target_rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(HB_THREADS, 1)
+    k_hist2d_bands(const BandJob* __restrict__ jobs, const unsigned long long* __restrict__ dWq, int64_t N) {
+    extern __shared__ __align__(128) unsigned char bsm2[];
+    __shared__ __align__(8) unsigned long long full[HB_STAGES], empty[HB_STAGES];
+    const unsigned rank = cluster_ctarank();
+    const BandJob jb = jobs[blockIdx.x >> 2];
+    unsigned* hlo = reinterpret_cast<unsigned*>(bsm2);  // [64][256]
+    unsigned* hhi = hlo + 64 * 256;
+    unsigned char* stage0 = bsm2 + 2 * 64 * 256 * 4;
+    const size_t stage_bytes = (size_t)HB_CHUNK * 10;  // x bytes | y bytes | weights
+    for (int i = threadIdx.x; i < 2 * 64 * 256; i += blockDim.x) hlo[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HB_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();  // every CTA's barriers exist before any multicast or remote arrive
+    const int nchunks = (int)((N + HB_CHUNK - 1) / HB_CHUNK);
+    auto chunk_cnt = [&](int c) { return (int)min((int64_t)HB_CHUNK, N - (int64_t)c * HB_CHUNK); };
+    auto chunk_bytes = [&](int c) {
+        const unsigned cnt = (unsigned)chunk_cnt(c);
+        const unsigned b1 = (cnt + 15u) & ~15u;  // byte streams, padded to 16 (arrays are padded)
+        return 2u * b1 + ((cnt + 1u) & ~1u) * 8u;
+    };
+    auto issue = [&](int c) {  // leader only
+        const int s = c % HB_STAGES;
+        const unsigned cnt = (unsigned)chunk_cnt(c);
+        const unsigned b1 = (cnt + 15u) & ~15u;
+        const int64_t off = (int64_t)c * HB_CHUNK;
+        unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        bulk_g2s_mcast(st, jb.ia + off, b1, &full[s], (unsigned short)0xF);
+        bulk_g2s_mcast(st + HB_CHUNK, jb.ib + off, b1, &full[s], (unsigned short)0xF);
+        bulk_g2s_mcast(st + 2 * HB_CHUNK, dWq + off, ((cnt + 1u) & ~1u) * 8u, &full[s], (unsigned short)0xF);
+    };
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < HB_STAGES && c < nchunks; c++) mbar_expect_tx(&full[c % HB_STAGES], chunk_bytes(c));
+        if (rank == 0)
+            for (int c = 0; c < HB_STAGES && c < nchunks; c++) issue(c);
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c % HB_STAGES;
+        const unsigned ph = (unsigned)((c / HB_STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        const int cnt = chunk_cnt(c);
+        const unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        const uint2* pa = reinterpret_cast<const uint2*>(st);
+        const uint2* pb = reinterpret_cast<const uint2*>(st + HB_CHUNK);
+        const unsigned long long* pw = reinterpret_cast<const unsigned long long*>(st + 2 * HB_CHUNK);
+        // 512 threads x 8 consecutive rows = one chunk
+        const int r0 = threadIdx.x * 8;
+        if (r0 < cnt) {
+            const uint2 a8 = pa[threadIdx.x], b8 = pb[threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned a = ((k < 4 ? a8.x : a8.y) >> (8 * (k & 3))) & 0xffu;
+                const unsigned b = ((k < 4 ? b8.x : b8.y) >> (8 * (k & 3))) & 0xffu;
+                if ((b & 3u) == rank && r0 + k < cnt) {
+                    const unsigned bin = ((b >> 2) << 8) | a;
+                    smem_add_u64(hlo + bin, hhi + bin, pw[r0 + k]);
+                }
+            }
+        }
+        __syncthreads();  // everyone is done reading this stage
+        if (threadIdx.x == 0) {
+            mbar_arrive_remote(&empty[s], 0);  // tell the leader
+            if (c + HB_STAGES < nchunks) mbar_expect_tx(&full[s], chunk_bytes(c + HB_STAGES));
+            if (rank == 0 && c + HB_STAGES < nchunks) {
+                mbar_wait_cluster(&empty[s], ph);
+                issue(c + HB_STAGES);
+            }
+        }
+    }
+    __syncthreads();
+    // write this CTA's rows (y = 4*row + rank)
+    for (int i = threadIdx.x; i < 64 * 256; i += blockDim.x) {
+        const int row = i >> 8, col = i & 255;
+        jb.grid[(size_t)(row * 4 + rank) * 256 + col] = ((unsigned long long)hhi[i] << 32) | hlo[i];
+    }
+    cluster_sync_all();  // nobody exits while a peer may still signal its barriers
+}
