@@ -523,8 +523,17 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             b = e;
         }
     }
-    auto conv_smem = [](int wmax) { return ((size_t)(CV_TY + CV_KC - 1) * 8 * cv_q(wmax) + (size_t)CV_KC * cv_kp(wmax)) * 8; };
-    const size_t smem_max = conv_smem(wmax_all);
+    // kernel rows per shared-memory chunk: as many as fit a per-mode budget (fewer refills of the input tile)
+    auto conv_smem = [](int wmax, int kc) { return ((size_t)(CV_TY + kc - 1) * 8 * cv_q(wmax) + (size_t)kc * cv_kp(wmax)) * 8; };
+    auto pick_kc = [&](int wmax, size_t budget) {
+        int kc = 2 * wmax + 1;
+        while (kc > CV_KC && conv_smem(wmax, kc) > budget) kc--;
+        return std::max(kc, std::min(CV_KC, 2 * wmax + 1));
+    };
+    const size_t budget0 = std::min<size_t>(100 << 10, (size_t)ctx->max_smem - 4096), budget1 = std::min<size_t>(54 << 10, (size_t)ctx->max_smem - 4096);
+    size_t smem_max = 0;
+    for (const Grp& g : groups)
+        smem_max = std::max(smem_max, std::max(conv_smem(g.wmax, pick_kc(g.wmax, budget0)), conv_smem(g.wmax, pick_kc(g.wmax, budget1))));
     if (smem_max > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "window too large for the convolution kernel");
     CK2(cudaFuncSetAttribute(k_conv2d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     CK2(cudaFuncSetAttribute(k_conv2d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
@@ -538,12 +547,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
         const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
         dim3 gc((unsigned)tiles, (unsigned)nj);
-        k_conv2d<0><<<gc, 256, conv_smem(g.wmax), ctx->stream>>>(dcj + g.b, 0, g.wmax);
+        const int kc0 = pick_kc(g.wmax, budget0), kc1 = pick_kc(g.wmax, budget1);
+        k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
         dim3 gb(64, (unsigned)nj);
         k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
         ctx->launches += 4;
         for (int it = 0; it < max_mbc; it++) {
-            k_conv2d<1><<<gc, 256, conv_smem(g.wmax), ctx->stream>>>(dcj + g.b, it, g.wmax);
+            k_conv2d<1><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, it, g.wmax, kc1);
             ctx->launches++;
         }
     }

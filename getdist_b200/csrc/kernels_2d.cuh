@@ -443,7 +443,7 @@ __host__ __device__ __forceinline__ int cv_q(int wmax) {
 // coalesced fills.  Kernel rows are stored reversed and zero padded to a multiple of 8 taps; the window lives
 // in 16 registers that rotate through a fully unrolled block of 8 taps (one 8-byte load per tap per thread).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs, int iter, int wmax) {
+__global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs, int iter, int wmax, int kcmax) {
     extern __shared__ __align__(16) double csm[];
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     if (oy0 >= G) return;
     const int q = cv_q(wmax), pitch = 8 * q, kp = cv_kp(wmax);
     double* in_s = csm;
-    double* wk_s = csm + (size_t)(CV_TY + CV_KC - 1) * pitch;
+    double* wk_s = csm + (size_t)(CV_TY + kcmax - 1) * pitch;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const double* P = (MODE == 1) ? ((iter & 1) ? jb.Pn : jb.P) : nullptr;
     double* Pout = (MODE == 1) ? ((iter & 1) ? jb.P : jb.Pn) : jb.P;
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
 #pragma unroll
     for (int m = 0; m < CV_MX; m++) acc[m] = accx[m] = accy[m] = 0;
     const int ncol = CV_TX + Kp;  // columns b = ox0 - w + c, c < ncol (zero beyond the grid / beyond 2w)
-    for (int k0 = 0; k0 < K; k0 += CV_KC) {
-        const int kc = min(CV_KC, K - k0);
+    for (int k0 = 0; k0 < K; k0 += kcmax) {
+        const int kc = min(kcmax, K - k0);
         __syncthreads();
         // kernel chunk, columns reversed and zero padded: wk_s[kk][kr] = W[k0+kk][2w - kr] for kr < K, else 0
         for (int it = threadIdx.x; it < kc * kp; it += blockDim.x) {
