@@ -32,7 +32,8 @@ class Spec1D(C.Structure):
                 ("range_min", C.c_double), ("range_max", C.c_double), ("param_min", C.c_double),
                 ("param_max", C.c_double), ("sigma_range", C.c_double), ("err", C.c_double), ("neff", C.c_double),
                 ("smooth_scale_1D", C.c_double), ("width", C.c_double), ("boundary_correction_order", C.c_int32),
-                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32)]
+                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32),
+                ("periodic", C.c_int32), ("pad", C.c_int32)]
 
 
 class Result1D(C.Structure):
@@ -52,7 +53,8 @@ class Spec2D(C.Structure):
                 ("shear_i", C.c_int32), ("shear_j", C.c_int32), ("shear_swapped", C.c_int32),
                 ("r0", C.c_double), ("r1", C.c_double), ("S00", C.c_double), ("S10", C.c_double), ("S11", C.c_double),
                 ("p1_min", C.c_double), ("p1_max", C.c_double),
-                ("n_contours", C.c_int32), ("pad2", C.c_int32), ("contours", C.c_double * 4)]
+                ("n_contours", C.c_int32), ("pad2", C.c_int32), ("contours", C.c_double * 4),
+                ("x_periodic", C.c_int32), ("y_periodic", C.c_int32)]
 
 
 class Result2D(C.Structure):
@@ -119,7 +121,7 @@ def load():
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
     lib.gdk_hist2d_batch.restype = i32
-    if lib.gdk_abi_version() != 2:
+    if lib.gdk_abi_version() != 3:
         raise GdkError("libgdk.so ABI version mismatch")
     _lib = lib
     return lib

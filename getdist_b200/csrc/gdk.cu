@@ -504,11 +504,10 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     rc = gdk_upload_segs(ctx, segs, ctx->segs);
     if (rc) return rc;
     dim3 g((unsigned)segs.size(), (unsigned)np);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->q_attr_set) {
         CK(cudaFuncSetAttribute(k_qhist, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QMAXF * B2 * 4 + B1 * 4));
         CK(cudaFuncSetAttribute(k_qselect, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * QCAP * 8));
-        attr_set = true;
+        ctx->q_attr_set = true;
     }
     // pass 1: shared histogram per parameter
     CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B1 * 8, ctx->stream));
@@ -589,18 +588,16 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
         if (ctx->bytes2d.ensure((size_t)n * sizeof(Hist1dJobT))) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D job table");
         Hist1dJobT* djt = reinterpret_cast<Hist1dJobT*>(ctx->bytes2d.p);
         CK(cudaMemcpyAsync(djt, jt.data(), (size_t)n * sizeof(Hist1dJobT), cudaMemcpyHostToDevice, ctx->stream));
-        static size_t tma_set = 0;
-        if (smem_tma > tma_set) {
+        if (smem_tma > ctx->h1_tma_smem) {
             CK(cudaFuncSetAttribute(k_hist1d_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_tma, 48 * 1024)));
-            tma_set = std::max<size_t>(smem_tma, 48 * 1024);
+            ctx->h1_tma_smem = std::max<size_t>(smem_tma, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
         k_hist1d_tma<<<g, 256, smem_tma, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, djt, ctx->gbins.p, gstride);
     } else {
-        static int smem_set = 0;
-        if (maxF * 8 > smem_set) {
+        if ((size_t)maxF * 8 > ctx->h1_smem) {
             CK(cudaFuncSetAttribute(k_hist1d, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(maxF * 8, 48 * 1024)));
-            smem_set = std::max(maxF * 8, 48 * 1024);
+            ctx->h1_smem = (size_t)std::max(maxF * 8, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
         k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->jobs1d.p, ctx->gbins.p, gstride);
@@ -660,10 +657,9 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
     if (!use_smem && ctx->gwork.ensure((size_t)n * 9 * maxF)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D workspace");
     CK(cudaMemcpyAsync(ctx->specs1d.p, specs, n * sizeof(gdk_spec1d), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tabs1d.p, tabs.data(), n * sizeof(Kde1dTables), cudaMemcpyHostToDevice, ctx->stream));
-    static size_t smem_set = 0;
-    if (use_smem && smem_need > smem_set) {
+    if (use_smem && smem_need > ctx->kde1d_smem) {
         CK(cudaFuncSetAttribute(k_kde1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_need, 48 * 1024)));
-        smem_set = std::max<size_t>(smem_need, 48 * 1024);
+        ctx->kde1d_smem = std::max<size_t>(smem_need, 48 * 1024);
     }
     const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
     double* dP = dev_out ? P_out : ctx->fbuf.p;

@@ -436,6 +436,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (ctx->bytes2d_mx.ensure((size_t)n * 8 * 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "max buffer");
     CK2(cudaMemsetAsync(ctx->bytes2d_mx.p, 0, (size_t)n * 64, ctx->stream));
     int max_mbc = 0;
+    bool any_periodic = false;
     for (int i = 0; i < n; i++) {
         const gdk_spec2d& s = specs[i];
         const int G = s.fine_bins, w = res[i].winw, K = 2 * w + 1;
@@ -451,9 +452,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         c.ry = res[i].ry;
         c.c = res[i].c;
         if (s.bw_mode == GDK_BW2D_FIXED) c.c = s.kernel_corr;
-        c.bounded = (has_prior && s.boundary_correction_order >= 0) ? 1 : 0;
+        c.xper = s.x_periodic ? 1 : 0;
+        c.yper = s.y_periodic ? 1 : 0;
+        const bool both_per = c.xper && c.yper;  // mcsamples.py:1921, 1963: both blocks are skipped
+        c.bounded = (has_prior && s.boundary_correction_order >= 0 && !both_per) ? 1 : 0;
         c.bco = s.boundary_correction_order;
-        c.mbc = s.mult_bias_correction_order;
+        c.mbc = both_per ? 0 : s.mult_bias_correction_order;
+        any_periodic = any_periodic || c.xper || c.yper;
         c.nc = std::max(0, std::min(4, s.n_contours));
         for (int k = 0; k < 4; k++) c.contours[k] = s.contours[k];
         c.xb = s.x_has_bot;
@@ -549,12 +554,21 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         dim3 gc((unsigned)tiles, (unsigned)nj);
         const int kc0 = pick_kc(g.wmax, budget0), kc1 = pick_kc(g.wmax, budget1);
         k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
+        dim3 gcirc((unsigned)((g.Gmax * g.Gmax + 255) / 256), (unsigned)nj);
+        if (any_periodic) {
+            k_conv2d_circ<0><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            ctx->launches++;
+        }
         dim3 gb(64, (unsigned)nj);
         k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
         ctx->launches += 4;
         for (int it = 0; it < max_mbc; it++) {
             k_conv2d<1><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, it, g.wmax, kc1);
             ctx->launches++;
+            if (any_periodic) {
+                k_conv2d_circ<1><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, it);
+                ctx->launches++;
+            }
         }
     }
     // output

@@ -98,6 +98,9 @@ struct gdk_ctx {
     Kde2dConsts k2d;
     DevBuf<unsigned char> ix8;
     bool cluster_ok = false, use_bands = false;
+    // per-context (= per-device) record of opted-in dynamic shared-memory sizes
+    bool q_attr_set = false;
+    size_t h1_tma_smem = 0, h1_smem = 0, kde1d_smem = 0;
     DevBuf<cplx> cwork2d;
 };
 

@@ -82,6 +82,25 @@ GDK_HD void conv_same(const C& co, const double* x, const double* win, int w, in
     co.sync();
 }
 
+// circular convolution of convolve1D_periodic (convolve.py:326-367): the last bin is folded onto the first,
+// period F-1, centred kernel; the result is extended by its first element.
+template <class C>
+GDK_HD void conv_circ(const C& co, const double* x, const double* win, int w, int F, double* out) {
+    const int Nc = F - 1;
+    for (int i = co.tid; i < F; i += co.nt) {
+        const int ic = i == Nc ? 0 : i;
+        double acc = 0;
+        for (int u = -w; u <= w; u++) {
+            int s = (ic - u) % Nc;
+            if (s < 0) s += Nc;
+            const double v = x[s] + (s == 0 ? x[Nc] : 0.0);
+            acc += win[u + w] * v;
+        }
+        out[i] = acc;
+    }
+    co.sync();
+}
+
 template <class C>
 GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kde1dWork& W, double* P_out,
                        gdk_result1d* res) {
@@ -152,8 +171,10 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
     }
     if (smooth_1D < 2) status |= GDK_ST_SMALL_SMOOTH;
     smooth_1D = fmin(fmax(1.0, smooth_1D), (double)(F / 2));
+    const bool periodic = sp.periodic != 0;
     int winw = (int)rint(2.5 * smooth_1D);  // Python round(): half to even
-    if (winw > F / 2 - 2) winw = F / 2 - 2;
+    const int wcap = (periodic ? F - 1 : F) / 2 - 2;
+    if (winw > wcap) winw = wcap;
     const int w = winw;
 
     // ---- Kernel1D, mcsamples.py:129-135 ----------------------------------------------------------
@@ -171,7 +192,9 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
     const bool bot = sp.has_limits_bot != 0, top = sp.has_limits_top != 0;
     const int bco = sp.boundary_correction_order;
     // ---- P = bins (*) Win, plus the boundary-kernel moments in the same sweep ----------------------
-    if ((bot || top) && bco >= 0) {
+    if (periodic) {
+        conv_circ(co, W.bins, W.win, w, F, W.P);
+    } else if ((bot || top) && bco >= 0) {
         // prior mask of length F+2w: 0 outside the bounded side, 1/2 on the boundary bin, 1 inside.
         // 'valid' conv: a_r[i] = sum_u u^r win(u) mask[i + w - u];   'same' conv: xP, x2P on bins.
         for (int i = co.tid; i < F; i += co.nt) {
@@ -255,6 +278,12 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
             W.aux[i] = W.bins[i] / (p == 0 ? 1.0 : p);
         }
         co.sync();
+        if (periodic) {  // mcsamples.py:1663-1666: P *= circular conv, no normaliser
+            conv_circ(co, W.aux, W.win, w, F, W.aux2);
+            for (int i = co.tid; i < F; i += co.nt) W.P[i] = W.P[i] * W.aux2[i];
+            co.sync();
+            continue;
+        }
         for (int i = co.tid; i < F; i += co.nt) {
             const int ulo = (i - (F - 1) > -w) ? i - (F - 1) : -w;
             const int uhi = (i < w) ? i : w;

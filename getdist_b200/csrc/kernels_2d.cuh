@@ -395,6 +395,7 @@ struct ConvJob {
     int xb, xt, yb, yt;
     int nc, pad;
     double contours[4];
+    int xper, yper;  // periodic axes
 };
 
 // window: one CTA per job
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     extern __shared__ __align__(16) double csm[];
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
+    if (jb.xper | jb.yper) return;  // periodic pairs: k_conv2d_circ
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const int Kp = (K + 7) & ~7;
     const int tilesx = (G + CV_TX - 1) / CV_TX;
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(256) k_mask_T(const ConvJob* __restrict__ jobs
     const int ku = blockIdx.x;
     if (ku >= K || !jb.T) return;
     const double* wrow = jb.Wk + (size_t)ku * K;
-    const int eb = jb.bounded ? jb.xb : 0, et = jb.bounded ? jb.xt : 0;
+    const int eb = (jb.bounded && !jb.xper) ? jb.xb : 0, et = (jb.bounded && !jb.xper) ? jb.xt : 0;
     for (int x = threadIdx.x; x < G; x += blockDim.x) {
         double t0 = 0, t1 = 0, t2 = 0, tb = 0;
         for (int kv = 0; kv < K; kv++) {
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(256) k_mask_T(const ConvJob* __restrict__ jobs
             t0 += wv * m;
             t1 += wx * m;
             t2 += (wx * (double)v) * m;
-            const double mb = (s < 0 || s > G - 1) ? 0.0 : m;
+            const double mb = (!jb.xper && (s < 0 || s > G - 1)) ? 0.0 : m;
             tb += wv * mb;
         }
         const size_t base = ((size_t)ku) * G + x;
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ j
     if (!jb.T) return;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= G) return;
-    const int eb = jb.bounded ? jb.yb : 0, et = jb.bounded ? jb.yt : 0;
+    const int eb = (jb.bounded && !jb.yper) ? jb.yb : 0, et = (jb.bounded && !jb.yper) ? jb.yt : 0;
     const double* T0 = jb.T + x;
     const double* T1 = jb.T + plane + x;
     const double* T2 = jb.T + 2 * plane + x;
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ j
             for (int u = ulo; u <= uhi; u++) {
                 const int sidx = y - u;
                 const double m = mask1d(sidx, G, eb, et);
-                const double mb = (sidx < 0 || sidx > G - 1) ? 0.0 : m;
+                const double mb = (!jb.yper && (sidx < 0 || sidx > G - 1)) ? 0.0 : m;
                 const size_t o = (size_t)(u + w) * G;
                 ab += (mb - 1.0) * T3[o];
                 if (jb.bounded && m != 1.0) {
@@ -891,4 +893,76 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(HB_THREADS, 1)
         jb.grid[(size_t)(row * 4 + rank) * 256 + col] = ((unsigned long long)hhi[i] << 32) | hlo[i];
     }
     cluster_sync_all();  // nobody exits while a peer may still signal its barriers
+}
+
+// Circular convolution for pairs with a periodic axis (convolve2D_periodic, convolve.py:215-323): the last
+// row/column of a periodic axis is folded onto the first (period G-1); the reference's FFT has the size of the
+// folded array in BOTH axes, so the non-periodic axis wraps as well (period G) -- reproduced here.  Rare path:
+// one thread per output pixel, inputs through L2.  Same MODE semantics as k_conv2d.  grid (ceil(G*G/256), njobs).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__ jobs, int iter) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (MODE == 1 && iter >= jb.mbc) return;
+    if (!(jb.xper | jb.yper)) return;
+    const int G = jb.G, w = jb.w, K = 2 * w + 1;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    double tmax = 0;
+    if (o < G * G) {
+        const int y = o / G, x = o - y * G;
+        const int Ny = jb.yper ? G - 1 : G, Nx = jb.xper ? G - 1 : G;
+        const int yc = y % Ny, xc = x % Nx;
+        const double* P = (MODE == 1) ? ((iter & 1) ? jb.Pn : jb.P) : nullptr;
+        double* Pout = (MODE == 1) ? ((iter & 1) ? jb.P : jb.Pn) : jb.P;
+        double thr = 0;
+        if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
+        const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
+        auto src = [&](int a, int b) {  // unfolded source element
+            double v = jb.hist[(size_t)a * G + b];
+            if (MODE == 1) {
+                const double p = P[(size_t)a * G + b];
+                if (p > thr) v = v / p;
+            }
+            return v;
+        };
+        auto folded = [&](int a, int b) {  // element (a, b) of the folded array
+            double v = src(a, b);
+            const bool fy = jb.yper && a == 0, fx = jb.xper && b == 0;
+            if (fy) v += src(G - 1, b);
+            if (fx) v += src(a, G - 1);
+            if (fy && fx) v += src(G - 1, G - 1);
+            return v;
+        };
+        double acc = 0, accx = 0, accy = 0;
+        for (int ku = 0; ku < K; ku++) {
+            const int u = ku - w;
+            int a = (yc - u) % Ny;
+            if (a < 0) a += Ny;
+            for (int kv = 0; kv < K; kv++) {
+                const int v = kv - w;
+                int b = (xc - v) % Nx;
+                if (b < 0) b += Nx;
+                const double wv = jb.Wk[(size_t)ku * K + kv];
+                const double c = folded(a, b);
+                acc = fma(wv, c, acc);
+                if (moments) {
+                    accx = fma(wv * (double)v, c, accx);
+                    accy = fma(wv * (double)u, c, accy);
+                }
+            }
+        }
+        if (MODE == 0) {
+            jb.P[o] = acc;
+            if (moments) {
+                jb.xP[o] = accx;
+                jb.yP[o] = accy;
+            }
+            tmax = acc;
+        } else {
+            const double vv = P[o] * acc / jb.a00b[o];
+            Pout[o] = vv;
+            tmax = vv;
+        }
+    }
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
 }

@@ -14,7 +14,7 @@ Everything N-sized or grid-sized runs on the device through the C-ABI (getdist_b
 keeps only the scalar per-parameter logic (``_initParam`` limit tests, grid geometry, 2D branch selection and
 2x2 Cholesky algebra), settings handling, caching and error/warning behaviour.  There is no CPU fallback:
 options of the reference that the device path does not implement yet raise ``NotImplementedError``
-(meanlikes, mask_function, periodic parameters -- SURVEY.md s8f).
+(meanlikes, mask_function -- SURVEY.md s8f).
 
 ``prefetch_triangle`` computes all 1D and 2D densities of a parameter list in batched launches and fills the
 caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by getdist.plots) then hit.
@@ -114,8 +114,12 @@ class ParamBounds:
             self.lower[name] = float(lo)
         if hi is not None and not (isinstance(hi, str) and hi == "N"):
             self.upper[name] = float(hi)
-        if len(r) > 2 and r[2]:
-            self.periodic.add(name)
+        if len(r) > 2:
+            periodic = r[2]
+            if periodic is True or isinstance(periodic, str) and periodic.upper() in ["T", "TRUE", "PERIODIC"]:
+                if name not in self.upper or name not in self.lower:
+                    raise ValueError("Periodic parameter must have lower and upper bound: %s" % name)
+                self.periodic.add(name)
 
     def getLower(self, name):
         return self.lower.get(name)
@@ -183,6 +187,34 @@ class MCSamples:
         else:
             self.norm = None
         self.updateBaseStatistics()
+
+    # ------------------------------------------------------------------ pickling / copying
+    def __getstate__(self):
+        """Picklable / deep-copyable like the reference object (mcsamples.py:125, 316): the device context is not
+        part of the state; it is re-created and the samples re-uploaded lazily on first use after loading."""
+        d = self.__dict__.copy()
+        d["_device"] = self._ctx.device
+        d.pop("_ctx", None)
+        d["_device_valid"] = False
+        return d
+
+    def __setstate__(self, d):
+        device = d.pop("_device", 0)
+        self.__dict__.update(d)
+        self._ctx = _abi.Context(device)
+        self._device_valid = False
+        self.needs_update = True
+
+    def copy(self, label=None, settings=None):
+        """mcsamples.py:316-322."""
+        import copy as _copy
+
+        new = _copy.deepcopy(self)
+        if label is not None:
+            new.label = label
+        if settings:
+            new.updateSettings(settings)
+        return new
 
     # ------------------------------------------------------------------ settings
     def updateSettings(self, settings=None, ini=None, doUpdate=True):
@@ -593,8 +625,6 @@ class MCSamples:
 
     def _spec_1d(self, j, kwargs):
         par = self.paramNames.names[j]
-        if par.periodic:
-            raise NotImplementedError("periodic parameters are not on the device path yet (SURVEY.md s8f-3)")
         num_bins = kwargs.get("num_bins", self.num_bins)
         smooth_scale_1D = kwargs.get("smooth_scale_1D", self.smooth_scale_1D)
         bco = kwargs.get("boundary_correction_order", self.boundary_correction_order)
@@ -603,14 +633,14 @@ class MCSamples:
         paramrange = par.range_max - par.range_min
         if paramrange <= 0:
             raise MCSamplesError("Parameter range is <= 0: " + par.name)
-        if par.has_limits and bco > 2:
+        if par.has_limits and not par.periodic and bco > 2:
             raise SettingError("Unknown boundary_correction_order (expected 0, 1, 2)")
         width = paramrange / (num_bins - 1)
         binmin, binmax = self._bin_geometry(par, fine_bins)
         neff = self._get1DNeff(par, j) if smooth_scale_1D <= 0 else 1.0
         return _abi.Spec1D(j, fine_bins, binmin, binmax, par.range_min, par.range_max, par.param_min, par.param_max,
                            par.sigma_range, par.err, neff, float(smooth_scale_1D), width, int(bco), int(mbc),
-                           int(par.has_limits_bot), int(par.has_limits_top))
+                           int(par.has_limits_bot), int(par.has_limits_top), int(par.periodic), 0)
 
     def _densities_1d(self, indices, meanlikes=False, _out=None, _device_ptr=None, **kwargs):
         if meanlikes:
@@ -698,8 +728,6 @@ class MCSamples:
 
     def _spec_2d(self, j, j2, kwargs):
         parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
-        if parx.periodic or pary.periodic:
-            raise NotImplementedError("periodic parameters are not on the device path yet (SURVEY.md s8f-3)")
         base_fine_bins_2D = int(kwargs.get("fine_bins_2D", self.fine_bins_2D))
         bco = kwargs.get("boundary_correction_order", self.boundary_correction_order)
         mbc = kwargs.get("mult_bias_correction_order", self.mult_bias_correction_order)
@@ -714,7 +742,7 @@ class MCSamples:
             raise SettingError("max_corr_2D cannot be >=1")
         if abs(corr) < 0.1:
             corr = 0.0
-        if has_prior and bco > 1:
+        if has_prior and bco > 1 and not (parx.periodic and pary.periodic):
             raise SettingError("unknown boundary_correction_order (expected 0 or 1)")
         angle_scale = max(0.2, np.sqrt(1 - min(self.max_corr_2D, abs(corr)) ** 2))
         nbin2D = int(round(self.num_bins_2D / angle_scale))
@@ -741,6 +769,7 @@ class MCSamples:
         sp.mult_bias_correction_order = int(mbc)
         sp.x_has_bot, sp.x_has_top = int(parx.has_limits_bot), int(parx.has_limits_top)
         sp.y_has_bot, sp.y_has_top = int(pary.has_limits_bot), int(pary.has_limits_top)
+        sp.x_periodic, sp.y_periodic = int(parx.periodic), int(pary.periodic)
         sp.neff = 1.0
         if smooth_scale_2D < 0:
             # branch selection of getAutoBandwidth2D, mcsamples.py:1325-1409

@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct gdk_ctx gdk_ctx;
 
-#define GDK_ABI_VERSION 2
+#define GDK_ABI_VERSION 3
 
 /* error codes */
 #define GDK_OK 0
@@ -133,6 +133,8 @@ typedef struct gdk_spec1d {
     int32_t boundary_correction_order; /* -1 off, 0, 1, 2                                         */
     int32_t mult_bias_correction_order;
     int32_t has_limits_bot, has_limits_top;
+    int32_t periodic, pad;             /* par.periodic: circular convolution (convolve.py:326-367), no boundary /
+                                          normaliser correction (mcsamples.py:1588-1666)            */
 } gdk_spec1d;
 
 typedef struct gdk_result1d {
@@ -184,6 +186,8 @@ typedef struct gdk_spec2d {
      * get2DDensityGridData(get_density=False), mcsamples.py:1994-2002): probability fractions, 0..4 of them */
     int32_t n_contours, pad2;
     double contours[4];
+    int32_t x_periodic, y_periodic;    /* periodic axes: convolve2D_periodic (convolve.py:215-323), masks only on the
+                                          non-periodic axes (mcsamples.py:1688-1712, 1874-1976)      */
 } gdk_spec2d;
 
 typedef struct gdk_result2d {

@@ -615,8 +615,55 @@ def conv1d(x, k, mode):
 
 
 def conv2d(x, k, mode):
-    """convolve.py:205-212, 405-436: FFT linear convolution, modes 'same' / 'valid'."""
+    """convolve.py:205-212, 405-436: FFT linear convolution, modes 'same' / 'valid'; periodic modes :215-323."""
+    if mode in ("periodic_both", "periodic_x", "periodic_y"):
+        return conv2d_periodic(x, k, periodic_x=mode != "periodic_y", periodic_y=mode != "periodic_x")
     return fftconvolve(x, k, mode)
+
+
+def conv1d_periodic(x, k):
+    """convolve.py:326-367: the last bin is folded onto the first, circular convolution of length n-1 with the
+    centred kernel, result extended by its first element."""
+    xc = x[:-1].copy()
+    xc[0] += x[-1]
+    N, M = xc.shape[0], k.shape[0]
+    hpad = np.zeros(N)
+    hpad[:M] = k
+    hpad = np.roll(hpad, -(M // 2))
+    res = np.fft.irfft(np.fft.rfft(xc) * np.fft.rfft(hpad), n=N)
+    return np.append(res, res[0])
+
+
+def conv2d_periodic(x, k, periodic_x=True, periodic_y=True):
+    """convolve.py:215-323.  NB the transform has the size of the folded array in BOTH axes, so the convolution
+    is circular along a non-periodic axis as well (as in the reference)."""
+    ny, nx = x.shape
+    ky, kx = k.shape
+    if periodic_x and periodic_y:
+        xc = x[:-1, :-1].copy()
+        xc[0, :] += x[-1, :-1]
+        xc[:, 0] += x[:-1, -1]
+        xc[0, 0] += x[-1, -1]
+    elif periodic_x:
+        xc = x[:, :-1].copy()
+        xc[:, 0] += x[:, -1]
+    else:
+        xc = x[:-1, :].copy()
+        xc[0, :] += x[-1, :]
+    Ny, Nx = xc.shape
+    hpad = np.zeros((Ny, Nx))
+    hpad[:ky, :kx] = k
+    hpad = np.roll(np.roll(hpad, -(ky // 2), axis=0), -(kx // 2), axis=1)
+    res = np.fft.irfftn(np.fft.rfftn(xc) * np.fft.rfftn(hpad), (Ny, Nx), axes=(0, 1))
+    out = np.empty((ny, nx))
+    out[:Ny, :Nx] = res
+    if periodic_y:
+        out[-1, :Nx] = res[0, :]
+    if periodic_x:
+        out[:Ny, -1] = res[:, 0]
+    if periodic_x and periodic_y:
+        out[-1, -1] = res[0, 0]
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -661,7 +708,9 @@ class OracleSamples:
         self.fullcov = None
         self.corrmat = None
         for par in self.pars:
-            lo, hi = self.ranges.get(par.name, (None, None))
+            rg = self.ranges.get(par.name, (None, None))
+            lo, hi = rg[0], rg[1]
+            par.periodic = len(rg) > 2 and (rg[2] is True or (isinstance(rg[2], str) and rg[2].upper() in ("T", "TRUE", "PERIODIC")))
             par.limmin, par.limmax = lo, hi
             par.has_limits_bot = lo is not None
             par.has_limits_top = hi is not None
@@ -765,13 +814,16 @@ class OracleSamples:
         if smooth_1D < 2:
             log.warning("fine_bins not large enough to well sample smoothing scale - " + par.name)
         smooth_1D = min(max(1.0, smooth_1D), fine_bins // 2)
-        winw = min(int(round(2.5 * smooth_1D)), fine_bins // 2 - 2)
+        winw = min(int(round(2.5 * smooth_1D)), ((fine_bins - 1) if par.periodic else fine_bins) // 2 - 2)
         kx = np.arange(-winw, winw + 1)
         Win = np.exp(-((kx / smooth_1D) ** 2) / 2.0)
         Win = Win / np.sum(Win)  # mcsamples.py:129-135
 
-        P = conv1d(bins, Win, "same")
-        if par.has_limits and boundary_correction_order >= 0:
+        def cconv(a):  # mcsamples.py:1592-1593: convolution mode follows the parameter
+            return conv1d_periodic(a, Win) if par.periodic else conv1d(a, Win, "same")
+
+        P = cconv(bins)
+        if par.has_limits and not par.periodic and boundary_correction_order >= 0:
             # mcsamples.py:1600-1637
             prior_mask = np.ones(fine_bins + 2 * winw)
             if par.has_limits_bot:
@@ -805,7 +857,7 @@ class OracleSamples:
                 P[sel] = normed * np.exp(np.minimum(corrected / normed, 4) - 1)
             else:
                 raise OracleSettingError("Unknown boundary_correction_order (expected 0, 1, 2)")
-        elif boundary_correction_order == 2:
+        elif not par.periodic and boundary_correction_order == 2:
             # mcsamples.py:1638-1647
             xWin2 = Win * kx**2
             x2P = conv1d(bins, xWin2, "same")
@@ -827,9 +879,10 @@ class OracleSamples:
                 prob1 = P.copy()
                 prob1[prob1 == 0] = 1
                 fine = bins / prob1
-                conv = conv1d(fine, Win, "same")
+                conv = cconv(fine)
                 P = P * conv
-                P /= a0
+                if not par.periodic:
+                    P /= a0
         mx = np.max(P)
         if mx == 0:
             raise OracleDensityError("no samples in bin")
@@ -980,24 +1033,35 @@ class OracleSamples:
         Win = np.exp(-(ix1**2 * Cinv[0, 0] + ix2**2 * Cinv[1, 1] + 2 * Cinv[1, 0] * ix1 * ix2) / 2)
         Win /= np.sum(Win)
 
-        bins2D = conv2d(histbins, Win, "same")
+        if parx.periodic and pary.periodic:  # mcsamples.py:1874-1882
+            cmode = "periodic_both"
+        elif parx.periodic:
+            cmode = "periodic_x"
+        elif pary.periodic:
+            cmode = "periodic_y"
+        else:
+            cmode = "same"
+        both_periodic = parx.periodic and pary.periodic
+        bins2D = conv2d(histbins, Win, cmode)
         prior_mask = None
         if has_prior and boundary_correction_order >= 0 or mult_bias_correction_order:
             prior_mask = np.ones((ysize + 2 * winw, xsize + 2 * winw))
-        if has_prior and boundary_correction_order >= 0:
-            # mcsamples.py:1921-1961 with edge masks :1688-1703
-            if parx.has_limits_bot:
-                prior_mask[:, winw] /= 2
-                prior_mask[:, :winw] = 0
-            if parx.has_limits_top:
-                prior_mask[:, -(winw + 1)] /= 2
-                prior_mask[:, -winw:] = 0
-            if pary.has_limits_bot:
-                prior_mask[winw, :] /= 2
-                prior_mask[:winw:] = 0
-            if pary.has_limits_top:
-                prior_mask[-(winw + 1), :] /= 2
-                prior_mask[-winw:, :] = 0
+        if has_prior and boundary_correction_order >= 0 and not both_periodic:
+            # mcsamples.py:1921-1961 with edge masks :1688-1703 (non-periodic axes only)
+            if not parx.periodic:
+                if parx.has_limits_bot:
+                    prior_mask[:, winw] /= 2
+                    prior_mask[:, :winw] = 0
+                if parx.has_limits_top:
+                    prior_mask[:, -(winw + 1)] /= 2
+                    prior_mask[:, -winw:] = 0
+            if not pary.periodic:
+                if pary.has_limits_bot:
+                    prior_mask[winw, :] /= 2
+                    prior_mask[:winw:] = 0
+                if pary.has_limits_top:
+                    prior_mask[-(winw + 1), :] /= 2
+                    prior_mask[-winw:, :] = 0
             a00 = conv2d(prior_mask, Win, "valid")
             sel = a00 * bins2D > np.max(bins2D) * 1e-8
             a00 = a00[sel]
@@ -1016,8 +1080,8 @@ class OracleSamples:
                 a20 = conv2d(prior_mask, winx * indexes, "valid")[sel]
                 a02 = conv2d(prior_mask, winy * y, "valid")[sel]
                 a11 = conv2d(prior_mask, winy * indexes, "valid")[sel]
-                xP = conv2d(histbins, winx, "same")[sel]
-                yP = conv2d(histbins, winy, "same")[sel]
+                xP = conv2d(histbins, winx, cmode)[sel]
+                yP = conv2d(histbins, winy, cmode)[sel]
                 denom = a20 * a01**2 + a10**2 * a02 - a00 * a02 * a20 + a11**2 * a00 - 2 * a01 * a10 * a11
                 A = a11**2 - a02 * a20
                 Ax = a10 * a02 - a01 * a11
@@ -1026,18 +1090,20 @@ class OracleSamples:
                 bins2D[sel] = normed * np.exp(np.minimum(corrected / normed, 4) - 1)
             else:
                 raise OracleSettingError("unknown boundary_correction_order (expected 0 or 1)")
-        if mult_bias_correction_order:
-            # mcsamples.py:1963-1976 with :1705-1712
-            prior_mask[:, :winw] = 0
-            prior_mask[:, -winw:] = 0
-            prior_mask[:winw:] = 0
-            prior_mask[-winw:, :] = 0
+        if mult_bias_correction_order and not both_periodic:
+            # mcsamples.py:1963-1976 with :1705-1712 (margins zeroed along non-periodic axes only)
+            if not parx.periodic:
+                prior_mask[:, :winw] = 0
+                prior_mask[:, -winw:] = 0
+            if not pary.periodic:
+                prior_mask[:winw:] = 0
+                prior_mask[-winw:, :] = 0
             a00 = conv2d(prior_mask, Win, "valid")
             for _ in range(mult_bias_correction_order):
                 box = histbins.copy()
                 sel2 = bins2D > np.max(bins2D) * 1e-8
                 box[sel2] /= bins2D[sel2]
-                bins2D *= conv2d(box, Win, "same")
+                bins2D *= conv2d(box, Win, cmode)
                 bins2D /= a00
         mx = np.max(bins2D)
         if mx == 0:

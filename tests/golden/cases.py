@@ -121,6 +121,24 @@ def case_mcmc():
                 pairs=[(0, 1), (0, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
 
 
+def case_periodic():
+    """testPeriodic-like (getdist_test.py:181-225): a wrapped angle (periodic), a bounded radius, a free parameter
+    and a second angle -> 1D periodic, 2D periodic in x, in y and in both."""
+    rng = np.random.default_rng(42)
+    n = 30000
+    angle = rng.normal(0, 1, n) % (2 * np.pi)
+    radius = np.abs(rng.normal(2, 0.5, n))
+    free = rng.normal(size=n) + 0.3 * np.cos(angle)
+    phase = (rng.vonmises(1.0, 2.0, n) + 0.2 * free) % (2 * np.pi)
+    X = np.ascontiguousarray(np.column_stack([angle, radius, free, phase]))
+    w = np.random.default_rng(43).exponential(1.0, n)
+    ranges = {"angle": [0, 2 * np.pi, "periodic"], "radius": [0, 5], "phase": [0, 2 * np.pi, True]}
+    return dict(samples=X, weights=w, names=["angle", "radius", "free", "phase"], ranges=ranges, settings={},
+                pairs=[(0, 1), (1, 0), (0, 2), (0, 3), (2, 3)],
+                kwargs_1d=[{}, {"mult_bias_correction_order": 0}, {"fine_bins": 64}],
+                kwargs_2d=[{}, {"fine_bins_2D": 64}, {"mult_bias_correction_order": 0, "fine_bins_2D": 64}])
+
+
 CASES = {
     "mix3": case_mix3,
     "unit5": case_unit5,
@@ -128,6 +146,7 @@ CASES = {
     "highcorr": case_highcorr,
     "chains": case_chains,
     "mcmc": case_mcmc,
+    "periodic": case_periodic,
 }
 
 

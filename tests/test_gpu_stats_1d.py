@@ -178,3 +178,16 @@ def test_larger_n_properties():
     assert np.allclose(d.P, d2.P[::-1], atol=1e-10)
     assert np.allclose(d.x, -d2.x[::-1])
     np.testing.assert_allclose(mc.getMeans(), -mc2.getMeans(), rtol=1e-13)
+
+
+def test_pickle_and_copy_roundtrip(gpu_objs):
+    """the object stays picklable / deep-copyable (device handle excluded, samples re-uploaded lazily)"""
+    import pickle
+
+    case, g, mc = gpu_objs("mix3")
+    ref = mc.get1DDensity("b").P.copy()
+    mc2 = pickle.loads(pickle.dumps(mc))
+    assert np.array_equal(mc2.get1DDensity("b").P, ref)
+    np.testing.assert_allclose(mc2.getCov(), mc.getCov(), rtol=0, atol=0)
+    mc3 = mc.copy(settings={"fine_bins": 512})
+    assert mc3.get1DDensity("b").P.size == 512 and mc.get1DDensity("b").P.size == 1024

@@ -108,7 +108,8 @@ class Spec1D(C.Structure):
                 ("range_min", C.c_double), ("range_max", C.c_double), ("param_min", C.c_double),
                 ("param_max", C.c_double), ("sigma_range", C.c_double), ("err", C.c_double), ("neff", C.c_double),
                 ("smooth_scale_1D", C.c_double), ("width", C.c_double), ("boundary_correction_order", C.c_int32),
-                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32)]
+                ("mult_bias_correction_order", C.c_int32), ("has_limits_bot", C.c_int32), ("has_limits_top", C.c_int32),
+                ("periodic", C.c_int32), ("pad", C.c_int32)]
 
 
 class Res1D(C.Structure):
@@ -116,7 +117,7 @@ class Res1D(C.Structure):
                 ("status", C.c_uint32), ("n_feval", C.c_int32), ("pad", C.c_int32)]
 
 
-@pytest.mark.parametrize("name", ["mix3", "unit5", "bounded", "highcorr", "chains"])
+@pytest.mark.parametrize("name", ["mix3", "unit5", "bounded", "highcorr", "chains", "mcmc", "periodic"])
 def test_kde1d_core_vs_oracle_and_golden(hs, name):
     from oracle.getdist_oracle import bin_geometry, bin_indices
 
@@ -135,7 +136,7 @@ def test_kde1d_core_vs_oracle_and_golden(hs, name):
             sp = Spec1D(j, F, binmin, binmax, par.range_min, par.range_max, par.param_min, par.param_max,
                         par.sigma_range, par.err, o._neff(par), s["smooth_scale_1D"],
                         (par.range_max - par.range_min) / (s["num_bins"] - 1), s["boundary_correction_order"],
-                        s["mult_bias_correction_order"], int(par.has_limits_bot), int(par.has_limits_top))
+                        s["mult_bias_correction_order"], int(par.has_limits_bot), int(par.has_limits_top), int(par.periodic), 0)
             P = np.empty(F)
             res = Res1D()
             hs.hs_kde1d(C.byref(sp), dptr(bins), dptr(P), C.byref(res))
