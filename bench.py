@@ -225,7 +225,7 @@ def run_ours(args):
         if my2d:
             # every 2D grid of the C2 workload is G x G; a scaled-up grid would not fit the packed tensor
             specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr(), _contours=[])
-            assert all(s.fine_bins == G for s in specs)
+            assert np.all(specs["fine_bins"] == G)
             ph = mc._ctx.phase_ms()
             for k in ("hist2d", "shear", "xform2d", "bw2d", "conv2d"):
                 phases[k] = ph[k]

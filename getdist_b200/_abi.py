@@ -221,8 +221,14 @@ class Context:
 
     def density2d_batch(self, specs, out=None, device_ptr=None):
         n = len(specs)
-        arr = (Spec2D * n)(*specs)
-        sizes = np.array([s.fine_bins * s.fine_bins for s in specs], dtype=np.int64)
+        if isinstance(specs, np.ndarray):  # structured array with the gdk_spec2d layout (vectorised planner)
+            assert specs.dtype.itemsize == C.sizeof(Spec2D) and specs.flags.c_contiguous
+            arr = C.c_void_p(specs.ctypes.data)
+            fb = specs["fine_bins"].astype(np.int64)
+            sizes = fb * fb
+        else:
+            arr = (Spec2D * n)(*specs)
+            sizes = np.array([s.fine_bins * s.fine_bins for s in specs], dtype=np.int64)
         offsets = np.zeros(n, dtype=np.int64)
         offsets[1:] = np.cumsum(sizes)[:-1]
         total = int(sizes.sum())

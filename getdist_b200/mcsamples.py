@@ -128,6 +128,19 @@ class ParamBounds:
         return self.upper.get(name)
 
 
+class _SpecView:
+    """attribute access to one row of the structured gdk_spec2d array"""
+
+    __slots__ = ("_r",)
+
+    def __init__(self, row):
+        self._r = row
+
+    def __getattr__(self, k):
+        v = self._r[k]
+        return v.item() if hasattr(v, "item") and np.ndim(v) == 0 else v
+
+
 class ParamConfidenceData:
     """Handle standing in for chains.ParamConfidenceData: the device resolves order statistics directly, so
     the handle only remembers which column it refers to."""
@@ -821,23 +834,135 @@ class MCSamples:
                 sp.ry_fixed = smooth_scale_2D * fine_bins_2D / nbin2D
         return sp
 
+    def _specs_2d_batch(self, pairs, kwargs):
+        """Vectorised equivalent of [_spec_2d(j, j2, kwargs) for (j, j2) in pairs]: the same IEEE operations on
+        numpy arrays (the 2x2 Cholesky / inverse of the shear branch as stacked LAPACK calls), written straight
+        into a structured array with the layout of gdk_spec2d.  Keeps the host out of the critical path of a
+        2016-pair triangle."""
+        n = len(pairs)
+        names = self.paramNames.names
+        jx = np.fromiter((p[0] for p in pairs), dtype=np.int64, count=n)
+        jy = np.fromiter((p[1] for p in pairs), dtype=np.int64, count=n)
+
+        used = np.zeros(len(names), dtype=bool)
+        used[jx] = True
+        used[jy] = True
+
+        def col(a, dt=np.float64):  # parameters outside this batch may not have their ranges yet
+            return np.array([getattr(par, a) if u else 0 for par, u in zip(names, used)], dtype=dt)
+
+        rmin, rmax, pmin, pmax = col("range_min"), col("range_max"), col("param_min"), col("param_max")
+        sig, err = col("sigma_range"), col("err")
+        hb, ht, per = col("has_limits_bot", bool), col("has_limits_top", bool), col("periodic", bool)
+        hl = hb | ht
+        base = int(kwargs.get("fine_bins_2D", self.fine_bins_2D))
+        bco = int(kwargs.get("boundary_correction_order", self.boundary_correction_order))
+        mbc = int(kwargs.get("mult_bias_correction_order", self.mult_bias_correction_order))
+        smooth = float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D))
+        if abs(self.max_corr_2D) > 1:
+            raise SettingError("max_corr_2D cannot be >=1")
+        actual = self.getCorrelationMatrix()[jy, jx]
+        corr = actual.copy()
+        one = np.abs(np.abs(corr) - 1.0) <= 1e-8
+        for k in np.nonzero(one)[0]:
+            log.warning("Parameters are 100%% correlated: %s, %s", names[jx[k]].name, names[jy[k]].name)
+        corr[one] = np.sign(corr[one]) * self.max_corr_2D
+        corr[np.abs(corr) < 0.1] = 0.0
+        has_prior = hl[jx] | hl[jy]
+        if bco > 1 and np.any(has_prior & ~(per[jx] & per[jy])):
+            raise SettingError("unknown boundary_correction_order (expected 0 or 1)")
+        angle = np.maximum(0.2, np.sqrt(1 - np.minimum(self.max_corr_2D, np.abs(corr)) ** 2))
+        nbin2D = np.rint(self.num_bins_2D / angle).astype(np.int64)
+        scaled = 192 * (3 / angle).astype(np.int64) // 3
+        fine = np.where((corr != 0) & (base < scaled) & ((1 / angle).astype(np.int64) > 1), scaled, base).astype(np.int64)
+
+        def geom(j):
+            border = (rmax[j] - rmin[j]) * 0.1
+            lo = np.minimum(pmin[j], rmin[j])
+            lo = np.where(hb[j], lo, lo - border)
+            hi = np.maximum(pmax[j], rmax[j])
+            hi = np.where(ht[j], hi, hi + border)
+            return lo, hi
+
+        xlo, xhi = geom(jx)
+        ylo, yhi = geom(jy)
+        fwx = (xhi - xlo) / (fine - 1)
+        fwy = (yhi - ylo) / (fine - 1)
+        sp = np.zeros(n, dtype=np.dtype(_abi.Spec2D))
+        sp["px"], sp["py"] = jx, jy
+        sp["fine_bins"], sp["base_fine_bins"] = fine, base
+        sp["xbinmin"], sp["xbinmax"], sp["ybinmin"], sp["ybinmax"] = xlo, xhi, ylo, yhi
+        sp["x_sigma_range"], sp["y_sigma_range"] = sig[jx], sig[jy]
+        sp["x_err"], sp["y_err"] = err[jx], err[jy]
+        sp["corr"], sp["kernel_corr"] = actual, corr
+        sp["max_corr_2D"] = self.max_corr_2D
+        sp["smooth_scale_2D"] = smooth
+        sp["boundary_correction_order"], sp["mult_bias_correction_order"] = bco, mbc
+        sp["x_has_bot"], sp["x_has_top"], sp["y_has_bot"], sp["y_has_top"] = hb[jx], ht[jx], hb[jy], ht[jy]
+        sp["x_periodic"], sp["y_periodic"] = per[jx], per[jy]
+        sp["neff"] = 1.0
+        if smooth < 0:
+            if self.use_effective_samples_2D and np.any(np.abs(actual) < 0.999):
+                raise NotImplementedError("use_effective_samples_2D needs the 2D autocorrelation N_eff: use the reference")
+            neff = np.array([par.N_eff_kde if u else np.nan for par, u in zip(names, used)], dtype=np.float64)
+            sp["neff"] = np.minimum(neff[jx], neff[jy])
+            do_corr = ~hl[jx] | ~hl[jy]
+            shear = (0.2 < np.abs(actual)) & (np.abs(actual) <= self.max_corr_2D) & do_corr
+            rule = ~shear & ((np.abs(actual) > self.max_corr_2D) | (~do_corr & (actual > 0.8)))
+            mode = np.where(shear, _abi.BW2D_SHEAR, np.where(rule, _abi.BW2D_RULE, _abi.BW2D_PLAIN))
+            sp["bw_mode"] = mode
+            ks = np.nonzero(shear)[0]
+            if ks.size:
+                swapped = hl[jy[ks]]  # pary.has_limits: (i, j) = (py, px)
+                si = np.where(swapped, jy[ks], jx[ks])
+                sk = np.where(swapped, jx[ks], jy[ks])
+                # imin / imax: limits of x, overridden by those of y when y has limits (mcsamples.py:1352-1362)
+                imin = np.where(hb[jx[ks]], rmin[jx[ks]], np.nan)
+                imax = np.where(ht[jx[ks]], rmax[jx[ks]], np.nan)
+                imin = np.where(swapped & hb[jy[ks]], rmin[jy[ks]], imin)
+                imax = np.where(swapped & ht[jy[ks]], rmax[jy[ks]], imax)
+                cov = self.fullcov
+                covs = np.empty((ks.size, 2, 2))
+                covs[:, 0, 0], covs[:, 0, 1] = cov[si, si], cov[si, sk]
+                covs[:, 1, 0], covs[:, 1, 1] = cov[sk, si], cov[sk, sk]
+                S = np.linalg.cholesky(covs)
+                ichol = np.linalg.inv(S)
+                S = S * ichol[:, 0:1, 0:1]
+                r = ichol[:, 1, :] / ichol[:, 0, 0][:, None]
+                sp["shear_i"][ks], sp["shear_j"][ks], sp["shear_swapped"][ks] = si, sk, swapped
+                sp["r0"][ks], sp["r1"][ks] = r[:, 0], r[:, 1]
+                sp["S00"][ks], sp["S10"][ks], sp["S11"][ks] = S[:, 0, 0], S[:, 1, 0], S[:, 1, 1]
+                mn, mx = self._xmin[si], self._xmax[si]
+                delta = mx - mn
+                sp["p1_min"][ks] = np.where(np.isnan(imin), mn - delta * 0.1, imin)
+                sp["p1_max"][ks] = np.where(np.isnan(imax), mx + delta * 0.1, imax)
+        else:
+            sp["bw_mode"] = _abi.BW2D_FIXED
+            if smooth < 1.0:
+                sp["rx_fixed"] = smooth * err[jx] / fwx
+                sp["ry_fixed"] = smooth * err[jy] / fwy
+            else:
+                sp["rx_fixed"] = smooth * fine / nbin2D
+                sp["ry_fixed"] = smooth * fine / nbin2D
+        return sp
+
     def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, **kwargs):
         self._ensure_param_ranges([p for pr in pairs for p in pr])
         if float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D)) < 0:
             self._ensure_neff([p for pr in pairs for p in pr])
-        specs = [self._spec_2d(j, j2, kwargs) for (j, j2) in pairs]
+        specs = self._specs_2d_batch(pairs, kwargs)
         if _contours is None:
             _contours = list(self.contours[:4])  # batched prefetch: the analysis-settings contours
         conts = [float(c) for c in _contours[:4]] if len(_contours) <= 4 else []
-        for sp in specs:
-            sp.n_contours = len(conts)
-            for k, c in enumerate(conts):
-                sp.contours[k] = c
+        specs["n_contours"] = len(conts)
+        for k, c in enumerate(conts):
+            specs["contours"][:, k] = c
         buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
         out = []
-        for (j, j2), sp, off, r in zip(pairs, specs, offsets, res):
+        for (j, j2), spr, off, r in zip(pairs, specs, offsets, res):
+            sp = _SpecView(spr)
             parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
             if r.status & _abi.ST_BIAS_NEG:
                 raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)

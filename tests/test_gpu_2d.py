@@ -199,3 +199,26 @@ def test_band_path_matches_bincount():
         d = mc.get2DDensity(jx, jy)
         tol = 1e-5 if d._gdk["status"] & AMISE_BITS else 1e-6
         assert np.max(np.abs(d.P - o.density_2d(jx, jy).P)) < tol
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_vectorised_planner_equals_per_pair_planner(gpu_objs, name):
+    """_specs_2d_batch (numpy, stacked LAPACK) must produce the same gdk_spec2d bytes as _spec_2d per pair"""
+    import ctypes as C
+
+    from getdist_b200 import _abi
+
+    case, g, mc = gpu_objs(name)
+    P = mc.n
+    pairs = [(i, k) for i in range(P) for k in range(P) if i != k]
+    mc._ensure_param_ranges(range(P))
+    mc._ensure_neff(range(P))
+    for kw in case["kwargs_2d"]:
+        batch = mc._specs_2d_batch(pairs, kw)
+        for row, (j, j2) in zip(batch, pairs):
+            single = mc._spec_2d(j, j2, kw)
+            for fname, _ in _abi.Spec2D._fields_:
+                a, b = row[fname], getattr(single, fname)
+                if fname == "contours":
+                    continue
+                assert a == b, (name, kw, j, j2, fname, a, b)
