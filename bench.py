@@ -338,8 +338,11 @@ def run_ours(args):
     roof = None
     if phases.get("hist2d", 0) > 0:
         ach = algo_bytes["hist2d"] / (phases["hist2d"] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture of exactly this
+        # workload (profiles/r1m_ncu_full_summary.csv: 50.80 + 0.86 GB); other sizes have no capture -> null
+        traffic = 51.66e9 if (N == 10_000_000 and P == 64 and world == 1) else None
         roof = {"kernel": "k_hist2d_tiles", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes": algo_bytes["hist2d"], "kernel_ms": phases["hist2d"],
+                "traffic": traffic, "algorithmic_bytes": algo_bytes["hist2d"], "kernel_ms": phases["hist2d"],
                 "peak_source": peak_src, "dominant_phase_by_time": dom,
                 "note": "algorithmic bytes = N*24 B per pair (standalone per-pair sweep, SURVEY s8d); the tiled kernel "
                         "reads far less from DRAM and is bound by L2 atomic throughput: updates/s = %.3e"
