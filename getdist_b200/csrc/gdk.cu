@@ -125,6 +125,8 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->cluster_ok = cl != 0 && prop.major >= 9;
         const char* eb = getenv("GDK_BANDS");
         ctx->use_bands = eb && eb[0] == '1';
+        const char* eh = getenv("GDK_HOT");
+        ctx->use_hot = !(eh && eh[0] == '0');
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {
@@ -409,6 +411,8 @@ static int compute_moments(gdk_ctx* ctx) {
     ctx->have_moments = true;
     return 0;
 }
+
+int gdk_compute_moments(gdk_ctx* ctx) { return compute_moments(ctx); }
 
 extern "C" int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double* cov, double* scalars, double* xmin,
                                double* xmax, double* chain_means, double* chain_covs, double* chain_norms) {

@@ -84,7 +84,17 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
 
     // ---------------- shared-memory privatised path for the 256 x 256 grids ----------------
     std::vector<char> in_bands(n, 0);
-    std::vector<int> band_pairs;
+    std::vector<int> band_pairs, hot_pairs;
+    {
+        // default for 256^2 grids: hot-window privatisation (k_bin8 + k_hist2d_hot); GDK_HOT=0 falls back to REDG tiles
+        const size_t hot_smem = (size_t)4 * 2 * HW * HW * 4;
+        if (ctx->use_hot && !ctx->use_bands && ctx->N >= (1 << 17) && hot_smem + 2048 <= (size_t)ctx->max_smem)
+            for (int i = 0; i < n; i++)
+                if (specs[i].fine_bins == 256) {
+                    in_bands[i] = 1;  // excluded from the REDG tiles
+                    hot_pairs.push_back(i);
+                }
+    }
     {
         // Opt-in (GDK_BANDS=1 at context creation).  Measured on B200 at C2 (profiles/README.md, r1h): 218 ms vs
         // 103 ms for the tiled REDG kernel -- with 128 KB of exact 64-bit bins per CTA the multicast ring is only
@@ -184,7 +194,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     {
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_HIST2D);
-        if (!band_pairs.empty()) {
+        const std::vector<int>& b8pairs = hot_pairs.empty() ? band_pairs : hot_pairs;
+        if (!b8pairs.empty()) {
             // byte bin indices per parameter (geometry of a parameter is the same in every 256^2 pair)
             std::map<int, int> slot;
             std::vector<Bin8Job> bj;
@@ -194,13 +205,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 slot[p] = (int)bj.size();
                 bj.push_back(Bin8Job{p, 0, lo, fw, 1.0 / fw});
             };
-            for (int i : band_pairs) {
+            for (int i : b8pairs) {
                 add(specs[i].px, specs[i].xbinmin, specs[i].xbinmax);
                 add(specs[i].py, specs[i].ybinmin, specs[i].ybinmax);
             }
             // a parameter must have ONE geometry across the batch; otherwise route the odd pairs through the tiles
             bool consistent = true;
-            for (int i : band_pairs) {
+            for (int i : b8pairs) {
                 const Bin8Job& a = bj[slot[specs[i].px]];
                 const Bin8Job& b = bj[slot[specs[i].py]];
                 if (a.binmin != specs[i].xbinmin || a.fw != (specs[i].xbinmax - specs[i].xbinmin) / 255.0 ||
@@ -219,6 +230,81 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             if (rc) return rc;
             dim3 g8((unsigned)segs8.size(), (unsigned)np8);
             k_bin8<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld);
+            ctx->launches++;
+            if (!hot_pairs.empty()) {
+                // 2 x 2 tiles over (x parameter, y parameter); window origin from the weighted mean of each parameter
+                std::vector<int> A, B;
+                for (int i : hot_pairs) {
+                    A.push_back(specs[i].px);
+                    B.push_back(specs[i].py);
+                }
+                std::sort(A.begin(), A.end());
+                A.erase(std::unique(A.begin(), A.end()), A.end());
+                std::sort(B.begin(), B.end());
+                B.erase(std::unique(B.begin(), B.end()), B.end());
+                std::map<int, int> ia, ib;
+                for (size_t k = 0; k < A.size(); k++) ia[A[k]] = (int)k;
+                for (size_t k = 0; k < B.size(); k++) ib[B[k]] = (int)k;
+                auto origin = [&](int p) {
+                    const Bin8Job& j = bj[slot[p]];
+                    int c = (int)floor((ctx->means[p] - j.binmin) / j.fw + 0.5) - HW / 2;
+                    return std::max(0, std::min(256 - HW, c));
+                };
+                std::vector<HotTile> ht;
+                std::map<std::pair<int, int>, int> tix;
+                for (int i : hot_pairs) {
+                    const gdk_spec2d& sp = specs[i];
+                    const int a = ia[sp.px], b = ib[sp.py];
+                    const std::pair<int, int> key(a / 2, b / 2);
+                    auto it = tix.find(key);
+                    if (it == tix.end()) {
+                        HotTile t{};
+                        for (int x = 0; x < 2; x++)
+                            for (int y = 0; y < 2; y++) t.off[x][y] = -1;
+                        t.ia[0] = t.ia[1] = t.ib[0] = t.ib[1] = ctx->ix8.p;
+                        it = tix.emplace(key, (int)ht.size()).first;
+                        ht.push_back(t);
+                    }
+                    HotTile* t = &ht[it->second];
+                    const int la = a % 2, lb = b % 2;
+                    if (t->off[la][lb] >= 0) {  // duplicate request: own tile
+                        HotTile d{};
+                        for (int x = 0; x < 2; x++)
+                            for (int y = 0; y < 2; y++) d.off[x][y] = -1;
+                        d.ia[0] = d.ia[1] = d.ib[0] = d.ib[1] = ctx->ix8.p;
+                        ht.push_back(d);
+                        t = &ht.back();
+                        t->na = t->nb = 0;
+                        t->off[0][0] = goff[i];
+                        t->na = t->nb = 1;
+                        t->ia[0] = ctx->ix8.p + (size_t)slot[sp.px] * ctx->ld;
+                        t->ib[0] = ctx->ix8.p + (size_t)slot[sp.py] * ctx->ld;
+                        t->ax0[0] = origin(sp.px);
+                        t->by0[0] = origin(sp.py);
+                        continue;
+                    }
+                    t->na = std::max(t->na, la + 1);
+                    t->nb = std::max(t->nb, lb + 1);
+                    t->ia[la] = ctx->ix8.p + (size_t)slot[sp.px] * ctx->ld;
+                    t->ib[lb] = ctx->ix8.p + (size_t)slot[sp.py] * ctx->ld;
+                    t->ax0[la] = origin(sp.px);
+                    t->by0[lb] = origin(sp.py);
+                    t->off[la][lb] = goff[i];
+                }
+                HotTile* dht = nullptr;
+                rc = upload_vec(ctx, ht, ctx->bytes2d_d, &dht);
+                if (rc) return rc;
+                // long segments amortise the window flush (4 x 4096 reductions per CTA); segments are the fast index
+                const int64_t seglen = (std::max<int64_t>(1 << 16, (ctx->N + 255) / 256) + 3) & ~int64_t(3);
+                std::vector<Seg> segsh = gdk_make_segments(ctx, seglen);
+                rc = gdk_upload_segs(ctx, segsh, ctx->segs);
+                if (rc) return rc;
+                const size_t hot_smem = (size_t)4 * 2 * HW * HW * 4;
+                CK2(cudaFuncSetAttribute(k_hist2d_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_smem));
+                dim3 gh((unsigned)segsh.size(), (unsigned)ht.size());
+                k_hist2d_hot<<<gh, 1024, hot_smem, ctx->stream>>>(dht, ctx->dWq.p, ctx->segs.p, ctx->gbins2.p);
+                ctx->launches++;
+            } else {
             std::vector<BandJob> jobs(band_pairs.size());
             for (size_t k = 0; k < band_pairs.size(); k++) {
                 const int i = band_pairs[k];
@@ -231,7 +317,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             const size_t band_smem = (size_t)2 * 64 * 256 * 4 + (size_t)HB_STAGES * HB_CHUNK * 10;
             CK2(cudaFuncSetAttribute(k_hist2d_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem));
             k_hist2d_bands<<<(unsigned)(4 * jobs.size()), HB_THREADS, band_smem, ctx->stream>>>(dband, ctx->dWq.p, ctx->N);
-            ctx->launches += 2;
+            ctx->launches++;
+            }
         }
         if (ntiles) {
             // Row segments are the FAST grid index: all CTAs resident at one time (~5 per SM) then work on one or
@@ -287,6 +374,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 sgroups.push_back(g);
             }
             ShearGroup& g = sgroups.back();
+            g.mean1 = ctx->means[j.pi];
+            g.mean2[g.nj] = j.r0 * ctx->means[j.pi] + j.r1 * ctx->means[j.pj];
             g.pj[g.nj] = j.pj;
             g.job[g.nj] = ord[k];
             g.r0[g.nj] = j.r0;
@@ -300,7 +389,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         const int ngroups = (int)sgroups.size();
         // fine segments (fast grid index) keep the <= 8 grids of a group L2-resident for the reductions
         const int64_t want = std::max<int64_t>((int64_t)ctx->num_sms * 8 / ngroups + 1, std::min<int64_t>((int64_t)ctx->num_sms * 6, 64));
-        const int64_t seglen = std::max<int64_t>(1 << 13, (ctx->N + want - 1) / want);
+        const int64_t seglen = std::max<int64_t>(1 << 16, (ctx->N + want - 1) / want);  // long: amortises the window flush
         std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
         rc = gdk_upload_segs(ctx, segs, ctx->segs);
         if (rc) return rc;
@@ -313,7 +402,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         dim3 g((unsigned)nseg, (unsigned)ngroups);
         k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsg, part);
         k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
-        k_shear_hist<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
+        const size_t sh_smem = (size_t)SG * 2 * HW * HW * 4;
+        CK2(cudaFuncSetAttribute(k_shear_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_smem));
+        k_shear_hist<<<g, 1024, sh_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
         ctx->launches += 3;
         pt.end();
         CK2(cudaGetLastError());
@@ -636,6 +727,10 @@ static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, doub
         if (s.boundary_correction_order > 1) return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: boundary_correction_order must be <= 1", i);
         if (s.bw_mode == GDK_BW2D_SHEAR && (s.shear_i < 0 || s.shear_i >= ctx->P || s.shear_j < 0 || s.shear_j >= ctx->P))
             return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: bad shear parameters", i);
+    }
+    if (ctx->use_hot) {  // the hot-window origins come from the weighted means
+        int rcm = gdk_compute_moments(ctx);
+        if (rcm) return rcm;
     }
     // chunks bounded by a memory budget
     size_t freeb = 0, totalb = 0;

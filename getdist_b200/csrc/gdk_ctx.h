@@ -97,7 +97,7 @@ struct gdk_ctx {
     DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena, qbase;
     Kde2dConsts k2d;
     DevBuf<unsigned char> ix8;
-    bool cluster_ok = false, use_bands = false;
+    bool cluster_ok = false, use_bands = false, use_hot = true;
     // per-context (= per-device) record of opted-in dynamic shared-memory sizes
     bool q_attr_set = false;
     size_t h1_tma_smem = 0, h1_smem = 0, kde1d_smem = 0;
@@ -112,6 +112,7 @@ struct PhaseTimer {
 };
 
 int gdk_fail(gdk_ctx* c, int code, const char* fmt, ...);
+int gdk_compute_moments(gdk_ctx* ctx);
 std::vector<Seg> gdk_make_segments(const gdk_ctx* c, int64_t seglen);
 int gdk_upload_segs(gdk_ctx* ctx, const std::vector<Seg>& v, DevBuf<Seg>& buf);
 const Kde1dTablesHost* gdk_tables_for(gdk_ctx* ctx, int n);

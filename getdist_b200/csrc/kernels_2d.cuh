@@ -21,6 +21,7 @@
 // histograms
 // ----------------------------------------------------------------------------------------------------
 #define HT 8  // tile edge (parameters per side)
+#define HW 64 // edge of a shared-memory hot window (bins), see k_hist2d_hot / k_shear_hist
 
 struct Tile2d {
     int na, nb, G, pad;
@@ -99,13 +100,14 @@ __device__ __forceinline__ double shear_p2(double xi, double xj, double r0, doub
 }
 
 // Jobs that share their p1 column are processed together: x_i is read once per row for up to SG jobs.
-#define SG 8
+#define SG 4  // four jobs per group: four 64 x 64 shared-memory windows in k_shear_hist
 struct ShearGroup {
     int pi, nj, Gb, pad;
     int pj[SG], job[SG];
     double r0[SG], r1[SG];
     double p1_min, dx1, inv1;
     long long off[SG];
+    double mean1, mean2[SG];  // weighted means of p1 and of each p2 = r0*mean_i + r1*mean_j (window centres)
 };
 
 // grid (nseg, ngroups): partial min/max of p2 per job -> part[(job*nseg + seg)*2]
@@ -182,24 +184,37 @@ __global__ void k_shear_geom(const double* __restrict__ part, int nseg, int njob
     geom[j] = ShearGeom{rmin, dx, 1.0 / dx, R};
 }
 
-// grid (nseg, ngroups)
-__global__ void __launch_bounds__(256) k_shear_hist(const double* __restrict__ dX, int64_t ld,
-                                                    const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
-                                                    const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
-                                                    unsigned long long* __restrict__ grids) {
+// grid (nseg, ngroups), 1024 threads, dynamic smem = SG * HW*HW * 8 bytes.  Same hot-window privatisation as
+// k_hist2d_hot: each job keeps the HW x HW bins around the centre of its sheared cloud in shared memory.
+__global__ void __launch_bounds__(1024) k_shear_hist(const double* __restrict__ dX, int64_t ld,
+                                                     const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                     const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
+                                                     unsigned long long* __restrict__ grids) {
+    extern __shared__ unsigned ssm2[];  // per job: lo[HW*HW], hi[HW*HW]
     __shared__ ShearGroup g;
     __shared__ ShearGeom gm[SG];
+    __shared__ int ax0, by0[SG];
     {
         const int* src = reinterpret_cast<const int*>(groups + blockIdx.y);
         int* dst = reinterpret_cast<int*>(&g);
         for (int i = threadIdx.x; i < (int)(sizeof(ShearGroup) / 4); i += blockDim.x) dst[i] = src[i];
     }
+    for (int i = threadIdx.x; i < SG * 2 * HW * HW; i += blockDim.x) ssm2[i] = 0;
     __syncthreads();
-    if (threadIdx.x < g.nj) gm[threadIdx.x] = geom[g.job[threadIdx.x]];
+    const int G = g.Gb, nj = g.nj;
+    if (threadIdx.x < nj) {
+        gm[threadIdx.x] = geom[g.job[threadIdx.x]];
+        const int c = bin_index_trunc(g.mean2[threadIdx.x], gm[threadIdx.x].rmin, gm[threadIdx.x].dx, gm[threadIdx.x].inv) - HW / 2;
+        by0[threadIdx.x] = max(0, min(G - HW, c));
+    }
+    if (threadIdx.x == 0) {
+        const int c = bin_index_trunc(g.mean1, g.p1_min, g.dx1, g.inv1) - HW / 2;
+        ax0 = max(0, min(G - HW, c));
+    }
     __syncthreads();
+    const bool hot = G >= HW;
     const Seg sg = segs[blockIdx.x];
     const double* xi = dX + (int64_t)g.pi * ld;
-    const int G = g.Gb, nj = g.nj;
     for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
         const double a = ldg_stream(xi + r);
         const unsigned long long w = dWq[r];
@@ -209,12 +224,32 @@ __global__ void __launch_bounds__(256) k_shear_hist(const double* __restrict__ d
             if (k < nj) b[k] = ldg_stream(dX + (int64_t)g.pj[k] * ld + r);
         const int b1 = bin_index_trunc(a, g.p1_min, g.dx1, g.inv1);
         if (w == 0 || b1 < 0 || b1 >= G) continue;
+        const unsigned dx = (unsigned)(b1 - ax0);
 #pragma unroll
         for (int k = 0; k < SG; k++)
             if (k < nj) {
                 const int b2 = bin_index_trunc(shear_p2(a, b[k], g.r0[k], g.r1[k]), gm[k].rmin, gm[k].dx, gm[k].inv);
-                if (b2 >= 0 && b2 < G) atomicAdd(grids + g.off[k] + (long long)b2 * G + b1, w);
+                if (b2 < 0 || b2 >= G) continue;
+                const unsigned dy = (unsigned)(b2 - by0[k]);
+                if (hot && dx < (unsigned)HW && dy < (unsigned)HW) {
+                    unsigned* base = ssm2 + k * 2 * HW * HW;
+                    const unsigned bin = dy * HW + dx;
+                    const unsigned vlo = (unsigned)w;
+                    const unsigned old = atomicAdd(base + bin, vlo);
+                    atomicAdd(base + HW * HW + bin, (unsigned)(w >> 32) + ((old + vlo < old) ? 1u : 0u));
+                } else {
+                    atomicAdd(grids + g.off[k] + (long long)b2 * G + b1, w);
+                }
             }
+    }
+    __syncthreads();
+    if (!hot) return;
+    for (int k = 0; k < nj; k++) {
+        const unsigned* base = ssm2 + k * 2 * HW * HW;
+        for (int i = threadIdx.x; i < HW * HW; i += blockDim.x) {
+            const unsigned long long v = ((unsigned long long)base[HW * HW + i] << 32) | base[i];
+            if (v) atomicAdd(grids + g.off[k] + (long long)(by0[k] + i / HW) * G + ax0 + (i % HW), v);
+        }
     }
 }
 
@@ -965,4 +1000,101 @@ __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__
     }
     tmax = warp_max(tmax);
     if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// hot-window privatisation of the 256 x 256 histograms (default path for those grids)
+// ----------------------------------------------------------------------------------------------------
+// profiles/r1m: the tiled REDG kernel sits at 81 % of L2 throughput -- the L2 atomic units are the wall.  Most
+// updates of a marginal 2D histogram land in a small central region (about 3/4 of a Gaussian's mass within
+// +-1.5 sigma per axis = 64 x 64 bins of the 256^2 grid), so a CTA working on a 2 x 2 tile of pairs keeps the four
+// 64 x 64 windows (4 x 32 KB, two 32-bit limbs per bin, native ATOMS) in shared memory, reads the pre-binned byte
+// columns of k_bin8 (4 B + one weight per row for 4 pairs) and only sends the updates that fall outside a window
+// to L2 as REDG.  Windows are flushed once per CTA with integer global reductions.  Exactness is unchanged:
+// every path accumulates the same 64-bit fixed-point weights.
+struct HotTile {
+    const unsigned char* ia[2];
+    const unsigned char* ib[2];
+    int na, nb;
+    int ax0[2], by0[2];    // window origin per parameter (column / row of the grid)
+    long long off[2][2];   // grid offset of pair (a, b) or -1
+};
+
+// grid (nseg, ntiles), 256 threads, dynamic smem = 4 * HW*HW * 8 bytes
+__global__ void __launch_bounds__(1024) k_hist2d_hot(const HotTile* __restrict__ tiles, const unsigned long long* __restrict__ dWq,
+                                                    const Seg* __restrict__ segs, unsigned long long* __restrict__ grids) {
+    extern __shared__ unsigned hsm2[];  // per window: lo[HW*HW], hi[HW*HW]
+    __shared__ HotTile T;
+    {
+        const int* src = reinterpret_cast<const int*>(tiles + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(HotTile) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < 4 * 2 * HW * HW; i += blockDim.x) hsm2[i] = 0;
+    __syncthreads();
+    const Seg sg = segs[blockIdx.x];
+    const int na = T.na, nb = T.nb;
+    auto update = [&](unsigned av, unsigned bv, int pa, int pb, unsigned long long wv) {
+        const long long off = T.off[pa][pb];
+        if (off < 0) return;
+        const unsigned dx = av - (unsigned)T.ax0[pa], dy = bv - (unsigned)T.by0[pb];
+        if (dx < (unsigned)HW && dy < (unsigned)HW) {
+            unsigned* base = hsm2 + (pa * 2 + pb) * 2 * HW * HW;
+            const unsigned bin = dy * HW + dx;
+            const unsigned vlo = (unsigned)wv;
+            const unsigned old = atomicAdd(base + bin, vlo);
+            atomicAdd(base + HW * HW + bin, (unsigned)(wv >> 32) + ((old + vlo < old) ? 1u : 0u));
+        } else {
+            atomicAdd(grids + off + (long long)bv * 256 + av, wv);
+        }
+    };
+    if ((sg.r0 & 3) == 0) {
+        // four consecutive rows per thread: one 32-bit load per byte column, two 16-byte loads of weights
+        const int64_t nq = (sg.r1 - sg.r0) >> 2;
+        for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+            const int64_t r = sg.r0 + 4 * q;
+            unsigned a4[2] = {0, 0}, b4[2] = {0, 0};
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (p < na) a4[p] = *reinterpret_cast<const unsigned*>(T.ia[p] + r);
+                if (p < nb) b4[p] = *reinterpret_cast<const unsigned*>(T.ib[p] + r);
+            }
+            const ulonglong2 w01 = ldg_stream2_u64(dWq + r), w23 = ldg_stream2_u64(dWq + r + 2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long wv = k == 0 ? w01.x : (k == 1 ? w01.y : (k == 2 ? w23.x : w23.y));
+                if (wv == 0) continue;
+#pragma unroll
+                for (int pa = 0; pa < 2; pa++)
+#pragma unroll
+                    for (int pb = 0; pb < 2; pb++)
+                        if (pa < na && pb < nb) update((a4[pa] >> (8 * k)) & 0xffu, (b4[pb] >> (8 * k)) & 0xffu, pa, pb, wv);
+            }
+        }
+        for (int64_t r = sg.r0 + 4 * nq + threadIdx.x; r < sg.r1; r += blockDim.x) {  // tail rows
+            const unsigned long long wv = dWq[r];
+            if (wv == 0) continue;
+            for (int pa = 0; pa < na; pa++)
+                for (int pb = 0; pb < nb; pb++) update(T.ia[pa][r], T.ib[pb][r], pa, pb, wv);
+        }
+    } else {
+        for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+            const unsigned long long wv = dWq[r];
+            if (wv == 0) continue;
+            for (int pa = 0; pa < na; pa++)
+                for (int pb = 0; pb < nb; pb++) update(T.ia[pa][r], T.ib[pb][r], pa, pb, wv);
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < 4; q++) {
+        const int pa = q >> 1, pb = q & 1;
+        if (pa >= na || pb >= nb) continue;
+        const long long off = T.off[pa][pb];
+        if (off < 0) continue;
+        const unsigned* base = hsm2 + q * 2 * HW * HW;
+        for (int i = threadIdx.x; i < HW * HW; i += blockDim.x) {
+            const unsigned long long v = ((unsigned long long)base[HW * HW + i] << 32) | base[i];
+            if (v) atomicAdd(grids + off + (long long)(T.by0[pb] + (i / HW)) * 256 + T.ax0[pa] + (i % HW), v);
+        }
+    }
 }

@@ -160,14 +160,17 @@ def test_repeatable(gpu_objs):
         assert np.array_equal(x.P, y.P)
 
 
-def test_band_path_matches_bincount():
-    """opt-in cluster/multicast shared-memory path (GDK_BANDS=1, N >= 2^17, 256^2 grids): k_bin8 + k_hist2d_bands"""
+@pytest.mark.parametrize("mode", ["hot", "bands", "tiles"])
+def test_privatised_paths_match_bincount(mode):
+    """N >= 2^17 and 256^2 grids: default hot-window path (k_bin8 + k_hist2d_hot), the opt-in cluster/multicast path
+    (GDK_BANDS=1: k_hist2d_bands) and the REDG tiles (GDK_HOT=0) must all reproduce np.bincount"""
     import os
 
     from getdist_b200 import MCSamples
     from oracle.getdist_oracle import bin_indices
 
-    os.environ["GDK_BANDS"] = "1"  # read at context creation
+    env = {"hot": {}, "bands": {"GDK_BANDS": "1"}, "tiles": {"GDK_HOT": "0"}}[mode]
+    os.environ.update(env)  # read at context creation
 
     rng = np.random.default_rng(12)
     N, P = 300_007, 5  # odd N: partial last chunk
@@ -176,7 +179,8 @@ def test_band_path_matches_bincount():
     w = rng.exponential(1.0, N)
     w[rng.random(N) < 0.01] = 0.0
     mc = MCSamples(samples=X, weights=w, names=["a", "b", "c", "d", "e"], sampler="uncorrelated")
-    os.environ.pop("GDK_BANDS")
+    for k in env:
+        os.environ.pop(k)
     pairs = [(i, k) for i in range(P) for k in range(i + 1, P)] + [(3, 1)]
     mc._ensure_param_ranges(range(P))
     mc._ensure_neff(range(P))
