@@ -35,7 +35,7 @@ struct Arena {
 static size_t bytes_per_pair_estimate(const gdk_spec2d& s) {
     const size_t g = (size_t)s.fine_bins * s.fine_bins * 8, gb = (size_t)s.base_fine_bins * s.base_fine_bins * 8;
     const size_t w = 256;  // generous window half-width guess for the T scratch
-    return g * 12 + gb * 6 + (2 * w + 1) * (size_t)s.fine_bins * 4 * 8 + (2 * w + 1) * (2 * w + 1) * 8;
+    return g * 13 + gb * 6 + (2 * w + 1) * (size_t)s.fine_bins * 4 * 8 + (2 * w + 1) * (2 * w + 1) * 8;
 }
 
 template <class T>
@@ -560,6 +560,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         c.P = take_d((size_t)G * G);
         c.Pn = c.mbc ? take_d((size_t)G * G) : c.P;
         c.a00b = c.mbc ? take_d((size_t)G * G) : nullptr;
+        c.box = c.mbc ? take_d((size_t)G * G) : nullptr;
         c.T = (c.mbc || c.bounded) ? take_d((size_t)K * G * 4) : nullptr;
         if (c.bounded) {
             c.maps = take_d((size_t)G * G * 6);
@@ -569,7 +570,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             }
         }
         c.mx = reinterpret_cast<unsigned long long*>(ctx->bytes2d_mx.p) + (size_t)i * 8;
-        if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || !c.T)) || (c.bounded && (!c.maps || !c.T || (c.bco == 1 && (!c.xP || !c.yP)))))
+        if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || !c.T || !c.box)) || (c.bounded && (!c.maps || !c.T || (c.bco == 1 && (!c.xP || !c.yP)))))
             return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (convolution stage, pair %d)", i);
         wmax_all = std::max(wmax_all, w);
         max_mbc = std::max(max_mbc, c.mbc);
@@ -654,8 +655,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
         ctx->launches += 4;
         for (int it = 0; it < max_mbc; it++) {
+            k_make_box<<<gb, 256, 0, ctx->stream>>>(dcj + g.b, it);
             k_conv2d<1><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, it, g.wmax, kc1);
-            ctx->launches++;
+            ctx->launches += 2;
             if (any_periodic) {
                 k_conv2d_circ<1><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, it);
                 ctx->launches++;

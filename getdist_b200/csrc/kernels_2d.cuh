@@ -21,7 +21,7 @@
 // histograms
 // ----------------------------------------------------------------------------------------------------
 #define HT 8  // tile edge (parameters per side)
-#define HW 64 // edge of a shared-memory hot window (bins), see k_hist2d_hot / k_shear_hist
+#define HW 64 // edge of a shared-memory hot window (bins), see k_hist2d_hot / k_shear_hist (80 was measured: no gain)
 
 struct Tile2d {
     int na, nb, G, pad;
@@ -420,6 +420,7 @@ struct ConvJob {
     double* yP;
     double* maps;        // bounded: 6 maps a00,a10,a01,a20,a02,a11 (G*G each)
     double* a00b;        // bias-correction normaliser map
+    double* box;         // hist / P where P > 1e-8 max(P), else hist: input of the bias-correction convolution
     double* T;           // scratch K x G x 3
     unsigned long long* mx;  // [8] running maxima (bit patterns of non-negative doubles):
                              // 0 = hist*W, 1 = after boundary correction, 2 + it = after bias iteration it
@@ -511,21 +512,21 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
             const int kk = it / kp, kr = it - kk * kp;
             wk_s[it] = (kr < K) ? jb.Wk[(size_t)(k0 + kk) * K + (2 * w - kr)] : 0.0;
         }
-        // input rows a = abase + r, r < CV_TY + kc - 1
+        // input rows a = abase + r, r < CV_TY + kc - 1; one warp per row, lanes stride over the columns
         const int abase = oy0 - (k0 + kc - 1) + w;
         const int nrow = CV_TY + kc - 1;
-        for (int it = threadIdx.x; it < nrow * pitch; it += blockDim.x) {
-            const int r = it / pitch, c = it - r * pitch;  // c < 8q covers every stored position
-            const int a = abase + r, b = ox0 - w + c;
-            double v = 0;
-            if (c < ncol + 8 && a >= 0 && a < G && b >= 0 && b < G) {
-                v = jb.hist[(size_t)a * G + b];
-                if (MODE == 1) {
-                    const double p = P[(size_t)a * G + b];
-                    if (p > thr) v = v / p;
-                }
+        const double* srcp = (MODE == 1) ? jb.box : jb.hist;
+        for (int r = threadIdx.x >> 5; r < nrow; r += 8) {
+            const int a = abase + r;
+            const bool rowok = a >= 0 && a < G;
+            const double* srow = srcp + (size_t)(rowok ? a : 0) * G;
+            double* drow = in_s + r * pitch;
+            for (int c = threadIdx.x & 31; c < pitch; c += 32) {
+                const int b = ox0 - w + c;
+                double v = 0;
+                if (rowok && c < ncol + 8 && b >= 0 && b < G) v = srow[b];
+                drow[(c & 7) * q + (c >> 3)] = v;
             }
-            in_s[r * pitch + (c & 7) * q + (c >> 3)] = v;
         }
         __syncthreads();
         for (int kk = 0; kk < kc; kk++) {
@@ -952,12 +953,7 @@ __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__
         if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
         const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
         auto src = [&](int a, int b) {  // unfolded source element
-            double v = jb.hist[(size_t)a * G + b];
-            if (MODE == 1) {
-                const double p = P[(size_t)a * G + b];
-                if (p > thr) v = v / p;
-            }
-            return v;
+            return (MODE == 1) ? jb.box[(size_t)a * G + b] : jb.hist[(size_t)a * G + b];
         };
         auto folded = [&](int a, int b) {  // element (a, b) of the folded array
             double v = src(a, b);
@@ -1096,5 +1092,19 @@ __global__ void __launch_bounds__(1024) k_hist2d_hot(const HotTile* __restrict__
             const unsigned long long v = ((unsigned long long)base[HW * HW + i] << 32) | base[i];
             if (v) atomicAdd(grids + off + (long long)(T.by0[pb] + (i / HW)) * 256 + T.ax0[pa] + (i % HW), v);
         }
+    }
+}
+
+// box = hist / P where P > 1e-8 max(P), else hist (mcsamples.py:1969-1971): the input of bias iteration `iter`.
+// grid (64, njobs)
+__global__ void __launch_bounds__(256) k_make_box(const ConvJob* __restrict__ jobs, int iter) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (iter >= jb.mbc) return;
+    const size_t gg = (size_t)jb.G * jb.G;
+    const double* P = (iter & 1) ? jb.Pn : jb.P;
+    const double thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < gg; o += (size_t)gridDim.x * blockDim.x) {
+        const double h = jb.hist[o], p = P[o];
+        jb.box[o] = p > thr ? h / p : h;
     }
 }
