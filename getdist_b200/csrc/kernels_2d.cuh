@@ -380,7 +380,7 @@ struct Bw2dJob {
 };
 
 // grid (npairs), 512 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
-__global__ void __launch_bounds__(512) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
+__global__ void __launch_bounds__(256, 3) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
                                               const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res) {
     extern __shared__ __align__(16) unsigned char bsm[];
     __shared__ double red[32];
@@ -540,9 +540,17 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
                 const int qi = 1 + (tb >> 3);
 #pragma unroll
                 for (int j = 0; j < 8; j++) nx[j] = irow[j * q + qi];  // columns tx*8 + tb + 8 + j
+                // eight taps as four 16-byte (broadcast) loads
+                double wv8[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(wr + tb + j);
+                    wv8[j] = t2.x;
+                    wv8[j + 1] = t2.y;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const double wv = wr[tb + j];
+                    const double wv = wv8[j];
                     // window of tap tb+j: columns tx*8 + tb + j + m, m = 0..7  ->  v[j+m] for j+m < 8, else nx[j+m-8]
                     if (!moments) {
 #pragma unroll
