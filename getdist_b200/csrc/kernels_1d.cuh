@@ -29,6 +29,18 @@ __device__ __forceinline__ int bin_index_trunc(double x, double rmin, double dx,
     return (int)__ddiv_rn(d, dx);
 }
 
+// Same result as bin_index_trunc with the quotient evaluated in 32-bit fixed point (one DMUL + F2I): the low 20 bits
+// of I are the fractional part, and only when it lies within 8 * 2^-20 of an integer -- or the conversion saturated
+// (d < 0 -> 0, huge -> 0xffffffff) -- is the exact IEEE division executed, out of line.  The approximation error of
+// d * inv is < 2^-40 bins for indices below 4096, so the fast path never disagrees with the division.
+__device__ __noinline__ int bin_index_trunc_exact(double d, double dx) { return (int)__ddiv_rn(d, dx); }
+__device__ __forceinline__ int bin_index_trunc_fx(double x, double rmin, double dx, double inv_scaled /* 2^20 / dx */) {
+    const double d = __dsub_rn(x, rmin);
+    const unsigned I = __double2uint_rd(__dmul_rn(d, inv_scaled));
+    if (__builtin_expect(((I & 0xfffffu) - 8u) >= (0xfffffu - 15u), 0)) return bin_index_trunc_exact(d, dx);
+    return (int)(I >> 20);
+}
+
 // ---- TMA (bulk async copy) helpers: global -> shared with an mbarrier ------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -184,6 +196,9 @@ __global__ void __launch_bounds__(256) k_hist1d_tma(const double* __restrict__ d
         for (int c = 0; c < H1_STAGES && c < nchunks; c++) issue(c);
     const unsigned fmask = (1u << jb.sh) - 1u;
     const double kscale = jb.inv_width * jb.scale, khalf = 0.5 * jb.scale;
+    unsigned hbase = (unsigned)__cvta_generic_to_shared(hlo);
+    asm volatile("mov.u32 %0, %0;" : "+r"(hbase));  // opaque: the 32-bit shared address stays in a register
+    const unsigned hoff = (unsigned)F * 4u;
     for (int c = 0; c < nchunks; c++) {
         const int s = c % H1_STAGES;
         const unsigned ph = (unsigned)((c / H1_STAGES) & 1);
@@ -219,12 +234,7 @@ __global__ void __launch_bounds__(256) k_hist1d_tma(const double* __restrict__ d
                 const unsigned I = __double2uint_rd(fma(d, kscale, khalf));
                 unsigned b = I >> jb.sh;
                 if (__builtin_expect(((I & fmask) - 8u) >= (fmask - 15u), 0)) b = bin_index_exact(d, jb.fine_width);
-                if (b < (unsigned)F) {
-                    const unsigned vlo = (unsigned)we;
-                    const unsigned old = atomicAdd(hlo + b, vlo);
-                    // high limb + carry, unconditionally: it is non-zero for almost every sample anyway
-                    atomicAdd(hhi + b, (unsigned)(we >> 32) + ((old + vlo < old) ? 1u : 0u));
-                }
+                if (b < (unsigned)F) smem_add_u64_addr(hbase + (b << 2), hoff, we);
             }
         }
     }

@@ -14,6 +14,7 @@
 //   k_boundary2d     linear boundary correction (mcsamples.py:1927-1959)
 //   k_finalize2d     normalize('max') (densities.py:71-92)
 #pragma once
+#include <type_traits>
 #include "kde2d_core.cuh"
 #include "kernels_1d.cuh"
 
@@ -21,6 +22,7 @@
 // histograms
 // ----------------------------------------------------------------------------------------------------
 #define HT 8  // tile edge (parameters per side)
+static_assert(true, "");
 #define HW 64 // edge of a shared-memory hot window (bins), see k_hist2d_hot / k_shear_hist (80 was measured: no gain)
 
 struct Tile2d {
@@ -213,8 +215,11 @@ __global__ void __launch_bounds__(1024) k_shear_hist(const double* __restrict__ 
     }
     __syncthreads();
     const bool hot = G >= HW;
+    unsigned smem0 = (unsigned)__cvta_generic_to_shared(ssm2);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem0));  // opaque: stays in a register (see k_hist2d_hot)
     const Seg sg = segs[blockIdx.x];
     const double* xi = dX + (int64_t)g.pi * ld;
+    const double p1_min = g.p1_min, dx1 = g.dx1, inv1s = g.inv1 * 1048576.0;
     for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
         const double a = ldg_stream(xi + r);
         const unsigned long long w = dWq[r];
@@ -222,21 +227,17 @@ __global__ void __launch_bounds__(1024) k_shear_hist(const double* __restrict__ 
 #pragma unroll
         for (int k = 0; k < SG; k++)
             if (k < nj) b[k] = ldg_stream(dX + (int64_t)g.pj[k] * ld + r);
-        const int b1 = bin_index_trunc(a, g.p1_min, g.dx1, g.inv1);
+        const int b1 = bin_index_trunc_fx(a, p1_min, dx1, inv1s);
         if (w == 0 || b1 < 0 || b1 >= G) continue;
         const unsigned dx = (unsigned)(b1 - ax0);
 #pragma unroll
         for (int k = 0; k < SG; k++)
             if (k < nj) {
-                const int b2 = bin_index_trunc(shear_p2(a, b[k], g.r0[k], g.r1[k]), gm[k].rmin, gm[k].dx, gm[k].inv);
+                const int b2 = bin_index_trunc_fx(shear_p2(a, b[k], g.r0[k], g.r1[k]), gm[k].rmin, gm[k].dx, gm[k].inv * 1048576.0);
                 if (b2 < 0 || b2 >= G) continue;
                 const unsigned dy = (unsigned)(b2 - by0[k]);
-                if (hot && dx < (unsigned)HW && dy < (unsigned)HW) {
-                    unsigned* base = ssm2 + k * 2 * HW * HW;
-                    const unsigned bin = dy * HW + dx;
-                    const unsigned vlo = (unsigned)w;
-                    const unsigned old = atomicAdd(base + bin, vlo);
-                    atomicAdd(base + HW * HW + bin, (unsigned)(w >> 32) + ((old + vlo < old) ? 1u : 0u));
+                if (hot && (dx | dy) < (unsigned)HW) {
+                    smem_add_u64_addr(smem0 + (unsigned)k * (2u * HW * HW * 4u) + ((dy * HW + dx) << 2), HW * HW * 4u, w);
                 } else {
                     atomicAdd(grids + g.off[k] + (long long)b2 * G + b1, w);
                 }
@@ -1016,6 +1017,7 @@ __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__
 // columns of k_bin8 (4 B + one weight per row for 4 pairs) and only sends the updates that fall outside a window
 // to L2 as REDG.  Windows are flushed once per CTA with integer global reductions.  Exactness is unchanged:
 // every path accumulates the same 64-bit fixed-point weights.
+static_assert(HW == 64, "k_hist2d_hot packs dy * HW * 4 as a byte shift");
 struct HotTile {
     const unsigned char* ia[2];
     const unsigned char* ib[2];
@@ -1038,16 +1040,25 @@ __global__ void __launch_bounds__(1024) k_hist2d_hot(const HotTile* __restrict__
     __syncthreads();
     const Seg sg = segs[blockIdx.x];
     const int na = T.na, nb = T.nb;
+    // per-CTA constants in registers: window origins replicated into the four byte lanes, grid offsets, and the
+    // 32-bit shared-memory address of window 0 (explicit .shared atomics: no generic-address arithmetic per update)
+    unsigned smem0 = (unsigned)__cvta_generic_to_shared(hsm2);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem0));  // opaque: keep it in a register instead of re-deriving it per update
+    unsigned axr[2], byr[2];
+    long long offr[2][2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        axr[p] = (unsigned)T.ax0[p] * 0x01010101u;
+        byr[p] = (unsigned)T.by0[p] * 0x01010101u;
+#pragma unroll
+        for (int q = 0; q < 2; q++) offr[p][q] = (p < na && q < nb) ? T.off[p][q] : -1;
+    }
     auto update = [&](unsigned av, unsigned bv, int pa, int pb, unsigned long long wv) {
-        const long long off = T.off[pa][pb];
+        const long long off = offr[pa][pb];
         if (off < 0) return;
-        const unsigned dx = av - (unsigned)T.ax0[pa], dy = bv - (unsigned)T.by0[pb];
-        if (dx < (unsigned)HW && dy < (unsigned)HW) {
-            unsigned* base = hsm2 + (pa * 2 + pb) * 2 * HW * HW;
-            const unsigned bin = dy * HW + dx;
-            const unsigned vlo = (unsigned)wv;
-            const unsigned old = atomicAdd(base + bin, vlo);
-            atomicAdd(base + HW * HW + bin, (unsigned)(wv >> 32) + ((old + vlo < old) ? 1u : 0u));
+        const unsigned dx = (av - axr[pa]) & 0xffu, dy = (bv - byr[pb]) & 0xffu;
+        if ((dx | dy) < (unsigned)HW) {
+            smem_add_u64_addr(smem0 + (unsigned)(pa * 2 + pb) * (2u * HW * HW * 4u) + ((dy * HW + dx) << 2), HW * HW * 4u, wv);
         } else {
             atomicAdd(grids + off + (long long)bv * 256 + av, wv);
         }
@@ -1055,26 +1066,50 @@ __global__ void __launch_bounds__(1024) k_hist2d_hot(const HotTile* __restrict__
     if ((sg.r0 & 3) == 0) {
         // four consecutive rows per thread: one 32-bit load per byte column, two 16-byte loads of weights
         const int64_t nq = (sg.r1 - sg.r0) >> 2;
-        for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
-            const int64_t r = sg.r0 + 4 * q;
-            unsigned a4[2] = {0, 0}, b4[2] = {0, 0};
+        const bool full = offr[0][0] >= 0 && offr[0][1] >= 0 && offr[1][0] >= 0 && offr[1][1] >= 0;
+        auto quads = [&](auto FULL) {
+            constexpr bool kFull = decltype(FULL)::value;
+            for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+                const int64_t r = sg.r0 + 4 * q;
+                unsigned a4[2] = {0, 0}, b4[2] = {0, 0};
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
-                if (p < na) a4[p] = *reinterpret_cast<const unsigned*>(T.ia[p] + r);
-                if (p < nb) b4[p] = *reinterpret_cast<const unsigned*>(T.ib[p] + r);
+                for (int p = 0; p < 2; p++) {
+                    if (kFull || p < na) a4[p] = *reinterpret_cast<const unsigned*>(T.ia[p] + r);
+                    if (kFull || p < nb) b4[p] = *reinterpret_cast<const unsigned*>(T.ib[p] + r);
+                }
+                const ulonglong2 w01 = ldg_stream2_u64(dWq + r), w23 = ldg_stream2_u64(dWq + r + 2);
+                // window-relative coordinates of the four rows at once (per-byte wrapping subtraction)
+                unsigned da[2], db[2];
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    da[p] = __vsub4(a4[p], axr[p]);
+                    db[p] = __vsub4(b4[p], byr[p]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned long long wv = k == 0 ? w01.x : (k == 1 ? w01.y : (k == 2 ? w23.x : w23.y));
+                    if (wv == 0) continue;
+#pragma unroll
+                    for (int pa = 0; pa < 2; pa++)
+#pragma unroll
+                        for (int pb = 0; pb < 2; pb++) {
+                            if (!kFull && offr[pa][pb] < 0) continue;  // CTA-uniform
+                            if (((da[pa] | db[pb]) & (0xC0u << (8 * k))) == 0) {  // both coordinates < 64: inside the window
+                                const unsigned dx = __byte_perm(da[pa], 0, 0x4440 | k);          // byte k -> bits 0..7
+                                const unsigned dy8 = __byte_perm(db[pb], 0, 0x4404 | (k << 4));  // byte k -> bits 8..15 = dy * HW * 4
+                                smem_add_u64_addr(smem0 + (unsigned)(pa * 2 + pb) * (2u * HW * HW * 4u) + dy8 + (dx << 2), HW * HW * 4u, wv);
+                            } else {
+                                const unsigned av = (a4[pa] >> (8 * k)) & 0xffu, bv = (b4[pb] >> (8 * k)) & 0xffu;
+                                atomicAdd(grids + offr[pa][pb] + (long long)bv * 256 + av, wv);
+                            }
+                        }
+                }
             }
-            const ulonglong2 w01 = ldg_stream2_u64(dWq + r), w23 = ldg_stream2_u64(dWq + r + 2);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned long long wv = k == 0 ? w01.x : (k == 1 ? w01.y : (k == 2 ? w23.x : w23.y));
-                if (wv == 0) continue;
-#pragma unroll
-                for (int pa = 0; pa < 2; pa++)
-#pragma unroll
-                    for (int pb = 0; pb < 2; pb++)
-                        if (pa < na && pb < nb) update((a4[pa] >> (8 * k)) & 0xffu, (b4[pb] >> (8 * k)) & 0xffu, pa, pb, wv);
-            }
-        }
+        };
+        if (full)
+            quads(std::true_type{});
+        else
+            quads(std::false_type{});
         for (int64_t r = sg.r0 + 4 * nq + threadIdx.x; r < sg.r1; r += blockDim.x) {  // tail rows
             const unsigned long long wv = dWq[r];
             if (wv == 0) continue;

@@ -81,6 +81,19 @@ __device__ __forceinline__ void smem_add_u64(unsigned* lo, unsigned* hi, unsigne
     if (vhi | carry) atomicAdd(hi, vhi + carry);
 }
 
+// Same, addressed by 32-bit shared-window addresses (explicit atom.shared / red.shared: the generic-pointer form
+// makes the compiler rebuild the shared window base around every update); the high limb lives `hi_off` bytes above
+// the low limb.  add.cc/addc fold the carry of the low limb into the high-limb addend.  No "memory" clobber on purpose
+// (it would make the compiler reload every shared-memory parameter after each update): the bins are only read back
+// after a __syncthreads(), which is a compiler barrier.
+__device__ __forceinline__ void smem_add_u64_addr(unsigned addr_lo, unsigned hi_off, unsigned long long v) {
+    const unsigned vlo = (unsigned)v, vhi = (unsigned)(v >> 32);
+    unsigned old, c;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr_lo), "r"(vlo));
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(c) : "r"(old), "r"(vlo), "r"(vhi));
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr_lo + hi_off), "r"(c));
+}
+
 // One histogram pass.  grid (nseg, nparams).
 //   shared_first != 0: one histogram per parameter over slot 0's interval (first pass).
 //   else             : each refining slot s owns bins [s*nbins, (s+1)*nbins).
@@ -130,6 +143,9 @@ __global__ void __launch_bounds__(1024) k_qhist(const double* __restrict__ dX, i
         if (threadIdx.x < na) atomicOr(&tbl[(int)((s_lo[threadIdx.x] - qb.klo0) >> qb.shift0)], 1u << threadIdx.x);
         __syncthreads();
     }
+    unsigned hbase = (unsigned)__cvta_generic_to_shared(hlo);
+    asm volatile("mov.u32 %0, %0;" : "+r"(hbase));  // opaque: the 32-bit shared address stays in a register
+    const unsigned hoff = (unsigned)(nh * nbins) * 4u;
     for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
         unsigned long long key[4], wq[4];
 #pragma unroll
@@ -150,7 +166,7 @@ __global__ void __launch_bounds__(1024) k_qhist(const double* __restrict__ dX, i
                 const unsigned long long d = key[k] - s_lo[0];
                 if (d <= s_w[0]) {
                     const int bin = (int)(d >> s_shift[0]);
-                    smem_add_u64(hlo + bin, hhi + bin, wq[k]);
+                    smem_add_u64_addr(hbase + ((unsigned)bin << 2), hoff, wq[k]);
                 }
             } else {
                 unsigned m = tbl[(int)((key[k] - qb.klo0) >> qb.shift0)];
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(1024) k_qhist(const double* __restrict__ dX, i
                     const unsigned long long d = key[k] - s_lo[t];
                     if (d <= s_w[t]) {
                         const int bin = s_slot[t] * nbins + (int)(d >> s_shift[t]);
-                        smem_add_u64(hlo + bin, hhi + bin, dWq[r]);
+                        smem_add_u64_addr(hbase + ((unsigned)bin << 2), hoff, dWq[r]);
                     }
                 }
             }
