@@ -127,6 +127,10 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->use_bands = eb && eb[0] == '1';
         const char* eh = getenv("GDK_HOT");
         ctx->use_hot = !(eh && eh[0] == '0');
+        const char* es = getenv("GDK_SORTED");
+        ctx->use_sorted = !(es && es[0] == '0');
+        const char* em = getenv("GDK_SORTED_MIN_N");
+        if (em) ctx->sorted_min_n = atoll(em);
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) {

@@ -85,10 +85,20 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     // ---------------- shared-memory privatised path for the 256 x 256 grids ----------------
     std::vector<char> in_bands(n, 0);
     std::vector<int> band_pairs, hot_pairs;
+    bool sorted = false;
     {
         // default for 256^2 grids: hot-window privatisation (k_bin8 + k_hist2d_hot); GDK_HOT=0 falls back to REDG tiles
         const size_t hot_smem = (size_t)4 * 2 * HW * HW * 4;
-        if (ctx->use_hot && !ctx->use_bands && ctx->N >= (1 << 17) && hot_smem + 2048 <= (size_t)ctx->max_smem)
+        // default: bucket-sorted sweep (k_bin8c + k_bucket_scatter + k_hist2d_sorted); GDK_SORTED=0 -> hot windows
+        if (ctx->use_sorted && !ctx->use_bands && ctx->N >= ctx->sorted_min_n && ctx->N < (int64_t)0xfffffff0u &&
+            (size_t)2 * 256 * 32 * 4 + 4096 <= (size_t)ctx->max_smem) {
+            for (int i = 0; i < n; i++)
+                if (specs[i].fine_bins == 256) {
+                    in_bands[i] = 1;
+                    hot_pairs.push_back(i);
+                }
+            sorted = !hot_pairs.empty();
+        } else if (ctx->use_hot && !ctx->use_bands && ctx->N >= (1 << 17) && hot_smem + 2048 <= (size_t)ctx->max_smem)
             for (int i = 0; i < n; i++)
                 if (specs[i].fine_bins == 256) {
                     in_bands[i] = 1;  // excluded from the REDG tiles
@@ -229,9 +239,72 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             rc = gdk_upload_segs(ctx, segs8, ctx->segs);
             if (rc) return rc;
             dim3 g8((unsigned)segs8.size(), (unsigned)np8);
+            const int pitch = (np8 + 31) & ~31;
+            if (sorted && (size_t)128 * pitch > (size_t)48 * 1024) sorted = false;  // very wide batches: hot windows
+            if (sorted) {
+                // ---- bucket-sorted sweep: byte bins (column- and row-major), one counting sort per parameter ----
+                const int64_t pld = (ctx->N + 31) & ~int64_t(31);
+                if (ctx->bucket.ensure((size_t)np8 * (256 + 257 + 256)) || ctx->brm.ensure((size_t)ctx->ld * pitch) ||
+                    ctx->perm.ensure((size_t)np8 * pld))
+                    return gdk_fail(ctx, GDK_ERR_NOMEM, "bucket-sorted sweep work space (%zu MB)",
+                                    ((size_t)np8 * pld * 4 + (size_t)ctx->ld * pitch) >> 20);
+                unsigned* counts = ctx->bucket.p;
+                unsigned* start = counts + (size_t)np8 * 256;
+                unsigned* cursor = start + (size_t)np8 * 257;
+                CK2(cudaMemsetAsync(counts, 0, (size_t)np8 * 256 * 4, ctx->stream));
+                k_bin8c<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld, counts);
+                k_bucket_scan<<<np8, 256, 0, ctx->stream>>>(counts, start, cursor);
+                k_bin8_rowmajor<<<(unsigned)((ctx->N + 127) / 128), 256, (size_t)128 * pitch, ctx->stream>>>(
+                    ctx->ix8.p, ctx->ld, np8, pitch, ctx->N, ctx->brm.p);
+                dim3 gs((unsigned)((ctx->N + 8191) / 8192), (unsigned)np8);
+                k_bucket_scatter<<<gs, 1024, 0, ctx->stream>>>(ctx->ix8.p, ctx->ld, ctx->N, cursor, ctx->perm.p, pld);
+                ctx->launches += 4;
+                // circular rule: the anchor of a pair is the parameter from which the other one is at most np8/2
+                // slots ahead (mod np8); every anchor gets <= np8/2 partners, 32 per job
+                struct Partner { int col, sb, sc; long long off; };
+                std::vector<std::vector<Partner>> plist(np8);
+                for (int i : hot_pairs) {
+                    const int sx = slot[specs[i].px], sy = slot[specs[i].py];
+                    const int d = ((sy - sx) % np8 + np8) % np8;
+                    const bool anchor_x = (2 * d < np8) || (2 * d == np8 && sx < sy) || sx == sy;
+                    if (anchor_x)
+                        plist[sx].push_back(Partner{sy, 256, 1, goff[i]});  // rows of bucket c fill column c: [iy][c]
+                    else
+                        plist[sy].push_back(Partner{sx, 1, 256, goff[i]});  // rows of bucket c fill row c: [c][ix]
+                }
+                std::vector<SortJob> sj;
+                for (int a = 0; a < np8; a++)
+                    for (size_t k0 = 0; k0 < plist[a].size(); k0 += 32) {
+                        SortJob j{};
+                        j.slot = a;
+                        j.nl = (int)std::min<size_t>(32, plist[a].size() - k0);
+                        j.lg = 0;
+                        while ((1 << j.lg) < j.nl) j.lg++;
+                        for (int l = 0; l < j.nl; l++) {
+                            const Partner& q = plist[a][k0 + l];
+                            j.pcol[l] = q.col;
+                            j.sb[l] = q.sb;
+                            j.sc[l] = q.sc;
+                            j.off[l] = q.off;
+                        }
+                        sj.push_back(j);
+                    }
+                SortJob* dsj = nullptr;
+                rc = upload_vec(ctx, sj, ctx->bytes2d_s, &dsj);
+                if (rc) return rc;
+                const int chunk = 16384;
+                const size_t srt_smem = (size_t)2 * 256 * 32 * 4;
+                CK2(cudaFuncSetAttribute(k_hist2d_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt_smem));
+                dim3 gh((unsigned)((ctx->N + chunk - 1) / chunk), (unsigned)sj.size());
+                k_hist2d_sorted<<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsj, ctx->perm.p, pld, start, ctx->brm.p, pitch,
+                                                                            ctx->dWq.p, ctx->gbins2.p, chunk, ctx->N);
+                ctx->launches++;
+            } else {
             k_bin8<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld);
             ctx->launches++;
-            if (!hot_pairs.empty()) {
+            }
+            if (sorted) {
+            } else if (!hot_pairs.empty()) {
                 // 2 x 2 tiles over (x parameter, y parameter); window origin from the weighted mean of each parameter
                 std::vector<int> A, B;
                 for (int i : hot_pairs) {

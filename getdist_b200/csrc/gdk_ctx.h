@@ -97,7 +97,11 @@ struct gdk_ctx {
     DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena, qbase;
     Kde2dConsts k2d;
     DevBuf<unsigned char> ix8;
-    bool cluster_ok = false, use_bands = false, use_hot = true;
+    bool cluster_ok = false, use_bands = false, use_hot = true, use_sorted = true;
+    int64_t sorted_min_n = 1 << 15;
+    DevBuf<unsigned char> brm;      // row-major byte bins [N][pitch] (bucket-sorted sweep)
+    DevBuf<unsigned> perm, bucket;  // per-parameter permutations; bucket counts / starts / cursors
+    DevBuf<unsigned char> bytes2d_s;
     // per-context (= per-device) record of opted-in dynamic shared-memory sizes
     bool q_attr_set = false;
     size_t h1_tma_smem = 0, h1_smem = 0, kde1d_smem = 0;

@@ -1151,3 +1151,248 @@ __global__ void __launch_bounds__(256) k_make_box(const ConvJob* __restrict__ jo
         jb.box[o] = p > thr ? h / p : h;
     }
 }
+
+// ----------------------------------------------------------------------------------------------------
+// bucket-sorted sweep for the 256 x 256 histograms (default path for those grids)
+// ----------------------------------------------------------------------------------------------------
+// profiles/r1s: k_hist2d_hot is bound by shared-memory atomics (L1 85 %, ~3.7 bank-conflict wavefronts per
+// update because the 32 lanes of a warp hit random bins) plus the 27 % of updates that miss the windows and go
+// to L2.  Here the rows are counting-sorted by the bin of an ANCHOR parameter a (256 buckets; one permutation per
+// parameter, built on the device), so all rows of bucket c update only column c (or row c) of the grids (a, b):
+// 256 bins per partner b.  A CTA keeps those 256 bins for 32 lanes in shared memory laid out [bin][lane]: the
+// lane index is the bank, so every shared atomic is conflict-free and two lanes of a warp never share an address.
+// A lane is one (row-slot, partner) combination: with nl <= 16 partners a warp processes 32 / nlp rows per step
+// into per-lane replica histograms that the flush sums.  Per row visit the warp gathers one row of the row-major
+// byte matrix (the partners' bins, 1-2 sectors) and the weight.  Every pair (i, j) is covered once by the circular
+// rule "anchor i has partners i+1 .. i+P/2 (mod P)".  Buckets with few rows in a chunk (distribution tails) go
+// straight to L2 reductions.  Same 64-bit fixed-point weights as every other path: bit-identical histograms.
+#define SRT_THREADS 512
+#define SRT_BIG 96  // rows of one bucket inside a chunk from which the shared-memory path pays for its flush
+struct SortJob {
+    int slot, nl, lg, pad;  // anchor slot, partners (<= 32), log2(lanes per row)
+    int pcol[32];           // partner column in the row-major byte matrix
+    int sb[32], sc[32];     // grid strides of the partner's bin / of the anchor's bucket
+    long long off[32];      // grid offsets (elements)
+};
+
+// k_bin8 + per-parameter bucket counts.  grid (nseg, nparams), 256 threads.
+__global__ void __launch_bounds__(256) k_bin8c(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
+                                               const Bin8Job* __restrict__ jobs, unsigned char* __restrict__ out, int64_t old,
+                                               unsigned* __restrict__ counts) {
+    __shared__ unsigned cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const Bin8Job jb = jobs[blockIdx.y];
+    const Seg sg = segs[blockIdx.x];
+    const double* x = dX + (int64_t)jb.param * ld;
+    unsigned char* o = out + (int64_t)blockIdx.y * old;
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        const int b = bin_index_round(ldg_stream(x + r), jb.binmin, jb.fw, jb.inv);
+        const int c = b < 0 ? 0 : (b > 255 ? 255 : b);
+        o[r] = (unsigned char)c;
+        atomicAdd(&cnt[c], 1u);
+    }
+    __syncthreads();
+    if (cnt[threadIdx.x]) atomicAdd(counts + (size_t)blockIdx.y * 256 + threadIdx.x, cnt[threadIdx.x]);
+}
+
+// exclusive scan of the 256 bucket counts of each parameter.  grid nparams, 256 threads.
+// start[p*257 + c] = first position of bucket c (start[p*257 + 256] = N); cursor[p*256 + c] = the same (consumed by
+// k_bucket_scatter).
+__global__ void __launch_bounds__(256) k_bucket_scan(const unsigned* __restrict__ counts, unsigned* __restrict__ start,
+                                                     unsigned* __restrict__ cursor) {
+    __shared__ unsigned s[256];
+    const int t = threadIdx.x, p = blockIdx.x;
+    const unsigned own = counts[(size_t)p * 256 + t];
+    s[t] = own;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const unsigned v = t >= d ? s[t - d] : 0u;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    const unsigned excl = s[t] - own;
+    start[(size_t)p * 257 + t] = excl;
+    cursor[(size_t)p * 256 + t] = excl;
+    if (t == 255) start[(size_t)p * 257 + 256] = s[255];
+}
+
+// row-major copy of the byte bins: Brm[r * pitch + slot] = ix8[slot * ld + r].  grid ceil(N / 128), 256 threads,
+// dynamic smem 128 * pitch bytes.
+__global__ void __launch_bounds__(256) k_bin8_rowmajor(const unsigned char* __restrict__ ix8, int64_t ld, int np, int pitch,
+                                                       int64_t N, unsigned char* __restrict__ Brm) {
+    extern __shared__ unsigned char btile[];  // [128][pitch]
+    const int64_t r0 = (int64_t)blockIdx.x * 128;
+    for (int i = threadIdx.x; i < 128 * pitch / 4; i += blockDim.x) reinterpret_cast<unsigned*>(btile)[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * 32; i += blockDim.x) {
+        const int p = i >> 5, q = i & 31;
+        // ld is a multiple of 64 and r0 of 128: the 4-byte word stays inside the column's allocation
+        const unsigned wv = (r0 + 4 * q < ld) ? *reinterpret_cast<const unsigned*>(ix8 + (int64_t)p * ld + r0 + 4 * q) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) btile[(4 * q + k) * pitch + p] = (unsigned char)(wv >> (8 * k));
+    }
+    __syncthreads();
+    const int64_t rows = min((int64_t)128, N - r0);
+    const int nwords = (int)(rows * pitch / 4);
+    unsigned* o = reinterpret_cast<unsigned*>(Brm + r0 * pitch);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) o[i] = reinterpret_cast<const unsigned*>(btile)[i];
+}
+
+// counting-sort scatter: perm[slot * pld + position] = row, rows grouped by the bucket of parameter `slot`.
+// grid (ceil(N / 8192), nparams), 1024 threads, 8 rows per thread.  Order inside a bucket is arbitrary (the
+// histograms are integer sums).
+__global__ void __launch_bounds__(1024) k_bucket_scatter(const unsigned char* __restrict__ ix8, int64_t ld, int64_t N,
+                                                         unsigned* __restrict__ cursor, unsigned* __restrict__ perm, int64_t pld) {
+    __shared__ unsigned cnt[256], base[256];
+    const int p = blockIdx.y;
+    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned char* col = ix8 + (int64_t)p * ld;
+    const int64_t r0 = (int64_t)blockIdx.x * 8192;
+    unsigned wv[2], rank[8];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int64_t rr = r0 + ((int64_t)k * 1024 + threadIdx.x) * 4;
+        wv[k] = rr < N ? *reinterpret_cast<const unsigned*>(col + rr) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (rr + j < N) rank[k * 4 + j] = atomicAdd(&cnt[(wv[k] >> (8 * j)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256 && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + (size_t)p * 256 + threadIdx.x, cnt[threadIdx.x]);
+    __syncthreads();
+    unsigned* pm = perm + (int64_t)p * pld;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int64_t rr = r0 + ((int64_t)k * 1024 + threadIdx.x) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (rr + j < N) pm[base[(wv[k] >> (8 * j)) & 255u] + rank[k * 4 + j]] = (unsigned)(rr + j);
+    }
+}
+
+// grid (nchunks, njobs), SRT_THREADS threads, dynamic smem = 2 * 256 * 32 * 4 bytes (lo limbs, hi limbs; [bin][lane]).
+__global__ void __launch_bounds__(SRT_THREADS, 2)
+    k_hist2d_sorted(const SortJob* __restrict__ jobs, const unsigned* __restrict__ perm, int64_t pld,
+                    const unsigned* __restrict__ start, const unsigned char* __restrict__ Brm, int pitch,
+                    const unsigned long long* __restrict__ wq, unsigned long long* __restrict__ grids, int chunk, int64_t N) {
+    extern __shared__ unsigned ssrt[];  // lo[256 * 32], hi[256 * 32]
+    __shared__ SortJob J;
+    __shared__ unsigned sst[257];
+    {
+        const int* src = reinterpret_cast<const int*>(jobs + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&J);
+        for (int i = threadIdx.x; i < (int)(sizeof(SortJob) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < 2 * 256 * 32; i += blockDim.x) ssrt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) sst[i] = start[(size_t)J.slot * 257 + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lg = J.lg, nlp = 1 << lg;      // lanes per row
+    const int rs = lane >> lg, pl = lane & (nlp - 1), R = 32 >> lg;  // row slot of this lane, partner, rows per step
+    const bool act = pl < J.nl;
+    const int pcol = act ? J.pcol[pl] : 0, acol = J.slot;
+    const long long off = act ? J.off[pl] : 0;
+    const int sb = act ? J.sb[pl] : 0, sc = act ? J.sc[pl] : 0;
+    const unsigned* pm = perm + (int64_t)J.slot * pld;
+    unsigned smem_lane = (unsigned)__cvta_generic_to_shared(ssrt) + (unsigned)lane * 4u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem_lane));
+    const int64_t cs = (int64_t)blockIdx.x * chunk, ce = min(N, cs + (int64_t)chunk);
+
+    // rows [lo, hi) of the permutation; SMEM_PATH: into the shared bins of one bucket, else straight to the grids in L2
+    const unsigned char* rowp = Brm + pcol;  // + row * pitch = this lane's partner byte
+    asm volatile("mov.u64 %0, %0;" : "+l"(rowp));  // opaque: one register pair, one IMAD.WIDE per row
+    const unsigned upitch = (unsigned)pitch;
+    auto rows = [&](int64_t lo, int64_t hi, auto SMEM_PATH) {
+        constexpr bool kSmem = decltype(SMEM_PATH)::value;
+        for (int64_t b0 = lo + (int64_t)warp * 32; b0 < hi; b0 += (int64_t)nwarps * 32) {
+            const bool fullblk = b0 + 32 <= hi;
+            const unsigned rl = (fullblk || b0 + lane < hi) ? pm[b0 + lane] : 0xffffffffu;
+            for (int it0 = 0; it0 < nlp; it0 += 4) {  // nlp steps cover the 32 positions, 4 steps of loads in flight
+                unsigned rr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) rr[u] = __shfl_sync(0xffffffffu, rl, ((it0 + u) * R + rs) & 31);
+                if (!act) continue;
+                if (fullblk && it0 + 4 <= nlp) {  // common case: every step of the batch is a real row
+                    unsigned bv[4], cv[4];
+                    unsigned long long wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned char* row = rowp + (unsigned long long)rr[u] * upitch;
+                        bv[u] = *row;
+                        if (!kSmem) cv[u] = row[acol - pcol];
+                        wv[u] = wq[rr[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (kSmem)
+                            smem_add_u64_addr(smem_lane + bv[u] * 128u, 256u * 32u * 4u, wv[u]);
+                        else if (wv[u])
+                            atomicAdd(grids + off + (long long)bv[u] * sb + (long long)cv[u] * sc, wv[u]);
+                    }
+                } else {
+                    for (int u = 0; u < 4; u++) {
+                        if (it0 + u >= nlp || rr[u] == 0xffffffffu) continue;
+                        const unsigned char* row = rowp + (unsigned long long)rr[u] * upitch;
+                        const unsigned bvv = *row;
+                        const unsigned long long wvv = wq[rr[u]];
+                        if (kSmem)
+                            smem_add_u64_addr(smem_lane + bvv * 128u, 256u * 32u * 4u, wvv);
+                        else if (wvv)
+                            atomicAdd(grids + off + (long long)bvv * sb + (long long)row[acol - pcol] * sc, wvv);
+                    }
+                }
+            }
+        }
+    };
+    auto flush = [&](int c) {
+        for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {  // i & 31 == lane: this thread's own partner
+            const unsigned vlo = ssrt[i], vhi = ssrt[256 * 32 + i];
+            if (vlo | vhi) {
+                atomicAdd(grids + off + (long long)(i >> 5) * sb + (long long)c * sc, ((unsigned long long)vhi << 32) | vlo);
+                ssrt[i] = 0;
+                ssrt[256 * 32 + i] = 0;
+            }
+        }
+    };
+    // first bucket that reaches into this chunk: largest c with sst[c] <= cs
+    int c = 0;
+    {
+        int lo = 0, hi = 256;  // invariant: sst[lo] <= cs, (hi == 256 or sst[hi] > cs)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int64_t)sst[mid] <= cs) lo = mid; else hi = mid;
+        }
+        c = lo;
+    }
+    while (c < 256) {
+        const int64_t s0 = sst[c], s1 = sst[c + 1];
+        if (s0 >= ce) break;
+        const int64_t lo = max(s0, cs), hi = min(s1, ce);
+        if (hi <= lo) {
+            c++;
+            continue;
+        }
+        if (hi - lo >= SRT_BIG) {
+            rows(lo, hi, std::true_type{});
+            __syncthreads();
+            flush(c);
+            __syncthreads();
+            c++;
+        } else {  // a run of small buckets: one pass, the bucket comes from the row's own byte
+            int c2 = c + 1;
+            int64_t end = hi;
+            while (c2 < 256 && (int64_t)sst[c2] < ce) {
+                const int64_t e2 = min((int64_t)sst[c2 + 1], ce);
+                if (e2 - (int64_t)sst[c2] >= SRT_BIG) break;
+                end = e2;
+                c2++;
+            }
+            rows(lo, end, std::false_type{});
+            c = c2;
+        }
+    }
+}

@@ -108,6 +108,7 @@ class Grid1D:
     h: float | None = None  # bandwidth fraction actually used (kde_h after fallback), for diagnostics
     winw: int = 0
     smooth_bins: float = 0.0
+    likes: np.ndarray | None = None  # mean likelihoods (meanlikes=True), mcsamples.py:1672-1684
 
 
 @dataclass
@@ -122,6 +123,8 @@ class Grid2D:
     winw: int = 0
     fine_bins: int = 0
     extra: dict = field(default_factory=dict)
+    likes: np.ndarray | None = None  # mean likelihoods (meanlikes=True, get_density=False), mcsamples.py:2004-2006
+    mask: np.ndarray | None = None   # bool_mask of a mask_function, mcsamples.py:1917, 1986
 
 
 # --------------------------------------------------------------------------------------
@@ -673,13 +676,16 @@ class OracleSamples:
     """Restates the MCSamples/Chains/WeightedSamples hot-path surface."""
 
     def __init__(self, samples, weights=None, names=None, ranges=None, sampler="uncorrelated", settings=None,
-                 chain_offsets=None):
+                 chain_offsets=None, loglikes=None):
         if isinstance(samples, (list, tuple)):
             # chains.py:1488-1503 (makeSingle)
             chain_offsets = np.cumsum([0] + [s.shape[0] for s in samples])
             if weights is not None:
                 weights = np.hstack(list(weights))
+            if loglikes is not None:
+                loglikes = np.hstack(list(loglikes))
             samples = np.vstack(list(samples))
+        self.loglikes = None if loglikes is None else np.asarray(loglikes, dtype=np.float64)
         self.samples = np.asarray(samples, dtype=np.float64)
         self.numrows, self.n = self.samples.shape
         self.weights = np.ones(self.numrows) if weights is None else np.asarray(weights, dtype=np.float64)
@@ -701,6 +707,8 @@ class OracleSamples:
     def update_base_statistics(self):
         self.norm = np.sum(self.weights)
         self.means = weighted_means(self.samples, self.weights)
+        # chains.py:380-383
+        self.mean_loglike = None if self.loglikes is None else self.weights.dot(self.loglikes) / self.norm
         self.vars = weighted_vars(self.samples, self.weights, self.means)
         self.sddev = np.sqrt(self.vars)
         self.mean_mult = self.norm / self.numrows
@@ -783,8 +791,8 @@ class OracleSamples:
             return h * N_eff ** (1.0 / 5 - 1.0 / (4 * m + 5))
         return h
 
-    def density_1d(self, j, **kwargs):
-        """mcsamples.py:1517-1686 (``get1DDensityGridData``), meanlikes=False, non-periodic."""
+    def density_1d(self, j, meanlikes=False, **kwargs):
+        """mcsamples.py:1517-1686 (``get1DDensityGridData``)."""
         j = self._num(j)
         par = self.init_param_ranges(j)
         s = self.settings
@@ -801,6 +809,12 @@ class OracleSamples:
         binmin, binmax, fine_width = bin_geometry(par, fine_bins)
         ix = bin_indices(self.samples[:, j], binmin, fine_width)
         bins = np.bincount(ix, weights=self.weights, minlength=fine_bins)
+        if meanlikes:  # mcsamples.py:1556-1561
+            if s.get("shade_likes_is_mean_loglikes", False):
+                lw = self.weights * self.loglikes
+            else:
+                lw = self.weights * np.exp(self.mean_loglike - self.loglikes)
+            finebinlikes = np.bincount(ix, weights=lw, minlength=fine_bins)
 
         if smooth_scale_1D <= 0:
             bandwidth = self.auto_bandwidth_1d(bins, par, mult_bias_correction_order, boundary_correction_order) * (
@@ -823,6 +837,8 @@ class OracleSamples:
             return conv1d_periodic(a, Win) if par.periodic else conv1d(a, Win, "same")
 
         P = cconv(bins)
+        if meanlikes:
+            rawbins = P.copy()  # mcsamples.py:1597-1598
         if par.has_limits and not par.periodic and boundary_correction_order >= 0:
             # mcsamples.py:1600-1637
             prior_mask = np.ones(fine_bins + 2 * winw)
@@ -888,7 +904,19 @@ class OracleSamples:
             raise OracleDensityError("no samples in bin")
         P = P / mx  # densities.py:71-92, by='max'
         x = np.linspace(binmin, binmax, fine_bins)
-        return Grid1D(x, P, (par.range_min, par.range_max), h=par.kde_h, winw=winw, smooth_bins=smooth_1D)
+        likes = None
+        if meanlikes:  # mcsamples.py:1672-1682
+            sel = P > 0
+            finebinlikes[sel] /= P[sel]
+            binlikes = cconv(finebinlikes)
+            binlikes[sel] *= P[sel] / rawbins[sel]
+            if s.get("shade_likes_is_mean_loglikes", False):
+                maxbin = np.min(binlikes)
+                binlikes = np.where((binlikes - maxbin) < 30, np.exp(-(binlikes - maxbin)), 0)
+                binlikes[rawbins == 0] = 0
+            binlikes /= np.max(binlikes)
+            likes = binlikes
+        return Grid1D(x, P, (par.range_min, par.range_max), h=par.kde_h, winw=winw, smooth_bins=smooth_1D, likes=likes)
 
     # ---- 2D ---------------------------------------------------------------------------
     def _hist2d(self, ixs, iys, xsize, ysize):
@@ -975,9 +1003,8 @@ class OracleSamples:
             hy *= scale
         return hx, hy, c, info
 
-    def density_2d(self, j, j2, **kwargs):
-        """mcsamples.py:1748-1990 (``get2DDensityGridData(get_density=True)``), meanlikes=False,
-        no mask_function, non-periodic."""
+    def density_2d(self, j, j2, meanlikes=False, mask_function=None, **kwargs):
+        """mcsamples.py:1748-2010 (``get2DDensityGridData``; ``likes`` as in the get_density=False return)."""
         j, j2 = self._num(j), self._num(j2)
         parx = self.init_param_ranges(j)
         pary = self.init_param_ranges(j2)
@@ -987,7 +1014,7 @@ class OracleSamples:
         mult_bias_correction_order = kwargs.get("mult_bias_correction_order", s["mult_bias_correction_order"])
         smooth_scale_2D = float(kwargs.get("smooth_scale_2D", s["smooth_scale_2D"]))
         max_corr_2D = s["max_corr_2D"]
-        has_prior = parx.has_limits or pary.has_limits
+        has_prior = parx.has_limits or pary.has_limits or mask_function is not None  # mcsamples.py:1794
 
         corr = self.get_correlation_matrix()[j2][j]
         actual_corr = corr
@@ -1011,6 +1038,10 @@ class OracleSamples:
         iys = bin_indices(self.samples[:, j2], ybinmin, finewidthy)
         xsize = ysize = fine_bins_2D
         histbins = self._hist2d(ixs, iys, xsize, ysize)
+        if meanlikes:  # mcsamples.py:1829-1831
+            likeweights = self.weights * np.exp(self.mean_loglike - self.loglikes)
+            finebinlikes = np.bincount(ixs + iys * xsize, weights=likeweights, minlength=xsize * ysize).reshape(
+                (ysize, xsize))
         info = {}
         if smooth_scale_2D < 0:
             rx, ry, corr, info = self.auto_bandwidth_2d(
@@ -1043,9 +1074,26 @@ class OracleSamples:
             cmode = "same"
         both_periodic = parx.periodic and pary.periodic
         bins2D = conv2d(histbins, Win, cmode)
+        bin2Dlikes = None
+        if meanlikes:  # mcsamples.py:1886-1901
+            bin2Dlikes = conv2d(finebinlikes, Win, cmode)
+            if mult_bias_correction_order:
+                lsel = bin2Dlikes > 0
+                finebinlikes[lsel] /= bin2Dlikes[lsel]
+                likes2 = conv2d(finebinlikes, Win, cmode)
+                likes2[lsel] *= bin2Dlikes[lsel]
+                bin2Dlikes = likes2
+            mxl = 1e-4 * np.max(bins2D)
+            bin2Dlikes[bins2D > mxl] /= bins2D[bins2D > mxl]
+            bin2Dlikes[bins2D <= mxl] = 0
         prior_mask = None
-        if has_prior and boundary_correction_order >= 0 or mult_bias_correction_order:
+        bool_mask = None
+        if has_prior and boundary_correction_order >= 0 or mult_bias_correction_order or mask_function:
             prior_mask = np.ones((ysize + 2 * winw, xsize + 2 * winw))
+            if mask_function:  # mcsamples.py:1909-1919
+                mask_function(xbinmin - winw * finewidthx, ybinmin - winw * finewidthy, finewidthx, finewidthy,
+                              prior_mask)
+                bool_mask = prior_mask[winw:-winw, winw:-winw] < 1e-8
         if has_prior and boundary_correction_order >= 0 and not both_periodic:
             # mcsamples.py:1921-1961 with edge masks :1688-1703 (non-periodic axes only)
             if not parx.periodic:
@@ -1104,7 +1152,12 @@ class OracleSamples:
                 sel2 = bins2D > np.max(bins2D) * 1e-8
                 box[sel2] /= bins2D[sel2]
                 bins2D *= conv2d(box, Win, cmode)
-                bins2D /= a00
+                if mask_function:
+                    bins2D[~bool_mask] /= a00[~bool_mask]
+                else:
+                    bins2D /= a00
+        if mask_function:
+            bins2D[bool_mask] = 0
         mx = np.max(bins2D)
         if mx == 0:
             raise OracleDensityError("no samples in bin")
@@ -1113,6 +1166,9 @@ class OracleSamples:
         y = np.linspace(ybinmin, ybinmax, ysize)
         g = Grid2D(x, y, bins2D, ((parx.range_min, parx.range_max), (pary.range_min, pary.range_max)),
                    rx=rx, ry=ry, corr=corr, winw=winw, fine_bins=fine_bins_2D)
+        if meanlikes:  # mcsamples.py:2004-2006
+            g.likes = bin2Dlikes / np.max(bin2Dlikes)
+        g.mask = bool_mask
         g.extra = {k: v for k, v in info.items() if k != "opt"}
         opt = info.get("opt")
         if opt is not None:

@@ -139,6 +139,40 @@ def case_periodic():
                 kwargs_2d=[{}, {"fine_bins_2D": 64}, {"mult_bias_correction_order": 0, "fine_bins_2D": 64}])
 
 
+def likes_mask(minx, miny, stepx, stepy, mask):
+    """mask_function of case_likes (signature of mcsamples.py:1909-1916): excludes the half plane x + 0.5 y > 1.2,
+    which holds no samples (with samples inside the masked region the reference's linear boundary correction
+    divides noise by noise there and its result changes at the 1e-2 level with the FFT size)"""
+    ny, nx = mask.shape
+    x = minx + stepx * np.arange(nx)
+    y = miny + stepy * np.arange(ny)
+    mask[(x[None, :] + 0.5 * y[:, None]) > 1.2] = 0
+
+
+def case_likes():
+    """meanlikes / mask_function: correlated Gaussian with its true -log(likelihood), one parameter
+    cut by a hard prior, Exponential weights; 1D mean likelihoods, 2D mean likelihoods (with and without the bias
+    correction) and a prior mask on pair (0, 1)."""
+    rng = np.random.default_rng(909)
+    N, P = 40000, 4
+    L = _ar1_chol(P, 0.6)
+    out = np.empty((0, P))
+    while out.shape[0] < N:
+        Z = rng.normal(size=(N, P)).dot(L.T)
+        out = np.vstack([out, Z[(Z[:, 2] > -0.8) & (Z[:, 0] + Z[:, 1] < 1.2)]])  # l0 + 0.5 l1 < 1.2: the prior of likes_mask
+    Z = out[:N]
+    Rinv = np.linalg.inv(L.dot(L.T))
+    loglikes = 0.5 * np.einsum("ni,ij,nj->n", Z, Rinv, Z) + 3.7
+    X = np.ascontiguousarray(Z * np.array([1.0, 2.0, 0.5, 30.0]) + np.array([0.0, 0.0, 0.0, 400.0]))
+    w = np.random.default_rng(910).exponential(1.0, N)
+    return dict(samples=X, weights=w, loglikes=loglikes, names=["l0", "l1", "l2", "l3"], ranges={"l2": (-0.4, None)},
+                settings={}, pairs=[(0, 1), (1, 2), (3, 2)], kwargs_1d=[{}], kwargs_2d=[{}],
+                meanlikes=True, likes_kwargs_1d=[{}, {"mult_bias_correction_order": 0}, {"smooth_scale_1D": 0.4}],
+                likes_kwargs_2d=[{}, {"mult_bias_correction_order": 0}, {"smooth_scale_2D": 0.5, "fine_bins_2D": 128}],
+                mask_function=likes_mask, mask_pairs=[(0, 1)],
+                mask_kwargs_2d=[{}, {"mult_bias_correction_order": 0, "fine_bins_2D": 128}])
+
+
 CASES = {
     "mix3": case_mix3,
     "unit5": case_unit5,
@@ -147,6 +181,7 @@ CASES = {
     "chains": case_chains,
     "mcmc": case_mcmc,
     "periodic": case_periodic,
+    "likes": case_likes,
 }
 
 
@@ -159,6 +194,8 @@ def input_digest(case):
     if w is not None:
         for a in (w if isinstance(w, list) else [w]):
             h.update(np.ascontiguousarray(a).tobytes())
+    if case.get("meanlikes"):  # cases whose goldens depend on the log-likelihoods
+        h.update(np.ascontiguousarray(case["loglikes"]).tobytes())
     return h.hexdigest()
 
 

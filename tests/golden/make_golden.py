@@ -86,6 +86,28 @@ def run_case(name):
             if not kw:
                 dc = mc.get2DDensityGridData(jx, jy, num_plot_contours=3)
                 out["d2/%s/%d_%d/contours" % (tag, jx, jy)] = np.asarray(dc.contours)
+    if case.get("meanlikes"):
+        out["mean_loglike"] = np.array(mc.mean_loglike)
+        for kw in case["likes_kwargs_1d"]:
+            tag = kw_tag(kw)
+            for j in range(P):
+                d = mc.get1DDensityGridData(j, meanlikes=True, **kw)
+                out["l1/%s/%d/P" % (tag, j)] = d.P
+                out["l1/%s/%d/likes" % (tag, j)] = d.likes
+        for kw in case["likes_kwargs_2d"]:
+            tag = kw_tag(kw)
+            for (jx, jy) in case["pairs"]:
+                d = mc.get2DDensityGridData(jx, jy, meanlikes=True, **kw)
+                out["l2/%s/%d_%d/P" % (tag, jx, jy)] = d.P
+                out["l2/%s/%d_%d/likes" % (tag, jx, jy)] = d.likes
+                out["l2/%s/%d_%d/contours" % (tag, jx, jy)] = np.asarray(d.contours)
+    if case.get("mask_function"):
+        for kw in case["mask_kwargs_2d"]:
+            tag = kw_tag(kw)
+            for (jx, jy) in case["mask_pairs"]:
+                d = mc.get2DDensityGridData(jx, jy, mask_function=case["mask_function"], get_density=True, **kw)
+                out["m2/%s/%d_%d/P" % (tag, jx, jy)] = d.P
+                out["m2/%s/%d_%d/mask" % (tag, jx, jy)] = np.asarray(d.mask)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "ok", len(out), "arrays")
 

@@ -24,4 +24,5 @@ def make_oracle(case):
     from oracle.getdist_oracle import OracleSamples
 
     return OracleSamples(case["samples"], case["weights"], names=case["names"], ranges=case["ranges"],
-                         sampler=case.get("sampler", "uncorrelated"), settings=case["settings"])
+                         sampler=case.get("sampler", "uncorrelated"), settings=case["settings"],
+                         loglikes=case.get("loglikes") if case.get("meanlikes") else None)

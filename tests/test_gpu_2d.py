@@ -160,16 +160,21 @@ def test_repeatable(gpu_objs):
         assert np.array_equal(x.P, y.P)
 
 
-@pytest.mark.parametrize("mode", ["hot", "bands", "tiles"])
+HIST2D_MODES = {"sorted": {}, "hot": {"GDK_SORTED": "0"}, "bands": {"GDK_BANDS": "1"},
+                "tiles": {"GDK_HOT": "0", "GDK_SORTED": "0"}}
+
+
+@pytest.mark.parametrize("mode", list(HIST2D_MODES))
 def test_privatised_paths_match_bincount(mode):
-    """N >= 2^17 and 256^2 grids: default hot-window path (k_bin8 + k_hist2d_hot), the opt-in cluster/multicast path
-    (GDK_BANDS=1: k_hist2d_bands) and the REDG tiles (GDK_HOT=0) must all reproduce np.bincount"""
+    """N >= 2^17 and 256^2 grids: the default bucket-sorted sweep (k_bin8c + k_bucket_scatter + k_hist2d_sorted), the
+    hot-window path (GDK_SORTED=0: k_bin8 + k_hist2d_hot), the opt-in cluster/multicast path (GDK_BANDS=1:
+    k_hist2d_bands) and the REDG tiles (GDK_HOT=0) must all reproduce np.bincount"""
     import os
 
     from getdist_b200 import MCSamples
     from oracle.getdist_oracle import bin_indices
 
-    env = {"hot": {}, "bands": {"GDK_BANDS": "1"}, "tiles": {"GDK_HOT": "0"}}[mode]
+    env = HIST2D_MODES[mode]
     os.environ.update(env)  # read at context creation
 
     rng = np.random.default_rng(12)
@@ -226,3 +231,40 @@ def test_vectorised_planner_equals_per_pair_planner(gpu_objs, name):
                 if fname == "contours":
                     continue
                 assert a == b, (name, kw, j, j2, fname, a, b)
+
+
+@pytest.mark.parametrize("P,N", [(2, 40_001), (9, 70_000), (40, 50_003), (70, 33_000)])
+def test_sorted_sweep_partner_layouts(P, N):
+    """bucket-sorted sweep with 1 partner (32 rows per warp step), 4 (8 rows), 20 (1 row, 12 idle lanes) and 35
+    partners per anchor (two lane groups), plus reversed / duplicated pair requests: every grid == np.bincount"""
+    from getdist_b200 import MCSamples
+    from oracle.getdist_oracle import bin_indices
+
+    rng = np.random.default_rng(100 + P)
+    rho = 0.5
+    Z = rng.normal(size=(N, P))
+    X = np.empty_like(Z)
+    X[:, 0] = Z[:, 0]
+    for k in range(1, P):
+        X[:, k] = rho * X[:, k - 1] + np.sqrt(1 - rho * rho) * Z[:, k]
+    X = X * 10.0 ** rng.uniform(-2, 2, P) + rng.uniform(-5, 5, P)
+    w = rng.exponential(1.0, N)
+    w[rng.random(N) < 0.02] = 0.0
+    mc = MCSamples(samples=X, weights=w, names=["p%d" % i for i in range(P)], sampler="uncorrelated")
+    pairs = [(i, k) for i in range(P) for k in range(i + 1, P)]
+    pairs += [(P - 1, 0), (1, 0), (0, 1)]  # reversed and duplicated requests
+    mc._ensure_param_ranges(range(P))
+    mc._ensure_neff(range(P))
+    specs = [mc._spec_2d(j, j2, {"fine_bins_2D": 256}) for (j, j2) in pairs]
+    assert all(s.fine_bins == 256 for s in specs)
+    buf, offs = mc._ctx.hist2d_batch(specs)
+    G = 256
+    bins = {}
+    for sp, off in zip(specs, offs):
+        for p, lo, hi in ((sp.px, sp.xbinmin, sp.xbinmax), (sp.py, sp.ybinmin, sp.ybinmax)):
+            if p not in bins:
+                bins[p] = bin_indices(X[:, p], lo, (hi - lo) / (G - 1))
+        ref = np.bincount(bins[sp.px] + bins[sp.py] * G, weights=w, minlength=G * G)
+        got = buf[off: off + G * G]
+        assert np.all((ref == 0) == (got == 0)), (sp.px, sp.py)
+        assert np.max(np.abs(got - ref)) <= 1e-11 * np.max(ref), (sp.px, sp.py)

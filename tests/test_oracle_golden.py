@@ -78,3 +78,29 @@ def test_density_2d(name):
             st = grid_stride(d.P.shape[0])
             ref = g["d2/%s/%d_%d/P" % (tag, jx, jy)]
             assert np.max(np.abs(d.P[::st, ::st] - ref)) < 1e-9, (name, tag, jx, jy)
+
+
+def test_meanlikes_and_mask_function():
+    """mean likelihoods (mcsamples.py:1556-1561, 1672-1684, 1829-1831, 1886-1901, 2004-2006) and
+    mask_function (mcsamples.py:1909-1919, 1973-1979) of the oracle against the reference goldens"""
+    case, g = load_case("likes")
+    o = make_oracle(case)
+    np.testing.assert_allclose(o.mean_loglike, float(g["mean_loglike"]), rtol=1e-13)
+    for kw in case["likes_kwargs_1d"]:
+        tag = kw_tag(kw)
+        for j in range(o.n):
+            d = o.density_1d(j, meanlikes=True, **kw)
+            assert np.max(np.abs(d.P - g["l1/%s/%d/P" % (tag, j)])) < 1e-10
+            assert np.max(np.abs(d.likes - g["l1/%s/%d/likes" % (tag, j)])) < 1e-9, (tag, j)
+    for kw in case["likes_kwargs_2d"]:
+        tag = kw_tag(kw)
+        for (jx, jy) in case["pairs"]:
+            d = o.density_2d(jx, jy, meanlikes=True, **kw)
+            assert np.max(np.abs(d.P - g["l2/%s/%d_%d/P" % (tag, jx, jy)])) < 1e-9
+            assert np.max(np.abs(d.likes - g["l2/%s/%d_%d/likes" % (tag, jx, jy)])) < 1e-8, (tag, jx, jy)
+    for kw in case["mask_kwargs_2d"]:
+        tag = kw_tag(kw)
+        for (jx, jy) in case["mask_pairs"]:
+            d = o.density_2d(jx, jy, mask_function=case["mask_function"], **kw)
+            assert np.array_equal(d.mask, g["m2/%s/%d_%d/mask" % (tag, jx, jy)])
+            assert np.max(np.abs(d.P - g["m2/%s/%d_%d/P" % (tag, jx, jy)])) < 1e-9, (tag, jx, jy)
