@@ -257,8 +257,10 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     total_ms = 0.0
+    step_ms = []
     for _ in range(args.steps):
-        total_ms += step_resident()
+        step_ms.append(step_resident())
+        total_ms += step_ms[-1]
     barrier()
     clk = clocks.stop() if rank == 0 else None
     launches = mc._ctx.launch_count() - l0
@@ -395,7 +397,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_step": e2e_s, "checksum": checksum, "parts": e2e_parts,
                 "path": "MCSamples.setSamples(pinned host) + updateBaseStatistics [H2D + moments] -> quantiles -> 1D + 2D batches -> pinned host grids"},
-        "gpu_launches": int(launches), "phases_ms": phases, "clocks": clk, "roofline": roof, "hist1d": hist1d,
+        "gpu_launches": int(launches), "phases_ms": phases, "step_ms": [round(x, 3) for x in step_ms], "clocks": clk, "roofline": roof, "hist1d": hist1d,
         "cpu_baseline": cpu, "parity_check": parity,
     }
     print(json.dumps(line))

@@ -239,26 +239,16 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             rc = gdk_upload_segs(ctx, segs8, ctx->segs);
             if (rc) return rc;
             dim3 g8((unsigned)segs8.size(), (unsigned)np8);
-            const int pitch = (np8 + 31) & ~31;
-            if (sorted && (size_t)128 * pitch > (size_t)48 * 1024) sorted = false;  // very wide batches: hot windows
             if (sorted) {
-                // ---- bucket-sorted sweep: byte bins (column- and row-major), one counting sort per parameter ----
-                const int64_t pld = (ctx->N + 31) & ~int64_t(31);
-                if (ctx->bucket.ensure((size_t)np8 * (256 + 257 + 256)) || ctx->brm.ensure((size_t)ctx->ld * pitch) ||
-                    ctx->perm.ensure((size_t)np8 * pld))
-                    return gdk_fail(ctx, GDK_ERR_NOMEM, "bucket-sorted sweep work space (%zu MB)",
-                                    ((size_t)np8 * pld * 4 + (size_t)ctx->ld * pitch) >> 20);
-                unsigned* counts = ctx->bucket.p;
-                unsigned* start = counts + (size_t)np8 * 256;
-                unsigned* cursor = start + (size_t)np8 * 257;
-                CK2(cudaMemsetAsync(counts, 0, (size_t)np8 * 256 * 4, ctx->stream));
-                k_bin8c<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld, counts);
-                k_bucket_scan<<<np8, 256, 0, ctx->stream>>>(counts, start, cursor);
-                k_bin8_rowmajor<<<(unsigned)((ctx->N + 127) / 128), 256, (size_t)128 * pitch, ctx->stream>>>(
-                    ctx->ix8.p, ctx->ld, np8, pitch, ctx->N, ctx->brm.p);
-                dim3 gs((unsigned)((ctx->N + 8191) / 8192), (unsigned)np8);
-                k_bucket_scatter<<<gs, 1024, 0, ctx->stream>>>(ctx->ix8.p, ctx->ld, ctx->N, cursor, ctx->perm.p, pld);
-                ctx->launches += 4;
+                // ---- bucket-sorted sweep: byte bins + bucket counts, then per batch of <= 64 (anchor, 32 partners)
+                // jobs: counting-sort scatter of 32-byte records + weights, and the conflict-free sweep over them ----
+                int pitch = (np8 + 36 + 3) & ~3;
+                if (((pitch >> 2) & 1) == 0) pitch += 4;  // odd number of words per row: conflict-free row-strided loads
+                int rows = 1024;
+                auto rec_smem = [&](int r, int nj) { return (size_t)r * pitch + (size_t)nj * 256 * 8 + (size_t)r * 44 + 2048; };
+                while (rows > 32 && rec_smem(rows, SRT_MAXJOBS) + 1024 > (size_t)ctx->max_smem) rows >>= 1;
+                if (rec_smem(rows, SRT_MAXJOBS) + 1024 > (size_t)ctx->max_smem)
+                    return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "too many parameters (%d) in one 2D batch for the bucket-sorted sweep", np8);
                 // circular rule: the anchor of a pair is the parameter from which the other one is at most np8/2
                 // slots ahead (mod np8); every anchor gets <= np8/2 partners, 32 per job
                 struct Partner { int col, sb, sc; long long off; };
@@ -273,13 +263,18 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                         plist[sy].push_back(Partner{sx, 1, 256, goff[i]});  // rows of bucket c fill row c: [c][ix]
                 }
                 std::vector<SortJob> sj;
-                for (int a = 0; a < np8; a++)
+                for (int a = 0; a < np8; a++) {
+                    // partners in circular order after the anchor, so that a full triangle gives contiguous windows
+                    std::stable_sort(plist[a].begin(), plist[a].end(), [&](const Partner& x, const Partner& y) {
+                        return ((x.col - a - 1 + 2 * np8) % np8) < ((y.col - a - 1 + 2 * np8) % np8);
+                    });
                     for (size_t k0 = 0; k0 < plist[a].size(); k0 += 32) {
                         SortJob j{};
                         j.slot = a;
                         j.nl = (int)std::min<size_t>(32, plist[a].size() - k0);
                         j.lg = 0;
                         while ((1 << j.lg) < j.nl) j.lg++;
+                        for (int l = 0; l < 32; l++) j.pcol[l] = a;
                         for (int l = 0; l < j.nl; l++) {
                             const Partner& q = plist[a][k0 + l];
                             j.pcol[l] = q.col;
@@ -287,18 +282,64 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                             j.sc[l] = q.sc;
                             j.off[l] = q.off;
                         }
+                        j.c0 = j.pcol[0];
+                        for (int l = 0; l < j.nl; l++)
+                            if (j.pcol[l] != (j.c0 + l) % np8 || j.c0 + l >= np8 + std::min(32, np8)) j.c0 = -1;
                         sj.push_back(j);
                     }
+                }
+                // jobs of one launch share their lane layout: order by lanes per row (stable: anchors stay grouped)
+                std::stable_sort(sj.begin(), sj.end(), [](const SortJob& x, const SortJob& y) { return x.lg > y.lg; });
+                const int njobs = (int)sj.size();
+                const int nbatch_max = std::min(njobs, SRT_MAXJOBS);
+                const int64_t pld = (ctx->N + 31) & ~int64_t(31);
+                if (ctx->bucket.ensure((size_t)np8 * (256 + 257) + (size_t)njobs * 256) || ctx->recs.ensure((size_t)nbatch_max * pld * 32) ||
+                    ctx->recw.ensure((size_t)nbatch_max * pld))
+                    return gdk_fail(ctx, GDK_ERR_NOMEM, "bucket-sorted sweep work space (%zu MB)", ((size_t)nbatch_max * pld * 40) >> 20);
+                unsigned* counts = ctx->bucket.p;
+                unsigned* start = counts + (size_t)np8 * 256;
+                unsigned* cursor = start + (size_t)np8 * 257;
+                CK2(cudaMemsetAsync(counts, 0, (size_t)np8 * 256 * 4, ctx->stream));
+                k_bin8c<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld, counts);
+                k_bucket_scan<<<np8, 256, 0, ctx->stream>>>(counts, start);
+                ctx->launches += 2;
                 SortJob* dsj = nullptr;
                 rc = upload_vec(ctx, sj, ctx->bytes2d_s, &dsj);
                 if (rc) return rc;
+                k_cursor_init<<<njobs, 256, 0, ctx->stream>>>(dsj, start, cursor);
+                ctx->launches++;
                 const int chunk = 16384;
                 const size_t srt_smem = (size_t)2 * 256 * 32 * 4;
-                CK2(cudaFuncSetAttribute(k_hist2d_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt_smem));
-                dim3 gh((unsigned)((ctx->N + chunk - 1) / chunk), (unsigned)sj.size());
-                k_hist2d_sorted<<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsj, ctx->perm.p, pld, start, ctx->brm.p, pitch,
-                                                                            ctx->dWq.p, ctx->gbins2.p, chunk, ctx->N);
-                ctx->launches++;
+                CK2(cudaFuncSetAttribute(k_bucket_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem(rows, SRT_MAXJOBS)));
+                for (int b0 = 0; b0 < njobs; b0 += SRT_MAXJOBS) {
+                    const int nb = std::min(SRT_MAXJOBS, njobs - b0);
+                    k_bucket_records<<<(unsigned)((ctx->N + rows - 1) / rows), 1024, rec_smem(rows, nb), ctx->stream>>>(
+                        ctx->ix8.p, ctx->ld, np8, pitch, rows, ctx->N, ctx->dWq.p, dsj + b0, nb, cursor + (size_t)b0 * 256,
+                        reinterpret_cast<uint4*>(ctx->recs.p), ctx->recw.p, pld);
+                    ctx->launches++;
+                    for (int j0 = 0; j0 < nb;) {  // sub-ranges of equal lane layout
+                        int j1 = j0;
+                        while (j1 < nb && sj[b0 + j1].lg == sj[b0 + j0].lg) j1++;
+                        dim3 gh((unsigned)((ctx->N + chunk - 1) / chunk), (unsigned)(j1 - j0));
+#define GDK_LAUNCH_REC(LG)                                                                                                   \
+    case LG:                                                                                                                 \
+        CK2(cudaFuncSetAttribute(k_hist2d_records<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt_smem));        \
+        k_hist2d_records<LG><<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsj + b0, j0, ctx->recs.p, ctx->recw.p, pld, start, \
+                                                                         ctx->gbins2.p, chunk, ctx->N);                      \
+        break;
+                        switch (sj[b0 + j0].lg) {
+                            GDK_LAUNCH_REC(0)
+                            GDK_LAUNCH_REC(1)
+                            GDK_LAUNCH_REC(2)
+                            GDK_LAUNCH_REC(3)
+                            GDK_LAUNCH_REC(4)
+                            GDK_LAUNCH_REC(5)
+                        }
+#undef GDK_LAUNCH_REC
+                        ctx->launches++;
+                        j0 = j1;
+                    }
+                }
             } else {
             k_bin8<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld);
             ctx->launches++;

@@ -99,8 +99,9 @@ struct gdk_ctx {
     DevBuf<unsigned char> ix8;
     bool cluster_ok = false, use_bands = false, use_hot = true, use_sorted = true;
     int64_t sorted_min_n = 1 << 15;
-    DevBuf<unsigned char> brm;      // row-major byte bins [N][pitch] (bucket-sorted sweep)
-    DevBuf<unsigned> perm, bucket;  // per-parameter permutations; bucket counts / starts / cursors
+    DevBuf<unsigned char> recs;         // bucket-sorted sweep: 32-byte records [job][position]
+    DevBuf<unsigned long long> recw;    // ... and their fixed-point weights
+    DevBuf<unsigned> bucket;            // bucket counts / starts / write cursors
     DevBuf<unsigned char> bytes2d_s;
     // per-context (= per-device) record of opted-in dynamic shared-memory sizes
     bool q_attr_set = false;

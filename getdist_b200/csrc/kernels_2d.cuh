@@ -1157,22 +1157,27 @@ __global__ void __launch_bounds__(256) k_make_box(const ConvJob* __restrict__ jo
 // ----------------------------------------------------------------------------------------------------
 // profiles/r1s: k_hist2d_hot is bound by shared-memory atomics (L1 85 %, ~3.7 bank-conflict wavefronts per
 // update because the 32 lanes of a warp hit random bins) plus the 27 % of updates that miss the windows and go
-// to L2.  Here the rows are counting-sorted by the bin of an ANCHOR parameter a (256 buckets; one permutation per
-// parameter, built on the device), so all rows of bucket c update only column c (or row c) of the grids (a, b):
-// 256 bins per partner b.  A CTA keeps those 256 bins for 32 lanes in shared memory laid out [bin][lane]: the
-// lane index is the bank, so every shared atomic is conflict-free and two lanes of a warp never share an address.
-// A lane is one (row-slot, partner) combination: with nl <= 16 partners a warp processes 32 / nlp rows per step
-// into per-lane replica histograms that the flush sums.  Per row visit the warp gathers one row of the row-major
-// byte matrix (the partners' bins, 1-2 sectors) and the weight.  Every pair (i, j) is covered once by the circular
-// rule "anchor i has partners i+1 .. i+P/2 (mod P)".  Buckets with few rows in a chunk (distribution tails) go
-// straight to L2 reductions.  Same 64-bit fixed-point weights as every other path: bit-identical histograms.
+// to L2.  Here the rows are counting-sorted by the bin of an ANCHOR parameter a (256 buckets), so all rows of
+// bucket c update only column c (or row c) of the grids (a, b): 256 bins per partner b.  A CTA keeps those 256
+// bins for 32 lanes in shared memory laid out [bin][lane]: the lane index is the bank, so every shared atomic is
+// conflict-free and two lanes of a warp never share an address.  A lane is one (row-slot, partner) combination:
+// with nl <= 16 partners a warp processes 32 / nlp rows per step into per-lane replica histograms that the flush
+// sums.  Every pair (i, j) is covered once by the circular rule "anchor i has partners i+1 .. i+P/2 (mod P)".
+//
+// The sort is MATERIALISED (profiles/r2a: gathering rows through a permutation cost 196 B of DRAM traffic per row
+// visit, 125 GB per triangle): k_bucket_records writes, for every (anchor, 32 partners) job, one 32-byte record
+// per row -- the partners' byte bins in lane order -- plus the 64-bit fixed-point weight at the row's position in
+// bucket order; k_hist2d_records then streams records and weights sequentially (40 B per row visit).
+// Buckets with few rows in a chunk (distribution tails) go straight to L2 reductions.  Same fixed-point weights
+// as every other path: bit-identical histograms.
 #define SRT_THREADS 512
-#define SRT_BIG 96  // rows of one bucket inside a chunk from which the shared-memory path pays for its flush
+#define SRT_BIG 96      // rows of one bucket inside a chunk from which the shared-memory path pays for its flush
+#define SRT_MAXJOBS 32  // jobs per batch (shared-memory tables of k_bucket_records: 32 x 256 x 8 B)
 struct SortJob {
-    int slot, nl, lg, pad;  // anchor slot, partners (<= 32), log2(lanes per row)
-    int pcol[32];           // partner column in the row-major byte matrix
-    int sb[32], sc[32];     // grid strides of the partner's bin / of the anchor's bucket
-    long long off[32];      // grid offsets (elements)
+    int slot, nl, lg, c0;  // anchor slot, partners (<= 32), log2(lanes per row), first partner column if contiguous else -1
+    int pcol[32];          // partner column (slot) per lane
+    int sb[32], sc[32];    // grid strides of the partner's bin / of the anchor's bucket
+    long long off[32];     // grid offsets (elements)
 };
 
 // k_bin8 + per-parameter bucket counts.  grid (nseg, nparams), 256 threads.
@@ -1186,21 +1191,30 @@ __global__ void __launch_bounds__(256) k_bin8c(const double* __restrict__ dX, in
     const Seg sg = segs[blockIdx.x];
     const double* x = dX + (int64_t)jb.param * ld;
     unsigned char* o = out + (int64_t)blockIdx.y * old;
-    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const int b = bin_index_round(ldg_stream(x + r), jb.binmin, jb.fw, jb.inv);
-        const int c = b < 0 ? 0 : (b > 255 ? 255 : b);
-        o[r] = (unsigned char)c;
-        atomicAdd(&cnt[c], 1u);
+    for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
+        double xv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // four independent loads in flight
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            xv[k] = r < sg.r1 ? ldg_stream(x + r) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = r0 + (int64_t)k * blockDim.x;
+            if (r >= sg.r1) break;
+            const int b = bin_index_round(xv[k], jb.binmin, jb.fw, jb.inv);
+            const int c = b < 0 ? 0 : (b > 255 ? 255 : b);
+            o[r] = (unsigned char)c;
+            atomicAdd(&cnt[c], 1u);
+        }
     }
     __syncthreads();
     if (cnt[threadIdx.x]) atomicAdd(counts + (size_t)blockIdx.y * 256 + threadIdx.x, cnt[threadIdx.x]);
 }
 
 // exclusive scan of the 256 bucket counts of each parameter.  grid nparams, 256 threads.
-// start[p*257 + c] = first position of bucket c (start[p*257 + 256] = N); cursor[p*256 + c] = the same (consumed by
-// k_bucket_scatter).
-__global__ void __launch_bounds__(256) k_bucket_scan(const unsigned* __restrict__ counts, unsigned* __restrict__ start,
-                                                     unsigned* __restrict__ cursor) {
+// start[p*257 + c] = first position of bucket c (start[p*257 + 256] = N).
+__global__ void __launch_bounds__(256) k_bucket_scan(const unsigned* __restrict__ counts, unsigned* __restrict__ start) {
     __shared__ unsigned s[256];
     const int t = threadIdx.x, p = blockIdx.x;
     const unsigned own = counts[(size_t)p * 256 + t];
@@ -1212,77 +1226,158 @@ __global__ void __launch_bounds__(256) k_bucket_scan(const unsigned* __restrict_
         s[t] += v;
         __syncthreads();
     }
-    const unsigned excl = s[t] - own;
-    start[(size_t)p * 257 + t] = excl;
-    cursor[(size_t)p * 256 + t] = excl;
+    start[(size_t)p * 257 + t] = s[t] - own;
     if (t == 255) start[(size_t)p * 257 + 256] = s[255];
 }
 
-// row-major copy of the byte bins: Brm[r * pitch + slot] = ix8[slot * ld + r].  grid ceil(N / 128), 256 threads,
-// dynamic smem 128 * pitch bytes.
-__global__ void __launch_bounds__(256) k_bin8_rowmajor(const unsigned char* __restrict__ ix8, int64_t ld, int np, int pitch,
-                                                       int64_t N, unsigned char* __restrict__ Brm) {
-    extern __shared__ unsigned char btile[];  // [128][pitch]
-    const int64_t r0 = (int64_t)blockIdx.x * 128;
-    for (int i = threadIdx.x; i < 128 * pitch / 4; i += blockDim.x) reinterpret_cast<unsigned*>(btile)[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < np * 32; i += blockDim.x) {
-        const int p = i >> 5, q = i & 31;
-        // ld is a multiple of 64 and r0 of 128: the 4-byte word stays inside the column's allocation
-        const unsigned wv = (r0 + 4 * q < ld) ? *reinterpret_cast<const unsigned*>(ix8 + (int64_t)p * ld + r0 + 4 * q) : 0u;
-#pragma unroll
-        for (int k = 0; k < 4; k++) btile[(4 * q + k) * pitch + p] = (unsigned char)(wv >> (8 * k));
-    }
-    __syncthreads();
-    const int64_t rows = min((int64_t)128, N - r0);
-    const int nwords = (int)(rows * pitch / 4);
-    unsigned* o = reinterpret_cast<unsigned*>(Brm + r0 * pitch);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) o[i] = reinterpret_cast<const unsigned*>(btile)[i];
+// write cursors of a batch of jobs: cursor[j*256 + c] = start[slot_j*257 + c].  grid njobs, 256 threads.
+__global__ void __launch_bounds__(256) k_cursor_init(const SortJob* __restrict__ jobs, const unsigned* __restrict__ start,
+                                                     unsigned* __restrict__ cursor) {
+    cursor[(size_t)blockIdx.x * 256 + threadIdx.x] = start[(size_t)jobs[blockIdx.x].slot * 257 + threadIdx.x];
 }
 
-// counting-sort scatter: perm[slot * pld + position] = row, rows grouped by the bucket of parameter `slot`.
-// grid (ceil(N / 8192), nparams), 1024 threads, 8 rows per thread.  Order inside a bucket is arbitrary (the
-// histograms are integer sums).
-__global__ void __launch_bounds__(1024) k_bucket_scatter(const unsigned char* __restrict__ ix8, int64_t ld, int64_t N,
-                                                         unsigned* __restrict__ cursor, unsigned* __restrict__ perm, int64_t pld) {
-    __shared__ unsigned cnt[256], base[256];
-    const int p = blockIdx.y;
-    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const unsigned char* col = ix8 + (int64_t)p * ld;
-    const int64_t r0 = (int64_t)blockIdx.x * 8192;
-    unsigned wv[2], rank[8];
+// counting-sort scatter for a batch of jobs.  grid ceil(N / rows), 1024 threads.  A CTA stages its rows of the
+// column-major byte bins as a row-major tile in shared memory (row pitch `pitch`: np + 36 bytes so that the 32
+// partner columns of a contiguous circular window never wrap; pitch / 4 is odd -> conflict-free row-strided
+// loads), counts the rows per (job, bucket), reserves a range of every non-empty bucket with one global atomic,
+// and then, job by job, sorts its rows by bucket INSIDE shared memory and copies the sorted run out: the records
+// of one bucket land next to each other, so consecutive lanes write consecutive 16-byte halves (profiles/r2b: one
+// scattered 32-byte record + weight per thread ran at 1.3 TB/s of DRAM writes, bound by store-sector requests).
+// Order inside a bucket is arbitrary (integer sums).
+// dynamic smem: rows * pitch (tile) + njobs * 256 * 8 (counts -> global-minus-local offsets, local starts)
+//               + rows * 44 (staged records, weights, positions) + 2 * 256 * 4 (local cursors)
+__global__ void __launch_bounds__(1024) k_bucket_records(const unsigned char* __restrict__ ix8, int64_t ld, int np, int pitch,
+                                                         int rows, int64_t N, const unsigned long long* __restrict__ wq,
+                                                         const SortJob* __restrict__ jobs, int njobs, unsigned* __restrict__ cursor,
+                                                         uint4* __restrict__ recs, unsigned long long* __restrict__ ws, int64_t pld) {
+    extern __shared__ __align__(16) unsigned char rsm[];
+    uint4* stage_rec = reinterpret_cast<uint4*>(rsm);                                            // [rows][2]
+    unsigned long long* stage_w = reinterpret_cast<unsigned long long*>(rsm + (size_t)rows * 32);  // [rows]
+    unsigned* stage_pos = reinterpret_cast<unsigned*>(rsm + (size_t)rows * 40);                  // [rows]
+    unsigned* lcur = reinterpret_cast<unsigned*>(rsm + (size_t)rows * 44);                       // [2][256]
+    unsigned* gdel = lcur + 512;                                                                  // [njobs][256]
+    unsigned* lstart = gdel + (size_t)njobs * 256;                                                // [njobs][256]
+    unsigned char* tile = reinterpret_cast<unsigned char*>(lstart + (size_t)njobs * 256);         // [rows][pitch]
+    __shared__ int jslot[SRT_MAXJOBS], jc0[SRT_MAXJOBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows;
+    const int nrow = (int)min((int64_t)rows, N - r0);
+    for (int i = threadIdx.x; i < njobs * 256; i += blockDim.x) gdel[i] = 0;
+    if (threadIdx.x < njobs) {
+        jslot[threadIdx.x] = jobs[threadIdx.x].slot;
+        jc0[threadIdx.x] = jobs[threadIdx.x].c0;
+    }
+    // stage: a warp item = 4 parameters x 8 words (32 rows): four sectors per request, byte stores that hit 8 banks
+    // (the 4 parameters of one row share a word)
+    {
+        const int ql = lane & 7, pl = lane >> 3;
+        const int npg = (np + 3) >> 2, nqb = (rows + 31) >> 5;
+        for (int it = warp; it < npg * nqb; it += nwarps) {
+            const int pg = it / nqb, qb = it - pg * nqb;
+            const int p = pg * 4 + pl, q = qb * 8 + ql;  // word q = rows 4q .. 4q+3 of the tile
+            if (p < np && 4 * q < rows) {
+                const unsigned wv = (r0 + 4 * q < ld) ? *reinterpret_cast<const unsigned*>(ix8 + (int64_t)p * ld + r0 + 4 * q) : 0u;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int64_t rr = r0 + ((int64_t)k * 1024 + threadIdx.x) * 4;
-        wv[k] = rr < N ? *reinterpret_cast<const unsigned*>(col + rr) : 0u;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (rr + j < N) rank[k * 4 + j] = atomicAdd(&cnt[(wv[k] >> (8 * j)) & 255u], 1u);
+                for (int k = 0; k < 4; k++) {
+                    unsigned char* row = tile + (size_t)(4 * q + k) * pitch;
+                    const unsigned char b = (unsigned char)(wv >> (8 * k));
+                    row[p] = b;
+                    if (p < 32) row[np + p] = b;  // wrap-around copy of the first 32 columns
+                }
+            }
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 256 && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + (size_t)p * 256 + threadIdx.x, cnt[threadIdx.x]);
+    // phase A: rows per (job, bucket)
+    for (int t = threadIdx.x; t < nrow; t += blockDim.x) {
+        const unsigned char* row = tile + (size_t)t * pitch;
+        for (int j = 0; j < njobs; j++) atomicAdd(&gdel[j * 256 + row[jslot[j]]], 1u);
+    }
     __syncthreads();
-    unsigned* pm = perm + (int64_t)p * pld;
+    // phase B: one warp per job: exclusive scan of the 256 counts (8 buckets per lane) -> local starts; one global
+    // atomic per non-empty bucket reserves [base, base + count); gdel = base - local start
+    for (int j = warp; j < njobs; j += nwarps) {
+        unsigned v[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int64_t rr = r0 + ((int64_t)k * 1024 + threadIdx.x) * 4;
+        for (int k = 0; k < 8; k++) {
+            v[k] = gdel[j * 256 + lane * 8 + k];
+            sum += v[k];
+        }
+        unsigned incl = sum;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (rr + j < N) pm[base[(wv[k] >> (8 * j)) & 255u] + rank[k * 4 + j]] = (unsigned)(rr + j);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        unsigned pre = incl - sum;
+        unsigned base[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) base[k] = v[k] ? atomicAdd(cursor + (size_t)j * 256 + lane * 8 + k, v[k]) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            lstart[j * 256 + lane * 8 + k] = pre;
+            gdel[j * 256 + lane * 8 + k] = base[k] - pre;
+            pre += v[k];
+        }
+    }
+    __syncthreads();
+    // phase C, job by job: local counting sort into the staging buffers, then a coalesced copy-out (rows <= 1024:
+    // one row per thread)
+    const bool has_row = (int)threadIdx.x < nrow;
+    const unsigned char* row = tile + (size_t)threadIdx.x * pitch;
+    const unsigned long long wrow_q = has_row ? wq[r0 + threadIdx.x] : 0ull;
+    if (threadIdx.x < 256 && njobs > 0) lcur[threadIdx.x] = lstart[threadIdx.x];
+    for (int j = 0; j < njobs; j++) {
+        unsigned* cur = lcur + (j & 1) * 256;
+        __syncthreads();  // cursors of job j ready; copy-out of job j-1 has finished reading the staging buffers
+        const int slot = jslot[j], c0 = jc0[j];
+        if (has_row) {
+            const unsigned c = row[slot];
+            const unsigned li = atomicAdd(&cur[c], 1u);
+            unsigned v[8];
+            if (c0 >= 0) {  // contiguous window [c0, c0 + 32): nine aligned words, funnel-shifted
+                const unsigned* wrow = reinterpret_cast<const unsigned*>(row) + (c0 >> 2);
+                const unsigned sh = (unsigned)(c0 & 3) * 8u;
+                unsigned prev = wrow[0];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const unsigned next = wrow[k + 1];
+                    v[k] = __funnelshift_r(prev, next, sh);
+                    prev = next;
+                }
+            } else {
+                const int* pc = jobs[j].pcol;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    v[k] = (unsigned)row[pc[4 * k]] | ((unsigned)row[pc[4 * k + 1]] << 8) | ((unsigned)row[pc[4 * k + 2]] << 16) |
+                           ((unsigned)row[pc[4 * k + 3]] << 24);
+            }
+            stage_rec[2 * li] = make_uint4(v[0], v[1], v[2], v[3]);
+            stage_rec[2 * li + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+            stage_w[li] = wrow_q;
+            stage_pos[li] = li + gdel[j * 256 + c];
+        }
+        __syncthreads();
+        uint4* dstj = recs + (size_t)j * pld * 2;
+        for (int i = threadIdx.x; i < 2 * nrow; i += blockDim.x) dstj[(size_t)stage_pos[i >> 1] * 2 + (i & 1)] = stage_rec[i];
+        for (int i = threadIdx.x; i < nrow; i += blockDim.x) ws[(size_t)j * pld + stage_pos[i]] = stage_w[i];
+        if (threadIdx.x < 256 && j + 1 < njobs) lcur[((j + 1) & 1) * 256 + threadIdx.x] = lstart[(j + 1) * 256 + threadIdx.x];
     }
 }
 
 // grid (nchunks, njobs), SRT_THREADS threads, dynamic smem = 2 * 256 * 32 * 4 bytes (lo limbs, hi limbs; [bin][lane]).
+// LG = log2(lanes per row) of every job of the launch (the host groups jobs by it).
+template <int LG>
 __global__ void __launch_bounds__(SRT_THREADS, 2)
-    k_hist2d_sorted(const SortJob* __restrict__ jobs, const unsigned* __restrict__ perm, int64_t pld,
-                    const unsigned* __restrict__ start, const unsigned char* __restrict__ Brm, int pitch,
-                    const unsigned long long* __restrict__ wq, unsigned long long* __restrict__ grids, int chunk, int64_t N) {
+    k_hist2d_records(const SortJob* __restrict__ jobs, int job0, const unsigned char* __restrict__ recs,
+                     const unsigned long long* __restrict__ ws, int64_t pld, const unsigned* __restrict__ start,
+                     unsigned long long* __restrict__ grids, int chunk, int64_t N) {
     extern __shared__ unsigned ssrt[];  // lo[256 * 32], hi[256 * 32]
     __shared__ SortJob J;
     __shared__ unsigned sst[257];
+    const int jix = job0 + blockIdx.y;  // job index inside the batch = index of its record block
     {
-        const int* src = reinterpret_cast<const int*>(jobs + blockIdx.y);
+        const int* src = reinterpret_cast<const int*>(jobs + jix);
         int* dst = reinterpret_cast<int*>(&J);
         for (int i = threadIdx.x; i < (int)(sizeof(SortJob) / 4); i += blockDim.x) dst[i] = src[i];
     }
@@ -1290,63 +1385,59 @@ __global__ void __launch_bounds__(SRT_THREADS, 2)
     __syncthreads();
     for (int i = threadIdx.x; i < 257; i += blockDim.x) sst[i] = start[(size_t)J.slot * 257 + i];
     __syncthreads();
+    constexpr int NLP = 1 << LG, R = 32 >> LG;                  // lanes per row, rows per step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int lg = J.lg, nlp = 1 << lg;      // lanes per row
-    const int rs = lane >> lg, pl = lane & (nlp - 1), R = 32 >> lg;  // row slot of this lane, partner, rows per step
+    const int rs = lane >> LG, pl = lane & (NLP - 1);          // row slot of this lane, partner
     const bool act = pl < J.nl;
-    const int pcol = act ? J.pcol[pl] : 0, acol = J.slot;
     const long long off = act ? J.off[pl] : 0;
     const int sb = act ? J.sb[pl] : 0, sc = act ? J.sc[pl] : 0;
-    const unsigned* pm = perm + (int64_t)J.slot * pld;
+    const unsigned char* rj = recs + ((size_t)jix * pld + rs) * 32 + pl;  // + position * 32: this lane's partner byte of row slot rs
+    const unsigned long long* wj = ws + (size_t)jix * pld + rs;
     unsigned smem_lane = (unsigned)__cvta_generic_to_shared(ssrt) + (unsigned)lane * 4u;
     asm volatile("mov.u32 %0, %0;" : "+r"(smem_lane));
     const int64_t cs = (int64_t)blockIdx.x * chunk, ce = min(N, cs + (int64_t)chunk);
 
-    // rows [lo, hi) of the permutation; SMEM_PATH: into the shared bins of one bucket, else straight to the grids in L2
-    const unsigned char* rowp = Brm + pcol;  // + row * pitch = this lane's partner byte
-    asm volatile("mov.u64 %0, %0;" : "+l"(rowp));  // opaque: one register pair, one IMAD.WIDE per row
-    const unsigned upitch = (unsigned)pitch;
-    auto rows = [&](int64_t lo, int64_t hi, auto SMEM_PATH) {
-        constexpr bool kSmem = decltype(SMEM_PATH)::value;
+    // positions [lo, hi) of bucket c into the shared bins: blocks of 32 positions per warp, NLP steps of R rows
+    auto rows_smem = [&](int64_t lo, int64_t hi) {
         for (int64_t b0 = lo + (int64_t)warp * 32; b0 < hi; b0 += (int64_t)nwarps * 32) {
-            const bool fullblk = b0 + 32 <= hi;
-            const unsigned rl = (fullblk || b0 + lane < hi) ? pm[b0 + lane] : 0xffffffffu;
-            for (int it0 = 0; it0 < nlp; it0 += 4) {  // nlp steps cover the 32 positions, 4 steps of loads in flight
-                unsigned rr[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) rr[u] = __shfl_sync(0xffffffffu, rl, ((it0 + u) * R + rs) & 31);
+            const unsigned char* rb = rj + (size_t)b0 * 32;
+            const unsigned long long* wb = wj + b0;
+            if (b0 + 32 <= hi) {
                 if (!act) continue;
-                if (fullblk && it0 + 4 <= nlp) {  // common case: every step of the batch is a real row
-                    unsigned bv[4], cv[4];
+#pragma unroll
+                for (int it0 = 0; it0 < NLP; it0 += 4) {  // four steps of loads in flight
+                    unsigned bv[4];
                     unsigned long long wv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const unsigned char* row = rowp + (unsigned long long)rr[u] * upitch;
-                        bv[u] = *row;
-                        if (!kSmem) cv[u] = row[acol - pcol];
-                        wv[u] = wq[rr[u]];
-                    }
+                    for (int u = 0; u < 4; u++)
+                        if (it0 + u < NLP) {
+                            bv[u] = __ldg(rb + (it0 + u) * R * 32);
+                            wv[u] = __ldg(wb + (it0 + u) * R);  // same address across the lanes of a row: broadcast
+                        }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (kSmem)
-                            smem_add_u64_addr(smem_lane + bv[u] * 128u, 256u * 32u * 4u, wv[u]);
-                        else if (wv[u])
-                            atomicAdd(grids + off + (long long)bv[u] * sb + (long long)cv[u] * sc, wv[u]);
-                    }
-                } else {
-                    for (int u = 0; u < 4; u++) {
-                        if (it0 + u >= nlp || rr[u] == 0xffffffffu) continue;
-                        const unsigned char* row = rowp + (unsigned long long)rr[u] * upitch;
-                        const unsigned bvv = *row;
-                        const unsigned long long wvv = wq[rr[u]];
-                        if (kSmem)
-                            smem_add_u64_addr(smem_lane + bvv * 128u, 256u * 32u * 4u, wvv);
-                        else if (wvv)
-                            atomicAdd(grids + off + (long long)bvv * sb + (long long)row[acol - pcol] * sc, wvv);
-                    }
+                    for (int u = 0; u < 4; u++)
+                        if (it0 + u < NLP) smem_add_u64_addr(smem_lane + bv[u] * 128u, 256u * 32u * 4u, wv[u]);
                 }
+            } else if (act) {
+                for (int it = 0; it < NLP; it++)
+                    if (b0 + it * R + rs < hi)
+                        smem_add_u64_addr(smem_lane + (unsigned)rb[it * R * 32] * 128u, 256u * 32u * 4u, wb[it * R]);
             }
         }
+    };
+    // positions [lo, hi) of a run of small buckets starting with bucket c: straight to the grids in L2
+    auto rows_global = [&](int64_t lo, int64_t hi, int c) {
+        if (!act) return;
+        for (int64_t b0 = lo + (int64_t)warp * 32; b0 < hi; b0 += (int64_t)nwarps * 32)
+            for (int it = 0; it < NLP; it++) {
+                const int64_t pos = b0 + it * R + rs;
+                if (pos >= hi) continue;
+                const unsigned long long w = wj[pos - rs];
+                if (w == 0) continue;
+                int cc = c;  // bucket of the position: the last c' with sst[c'] <= position
+                while (cc < 255 && (int64_t)sst[cc + 1] <= pos) cc++;
+                atomicAdd(grids + off + (long long)rj[(size_t)(pos - rs) * 32] * sb + (long long)cc * sc, w);
+            }
     };
     auto flush = [&](int c) {
         for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {  // i & 31 == lane: this thread's own partner
@@ -1377,12 +1468,12 @@ __global__ void __launch_bounds__(SRT_THREADS, 2)
             continue;
         }
         if (hi - lo >= SRT_BIG) {
-            rows(lo, hi, std::true_type{});
+            rows_smem(lo, hi);
             __syncthreads();
             flush(c);
             __syncthreads();
             c++;
-        } else {  // a run of small buckets: one pass, the bucket comes from the row's own byte
+        } else {  // a run of small buckets: one pass, straight to L2
             int c2 = c + 1;
             int64_t end = hi;
             while (c2 < 256 && (int64_t)sst[c2] < ce) {
@@ -1391,7 +1482,7 @@ __global__ void __launch_bounds__(SRT_THREADS, 2)
                 end = e2;
                 c2++;
             }
-            rows(lo, end, std::false_type{});
+            rows_global(lo, end, c);
             c = c2;
         }
     }
