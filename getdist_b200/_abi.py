@@ -115,13 +115,19 @@ def load():
     lib.gdk_density1d_batch.restype = i32
     lib.gdk_density2d_batch.argtypes = [vp, i32, vp, vp, vp, vp, u32]
     lib.gdk_density2d_batch.restype = i32
+    lib.gdk_set_loglikes.argtypes = [vp, vp, i64, vp]
+    lib.gdk_set_loglikes.restype = i32
+    lib.gdk_density1d_likes_batch.argtypes = [vp, i32, vp, vp, vp, i64, vp, u32]
+    lib.gdk_density1d_likes_batch.restype = i32
+    lib.gdk_density2d_likes_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, u32]
+    lib.gdk_density2d_likes_batch.restype = i32
     lib.gdk_lag_sums.argtypes = [vp, i32, vp, vp]
     lib.gdk_lag_sums.restype = i32
     lib.gdk_hist1d_batch.argtypes = [vp, i32, vp, vp, i64]
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
     lib.gdk_hist2d_batch.restype = i32
-    if lib.gdk_abi_version() != 3:
+    if lib.gdk_abi_version() != 4:
         raise GdkError("libgdk.so ABI version mismatch")
     _lib = lib
     return lib
@@ -179,6 +185,16 @@ class Context:
         self._ck(self.lib.gdk_set_samples(self.h, _ptr(X), N, P, rs, cs, _ptr(w), _ptr(co), nch), "gdk_set_samples")
         self.N, self.P, self.nchains = N, P, max(nch, 1)
 
+    def set_loglikes(self, loglikes):
+        """uploads the log-likelihoods, builds the mean-likelihood weights on the device, returns mean_loglike"""
+        if loglikes is None:
+            self._ck(self.lib.gdk_set_loglikes(self.h, None, 0, None), "gdk_set_loglikes")
+            return None
+        ll = np.ascontiguousarray(loglikes, dtype=np.float64)
+        out = C.c_double()
+        self._ck(self.lib.gdk_set_loglikes(self.h, _ptr(ll), ll.size, C.cast(C.byref(out), C.c_void_p)), "gdk_set_loglikes")
+        return float(out.value)
+
     def moments(self):
         P, nch = self.P, self.nchains
         out = dict(means=np.empty(P), vars=np.empty(P), cov=np.empty((P, P)), scalars=np.empty(8), xmin=np.empty(P),
@@ -197,11 +213,16 @@ class Context:
                  "gdk_weighted_quantiles")
         return out
 
-    def density1d_batch(self, specs, out=None, device_ptr=None):
+    def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
         n = len(specs)
         arr = (Spec1D * n)(*specs)
         stride = max(s.fine_bins for s in specs)
         res = (Result1D * n)()
+        if likes:  # get1DDensityGridData(meanlikes=True): (P, likes, results)
+            P, L = np.empty((n, stride)), np.empty((n, stride))
+            self._ck(self.lib.gdk_density1d_likes_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(P), _ptr(L), stride,
+                                                        C.cast(res, C.c_void_p), 0), "gdk_density1d_likes_batch")
+            return P, L, list(res)
         if device_ptr is not None:
             self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), stride,
                                                   C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density1d_batch")
@@ -219,7 +240,7 @@ class Context:
         self._ck(self.lib.gdk_hist1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), stride), "gdk_hist1d_batch")
         return out
 
-    def density2d_batch(self, specs, out=None, device_ptr=None):
+    def density2d_batch(self, specs, out=None, device_ptr=None, likes=False):
         n = len(specs)
         if isinstance(specs, np.ndarray):  # structured array with the gdk_spec2d layout (vectorised planner)
             assert specs.dtype.itemsize == C.sizeof(Spec2D) and specs.flags.c_contiguous
@@ -233,6 +254,11 @@ class Context:
         offsets[1:] = np.cumsum(sizes)[:-1]
         total = int(sizes.sum())
         res = (Result2D * n)()
+        if likes:  # get2DDensityGridData(meanlikes=True): (P, likes, offsets, results)
+            out, lout = np.empty(total), np.empty(total)
+            self._ck(self.lib.gdk_density2d_likes_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(lout), _ptr(offsets),
+                                                        C.cast(res, C.c_void_p), 0), "gdk_density2d_likes_batch")
+            return out, lout, offsets, list(res)
         if device_ptr is not None:
             self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), _ptr(offsets),
                                                   C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density2d_batch")

@@ -210,6 +210,7 @@ extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int
     if (!X || N <= 0 || P <= 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_set_samples: bad shape N=%lld P=%d", (long long)N, P);
     CK(cudaSetDevice(ctx->device));
     ctx->have_moments = false;
+    ctx->have_loglikes = false;
     ctx->N = N;
     ctx->P = P;
     ctx->ld = (N + 63) & ~int64_t(63);
@@ -314,6 +315,56 @@ extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->wq_total = h[0];
     ctx->n_outliers = (double)h[1];
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_set_loglikes(gdk_ctx* ctx, const double* loglikes, int64_t n, double* mean_loglike_out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (!loglikes) {
+        ctx->have_loglikes = false;
+        return GDK_OK;
+    }
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "gdk_set_loglikes: no samples set");
+    if (n != ctx->N) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_set_loglikes: %lld values for %lld rows", (long long)n, (long long)ctx->N);
+    CK(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->N;
+    if (ctx->dLL.ensure((size_t)ctx->ld) || ctx->dLW.ensure((size_t)ctx->ld) || ctx->dWlq.ensure((size_t)ctx->ld))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "log-likelihood buffers");
+    CK(cudaMemcpyAsync(ctx->dLL.p, loglikes, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int nb = ctx->num_sms * 4;
+    if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+    // mean_loglike = sum(w * loglike) / sum(w)   (chains.py:380-381)
+    k_wll_partial<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, ctx->dLL.p, N, ctx->scratch.p);
+    std::vector<double> part((size_t)nb * 4);
+    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double swl = 0;
+    for (int i = 0; i < nb; i++) swl += part[i];
+    if (!std::isfinite(swl)) return gdk_fail(ctx, GDK_ERR_ARG, "log-likelihoods must be finite (weighted sum %g)", swl);
+    ctx->mean_loglike = swl / ctx->sum_w;
+    // lw = w * exp(mean_loglike - loglike), then the same fixed-point construction as for the weights
+    k_like_weights<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, ctx->dLL.p, ctx->mean_loglike, N, ctx->dLW.p);
+    k_wstats<<<nb, 256, 0, ctx->stream>>>(ctx->dLW.p, N, ctx->scratch.p);
+    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sl = 0, mn = INFINITY;
+    for (int i = 0; i < nb; i++) {
+        sl += part[i * 4 + 0];
+        mn = std::min(mn, part[i * 4 + 3]);
+    }
+    if (!(mn >= 0) || !(sl > 0) || !std::isfinite(sl))
+        return gdk_fail(ctx, GDK_ERR_ARG, "mean-likelihood weights w*exp(mean_loglike - loglike) are not finite (sum %g)", sl);
+    int e = 0;
+    frexp(sl, &e);
+    ctx->wlscale = ldexp(1.0, 61 - e);
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
+    CK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
+    k_make_wq<<<nb, 256, 0, ctx->stream>>>(ctx->dLW.p, N, ctx->wlscale, INFINITY, ctx->dWlq.p, acc);
+    ctx->launches += 4;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->have_loglikes = true;
+    if (mean_loglike_out) *mean_loglike_out = ctx->mean_loglike;
     return GDK_OK;
 }
 
@@ -555,7 +606,10 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
 // -------------------------------------------------------------------------------------------------
 // 1D densities
 // -------------------------------------------------------------------------------------------------
-static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gstride_out) {
+static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gstride_out, const unsigned long long* wq = nullptr,
+                      DevBuf<unsigned long long>* outbuf = nullptr) {
+    if (!wq) wq = ctx->dWq.p;
+    DevBuf<unsigned long long>& gb = outbuf ? *outbuf : ctx->gbins;
     int maxF = 0;
     std::vector<Hist1dJob> jobs(n);
     for (int i = 0; i < n; i++) {
@@ -569,9 +623,9 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
     }
     const int64_t gstride = (maxF + 15) & ~15;
     *gstride_out = gstride;
-    if (ctx->gbins.ensure((size_t)n * gstride) || ctx->jobs1d.ensure(n)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D histogram buffers");
+    if (gb.ensure((size_t)n * gstride) || ctx->jobs1d.ensure(n)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D histogram buffers");
     if (maxF * 8 > ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "fine_bins %d exceeds shared memory", maxF);
-    CK(cudaMemsetAsync(ctx->gbins.p, 0, (size_t)n * gstride * 8, ctx->stream));
+    CK(cudaMemsetAsync(gb.p, 0, (size_t)n * gstride * 8, ctx->stream));
     CK(cudaMemcpyAsync(ctx->jobs1d.p, jobs.data(), n * sizeof(Hist1dJob), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 16 / n);
     const int64_t seglen = std::max<int64_t>(1 << 15, (ctx->N + want - 1) / want);
@@ -601,14 +655,14 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
             ctx->h1_tma_smem = std::max<size_t>(smem_tma, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
-        k_hist1d_tma<<<g, 256, smem_tma, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, djt, ctx->gbins.p, gstride);
+        k_hist1d_tma<<<g, 256, smem_tma, ctx->stream>>>(ctx->dX.p, ctx->ld, wq, ctx->segs.p, djt, gb.p, gstride);
     } else {
         if ((size_t)maxF * 8 > ctx->h1_smem) {
             CK(cudaFuncSetAttribute(k_hist1d, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(maxF * 8, 48 * 1024)));
             ctx->h1_smem = (size_t)std::max(maxF * 8, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
-        k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->jobs1d.p, ctx->gbins.p, gstride);
+        k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, wq, ctx->segs.p, ctx->jobs1d.p, gb.p, gstride);
     }
     ctx->launches++;
     pt.end();
@@ -636,7 +690,14 @@ extern "C" int32_t gdk_hist1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* s
 
 extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, int64_t stride,
                                        gdk_result1d* res, uint32_t flags) {
+    return gdk_density1d_likes_batch(ctx, n, specs, P_out, nullptr, stride, res, flags);
+}
+
+extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, double* likes_out,
+                                             int64_t stride, gdk_result1d* res, uint32_t flags) {
     if (!ctx) return GDK_ERR_ARG;
+    const bool likes = likes_out != nullptr;
+    if (likes && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "meanlikes needs gdk_set_loglikes");
     if (n <= 0 || !specs || !P_out || !res) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_density1d_batch: bad arguments");
     if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
     CK(cudaSetDevice(ctx->device));
@@ -647,7 +708,12 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
         if (stride < s.fine_bins) return gdk_fail(ctx, GDK_ERR_ARG, "spec %d: output stride too small", i);
     }
     int64_t gstride = 0;
-    int rc = run_hist1d(ctx, n, specs, &gstride);
+    int rc = 0;
+    if (likes) {  // second weighted histogram with the mean-likelihood weights (mcsamples.py:1561), same bin indices
+        rc = run_hist1d(ctx, n, specs, &gstride, ctx->dWlq.p, &ctx->gbins_l);
+        if (rc) return rc;
+    }
+    rc = run_hist1d(ctx, n, specs, &gstride);
     if (rc) return rc;
     // twiddle / cosine tables per density
     std::vector<Kde1dTables> tabs(n);
@@ -658,11 +724,12 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
         tabs[i] = Kde1dTables{t->tw, t->tw4, t->cos4};
         maxF = std::max(maxF, specs[i].fine_bins);
     }
-    const size_t smem_need = (size_t)9 * maxF * 8;
+    const int nwork = likes ? 11 : 9;  // work arrays of F doubles per density
+    const size_t smem_need = (size_t)nwork * maxF * 8;
     const int use_smem = smem_need <= (size_t)ctx->max_smem - 1024;
-    if (ctx->specs1d.ensure(n) || ctx->res1d.ensure(n) || ctx->tabs1d.ensure(n) || ctx->fbuf.ensure((size_t)n * gstride))
+    if (ctx->specs1d.ensure(n) || ctx->res1d.ensure(n) || ctx->tabs1d.ensure(n) || ctx->fbuf.ensure((size_t)n * gstride * (likes ? 2 : 1)))
         return gdk_fail(ctx, GDK_ERR_NOMEM, "1D density buffers");
-    if (!use_smem && ctx->gwork.ensure((size_t)n * 9 * maxF)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D workspace");
+    if (!use_smem && ctx->gwork.ensure((size_t)n * nwork * maxF)) return gdk_fail(ctx, GDK_ERR_NOMEM, "1D workspace");
     CK(cudaMemcpyAsync(ctx->specs1d.p, specs, n * sizeof(gdk_spec1d), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tabs1d.p, tabs.data(), n * sizeof(Kde1dTables), cudaMemcpyHostToDevice, ctx->stream));
     if (use_smem && smem_need > ctx->kde1d_smem) {
@@ -671,17 +738,23 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
     }
     const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
     double* dP = dev_out ? P_out : ctx->fbuf.p;
+    double* dL = !likes ? nullptr : (dev_out ? likes_out : ctx->fbuf.p + (size_t)n * gstride);
     const int64_t pstride = dev_out ? stride : gstride;
     PhaseTimer pt;
     pt.begin(ctx, GDK_PH_KDE1D);
     k_kde1d<<<n, 256, use_smem ? smem_need : 0, ctx->stream>>>(ctx->specs1d.p, ctx->gbins.p, gstride, 1.0 / ctx->wscale, ctx->isj,
-                                                               ctx->tabs1d.p, dP, pstride, ctx->res1d.p, ctx->gwork.p, use_smem);
+                                                               ctx->tabs1d.p, dP, pstride, ctx->res1d.p, ctx->gwork.p, use_smem,
+                                                               likes ? ctx->gbins_l.p : nullptr, 1.0 / ctx->wlscale, dL);
     ctx->launches++;
     pt.end();
     CK(cudaGetLastError());
     if (!dev_out)
         for (int i = 0; i < n; i++)
             CK(cudaMemcpyAsync(P_out + (int64_t)i * stride, ctx->fbuf.p + (int64_t)i * gstride, (size_t)specs[i].fine_bins * 8,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_out && likes)
+        for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(likes_out + (int64_t)i * stride, dL + (int64_t)i * gstride, (size_t)specs[i].fine_bins * 8,
                                cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(res, ctx->res1d.p, n * sizeof(gdk_result1d), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -32,10 +32,10 @@ struct Arena {
     }
 };
 
-static size_t bytes_per_pair_estimate(const gdk_spec2d& s) {
+static size_t bytes_per_pair_estimate(const gdk_spec2d& s, bool likes = false) {
     const size_t g = (size_t)s.fine_bins * s.fine_bins * 8, gb = (size_t)s.base_fine_bins * s.base_fine_bins * 8;
     const size_t w = 256;  // generous window half-width guess for the T scratch
-    return g * 13 + gb * 6 + (2 * w + 1) * (size_t)s.fine_bins * 4 * 8 + (2 * w + 1) * (2 * w + 1) * 8;
+    return g * (likes ? 18 : 13) + gb * 6 + (2 * w + 1) * (size_t)s.fine_bins * 4 * 8 + (2 * w + 1) * (2 * w + 1) * 8;
 }
 
 template <class T>
@@ -47,8 +47,9 @@ static int upload_vec(gdk_ctx* ctx, const std::vector<T>& v, DevBuf<unsigned cha
 }
 
 static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
-                           gdk_result2d* res, uint32_t flags, bool hist_only) {
+                           gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr) {
     const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
+    const bool likes = likes_out != nullptr && !hist_only;
     // ---------------- layout of the pair grids ----------------
     std::vector<long long> goff(n);
     size_t gtot = 0;
@@ -201,7 +202,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     int rc = upload_vec(ctx, tiles, ctx->bytes2d, &dtiles);
     if (rc) return rc;
     const int ntiles = (int)tiles.size();
-    {
+    // the histogram pass over all pairs of the chunk with fixed-point weights WQ into the grids GR
+    auto fill_hist = [&](const unsigned long long* WQ, unsigned long long* GR) -> int {
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_HIST2D);
         const std::vector<int>& b8pairs = hot_pairs.empty() ? band_pairs : hot_pairs;
@@ -314,7 +316,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 for (int b0 = 0; b0 < njobs; b0 += SRT_MAXJOBS) {
                     const int nb = std::min(SRT_MAXJOBS, njobs - b0);
                     k_bucket_records<<<(unsigned)((ctx->N + rows - 1) / rows), 1024, rec_smem(rows, nb), ctx->stream>>>(
-                        ctx->ix8.p, ctx->ld, np8, pitch, rows, ctx->N, ctx->dWq.p, dsj + b0, nb, cursor + (size_t)b0 * 256,
+                        ctx->ix8.p, ctx->ld, np8, pitch, rows, ctx->N, WQ, dsj + b0, nb, cursor + (size_t)b0 * 256,
                         reinterpret_cast<uint4*>(ctx->recs.p), ctx->recw.p, pld);
                     ctx->launches++;
                     for (int j0 = 0; j0 < nb;) {  // sub-ranges of equal lane layout
@@ -325,7 +327,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     case LG:                                                                                                                 \
         CK2(cudaFuncSetAttribute(k_hist2d_records<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt_smem));        \
         k_hist2d_records<LG><<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsj + b0, j0, ctx->recs.p, ctx->recw.p, pld, start, \
-                                                                         ctx->gbins2.p, chunk, ctx->N);                      \
+                                                                         GR, chunk, ctx->N);                      \
         break;
                         switch (sj[b0 + j0].lg) {
                             GDK_LAUNCH_REC(0)
@@ -416,21 +418,21 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 const size_t hot_smem = (size_t)4 * 2 * HW * HW * 4;
                 CK2(cudaFuncSetAttribute(k_hist2d_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hot_smem));
                 dim3 gh((unsigned)segsh.size(), (unsigned)ht.size());
-                k_hist2d_hot<<<gh, 1024, hot_smem, ctx->stream>>>(dht, ctx->dWq.p, ctx->segs.p, ctx->gbins2.p);
+                k_hist2d_hot<<<gh, 1024, hot_smem, ctx->stream>>>(dht, WQ, ctx->segs.p, GR);
                 ctx->launches++;
             } else {
             std::vector<BandJob> jobs(band_pairs.size());
             for (size_t k = 0; k < band_pairs.size(); k++) {
                 const int i = band_pairs[k];
                 jobs[k] = BandJob{ctx->ix8.p + (size_t)slot[specs[i].px] * ctx->ld, ctx->ix8.p + (size_t)slot[specs[i].py] * ctx->ld,
-                                  ctx->gbins2.p + goff[i]};
+                                  GR + goff[i]};
             }
             BandJob* dband = nullptr;
             rc = upload_vec(ctx, jobs, ctx->bytes2d_d, &dband);
             if (rc) return rc;
             const size_t band_smem = (size_t)2 * 64 * 256 * 4 + (size_t)HB_STAGES * HB_CHUNK * 10;
             CK2(cudaFuncSetAttribute(k_hist2d_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)band_smem));
-            k_hist2d_bands<<<(unsigned)(4 * jobs.size()), HB_THREADS, band_smem, ctx->stream>>>(dband, ctx->dWq.p, ctx->N);
+            k_hist2d_bands<<<(unsigned)(4 * jobs.size()), HB_THREADS, band_smem, ctx->stream>>>(dband, WQ, ctx->N);
             ctx->launches++;
             }
         }
@@ -445,12 +447,23 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             rc = gdk_upload_segs(ctx, segs, ctx->segs);
             if (rc) return rc;
             dim3 g((unsigned)segs.size(), (unsigned)ntiles);
-            k_hist2d_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dtiles, ctx->gbins2.p);
+            k_hist2d_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, WQ, ctx->segs.p, dtiles, GR);
             ctx->launches++;
         }
         pt.end();
         CK2(cudaGetLastError());
+        return 0;
+    };
+    if (likes) {  // second histogram with the mean-likelihood weights (mcsamples.py:1829-1831), same bin indices
+        if (ctx->gbins2l.ensure(gtot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D mean-likelihood grids");
+        CK2(cudaMemsetAsync(ctx->gbins2l.p, 0, gtot * 8, ctx->stream));
+        rc = fill_hist(ctx->dWlq.p, ctx->gbins2l.p);
+        if (rc) return rc;
+        k_u64_to_f64_inplace<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gbins2l.p, (int64_t)gtot, 1.0 / ctx->wlscale);
+        ctx->launches++;
     }
+    rc = fill_hist(ctx->dWq.p, ctx->gbins2.p);
+    if (rc) return rc;
     // ---------------- sheared re-binning ----------------
     ShearJob* dsj = nullptr;
     ShearGeom* dgeom = nullptr;
@@ -539,7 +552,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
 
     // ---------------- arena for everything grid-sized below ----------------
     size_t need = 0;
-    for (int i = 0; i < n; i++) need += bytes_per_pair_estimate(specs[i]);
+    for (int i = 0; i < n; i++) need += bytes_per_pair_estimate(specs[i], likes);
     need += (size_t)64 << 20;
     if (ctx->bytes_arena.ensure(need)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D work arena (%zu MB)", need >> 20);
     Arena ar{ctx->bytes_arena.p, ctx->bytes_arena.cap, 0};
@@ -638,8 +651,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     ar.used = mark;  // transform scratch is dead
     std::vector<ConvJob> cj(n);
     int wmax_all = 0;
-    if (ctx->bytes2d_mx.ensure((size_t)n * 8 * 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "max buffer");
-    CK2(cudaMemsetAsync(ctx->bytes2d_mx.p, 0, (size_t)n * 64, ctx->stream));
+    if (ctx->bytes2d_mx.ensure((size_t)n * 16 * 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "max buffer");
+    CK2(cudaMemsetAsync(ctx->bytes2d_mx.p, 0, (size_t)n * 128, ctx->stream));
     int max_mbc = 0;
     bool any_periodic = false;
     for (int i = 0; i < n; i++) {
@@ -683,7 +696,15 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 c.yP = take_d((size_t)G * G);
             }
         }
-        c.mx = reinterpret_cast<unsigned long long*>(ctx->bytes2d_mx.p) + (size_t)i * 8;
+        c.mx = reinterpret_cast<unsigned long long*>(ctx->bytes2d_mx.p) + (size_t)i * 16;
+        if (likes) {
+            c.lhist = reinterpret_cast<const double*>(ctx->gbins2l.p) + goff[i];
+            c.lmbc = s.mult_bias_correction_order;
+            c.lP = take_d((size_t)G * G);
+            c.lP2 = take_d((size_t)G * G);
+            c.lbox = c.lmbc ? take_d((size_t)G * G) : nullptr;
+            if (!c.lP || !c.lP2 || (c.lmbc && !c.lbox)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (mean likelihoods, pair %d)", i);
+        }
         if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || !c.T || !c.box)) || (c.bounded && (!c.maps || !c.T || (c.bco == 1 && (!c.xP || !c.yP)))))
             return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (convolution stage, pair %d)", i);
         wmax_all = std::max(wmax_all, w);
@@ -748,6 +769,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (smem_max > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "window too large for the convolution kernel");
     CK2(cudaFuncSetAttribute(k_conv2d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     CK2(cudaFuncSetAttribute(k_conv2d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+    if (likes) {
+        CK2(cudaFuncSetAttribute(k_conv2d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+        CK2(cudaFuncSetAttribute(k_conv2d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+    }
     for (const Grp& g : groups) {
         const int nj = g.e - g.b;
         const int K = 2 * g.wmax + 1;
@@ -766,6 +791,16 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             ctx->launches++;
         }
         dim3 gb(64, (unsigned)nj);
+        if (likes) {
+            // mean likelihoods (mcsamples.py:1886-1898): likes (*) Win, optional bias step, ratio to the raw bins2D
+            k_conv2d<2><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
+            if (any_periodic) k_conv2d_circ<2><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            k_likes2d<0><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+            k_conv2d<3><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
+            if (any_periodic) k_conv2d_circ<3><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            k_likes2d<1><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+            ctx->launches += any_periodic ? 6 : 4;
+        }
         k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
         ctx->launches += 4;
         for (int it = 0; it < max_mbc; it++) {
@@ -788,10 +823,25 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         if (ctx->f2.ensure(otot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D output buffer");
         dout = ctx->f2.p - offsets[0];  // offsets are relative to P_out; the chunk's first density sits at f2[0]
     }
+    double* dlout = nullptr;
+    if (likes) {
+        if (dev_out) {
+            dlout = likes_out;
+        } else {
+            size_t otot = 0;
+            for (int i = 0; i < n; i++) otot = std::max(otot, (size_t)(offsets[i] - offsets[0]) + (size_t)specs[i].fine_bins * specs[i].fine_bins);
+            if (ctx->f2l.ensure(otot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D mean-likelihood output buffer");
+            dlout = ctx->f2l.p - offsets[0];
+        }
+    }
     {
         dim3 gf(64, (unsigned)n);
         k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dout, doffs, dres);
         ctx->launches++;
+        if (likes) {
+            k_likes_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dlout, doffs);
+            ctx->launches++;
+        }
         bool any_contours = false;
         for (int i = 0; i < n; i++) any_contours = any_contours || specs[i].n_contours > 0;
         if (any_contours) {
@@ -817,6 +867,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                                     (size_t)specs[i].fine_bins * specs[i].fine_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
+    if (!dev_out && likes)
+        for (int i = 0; i < n; i++)
+            CK2(cudaMemcpyAsync(likes_out + offsets[i], ctx->f2l.p + (offsets[i] - offsets[0]),
+                                (size_t)specs[i].fine_bins * specs[i].fine_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK2(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < n; k++) {
         res[order[k]].status = res_sorted[k].status;
@@ -826,8 +880,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
 }
 
 static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
-                          gdk_result2d* res, uint32_t flags, bool hist_only) {
+                          gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr) {
     if (!ctx) return GDK_ERR_ARG;
+    if (likes_out && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "meanlikes needs gdk_set_loglikes");
     if (n <= 0 || !specs || !P_out || !offsets || (!hist_only && !res)) return gdk_fail(ctx, GDK_ERR_ARG, "2D batch: bad arguments");
     if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
     CK2(cudaSetDevice(ctx->device));
@@ -857,12 +912,12 @@ static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, doub
         size_t acc = 0;
         int e = b;
         while (e < n) {
-            const size_t add = bytes_per_pair_estimate(specs[e]);
+            const size_t add = bytes_per_pair_estimate(specs[e], likes_out != nullptr);
             if (e > b && acc + add > budget) break;
             acc += add;
             e++;
         }
-        int rc = density2d_chunk(ctx, e - b, specs + b, P_out, offsets + b, hist_only ? nullptr : res + b, flags, hist_only);
+        int rc = density2d_chunk(ctx, e - b, specs + b, P_out, offsets + b, hist_only ? nullptr : res + b, flags, hist_only, likes_out);
         if (rc) return rc;
         b = e;
     }
@@ -872,6 +927,11 @@ static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, doub
 extern "C" int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
                                        gdk_result2d* res, uint32_t flags) {
     return density2d_impl(ctx, n, specs, P_out, offsets, res, flags, false);
+}
+
+extern "C" int32_t gdk_density2d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, double* likes_out,
+                                             const int64_t* offsets, gdk_result2d* res, uint32_t flags) {
+    return density2d_impl(ctx, n, specs, P_out, offsets, res, flags, false, likes_out);
 }
 
 extern "C" int32_t gdk_hist2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* bins_out, const int64_t* offsets) {

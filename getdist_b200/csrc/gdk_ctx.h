@@ -75,6 +75,12 @@ struct gdk_ctx {
     double wscale = 1.0;
     unsigned long long wq_total = 0;
     double sum_w = 0, sum_w2 = 0, max_w = 0, min_w = 0, n_outliers = 0;
+    // mean-likelihood weights (gdk_set_loglikes): w * exp(mean_loglike - loglike) as float64 and fixed point
+    bool have_loglikes = false;
+    double mean_loglike = 0, wlscale = 1.0;
+    DevBuf<double> dLL, dLW;
+    DevBuf<unsigned long long> dWlq, gbins_l, gbins2l;
+    DevBuf<double> f2l;
     // cached moments
     bool have_moments = false;
     double norm = 0;

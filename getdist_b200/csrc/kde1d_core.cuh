@@ -32,6 +32,10 @@ struct Kde1dWork {
     const cplx* tw;      // n-th roots (pow2 path) or NULL
     const cplx* tw4;     // 4n-th roots, first n (pow2 path)
     const double* cos4;  // cos(2 pi j/4n) table (direct path)
+    // mean likelihoods (meanlikes=True, mcsamples.py:1556-1561, 1672-1684); all NULL when not requested
+    const double* likebins = nullptr;  // histogram of weights * exp(mean_loglike - loglikes)
+    double* raw = nullptr;             // scratch: the first convolution ("rawbins", mcsamples.py:1597-1598)
+    double* likes_out = nullptr;       // max-normalised mean likelihoods
 };
 
 template <class C>
@@ -194,6 +198,10 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
     // ---- P = bins (*) Win, plus the boundary-kernel moments in the same sweep ----------------------
     if (periodic) {
         conv_circ(co, W.bins, W.win, w, F, W.P);
+        if (W.raw) {
+            for (int i = co.tid; i < F; i += co.nt) W.raw[i] = W.P[i];
+            co.sync();
+        }
     } else if ((bot || top) && bco >= 0) {
         // prior mask of length F+2w: 0 outside the bounded side, 1/2 on the boundary bin, 1 inside.
         // 'valid' conv: a_r[i] = sum_u u^r win(u) mask[i + w - u];   'same' conv: xP, x2P on bins.
@@ -239,10 +247,15 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
                 }
             }
             W.P[i] = out;
+            if (W.raw) W.raw[i] = P;
         }
         co.sync();
     } else {
         conv_same(co, W.bins, W.win, w, F, W.P);
+        if (W.raw) {
+            for (int i = co.tid; i < F; i += co.nt) W.raw[i] = W.P[i];
+            co.sync();
+        }
         if (bco == 2) {
             // higher-order kernel for unbounded parameters, mcsamples.py:1638-1647
             double p2 = 0, p4 = 0;
@@ -310,6 +323,28 @@ GDK_HD void kde1d_core(const C& co, const gdk_spec1d& sp, const IsjConsts& K, Kd
     const double mx = co.max(pm);
     if (!(mx != 0)) status |= GDK_ST_ZERO_MAX;
     for (int i = co.tid; i < F; i += co.nt) P_out[i] = (mx != 0) ? W.P[i] / mx : W.P[i];
+    if (W.likebins && W.raw && W.likes_out) {
+        // ---- mean likelihoods, mcsamples.py:1672-1682 (shade_likes_is_mean_loglikes = False) ---------
+        for (int i = co.tid; i < F; i += co.nt) {
+            const double pf = (mx != 0) ? W.P[i] / mx : W.P[i];
+            W.aux[i] = pf > 0 ? W.likebins[i] / pf : W.likebins[i];
+        }
+        co.sync();
+        if (periodic)
+            conv_circ(co, W.aux, W.win, w, F, W.aux2);
+        else
+            conv_same(co, W.aux, W.win, w, F, W.aux2);
+        double lm = -INFINITY;
+        for (int i = co.tid; i < F; i += co.nt) {
+            const double pf = (mx != 0) ? W.P[i] / mx : W.P[i];
+            double v = W.aux2[i];
+            if (pf > 0) v *= pf / W.raw[i];
+            W.aux2[i] = v;
+            lm = fmax(lm, v);
+        }
+        const double lmx = co.max(lm);
+        for (int i = co.tid; i < F; i += co.nt) W.likes_out[i] = W.aux2[i] / lmx;
+    }
     if (co.tid == 0) {
         res->kde_h = kde_h;
         res->h_raw = h_raw;

@@ -258,19 +258,22 @@ struct Kde1dTables {
     const double* cos4;
 };
 
-// grid (n), 256 threads.  Work arrays: 9*F doubles, in dynamic shared memory when use_smem != 0, otherwise in
+// grid (n), 256 threads.  Work arrays: 9*F doubles (11*F with mean likelihoods), in dynamic shared memory when use_smem != 0, otherwise in
 // the per-density global workspace gwork + i*9*F.
 __global__ void __launch_bounds__(256) k_kde1d(const gdk_spec1d* __restrict__ specs, const unsigned long long* __restrict__ gbins,
                                                int64_t gstride, double inv_scale, IsjConsts K, const Kde1dTables* __restrict__ tabs,
                                                double* __restrict__ P_out, int64_t pstride, gdk_result1d* __restrict__ res,
-                                               double* __restrict__ gwork, int use_smem) {
+                                               double* __restrict__ gwork, int use_smem,
+                                               const unsigned long long* __restrict__ gbins_l, double inv_scale_l,
+                                               double* __restrict__ L_out) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ double red[32];
     __shared__ __align__(8) unsigned long long bar;
     const int i = blockIdx.x;
     const gdk_spec1d sp = specs[i];
     const int F = sp.fine_bins;
-    double* base = use_smem ? reinterpret_cast<double*>(dsm) : gwork + (int64_t)i * 9 * F;
+    const int nwork = gbins_l ? 11 : 9;
+    double* base = use_smem ? reinterpret_cast<double*>(dsm) : gwork + (int64_t)i * nwork * F;
     Kde1dWork W;
     W.bins = base;
     W.a2 = base + F;
@@ -301,6 +304,14 @@ __global__ void __launch_bounds__(256) k_kde1d(const gdk_spec1d* __restrict__ sp
         for (int k = threadIdx.x; k < F; k += blockDim.x) W.bins[k] = (double)raw[k] * inv_scale;
     } else {
         for (int k = threadIdx.x; k < F; k += blockDim.x) W.bins[k] = (double)g[k] * inv_scale;
+    }
+    if (gbins_l) {  // mean-likelihood histogram (meanlikes=True)
+        double* lb = base + 9 * F;
+        const unsigned long long* gl = gbins_l + (int64_t)i * gstride;
+        for (int k = threadIdx.x; k < F; k += blockDim.x) lb[k] = (double)gl[k] * inv_scale_l;
+        W.likebins = lb;
+        W.raw = base + 10 * F;
+        W.likes_out = L_out + (int64_t)i * pstride;
     }
     __syncthreads();
     CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};

@@ -433,6 +433,12 @@ struct ConvJob {
     int nc, pad;
     double contours[4];
     int xper, yper;  // periodic axes
+    // mean likelihoods (meanlikes=True, mcsamples.py:1829-1831, 1886-1901, 2004-2006); lhist == NULL: not requested
+    const double* lhist;  // histogram of weights * exp(mean_loglike - loglikes)
+    double* lP;           // lhist (*) Win
+    double* lbox;         // lhist / lP where lP > 0
+    double* lP2;          // conv(lbox) * lP where lP > 0 (bias-corrected likes); then reused for the ratio likes / bins2D
+    int lmbc, pad3;       // the mult_bias_correction_order setting itself (the likes ignore periodicity, :1890)
 };
 
 // window: one CTA per job
@@ -475,6 +481,8 @@ __host__ __device__ __forceinline__ int cv_q(int wmax) {
 // MODE 0: in = hist                      -> P (and xP, yP when bounded with order 1); running max -> mx[0]
 // MODE 1: in = box = hist / P where P > thr (thr = mx[1+iter]*1e-8) else hist
 //                                         -> next P = P * conv / a00b; running max -> mx[2+iter]
+// MODE 2: in = lhist (mean-likelihood histogram) -> lP           (jobs without lhist return)
+// MODE 3: in = lbox                              -> lP2 = conv * lP where lP > 0, else conv   (jobs with lmbc only)
 // grid (tiles, njobs), 256 threads = 16 (x) x 16 (y); every thread produces 8 consecutive outputs of one row.
 // Shared-memory input tile: row r, column c stored at r*8q + (c&7)*q + (c>>3) ("8-way column interleave"): the
 // sliding-window loads of the 16 threads of a row then hit 16 consecutive words (conflict free), and so do the
@@ -485,6 +493,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     extern __shared__ __align__(16) double csm[];
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
+    if (MODE >= 2 && (!jb.lhist || (MODE == 3 && !jb.lmbc))) return;
     if (jb.xper | jb.yper) return;  // periodic pairs: k_conv2d_circ
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const int Kp = (K + 7) & ~7;
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
         // input rows a = abase + r, r < CV_TY + kc - 1; one warp per row, lanes stride over the columns
         const int abase = oy0 - (k0 + kc - 1) + w;
         const int nrow = CV_TY + kc - 1;
-        const double* srcp = (MODE == 1) ? jb.box : jb.hist;
+        const double* srcp = (MODE == 1) ? jb.box : (MODE == 2 ? jb.lhist : (MODE == 3 ? jb.lbox : jb.hist));
         for (int r = threadIdx.x >> 5; r < nrow; r += 8) {
             const int a = abase + r;
             const bool rowok = a >= 0 && a < G;
@@ -588,15 +597,60 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
                     jb.yP[o] = accy[m];
                 }
                 tmax = fmax(tmax, acc[m]);
-            } else {
+            } else if (MODE == 1) {
                 const double vv = P[o] * acc[m] / jb.a00b[o];
                 Pout[o] = vv;
                 tmax = fmax(tmax, vv);
+            } else if (MODE == 2) {
+                jb.lP[o] = acc[m];
+            } else {
+                const double l1 = jb.lP[o];
+                jb.lP2[o] = l1 > 0 ? acc[m] * l1 : acc[m];
             }
         }
     }
+    if (MODE >= 2) return;
     tmax = warp_max(tmax);
     if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
+}
+
+// mean likelihoods, elementwise steps (mcsamples.py:1890-1898).  grid (64, njobs).
+// STEP 0: lbox = lhist / lP where lP > 0 (jobs with lmbc)
+// STEP 1: ratio = likes / bins2D where bins2D > 1e-4 max(bins2D), else 0 (bins2D = the first convolution, before any
+//         correction: runs before k_boundary2d); stored in lP2, running max -> mx[15]
+template <int STEP>
+__global__ void __launch_bounds__(256) k_likes2d(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (!jb.lhist || (STEP == 0 && !jb.lmbc)) return;
+    const size_t gg = (size_t)jb.G * jb.G;
+    const double thr = 1e-4 * __longlong_as_double((long long)jb.mx[0]);
+    double tmax = 0;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < gg; o += (size_t)gridDim.x * blockDim.x) {
+        if (STEP == 0) {
+            const double l1 = jb.lP[o], h = jb.lhist[o];
+            jb.lbox[o] = l1 > 0 ? h / l1 : h;
+        } else {
+            const double l = jb.lmbc ? jb.lP2[o] : jb.lP[o], p = jb.P[o];
+            const double v = p > thr ? l / p : 0.0;
+            jb.lP2[o] = v;
+            tmax = fmax(tmax, v);
+        }
+    }
+    if (STEP == 1) {
+        tmax = warp_max(tmax);
+        if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + 15, tmax);
+    }
+}
+
+// max-normalised mean likelihoods into the output (mcsamples.py:2004-2006).  grid (64, njobs)
+__global__ void __launch_bounds__(256) k_likes_finalize2d(const ConvJob* __restrict__ jobs, double* __restrict__ out,
+                                                          const long long* __restrict__ offs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (!jb.lhist) return;
+    const size_t gg = (size_t)jb.G * jb.G;
+    const double mx = __longlong_as_double((long long)jb.mx[15]);
+    double* o = out + offs[blockIdx.y];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < gg; i += (size_t)gridDim.x * blockDim.x) o[i] = jb.lP2[i] / mx;
 }
 
 // prior-mask factors along one axis (mcsamples.py:1688-1712): index s relative to the unpadded grid
@@ -948,6 +1002,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__ jobs, int iter) {
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
+    if (MODE >= 2 && (!jb.lhist || (MODE == 3 && !jb.lmbc))) return;
     if (!(jb.xper | jb.yper)) return;
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -962,7 +1017,8 @@ __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__
         if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
         const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
         auto src = [&](int a, int b) {  // unfolded source element
-            return (MODE == 1) ? jb.box[(size_t)a * G + b] : jb.hist[(size_t)a * G + b];
+            const double* sp = (MODE == 1) ? jb.box : (MODE == 2 ? jb.lhist : (MODE == 3 ? jb.lbox : jb.hist));
+            return sp[(size_t)a * G + b];
         };
         auto folded = [&](int a, int b) {  // element (a, b) of the folded array
             double v = src(a, b);
@@ -997,12 +1053,18 @@ __global__ void __launch_bounds__(256) k_conv2d_circ(const ConvJob* __restrict__
                 jb.yP[o] = accy;
             }
             tmax = acc;
-        } else {
+        } else if (MODE == 1) {
             const double vv = P[o] * acc / jb.a00b[o];
             Pout[o] = vv;
             tmax = vv;
+        } else if (MODE == 2) {
+            jb.lP[o] = acc;
+        } else {
+            const double l1 = jb.lP[o];
+            jb.lP2[o] = l1 > 0 ? acc * l1 : acc;
         }
     }
+    if (MODE >= 2) return;
     tmax = warp_max(tmax);
     if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
 }

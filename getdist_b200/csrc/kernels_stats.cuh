@@ -130,6 +130,27 @@ __global__ void k_make_wq(const double* __restrict__ w, int64_t N, double scale,
     }
 }
 
+// mean-likelihood weights (mcsamples.py:1556-1561, 1829-1831): pass 1 = per-block partials of sum(w * loglike)
+// (chains.py:380-381), pass 2 = lw = w * exp(mean_loglike - loglike)
+__global__ void k_wll_partial(const double* __restrict__ w, const double* __restrict__ ll, int64_t N, double* __restrict__ part) {
+    double s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) s += w[i] * ll[i];
+    __shared__ double sh[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += sh[i];
+        part[blockIdx.x] = a;
+    }
+}
+__global__ void k_like_weights(const double* __restrict__ w, const double* __restrict__ ll, double mean_loglike, int64_t N,
+                               double* __restrict__ lw) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        lw[i] = w[i] * exp(mean_loglike - ll[i]);
+}
+
 __global__ void k_fill(double* p, int64_t n, double v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }

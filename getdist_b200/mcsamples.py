@@ -169,7 +169,9 @@ class MCSamples:
         self.samples = samples
         self.numrows, self.n = samples.shape
         self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
-        self.loglikes = loglikes
+        self.loglikes = None if loglikes is None else np.asarray(loglikes, dtype=np.float64)
+        self.mean_loglike = None
+        self.shade_likes_is_mean_loglikes = False  # mcsamples.py:233
         self.label = label
         self.name_tag = name_tag
         if names is None:
@@ -209,6 +211,7 @@ class MCSamples:
         d["_device"] = self._ctx.device
         d.pop("_ctx", None)
         d["_device_valid"] = False
+        d["_loglikes_valid"] = False
         return d
 
     def __setstate__(self, d):
@@ -249,6 +252,17 @@ class MCSamples:
         if not self._device_valid:
             self._ctx.set_samples(self.samples, self.weights, self.chain_offsets)
             self._device_valid = True
+            self._loglikes_valid = False
+
+    def _ensure_loglikes(self):
+        """Upload the log-likelihoods once per sample store; the device computes mean_loglike (chains.py:380-381)
+        and the mean-likelihood weights weights * exp(mean_loglike - loglikes) (mcsamples.py:1560, 1830)."""
+        if self.loglikes is None:
+            raise MCSamplesError("meanlikes needs loglikes")
+        self._upload()
+        if not getattr(self, "_loglikes_valid", False):
+            self.mean_loglike = self._ctx.set_loglikes(self.loglikes)
+            self._loglikes_valid = True
 
     def _weightsChanged(self):
         """chains.py:310-323: invalidate everything derived from the samples (and the device copy)."""
@@ -264,7 +278,7 @@ class MCSamples:
         self.samples = np.asarray(samples, dtype=np.float64)
         self.numrows, self.n = self.samples.shape
         self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
-        self.loglikes = loglikes
+        self.loglikes = None if loglikes is None else np.asarray(loglikes, dtype=np.float64)
         self._weightsChanged()
 
     def updateBaseStatistics(self):
@@ -657,16 +671,22 @@ class MCSamples:
 
     def _densities_1d(self, indices, meanlikes=False, _out=None, _device_ptr=None, **kwargs):
         if meanlikes:
-            raise NotImplementedError("meanlikes is not on the device path yet (SURVEY.md s8f-3)")
+            if self.shade_likes_is_mean_loglikes:
+                raise NotImplementedError("shade_likes_is_mean_loglikes (signed weights * loglikes) is not on the device path")
+            self._ensure_loglikes()
         self._ensure_param_ranges(indices)
         if kwargs.get("smooth_scale_1D", self.smooth_scale_1D) <= 0:
             self._ensure_neff(indices)
         specs = [self._spec_1d(j, kwargs) for j in indices]
-        P, res = self._ctx.density1d_batch(specs, out=_out, device_ptr=_device_ptr)
+        L = None
+        if meanlikes:
+            P, L, res = self._ctx.density1d_batch(specs, likes=True)
+        else:
+            P, res = self._ctx.density1d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, res  # grids stay on the device (row i at device_ptr + i * max(fine_bins))
         out = []
-        for j, sp, row, r in zip(indices, specs, P, res):
+        for k, (j, sp, row, r) in enumerate(zip(indices, specs, P, res)):
             par = self.paramNames.names[j]
             if sp.smooth_scale_1D <= 0:
                 if r.status & _abi.ST_BW_FALLBACK:
@@ -686,7 +706,7 @@ class MCSamples:
                 raise DensitiesError("no samples in bin")
             x = np.linspace(sp.binmin, sp.binmax, sp.fine_bins)
             d = Density1D(x, P=row[: sp.fine_bins], view_ranges=[par.range_min, par.range_max])
-            d.likes = None
+            d.likes = None if L is None else L[k][: sp.fine_bins]  # mcsamples.py:1672-1684
             d._gdk = dict(kde_h=r.kde_h, smooth_1D=r.smooth_1D, winw=r.winw, status=r.status, n_feval=r.n_feval)
             if not kwargs:
                 self.density1D[par.name] = d
@@ -708,8 +728,8 @@ class MCSamples:
         """mcsamples.py:1748-2010."""
         if self.needs_update:
             self.updateBaseStatistics()
-        if meanlikes or mask_function is not None:
-            raise NotImplementedError("meanlikes / mask_function are not on the device path yet (SURVEY.md s8f-3)")
+        if mask_function is not None:
+            raise NotImplementedError("mask_function is not on the device path yet (SURVEY.md s8f-3)")
         j, parx = self._parAndNumber(j)
         j2, pary = self._parAndNumber(j2)
         if j is None or j2 is None:
@@ -719,7 +739,10 @@ class MCSamples:
             ncontours = min(num_plot_contours, ncontours)
         want = [] if get_density else list(self.contours[:ncontours])
         density = None
-        if not kwargs:
+        if meanlikes:
+            # mcsamples.py:1829-1831, 1886-1901, 2004-2006 (likes are only attached when get_density=False)
+            density = self._densities_2d([(j, j2)], _contours=want, _likes=True, **kwargs)[0]
+        elif not kwargs:
             cached = self._density2D.get((j, j2))
             if cached is not None:
                 # a fresh object per call, as the reference returns (callers normalise in place)
@@ -736,7 +759,7 @@ class MCSamples:
             density.contours = np.array(dev[1][:len(want)])
         else:
             density.contours = density.getContourLevels(want)  # more than 4 contours: host numpy
-        density.likes = None
+        density.likes = getattr(density, "_likes2d", None) if meanlikes else None
         return density
 
     def _spec_2d(self, j, j2, kwargs):
@@ -946,7 +969,9 @@ class MCSamples:
                 sp["ry_fixed"] = smooth * fine / nbin2D
         return sp
 
-    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, **kwargs):
+    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, **kwargs):
+        if _likes:
+            self._ensure_loglikes()
         self._ensure_param_ranges([p for pr in pairs for p in pr])
         if float(kwargs.get("smooth_scale_2D", self.smooth_scale_2D)) < 0:
             self._ensure_neff([p for pr in pairs for p in pr])
@@ -957,7 +982,11 @@ class MCSamples:
         specs["n_contours"] = len(conts)
         for k, c in enumerate(conts):
             specs["contours"][:, k] = c
-        buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
+        lbuf = None
+        if _likes:
+            buf, lbuf, offsets, res = self._ctx.density2d_batch(specs, likes=True)
+        else:
+            buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
         out = []
@@ -983,6 +1012,8 @@ class MCSamples:
             d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
                           n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G,
                           levels=(conts, [r.levels[k] for k in range(len(conts))]) if conts else None)
+            if lbuf is not None:
+                d._likes2d = lbuf[off: off + G * G].reshape(G, G)
             if not kwargs:
                 self._density2D[(j, j2)] = d
             out.append(d)

@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct gdk_ctx gdk_ctx;
 
-#define GDK_ABI_VERSION 3
+#define GDK_ABI_VERSION 4
 
 /* error codes */
 #define GDK_OK 0
@@ -94,6 +94,13 @@ double gdk_phase_ms(gdk_ctx* ctx, int32_t phase);
 int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
                         int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains);
 
+/* log-likelihoods of the stored rows -- replaces the mean_loglike dot product of setMeans (chains.py:380-381)
+ * and the N-sized mean-likelihood weights  weights * exp(mean_loglike - loglikes)  of the `meanlikes` option
+ * (mcsamples.py:1556-1561, 1829-1831), built on the device (float64, then the same 64-bit fixed point as the
+ * sample weights).  loglikes: n = N doubles (borrowed) or NULL to clear.  mean_loglike_out (optional) receives
+ * sum(w * loglikes) / sum(w).  Call after gdk_set_samples.                                                    */
+int32_t gdk_set_loglikes(gdk_ctx* ctx, const double* loglikes, int64_t n, double* mean_loglike_out);
+
 /* ---------------------------------------------------------------------------------------------
  * weighted moments -- replaces setMeans/getMeans (chains.py:373-398), getVars (:400-412),
  * cov/_setCov/getCov (:709-733, 339-361), the w statistics of updateBaseStatistics
@@ -151,6 +158,12 @@ typedef struct gdk_result1d {
 int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, int64_t stride,
                             gdk_result1d* res, uint32_t flags);
 
+/* Same, plus the mean likelihoods of get1DDensityGridData(meanlikes=True) (mcsamples.py:1556-1561, 1597-1598,
+ * 1672-1684; default shade_likes_is_mean_loglikes = False): likes_out laid out like P_out (NULL: plain call).
+ * Needs gdk_set_loglikes.                                                                                   */
+int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, double* likes_out,
+                                  int64_t stride, gdk_result1d* res, uint32_t flags);
+
 /* ---------------------------------------------------------------------------------------------
  * 2D densities -- replaces the body of get2DDensityGridData (mcsamples.py:1748-1990) after
  * _initParamRanges: _binSamples x2 + _make2Dhist (:1821-1827, 1724-1728), getAutoBandwidth2D
@@ -204,6 +217,11 @@ typedef struct gdk_result2d {
 /* P_out: densities packed back to back; density i (G_i x G_i doubles, [y][x]) at P_out + offsets[i]. */
 int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out,
                             const int64_t* offsets, gdk_result2d* res, uint32_t flags);
+
+/* Same, plus the mean likelihoods of get2DDensityGridData(meanlikes=True) (mcsamples.py:1829-1831, 1886-1901,
+ * 2004-2006): likes_out laid out like P_out (NULL: plain call), max-normalised.  Needs gdk_set_loglikes.     */
+int32_t gdk_density2d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, double* likes_out,
+                                  const int64_t* offsets, gdk_result2d* res, uint32_t flags);
 
 /* ---------------------------------------------------------------------------------------------
  * lagged sums over the stored rows -- the N-sized arithmetic of the MCMC effective-sample estimate

@@ -79,7 +79,15 @@ int hs_dct2(const double* in, int n, int nl, double* out) {
 }
 
 // full 1D grid stage on a given histogram
+int hs_kde1d_likes(const gdk_spec1d* sp, const double* bins, const double* likebins, double* P_out, double* likes_out,
+                   gdk_result1d* res);
 int hs_kde1d(const gdk_spec1d* sp, const double* bins, double* P_out, gdk_result1d* res) {
+    return hs_kde1d_likes(sp, bins, nullptr, P_out, nullptr, res);
+}
+
+// likebins / likes_out may be NULL (plain density)
+int hs_kde1d_likes(const gdk_spec1d* sp, const double* bins, const double* likebins, double* P_out, double* likes_out,
+                   gdk_result1d* res) {
     CoopHost co;
     const int F = sp->fine_bins;
     IsjConsts K;
@@ -108,6 +116,12 @@ int hs_kde1d(const gdk_spec1d* sp, const double* bins, double* P_out, gdk_result
         c4.resize(4 * (size_t)F);
         gdk_fill_cos(c4.data(), 4 * F);
         W.cos4 = c4.data();
+    }
+    std::vector<double> raw(F);
+    if (likebins && likes_out) {
+        W.likebins = likebins;
+        W.raw = raw.data();
+        W.likes_out = likes_out;
     }
     kde1d_core(co, *sp, K, W, P_out, res);
     return 0;

@@ -268,3 +268,40 @@ def test_sorted_sweep_partner_layouts(P, N):
         got = buf[off: off + G * G]
         assert np.all((ref == 0) == (got == 0)), (sp.px, sp.py)
         assert np.max(np.abs(got - ref)) <= 1e-11 * np.max(ref), (sp.px, sp.py)
+
+
+def test_meanlikes_1d_2d():
+    """get1DDensityGridData / get2DDensityGridData(meanlikes=True) on the device against the reference
+    goldens and the oracle (case 'likes')"""
+    from getdist_b200 import MCSamples
+
+    case, g = load_case("likes")
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], loglikes=case["loglikes"], names=case["names"],
+                   ranges=case["ranges"], sampler="uncorrelated")
+    o = make_oracle(case)
+    worst1 = worst2 = 0
+    for kw in case["likes_kwargs_1d"]:
+        tag = kw_tag(kw)
+        for j in range(len(case["names"])):
+            d = mc.get1DDensityGridData(j, meanlikes=True, **kw)
+            assert np.max(np.abs(d.P - g["l1/%s/%d/P" % (tag, j)])) < 1e-6
+            err = np.max(np.abs(d.likes - g["l1/%s/%d/likes" % (tag, j)]))
+            assert err < 1e-6, (tag, j, err)
+            worst1 = max(worst1, err)
+    np.testing.assert_allclose(mc.mean_loglike, float(g["mean_loglike"]), rtol=1e-12)
+    for kw in case["likes_kwargs_2d"]:
+        tag = kw_tag(kw)
+        for (jx, jy) in case["pairs"]:
+            d = mc.get2DDensityGridData(jx, jy, meanlikes=True, **kw)
+            amise = bool(d._gdk["status"] & AMISE_BITS)
+            tol = 1e-5 if amise else 1e-6
+            assert np.max(np.abs(d.P - g["l2/%s/%d_%d/P" % (tag, jx, jy)])) < tol
+            err = np.max(np.abs(d.likes - g["l2/%s/%d_%d/likes" % (tag, jx, jy)]))
+            assert err < 10 * tol, (tag, jx, jy, err)
+            assert np.max(np.abs(d.likes - o.density_2d(jx, jy, meanlikes=True, **kw).likes)) < 10 * tol
+            np.testing.assert_allclose(d.contours, g["l2/%s/%d_%d/contours" % (tag, jx, jy)], rtol=1e-4 if amise else 1e-7)
+            worst2 = max(worst2, err)
+    # without meanlikes the attribute is None; get_density=True returns no likes (mcsamples.py:1992-1993)
+    assert mc.get2DDensityGridData(0, 1).likes is None
+    assert mc.get1DDensityGridData(0).likes is None
+    print("meanlikes worst 1D", worst1, "2D", worst2)

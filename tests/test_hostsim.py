@@ -209,3 +209,35 @@ def test_contour_levels_core(hs):
             out = hs.hs_contours(dptr(P), P.shape[0], dptr(conts), 3, dptr(lv))
             assert out == 0
             np.testing.assert_allclose(lv[:3], ref, rtol=1e-9, atol=1e-14)
+
+
+def test_kde1d_core_meanlikes(hs):
+    """mean likelihoods of the 1D grid stage (kde1d_core, mcsamples.py:1556-1561, 1597-1598, 1672-1684) against the
+    oracle and the reference golden (case 'likes': unbounded, bounded, and fixed-width kernels)"""
+    from oracle.getdist_oracle import bin_geometry, bin_indices
+
+    case, g = load_case("likes")
+    o = make_oracle(case)
+    lw = o.weights * np.exp(o.mean_loglike - o.loglikes)
+    for kw in case["likes_kwargs_1d"]:
+        tag = kw_tag(kw)
+        for j in range(o.n):
+            d = o.density_1d(j, meanlikes=True, **kw)
+            par = o.pars[j]
+            s = dict(o.settings)
+            s.update(kw)
+            F = s["fine_bins"]
+            binmin, binmax, fw = bin_geometry(par, F)
+            ix = bin_indices(o.samples[:, j], binmin, fw)
+            bins = np.bincount(ix, weights=o.weights, minlength=F)
+            lbins = np.bincount(ix, weights=lw, minlength=F)
+            sp = Spec1D(j, F, binmin, binmax, par.range_min, par.range_max, par.param_min, par.param_max,
+                        par.sigma_range, par.err, o._neff(par), s["smooth_scale_1D"],
+                        (par.range_max - par.range_min) / (s["num_bins"] - 1), s["boundary_correction_order"],
+                        s["mult_bias_correction_order"], int(par.has_limits_bot), int(par.has_limits_top), int(par.periodic), 0)
+            P, L = np.empty(F), np.empty(F)
+            res = Res1D()
+            hs.hs_kde1d_likes(C.byref(sp), dptr(bins), dptr(lbins), dptr(P), dptr(L), C.byref(res))
+            assert np.max(np.abs(P - d.P)) < 1e-7
+            assert np.max(np.abs(L - d.likes)) < 1e-6, (tag, j, np.max(np.abs(L - d.likes)))
+            assert np.max(np.abs(L - g["l1/%s/%d/likes" % (tag, j)])) < 1e-6, (tag, j)
