@@ -216,7 +216,10 @@ def run_ours(args):
 
     phases = {}
 
+    host_log = []
+
     def step_resident():
+        th0 = time.perf_counter()
         mc.invalidate_density_caches()
         mc._ctx.timer_start()
         if my1d:
@@ -232,7 +235,12 @@ def run_ours(args):
                 phases[k] = ph[k]
             if "quantiles" not in phases:
                 phases["quantiles"] = ph["quantiles"]
+        th1 = time.perf_counter()
         ms = mc._ctx.timer_stop_ms()
+        wl = mc._ctx.wall_ms()
+        # host wall clock of the step and of the library calls inside it: the rest is the Python planner
+        host_log.append({"wall_ms": round((th1 - th0) * 1e3, 2), "lib_1d_ms": round(wl["call_1d"], 2),
+                         "lib_2d_ms": round(wl["call_2d"], 2), "lib_quant_ms": round(wl["call_quantiles"], 2)})
         if world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -258,11 +266,14 @@ def run_ours(args):
         clocks.start()
     total_ms = 0.0
     step_ms = []
+    mc._ctx.set_kernel_timing(True)  # event pairs around the tagged kernels of the timed steps (roofline figures)
     for _ in range(args.steps):
         step_ms.append(step_resident())
         total_ms += step_ms[-1]
     barrier()
     clk = clocks.stop() if rank == 0 else None
+    kstats = mc._ctx.kernel_stats()
+    mc._ctx.set_kernel_timing(False)
     launches = mc._ctx.launch_count() - l0
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -337,35 +348,58 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = max(("hist2d", "conv2d", "xform2d", "bw2d", "shear", "hist1d", "kde1d", "quantiles"),
               key=lambda k: phases.get(k, 0) or 0)
-    # 2D histogram phase = k_bin8 (every used column once: 8 B in, 1 B out per sample) + k_hist2d_hot (per 2 x 2 tile of
-    # pairs: four 1-byte bin columns + one 8-byte fixed-point weight per sample => 3 B per pair-sample).  These are the
-    # bytes this design has to move; the reference-shaped figure (one standalone sweep per pair, N*24 B)
-    # is reported next to it as `standalone_equiv`.
-    used2d = len({j for pr in my2d for j in pr})
-    algo_bytes = {"hist2d": N * (3.0 * len(my2d) + 9.0 * used2d), "hist1d": N * (len(my1d) + 1) * 8.0}
+    # Per-kernel figures: the library brackets the tagged kernels of the timed steps with CUDA-event pairs on its
+    # stream and counts the ALGORITHMIC bytes / flops of every launch where the launch parameters are known
+    # (gdk_kernel_stat; DESIGN.md s4 states the per-unit figures).  achieved = bytes per launch / average launch time.
+    # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of exactly
+    # this workload (profiles/r2c_*, r2f_*); other sizes have no capture -> null.
+    c2 = (N == 10_000_000 and P == 64 and world == 1)
+    ncu_traffic = {"k_bin8c": 5.96e9, "k_bucket_records": 13.49e9, "k_hist2d_records": 13.30e9,
+                   "k_shear_minmax_tiled": 8.20e9, "k_shear_hist": 63.76e9}
+    limiter = {
+        "k_hist2d_records": "LSU / shared-memory atomic pipe (ncu l1tex 82 %): per row visit one byte load, one weight load and "
+                            "two conflict-free 32-bit ATOMS (64-bit fixed-point add); DRAM streams at 1.7 TB/s",
+        "k_bucket_records": "shared-memory pipe (ncu l1tex 71 %): in-CTA counting sort + coalesced copy-out, DRAM writes at 2.5 TB/s",
+        "k_shear_hist": "instruction issue (62 %) + shared-memory atomics (l1tex 73 %) of the hot-window privatisation",
+        "k_shear_minmax_tiled": "FP64 / issue: 5 FP64 ops per pair-sample from a shared-memory tile; DRAM 1.2 TB/s",
+        "k_bin8c": "exact round-half-up bin index per sample (FP64 divide guard) + byte store",
+    }
+    FP64_NOMINAL = 37.0  # TFLOP/s, NVIDIA HGX B200 datasheet (296 TF / 8 GPUs); no measured FP64 peak on this pool
+    kernels = []
+    for nm, st in kstats.items():
+        if st["ms"] <= 0:
+            continue
+        per_launch_ms = st["ms"] / st["launches"]
+        ent = {"kernel": nm, "launches_per_step": st["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
+               "ms_per_step": st["ms"] / args.steps}
+        if nm.startswith("k_conv2d"):
+            tf = st["flops"] / (st["ms"] * 1e-3) / 1e12
+            ent.update({"bound": "fp64", "achieved": tf, "peak": FP64_NOMINAL, "unit": "TFLOP/s", "frac": tf / FP64_NOMINAL,
+                        "peak_source": "nominal FP64 vector peak (datasheet), not measured", "traffic": None,
+                        "algorithmic_flops_per_launch": st["flops"] / st["launches"]})
+        else:
+            gbs = st["bytes"] / (st["ms"] * 1e-3) / 1e9
+            ent.update({"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "peak_source": peak_src, "traffic": ncu_traffic.get(nm) if c2 else None,
+                        "algorithmic_bytes_per_launch": st["bytes"] / st["launches"], "limiter": limiter.get(nm)})
+        kernels.append(ent)
+    kernels.sort(key=lambda e: -e["ms_per_step"])
+    hbm_kernels = [e for e in kernels if e["bound"] == "hbm"]
     roof = None
-    if phases.get("hist2d", 0) > 0:
-        t2 = phases["hist2d"] * 1e-3
-        ach = algo_bytes["hist2d"] / t2 / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of the k_hist2d_hot launch from the ncu --set full capture of exactly
-        # this workload (profiles/r1s_ncu_full_summary.csv: 51.48 + 0.44 GB); other sizes have no capture -> null
-        traffic = 51.92e9 if (N == 10_000_000 and P == 64 and world == 1) else None
-        roof = {"kernel": "k_hist2d_hot (+ k_bin8 pre-binning, same CUDA-event phase)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "algorithmic_bytes": algo_bytes["hist2d"], "kernel_ms": phases["hist2d"], "peak_source": peak_src,
-                "dominant_phase_by_time": dom,
-                "limiter": "shared-memory atomic pipe, not HBM: ncu l1tex throughput 85 %, ~3 wavefronts per ATOMS "
-                           "(profiles/r1s); two native 32-bit ATOMS per 64-bit fixed-point update",
-                "bin_updates_per_s": N * len(my2d) / t2,
-                "standalone_equiv": {"bytes": N * 24.0 * len(my2d), "gbs": N * 24.0 * len(my2d) / t2 / 1e9,
-                                     "note": "N*24 B per pair as the reference sweeps it (SURVEY s8d); tiling + byte "
-                                             "pre-binning remove this traffic, so it exceeds the HBM peak"}}
+    if hbm_kernels:
+        top = hbm_kernels[0]  # the HBM-side kernel with the largest share of the step
+        roof = dict(top)
+        roof["dominant_phase_by_time"] = dom
+        roof["share_of_step"] = top["ms_per_step"] / ms_per_step
+        roof["note"] = ("dominant data-path kernel by CUDA-event time; `kernels` lists every tagged kernel (the FP64 "
+                        "convolutions are compute-bound and carry a TFLOP/s figure instead)")
+    algo_bytes = {"hist1d": N * (len(my1d) + 1) * 8.0}
     hist1d = None
     if phases.get("hist1d", 0) > 0:
         a1 = algo_bytes["hist1d"] / (phases["hist1d"] * 1e-3) / 1e9
         hist1d = {"kernel": "k_hist1d_tma", "bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak,
                   "algorithmic_bytes": algo_bytes["hist1d"], "kernel_ms": phases["hist1d"],
-                  "traffic": 5.97e9 if (N == 10_000_000 and P == 64 and world == 1) else None}
+                  "traffic": 5.97e9 if c2 else None}
 
     # ---------------- CPU baseline on a bounded sample + parity check against it ----------------
     cpu = None
@@ -397,7 +431,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_step": e2e_s, "checksum": checksum, "parts": e2e_parts,
                 "path": "MCSamples.setSamples(pinned host) + updateBaseStatistics [H2D + moments] -> quantiles -> 1D + 2D batches -> pinned host grids"},
-        "gpu_launches": int(launches), "phases_ms": phases, "step_ms": [round(x, 3) for x in step_ms], "clocks": clk, "roofline": roof, "hist1d": hist1d,
+        "gpu_launches": int(launches), "phases_ms": phases, "step_ms": [round(x, 3) for x in step_ms], "host_ms": host_log[-len(step_ms):], "clocks": clk, "roofline": roof, "kernels": kernels, "hist1d": hist1d,
         "cpu_baseline": cpu, "parity_check": parity,
     }
     print(json.dumps(line))

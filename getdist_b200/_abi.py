@@ -105,6 +105,10 @@ def load():
     lib.gdk_timer_stop_ms.restype = dbl
     lib.gdk_phase_ms.argtypes = [vp, i32]
     lib.gdk_phase_ms.restype = dbl
+    lib.gdk_set_kernel_timing.argtypes = [vp, i32]
+    lib.gdk_set_kernel_timing.restype = i32
+    lib.gdk_kernel_stat.argtypes = [vp, i32, i32]
+    lib.gdk_kernel_stat.restype = dbl
     lib.gdk_set_samples.argtypes = [vp, vp, i64, i32, i64, i64, vp, vp, i32]
     lib.gdk_set_samples.restype = i32
     lib.gdk_moments.argtypes = [vp] + [vp] * 9
@@ -300,6 +304,26 @@ class Context:
 
     def phase_ms(self):
         return {nm: self.lib.gdk_phase_ms(self.h, i) for i, nm in enumerate(PHASES)}
+
+    KERNEL_SLOTS = ("k_bin8c", "k_bucket_records", "k_hist2d_records", "k_shear_minmax_tiled", "k_shear_hist",
+                    "k_conv2d<0>", "k_conv2d<1>")
+
+    def set_kernel_timing(self, on):
+        self._ck(self.lib.gdk_set_kernel_timing(self.h, 1 if on else 0), "gdk_set_kernel_timing")
+
+    def kernel_stats(self):
+        """{kernel: dict(ms, launches, bytes, flops)} accumulated since set_kernel_timing(True)"""
+        out = {}
+        for i, nm in enumerate(self.KERNEL_SLOTS):
+            n = int(self.lib.gdk_kernel_stat(self.h, i, 1))
+            if n > 0:
+                out[nm] = dict(ms=self.lib.gdk_kernel_stat(self.h, i, 0), launches=n,
+                               bytes=self.lib.gdk_kernel_stat(self.h, i, 2), flops=self.lib.gdk_kernel_stat(self.h, i, 3))
+        return out
+
+    def wall_ms(self):
+        """host wall clock spent inside the last 1D batch / 2D batch / quantile call"""
+        return {nm: self.lib.gdk_phase_ms(self.h, 10 + i) for i, nm in enumerate(("call_1d", "call_2d", "call_quantiles"))}
 
     def launch_count(self):
         return int(self.lib.gdk_launch_count(self.h))

@@ -2,6 +2,7 @@
 // include/gdk.h.  No torch types, no Python: plain CUDA runtime.  All arithmetic runs in the kernels of
 // kernels_*.cuh / kde*_core.cuh; the host code only plans launches and does O(P^2) bookkeeping.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -91,6 +92,56 @@ const Kde1dTablesHost* gdk_tables_for(gdk_ctx* ctx, int n) {
     return &r.first->second;
 }
 
+KernelTimer::KernelTimer(gdk_ctx* c, int slot, double bytes, double flops) : ctx(c) {
+    if (!c->ktiming) return;
+    if (c->kev_used == (int)c->kev.size()) {
+        gdk_ctx::KEv e{};
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+        c->kev.push_back(e);
+    }
+    idx = c->kev_used++;
+    c->kev[idx].slot = slot;
+    c->kbytes[slot] += bytes;
+    c->kflops[slot] += flops;
+    c->klaunches[slot]++;
+    cudaEventRecord(c->kev[idx].a, c->stream);
+}
+KernelTimer::~KernelTimer() {
+    if (idx >= 0) cudaEventRecord(ctx->kev[idx].b, ctx->stream);
+}
+
+extern "C" int32_t gdk_set_kernel_timing(gdk_ctx* ctx, int32_t on) {
+    if (!ctx) return GDK_ERR_ARG;
+    ctx->ktiming = on != 0;
+    ctx->kev_used = 0;
+    while (on && ctx->kev.size() < 512) {  // event pairs are created up front, not inside the timed steps
+        gdk_ctx::KEv e{};
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) break;
+        ctx->kev.push_back(e);
+    }
+    for (int i = 0; i < GDK_K_NSLOT; i++) {
+        ctx->kbytes[i] = ctx->kflops[i] = 0;
+        ctx->klaunches[i] = 0;
+    }
+    return GDK_OK;
+}
+
+extern "C" double gdk_kernel_stat(gdk_ctx* ctx, int32_t slot, int32_t what) {
+    if (!ctx || slot < 0 || slot >= GDK_K_NSLOT) return -1.0;
+    if (what == 1) return (double)ctx->klaunches[slot];
+    if (what == 2) return ctx->kbytes[slot];
+    if (what == 3) return ctx->kflops[slot];
+    double ms = 0;
+    for (int i = 0; i < ctx->kev_used; i++)
+        if (ctx->kev[i].slot == slot) {
+            float t = 0;
+            if (cudaEventSynchronize(ctx->kev[i].b) != cudaSuccess || cudaEventElapsedTime(&t, ctx->kev[i].a, ctx->kev[i].b) != cudaSuccess)
+                return -1.0;
+            ms += t;
+        }
+    return ms;
+}
+
 void PhaseTimer::begin(gdk_ctx* c, int ph) {
     ctx = c;
     phase = ph;
@@ -129,6 +180,8 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->use_hot = !(eh && eh[0] == '0');
         const char* es = getenv("GDK_SORTED");
         ctx->use_sorted = !(es && es[0] == '0');
+        const char* ess = getenv("GDK_SHEAR_SORTED");
+        ctx->shear_sorted = ess && ess[0] == '1';
         const char* em = getenv("GDK_SORTED_MIN_N");
         if (em) ctx->sorted_min_n = atoll(em);
     }
@@ -194,6 +247,7 @@ extern "C" double gdk_timer_stop_ms(gdk_ctx* ctx) {
     return (double)ms;
 }
 extern "C" double gdk_phase_ms(gdk_ctx* ctx, int32_t phase) {
+    if (ctx && phase >= 10 && phase < 14) return ctx->wall_ms[phase - 10];
     if (!ctx || phase < 0 || phase >= GDK_NPHASE || !ctx->phase_valid[phase]) return -1.0;
     float ms = 0;
     if (cudaEventSynchronize(ctx->ev1[phase]) != cudaSuccess) return -1.0;
@@ -506,6 +560,7 @@ extern "C" int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double
 extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf,
                                           double* out) {
     if (!ctx) return GDK_ERR_ARG;
+    WallTimer wt{ctx, 2};
     if (!params || !fracs || !out || np <= 0 || nf <= 0 || nf > QMAXF)
         return gdk_fail(ctx, GDK_ERR_ARG, "gdk_weighted_quantiles: need 1 <= nf <= %d", QMAXF);
     int rc = compute_moments(ctx);  // column min / max
@@ -696,6 +751,7 @@ extern "C" int32_t gdk_density1d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d
 extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec1d* specs, double* P_out, double* likes_out,
                                              int64_t stride, gdk_result1d* res, uint32_t flags) {
     if (!ctx) return GDK_ERR_ARG;
+    WallTimer wt{ctx, 0};
     const bool likes = likes_out != nullptr;
     if (likes && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "meanlikes needs gdk_set_loglikes");
     if (n <= 0 || !specs || !P_out || !res) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_density1d_batch: bad arguments");

@@ -302,7 +302,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 unsigned* start = counts + (size_t)np8 * 256;
                 unsigned* cursor = start + (size_t)np8 * 257;
                 CK2(cudaMemsetAsync(counts, 0, (size_t)np8 * 256 * 4, ctx->stream));
-                k_bin8c<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld, counts);
+                {
+                    KernelTimer kt(ctx, GDK_K_BIN8C, (double)ctx->N * np8 * 9.0, 0);
+                    k_bin8c<<<g8, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, dbj, ctx->ix8.p, ctx->ld, counts);
+                }
                 k_bucket_scan<<<np8, 256, 0, ctx->stream>>>(counts, start);
                 ctx->launches += 2;
                 SortJob* dsj = nullptr;
@@ -315,9 +318,12 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 CK2(cudaFuncSetAttribute(k_bucket_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem(rows, SRT_MAXJOBS)));
                 for (int b0 = 0; b0 < njobs; b0 += SRT_MAXJOBS) {
                     const int nb = std::min(SRT_MAXJOBS, njobs - b0);
-                    k_bucket_records<<<(unsigned)((ctx->N + rows - 1) / rows), 1024, rec_smem(rows, nb), ctx->stream>>>(
-                        ctx->ix8.p, ctx->ld, np8, pitch, rows, ctx->N, WQ, dsj + b0, nb, cursor + (size_t)b0 * 256,
-                        reinterpret_cast<uint4*>(ctx->recs.p), ctx->recw.p, pld);
+                    {
+                        KernelTimer kt(ctx, GDK_K_BUCKET_RECORDS, (double)ctx->N * (np8 + 8.0 + 40.0 * nb), 0);
+                        k_bucket_records<<<(unsigned)((ctx->N + rows - 1) / rows), 1024, rec_smem(rows, nb), ctx->stream>>>(
+                            ctx->ix8.p, ctx->ld, np8, pitch, rows, ctx->N, WQ, dsj + b0, nb, cursor + (size_t)b0 * 256,
+                            reinterpret_cast<uint4*>(ctx->recs.p), ctx->recw.p, pld);
+                    }
                     ctx->launches++;
                     for (int j0 = 0; j0 < nb;) {  // sub-ranges of equal lane layout
                         int j1 = j0;
@@ -329,13 +335,16 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         k_hist2d_records<LG><<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsj + b0, j0, ctx->recs.p, ctx->recw.p, pld, start, \
                                                                          GR, chunk, ctx->N);                      \
         break;
-                        switch (sj[b0 + j0].lg) {
-                            GDK_LAUNCH_REC(0)
-                            GDK_LAUNCH_REC(1)
-                            GDK_LAUNCH_REC(2)
-                            GDK_LAUNCH_REC(3)
-                            GDK_LAUNCH_REC(4)
-                            GDK_LAUNCH_REC(5)
+                        {
+                            KernelTimer kt(ctx, GDK_K_HIST2D_RECORDS, (double)ctx->N * 40.0 * (j1 - j0), 0);
+                            switch (sj[b0 + j0].lg) {
+                                GDK_LAUNCH_REC(0)
+                                GDK_LAUNCH_REC(1)
+                                GDK_LAUNCH_REC(2)
+                                GDK_LAUNCH_REC(3)
+                                GDK_LAUNCH_REC(4)
+                                GDK_LAUNCH_REC(5)
+                            }
                         }
 #undef GDK_LAUNCH_REC
                         ctx->launches++;
@@ -471,9 +480,14 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (nshear) {
         rc = upload_vec(ctx, sjobs, ctx->bytes2d_b, &dsj);
         if (rc) return rc;
-        // groups of jobs sharing (p1 column, p1 geometry, grid size): x_i is read once per row for the group
         std::vector<int> ord(nshear);
         for (int i = 0; i < nshear; i++) ord[i] = i;
+        // default: column-tiled min/max pass (k_shear_minmax_tiled) + hot-window re-binning (k_shear_hist);
+        // GDK_SHEAR_SORTED=1: bucket-sorted records for the re-binning as well (measured slower at C2, profiles/r2e)
+        const bool shear_tiled = ctx->use_sorted;
+        bool shear_sorted = shear_tiled && ctx->shear_sorted && ctx->N >= ctx->sorted_min_n && ctx->N < (int64_t)0xfffffff0u;
+        for (int i = 0; i < nshear; i++) shear_sorted = shear_sorted && sjobs[i].Gb == 256;
+        bool geom_done = false;
         auto keyless = [&](int a, int b) {
             const ShearJob &A = sjobs[a], &B = sjobs[b];
             if (A.pi != B.pi) return A.pi < B.pi;
@@ -483,6 +497,182 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             return A.pj < B.pj;
         };
         std::sort(ord.begin(), ord.end(), keyless);
+        if (shear_tiled) {
+            // ---- column-tiled passes (kernels_2d.cuh, "bucket-sorted sweep for the sheared re-binning") ----
+            // anchors = (p1 column, p1 geometry) with <= SHR_MAXCOLS-1 partners each, in column order
+            struct Anchor { int pi; double p1_min, dx1, inv1; std::vector<int> jobs; };
+            std::vector<Anchor> anchors;
+            for (int k = 0; k < nshear; k++) {
+                const ShearJob& j = sjobs[ord[k]];
+                bool fresh = anchors.empty();
+                if (!fresh) {
+                    const Anchor& a = anchors.back();
+                    fresh = (int)a.jobs.size() == SHR_MAXCOLS - 1 || a.pi != j.pi || a.p1_min != j.p1_min || a.dx1 != j.dx1;
+                }
+                if (fresh) anchors.push_back(Anchor{j.pi, j.p1_min, j.dx1, j.inv1, {}});
+                anchors.back().jobs.push_back(ord[k]);
+            }
+            // batches of consecutive anchors whose columns fit one shared-memory tile
+            std::vector<ShearBatch> batches;
+            std::vector<ShearRecJob> rjobs;
+            std::vector<ShearPairRef> prefs;
+            std::vector<SortJob> sjs;
+            {
+                std::vector<int> cols;
+                auto col_of = [&](int p) {
+                    for (size_t c = 0; c < cols.size(); c++)
+                        if (cols[c] == p) return (int)c;
+                    return -1;
+                };
+                ShearBatch cur{};
+                auto close = [&]() {
+                    if (!cur.njobs) return;
+                    cur.ncols = (int)cols.size();
+                    for (size_t c = 0; c < cols.size(); c++) cur.cols[c] = cols[c];
+                    batches.push_back(cur);
+                    cols.clear();
+                };
+                for (size_t ai = 0; ai < anchors.size(); ai++) {
+                    const Anchor& a = anchors[ai];
+                    std::vector<int> add;
+                    auto want = [&](int p) {
+                        if (col_of(p) < 0 && std::find(add.begin(), add.end(), p) == add.end()) add.push_back(p);
+                    };
+                    want(a.pi);
+                    for (int jb : a.jobs) want(sjobs[jb].pj);
+                    if (cur.njobs && (cols.size() + add.size() > (size_t)SHR_MAXCOLS || cur.njobs == SHR_MAXJOBS ||
+                                      cur.npairs + (int)a.jobs.size() > 16 * SHR_MAXPW)) {
+                        close();
+                        add.clear();
+                        want(a.pi);
+                        for (int jb : a.jobs) want(sjobs[jb].pj);
+                    }
+                    if (!cur.njobs || cols.empty()) {
+                        cur = ShearBatch{};
+                        cur.job0 = (int)rjobs.size();
+                        cur.pair0 = (int)prefs.size();
+                    }
+                    for (int p : add) cols.push_back(p);
+                    ShearRecJob rj{};
+                    rj.acol = col_of(a.pi);
+                    rj.np = (int)a.jobs.size();
+                    rj.pair0 = (int)prefs.size() - cur.pair0;
+                    rj.p1_min = a.p1_min;
+                    rj.dx1 = a.dx1;
+                    rj.inv1s = a.inv1 * 1048576.0;
+                    SortJob sj{};
+                    sj.slot = (int)rjobs.size();
+                    sj.nl = rj.np;
+                    while ((1 << sj.lg) < sj.nl) sj.lg++;
+                    sj.c0 = -1;
+                    for (int l = 0; l < rj.np; l++) {
+                        const ShearJob& j = sjobs[a.jobs[l]];
+                        prefs.push_back(ShearPairRef{rj.acol, col_of(j.pj), a.jobs[l], cur.njobs, j.r0, j.r1});
+                        sj.sb[l] = 256;  // rot grid [b2][b1]
+                        sj.sc[l] = 1;
+                        sj.off[l] = j.off;
+                    }
+                    rjobs.push_back(rj);
+                    sjs.push_back(sj);
+                    cur.njobs++;
+                    cur.npairs += rj.np;
+                }
+                close();
+            }
+            const int nanch = (int)rjobs.size(), nbatch = (int)batches.size();
+            ShearBatch* dbat = nullptr;
+            ShearRecJob* drj = nullptr;
+            ShearPairRef* dpr = nullptr;
+            SortJob* dsortj = nullptr;
+            rc = upload_vec(ctx, batches, ctx->bytes2d_c, &dbat);
+            if (rc) return rc;
+            rc = upload_vec(ctx, rjobs, ctx->bytes2d_sh1, &drj);
+            if (rc) return rc;
+            rc = upload_vec(ctx, prefs, ctx->bytes2d_sh2, &dpr);
+            if (rc) return rc;
+            rc = upload_vec(ctx, sjs, ctx->bytes2d_s, &dsortj);
+            if (rc) return rc;
+            const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / nbatch);
+            int64_t seglen = std::max<int64_t>(16 * SHR_ROWS, (ctx->N + want - 1) / want);
+            seglen = (seglen + SHR_ROWS - 1) / SHR_ROWS * SHR_ROWS;
+            std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+            rc = gdk_upload_segs(ctx, segs, ctx->segs);
+            if (rc) return rc;
+            const int nseg = (int)segs.size();
+            const int64_t pld = (ctx->N + 31) & ~int64_t(31);
+            int maxjobs = 0;
+            size_t mm_smem = 0, rec_smem = 0;
+            for (const ShearBatch& b : batches) {
+                maxjobs = std::max(maxjobs, b.njobs);
+                mm_smem = std::max(mm_smem, (size_t)b.ncols * SHR_ROWS * 8 + (size_t)b.npairs * sizeof(ShearPairRef) + (size_t)b.njobs * 1024);
+                rec_smem = std::max(rec_smem, (size_t)SHR_ROWS * 44 + 2048 + (size_t)b.njobs * (2048 + SHR_ROWS) + 32 * sizeof(ShearLaneParam) +
+                                                  (size_t)b.ncols * SHR_ROWS * 8);
+            }
+            if (ctx->scratch.ensure((size_t)nshear * nseg * 2 + (size_t)nshear * 4 + 8) || ctx->bucket2.ensure((size_t)nanch * (256 + 257 + 256)) ||
+                (shear_sorted && (ctx->recs.ensure((size_t)maxjobs * pld * 32) || ctx->recw.ensure((size_t)maxjobs * pld))))
+                return gdk_fail(ctx, GDK_ERR_NOMEM, "sheared re-binning work space");
+            double* part = ctx->scratch.p;
+            dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
+            unsigned* counts = ctx->bucket2.p;
+            unsigned* start = counts + (size_t)nanch * 256;
+            unsigned* cursor = start + (size_t)nanch * 257;
+            CK2(cudaFuncSetAttribute(k_shear_minmax_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(mm_smem, 48 << 10)));
+            CK2(cudaFuncSetAttribute(k_shear_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(rec_smem, 48 << 10)));
+            PhaseTimer pt;
+            pt.begin(ctx, GDK_PH_SHEAR);
+            CK2(cudaMemsetAsync(counts, 0, (size_t)nanch * 256 * 4, ctx->stream));
+            dim3 gm((unsigned)nseg, (unsigned)nbatch);
+            {
+                double colsum = 0;
+                for (const ShearBatch& b : batches) colsum += b.ncols;
+                KernelTimer kt(ctx, GDK_K_SHEAR_MINMAX, (double)ctx->N * colsum * 8.0, (double)ctx->N * nshear * 3.0);
+                k_shear_minmax_tiled<<<gm, SHR_ROWS, mm_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dbat, drj, dpr, part,
+                                                                             shear_sorted ? counts : nullptr);
+            }
+            k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
+            ctx->launches += 2;
+            geom_done = true;
+            if (shear_sorted) {
+                k_bucket_scan<<<nanch, 256, 0, ctx->stream>>>(counts, start);
+                k_cursor_init<<<nanch, 256, 0, ctx->stream>>>(dsortj, start, cursor);
+                ctx->launches += 2;
+            }
+            const int chunk = 16384;
+            const size_t srt_smem = (size_t)2 * 256 * 32 * 4;
+            for (int b = 0; b < nbatch && shear_sorted; b++) {
+                const ShearBatch& B = batches[b];
+                k_shear_records<<<(unsigned)((ctx->N + SHR_ROWS - 1) / SHR_ROWS), SHR_ROWS, rec_smem, ctx->stream>>>(
+                    ctx->dX.p, ctx->ld, ctx->N, ctx->dWq.p, dbat, b, drj, dpr, dgeom, cursor + (size_t)B.job0 * 256,
+                    reinterpret_cast<uint4*>(ctx->recs.p), ctx->recw.p, pld);
+                ctx->launches++;
+                for (int j0 = 0; j0 < B.njobs;) {  // sub-ranges of equal lane layout
+                    int j1 = j0;
+                    while (j1 < B.njobs && sjs[B.job0 + j1].lg == sjs[B.job0 + j0].lg) j1++;
+                    dim3 gh((unsigned)((ctx->N + chunk - 1) / chunk), (unsigned)(j1 - j0));
+#define GDK_LAUNCH_REC(LG)                                                                                                       \
+    case LG:                                                                                                                     \
+        CK2(cudaFuncSetAttribute(k_hist2d_records<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt_smem));            \
+        k_hist2d_records<LG><<<gh, SRT_THREADS, srt_smem, ctx->stream>>>(dsortj + B.job0, j0, ctx->recs.p, ctx->recw.p, pld, start, \
+                                                                         ctx->gbins_rot.p, chunk, ctx->N);                       \
+        break;
+                    switch (sjs[B.job0 + j0].lg) {
+                        GDK_LAUNCH_REC(0)
+                        GDK_LAUNCH_REC(1)
+                        GDK_LAUNCH_REC(2)
+                        GDK_LAUNCH_REC(3)
+                        GDK_LAUNCH_REC(4)
+                        GDK_LAUNCH_REC(5)
+                    }
+#undef GDK_LAUNCH_REC
+                    ctx->launches++;
+                    j0 = j1;
+                }
+            }
+            pt.end();
+            CK2(cudaGetLastError());
+        }
+        if (!shear_sorted) {
+        // groups of jobs sharing (p1 column, p1 geometry, grid size): x_i is read once per row for the group
         std::vector<ShearGroup> sgroups;
         for (int k = 0; k < nshear; k++) {
             const ShearJob& j = sjobs[ord[k]];
@@ -521,20 +711,30 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         rc = gdk_upload_segs(ctx, segs, ctx->segs);
         if (rc) return rc;
         const int nseg = (int)segs.size();
-        if (ctx->scratch.ensure((size_t)nshear * nseg * 2 + (size_t)nshear * 4 + 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "shear scratch");
-        double* part = ctx->scratch.p;
-        dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
         PhaseTimer pt;
-        pt.begin(ctx, GDK_PH_SHEAR);
         dim3 g((unsigned)nseg, (unsigned)ngroups);
-        k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsg, part);
-        k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
+        if (!geom_done) {
+            if (ctx->scratch.ensure((size_t)nshear * nseg * 2 + (size_t)nshear * 4 + 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "shear scratch");
+            double* part = ctx->scratch.p;
+            dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
+            pt.begin(ctx, GDK_PH_SHEAR);
+            k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsg, part);
+            k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
+        } else {
+            pt.resume(ctx, GDK_PH_SHEAR);
+        }
         const size_t sh_smem = (size_t)SG * 2 * HW * HW * 4;
         CK2(cudaFuncSetAttribute(k_shear_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_smem));
-        k_shear_hist<<<g, 1024, sh_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
+        {
+            double colsum = 0;  // per group: x_i + nj partner columns + the weights
+            for (const ShearGroup& sgp : sgroups) colsum += 2.0 + sgp.nj;
+            KernelTimer kt(ctx, GDK_K_SHEAR_HIST, (double)ctx->N * colsum * 8.0, (double)ctx->N * nshear * 3.0);
+            k_shear_hist<<<g, 1024, sh_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
+        }
         ctx->launches += 3;
         pt.end();
         CK2(cudaGetLastError());
+        }
     }
     // fixed point -> float64, in place
     k_u64_to_f64_inplace<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->gbins2.p, (int64_t)gtot, 1.0 / ctx->wscale);
@@ -746,7 +946,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             int lim = 32;
             while (lim < cjs[b].w) lim *= 2;
             int e = b, gm = 0, wm = 0;
-            while (e < n && cjs[e].w <= lim) {
+            while (e < n && cjs[e].w <= lim && e - b < 384) {  // <= 384 jobs: the finished grids of a group are copied
+                                                                // back (second stream) while the next group computes
                 gm = std::max(gm, cjs[e].G);
                 wm = std::max(wm, cjs[e].w);
                 e++;
@@ -773,46 +974,6 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         CK2(cudaFuncSetAttribute(k_conv2d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
         CK2(cudaFuncSetAttribute(k_conv2d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     }
-    for (const Grp& g : groups) {
-        const int nj = g.e - g.b;
-        const int K = 2 * g.wmax + 1;
-        // mask tables / maps (jobs without bias correction and without boundary correction skip internally)
-        dim3 gt((unsigned)K, (unsigned)nj);
-        k_mask_T<<<gt, 256, 0, ctx->stream>>>(dcj + g.b);
-        dim3 gm((unsigned)((g.Gmax + 255) / 256), (unsigned)nj);
-        k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
-        const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
-        dim3 gc((unsigned)tiles, (unsigned)nj);
-        const int kc0 = pick_kc(g.wmax, budget0), kc1 = pick_kc(g.wmax, budget1);
-        k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
-        dim3 gcirc((unsigned)((g.Gmax * g.Gmax + 255) / 256), (unsigned)nj);
-        if (any_periodic) {
-            k_conv2d_circ<0><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
-            ctx->launches++;
-        }
-        dim3 gb(64, (unsigned)nj);
-        if (likes) {
-            // mean likelihoods (mcsamples.py:1886-1898): likes (*) Win, optional bias step, ratio to the raw bins2D
-            k_conv2d<2><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
-            if (any_periodic) k_conv2d_circ<2><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
-            k_likes2d<0><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
-            k_conv2d<3><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
-            if (any_periodic) k_conv2d_circ<3><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
-            k_likes2d<1><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
-            ctx->launches += any_periodic ? 6 : 4;
-        }
-        k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
-        ctx->launches += 4;
-        for (int it = 0; it < max_mbc; it++) {
-            k_make_box<<<gb, 256, 0, ctx->stream>>>(dcj + g.b, it);
-            k_conv2d<1><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, it, g.wmax, kc1);
-            ctx->launches += 2;
-            if (any_periodic) {
-                k_conv2d_circ<1><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, it);
-                ctx->launches++;
-            }
-        }
-    }
     // output
     double* dout = nullptr;
     if (dev_out) {
@@ -834,43 +995,94 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             dlout = ctx->f2l.p - offsets[0];
         }
     }
-    {
-        dim3 gf(64, (unsigned)n);
-        k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dout, doffs, dres);
+    bool any_contours = false;
+    for (int i = 0; i < n; i++) any_contours = any_contours || specs[i].n_contours > 0;
+    while (ctx->pipe_events.size() < groups.size()) {
+        cudaEvent_t e;
+        CK2(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    int gidx = 0;
+    for (const Grp& g : groups) {
+        const int nj = g.e - g.b;
+        const int K = 2 * g.wmax + 1;
+        // mask tables / maps (jobs without bias correction and without boundary correction skip internally)
+        dim3 gt((unsigned)K, (unsigned)nj);
+        k_mask_T<<<gt, 256, 0, ctx->stream>>>(dcj + g.b);
+        dim3 gm((unsigned)((g.Gmax + 255) / 256), (unsigned)nj);
+        k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
+        const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
+        dim3 gc((unsigned)tiles, (unsigned)nj);
+        const int kc0 = pick_kc(g.wmax, budget0), kc1 = pick_kc(g.wmax, budget1);
+        double cflops0 = 0, cflops1 = 0, cbytes = 0;
+        for (int k = g.b; k < g.e; k++) {
+            const double K2 = (2.0 * cjs[k].w + 1) * (2.0 * cjs[k].w + 1), G2 = (double)cjs[k].G * cjs[k].G;
+            cflops0 += 2.0 * G2 * K2 * ((cjs[k].bounded && cjs[k].bco == 1) ? 3.0 : 1.0);
+            cflops1 += 2.0 * G2 * K2;
+            cbytes += 16.0 * G2;
+        }
+        {
+            KernelTimer kt(ctx, GDK_K_CONV2D_0, cbytes, cflops0);
+            k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
+        }
+        dim3 gcirc((unsigned)((g.Gmax * g.Gmax + 255) / 256), (unsigned)nj);
+        if (any_periodic) {
+            k_conv2d_circ<0><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            ctx->launches++;
+        }
+        dim3 gb(64, (unsigned)nj);
+        if (likes) {
+            // mean likelihoods (mcsamples.py:1886-1898): likes (*) Win, optional bias step, ratio to the raw bins2D
+            k_conv2d<2><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
+            if (any_periodic) k_conv2d_circ<2><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            k_likes2d<0><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+            k_conv2d<3><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
+            if (any_periodic) k_conv2d_circ<3><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, 0);
+            k_likes2d<1><<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+            ctx->launches += any_periodic ? 6 : 4;
+        }
+        k_boundary2d<<<gb, 256, 0, ctx->stream>>>(dcj + g.b);
+        ctx->launches += 4;
+        for (int it = 0; it < max_mbc; it++) {
+            k_make_box<<<gb, 256, 0, ctx->stream>>>(dcj + g.b, it);
+            {
+                KernelTimer kt(ctx, GDK_K_CONV2D_1, cbytes, cflops1);
+                k_conv2d<1><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, it, g.wmax, kc1);
+            }
+            ctx->launches += 2;
+            if (any_periodic) {
+                k_conv2d_circ<1><<<gcirc, 256, 0, ctx->stream>>>(dcj + g.b, it);
+                ctx->launches++;
+            }
+        }
+        // normalised output of this group; its device->host copies run on the second stream behind an event
+        dim3 gf(64, (unsigned)nj);
+        k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
         ctx->launches++;
         if (likes) {
-            k_likes_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj, dlout, doffs);
+            k_likes_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj + g.b, dlout, doffs + g.b);
             ctx->launches++;
         }
-        bool any_contours = false;
-        for (int i = 0; i < n; i++) any_contours = any_contours || specs[i].n_contours > 0;
         if (any_contours) {
-            k_contours2d<<<n, 1024, 0, ctx->stream>>>(dcj, dout, doffs, dres);
+            k_contours2d<<<nj, 1024, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
             ctx->launches++;
         }
+        if (!dev_out) {
+            cudaEvent_t ev = ctx->pipe_events[gidx];
+            CK2(cudaEventRecord(ev, ctx->stream));
+            CK2(cudaStreamWaitEvent(ctx->stream2, ev, 0));
+            for (int k = g.b; k < g.e; k++) {
+                const size_t cnt = (size_t)cjs[k].G * cjs[k].G * 8;
+                CK2(cudaMemcpyAsync(P_out + offs_sorted[k], dout + offs_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+                if (likes) CK2(cudaMemcpyAsync(likes_out + offs_sorted[k], dlout + offs_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+            }
+        }
+        gidx++;
     }
     pt.end();
     CK2(cudaGetLastError());
     CK2(cudaMemcpyAsync(res_sorted.data(), dres, (size_t)n * sizeof(gdk_result2d), cudaMemcpyDeviceToHost, ctx->stream));
-    if (!dev_out) {
-        // the chunk's densities are contiguous in P_out when offsets are packed back to back; copy per density
-        // otherwise
-        bool packed = true;
-        for (int i = 0; i + 1 < n; i++)
-            if (offsets[i + 1] != offsets[i] + (int64_t)specs[i].fine_bins * specs[i].fine_bins) packed = false;
-        if (packed) {
-            size_t cnt = (size_t)(offsets[n - 1] - offsets[0]) + (size_t)specs[n - 1].fine_bins * specs[n - 1].fine_bins;
-            CK2(cudaMemcpyAsync(P_out + offsets[0], ctx->f2.p, cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        } else {
-            for (int i = 0; i < n; i++)
-                CK2(cudaMemcpyAsync(P_out + offsets[i], ctx->f2.p + (offsets[i] - offsets[0]),
-                                    (size_t)specs[i].fine_bins * specs[i].fine_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-    }
-    if (!dev_out && likes)
-        for (int i = 0; i < n; i++)
-            CK2(cudaMemcpyAsync(likes_out + offsets[i], ctx->f2l.p + (offsets[i] - offsets[0]),
-                                (size_t)specs[i].fine_bins * specs[i].fine_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_out) CK2(cudaStreamSynchronize(ctx->stream2));
     CK2(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < n; k++) {
         res[order[k]].status = res_sorted[k].status;
@@ -882,6 +1094,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
 static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
                           gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr) {
     if (!ctx) return GDK_ERR_ARG;
+    WallTimer wt{ctx, 1};
     if (likes_out && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "meanlikes needs gdk_set_loglikes");
     if (n <= 0 || !specs || !P_out || !offsets || (!hist_only && !res)) return gdk_fail(ctx, GDK_ERR_ARG, "2D batch: bad arguments");
     if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");

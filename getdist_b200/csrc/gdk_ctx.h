@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <stdint.h>
 
+#include <chrono>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -64,6 +66,16 @@ struct gdk_ctx {
     int phase_valid[GDK_NPHASE];
     std::string err;
     int64_t launches = 0;
+    bool ktiming = false;
+    struct KEv {
+        cudaEvent_t a, b;
+        int slot;
+    };
+    std::vector<KEv> kev;
+    int kev_used = 0;
+    double kbytes[8] = {0}, kflops[8] = {0};
+    int klaunches[8] = {0};
+    double wall_ms[4] = {0, 0, 0, 0};  // host wall clock of the last 1D / 2D batch call, quantile call (gdk_phase_ms 10..12)
     // sample store
     int64_t N = 0, ld = 0;
     int P = 0, nchains = 1;
@@ -103,23 +115,56 @@ struct gdk_ctx {
     DevBuf<unsigned char> bytes2d, bytes2d_b, bytes2d_c, bytes2d_d, bytes2d_e, bytes2d_res, bytes2d_mx, bytes_arena, qbase;
     Kde2dConsts k2d;
     DevBuf<unsigned char> ix8;
-    bool cluster_ok = false, use_bands = false, use_hot = true, use_sorted = true;
+    bool cluster_ok = false, use_bands = false, use_hot = true, use_sorted = true, shear_sorted = false;
     int64_t sorted_min_n = 1 << 15;
     DevBuf<unsigned char> recs;         // bucket-sorted sweep: 32-byte records [job][position]
     DevBuf<unsigned long long> recw;    // ... and their fixed-point weights
     DevBuf<unsigned> bucket;            // bucket counts / starts / write cursors
-    DevBuf<unsigned char> bytes2d_s;
+    DevBuf<unsigned char> bytes2d_s, bytes2d_sh1, bytes2d_sh2;
+    DevBuf<unsigned> bucket2;           // sheared sweep: anchor bucket counts / starts / cursors
     // per-context (= per-device) record of opted-in dynamic shared-memory sizes
     bool q_attr_set = false;
     size_t h1_tma_smem = 0, h1_smem = 0, kde1d_smem = 0;
     DevBuf<cplx> cwork2d;
+    std::vector<cudaEvent_t> pipe_events;  // group-finished events of the 2D output pipeline
+};
+
+// per-kernel CUDA-event timing + algorithmic work counters for the bench's roofline figures (gdk_set_kernel_timing)
+enum {
+    GDK_K_BIN8C = 0,
+    GDK_K_BUCKET_RECORDS = 1,
+    GDK_K_HIST2D_RECORDS = 2,
+    GDK_K_SHEAR_MINMAX = 3,
+    GDK_K_SHEAR_HIST = 4,
+    GDK_K_CONV2D_0 = 5,
+    GDK_K_CONV2D_1 = 6,
+    GDK_K_NSLOT = 8
+};
+struct KernelTimer {  // records an event pair around one launch when timing is on
+    gdk_ctx* ctx;
+    int idx = -1;
+    KernelTimer(gdk_ctx* c, int slot, double bytes, double flops);
+    ~KernelTimer();
 };
 
 struct PhaseTimer {
     gdk_ctx* ctx = nullptr;
     int phase = 0;
     void begin(gdk_ctx* c, int ph);
+    void resume(gdk_ctx* c, int ph) {  // continue a phase begun earlier in the same call: end() moves its stop event
+        ctx = c;
+        phase = ph;
+    }
     void end();
+};
+
+struct WallTimer {
+    gdk_ctx* ctx;
+    int slot;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~WallTimer() {
+        if (ctx) ctx->wall_ms[slot] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
 };
 
 int gdk_fail(gdk_ctx* c, int code, const char* fmt, ...);

@@ -1549,3 +1549,253 @@ __global__ void __launch_bounds__(SRT_THREADS, 2)
         }
     }
 }
+
+// ----------------------------------------------------------------------------------------------------
+// bucket-sorted sweep for the sheared re-binning (kde.bin_samples of (p1, r0*x_i + r1*x_j), 256 x 256 grids)
+// ----------------------------------------------------------------------------------------------------
+// profiles/r1s: k_shear_minmax streams 52 GB (every job re-reads both of its columns; DRAM bound, 9.5 ms) and
+// k_shear_hist another 63 GB with hot-window atomics (21.5 ms).  Here anchors (= p1 columns) whose partner sets
+// overlap are batched: a CTA stages a tile of rows x (<= SHR_MAXCOLS distinct columns) float64 values in shared
+// memory ONCE per pass and evaluates every sheared pair of the batch from it (11 GB per pass at C2).
+//   pass 1 (k_shear_minmax_tiled): min / max of p2 per job + the bucket counts of b1 per anchor;
+//   pass 2 (k_shear_records): b1 -> bucket, the partners' b2 bins -> one 32-byte record per (row, anchor), written
+//          in bucket order exactly like k_bucket_records; k_hist2d_records then sweeps the records.
+// p2 is evaluated with the same explicit multiply / multiply / add as everywhere else (no FMA contraction).
+#define SHR_ROWS 512
+#define SHR_MAXCOLS 18
+#define SHR_MAXJOBS 16
+struct ShearPairRef {  // one sheared job inside a batch
+    int acol, pcol, job, anchor;  // tile columns of x_i and x_j, global job index, anchor index inside the batch
+    double r0, r1;
+};
+struct ShearRecJob {  // one anchor (p1 column + geometry) with <= 32 partners
+    int acol, np, pair0, pad;  // tile column of p1, partners, first ShearPairRef of this anchor (consecutive)
+    double p1_min, dx1, inv1s;  // inv1s = 2^20 / dx1
+};
+struct ShearBatch {
+    int ncols, njobs, npairs, job0;  // job0: index of the batch's first anchor (row of counts / start / cursor)
+    int pair0, pad[3];                // first ShearPairRef of the batch
+    int cols[SHR_MAXCOLS];            // parameter (column of dX) per tile column
+};
+
+// grid (nseg, nbatches), 512 threads.  dynamic smem: ncols * SHR_ROWS * 8 (tile) + npairs * 32 (pair table) +
+// njobs * 1024 (b1 bucket counts, only when counts != NULL).
+// part[(job * nseg + seg) * 2 + {0, 1}] = min, max of p2 over the segment.  Pair i of the batch belongs to warp
+// i % 16, which keeps its running min / max in registers across all tiles of the segment (<= SHR_MAXPW pairs per
+// warp) and reduces across lanes once at the end.
+#define SHR_MAXPW 8  // pairs per warp: batches hold <= 16 * SHR_MAXPW pairs
+__global__ void __launch_bounds__(512) k_shear_minmax_tiled(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
+                                                            int nseg, const ShearBatch* __restrict__ batches,
+                                                            const ShearRecJob* __restrict__ jobs, const ShearPairRef* __restrict__ pairs,
+                                                            double* __restrict__ part, unsigned* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    __shared__ ShearBatch B;
+    {
+        const int* src = reinterpret_cast<const int*>(batches + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&B);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShearBatch) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    double* tile = reinterpret_cast<double*>(msm);                                      // [ncols][SHR_ROWS]
+    ShearPairRef* sp = reinterpret_cast<ShearPairRef*>(tile + (size_t)B.ncols * SHR_ROWS);  // [npairs]
+    unsigned* cnt = reinterpret_cast<unsigned*>(sp + B.npairs);                         // [njobs][256]
+    const ShearRecJob* bj = jobs + B.job0;
+    for (int i = threadIdx.x; i < B.npairs; i += blockDim.x) sp[i] = pairs[B.pair0 + i];
+    if (counts)
+        for (int i = threadIdx.x; i < B.njobs * 256; i += blockDim.x) cnt[i] = 0;
+    const Seg sg = segs[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double mn[SHR_MAXPW], mx[SHR_MAXPW];
+#pragma unroll
+    for (int k = 0; k < SHR_MAXPW; k++) {
+        mn[k] = INFINITY;
+        mx[k] = -INFINITY;
+    }
+    for (int64_t t0 = sg.r0; t0 < sg.r1; t0 += SHR_ROWS) {
+        const int nrow = (int)min((int64_t)SHR_ROWS, sg.r1 - t0);
+        __syncthreads();  // previous tile fully consumed (and the tables above are visible)
+        for (int c = 0; c < B.ncols; c++) {
+            const double* col = dX + (int64_t)B.cols[c] * ld + t0;
+            for (int t = threadIdx.x; t < nrow; t += blockDim.x) tile[c * SHR_ROWS + t] = ldg_stream(col + t);
+        }
+        __syncthreads();
+        if (counts)  // bucket counts of b1 per anchor (one row per thread)
+            for (int t = threadIdx.x; t < nrow; t += blockDim.x)
+                for (int j = 0; j < B.njobs; j++) {
+                    const int b1 = bin_index_trunc_fx(tile[bj[j].acol * SHR_ROWS + t], bj[j].p1_min, bj[j].dx1, bj[j].inv1s);
+                    atomicAdd(&cnt[j * 256 + min(max(b1, 0), 255)], 1u);
+                }
+#pragma unroll
+        for (int k = 0; k < SHR_MAXPW; k++) {
+            const int i = warp + k * 16;
+            if (i < B.npairs) {
+                const ShearPairRef pr = sp[i];
+                const double* xi = tile + pr.acol * SHR_ROWS + lane;
+                const double* xj = tile + pr.pcol * SHR_ROWS + lane;
+                if (nrow == SHR_ROWS) {
+#pragma unroll
+                    for (int m = 0; m < SHR_ROWS / 32; m++) {
+                        const double p2 = shear_p2(xi[32 * m], xj[32 * m], pr.r0, pr.r1);
+                        mn[k] = p2 < mn[k] ? p2 : mn[k];  // finite samples: plain compares, not the NaN-aware fmin / fmax
+                        mx[k] = p2 > mx[k] ? p2 : mx[k];
+                    }
+                } else {
+                    for (int t = lane; t < nrow; t += 32) {
+                        const double p2 = shear_p2(xi[t - lane], xj[t - lane], pr.r0, pr.r1);
+                        mn[k] = p2 < mn[k] ? p2 : mn[k];
+                        mx[k] = p2 > mx[k] ? p2 : mx[k];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SHR_MAXPW; k++) {
+        const int i = warp + k * 16;
+        if (i < B.npairs) {
+            const double a = warp_min(mn[k]), b = warp_max(mx[k]);
+            if (lane == 0) {
+                part[((int64_t)sp[i].job * nseg + blockIdx.x) * 2 + 0] = a;
+                part[((int64_t)sp[i].job * nseg + blockIdx.x) * 2 + 1] = b;
+            }
+        }
+    }
+    if (counts) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < B.njobs * 256; i += blockDim.x)
+            if (cnt[i]) atomicAdd(counts + (size_t)B.job0 * 256 + i, cnt[i]);
+    }
+}
+
+// grid ceil(N / SHR_ROWS), 512 threads, one launch per batch.  Structure of k_bucket_records (count, reserve, local
+// sort, coalesced copy-out) with the record bytes computed from the float64 tile.  Rows whose b1 falls outside the
+// grid keep weight 0 (kde.bin_samples ranges cover the samples, so this only guards bad hard limits).
+// dynamic smem: SHR_ROWS * 44 + 2048 + njobs * (2048 + SHR_ROWS) + 32 * 48 + ncols * SHR_ROWS * 8
+struct ShearLaneParam {
+    double r0, r1, rmin, dx, invs;  // invs = 2^20 / dx of the job's p2 range
+    int pcol, pad;
+};
+__global__ void __launch_bounds__(512) k_shear_records(const double* __restrict__ dX, int64_t ld, int64_t N,
+                                                       const unsigned long long* __restrict__ wq, const ShearBatch* __restrict__ batches,
+                                                       int batch, const ShearRecJob* __restrict__ jobs,
+                                                       const ShearPairRef* __restrict__ pairs, const ShearGeom* __restrict__ geom,
+                                                       unsigned* __restrict__ cursor, uint4* __restrict__ recs,
+                                                       unsigned long long* __restrict__ ws, int64_t pld) {
+    extern __shared__ __align__(16) unsigned char rsm2[];
+    __shared__ ShearBatch B;
+    {
+        const int* src = reinterpret_cast<const int*>(batches + batch);
+        int* dst = reinterpret_cast<int*>(&B);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShearBatch) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int njobs = B.njobs;
+    uint4* stage_rec = reinterpret_cast<uint4*>(rsm2);                                                  // [SHR_ROWS][2]
+    unsigned long long* stage_w = reinterpret_cast<unsigned long long*>(rsm2 + (size_t)SHR_ROWS * 32);  // [SHR_ROWS]
+    unsigned* stage_pos = reinterpret_cast<unsigned*>(rsm2 + (size_t)SHR_ROWS * 40);                    // [SHR_ROWS]
+    unsigned* lcur = reinterpret_cast<unsigned*>(rsm2 + (size_t)SHR_ROWS * 44);                         // [2][256]
+    unsigned* gdel = lcur + 512;                                                                          // [njobs][256]
+    unsigned* lstart = gdel + (size_t)njobs * 256;                                                        // [njobs][256]
+    ShearLaneParam* lp = reinterpret_cast<ShearLaneParam*>(lstart + (size_t)njobs * 256);                 // [32]
+    double* tile = reinterpret_cast<double*>(lp + 32);                                                    // [ncols][SHR_ROWS]
+    unsigned char* b1s = reinterpret_cast<unsigned char*>(tile + (size_t)B.ncols * SHR_ROWS);             // [njobs][SHR_ROWS]
+    const ShearRecJob* bj = jobs + B.job0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * SHR_ROWS;
+    const int nrow = (int)min((int64_t)SHR_ROWS, N - r0);
+    for (int i = threadIdx.x; i < njobs * 256; i += blockDim.x) gdel[i] = 0;
+    for (int c = 0; c < B.ncols; c++) {
+        const double* col = dX + (int64_t)B.cols[c] * ld + r0;
+        for (int t = threadIdx.x; t < nrow; t += blockDim.x) tile[c * SHR_ROWS + t] = ldg_stream(col + t);
+    }
+    __syncthreads();
+    const int t = threadIdx.x;  // SHR_ROWS == blockDim.x: one row per thread
+    const bool has_row = t < nrow;
+    unsigned skipmask = 0;
+    // phase A: b1 of every anchor, rows per (anchor, bucket)
+    if (has_row)
+        for (int j = 0; j < njobs; j++) {
+            const int b1 = bin_index_trunc_fx(tile[bj[j].acol * SHR_ROWS + t], bj[j].p1_min, bj[j].dx1, bj[j].inv1s);
+            if (b1 < 0 || b1 > 255) skipmask |= 1u << j;
+            const int c = min(max(b1, 0), 255);
+            b1s[j * SHR_ROWS + t] = (unsigned char)c;
+            atomicAdd(&gdel[j * 256 + c], 1u);
+        }
+    __syncthreads();
+    // phase B: one warp per anchor: local starts + one global atomic per non-empty bucket (see k_bucket_records)
+    for (int j = warp; j < njobs; j += nwarps) {
+        unsigned v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = gdel[j * 256 + lane * 8 + k];
+            sum += v[k];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        unsigned pre = incl - sum;
+        unsigned base[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) base[k] = v[k] ? atomicAdd(cursor + (size_t)j * 256 + lane * 8 + k, v[k]) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            lstart[j * 256 + lane * 8 + k] = pre;
+            gdel[j * 256 + lane * 8 + k] = base[k] - pre;
+            pre += v[k];
+        }
+    }
+    __syncthreads();
+    const unsigned long long wrow_q = has_row ? wq[r0 + t] : 0ull;
+    if (threadIdx.x < 256 && njobs > 0) lcur[threadIdx.x] = lstart[threadIdx.x];
+    for (int j = 0; j < njobs; j++) {
+        unsigned* cur = lcur + (j & 1) * 256;
+        const ShearRecJob jb = bj[j];
+        if (threadIdx.x < 32) {  // the partners' parameters of this anchor (read back after the barrier below)
+            ShearLaneParam q{};
+            if ((int)threadIdx.x < jb.np) {
+                const ShearPairRef pr = pairs[B.pair0 + jb.pair0 + threadIdx.x];
+                const ShearGeom g = geom[pr.job];
+                q.r0 = pr.r0;
+                q.r1 = pr.r1;
+                q.rmin = g.rmin;
+                q.dx = g.dx;
+                q.invs = g.inv * 1048576.0;
+                q.pcol = pr.pcol;
+            }
+            lp[threadIdx.x] = q;
+        }
+        __syncthreads();  // cursors + lane parameters of job j ready; copy-out of job j-1 done with the staging buffers
+        if (has_row) {
+            const unsigned c = b1s[j * SHR_ROWS + t];
+            const unsigned li = atomicAdd(&cur[c], 1u);
+            const double xi = tile[jb.acol * SHR_ROWS + t];
+            unsigned v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                v[k] = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int l = 4 * k + b;
+                    if (l < jb.np) {
+                        const ShearLaneParam q = lp[l];
+                        const double p2 = shear_p2(xi, tile[q.pcol * SHR_ROWS + t], q.r0, q.r1);
+                        const int b2 = bin_index_trunc_fx(p2, q.rmin, q.dx, q.invs);
+                        v[k] |= (unsigned)min(max(b2, 0), 255) << (8 * b);
+                    }
+                }
+            }
+            stage_rec[2 * li] = make_uint4(v[0], v[1], v[2], v[3]);
+            stage_rec[2 * li + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+            stage_w[li] = ((skipmask >> j) & 1u) ? 0ull : wrow_q;
+            stage_pos[li] = li + gdel[j * 256 + c];
+        }
+        __syncthreads();
+        uint4* dstj = recs + (size_t)j * pld * 2;
+        for (int i = threadIdx.x; i < 2 * nrow; i += blockDim.x) dstj[(size_t)stage_pos[i >> 1] * 2 + (i & 1)] = stage_rec[i];
+        for (int i = threadIdx.x; i < nrow; i += blockDim.x) ws[(size_t)j * pld + stage_pos[i]] = stage_w[i];
+        if (threadIdx.x < 256 && j + 1 < njobs) lcur[((j + 1) & 1) * 256 + threadIdx.x] = lstart[(j + 1) * 256 + threadIdx.x];
+    }
+}

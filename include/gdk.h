@@ -82,6 +82,13 @@ double gdk_timer_stop_ms(gdk_ctx* ctx);
  * 0 = 1D histogram sweep, 1 = 1D grid stage, 2 = 2D histogram pass, 3 = 2D shear re-bin,
  * 4 = 2D transforms, 5 = 2D bandwidth, 6 = 2D convolution stage, 7 = moments, 8 = quantiles, 9 = upload */
 double gdk_phase_ms(gdk_ctx* ctx, int32_t phase);
+/* Per-kernel CUDA-event timing for the bench's roofline figures.  gdk_set_kernel_timing(ctx, 1) resets the counters
+ * and makes the batch calls bracket the launches of the tagged kernels with event pairs (on the library stream);
+ * gdk_kernel_stat(ctx, slot, what): what 0 = summed event time (ms), 1 = launches, 2 = algorithmic bytes,
+ * 3 = algorithmic flops, accumulated since the reset.  Slots: 0 k_bin8c, 1 k_bucket_records, 2 k_hist2d_records,
+ * 3 k_shear_minmax_tiled, 4 k_shear_hist, 5 k_conv2d<0>, 6 k_conv2d<1>.                                          */
+int32_t gdk_set_kernel_timing(gdk_ctx* ctx, int32_t on);
+double gdk_kernel_stat(gdk_ctx* ctx, int32_t slot, int32_t what);
 
 /* ---------------------------------------------------------------------------------------------
  * data residency -- replaces WeightedSamples.setSamples / Chains.makeSingle state

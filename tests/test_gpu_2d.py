@@ -161,7 +161,7 @@ def test_repeatable(gpu_objs):
 
 
 HIST2D_MODES = {"sorted": {}, "hot": {"GDK_SORTED": "0"}, "bands": {"GDK_BANDS": "1"},
-                "tiles": {"GDK_HOT": "0", "GDK_SORTED": "0"}}
+                "tiles": {"GDK_HOT": "0", "GDK_SORTED": "0"}, "shear_records": {"GDK_SHEAR_SORTED": "1"}}
 
 
 @pytest.mark.parametrize("mode", list(HIST2D_MODES))
