@@ -206,7 +206,7 @@ def run_ours(args):
     from getdist_b200.parallel import partition_triangle
 
     idx, pairs = mc.triangle_pairs()
-    my1d, my2d, max1d, per = partition_triangle(idx, pairs, rank, world)
+    my1d, my2d, max1d, per, hints = partition_triangle(idx, pairs, rank, world, with_hints=True)
     F, G = SETTINGS["fine_bins"], SETTINGS["fine_bins_2D"]
     d1 = torch.zeros((max1d, F), dtype=torch.float64, device="cuda")
     d2 = torch.zeros((per, G * G), dtype=torch.float64, device="cuda")
@@ -228,7 +228,7 @@ def run_ours(args):
             phases["hist1d"], phases["kde1d"], phases["quantiles"] = ph["hist1d"], ph["kde1d"], ph["quantiles"]
         if my2d:
             # every 2D grid of the C2 workload is G x G; a scaled-up grid would not fit the packed tensor
-            specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr(), _contours=[])
+            specs, offs, res = mc._densities_2d(my2d, _device_ptr=d2.data_ptr(), _contours=[], _anchor_hints=hints)
             assert np.all(specs["fine_bins"] == G)
             ph = mc._ctx.phase_ms()
             for k in ("hist2d", "shear", "xform2d", "bw2d", "conv2d"):
@@ -305,7 +305,7 @@ def run_ours(args):
         e2e_parts["moments_ms_events"] = m._ctx.phase_ms()["moments"]
         a = m._densities_1d(my1d, _out=out1) if my1d else []
         t2 = time.perf_counter()
-        b = m._densities_2d(my2d, _out=out2, _contours=[]) if my2d else []
+        b = m._densities_2d(my2d, _out=out2, _contours=[], _anchor_hints=hints) if my2d else []
         t3 = time.perf_counter()
         s = float(out1[0, F // 2]) + float(out2[G * G // 2])
         e2e_parts.update(upload_and_moments_s=t1 - t0, d1_s=t2 - t1, d2_s=t3 - t2)

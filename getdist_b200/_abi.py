@@ -53,7 +53,7 @@ class Spec2D(C.Structure):
                 ("shear_i", C.c_int32), ("shear_j", C.c_int32), ("shear_swapped", C.c_int32),
                 ("r0", C.c_double), ("r1", C.c_double), ("S00", C.c_double), ("S10", C.c_double), ("S11", C.c_double),
                 ("p1_min", C.c_double), ("p1_max", C.c_double),
-                ("n_contours", C.c_int32), ("pad2", C.c_int32), ("contours", C.c_double * 4),
+                ("n_contours", C.c_int32), ("anchor_hint", C.c_int32), ("contours", C.c_double * 4),
                 ("x_periodic", C.c_int32), ("y_periodic", C.c_int32)]
 
 

@@ -217,9 +217,15 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 slot[p] = (int)bj.size();
                 bj.push_back(Bin8Job{p, 0, lo, fw, 1.0 / fw});
             };
-            for (int i : b8pairs) {
-                add(specs[i].px, specs[i].xbinmin, specs[i].xbinmax);
-                add(specs[i].py, specs[i].ybinmin, specs[i].ybinmax);
+            {
+                // slots in ascending parameter order: the circular partner windows of the bucket-sorted sweep are then
+                // contiguous byte ranges of the row-major tile whatever order the pairs arrive in
+                std::map<int, std::pair<double, double>> first;
+                for (int i : b8pairs) {
+                    first.emplace(specs[i].px, std::make_pair(specs[i].xbinmin, specs[i].xbinmax));
+                    first.emplace(specs[i].py, std::make_pair(specs[i].ybinmin, specs[i].ybinmax));
+                }
+                for (const auto& kv : first) add(kv.first, kv.second.first, kv.second.second);
             }
             // a parameter must have ONE geometry across the batch; otherwise route the odd pairs through the tiles
             bool consistent = true;
@@ -258,7 +264,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 for (int i : hot_pairs) {
                     const int sx = slot[specs[i].px], sy = slot[specs[i].py];
                     const int d = ((sy - sx) % np8 + np8) % np8;
-                    const bool anchor_x = (2 * d < np8) || (2 * d == np8 && sx < sy) || sx == sy;
+                    bool anchor_x = (2 * d < np8) || (2 * d == np8 && sx < sy) || sx == sy;
+                    if (specs[i].anchor_hint == 1) anchor_x = true;
+                    if (specs[i].anchor_hint == 2) anchor_x = false;
                     if (anchor_x)
                         plist[sx].push_back(Partner{sy, 256, 1, goff[i]});  // rows of bucket c fill column c: [iy][c]
                     else

@@ -969,7 +969,7 @@ class MCSamples:
                 sp["ry_fixed"] = smooth * fine / nbin2D
         return sp
 
-    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, **kwargs):
+    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, _anchor_hints=None, **kwargs):
         if _likes:
             self._ensure_loglikes()
         self._ensure_param_ranges([p for pr in pairs for p in pr])
@@ -980,6 +980,8 @@ class MCSamples:
             _contours = list(self.contours[:4])  # batched prefetch: the analysis-settings contours
         conts = [float(c) for c in _contours[:4]] if len(_contours) <= 4 else []
         specs["n_contours"] = len(conts)
+        if _anchor_hints is not None:
+            specs["anchor_hint"] = np.asarray(_anchor_hints, dtype=np.int32)
         for k, c in enumerate(conts):
             specs["contours"][:, k] = c
         lbuf = None

@@ -3,27 +3,54 @@ computes a slice of the list and ONE all-gather of the result grids follows (SUR
 used for the collective only (NCCL on device tensors in production, gloo on CPU tensors in the tests)."""
 
 
-def partition_triangle(idx, pairs, rank, world):
-    """1D densities round-robin; 2D pairs in contiguous equal blocks (keeps the 8x8 histogram tiles dense).
+def _anchor_position(pos_i, pos_k, P):
+    """Position (in the parameter list) of the pair's anchor under the circular rule of the bucket-sorted 2D
+    histogram sweep: parameter i owns the pairs with the next P/2 parameters (mod P)."""
+    d = (pos_k - pos_i) % P
+    return pos_i if (2 * d < P or (2 * d == P and pos_i < pos_k)) else pos_k
+
+
+def split_pairs(idx, pairs, world):
+    """Pairs grouped by rank so that every anchor's pairs stay on one rank (each rank then sweeps P/world full
+    32-lane jobs instead of P partly filled ones).  Returns (lists, hints): hints[r][k] = 1 if the anchor of
+    lists[r][k] is its x parameter, 2 if it is its y parameter (gdk_spec2d.anchor_hint)."""
+    P = len(idx)
+    pos = {p: n for n, p in enumerate(idx)}
+    blk = (P + world - 1) // world
+    lists = [[] for _ in range(world)]
+    hints = [[] for _ in range(world)]
+    for (a, b) in pairs:
+        ap = _anchor_position(pos[a], pos[b], P)
+        r = min(ap // blk, world - 1)
+        lists[r].append((a, b))
+        hints[r].append(1 if ap == pos[a] else 2)
+    return lists, hints
+
+
+def partition_triangle(idx, pairs, rank, world, with_hints=False):
+    """1D densities round-robin; 2D pairs by anchor blocks (split_pairs).
     Returns (my1d, my2d, max1d, per2d): per2d / max1d are the padded per-rank counts used for the all-gather."""
     my1d = idx[rank::world]
-    per = (len(pairs) + world - 1) // world
-    my2d = pairs[rank * per: (rank + 1) * per]
+    lists, hints = split_pairs(idx, pairs, world)
+    per = max(len(l) for l in lists)
     max1d = (len(idx) + world - 1) // world
-    return my1d, my2d, max1d, per
+    if with_hints:
+        return my1d, lists[rank], max1d, per, (hints[rank] if world > 1 else None)
+    return my1d, lists[rank], max1d, per
 
 
 def gather_order(idx, pairs, world):
     """Row index in the gathered (world*padded) tensors for every density, in the caller's order."""
     max1d = (len(idx) + world - 1) // world
-    per = (len(pairs) + world - 1) // world
+    lists, _ = split_pairs(idx, pairs, world)
+    per = max(len(l) for l in lists)
     rows1d = {}
     for r in range(world):
         for k, j in enumerate(idx[r::world]):
             rows1d[j] = r * max1d + k
     rows2d = {}
     for r in range(world):
-        for k, pr in enumerate(pairs[r * per: (r + 1) * per]):
+        for k, pr in enumerate(lists[r]):
             rows2d[pr] = r * per + k
     return [rows1d[j] for j in idx], [rows2d[p] for p in pairs]
 

@@ -204,7 +204,9 @@ typedef struct gdk_spec2d {
     double p1_min, p1_max;             /* range of p1 (imin/imax or sample min/max +- 10%)        */
     /* contour levels of the normalised grid (getContourLevels, densities.py:19-56; requested by
      * get2DDensityGridData(get_density=False), mcsamples.py:1994-2002): probability fractions, 0..4 of them */
-    int32_t n_contours, pad2;
+    int32_t n_contours;
+    int32_t anchor_hint;               /* bucket-sorted sweep: 0 = library chooses which parameter's bins order the rows of this
+                                          pair, 1 = px, 2 = py (multi-GPU partitions keep whole anchors on one rank)        */
     double contours[4];
     int32_t x_periodic, y_periodic;    /* periodic axes: convolve2D_periodic (convolve.py:215-323), masks only on the
                                           non-periodic axes (mcsamples.py:1688-1712, 1874-1976)      */

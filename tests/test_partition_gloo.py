@@ -71,3 +71,29 @@ def test_partition_covers_everything_once():
                 seen1 += a
                 seen2 += b
             assert sorted(seen1) == idx and sorted(seen2) == sorted(pairs)
+
+
+@pytest.mark.parametrize("P,world", [(64, 2), (64, 8), (9, 2), (33, 4)])
+def test_split_pairs_keeps_anchors_together(P, world):
+    """every pair appears once; all pairs of one anchor parameter land on one rank with a consistent hint; the
+    per-rank counts differ by at most one anchor's worth of pairs"""
+    from getdist_b200.parallel import _anchor_position, split_pairs
+
+    idx = list(range(100, 100 + P))
+    pairs = [(idx[i], idx[k]) for i in range(P) for k in range(i + 1, P)]
+    lists, hints = split_pairs(idx, pairs, world)
+    assert sorted(p for l in lists for p in l) == sorted(pairs)
+    owner = {}
+    for r in range(world):
+        for (a, b), h in zip(lists[r], hints[r]):
+            anchor = a if h == 1 else b
+            assert _anchor_position(a - 100, b - 100, P) == anchor - 100
+            assert owner.setdefault(anchor, r) == r
+    counts = [len(l) for l in lists]
+    blk = (P + world - 1) // world
+    assert max(counts) - min(c for c in counts if c) <= blk * (P // 2 + 1)
+    per_anchor = {}
+    for r in range(world):
+        for (a, b), h in zip(lists[r], hints[r]):
+            per_anchor[a if h == 1 else b] = per_anchor.get(a if h == 1 else b, 0) + 1
+    assert max(per_anchor.values()) <= P // 2 and min(per_anchor.values()) >= (P - 1) // 2
