@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgdk.so")
 
 GDK_OUT_DEVICE = 1
+GDK_BW_ONLY = 2
 
 ST_BW_FALLBACK = 1
 ST_BW_FAILED_NONE = 2
@@ -125,6 +126,8 @@ def load():
     lib.gdk_density1d_likes_batch.restype = i32
     lib.gdk_density2d_likes_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, u32]
     lib.gdk_density2d_likes_batch.restype = i32
+    lib.gdk_density2d_masked_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32]
+    lib.gdk_density2d_masked_batch.restype = i32
     lib.gdk_lag_sums.argtypes = [vp, i32, vp, vp]
     lib.gdk_lag_sums.restype = i32
     lib.gdk_hist1d_batch.argtypes = [vp, i32, vp, vp, i64]
@@ -272,6 +275,37 @@ class Context:
         self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets),
                                               C.cast(res, C.c_void_p), 0), "gdk_density2d_batch")
         return out, offsets, list(res)
+
+    def bandwidth2d_batch(self, specs):
+        """bandwidth stage only (GDK_BW_ONLY): results with rx, ry, c, winw, status; no grids"""
+        n = len(specs)
+        assert isinstance(specs, np.ndarray) and specs.dtype.itemsize == C.sizeof(Spec2D) and specs.flags.c_contiguous
+        offsets = np.zeros(n, dtype=np.int64)
+        res = (Result2D * n)()
+        self._ck(self.lib.gdk_density2d_batch(self.h, n, C.c_void_p(specs.ctypes.data), None, _ptr(offsets),
+                                              C.cast(res, C.c_void_p), GDK_BW_ONLY), "gdk_density2d_batch(GDK_BW_ONLY)")
+        return list(res)
+
+    def density2d_masked_batch(self, specs, masks, mask_w, likes=False):
+        """specs: structured array (bandwidths fixed); masks: list of (G+2w, G+2w) float64 arrays"""
+        n = len(specs)
+        assert isinstance(specs, np.ndarray) and specs.dtype.itemsize == C.sizeof(Spec2D) and specs.flags.c_contiguous
+        fb = specs["fine_bins"].astype(np.int64)
+        sizes = fb * fb
+        offsets = np.zeros(n, dtype=np.int64)
+        offsets[1:] = np.cumsum(sizes)[:-1]
+        msizes = np.array([m.size for m in masks], dtype=np.int64)
+        moff = np.zeros(n, dtype=np.int64)
+        moff[1:] = np.cumsum(msizes)[:-1]
+        mbuf = np.concatenate([np.ascontiguousarray(m, dtype=np.float64).ravel() for m in masks])
+        mw = np.ascontiguousarray(mask_w, dtype=np.int32)
+        out = np.empty(int(sizes.sum()))
+        lout = np.empty(int(sizes.sum())) if likes else None
+        res = (Result2D * n)()
+        self._ck(self.lib.gdk_density2d_masked_batch(self.h, n, C.c_void_p(specs.ctypes.data), _ptr(mbuf), _ptr(moff), _ptr(mw),
+                                                     _ptr(out), _ptr(lout), _ptr(offsets), C.cast(res, C.c_void_p), 0),
+                 "gdk_density2d_masked_batch")
+        return out, lout, offsets, list(res)
 
     def hist2d_batch(self, specs):
         n = len(specs)

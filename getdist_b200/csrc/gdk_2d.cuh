@@ -47,7 +47,8 @@ static int upload_vec(gdk_ctx* ctx, const std::vector<T>& v, DevBuf<unsigned cha
 }
 
 static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
-                           gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr) {
+                           gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr,
+                           const double* masks = nullptr, const int64_t* mask_offsets = nullptr, const int32_t* mask_w = nullptr) {
     const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
     const bool likes = likes_out != nullptr && !hist_only;
     // ---------------- layout of the pair grids ----------------
@@ -854,6 +855,29 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     }
     CK2(cudaMemcpyAsync(res, dres, (size_t)n * sizeof(gdk_result2d), cudaMemcpyDeviceToHost, ctx->stream));
     CK2(cudaStreamSynchronize(ctx->stream));
+    if (flags & GDK_BW_ONLY) return 0;
+    // user prior masks (mask_function): checked against the kernel half-width, then made resident
+    std::vector<long long> umoff(n, -1);
+    if (masks && mask_offsets) {
+        size_t utot = 0;
+        for (int i = 0; i < n; i++) {
+            if (mask_offsets[i] < 0) continue;
+            if (!mask_w || mask_w[i] != res[i].winw)
+                return gdk_fail(ctx, GDK_ERR_ARG, "pair %d: the mask was built for half-width %d but the kernel half-width is %d", i,
+                                mask_w ? mask_w[i] : -1, res[i].winw);
+            if (specs[i].x_periodic || specs[i].y_periodic)
+                return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "pair %d: mask_function with periodic parameters", i);
+            umoff[i] = (long long)utot;
+            const size_t gp = (size_t)specs[i].fine_bins + 2 * (size_t)res[i].winw;
+            utot += gp * gp;
+        }
+        if (ctx->umask.ensure(std::max<size_t>(utot, 1))) return gdk_fail(ctx, GDK_ERR_NOMEM, "prior masks");
+        for (int i = 0; i < n; i++) {
+            if (umoff[i] < 0) continue;
+            const size_t gp = (size_t)specs[i].fine_bins + 2 * (size_t)res[i].winw;
+            CK2(cudaMemcpyAsync(ctx->umask.p + umoff[i], masks + mask_offsets[i], gp * gp * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
 
     // ---------------- convolution stage ----------------
     ar.used = mark;  // transform scratch is dead
@@ -868,9 +892,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         const int G = s.fine_bins, w = res[i].winw, K = 2 * w + 1;
         if (w > 384) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "pair %d: kernel half-width %d exceeds the supported 384 bins", i, w);
         if (s.mult_bias_correction_order > 6) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "mult_bias_correction_order > 6");
-        const bool has_prior = s.x_has_bot || s.x_has_top || s.y_has_bot || s.y_has_top;
+        const bool has_prior = s.x_has_bot || s.x_has_top || s.y_has_bot || s.y_has_top || umoff[i] >= 0;  // mcsamples.py:1794
         ConvJob& c = cj[i];
         c = ConvJob{};
+        c.umask = umoff[i] >= 0 ? ctx->umask.p + umoff[i] : nullptr;
         c.hist = H + goff[i];
         c.G = G;
         c.w = w;
@@ -896,7 +921,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         c.Pn = c.mbc ? take_d((size_t)G * G) : c.P;
         c.a00b = c.mbc ? take_d((size_t)G * G) : nullptr;
         c.box = c.mbc ? take_d((size_t)G * G) : nullptr;
-        c.T = (c.mbc || c.bounded) ? take_d((size_t)K * G * 4) : nullptr;
+        c.T = ((c.mbc || c.bounded) && !c.umask) ? take_d((size_t)K * G * 4) : nullptr;
         if (c.bounded) {
             c.maps = take_d((size_t)G * G * 6);
             if (c.bco == 1) {
@@ -913,7 +938,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             c.lbox = c.lmbc ? take_d((size_t)G * G) : nullptr;
             if (!c.lP || !c.lP2 || (c.lmbc && !c.lbox)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (mean likelihoods, pair %d)", i);
         }
-        if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || !c.T || !c.box)) || (c.bounded && (!c.maps || !c.T || (c.bco == 1 && (!c.xP || !c.yP)))))
+        if (!c.Wk || !c.P || !c.Pn || (c.mbc && (!c.a00b || (!c.T && !c.umask) || !c.box)) ||
+            (c.bounded && (!c.maps || (!c.T && !c.umask) || (c.bco == 1 && (!c.xP || !c.yP)))))
             return gdk_fail(ctx, GDK_ERR_NOMEM, "2D arena exhausted (convolution stage, pair %d)", i);
         wmax_all = std::max(wmax_all, w);
         max_mbc = std::max(max_mbc, c.mbc);
@@ -1019,6 +1045,11 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         k_mask_T<<<gt, 256, 0, ctx->stream>>>(dcj + g.b);
         dim3 gm((unsigned)((g.Gmax + 255) / 256), (unsigned)nj);
         k_mask_maps<<<gm, 256, 0, ctx->stream>>>(dcj + g.b);
+        if (masks) {
+            dim3 gu((unsigned)((g.Gmax * g.Gmax + 255) / 256), (unsigned)nj);
+            k_umask_maps<<<gu, 256, 0, ctx->stream>>>(dcj + g.b);
+            ctx->launches++;
+        }
         const int tiles = ((g.Gmax + CV_TX - 1) / CV_TX) * ((g.Gmax + CV_TY - 1) / CV_TY);
         dim3 gc((unsigned)tiles, (unsigned)nj);
         const int kc0 = pick_kc(g.wmax, budget0), kc1 = pick_kc(g.wmax, budget1);
@@ -1065,6 +1096,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         }
         // normalised output of this group; its device->host copies run on the second stream behind an event
         dim3 gf(64, (unsigned)nj);
+        if (masks) {
+            k_umask_zero<<<gf, 256, 0, ctx->stream>>>(dcj + g.b);
+            ctx->launches++;
+        }
         k_finalize2d<<<gf, 256, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
         ctx->launches++;
         if (likes) {
@@ -1100,11 +1135,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
 }
 
 static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
-                          gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr) {
+                          gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr,
+                          const double* masks = nullptr, const int64_t* mask_offsets = nullptr, const int32_t* mask_w = nullptr) {
     if (!ctx) return GDK_ERR_ARG;
     WallTimer wt{ctx, 1};
     if (likes_out && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "meanlikes needs gdk_set_loglikes");
-    if (n <= 0 || !specs || !P_out || !offsets || (!hist_only && !res)) return gdk_fail(ctx, GDK_ERR_ARG, "2D batch: bad arguments");
+    if (n <= 0 || !specs || (!P_out && !(flags & GDK_BW_ONLY)) || !offsets || (!hist_only && !res))
+        return gdk_fail(ctx, GDK_ERR_ARG, "2D batch: bad arguments");
     if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
     CK2(cudaSetDevice(ctx->device));
     for (int i = 0; i < n; i++) {
@@ -1138,7 +1175,8 @@ static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, doub
             acc += add;
             e++;
         }
-        int rc = density2d_chunk(ctx, e - b, specs + b, P_out, offsets + b, hist_only ? nullptr : res + b, flags, hist_only, likes_out);
+        int rc = density2d_chunk(ctx, e - b, specs + b, P_out, offsets + b, hist_only ? nullptr : res + b, flags, hist_only, likes_out,
+                                 masks, mask_offsets ? mask_offsets + b : nullptr, mask_w ? mask_w + b : nullptr);
         if (rc) return rc;
         b = e;
     }
@@ -1153,6 +1191,13 @@ extern "C" int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d
 extern "C" int32_t gdk_density2d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, double* likes_out,
                                              const int64_t* offsets, gdk_result2d* res, uint32_t flags) {
     return density2d_impl(ctx, n, specs, P_out, offsets, res, flags, false, likes_out);
+}
+
+extern "C" int32_t gdk_density2d_masked_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, const double* masks,
+                                              const int64_t* mask_offsets, const int32_t* mask_w, double* P_out, double* likes_out,
+                                              const int64_t* offsets, gdk_result2d* res, uint32_t flags) {
+    if (ctx && (!masks || !mask_offsets || !mask_w)) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_density2d_masked_batch: masks, offsets and half-widths are required");
+    return density2d_impl(ctx, n, specs, P_out, offsets, res, flags, false, likes_out, masks, mask_offsets, mask_w);
 }
 
 extern "C" int32_t gdk_hist2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* bins_out, const int64_t* offsets) {

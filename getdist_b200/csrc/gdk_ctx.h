@@ -92,7 +92,7 @@ struct gdk_ctx {
     double mean_loglike = 0, wlscale = 1.0;
     DevBuf<double> dLL, dLW;
     DevBuf<unsigned long long> dWlq, gbins_l, gbins2l;
-    DevBuf<double> f2l;
+    DevBuf<double> f2l, umask;
     // cached moments
     bool have_moments = false;
     double norm = 0;

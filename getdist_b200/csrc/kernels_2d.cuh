@@ -439,6 +439,8 @@ struct ConvJob {
     double* lbox;         // lhist / lP where lP > 0
     double* lP2;          // conv(lbox) * lP where lP > 0 (bias-corrected likes); then reused for the ratio likes / bins2D
     int lmbc, pad3;       // the mult_bias_correction_order setting itself (the likes ignore periodicity, :1890)
+    // user prior mask (mask_function, mcsamples.py:1909-1919): (G + 2w)^2 doubles or NULL
+    const double* umask;
 };
 
 // window: one CTA per job
@@ -598,7 +600,9 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
                 }
                 tmax = fmax(tmax, acc[m]);
             } else if (MODE == 1) {
-                const double vv = P[o] * acc[m] / jb.a00b[o];
+                // mask_function: masked pixels are not divided by the normaliser (mcsamples.py:1973-1976)
+                const bool masked = jb.umask && jb.umask[(size_t)(oy + w) * (G + 2 * w) + ox + w] < 1e-8;
+                const double vv = masked ? P[o] * acc[m] : P[o] * acc[m] / jb.a00b[o];
                 Pout[o] = vv;
                 tmax = fmax(tmax, vv);
             } else if (MODE == 2) {
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(256) k_mask_T(const ConvJob* __restrict__ jobs
     const ConvJob jb = jobs[blockIdx.y];
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const int ku = blockIdx.x;
-    if (ku >= K || !jb.T) return;
+    if (ku >= K || !jb.T || jb.umask) return;
     const double* wrow = jb.Wk + (size_t)ku * K;
     const int eb = (jb.bounded && !jb.xper) ? jb.xb : 0, et = (jb.bounded && !jb.xper) ? jb.xt : 0;
     for (int x = threadIdx.x; x < G; x += blockDim.x) {
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ j
     const ConvJob jb = jobs[blockIdx.y];
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const size_t plane = (size_t)K * G, gg = (size_t)G * G;
-    if (!jb.T) return;
+    if (!jb.T || jb.umask) return;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= G) return;
     const int eb = (jb.bounded && !jb.yper) ? jb.yb : 0, et = (jb.bounded && !jb.yper) ? jb.yt : 0;
@@ -770,6 +774,69 @@ __global__ void __launch_bounds__(256) k_mask_maps(const ConvJob* __restrict__ j
     }
 }
 
+// mask_function (mcsamples.py:1909-1919): the prior mask is an arbitrary (G + 2w)^2 array, so the six boundary-kernel
+// moment maps and the bias normaliser are plain 'valid' convolutions of (user mask x edge masks) with the window
+// moments; one thread per output pixel (rare path).  grid (ceil(G*G/256), njobs).
+__global__ void __launch_bounds__(256) k_umask_maps(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (!jb.umask) return;
+    const int G = jb.G, w = jb.w, K = 2 * w + 1, Gp = G + 2 * w;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= G * G) return;
+    const int y = o / G, x = o - y * G;
+    const int xb = jb.bounded ? jb.xb : 0, xt = jb.bounded ? jb.xt : 0, yb = jb.bounded ? jb.yb : 0, yt = jb.bounded ? jb.yt : 0;
+    double a00 = 0, a10 = 0, a01 = 0, a20 = 0, a02 = 0, a11 = 0, ab = 0;
+    for (int ku = 0; ku < K; ku++) {
+        const int u = ku - w, sy = y - u;
+        const double my = mask1d(sy, G, yb, yt);
+        const double myb = (sy < 0 || sy > G - 1) ? 0.0 : my;
+        const double* urow = jb.umask + (size_t)(sy + w) * Gp + w;
+        const double* wrow = jb.Wk + (size_t)ku * K;
+        for (int kv = 0; kv < K; kv++) {
+            const int v = kv - w, sx = x - v;
+            const double um = urow[sx];
+            const double mxe = mask1d(sx, G, xb, xt);
+            const double m = um * mxe * my;
+            const double mb = um * ((sx < 0 || sx > G - 1) ? 0.0 : mxe) * myb;
+            const double wv = wrow[kv], wx = wv * (double)v, wy = wv * (double)u;
+            a00 += wv * m;
+            a10 += wx * m;
+            a01 += wy * m;
+            a20 += (wx * (double)v) * m;
+            a02 += (wy * (double)u) * m;
+            a11 += (wy * (double)v) * m;
+            ab += wv * mb;
+        }
+    }
+    const size_t gg = (size_t)G * G;
+    if (jb.a00b) jb.a00b[o] = ab;
+    if (jb.bounded) {
+        jb.maps[o] = a00;
+        jb.maps[gg + o] = a10;
+        jb.maps[2 * gg + o] = a01;
+        jb.maps[3 * gg + o] = a20;
+        jb.maps[4 * gg + o] = a02;
+        jb.maps[5 * gg + o] = a11;
+    }
+}
+
+// bins2D[bool_mask] = 0 (mcsamples.py:1978-1979) and the maximum of what remains -> mx[14].  grid (64, njobs)
+__global__ void __launch_bounds__(256) k_umask_zero(const ConvJob* __restrict__ jobs) {
+    const ConvJob jb = jobs[blockIdx.y];
+    if (!jb.umask) return;
+    const int G = jb.G, w = jb.w;
+    const size_t gg = (size_t)G * G;
+    double* P = (jb.mbc & 1) ? jb.Pn : jb.P;
+    double tmax = 0;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < gg; o += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(o / G), x = (int)(o - (size_t)y * G);
+        if (jb.umask[(size_t)(y + w) * (G + 2 * w) + x + w] < 1e-8) P[o] = 0;
+        tmax = fmax(tmax, P[o]);
+    }
+    tmax = warp_max(tmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + 14, tmax);
+}
+
 // boundary correction (mcsamples.py:1927-1959); running max of the corrected density -> mx[1]
 __global__ void __launch_bounds__(256) k_boundary2d(const ConvJob* __restrict__ jobs) {
     const ConvJob jb = jobs[blockIdx.y];
@@ -814,7 +881,7 @@ __global__ void __launch_bounds__(256) k_finalize2d(const ConvJob* __restrict__ 
     // final density buffer and its max slot: after mbc bias iterations
     const int it = jb.mbc;
     const double* P = (it & 1) ? jb.Pn : jb.P;
-    const int slot = 1 + it;
+    const int slot = jb.umask ? 14 : 1 + it;
     const double mx = __longlong_as_double((long long)jb.mx[slot]);
     double* o = out + offs[blockIdx.y];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < gg; i += (size_t)gridDim.x * blockDim.x)

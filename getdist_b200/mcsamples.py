@@ -728,8 +728,6 @@ class MCSamples:
         """mcsamples.py:1748-2010."""
         if self.needs_update:
             self.updateBaseStatistics()
-        if mask_function is not None:
-            raise NotImplementedError("mask_function is not on the device path yet (SURVEY.md s8f-3)")
         j, parx = self._parAndNumber(j)
         j2, pary = self._parAndNumber(j2)
         if j is None or j2 is None:
@@ -739,9 +737,12 @@ class MCSamples:
             ncontours = min(num_plot_contours, ncontours)
         want = [] if get_density else list(self.contours[:ncontours])
         density = None
-        if meanlikes:
-            # mcsamples.py:1829-1831, 1886-1901, 2004-2006 (likes are only attached when get_density=False)
-            density = self._densities_2d([(j, j2)], _contours=want, _likes=True, **kwargs)[0]
+        if meanlikes or mask_function is not None:
+            # mcsamples.py:1829-1831, 1886-1901, 2004-2006 (likes are only attached when get_density=False);
+            # mask_function: mcsamples.py:1909-1919, 1973-1979
+            if mask_function is not None and (parx.periodic or pary.periodic):
+                raise NotImplementedError("mask_function with periodic parameters is not on the device path")
+            density = self._densities_2d([(j, j2)], _contours=want, _likes=bool(meanlikes), _mask_function=mask_function, **kwargs)[0]
         elif not kwargs:
             cached = self._density2D.get((j, j2))
             if cached is not None:
@@ -969,7 +970,8 @@ class MCSamples:
                 sp["ry_fixed"] = smooth * fine / nbin2D
         return sp
 
-    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, _anchor_hints=None, **kwargs):
+    def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, _anchor_hints=None,
+                      _mask_function=None, **kwargs):
         if _likes:
             self._ensure_loglikes()
         self._ensure_param_ranges([p for pr in pairs for p in pr])
@@ -985,7 +987,30 @@ class MCSamples:
         for k, c in enumerate(conts):
             specs["contours"][:, k] = c
         lbuf = None
-        if _likes:
+        masks = None
+        if _mask_function is not None:
+            # the prior mask needs the kernel half-width (mcsamples.py:1863, 1909-1916): bandwidth stage first, then the
+            # full pipeline with that bandwidth fixed and the (G + 2w)^2 masks the user function filled in
+            res1 = self._ctx.bandwidth2d_batch(specs)
+            masks, mask_w = [], []
+            for spr, r in zip(specs, res1):
+                G, w = int(spr["fine_bins"]), int(r.winw)
+                fwx = (float(spr["xbinmax"]) - float(spr["xbinmin"])) / (G - 1)
+                fwy = (float(spr["ybinmax"]) - float(spr["ybinmin"])) / (G - 1)
+                pm = np.ones((G + 2 * w, G + 2 * w))
+                _mask_function(float(spr["xbinmin"]) - w * fwx, float(spr["ybinmin"]) - w * fwy, fwx, fwy, pm)
+                masks.append(pm)
+                mask_w.append(w)
+            specs2 = specs.copy()
+            for k, r in enumerate(res1):
+                if int(specs2["bw_mode"][k]) != 0:
+                    specs2["bw_mode"][k] = 0  # GDK_BW2D_FIXED: the widths (in bins) and correlation found above
+                    specs2["rx_fixed"][k], specs2["ry_fixed"][k], specs2["kernel_corr"][k] = r.rx, r.ry, r.c
+            buf, lbuf, offsets, res = self._ctx.density2d_masked_batch(specs2, masks, mask_w, likes=_likes)
+            for r2, r in zip(res, res1):  # bandwidth diagnostics and warnings come from the first stage
+                r2.status |= r.status
+                r2.hx, r2.hy, r2.t_star, r2.n_brent = r.hx, r.hy, r.t_star, r.n_brent
+        elif _likes:
             buf, lbuf, offsets, res = self._ctx.density2d_batch(specs, likes=True)
         else:
             buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
@@ -1011,12 +1036,16 @@ class MCSamples:
             y = np.linspace(sp.ybinmin, sp.ybinmax, G)
             d = Density2D(x, y, buf[off: off + G * G].reshape(G, G),
                           view_ranges=[(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
+            if masks is not None:  # bool_mask, mcsamples.py:1917, 1986
+                w = len(masks[len(out)]) - G
+                w //= 2
+                d.mask = np.asarray(masks[len(out)][w: w + G, w: w + G] < 1e-8)
             d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
                           n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G,
                           levels=(conts, [r.levels[k] for k in range(len(conts))]) if conts else None)
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
-            if not kwargs:
+            if not kwargs and masks is None and lbuf is None:
                 self._density2D[(j, j2)] = d
             out.append(d)
         return out

@@ -41,6 +41,8 @@ typedef struct gdk_ctx gdk_ctx;
 
 /* flags for the batch calls */
 #define GDK_OUT_DEVICE 1u /* P_out is a device pointer */
+#define GDK_BW_ONLY 2u    /* 2D: stop after the bandwidth stage -- only `res` (rx, ry, c, winw, status) is written; used by
+                             the mask_function path, whose prior mask needs the kernel half-width first          */
 
 /* per-density status bits (result structs) */
 #define GDK_ST_BW_FALLBACK 1u    /* 1D: ISJ root failed or too small -> rule-of-thumb (mcsamples.py:1258-1268)   */
@@ -231,6 +233,15 @@ int32_t gdk_density2d_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, do
  * 2004-2006): likes_out laid out like P_out (NULL: plain call), max-normalised.  Needs gdk_set_loglikes.     */
 int32_t gdk_density2d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, double* P_out, double* likes_out,
                                   const int64_t* offsets, gdk_result2d* res, uint32_t flags);
+
+/* Same, with a user prior mask per pair (mask_function of get2DDensityGridData, mcsamples.py:1909-1919, 1973-1979):
+ * pair i's mask is (G_i + 2 w_i)^2 doubles at masks + mask_offsets[i] (mask_offsets[i] < 0: none), built by the caller
+ * for the kernel half-width mask_w[i] that a GDK_BW_ONLY call returned; the specs must then carry that bandwidth as
+ * GDK_BW2D_FIXED (rx_fixed, ry_fixed, kernel_corr) so that the half-width is reproduced (checked).  Masked pixels
+ * (mask < 1e-8) are zero in P_out.  likes_out optional as above.  Periodic axes are not supported with a mask.  */
+int32_t gdk_density2d_masked_batch(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, const double* masks,
+                                   const int64_t* mask_offsets, const int32_t* mask_w, double* P_out, double* likes_out,
+                                   const int64_t* offsets, gdk_result2d* res, uint32_t flags);
 
 /* ---------------------------------------------------------------------------------------------
  * lagged sums over the stored rows -- the N-sized arithmetic of the MCMC effective-sample estimate
