@@ -182,6 +182,8 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->use_sorted = !(es && es[0] == '0');
         const char* ess = getenv("GDK_SHEAR_SORTED");
         ctx->shear_sorted = ess && ess[0] == '1';
+        const char* ebt = getenv("GDK_BW2D_THREADS");
+        if (ebt && (atoi(ebt) == 256 || atoi(ebt) == 512 || atoi(ebt) == 768)) ctx->bw2d_threads = atoi(ebt);
         const char* em = getenv("GDK_SORTED_MIN_N");
         if (em) ctx->sorted_min_n = atoll(em);
     }

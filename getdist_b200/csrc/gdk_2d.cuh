@@ -848,7 +848,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         CK2(cudaFuncSetAttribute(k_bw2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_BW2D);
-        k_bw2d<<<n, 256, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
+        k_bw2d<<<n, ctx->bw2d_threads, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
         ctx->launches++;
         pt.end();
         CK2(cudaGetLastError());

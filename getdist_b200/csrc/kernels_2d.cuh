@@ -381,7 +381,7 @@ struct Bw2dJob {
 };
 
 // grid (npairs), 512 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
-__global__ void __launch_bounds__(256, 3) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
+__global__ void __launch_bounds__(768, 1) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
                                               const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res) {
     extern __shared__ __align__(16) unsigned char bsm[];
     __shared__ double red[32];

@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_2d.py -x -q -m gpu 2>&1 | tail -15 > gpurun_out/r2i_tests.log
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err
-timeout 600 python bench.py --n 1000000 --p 256 --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/r2i_bench_p256.json 2> gpurun_out/r2i_bench_p256.err
-tail -3 gpurun_out/r2i_bench_p256.err
-ls -la gpurun_out
+for t in 256 512 768; do
+GDK_BW2D_THREADS=$t timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/r2j_bench_bw$t.json 2> gpurun_out/r2j_bench_bw$t.err
+done
+GDK_BW2D_THREADS=768 timeout 600 python -m pytest tests/test_gpu_2d.py -x -q -m gpu -k "density_2d or contour" 2>&1 | tail -4 > gpurun_out/r2j_tests768.log
+ls gpurun_out | head -50
