@@ -230,7 +230,7 @@ def run_ours(args):
     names = ["p%d" % i for i in range(P)]
 
     mc = MCSamples(samples=X, weights=w, names=names, sampler="uncorrelated", settings=SETTINGS, device=dev)
-    from getdist_b200.parallel import partition_triangle
+    from getdist_b200.parallel import exchange_param_ranges, partition_triangle
 
     idx, pairs = mc.triangle_pairs()
     my1d, my2d, max1d, per, hints = partition_triangle(idx, pairs, rank, world, with_hints=True)
@@ -249,6 +249,8 @@ def run_ours(args):
         th0 = time.perf_counter()
         mc.invalidate_density_caches()
         mc._ctx.timer_start()
+        if world > 1:  # quantiles sharded over the ranks + one small all-gather of the per-parameter table
+            exchange_param_ranges(mc, idx, rank, world, dist)  # the SAME list on every rank
         if my1d:
             mc._densities_1d(my1d, _device_ptr=d1.data_ptr())
             ph = mc._ctx.phase_ms()

@@ -562,13 +562,17 @@ class MCSamples:
                 self.paramNames.names[j].N_eff_kde = v
 
     # ------------------------------------------------------------------ parameter ranges
+    def _range_fracs(self):
+        """the 11 probability fractions _initParam asks confidence() for (mcsamples.py:1440-1443)"""
+        return np.array([self.range_confidence, 1 - self.range_confidence] + _QFRACS_TAIL)
+
     def _ensure_param_ranges(self, indices):
         """_initParam (mcsamples.py:1427-1484) for a set of parameters: one batched exact-quantile call for
         those not done yet, then the scalar range / limit logic per parameter."""
         todo = [j for j in dict.fromkeys(indices) if not self.paramNames.names[j]._ranges_ready]
         if not todo:
             return
-        fr = np.array([self.range_confidence, 1 - self.range_confidence] + _QFRACS_TAIL)
+        fr = self._range_fracs()
         q = self._ctx.weighted_quantiles(todo, fr)
         for row, j in zip(q, todo):
             self._finish_param(self.paramNames.names[j], j, row)

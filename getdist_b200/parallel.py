@@ -64,3 +64,35 @@ def all_gather_grids(local, world, dist=None):
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, local)
     return out
+
+
+def exchange_param_ranges(mc, indices, rank, world, dist=None, device="cuda"):
+    """Exact weighted quantiles (the _initParam step, mcsamples.py:1427-1484) sharded over the ranks: every rank
+    selects the order statistics of its share of the parameters on its own GPU, ONE small all-gather (11 doubles per
+    parameter) hands every rank the full table, and the scalar range logic then runs everywhere.  The values are
+    sample values selected by exact integer arithmetic, so every rank ends up with bit-identical ranges."""
+    import numpy as np
+
+    # every rank must pass the same set of parameters (and hold the same ready-state): the shares are dealt from
+    # the sorted list
+    todo = [j for j in sorted(set(indices)) if not mc.paramNames.names[j]._ranges_ready]
+    if not todo:
+        return
+    if world == 1 or dist is None:
+        mc._ensure_param_ranges(todo)
+        return
+    import torch
+
+    fr = mc._range_fracs()
+    mine = todo[rank::world]
+    per = (len(todo) + world - 1) // world
+    loc = np.zeros((per, fr.size))
+    if mine:
+        loc[: len(mine)] = mc._ctx.weighted_quantiles(mine, fr)
+    send = torch.from_numpy(loc).to(device)
+    recv = torch.empty((world * per, fr.size), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(recv, send)
+    table = recv.cpu().numpy()
+    for r in range(world):
+        for k, j in enumerate(todo[r::world]):
+            mc._finish_param(mc.paramNames.names[j], j, table[r * per + k])

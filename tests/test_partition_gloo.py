@@ -97,3 +97,54 @@ def test_split_pairs_keeps_anchors_together(P, world):
         for (a, b), h in zip(lists[r], hints[r]):
             per_anchor[a if h == 1 else b] = per_anchor.get(a if h == 1 else b, 0) + 1
     assert max(per_anchor.values()) <= P // 2 and min(per_anchor.values()) >= (P - 1) // 2
+
+
+class _FakePar:
+    def __init__(self):
+        self._ranges_ready = False
+        self.row = None
+
+
+class _FakeMC:
+    """stand-in with the three hooks exchange_param_ranges uses"""
+
+    def __init__(self, P):
+        import types
+
+        self.paramNames = types.SimpleNamespace(names=[_FakePar() for _ in range(P)])
+        self.calls = []
+        self._ctx = types.SimpleNamespace(weighted_quantiles=self._wq)
+
+    def _range_fracs(self):
+        return np.linspace(0.05, 0.95, 11)
+
+    def _wq(self, params, fr):
+        self.calls.append(list(params))
+        return np.array([[100.0 * j + f for f in fr] for j in params])
+
+    def _finish_param(self, par, j, row):
+        par.row = np.array(row)
+        par._ranges_ready = True
+
+
+def _range_worker(rank, world, port, P, ret):
+    from getdist_b200.parallel import exchange_param_ranges
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mc = _FakeMC(P)
+    exchange_param_ranges(mc, list(range(P)) + [0, 1], rank, world, dist, device="cpu")
+    fr = mc._range_fracs()
+    ok = all(p._ranges_ready and np.array_equal(p.row, 100.0 * j + fr) for j, p in enumerate(mc.paramNames.names))
+    ok = ok and sum(len(c) for c in mc.calls) == len(range(rank, P, world))  # only this rank's share was selected here
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_exchange_param_ranges_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_range_worker, args=(world, _free_port(), 7, ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
