@@ -93,6 +93,10 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """start of the timed region: only samples from here on are reported"""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -103,7 +107,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -286,13 +290,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    l0 = mc._ctx.launch_count()
+    # the clock sampler (one nvidia-smi process polling every 100 ms) is started BEFORE the warm-up: its start-up
+    # stalls kernel launches for tens of milliseconds; samples taken before the timed region are discarded below
     clocks = ClockSampler(dev)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    if rank == 0:
+        clocks.mark()
+    l0 = mc._ctx.launch_count()
     total_ms = 0.0
     step_ms = []
     mc._ctx.set_kernel_timing(True)  # event pairs around the tagged kernels of the timed steps (roofline figures)

@@ -1396,9 +1396,33 @@ __global__ void __launch_bounds__(1024) k_bucket_records(const unsigned char* __
         jslot[threadIdx.x] = jobs[threadIdx.x].slot;
         jc0[threadIdx.x] = jobs[threadIdx.x].c0;
     }
-    // stage: a warp item = 4 parameters x 8 words (32 rows): four sectors per request, byte stores that hit 8 banks
-    // (the 4 parameters of one row share a word)
-    {
+    // stage.  np % 4 == 0: a warp item = 16 parameters x 32 rows; a lane loads the words of 4 parameters x 4 rows,
+    // transposes the 4 x 4 bytes in registers and stores one word per row (bank = 4 ql (pitch/4 mod 8) + pl: all 32
+    // lanes distinct because pitch / 4 is odd).  Otherwise (small odd P): byte stores.
+    if ((np & 3) == 0) {
+        const int ql = lane & 7, pl = lane >> 3;
+        const int npg = (np + 15) >> 4, nqb = (rows + 31) >> 5;
+        for (int it = warp; it < npg * nqb; it += nwarps) {
+            const int pg = it / nqb, qb = it - pg * nqb;
+            const int p0 = pg * 16 + pl * 4, q = qb * 8 + ql;  // rows 4q .. 4q+3
+            if (p0 < np && 4 * q < rows) {
+                unsigned wv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    wv[j] = (r0 + 4 * q < ld) ? *reinterpret_cast<const unsigned*>(ix8 + (int64_t)(p0 + j) * ld + r0 + 4 * q) : 0u;
+                const unsigned t0 = __byte_perm(wv[0], wv[1], 0x5140), t1 = __byte_perm(wv[0], wv[1], 0x7362);
+                const unsigned t2 = __byte_perm(wv[2], wv[3], 0x5140), t3 = __byte_perm(wv[2], wv[3], 0x7362);
+                const unsigned o[4] = {__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410),
+                                       __byte_perm(t1, t3, 0x7632)};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    unsigned* row = reinterpret_cast<unsigned*>(tile + (size_t)(4 * q + k) * pitch);
+                    row[p0 >> 2] = o[k];
+                    if (p0 < 32) row[(np + p0) >> 2] = o[k];  // wrap-around copy of the first 32 columns
+                }
+            }
+        }
+    } else {
         const int ql = lane & 7, pl = lane >> 3;
         const int npg = (np + 3) >> 2, nqb = (rows + 31) >> 5;
         for (int it = warp; it < npg * nqb; it += nwarps) {
