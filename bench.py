@@ -297,6 +297,19 @@ def run_ours(args):
         clocks.start()
     for _ in range(args.warmup):
         step_resident()
+    # settle: on a cold box single steps still came out 10-40 % slow right after the W warm-up steps (clock / power
+    # state, first-touch of the 25 GB record scratch); up to 6 more UNTIMED steps until two in a row agree within 2 %
+    extra_warm, prev = 0, None
+    while extra_warm < 6:
+        cur = step_resident()
+        extra_warm += 1
+        if world > 1:  # the steps contain collectives: every rank must run the same number of them
+            if extra_warm == 2:
+                break
+            continue
+        if prev is not None and abs(cur - prev) <= 0.02 * prev:
+            break
+        prev = cur
     barrier()
     if rank == 0:
         clocks.mark()
@@ -464,7 +477,7 @@ def run_ours(args):
         "config": {"workload": workload_name(N, P),
                    "partition": "densities split across %d rank(s); every rank holds the full sample store; NCCL all-gather of grids" % world,
                    "l2": "inputs (%.1f GB) are larger than L2; no flush needed between steps" % ((N * P * 8 + N * 8) / 1e9),
-                   "datagen_s": t_gen},
+                   "datagen_s": t_gen, "extra_untimed_settle_steps": extra_warm},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_step": e2e_s, "checksum": checksum, "parts": e2e_parts,
                 "path": "MCSamples.setSamples(pinned host) + updateBaseStatistics [H2D + moments] -> quantiles -> 1D + 2D batches -> pinned host grids"},
