@@ -107,6 +107,61 @@ class Density1D(GridDensity):
 
     __call__ = Prob
 
+    # ---- equal-density credible limits (densities.py:186-248 of the reference): host-side, grid-sized ----------
+    def initLimitGrids(self, factor=None):
+        """Spline-refined copy of the density (factor x finer), its total and the ascending cumulative sum of its
+        sorted values: the tables getLimits() searches (reference densities.py:186-205)."""
+        from scipy.interpolate import splev, splrep
+
+        if self.spl is None:
+            self.spl = splrep(self.x, self.P, s=0)
+        g = _LimitGrids()
+        g.factor = max(2, 20000 // self.n) if factor is None else factor
+        g.bign = (self.n - 1) * g.factor + 1
+        g.grid = splev(self.x[0] + np.arange(g.bign) * self.spacing / g.factor, self.spl)
+        g.norm = np.sum(g.grid) - 0.5 * self.P[-1] - 0.5 * self.P[0]
+        g.sortgrid = np.sort(g.grid)
+        g.cumsum = np.cumsum(g.sortgrid)
+        return g
+
+    def getLimits(self, p, interpGrid=None, accuracy_factor=None):
+        """(min, max, has_min_boundary, has_max_boundary) of the equal-density interval holding probability p
+        (tuple for a scalar p, list of tuples otherwise); a side whose end bin lies above the density level has no
+        limit there (reference densities.py:207-248)."""
+        g = interpGrid or self.initLimitGrids(accuracy_factor)
+        fracs = np.atleast_1d(p)
+        targets = (1 - fracs) * g.norm
+        fine = self.spacing / g.factor
+        out = []
+        for ix, target in zip(np.searchsorted(g.cumsum, targets), targets):
+            level = g.sortgrid[ix]
+            if ix > 0:
+                step = g.cumsum[ix] - g.cumsum[ix - 1]
+                t = (g.cumsum[ix] - target) / step
+                level = (1 - t) * level + t * g.sortgrid[ix + 1]
+            at_bot = g.grid[0] >= level
+            if at_bot:
+                lo = self.x[0]
+            else:
+                i = int(np.argmax(g.grid > level))  # first fine bin above the level; interpolate the crossing
+                lo = self.x[0] + (i - (g.grid[i] - level) / (g.grid[i] - g.grid[i - 1])) * fine
+            at_top = g.grid[-1] >= level
+            if at_top:
+                hi = self.x[-1]
+            else:
+                i = g.bign - int(np.argmax(g.grid[::-1] > level)) - 1  # last fine bin above the level
+                hi = self.x[0] + (i + (g.grid[i] - level) / (g.grid[i] - g.grid[i + 1])) * fine
+            if fracs is not p:
+                return lo, hi, at_bot, at_top
+            out.append((lo, hi, at_bot, at_top))
+        return out
+
+
+class _LimitGrids:
+    """tables built by Density1D.initLimitGrids"""
+
+    factor = bign = grid = norm = sortgrid = cumsum = None
+
 
 class Density2D(GridDensity):
     def __init__(self, x, y, P=None, view_ranges=None, mask=None):

@@ -185,6 +185,7 @@ class MCSamples:
         if self.sampler not in ("mcmc", "nested", "uncorrelated"):
             self.sampler = "mcmc"
         self.raise_on_bandwidth_errors = False
+        self.force_twotail = False  # mcsamples.py:263
         self.no_warning_params = []
         self.no_warning_chi2_params = True
         self.likeStats = None
@@ -244,6 +245,10 @@ class MCSamples:
             elif k in ANALYSIS_DEFAULTS and not isinstance(ANALYSIS_DEFAULTS[k], tuple):
                 v = type(ANALYSIS_DEFAULTS[k])(v)  # typed by the existing attribute, inifile.py:216-226
             setattr(self, k, v)
+        # how small the end bin must be relative to the peak for a two-tail limit (mcsamples.py:427-433)
+        from scipy.stats import norm as _norm
+
+        self.max_frac_twotail = [float(np.exp(-1.0 * _norm.ppf((1 - c) / 2) ** 2 / 2)) for c in self.contours]
         if doUpdate and self.samples is not None:
             self.updateBaseStatistics()
 
@@ -1053,6 +1058,57 @@ class MCSamples:
                 self._density2D[(j, j2)] = d
             out.append(d)
         return out
+
+    # ------------------------------------------------------------------ marginalised limits
+    def setMargeLimits(self, params=None, max_frac_twotail=None):
+        """Batched form of _setDensitiesandMarge1D (mcsamples.py:2442-2458): the 1D densities that are not cached yet
+        in one device batch, every order statistic the limit logic can ask for (4 per contour) in ONE device quantile
+        call, then the scalar logic of _setMargeLimits per parameter (getdist_b200/limits.py).  Sets `par.limits`
+        (list of ParamLimit, one per contour) and returns {name: limits}."""
+        from .limits import limit_fractions, marge_limits
+
+        if self.needs_update:
+            self.updateBaseStatistics()
+        idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]
+        if any(j is None for j in idx):
+            raise ParamError("unknown parameter")
+        missing = [j for j in idx if self.paramNames.names[j].name not in self.density1D]
+        if missing:
+            self._densities_1d(missing)
+        mft = self.max_frac_twotail if max_frac_twotail is None else max_frac_twotail
+        keys = limit_fractions(self.contours)
+        out = {}
+        for k0 in range(0, len(keys), 16):  # at most 16 target fractions per device call
+            part = keys[k0:k0 + 16]
+            fr = np.array([(1 - lf) if up else lf for lf, up in part])
+            q = self._ctx.weighted_quantiles(idx, fr)
+            for row, j in zip(q, idx):
+                out.setdefault(j, {}).update(dict(zip(part, row)))
+        res = {}
+        for j in idx:
+            par = self.paramNames.names[j]
+            table = out[j]
+            par.limits = marge_limits(self.density1D[par.name], par, self.contours, mft, lambda lf, up: table[(lf, up)],
+                                      force_twotail=self.force_twotail,
+                                      credible_interval_threshold=self.credible_interval_threshold)
+            res[par.name] = par.limits
+        return res
+
+    def _setMargeLimits(self, par, paramConfid=None, max_frac_twotail=None, density1D=None):
+        """mcsamples.py:2460-2531 for one parameter (paramConfid is not needed: the order statistics come from the
+        device).  A density passed in replaces the cached one for this call only."""
+        from .limits import limit_fractions, marge_limits
+
+        j, par = self._parAndNumber(par if not isinstance(par, ParamInfo) else par.name)
+        if density1D is None:
+            density1D = self.get1DDensity(par.name)
+        mft = self.max_frac_twotail if max_frac_twotail is None else max_frac_twotail
+        keys = limit_fractions(self.contours)[:16]
+        fr = np.array([(1 - lf) if up else lf for lf, up in keys])
+        table = dict(zip(keys, self._ctx.weighted_quantiles([j], fr)[0]))
+        par.limits = marge_limits(density1D, par, self.contours[:4], mft, lambda lf, up: table[(lf, up)],
+                                  force_twotail=self.force_twotail, credible_interval_threshold=self.credible_interval_threshold)
+        return par.limits
 
     # ------------------------------------------------------------------ batched driver
     def triangle_pairs(self, params=None):

@@ -112,6 +112,36 @@ def run_case(name):
     print(name, "ok", len(out), "arrays")
 
 
+LIMIT_CASES = ("mix3", "bounded", "likes")
+
+
+def run_limits():
+    """Marginalised limits of the reference (MCSamples._setMargeLimits, mcsamples.py:2460-2531) for every parameter of
+    a few cases -> limits.npz: per parameter the (lower, upper) pairs of the three default contours and the limit tags
+    encoded as 0 two, 1 '>', 2 '<', 3 none."""
+    code = {"two": 0, ">": 1, "<": 2, "none": 3}
+    out = {}
+    for name in LIMIT_CASES:
+        case = CASES[name]()
+        mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"] or None,
+                       sampler=case.get("sampler", "uncorrelated"), loglikes=case.get("loglikes"), settings=case["settings"] or None)
+        out[name + "/digest"] = np.array(input_digest(case))
+        out[name + "/contours"] = np.asarray(mc.contours)
+        out[name + "/max_frac_twotail"] = np.asarray(mc.max_frac_twotail)
+        for j, par in enumerate(mc.paramNames.names):
+            conf = mc.initParamConfidenceData(mc.samples[:, j])
+            mc._setMargeLimits(par, conf)
+            out["%s/%d/limits" % (name, j)] = np.array([[np.nan if l.lower is None else l.lower,
+                                                         np.nan if l.upper is None else l.upper] for l in par.limits])
+            out["%s/%d/tags" % (name, j)] = np.array([code[l.limitTag()] for l in par.limits])
+    np.savez_compressed(os.path.join(HERE, "limits.npz"), **out)
+    print("limits ok", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or list(CASES)):
-        run_case(nm)
+    names = sys.argv[1:] or list(CASES) + ["limits"]
+    for nm in names:
+        if nm == "limits":
+            run_limits()
+        else:
+            run_case(nm)

@@ -191,3 +191,25 @@ def test_pickle_and_copy_roundtrip(gpu_objs):
     np.testing.assert_allclose(mc2.getCov(), mc.getCov(), rtol=0, atol=0)
     mc3 = mc.copy(settings={"fine_bins": 512})
     assert mc3.get1DDensity("b").P.size == 512 and mc.get1DDensity("b").P.size == 1024
+
+
+@pytest.mark.parametrize("name", ["bounded", "likes"])
+def test_marge_limits(name):
+    """MCSamples.setMargeLimits (batched 1D densities + one device quantile call + the host limit logic)
+    against the limits of the unmodified reference (tests/golden/limits.npz)"""
+    import os
+
+    from getdist_b200 import MCSamples
+    from helpers import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "limits.npz"))
+    case, _ = load_case(name)
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"],
+                   sampler="uncorrelated", settings=case["settings"] or None)
+    lims = mc.setMargeLimits()
+    tags = {0: "two", 1: ">", 2: "<", 3: "none"}
+    for j, nm in enumerate(case["names"]):
+        ref, rt = g["%s/%d/limits" % (name, j)], g["%s/%d/tags" % (name, j)]
+        assert [l.limitTag() for l in lims[nm]] == [tags[int(t)] for t in rt], (name, nm)
+        got = np.array([[l.lower, l.upper] for l in lims[nm]], dtype=np.float64)
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7 * mc.sddev[j], err_msg=str((name, nm)))

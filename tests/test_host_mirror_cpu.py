@@ -1,0 +1,111 @@
+"""Host mirror (getdist_b200/mcsamples.py) on the CPU: the ctypes Context is replaced by a TEST DOUBLE that answers
+the same calls with numpy (moments, exact weighted quantiles) and with the device grid-stage code compiled for the
+host (tests/hostsim: kde1d_core on np.bincount histograms).  Checks the scalar host logic -- _initParam ranges,
+spec building, caching, marginalised limits -- without a GPU.  The product path itself never runs like this: the
+real Context raises without libgdk.so / a CUDA device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, load_case, make_oracle
+from test_hostsim import Res1D, Spec1D, dptr, hs  # noqa: F401  (hs: session fixture building tests/hostsim)
+
+
+class FakeContext:
+    """numpy / hostsim stand-in for getdist_b200._abi.Context (1D path only)"""
+
+    hs = None
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def close(self):
+        pass
+
+    def set_samples(self, X, w=None, chain_offsets=None):
+        self.X = np.asarray(X, dtype=np.float64)
+        self.N, self.P = self.X.shape
+        self.w = np.ones(self.N) if w is None else np.asarray(w, dtype=np.float64)
+        self.nchains = 1 if chain_offsets is None else len(chain_offsets) - 1
+
+    def moments(self):
+        from oracle.getdist_oracle import weighted_cov, weighted_means, weighted_vars
+
+        m = weighted_means(self.X, self.w)
+        return dict(means=m, vars=weighted_vars(self.X, self.w, m), cov=weighted_cov(self.X, self.w, m),
+                    scalars=np.array([self.w.sum(), (self.w**2).sum(), self.w.max(), 0.0, self.N, self.w.min(), 0, 0]),
+                    xmin=self.X.min(axis=0), xmax=self.X.max(axis=0), chain_means=m[None, :],
+                    chain_covs=np.zeros((1, self.P, self.P)), chain_norms=np.array([self.w.sum()]))
+
+    def weighted_quantiles(self, params, fracs):
+        from oracle.getdist_oracle import weighted_quantiles
+
+        return np.array([weighted_quantiles(self.X[:, j], self.w, np.asarray(fracs)) for j in params])
+
+    def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
+        from oracle.getdist_oracle import bin_indices
+
+        assert device_ptr is None and not likes
+        stride = max(s.fine_bins for s in specs)
+        P = np.zeros((len(specs), stride))
+        res = []
+        for i, s in enumerate(specs):
+            F = s.fine_bins
+            fw = (s.binmax - s.binmin) / (F - 1)
+            bins = np.bincount(bin_indices(self.X[:, s.param], s.binmin, fw), weights=self.w, minlength=F)
+            sp = Spec1D(*[getattr(s, f) for f, _ in Spec1D._fields_])
+            r, row = Res1D(), np.empty(F)
+            self.hs.hs_kde1d(C.byref(sp), dptr(bins), dptr(row), C.byref(r))
+            P[i, :F] = row
+            res.append(r)
+        return P, res
+
+
+@pytest.fixture()
+def fake_ctx(hs, monkeypatch):  # noqa: F811
+    from getdist_b200 import _abi
+
+    FakeContext.hs = hs
+    monkeypatch.setattr(_abi, "Context", FakeContext)
+    return FakeContext
+
+
+@pytest.mark.parametrize("name", ["mix3", "bounded", "likes"])
+def test_marge_limits_through_the_mirror(fake_ctx, name):
+    """MCSamples.setMargeLimits / _setMargeLimits (batched _setDensitiesandMarge1D) against the reference's limits"""
+    from getdist_b200 import MCSamples
+
+    g = np.load(os.path.join(GOLDEN, "limits.npz"))
+    case, gold = load_case(name)
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"],
+                   sampler="uncorrelated", settings=case["settings"] or None)
+    np.testing.assert_allclose(mc.max_frac_twotail, g[name + "/max_frac_twotail"], rtol=1e-13)
+    lims = mc.setMargeLimits()
+    tags = {0: "two", 1: ">", 2: "<", 3: "none"}
+    for j, nm in enumerate(case["names"]):
+        ref, rt = g["%s/%d/limits" % (name, j)], g["%s/%d/tags" % (name, j)]
+        assert [l.limitTag() for l in lims[nm]] == [tags[int(t)] for t in rt], (name, nm)
+        got = np.array([[l.lower, l.upper] for l in lims[nm]], dtype=np.float64)
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7 * mc.sddev[j], err_msg=str((name, nm)))
+        # ranges left by _initParam, and the cached density the limits were computed from
+        par = mc.paramNames.names[j]
+        gp = gold["d1/default/%d/par" % j]
+        np.testing.assert_allclose([par.range_min, par.range_max, par.sigma_range], gp[:3], rtol=1e-12)
+        assert np.max(np.abs(mc.get1DDensity(nm).P - gold["d1/default/%d/P" % j])) < 1e-7
+    one = mc._setMargeLimits(mc.paramNames.names[0])
+    assert [l.limitTag() for l in one] == [l.limitTag() for l in lims[case["names"][0]]]
+
+
+def test_unknown_parameter_and_cache(fake_ctx):
+    from getdist_b200 import MCSamples, ParamError
+
+    case, _ = load_case("mix3")
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], sampler="uncorrelated")
+    assert mc.get1DDensity("nope") is None
+    d = mc.get1DDensity("a")
+    assert mc.get1DDensity("a") is d  # cached when called without kwargs (mcsamples.py:1669-1670)
+    assert mc.get1DDensity("a", fine_bins=512) is not d
+    with pytest.raises(ParamError):
+        mc.setMargeLimits(["a", "zzz"])
