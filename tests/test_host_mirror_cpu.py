@@ -109,3 +109,40 @@ def test_unknown_parameter_and_cache(fake_ctx):
     assert mc.get1DDensity("a", fine_bins=512) is not d
     with pytest.raises(ParamError):
         mc.setMargeLimits(["a", "zzz"])
+
+
+@pytest.mark.parametrize("name", ["mix3", "unit5", "bounded", "highcorr", "periodic"])
+def test_2d_planner_on_cpu(fake_ctx, name):
+    """The 2D planner is pure host logic: the vectorised batch planner (_specs_2d_batch) must produce the same
+    gdk_spec2d fields as the per-pair planner (_spec_2d), and both must agree with the oracle's grid geometry,
+    scaled-up grid sizes (mcsamples.py:1812-1819) and branch selection on every golden case."""
+    from getdist_b200 import MCSamples, _abi
+    from oracle.getdist_oracle import bin_geometry
+
+    case, g = load_case(name)
+    mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"],
+                   sampler="uncorrelated", settings=case["settings"] or None)
+    o = make_oracle(case)
+    P = mc.n
+    pairs = [(i, k) for i in range(P) for k in range(P) if i != k]
+    mc._ensure_param_ranges(range(P))
+    mc._ensure_neff(range(P))
+    for kw in case["kwargs_2d"]:
+        batch = mc._specs_2d_batch(pairs, kw)
+        for row, (j, j2) in zip(batch, pairs):
+            single = mc._spec_2d(j, j2, kw)
+            for fname, _ in _abi.Spec2D._fields_:
+                if fname != "contours":
+                    assert row[fname] == getattr(single, fname), (name, kw, j, j2, fname)
+    for (jx, jy) in case["pairs"]:
+        sp = mc._spec_2d(jx, jy, {})
+        d = o.density_2d(jx, jy)
+        assert sp.fine_bins == d.fine_bins
+        parx, pary = o.pars[jx], o.pars[jy]
+        np.testing.assert_allclose([sp.xbinmin, sp.xbinmax], bin_geometry(parx, sp.fine_bins)[:2], rtol=1e-13)
+        np.testing.assert_allclose([sp.ybinmin, sp.ybinmax], bin_geometry(pary, sp.fine_bins)[:2], rtol=1e-13)
+        branch = d.extra.get("branch")
+        if branch == "shear":
+            assert sp.bw_mode == 2
+        elif branch == "plain":
+            assert sp.bw_mode == 1
