@@ -302,8 +302,18 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 // jobs of one launch share their lane layout: order by lanes per row (stable: anchors stay grouped)
                 std::stable_sort(sj.begin(), sj.end(), [](const SortJob& x, const SortJob& y) { return x.lg > y.lg; });
                 const int njobs = (int)sj.size();
-                const int nbatch_max = std::min(njobs, SRT_MAXJOBS);
                 const int64_t pld = (ctx->N + 31) & ~int64_t(31);
+                // jobs per batch: <= SRT_MAXJOBS, and the record scratch (40 B per row and job) within a third of the
+                // memory that is free or already held by it (very large N: smaller batches instead of an allocation failure)
+                int maxjobs = SRT_MAXJOBS;
+                {
+                    size_t freeb = 0, totalb = 0;
+                    cudaMemGetInfo(&freeb, &totalb);
+                    const size_t have = ctx->recs.cap + ctx->recw.cap * 8;
+                    const size_t fit = ((freeb + have) / 3) / ((size_t)pld * 40);
+                    maxjobs = (int)std::max<size_t>(1, std::min<size_t>((size_t)SRT_MAXJOBS, fit));
+                }
+                const int nbatch_max = std::min(njobs, maxjobs);
                 if (ctx->bucket.ensure((size_t)np8 * (256 + 257) + (size_t)njobs * 256) || ctx->recs.ensure((size_t)nbatch_max * pld * 32) ||
                     ctx->recw.ensure((size_t)nbatch_max * pld))
                     return gdk_fail(ctx, GDK_ERR_NOMEM, "bucket-sorted sweep work space (%zu MB)", ((size_t)nbatch_max * pld * 40) >> 20);
@@ -325,8 +335,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 const int chunk = 16384;
                 const size_t srt_smem = (size_t)2 * 256 * 32 * 4;
                 CK2(cudaFuncSetAttribute(k_bucket_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_smem(rows, SRT_MAXJOBS)));
-                for (int b0 = 0; b0 < njobs; b0 += SRT_MAXJOBS) {
-                    const int nb = std::min(SRT_MAXJOBS, njobs - b0);
+                for (int b0 = 0; b0 < njobs; b0 += maxjobs) {
+                    const int nb = std::min(maxjobs, njobs - b0);
                     {
                         KernelTimer kt(ctx, GDK_K_BUCKET_RECORDS, (double)ctx->N * (np8 + 8.0 + 40.0 * nb), 0);
                         k_bucket_records<<<(unsigned)((ctx->N + rows - 1) / rows), 1024, rec_smem(rows, nb), ctx->stream>>>(
