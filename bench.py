@@ -151,12 +151,17 @@ def _ref_task(k):
     """one worker task of the reference arm: a 1D and a 2D (shear branch) density on columns (2k, 2k+1)"""
     from oracle.getdist_oracle import OracleSamples
 
-    orc = _REF["orc"].get(k)
+    orc = _REF["orc"].get("mine")
     if orc is None:
+        # one object per WORKER PROCESS (its own pair of columns), whichever tasks the pool hands it
+        import multiprocessing as mp
+
+        ident = getattr(mp.current_process(), "_identity", None) or (k + 1,)
+        wk = ident[0] - 1
         X, w = _REF["X"], _REF["w"]
-        cols = [(2 * k) % X.shape[1], (2 * k + 1) % X.shape[1]]
-        orc = _REF["orc"][k] = OracleSamples(np.ascontiguousarray(X[:, cols]), w, names=["p%d" % c for c in cols],
-                                             sampler="uncorrelated", settings=SETTINGS)
+        cols = [(2 * wk) % X.shape[1], (2 * wk + 1) % X.shape[1]]
+        orc = _REF["orc"]["mine"] = OracleSamples(np.ascontiguousarray(X[:, cols]), w, names=["p%d" % c for c in cols],
+                                                  sampler="uncorrelated", settings=SETTINGS)
     orc.density_1d(0)
     orc.density_2d(0, 1)
     return 2
