@@ -9,33 +9,28 @@ class DensitiesError(Exception):
 
 
 def getContourLevels(inbins, contours=(0.68, 0.95), missing_norm=0, half_edge=True):
-    """Density levels enclosing the given probability fractions (reference densities.py:19-56).
-    Host-side numpy on the returned grid; SURVEY s8f-2 lists a device version as a later row."""
-    contours = np.atleast_1d(contours)
-    levels = np.zeros(len(contours))
-    if half_edge:
-        a = inbins.copy()
-        for ax in range(a.ndim):
-            sl = [slice(None)] * a.ndim
-            sl[ax] = 0
-            a[tuple(sl)] /= 2
-            sl[ax] = -1
-            a[tuple(sl)] /= 2
-    else:
-        a = inbins
-    norm = np.sum(a)
-    targets = (1 - np.array(contours)) * norm - missing_norm
-    flat = a.reshape(-1)
-    order = inbins.reshape(-1).argsort()
-    sortgrid = flat[order]
-    cumsum = np.cumsum(sortgrid)
-    ixs = np.searchsorted(cumsum, targets)
-    for i, ix in enumerate(ixs):
-        if ix == 0:
+    """Density levels enclosing the given probability fractions (reference densities.py:19-56): grid cells are
+    visited in order of increasing density, their (edge-halved) masses accumulated, and the level is interpolated
+    between the two neighbouring sorted densities where the running mass passes (1 - contour) of the total.
+    Host-side numpy on a returned grid; the batched path computes the same levels on the device (k_contours2d)."""
+    fracs = np.atleast_1d(contours)
+    mass = np.array(inbins, dtype=np.float64, copy=True)
+    if half_edge:  # trapezoid weights: boundary cells count half along every axis
+        for ax in range(mass.ndim):
+            edge = [slice(None)] * mass.ndim
+            for end in (0, -1):
+                edge[ax] = end
+                mass[tuple(edge)] *= 0.5
+    rank = np.argsort(inbins, axis=None)
+    dens = mass.reshape(-1)[rank]
+    run = np.cumsum(dens)
+    want = (1 - np.asarray(fracs)) * mass.sum() - missing_norm
+    levels = np.zeros(len(fracs))
+    for k, (i, t) in enumerate(zip(np.searchsorted(run, want), want)):
+        if i == 0:
             raise DensitiesError("Contour level outside plotted ranges")
-        h = cumsum[ix] - cumsum[ix - 1]
-        d = (cumsum[ix] - targets[i]) / h
-        levels[i] = sortgrid[ix] * (1 - d) + d * sortgrid[ix - 1]
+        back = (run[i] - t) / (run[i] - run[i - 1])  # how far back towards the previous sorted cell
+        levels[k] = dens[i] * (1 - back) + back * dens[i - 1]
     return levels
 
 
@@ -176,9 +171,12 @@ class Density2D(GridDensity):
         self.setP(P)
 
     def integrate(self, P):
-        norm = (np.sum(P[1:-1, 1:-1]) + (P[0, 0] + P[0, -1] + P[-1, 0] + P[-1, -1]) / 4.0
-                + (np.sum(P[1:-1, 0]) + np.sum(P[0, 1:-1]) + np.sum(P[1:-1, -1]) + np.sum(P[-1, 1:-1])) / 2.0)
-        return norm * self.spacing
+        """trapezoid rule on the grid: corners weigh 1/4, edges 1/2 (reference densities.py:273-280)"""
+        wy = np.ones(P.shape[0])
+        wx = np.ones(P.shape[1])
+        wy[[0, -1]] = 0.5
+        wx[[0, -1]] = 0.5
+        return float(wy @ P @ wx) * self.spacing
 
     def norm_integral(self):
         return self.integrate(self.P)
