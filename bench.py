@@ -407,7 +407,7 @@ def run_ours(args):
     # stream and counts the ALGORITHMIC bytes / flops of every launch where the launch parameters are known
     # (gdk_kernel_stat; DESIGN.md s4 states the per-unit figures).  achieved = bytes per launch / average launch time.
     # `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of exactly
-    # this workload (profiles/r2c_*, r2f_*); other sizes have no capture -> null.
+    # this workload (profiles/r2c_*, r2k_*); other sizes have no capture -> null.
     c2 = (N == 10_000_000 and P == 64 and world == 1)
     ncu_traffic = {"k_bin8c": 5.96e9, "k_bucket_records": 13.49e9, "k_hist2d_records": 13.30e9,
                    "k_shear_minmax_tiled": 8.20e9, "k_shear_hist": 63.76e9}

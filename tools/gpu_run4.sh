@@ -1,3 +1,4 @@
+# Multi-GPU bench line (four B200): /usr/local/graft/bin/gpurun --gpus 4 --timeout 400 -- "bash tools/gpu_run4.sh"
 set -x
 cd $GRAFT_REPO_ROOT
 free -g | head -2 > gpurun_out/r2m_mem.txt; nproc >> gpurun_out/r2m_mem.txt
