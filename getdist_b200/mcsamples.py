@@ -819,8 +819,8 @@ class MCSamples:
         sp.neff = 1.0
         if smooth_scale_2D < 0:
             # branch selection of getAutoBandwidth2D, mcsamples.py:1325-1409
-            if self.use_effective_samples_2D and abs(actual_corr) < 0.999:
-                raise NotImplementedError("use_effective_samples_2D needs the 2D autocorrelation N_eff: use the reference")
+            # use_effective_samples_2D is inert on this path in the reference (getAutoBandwidth2D's use_2D_Neff=False
+            # default shadows the setting, mcsamples.py:1297, 1327-1331; verified by running it): always the 1D estimate
             sp.neff = min(self._get1DNeff(parx, j), self._get1DNeff(pary, j2))
             do_correlated = not parx.has_limits or not pary.has_limits
             min_corr = 0.2
@@ -935,8 +935,6 @@ class MCSamples:
         sp["x_periodic"], sp["y_periodic"] = per[jx], per[jy]
         sp["neff"] = 1.0
         if smooth < 0:
-            if self.use_effective_samples_2D and np.any(np.abs(actual) < 0.999):
-                raise NotImplementedError("use_effective_samples_2D needs the 2D autocorrelation N_eff: use the reference")
             neff = np.array([par.N_eff_kde if u else np.nan for par, u in zip(names, used)], dtype=np.float64)
             sp["neff"] = np.minimum(neff[jx], neff[jy])
             do_corr = ~hl[jx] | ~hl[jy]

@@ -146,3 +146,23 @@ def test_2d_planner_on_cpu(fake_ctx, name):
             assert sp.bw_mode == 2
         elif branch == "plain":
             assert sp.bw_mode == 1
+
+
+def test_use_effective_samples_2D_is_inert(fake_ctx):
+    """In the reference the setting never reaches getAutoBandwidth2D from get2DDensityGridData (its use_2D_Neff=False
+    default shadows it, mcsamples.py:1297, 1327-1331 -- checked by running the reference): same specs either way."""
+    from getdist_b200 import MCSamples, _abi
+
+    case, _ = load_case("mix3")
+    kw = dict(samples=case["samples"], weights=case["weights"], names=case["names"], sampler="uncorrelated")
+    a, b = MCSamples(**kw), MCSamples(**kw)
+    b.use_effective_samples_2D = True
+    for mc in (a, b):
+        mc._ensure_param_ranges(range(3))
+        mc._ensure_neff(range(3))
+    pairs = [(0, 1), (1, 2), (2, 0)]
+    sa, sb = a._specs_2d_batch(pairs, {}), b._specs_2d_batch(pairs, {})
+    assert sa.tobytes() == sb.tobytes()
+    for (j, j2) in pairs:
+        x, y = a._spec_2d(j, j2, {}), b._spec_2d(j, j2, {})
+        assert all(getattr(x, f) == getattr(y, f) for f, _ in _abi.Spec2D._fields_ if f != "contours")
