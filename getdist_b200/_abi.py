@@ -134,7 +134,13 @@ def load():
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
     lib.gdk_hist2d_batch.restype = i32
-    if lib.gdk_abi_version() != 4:
+    lib.gdk_weighted_quantiles_range.argtypes = [vp, vp, i32, vp, i32, i64, i64, vp]
+    lib.gdk_weighted_quantiles_range.restype = i32
+    lib.gdk_weight_fraction_rows.argtypes = [vp, vp, i32, vp]
+    lib.gdk_weight_fraction_rows.restype = i32
+    lib.gdk_histnd.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
+    lib.gdk_histnd.restype = i32
+    if lib.gdk_abi_version() != 5:
         raise GdkError("libgdk.so ABI version mismatch")
     _lib = lib
     return lib
@@ -219,6 +225,32 @@ class Context:
         self._ck(self.lib.gdk_weighted_quantiles(self.h, _ptr(params), params.size, _ptr(fracs), fracs.size, _ptr(out)),
                  "gdk_weighted_quantiles")
         return out
+
+    def weighted_quantiles_range(self, params, fracs, start, end):
+        """order statistics of the rows [start, end) (confidence(..., start=, end=), chains.py:793-838)"""
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        fracs = np.ascontiguousarray(fracs, dtype=np.float64)
+        out = np.empty((params.size, fracs.size))
+        self._ck(self.lib.gdk_weighted_quantiles_range(self.h, _ptr(params), params.size, _ptr(fracs), fracs.size, int(start), int(end),
+                                                       _ptr(out)), "gdk_weighted_quantiles_range")
+        return out
+
+    def weight_fraction_rows(self, fracs):
+        """np.searchsorted(np.cumsum(weights), fracs * sum(weights)) (getFractionIndices, mcsamples.py:668-680)"""
+        fracs = np.ascontiguousarray(fracs, dtype=np.float64)
+        out = np.empty(fracs.size, dtype=np.int64)
+        self._ck(self.lib.gdk_weight_fraction_rows(self.h, _ptr(fracs), fracs.size, _ptr(out)), "gdk_weight_fraction_rows")
+        return out
+
+    def histnd(self, params, nbins, binmin, binmax, which=0):
+        """raw ND histogram, returned with the reference's shape nbins[::-1] (C order: axis 0 of `params` is the fastest)"""
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        nb = np.ascontiguousarray(nbins, dtype=np.int32)
+        lo = np.ascontiguousarray(binmin, dtype=np.float64)
+        hi = np.ascontiguousarray(binmax, dtype=np.float64)
+        out = np.empty(int(np.prod(nb.astype(np.int64))))
+        self._ck(self.lib.gdk_histnd(self.h, params.size, _ptr(params), _ptr(nb), _ptr(lo), _ptr(hi), int(which), _ptr(out)), "gdk_histnd")
+        return out.reshape(tuple(int(n) for n in nb[::-1]))
 
     def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
         n = len(specs)

@@ -184,6 +184,8 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         ctx->shear_sorted = ess && ess[0] == '1';
         const char* ebt = getenv("GDK_BW2D_THREADS");
         if (ebt && (atoi(ebt) == 256 || atoi(ebt) == 512 || atoi(ebt) == 768)) ctx->bw2d_threads = atoi(ebt);
+        const char* enp = getenv("GDK_SHEAR_NP");
+        if (enp && atoi(enp) >= 1 && atoi(enp) <= 6) ctx->shear_np = atoi(enp);
         const char* em = getenv("GDK_SORTED_MIN_N");
         if (em) ctx->sorted_min_n = atoll(em);
     }
@@ -559,8 +561,34 @@ extern "C" int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double
 // -------------------------------------------------------------------------------------------------
 // weighted quantiles
 // -------------------------------------------------------------------------------------------------
-extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf,
-                                          double* out) {
+// segments of the row range [a, b) (interior cuts on even rows), chain index 0
+static std::vector<Seg> make_segments_range(int64_t a, int64_t b, int64_t seglen) {
+    std::vector<Seg> v;
+    seglen = std::max<int64_t>(2, seglen & ~int64_t(1));
+    int64_t r = a;
+    while (r < b) {
+        int64_t e = std::min(b, ((r + seglen) & ~int64_t(1)));
+        if (e <= r) e = b;
+        v.push_back(Seg{r, e, 0, 0});
+        r = e;
+    }
+    return v;
+}
+
+// total fixed-point weight of the rows [a, b)
+static int range_weight(gdk_ctx* ctx, int64_t a, int64_t b, unsigned long long* out) {
+    if (ctx->scratch.ensure(16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
+    CK(cudaMemsetAsync(acc, 0, 8, ctx->stream));
+    k_sum_u64<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->dWq.p + a, b - a, acc);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, acc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int quantiles_impl(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf, int64_t row_begin,
+                          int64_t row_end, double* out) {
     if (!ctx) return GDK_ERR_ARG;
     WallTimer wt{ctx, 2};
     if (!params || !fracs || !out || np <= 0 || nf <= 0 || nf > QMAXF)
@@ -569,6 +597,15 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const int P = ctx->P;
+    const bool ranged = !(row_begin == 0 && row_end == ctx->N);
+    if (row_begin < 0 || row_end > ctx->N || row_begin >= row_end)
+        return gdk_fail(ctx, GDK_ERR_ARG, "gdk_weighted_quantiles_range: bad row range [%lld, %lld)", (long long)row_begin, (long long)row_end);
+    unsigned long long wq_total = ctx->wq_total;
+    if (ranged) {
+        rc = range_weight(ctx, row_begin, row_end, &wq_total);
+        if (rc) return rc;
+        if (wq_total == 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_weighted_quantiles_range: the rows [%lld, %lld) carry no weight", (long long)row_begin, (long long)row_end);
+    }
     for (int i = 0; i < np; i++)
         if (params[i] < 0 || params[i] >= P) return gdk_fail(ctx, GDK_ERR_ARG, "parameter index %d out of range", params[i]);
     const int B1_LOG2 = 13, B2_LOG2 = 10;
@@ -587,11 +624,11 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
             q.state = 1;  // unused slots stay "resolved"
             q.value = 0;
             if (s < nf) {
-                double t = ceil(fracs[s] * (double)ctx->wq_total);
+                double t = ceil(fracs[s] * (double)wq_total);
                 if (!(t >= 1.0)) t = 1.0;
-                if (t > (double)ctx->wq_total) t = (double)ctx->wq_total;
+                if (t > (double)wq_total) t = (double)wq_total;
                 q.target = (unsigned long long)t;
-                if (q.target > ctx->wq_total) q.target = ctx->wq_total;
+                if (q.target > wq_total) q.target = wq_total;
                 if (klo == khi) {
                     q.value = key_to_f64(klo);
                 } else {
@@ -615,8 +652,8 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
     QBase* dqbase = reinterpret_cast<QBase*>(ctx->qbase.p);
     CK(cudaMemcpyAsync(dqbase, qbase.data(), (size_t)np * sizeof(QBase), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 6 / np);
-    const int64_t seglen = std::max<int64_t>(1 << 15, (ctx->N + want - 1) / want);
-    std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+    const int64_t seglen = std::max<int64_t>(1 << 15, (row_end - row_begin + want - 1) / want);
+    std::vector<Seg> segs = ranged ? make_segments_range(row_begin, row_end, seglen) : gdk_make_segments(ctx, seglen);
     rc = gdk_upload_segs(ctx, segs, ctx->segs);
     if (rc) return rc;
     dim3 g((unsigned)segs.size(), (unsigned)np);
@@ -657,6 +694,124 @@ extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, i
             if (q.state != 1) return gdk_fail(ctx, GDK_ERR_STATE, "quantile selection did not converge (param %d, frac %g)", params[i], fracs[s]);
             out[(size_t)i * nf + s] = q.value;
         }
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf,
+                                          double* out) {
+    if (!ctx) return GDK_ERR_ARG;
+    return quantiles_impl(ctx, params, np, fracs, nf, 0, ctx->N, out);
+}
+
+extern "C" int32_t gdk_weighted_quantiles_range(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs, int32_t nf,
+                                                int64_t row_begin, int64_t row_end, double* out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    return quantiles_impl(ctx, params, np, fracs, nf, row_begin, row_end, out);
+}
+
+// getFractionIndices (mcsamples.py:668-680): np.searchsorted(np.cumsum(weights), fracs * norm) -- the first row whose
+// inclusive cumulative weight reaches the target (exact fixed-point sums).  Two levels: per-chunk totals, host prefix over
+// the chunks, then one CTA per target scans its chunk.
+extern "C" int32_t gdk_weight_fraction_rows(gdk_ctx* ctx, const double* fracs, int32_t nf, int64_t* rows_out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (!fracs || !rows_out || nf <= 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_weight_fraction_rows: bad arguments");
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->N;
+    const int nchunk = (int)((N + FRC_CHUNK - 1) / FRC_CHUNK);
+    if (ctx->qhist.ensure((size_t)nchunk + 2 * (size_t)nf + 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "fraction buffers");
+    unsigned long long* dsum = ctx->qhist.p;
+    k_chunk_sums_u64<<<nchunk, 256, 0, ctx->stream>>>(ctx->dWq.p, N, dsum);
+    ctx->launches++;
+    std::vector<unsigned long long> sums(nchunk);
+    CK(cudaMemcpyAsync(sums.data(), dsum, (size_t)nchunk * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned long long> job(2 * (size_t)nf);  // (chunk, remaining target inside the chunk)
+    std::vector<int> direct(nf, 0);
+    for (int i = 0; i < nf; i++) {
+        double t = ceil(fracs[i] * (double)ctx->wq_total);
+        if (!(t > 0)) t = 0;
+        unsigned long long target = t >= (double)ctx->wq_total ? ctx->wq_total : (unsigned long long)t;
+        unsigned long long run = 0;
+        int c = 0;
+        while (c < nchunk - 1 && run + sums[c] < target) run += sums[c++];
+        job[2 * i] = (unsigned long long)c;
+        job[2 * i + 1] = target - run;
+    }
+    unsigned long long* djob = dsum + nchunk;
+    long long* drow = reinterpret_cast<long long*>(djob + 2 * (size_t)nf);
+    CK(cudaMemcpyAsync(djob, job.data(), job.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_fraction_rows<<<nf, 256, 0, ctx->stream>>>(ctx->dWq.p, N, djob, drow);
+    ctx->launches++;
+    std::vector<long long> rows(nf);
+    CK(cudaMemcpyAsync(rows.data(), drow, (size_t)nf * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (int i = 0; i < nf; i++) rows_out[i] = rows[i];
+    return GDK_OK;
+}
+
+// raw ND histogram: _binSamples per axis + _makeNDhist (mcsamples.py:1486-1498, 2065-2079); axis 0 is the fastest index
+extern "C" int32_t gdk_histnd(gdk_ctx* ctx, int32_t ndim, const int32_t* params, const int32_t* nbins, const double* binmin,
+                              const double* binmax, int32_t which, double* out) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (ndim < 1 || ndim > HND_MAXD || !params || !nbins || !binmin || !binmax || !out || which < 0 || which > 2)
+        return gdk_fail(ctx, GDK_ERR_ARG, "gdk_histnd: need 1 <= ndim <= %d", HND_MAXD);
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    if (which != 0 && !ctx->have_loglikes) return gdk_fail(ctx, GDK_ERR_STATE, "gdk_histnd: mean / max likelihoods need gdk_set_loglikes");
+    CK(cudaSetDevice(ctx->device));
+    HistNdJob jb{};
+    jb.ndim = ndim;
+    size_t total = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (params[d] < 0 || params[d] >= ctx->P) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_histnd: parameter %d out of range", params[d]);
+        if (nbins[d] < 2 || !(binmax[d] > binmin[d])) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_histnd: bad geometry for axis %d", d);
+        jb.param[d] = params[d];
+        jb.n[d] = nbins[d];
+        jb.stride[d] = (long long)total;
+        jb.binmin[d] = binmin[d];
+        jb.fw[d] = (binmax[d] - binmin[d]) / (nbins[d] - 1);
+        jb.inv[d] = 1.0 / jb.fw[d];
+        total *= (size_t)nbins[d];
+        if (total > ((size_t)1 << 28)) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "gdk_histnd: more than 2^28 bins");
+    }
+    if (ctx->gbins.ensure(total)) return gdk_fail(ctx, GDK_ERR_NOMEM, "ND histogram");
+    CK(cudaMemsetAsync(ctx->gbins.p, 0, total * 8, ctx->stream));
+    double shift = 0;
+    if (which == 2) {  // profile likelihood: max over the bin of exp(-bestfit - loglike), bestfit = max(-loglike)
+        const int nb = ctx->num_sms * 4;
+        if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+        k_wstats<<<nb, 256, 0, ctx->stream>>>(ctx->dLL.p, ctx->N, ctx->scratch.p);
+        ctx->launches++;
+        std::vector<double> part((size_t)nb * 4);
+        CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        double mn = INFINITY;
+        for (int i = 0; i < nb; i++) mn = std::min(mn, part[i * 4 + 3]);
+        shift = mn;  // exp(-bestfit - loglike) = exp(min(loglike) - loglike)
+    }
+    const size_t smem = total * 8 <= (size_t)ctx->max_smem - 4096 && which != 2 ? total * 8 : 0;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_histnd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = (int64_t)ctx->num_sms * 2;
+    std::vector<Seg> segs = gdk_make_segments(ctx, std::max<int64_t>(1 << 14, (ctx->N + want - 1) / want));
+    int rc = gdk_upload_segs(ctx, segs, ctx->segs);
+    if (rc) return rc;
+    k_histnd<<<(unsigned)segs.size(), 512, smem, ctx->stream>>>(ctx->dX.p, ctx->ld, which == 1 ? ctx->dWlq.p : ctx->dWq.p,
+                                                              which == 2 ? ctx->dLL.p : nullptr, shift, ctx->segs.p, jb, (int)total,
+                                                              smem ? 1 : 0, ctx->gbins.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (ctx->fbuf.ensure(total)) return gdk_fail(ctx, GDK_ERR_NOMEM, "ND histogram output");
+    if (which == 2) {
+        CK(cudaMemcpyAsync(out, ctx->gbins.p, total * 8, cudaMemcpyDeviceToHost, ctx->stream));  // bit patterns of doubles
+    } else {
+        k_bins_to_f64<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->gbins.p, ctx->fbuf.p, (int64_t)total,
+                                                                1.0 / (which == 1 ? ctx->wlscale : ctx->wscale));
+        ctx->launches++;
+        CK(cudaMemcpyAsync(out, ctx->fbuf.p, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
     return GDK_OK;
 }
 

@@ -559,8 +559,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                     };
                     want(a.pi);
                     for (int jb : a.jobs) want(sjobs[jb].pj);
+                    const int nu = ((int)a.jobs.size() + 3) / 4;  // units of <= 4 pairs (k_shear_minmax_tma)
                     if (cur.njobs && (cols.size() + add.size() > (size_t)SHR_MAXCOLS || cur.njobs == SHR_MAXJOBS ||
-                                      cur.npairs + (int)a.jobs.size() > 16 * SHR_MAXPW)) {
+                                      cur.npairs + (int)a.jobs.size() > 16 * SHR_MAXPW || cur.nunits + nu > SHR_MAXUNITS)) {
                         close();
                         add.clear();
                         want(a.pi);
@@ -576,6 +577,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                     rj.acol = col_of(a.pi);
                     rj.np = (int)a.jobs.size();
                     rj.pair0 = (int)prefs.size() - cur.pair0;
+                    for (int u = 0; u < nu; u++) {  // balanced split: 9 partners -> 3 + 3 + 3
+                        const int cnt = (int)a.jobs.size(), b0 = cnt * u / nu, b1 = cnt * (u + 1) / nu;
+                        cur.ufirst[cur.nunits] = (short)(rj.pair0 + b0);
+                        cur.unp[cur.nunits] = (unsigned char)(b1 - b0);
+                        cur.uacol[cur.nunits] = (unsigned char)rj.acol;
+                        cur.nunits++;
+                    }
                     rj.p1_min = a.p1_min;
                     rj.dx1 = a.dx1;
                     rj.inv1s = a.inv1 * 1048576.0;
@@ -643,10 +651,21 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             dim3 gm((unsigned)nseg, (unsigned)nbatch);
             {
                 double colsum = 0;
-                for (const ShearBatch& b : batches) colsum += b.ncols;
+                size_t tma_smem = 0;
+                for (const ShearBatch& b : batches) {
+                    colsum += b.ncols;
+                    tma_smem = std::max(tma_smem, (size_t)SHM_STAGES * b.ncols * SHR_ROWS * 8 + (size_t)b.npairs * sizeof(ShearPairRef));
+                }
+                bool aligned = !shear_sorted && tma_smem + 2048 <= (size_t)ctx->max_smem;  // bulk copies need 16-byte aligned tiles
+                for (const Seg& sgm : segs) aligned = aligned && ((sgm.r0 & 1) == 0);
                 KernelTimer kt(ctx, GDK_K_SHEAR_MINMAX, (double)ctx->N * colsum * 8.0, (double)ctx->N * nshear * 3.0);
-                k_shear_minmax_tiled<<<gm, SHR_ROWS, mm_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dbat, drj, dpr, part,
-                                                                             shear_sorted ? counts : nullptr);
+                if (aligned) {
+                    CK2(cudaFuncSetAttribute(k_shear_minmax_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tma_smem, 48 << 10)));
+                    k_shear_minmax_tma<<<gm, 544, tma_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dbat, dpr, part);
+                } else {
+                    k_shear_minmax_tiled<<<gm, SHR_ROWS, mm_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dbat, drj, dpr, part,
+                                                                                 shear_sorted ? counts : nullptr);
+                }
             }
             k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
             ctx->launches += 2;
@@ -691,66 +710,100 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             CK2(cudaGetLastError());
         }
         if (!shear_sorted) {
-        // groups of jobs sharing (p1 column, p1 geometry, grid size): x_i is read once per row for the group
+        // groups of jobs sharing (p1 column, p1 geometry, grid size): x_i is read once per row for the group.  An anchor's
+        // partners are split into balanced groups of <= shear_np jobs (9 partners -> 3 + 3 + 3): the fewer jobs a group
+        // has, the larger the shared-memory window each of them gets (k_shear_hist_w)
         std::vector<ShearGroup> sgroups;
-        for (int k = 0; k < nshear; k++) {
-            const ShearJob& j = sjobs[ord[k]];
-            bool fresh = sgroups.empty();
-            if (!fresh) {
-                const ShearGroup& g = sgroups.back();
-                fresh = g.nj == SG || g.pi != j.pi || g.Gb != j.Gb || g.p1_min != j.p1_min || g.dx1 != j.dx1;
-            }
-            if (fresh) {
+        const int npmax = std::max(1, std::min(SG, ctx->shear_np));
+        for (int k = 0; k < nshear;) {
+            const ShearJob& j0 = sjobs[ord[k]];
+            int e = k;
+            while (e < nshear && sjobs[ord[e]].pi == j0.pi && sjobs[ord[e]].Gb == j0.Gb && sjobs[ord[e]].p1_min == j0.p1_min &&
+                   sjobs[ord[e]].dx1 == j0.dx1)
+                e++;
+            const int cnt = e - k, ng = (cnt + npmax - 1) / npmax;
+            for (int gi = 0; gi < ng; gi++) {
+                const int b0 = k + (int)((long long)cnt * gi / ng), b1 = k + (int)((long long)cnt * (gi + 1) / ng);
                 ShearGroup g{};
-                g.pi = j.pi;
-                g.Gb = j.Gb;
-                g.p1_min = j.p1_min;
-                g.dx1 = j.dx1;
-                g.inv1 = j.inv1;
+                g.pi = j0.pi;
+                g.Gb = j0.Gb;
+                g.p1_min = j0.p1_min;
+                g.dx1 = j0.dx1;
+                g.inv1 = j0.inv1;
+                g.mean1 = ctx->means[j0.pi];
+                for (int q = b0; q < b1; q++) {
+                    const ShearJob& j = sjobs[ord[q]];
+                    g.mean2[g.nj] = j.r0 * ctx->means[j.pi] + j.r1 * ctx->means[j.pj];
+                    g.pj[g.nj] = j.pj;
+                    g.job[g.nj] = ord[q];
+                    g.r0[g.nj] = j.r0;
+                    g.r1[g.nj] = j.r1;
+                    g.off[g.nj] = j.off;
+                    g.nj++;
+                }
                 sgroups.push_back(g);
             }
-            ShearGroup& g = sgroups.back();
-            g.mean1 = ctx->means[j.pi];
-            g.mean2[g.nj] = j.r0 * ctx->means[j.pi] + j.r1 * ctx->means[j.pj];
-            g.pj[g.nj] = j.pj;
-            g.job[g.nj] = ord[k];
-            g.r0[g.nj] = j.r0;
-            g.r1[g.nj] = j.r1;
-            g.off[g.nj] = j.off;
-            g.nj++;
+            k = e;
         }
+        // one launch per group size: order by size (stable: neighbouring anchors stay neighbours -> shared columns hit L2)
+        std::stable_sort(sgroups.begin(), sgroups.end(), [](const ShearGroup& a, const ShearGroup& b) { return a.nj > b.nj; });
         ShearGroup* dsg = nullptr;
         rc = upload_vec(ctx, sgroups, ctx->bytes2d_c, &dsg);
         if (rc) return rc;
         const int ngroups = (int)sgroups.size();
-        // fine segments (fast grid index) keep the <= 8 grids of a group L2-resident for the reductions
-        const int64_t want = std::max<int64_t>((int64_t)ctx->num_sms * 8 / ngroups + 1, std::min<int64_t>((int64_t)ctx->num_sms * 6, 64));
-        const int64_t seglen = std::max<int64_t>(1 << 16, (ctx->N + want - 1) / want);  // long: amortises the window flush
-        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
-        rc = gdk_upload_segs(ctx, segs, ctx->segs);
-        if (rc) return rc;
-        const int nseg = (int)segs.size();
         PhaseTimer pt;
-        dim3 g((unsigned)nseg, (unsigned)ngroups);
         if (!geom_done) {
+            const int64_t want = std::max<int64_t>((int64_t)ctx->num_sms * 8 / ngroups + 1, std::min<int64_t>((int64_t)ctx->num_sms * 6, 64));
+            const int64_t seglen = std::max<int64_t>(1 << 16, (ctx->N + want - 1) / want);
+            std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
+            rc = gdk_upload_segs(ctx, segs, ctx->segs);
+            if (rc) return rc;
+            const int nseg = (int)segs.size();
             if (ctx->scratch.ensure((size_t)nshear * nseg * 2 + (size_t)nshear * 4 + 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "shear scratch");
             double* part = ctx->scratch.p;
             dgeom = reinterpret_cast<ShearGeom*>(ctx->scratch.p + (((size_t)nshear * nseg * 2 + 3) & ~size_t(3)));
             pt.begin(ctx, GDK_PH_SHEAR);
+            dim3 g((unsigned)nseg, (unsigned)ngroups);
             k_shear_minmax<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->segs.p, nseg, dsg, part);
             k_shear_geom<<<(nshear + 127) / 128, 128, 0, ctx->stream>>>(part, nseg, nshear, dsj, dgeom);
+            ctx->launches += 2;
         } else {
             pt.resume(ctx, GDK_PH_SHEAR);
         }
-        const size_t sh_smem = (size_t)SG * 2 * HW * HW * 4;
-        CK2(cudaFuncSetAttribute(k_shear_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_smem));
-        {
+        // long segments amortise the window flush (<= NP * W^2 reductions per CTA)
+        const int64_t wantseg = std::max<int64_t>(1, std::min<int64_t>(ctx->N / (1 << 18), 4096));
+        std::vector<Seg> hsegs = gdk_make_segments(ctx, (ctx->N + wantseg - 1) / wantseg);
+        rc = gdk_upload_segs(ctx, hsegs, ctx->segs2);
+        if (rc) return rc;
+        Seg* dhsegs = ctx->segs2.p;
+        const int nhseg = (int)hsegs.size();
+        for (int g0 = 0; g0 < ngroups;) {
+            int g1 = g0;
+            while (g1 < ngroups && sgroups[g1].nj == sgroups[g0].nj) g1++;
+            const int nj = sgroups[g0].nj;
             double colsum = 0;  // per group: x_i + nj partner columns + the weights
-            for (const ShearGroup& sgp : sgroups) colsum += 2.0 + sgp.nj;
-            KernelTimer kt(ctx, GDK_K_SHEAR_HIST, (double)ctx->N * colsum * 8.0, (double)ctx->N * nshear * 3.0);
-            k_shear_hist<<<g, 1024, sh_smem, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, dsg, dgeom, ctx->gbins_rot.p);
+            for (int q = g0; q < g1; q++) colsum += 2.0 + sgroups[q].nj;
+            KernelTimer kt(ctx, GDK_K_SHEAR_HIST, (double)ctx->N * colsum * 8.0, (double)ctx->N * (g1 - g0) * nj * 3.0);
+            dim3 g((unsigned)(g1 - g0), (unsigned)nhseg);
+#define GDK_LAUNCH_SHW(NP_, W_)                                                                                               \
+    case NP_: {                                                                                                               \
+        const size_t sm_ = (size_t)NP_ * 2 * W_ * W_ * 4;                                                                     \
+        CK2(cudaFuncSetAttribute(k_shear_hist_w<NP_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));            \
+        k_shear_hist_w<NP_, W_><<<g, 512, sm_, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, dhsegs, dsg + g0, dgeom,        \
+                                                               ctx->gbins_rot.p);                                            \
+    } break;
+            switch (nj) {
+                GDK_LAUNCH_SHW(1, 128)
+                GDK_LAUNCH_SHW(2, 112)
+                GDK_LAUNCH_SHW(3, 96)
+                GDK_LAUNCH_SHW(4, 80)
+                GDK_LAUNCH_SHW(5, 72)
+                GDK_LAUNCH_SHW(6, 64)
+            }
+#undef GDK_LAUNCH_SHW
+            ctx->launches++;
+            g0 = g1;
         }
-        ctx->launches += 3;
         pt.end();
         CK2(cudaGetLastError());
         }

@@ -317,3 +317,51 @@ __global__ void __launch_bounds__(256) k_kde1d(const gdk_spec1d* __restrict__ sp
     CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
     kde1d_core(co, sp, K, W, P_out + (int64_t)i * pstride, res + i);
 }
+
+// ---- raw ND histogram (getRawNDDensityGridData, mcsamples.py:2098-2166: _binSamples per axis + _makeNDhist) ----------
+#define HND_MAXD 8
+struct HistNdJob {
+    int ndim, pad;
+    int param[HND_MAXD], n[HND_MAXD];
+    long long stride[HND_MAXD];  // axis 0 is the fastest index (flat = sum ix_d * stride_d, mcsamples.py:2034-2046)
+    double binmin[HND_MAXD], fw[HND_MAXD], inv[HND_MAXD];
+};
+// grid (nseg), 512 threads.  use_smem: privatised two-limb bins in shared memory (total * 8 bytes), flushed with u64
+// reductions; otherwise straight L2 reductions.  ll != NULL: profile likelihood -- per-bin maximum of
+// exp(shift - loglike) kept as the bit pattern of a non-negative double (order preserving) with atomicMax.
+__global__ void __launch_bounds__(512) k_histnd(const double* __restrict__ dX, int64_t ld, const unsigned long long* __restrict__ wq,
+                                                const double* __restrict__ ll, double shift, const Seg* __restrict__ segs, HistNdJob jb,
+                                                int total, int use_smem, unsigned long long* __restrict__ gbins) {
+    extern __shared__ unsigned nsm[];
+    if (use_smem) {
+        for (int i = threadIdx.x; i < 2 * total; i += blockDim.x) nsm[i] = 0;
+        __syncthreads();
+    }
+    const Seg sg = segs[blockIdx.x];
+    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
+        long long flat = 0;
+        bool ok = true;
+        for (int d = 0; d < jb.ndim; d++) {
+            const int b = bin_index_round(ldg_stream(dX + (int64_t)jb.param[d] * ld + r), jb.binmin[d], jb.fw[d], jb.inv[d]);
+            ok = ok && b >= 0 && b < jb.n[d];
+            flat += (long long)b * jb.stride[d];
+        }
+        if (!ok) continue;
+        if (ll) {
+            const double v = exp(shift - ll[r]);
+            atomicMax(gbins + flat, (unsigned long long)__double_as_longlong(v));
+        } else if (use_smem) {
+            smem_add_u64(nsm + flat, nsm + total + flat, wq[r]);
+        } else {
+            const unsigned long long w = wq[r];
+            if (w) atomicAdd(gbins + flat, w);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const unsigned long long v = ((unsigned long long)nsm[total + i] << 32) | nsm[i];
+            if (v) atomicAdd(gbins + i, v);
+        }
+    }
+}

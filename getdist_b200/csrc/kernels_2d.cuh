@@ -102,7 +102,7 @@ __device__ __forceinline__ double shear_p2(double xi, double xj, double r0, doub
 }
 
 // Jobs that share their p1 column are processed together: x_i is read once per row for up to SG jobs.
-#define SG 4  // four jobs per group: four 64 x 64 shared-memory windows in k_shear_hist
+#define SG 6  // max jobs per group (k_shear_hist_w<NP, W>: NP <= SG windows of W x W bins in shared memory)
 struct ShearGroup {
     int pi, nj, Gb, pad;
     int pj[SG], job[SG];
@@ -186,70 +186,190 @@ __global__ void k_shear_geom(const double* __restrict__ part, int nseg, int njob
     geom[j] = ShearGeom{rmin, dx, 1.0 / dx, R};
 }
 
-// grid (nseg, ngroups), 1024 threads, dynamic smem = SG * HW*HW * 8 bytes.  Same hot-window privatisation as
-// k_hist2d_hot: each job keeps the HW x HW bins around the centre of its sheared cloud in shared memory.
-__global__ void __launch_bounds__(1024) k_shear_hist(const double* __restrict__ dX, int64_t ld,
-                                                     const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
-                                                     const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
-                                                     unsigned long long* __restrict__ grids) {
-    extern __shared__ unsigned ssm2[];  // per job: lo[HW*HW], hi[HW*HW]
+// Sheared re-binning (kde.bin_samples of (p1, r0*x_i + r1*x_j), kde_bandwidth.py:76-87) with hot-window privatisation:
+// grid (ngroups, nseg) -- GROUPS are the fast grid index, so the CTAs resident at one time sweep the same row
+// segment and the columns they share (an anchor's x_i, the partners it shares with neighbouring anchors) come out
+// of L2 instead of DRAM.  512 threads, one CTA per SM, dynamic smem = NP * W*W * 8 bytes: every job of the group
+// keeps the W x W bins around the centre of its sheared cloud in shared memory (two 32-bit limbs per bin, native
+// ATOMS); the few samples outside the window go to L2 reductions.  NP = partners of the group (exactly; the host
+// launches one instantiation per group size), W = window edge for that size (3 x 96^2, 4 x 80^2, 6 x 64^2 ... fill
+// the 227 KB of an SM).  Per-partner constants live in registers, rows are read two at a time with 16-byte loads and
+// prefetched one iteration ahead.
+template <int NP, int W>
+__global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restrict__ dX, int64_t ld,
+                                                         const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
+                                                         const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
+                                                         unsigned long long* __restrict__ grids) {
+    extern __shared__ unsigned ssm2[];  // per job: lo[W*W], hi[W*W]
     __shared__ ShearGroup g;
     __shared__ ShearGeom gm[SG];
-    __shared__ int ax0, by0[SG];
+    __shared__ int s_ax0, s_by0[SG];
     {
-        const int* src = reinterpret_cast<const int*>(groups + blockIdx.y);
+        const int* src = reinterpret_cast<const int*>(groups + blockIdx.x);
         int* dst = reinterpret_cast<int*>(&g);
         for (int i = threadIdx.x; i < (int)(sizeof(ShearGroup) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = threadIdx.x; i < SG * 2 * HW * HW; i += blockDim.x) ssm2[i] = 0;
+    for (int i = threadIdx.x; i < NP * 2 * W * W; i += blockDim.x) ssm2[i] = 0;
     __syncthreads();
-    const int G = g.Gb, nj = g.nj;
-    if (threadIdx.x < nj) {
+    const int G = g.Gb;
+    if (threadIdx.x < NP) {
         gm[threadIdx.x] = geom[g.job[threadIdx.x]];
-        const int c = bin_index_trunc(g.mean2[threadIdx.x], gm[threadIdx.x].rmin, gm[threadIdx.x].dx, gm[threadIdx.x].inv) - HW / 2;
-        by0[threadIdx.x] = max(0, min(G - HW, c));
+        const int c = bin_index_trunc(g.mean2[threadIdx.x], gm[threadIdx.x].rmin, gm[threadIdx.x].dx, gm[threadIdx.x].inv) - W / 2;
+        s_by0[threadIdx.x] = max(0, min(G - W, c));
     }
     if (threadIdx.x == 0) {
-        const int c = bin_index_trunc(g.mean1, g.p1_min, g.dx1, g.inv1) - HW / 2;
-        ax0 = max(0, min(G - HW, c));
+        const int c = bin_index_trunc(g.mean1, g.p1_min, g.dx1, g.inv1) - W / 2;
+        s_ax0 = max(0, min(G - W, c));
     }
     __syncthreads();
-    const bool hot = G >= HW;
+    const unsigned wlim = G >= W ? (unsigned)W : 0u;  // grids smaller than the window: everything takes the L2 path
     unsigned smem0 = (unsigned)__cvta_generic_to_shared(ssm2);
     asm volatile("mov.u32 %0, %0;" : "+r"(smem0));  // opaque: stays in a register (see k_hist2d_hot)
-    const Seg sg = segs[blockIdx.x];
-    const double* xi = dX + (int64_t)g.pi * ld;
+    const Seg sg = segs[blockIdx.y];
     const double p1_min = g.p1_min, dx1 = g.dx1, inv1s = g.inv1 * 1048576.0;
-    for (int64_t r = sg.r0 + threadIdx.x; r < sg.r1; r += blockDim.x) {
-        const double a = ldg_stream(xi + r);
-        const unsigned long long w = dWq[r];
-        double b[SG];
+    const int ax0 = s_ax0;
+    double r0[NP], r1[NP], rmin[NP], invs[NP];
+    int by0[NP];
+    const double* xj[NP];
 #pragma unroll
-        for (int k = 0; k < SG; k++)
-            if (k < nj) b[k] = ldg_stream(dX + (int64_t)g.pj[k] * ld + r);
-        const int b1 = bin_index_trunc_fx(a, p1_min, dx1, inv1s);
-        if (w == 0 || b1 < 0 || b1 >= G) continue;
-        const unsigned dx = (unsigned)(b1 - ax0);
+    for (int k = 0; k < NP; k++) {
+        r0[k] = g.r0[k];
+        r1[k] = g.r1[k];
+        rmin[k] = gm[k].rmin;
+        invs[k] = gm[k].inv * 1048576.0;
+        by0[k] = s_by0[k];
+        xj[k] = dX + (int64_t)g.pj[k] * ld;
+    }
+    const double* xi = dX + (int64_t)g.pi * ld;
+    unsigned long long* gk[NP];
 #pragma unroll
-        for (int k = 0; k < SG; k++)
-            if (k < nj) {
-                const int b2 = bin_index_trunc_fx(shear_p2(a, b[k], g.r0[k], g.r1[k]), gm[k].rmin, gm[k].dx, gm[k].inv * 1048576.0);
-                if (b2 < 0 || b2 >= G) continue;
-                const unsigned dy = (unsigned)(b2 - by0[k]);
-                if (hot && (dx | dy) < (unsigned)HW) {
-                    smem_add_u64_addr(smem0 + (unsigned)k * (2u * HW * HW * 4u) + ((dy * HW + dx) << 2), HW * HW * 4u, w);
-                } else {
-                    atomicAdd(grids + g.off[k] + (long long)b2 * G + b1, w);
-                }
+    for (int k = 0; k < NP; k++) gk[k] = grids + g.off[k];
+    // Two rows (2 * NP updates) at a time, written for instruction-level parallelism: all bin indices first (branch
+    // free; the exact division is a rare fix-up of the whole group), then all low-limb ATOMS back to back, then the
+    // carries into the high limbs, then the few out-of-window samples as L2 reductions.
+    auto update2 = [&](double a0, double a1, unsigned long long w0, unsigned long long w1, const double (&bx)[NP], const double (&by)[NP],
+                       bool second) {
+        const double d10 = __dsub_rn(a0, p1_min), d11 = __dsub_rn(a1, p1_min);
+        const unsigned I10 = __double2uint_rd(__dmul_rn(d10, inv1s)), I11 = __double2uint_rd(__dmul_rn(d11, inv1s));
+        auto edge = [](unsigned I) { return ((I & 0xfffffu) - 8u) >= (0xfffffu - 15u); };  // within 8 * 2^-20 of a bin edge / saturated
+        bool bad = edge(I10) | edge(I11);
+        double d2[2][NP];
+        unsigned I2[2][NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            d2[0][k] = __dsub_rn(shear_p2(a0, bx[k], r0[k], r1[k]), rmin[k]);
+            d2[1][k] = __dsub_rn(shear_p2(a1, by[k], r0[k], r1[k]), rmin[k]);
+            I2[0][k] = __double2uint_rd(__dmul_rn(d2[0][k], invs[k]));
+            I2[1][k] = __double2uint_rd(__dmul_rn(d2[1][k], invs[k]));
+            bad |= edge(I2[0][k]) | edge(I2[1][k]);
+        }
+        int b1[2] = {(int)(I10 >> 20), (int)(I11 >> 20)};
+        int b2[2][NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            b2[0][k] = (int)(I2[0][k] >> 20);
+            b2[1][k] = (int)(I2[1][k] >> 20);
+        }
+        if (__builtin_expect(bad, 0)) {  // some index sits on a bin edge: the exact IEEE division decides (kde_bandwidth.py:85-87)
+            if (edge(I10)) b1[0] = bin_index_trunc_exact(d10, dx1);
+            if (edge(I11)) b1[1] = bin_index_trunc_exact(d11, dx1);
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                if (edge(I2[0][k])) b2[0][k] = bin_index_trunc_exact(d2[0][k], gm[k].dx);
+                if (edge(I2[1][k])) b2[1][k] = bin_index_trunc_exact(d2[1][k], gm[k].dx);
             }
+        }
+        const unsigned dxr[2] = {(unsigned)(b1[0] - ax0), (unsigned)(b1[1] - ax0)};
+        const unsigned wl[2] = {(unsigned)w0, (unsigned)w1}, wh[2] = {(unsigned)(w0 >> 32), (unsigned)(w1 >> 32)};
+        unsigned addr[2][NP], hit[2][NP], old[2][NP];
+        unsigned miss = 0;
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const unsigned dy = (unsigned)(b2[r][k] - by0[k]);
+                hit[r][k] = (max(dxr[r], dy) < wlim) & (unsigned)(r == 0 || second);
+                miss |= hit[r][k] ^ 1u;
+                addr[r][k] = smem0 + (unsigned)k * (2u * W * W * 4u) + dy * (4u * W) + (dxr[r] << 2);
+                old[r][k] = 0;
+            }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < NP; k++)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+                             : "+r"(old[r][k])
+                             : "r"(addr[r][k]), "r"(wl[r]), "r"(hit[r][k]));
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                unsigned c;
+                asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(c) : "r"(old[r][k]), "r"(wl[r]), "r"(wh[r]));
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr[r][k] + W * W * 4u),
+                             "r"(c), "r"(hit[r][k]));
+            }
+        if (miss) {
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int k = 0; k < NP; k++)
+                    if (!hit[r][k] && (r == 0 || second) && (unsigned)b1[r] < (unsigned)G && (unsigned)b2[r][k] < (unsigned)G && (r ? w1 : w0))
+                        atomicAdd(gk[k] + b2[r][k] * G + b1[r], r ? w1 : w0);
+        }
+    };
+    // segments start on even rows (16-byte aligned pairs); an odd tail row is handled by thread 0
+    const int64_t npair = (sg.r1 - sg.r0) >> 1;
+    int64_t i = threadIdx.x;
+    double2 a2, b2v[NP];
+    ulonglong2 w2;
+    if (i < npair) {
+        a2 = ldg_stream2(xi + sg.r0 + 2 * i);
+        w2 = ldg_stream2_u64(dWq + sg.r0 + 2 * i);
+#pragma unroll
+        for (int k = 0; k < NP; k++) b2v[k] = ldg_stream2(xj[k] + sg.r0 + 2 * i);
+    }
+    while (i < npair) {
+        const int64_t in = i + blockDim.x;
+        double2 an, bn[NP];
+        ulonglong2 wn;
+        if (in < npair) {  // next pair of rows in flight while this one is binned
+            an = ldg_stream2(xi + sg.r0 + 2 * in);
+            wn = ldg_stream2_u64(dWq + sg.r0 + 2 * in);
+#pragma unroll
+            for (int k = 0; k < NP; k++) bn[k] = ldg_stream2(xj[k] + sg.r0 + 2 * in);
+        }
+        {
+            double bx[NP], by[NP];
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                bx[k] = b2v[k].x;
+                by[k] = b2v[k].y;
+            }
+            update2(a2.x, a2.y, w2.x, w2.y, bx, by, true);
+        }
+        a2 = an;
+        w2 = wn;
+#pragma unroll
+        for (int k = 0; k < NP; k++) b2v[k] = bn[k];
+        i = in;
+    }
+    if (((sg.r1 - sg.r0) & 1) && threadIdx.x == 0) {
+        const int64_t r = sg.r1 - 1;
+        double bx[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) bx[k] = xj[k][r];
+        update2(xi[r], xi[r], dWq[r], 0ull, bx, bx, false);
     }
     __syncthreads();
-    if (!hot) return;
-    for (int k = 0; k < nj; k++) {
-        const unsigned* base = ssm2 + k * 2 * HW * HW;
-        for (int i = threadIdx.x; i < HW * HW; i += blockDim.x) {
-            const unsigned long long v = ((unsigned long long)base[HW * HW + i] << 32) | base[i];
-            if (v) atomicAdd(grids + g.off[k] + (long long)(by0[k] + i / HW) * G + ax0 + (i % HW), v);
+    if (!wlim) return;
+#pragma unroll 1
+    for (int k = 0; k < NP; k++) {
+        const unsigned* base = ssm2 + k * 2 * W * W;
+        unsigned long long* gk = grids + g.off[k] + (long long)by0[k] * G + ax0;
+        for (int t = threadIdx.x; t < W * W; t += blockDim.x) {
+            const unsigned long long v = ((unsigned long long)base[W * W + t] << 32) | base[t];
+            if (v) atomicAdd(gk + (long long)(t / W) * G + (t % W), v);
         }
     }
 }
@@ -1663,10 +1783,14 @@ struct ShearRecJob {  // one anchor (p1 column + geometry) with <= 32 partners
     int acol, np, pair0, pad;  // tile column of p1, partners, first ShearPairRef of this anchor (consecutive)
     double p1_min, dx1, inv1s;  // inv1s = 2^20 / dx1
 };
+#define SHR_MAXUNITS 32  // k_shear_minmax_tma: 16 warps x 2 units of <= 4 pairs that share their p1 column
 struct ShearBatch {
     int ncols, njobs, npairs, job0;  // job0: index of the batch's first anchor (row of counts / start / cursor)
-    int pair0, pad[3];                // first ShearPairRef of the batch
+    int pair0, nunits, pad[2];        // first ShearPairRef of the batch; units of k_shear_minmax_tma
     int cols[SHR_MAXCOLS];            // parameter (column of dX) per tile column
+    short ufirst[SHR_MAXUNITS];       // unit -> first pair (index inside the batch), its pairs are consecutive
+    unsigned char unp[SHR_MAXUNITS];  // unit -> number of pairs (1..4)
+    unsigned char uacol[SHR_MAXUNITS];  // unit -> tile column of p1
 };
 
 // grid (nseg, nbatches), 512 threads.  dynamic smem: ncols * SHR_ROWS * 8 (tile) + npairs * 32 (pair table) +
@@ -1755,6 +1879,145 @@ __global__ void __launch_bounds__(512) k_shear_minmax_tiled(const double* __rest
         __syncthreads();
         for (int i = threadIdx.x; i < B.njobs * 256; i += blockDim.x)
             if (cnt[i]) atomicAdd(counts + (size_t)B.job0 * 256 + i, cnt[i]);
+    }
+}
+
+// TMA-pipelined form of the min / max pass (default when every segment starts on an even row): the row tiles
+// (<= SHR_MAXCOLS columns x SHR_ROWS rows of float64) are staged through a SHM_STAGES-deep shared-memory ring by bulk
+// async copies (cp.async.bulk -> UBLKCP) with full / empty mbarriers, so the next tile lands while the current one is
+// evaluated.  A warp owns two UNITS = (p1 column, <= 4 partners): x_i is read once per row and unit, the partners'
+// r0 / r1 and the running min / max stay in registers across all tiles of the segment (11 instructions per
+// pair-sample, 5 of them on the FP64 pipe, which is what bounds the pass once the loads are off the critical path).
+// grid (nseg, nbatches), 544 threads (16 consumer warps + 1 producer warp), one CTA per SM;
+// dynamic smem: SHM_STAGES * ncols * SHR_ROWS * 8 + npairs * 32.
+#define SHM_STAGES 2
+template <int NPU>
+__device__ __forceinline__ void shear_mm_unit(const double* __restrict__ tl, const ShearPairRef* __restrict__ pr, int acol, int lane,
+                                              int nrow, double (&mn)[4], double (&mx)[4]) {
+    double r0[NPU], r1[NPU];
+    const double* xj[NPU];
+#pragma unroll
+    for (int k = 0; k < NPU; k++) {
+        r0[k] = pr[k].r0;
+        r1[k] = pr[k].r1;
+        xj[k] = tl + pr[k].pcol * SHR_ROWS + lane;
+    }
+    const double* xi = tl + acol * SHR_ROWS + lane;
+    if (nrow == SHR_ROWS) {
+#pragma unroll
+        for (int m = 0; m < SHR_ROWS / 32; m++) {
+            const double a = xi[32 * m];
+#pragma unroll
+            for (int k = 0; k < NPU; k++) {
+                const double p2 = shear_p2(a, xj[k][32 * m], r0[k], r1[k]);
+                mn[k] = p2 < mn[k] ? p2 : mn[k];  // finite samples: plain compares, not the NaN-aware fmin / fmax
+                mx[k] = p2 > mx[k] ? p2 : mx[k];
+            }
+        }
+    } else {
+        for (int t = lane; t < nrow; t += 32) {
+            const double a = xi[t - lane];
+#pragma unroll
+            for (int k = 0; k < NPU; k++) {
+                const double p2 = shear_p2(a, xj[k][t - lane], r0[k], r1[k]);
+                mn[k] = p2 < mn[k] ? p2 : mn[k];
+                mx[k] = p2 > mx[k] ? p2 : mx[k];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(544, 1) k_shear_minmax_tma(const double* __restrict__ dX, int64_t ld, const Seg* __restrict__ segs,
+                                                             int nseg, const ShearBatch* __restrict__ batches,
+                                                             const ShearPairRef* __restrict__ pairs, double* __restrict__ part) {
+    extern __shared__ __align__(128) unsigned char msm[];
+    __shared__ ShearBatch B;
+    __shared__ __align__(8) unsigned long long full[SHM_STAGES], empty[SHM_STAGES];
+    {
+        const int* src = reinterpret_cast<const int*>(batches + blockIdx.y);
+        int* dst = reinterpret_cast<int*>(&B);
+        for (int i = threadIdx.x; i < (int)(sizeof(ShearBatch) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int ncols = B.ncols;
+    double* tile = reinterpret_cast<double*>(msm);                                                      // [stage][ncols][SHR_ROWS]
+    ShearPairRef* sp = reinterpret_cast<ShearPairRef*>(tile + (size_t)SHM_STAGES * ncols * SHR_ROWS);   // [npairs]
+    for (int i = threadIdx.x; i < B.npairs; i += blockDim.x) sp[i] = pairs[B.pair0 + i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SHM_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 16);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const Seg sg = segs[blockIdx.x];
+    const int64_t n = sg.r1 - sg.r0;
+    const int ntiles = (int)((n + SHR_ROWS - 1) / SHR_ROWS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto issue = [&](int c) {  // executed by the producer warp: lane l copies column l, l + 32, ...
+        const int s = c % SHM_STAGES;
+        const int64_t off = (int64_t)c * SHR_ROWS;
+        const int cnt = (int)min((int64_t)SHR_ROWS, n - off);
+        const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);  // columns are padded: one element past is readable
+        if (lane == 0) mbar_expect_tx(&full[s], bytes * (unsigned)ncols);
+        __syncwarp();
+        for (int col = lane; col < ncols; col += 32)
+            bulk_g2s(tile + ((size_t)s * ncols + col) * SHR_ROWS, dX + (int64_t)B.cols[col] * ld + sg.r0 + off, bytes, &full[s]);
+    };
+    if (warp == 16) {  // producer warp: keeps the ring full, never computes
+        for (int c = 0; c < ntiles; c++) {
+            if (c >= SHM_STAGES) mbar_wait(&empty[c % SHM_STAGES], (unsigned)(((c / SHM_STAGES) - 1) & 1));
+            issue(c);
+        }
+        return;
+    }
+    double mn[2][4], mx[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            mn[u][k] = INFINITY;
+            mx[u][k] = -INFINITY;
+        }
+    for (int c = 0; c < ntiles; c++) {
+        const int s = c % SHM_STAGES;
+        const unsigned ph = (unsigned)((c / SHM_STAGES) & 1);
+        mbar_wait(&full[s], ph);
+        const int nrow = (int)min((int64_t)SHR_ROWS, n - (int64_t)c * SHR_ROWS);
+        const double* tl = tile + (size_t)s * ncols * SHR_ROWS;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int unit = warp * 2 + u;
+            if (unit < B.nunits) {
+                const ShearPairRef* pr = sp + B.ufirst[unit];
+                const int acol = B.uacol[unit];
+                switch (B.unp[unit]) {
+                    case 1: shear_mm_unit<1>(tl, pr, acol, lane, nrow, mn[u], mx[u]); break;
+                    case 2: shear_mm_unit<2>(tl, pr, acol, lane, nrow, mn[u], mx[u]); break;
+                    case 3: shear_mm_unit<3>(tl, pr, acol, lane, nrow, mn[u], mx[u]); break;
+                    default: shear_mm_unit<4>(tl, pr, acol, lane, nrow, mn[u], mx[u]); break;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int unit = warp * 2 + u;
+        if (unit < B.nunits) {
+            const int np = B.unp[unit], first = B.ufirst[unit];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < np) {
+                    const double a = warp_min(mn[u][k]), b = warp_max(mx[u][k]);
+                    if (lane == 0) {
+                        part[((int64_t)sp[first + k].job * nseg + blockIdx.x) * 2 + 0] = a;
+                        part[((int64_t)sp[first + k].job * nseg + blockIdx.x) * 2 + 1] = b;
+                    }
+                }
+        }
     }
 }
 

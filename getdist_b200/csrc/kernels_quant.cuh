@@ -387,3 +387,71 @@ __global__ void __launch_bounds__(512) k_qselect(QSlot* __restrict__ slots, int 
         slots[gs] = q;
     }
 }
+
+// ---- helpers of the convergence tests (getConvergeTests, mcsamples.py:964-1034) ------------------------------------
+// sum of n fixed-point weights (order statistics on a row range: confidence(..., start, end), chains.py:814-838)
+__global__ void __launch_bounds__(256) k_sum_u64(const unsigned long long* __restrict__ w, int64_t n, unsigned long long* __restrict__ acc) {
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += w[i];
+    s = warp_sum_u64(s);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(acc, s);
+}
+
+#define FRC_CHUNK 4096
+// per-chunk totals of the fixed-point weights: grid ceil(N / FRC_CHUNK), 256 threads
+__global__ void __launch_bounds__(256) k_chunk_sums_u64(const unsigned long long* __restrict__ w, int64_t N, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned long long sh[8];
+    const int64_t r0 = (int64_t)blockIdx.x * FRC_CHUNK;
+    unsigned long long s = 0;
+    for (int t = threadIdx.x; t < FRC_CHUNK; t += blockDim.x)
+        if (r0 + t < N) s += w[r0 + t];
+    s = warp_sum_u64(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += sh[i];
+        sums[blockIdx.x] = t;
+    }
+}
+
+// one CTA per target: job = (chunk, target inside the chunk); first row of the chunk whose inclusive cumulative weight
+// reaches the target (np.searchsorted(cumsum, target), side='left'); clamps to the last row of the chunk
+__global__ void __launch_bounds__(256) k_fraction_rows(const unsigned long long* __restrict__ w, int64_t N,
+                                                       const unsigned long long* __restrict__ jobs, long long* __restrict__ rows) {
+    __shared__ unsigned long long pre[256];
+    const int64_t r0 = (int64_t)jobs[2 * blockIdx.x] * FRC_CHUNK;
+    const unsigned long long target = jobs[2 * blockIdx.x + 1];
+    constexpr int PER = FRC_CHUNK / 256;
+    unsigned long long v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int64_t r = r0 + (int64_t)threadIdx.x * PER + k;
+        v[k] = r < N ? w[r] : 0ull;
+        s += v[k];
+    }
+    pre[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive prefix over the 256 thread totals
+        unsigned long long run = 0;
+        for (int i = 0; i < 256; i++) {
+            const unsigned long long t = pre[i];
+            pre[i] = run;
+            run += t;
+        }
+        rows[blockIdx.x] = min(r0 + FRC_CHUNK, N) - 1;  // default: target beyond the chunk (rounding) -> its last row
+    }
+    __syncthreads();
+    unsigned long long run = pre[threadIdx.x];
+    if (run < target || (target == 0 && threadIdx.x == 0)) {
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const unsigned long long nxt = run + v[k];
+            if ((run < target || (target == 0 && k == 0 && threadIdx.x == 0)) && nxt >= target) {
+                const int64_t r = r0 + (int64_t)threadIdx.x * PER + k;
+                if (r < N) rows[blockIdx.x] = r;
+            }
+            run = nxt;
+        }
+    }
+}

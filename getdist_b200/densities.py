@@ -62,9 +62,10 @@ class GridDensity:
         self.spl = None
 
     def bounds(self):
+        """bounds in the order x, y, z ... (the axes are stored slowest first, reference densities.py:111-121)"""
         if self.view_ranges is not None:
             return self.view_ranges
-        return [(ax[0], ax[-1]) for ax in self.axes]
+        return [(ax[0], ax[-1]) for ax in self.axes][::-1]
 
     def getContourLevels(self, contours=(0.68, 0.95)):
         return getContourLevels(self.P, contours)
@@ -187,5 +188,51 @@ class Density2D(GridDensity):
         if self.spl is None:
             self.spl = RectBivariateSpline(self.x, self.y, self.P.T, s=0)
         return self.spl.ev(x, y) if not grid else self.spl(x, y)
+
+    __call__ = Prob
+
+
+class DensityND(GridDensity):
+    """ND marginalised density on a regular grid (reference densities.py:304-381): `xs` lists the axis vectors in the
+    order x, y, z ..., P is indexed slowest axis first (P[..., iy, ix])."""
+
+    def __init__(self, xs, P=None, view_ranges=None):
+        self.dim = len(xs)
+        self.x = xs[0]
+        if self.dim >= 2:
+            self.y = xs[1]
+        if self.dim >= 3:
+            self.z = xs[2]
+        self.xs = xs
+        self.axes = xs[::-1]
+        self.view_ranges = view_ranges
+        self.spacing = 1.0
+        for x in xs:
+            self.spacing = self.spacing * (x[1] - x[0])
+        self.likes = None
+        self.maxlikes = None
+        self.contours = None
+        self.setP(P)
+
+    def integrate(self, P):
+        """every grid point weighs 2^-(number of axes on which it sits on the boundary); like the reference
+        (densities.py:337-365) the sum is NOT multiplied by the cell volume"""
+        P = np.asarray(P)
+        w = np.ones(())
+        for size in P.shape:
+            e = np.ones(size)
+            e[[0, -1]] = 0.5
+            w = np.multiply.outer(w, e)
+        return float(np.sum(P * w))
+
+    def norm_integral(self):
+        return self.integrate(self.P)
+
+    def Prob(self, xs):
+        from scipy.interpolate import LinearNDInterpolator
+
+        if self.spl is None:
+            self.spl = LinearNDInterpolator(self.xs, self.P.T, rescale=True)
+        return self.spl(xs)
 
     __call__ = Prob

@@ -13,11 +13,17 @@ Mirrors, with the same names, argument meaning and error behaviour (reference pa
 Everything N-sized or grid-sized runs on the device through the C-ABI (getdist_b200/_abi.py); this module
 keeps only the scalar per-parameter logic (``_initParam`` limit tests, grid geometry, 2D branch selection and
 2x2 Cholesky algebra), settings handling, caching and error/warning behaviour.  There is no CPU fallback:
-options of the reference that the device path does not implement yet raise ``NotImplementedError``
-(meanlikes, mask_function -- SURVEY.md s8f).
+the few options of the reference that the device path does not implement (``shade_likes_is_mean_loglikes``,
+``range_ND_contour`` with likeStats, ``mask_function`` on periodic parameters) raise ``NotImplementedError``.
 
 ``prefetch_triangle`` computes all 1D and 2D densities of a parameter list in batched launches and fills the
-caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by getdist.plots) then hit.
+caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by getdist.plots) then hit; a serial
+caller that never calls it still gets batches: the first cache miss of ``get1DDensity`` / ``get2DDensityGridData``
+triggers a batched launch for the analysis' parameter set (``auto_prefetch``).
+
+Also here: ``getRawNDDensityGridData`` (mcsamples.py:2098-2235) on the histogram kernels and the
+MeanVar / Gelman-Rubin / split-quantile parts of ``getConvergeTests`` (mcsamples.py:964-1034) on the per-chain
+moment and order-statistics kernels.
 """
 import logging
 import math
@@ -26,7 +32,7 @@ from collections.abc import Mapping
 import numpy as np
 
 from . import _abi
-from .densities import DensitiesError, Density1D, Density2D  # noqa: F401
+from .densities import DensitiesError, Density1D, Density2D, DensityND  # noqa: F401
 
 log = logging.getLogger("getdist_b200")
 
@@ -57,6 +63,7 @@ ANALYSIS_DEFAULTS = dict(
     range_ND_contour=-1, range_confidence=0.001, converge_test_limit=0.95, fine_bins=1024, smooth_scale_1D=-1.0,
     boundary_correction_order=1, mult_bias_correction_order=1, smooth_scale_2D=-1.0, max_corr_2D=0.99,
     fine_bins_2D=256, use_effective_samples_2D=False, max_scatter_points=2000, num_bins=100, num_bins_2D=40,
+    num_bins_ND=12,
 )
 
 _QFRACS_TAIL = list(np.linspace(0.1, 0.9, 9))
@@ -67,7 +74,7 @@ class ParamInfo:
 
     def __init__(self, name, label=None):
         self.name = name
-        self.label = label or name
+        self.label = label or ""  # paramnames.py: an unset label stays empty (latexLabel falls back to the name)
         self.isDerived = False
         self.limmin = None
         self.limmax = None
@@ -98,6 +105,10 @@ class ParamNames:
             if p.name == name:
                 return i
         return -1
+
+    def parFormat(self):
+        """paramnames.py:380-382"""
+        return "%-" + str(max(9, max(len(p.name) for p in self.names)) + 1) + "s"
 
 
 class ParamBounds:
@@ -143,18 +154,63 @@ class _SpecView:
 
 class ParamConfidenceData:
     """Handle standing in for chains.ParamConfidenceData: the device resolves order statistics directly, so
-    the handle only remembers which column it refers to."""
+    the handle only remembers what it refers to: a stored column (index) with an optional row range, or an
+    arbitrary vector with its weights (held in a one-column device context of its own)."""
 
-    def __init__(self, index):
+    def __init__(self, index=None, start=0, end=None, ctx=None):
         self.index = index
+        self.start = start
+        self.end = end
+        self.ctx = ctx
+
+
+class ChainView:
+    """One of the separate chains the samples were combined from (stand-in for the WeightedSamples objects of
+    getSeparateChains, chains.py:1505-1527): row range and the per-chain moments of the fused device reduction."""
+
+    def __init__(self, index, start, end, means, cov, norm):
+        self.index, self.start, self.end = index, start, end
+        self.means, self.fullcov, self.norm = means, cov, norm
+
+    def getMeans(self, pars=None):
+        return self.means if pars is None else np.array([self.means[i] for i in pars])
+
+    def getCov(self, nparam=None, pars=None):
+        return self.fullcov[np.ix_(pars, pars)] if pars is not None else self.fullcov[:nparam, :nparam]
+
+
+def _parse_setting(default, v):
+    """typed by the default, as IniFile does (inifile.py:216-226): booleans from 'T'/'F' strings, floats stay floats"""
+    if isinstance(default, bool):
+        if isinstance(v, str):
+            return v.strip().lower() in ("t", "true", "1", "yes", "y")
+        return bool(v)
+    if isinstance(default, int) and not isinstance(v, str) and float(v) != int(v):
+        return float(v)  # e.g. a fractional ignore_rows
+    return type(default)(v)
+
+
+def _read_ini(ini):
+    """settings from a .ini file name (key = value lines, # comments) or from an object with a `.params` mapping"""
+    if hasattr(ini, "params"):
+        return dict(ini.params)
+    out = {}
+    with open(ini) as f:
+        for line in f:
+            line = line.split("#", 1)[0].strip()
+            if "=" in line:
+                k, v = line.split("=", 1)
+                out[k.strip()] = v.strip()
+    return out
 
 
 class MCSamples:
     def __init__(self, samples=None, weights=None, loglikes=None, names=None, labels=None, ranges=None, sampler=None,
-                 settings=None, label=None, device=0, name_tag=None, **kwargs):
+                 settings=None, label=None, device=0, name_tag=None, chain_offsets=None, **kwargs):
         if samples is None:
             raise MCSamplesError("getdist_b200.MCSamples needs in-memory samples (file loading stays in the reference)")
-        self.chain_offsets = None
+        # chain_offsets: row offsets of already combined chains (chains.py:1497), as the reference object holds them
+        self.chain_offsets = None if chain_offsets is None else np.asarray(chain_offsets, dtype=np.int64)
         if isinstance(samples, (list, tuple)) and len(samples) and np.ndim(samples[0]) == 2:
             # chains.py:1488-1503 (makeSingle)
             self.chain_offsets = np.cumsum(np.array([0] + [s.shape[0] for s in samples]))
@@ -189,6 +245,10 @@ class MCSamples:
         self.no_warning_params = []
         self.no_warning_chi2_params = True
         self.likeStats = None
+        self.max_split_tests = 4  # mcsamples.py:262
+        self.auto_prefetch = True  # first cache miss of a serial caller triggers a batched launch
+        self.auto_prefetch_max_params = 40
+        self._seen_2d = []
         for k, v in ANALYSIS_DEFAULTS.items():
             setattr(self, k, v)
         self.contours = np.array(self.contours)
@@ -235,15 +295,19 @@ class MCSamples:
 
     # ------------------------------------------------------------------ settings
     def updateSettings(self, settings=None, ini=None, doUpdate=True):
-        """mcsamples.py:472-499 (dictionary form; .ini files stay with the reference's IniFile)."""
+        """mcsamples.py:472-499: `settings` (a dict) override `ini` (a .ini file name or an object with `.params`)."""
         assert settings is None or isinstance(settings, Mapping)
+        merged = {}
         if ini is not None:
-            raise NotImplementedError("ini files are handled by the reference's IniFile; pass settings as a dict")
-        for k, v in (settings or {}).items():
+            merged.update(_read_ini(ini))
+        merged.update(settings or {})
+        for k, v in merged.items():
             if k == "contours":
                 v = np.array(v if not isinstance(v, str) else [float(x) for x in v.split()])
             elif k in ANALYSIS_DEFAULTS and not isinstance(ANALYSIS_DEFAULTS[k], tuple):
-                v = type(ANALYSIS_DEFAULTS[k])(v)  # typed by the existing attribute, inifile.py:216-226
+                v = _parse_setting(ANALYSIS_DEFAULTS[k], v)
+            elif ini is not None and not (settings and k in settings) and not hasattr(self, k):
+                continue  # unknown keys of an .ini file are not analysis settings
             setattr(self, k, v)
         # how small the end bin must be relative to the peak for a two-tail limit (mcsamples.py:427-433)
         from scipy.stats import norm as _norm
@@ -280,6 +344,16 @@ class MCSamples:
         self.needs_update = True
 
     def setSamples(self, samples, weights=None, loglikes=None):
+        """chains.py:262-308; a list of per-chain arrays is combined as in makeSingle (:1488-1503), anything else
+        forgets the chain boundaries of the previous samples."""
+        self.chain_offsets = None
+        if isinstance(samples, (list, tuple)) and len(samples) and np.ndim(samples[0]) == 2:
+            self.chain_offsets = np.cumsum(np.array([0] + [s.shape[0] for s in samples]))
+            if weights is not None:
+                weights = np.hstack([np.asarray(w, dtype=np.float64) for w in weights])
+            if loglikes is not None:
+                loglikes = np.hstack(list(loglikes))
+            samples = np.vstack([np.asarray(s, dtype=np.float64) for s in samples])
         self.samples = np.asarray(samples, dtype=np.float64)
         self.numrows, self.n = self.samples.shape
         self.weights = None if weights is None else np.asarray(weights, dtype=np.float64)
@@ -307,6 +381,7 @@ class MCSamples:
         self._xmin, self._xmax = m["xmin"], m["xmax"]
         self.density1D = {}
         self._density2D = {}
+        self._seen_2d = []
         self._initLimits()
         for par in self.paramNames.names:
             par.N_eff_kde = None
@@ -376,19 +451,21 @@ class MCSamples:
     def getGelmanRubinEigenvalues(self, nparam=None, chainlist=None):
         """chains.py:1446-1474; the per-chain means/covariances come from the fused device reduction, the
         P x P LAPACK work stays on the host."""
-        if chainlist is not None:
-            raise NotImplementedError("explicit chainlist: use the reference")
         if self.chain_offsets is None:
             raise WeightedSampleError("Samples were not combined from separate chains")
         if self.needs_update:
             self.updateBaseStatistics()
         nparam = nparam or self.paramNames.numNonDerived()
         m = self._mom
-        nch = m["chain_means"].shape[0]
+        # chainlist: chain indices or the ChainView objects of getSeparateChains() (a subset of the stored chains)
+        use = range(m["chain_means"].shape[0]) if chainlist is None else [getattr(c, "index", c) for c in chainlist]
+        nch = len(use)
+        if nch < 2:
+            raise WeightedSampleError("Gelman-Rubin needs at least two chains")
         means = self.means[:nparam]
         meanscov = np.zeros((nparam, nparam))
         meancov = np.zeros((nparam, nparam))
-        for c in range(nch):
+        for c in use:
             diff = m["chain_means"][c, :nparam] - means
             meanscov += np.outer(diff, diff)
             meancov += m["chain_covs"][c, :nparam, :nparam]
@@ -403,26 +480,50 @@ class MCSamples:
     def getGelmanRubin(self, nparam=None, chainlist=None):
         return np.max(self.getGelmanRubinEigenvalues(nparam, chainlist))
 
-    # ------------------------------------------------------------------ order statistics
-    def initParamConfidenceData(self, paramVec, start=0, end=None, weights=None):
-        if not isinstance(paramVec, (int, np.integer)) or start != 0 or end is not None or weights is not None:
-            raise NotImplementedError("device order statistics work on stored columns with the stored weights")
-        return ParamConfidenceData(int(paramVec))
-
-    def confidence(self, paramVec, limfrac, upper=False, start=0, end=None, weights=None):
-        """chains.py:814-838 on a stored column (index, name or ParamConfidenceData)."""
-        if isinstance(paramVec, ParamConfidenceData):
-            j = paramVec.index
-        else:
-            j, _ = self._parAndNumber(paramVec)
-            if j is None or start != 0 or end is not None or weights is not None:
-                raise NotImplementedError("device order statistics work on stored columns with the stored weights")
+    def getSeparateChains(self):
+        """chains.py:1505-1527: the separate chains as row ranges with their device-computed moments."""
+        if self.chain_offsets is None:
+            raise WeightedSampleError("Samples were not combined from separate chains")
         if self.needs_update:
             self.updateBaseStatistics()
+        m = self._mom
+        return [ChainView(c, int(a), int(b), m["chain_means"][c], m["chain_covs"][c], m["chain_norms"][c])
+                for c, (a, b) in enumerate(zip(self.chain_offsets[:-1], self.chain_offsets[1:]))]
+
+    # ------------------------------------------------------------------ order statistics
+    def initParamConfidenceData(self, paramVec, start=0, end=None, weights=None):
+        """chains.py:793-812.  A stored column (index / name) with the stored weights is addressed in place, with an
+        optional row range; an arbitrary vector or other weights are uploaded to a one-column device context."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        if weights is None and (isinstance(paramVec, (int, np.integer, str, ParamInfo))):
+            j, _ = self._parAndNumber(paramVec)
+            if j is None:
+                raise ParamError("unknown parameter %s" % (paramVec,))
+            end = self.numrows if end is None else (end if end >= 0 else self.numrows + end)
+            return ParamConfidenceData(j, int(start), int(end))
+        if isinstance(paramVec, (int, np.integer, str, ParamInfo)):
+            paramVec = self.samples[:, self._parAndNumber(paramVec)[0]]
+        vec = np.ascontiguousarray(np.asarray(paramVec, dtype=np.float64)[start:end]).reshape(-1, 1)
+        w = self.weights if weights is None else np.asarray(weights, dtype=np.float64)
+        w = None if w is None else np.ascontiguousarray(w[start:end])
+        ctx = _abi.Context(self._ctx.device)
+        ctx.set_samples(vec, w)
+        return ParamConfidenceData(ctx=ctx)
+
+    def confidence(self, paramVec, limfrac, upper=False, start=0, end=None, weights=None):
+        """chains.py:814-838: sample confidence limits by counting weight in the tails (exact order statistics)."""
+        d = paramVec if isinstance(paramVec, ParamConfidenceData) else self.initParamConfidenceData(paramVec, start, end, weights)
         fr = np.atleast_1d(np.asarray(limfrac, dtype=np.float64))
         if upper:
             fr = 1 - fr
-        out = np.concatenate([self._ctx.weighted_quantiles([j], fr[i:i + 16])[0] for i in range(0, fr.size, 16)])
+        if d.ctx is not None:
+            call = lambda f: d.ctx.weighted_quantiles([0], f)[0]  # noqa: E731
+        elif d.start == 0 and d.end in (None, self.numrows):
+            call = lambda f: self._ctx.weighted_quantiles([d.index], f)[0]  # noqa: E731
+        else:
+            call = lambda f: self._ctx.weighted_quantiles_range([d.index], f, d.start, d.end)[0]  # noqa: E731
+        out = np.concatenate([call(fr[i:i + 16]) for i in range(0, fr.size, 16)])
         return out if np.ndim(limfrac) else out[0]
 
     def twoTailLimits(self, paramVec, confidence):
@@ -452,11 +553,16 @@ class MCSamples:
                 out[i] = e.value
         while reqs:
             order = list(reqs)
-            res = self._ctx.lag_sums([reqs[i] for i in order])
+            jobs, span = [], []
+            for i in order:  # a generator may ask for several blocks of lags at once (a list of requests)
+                rq = reqs[i] if isinstance(reqs[i], list) else [reqs[i]]
+                span.append((len(jobs), len(rq), isinstance(reqs[i], list)))
+                jobs.extend(rq)
+            res = self._ctx.lag_sums(jobs)
             nxt = {}
-            for i, r in zip(order, res):
+            for i, (a, cnt, many) in zip(order, span):
                 try:
-                    nxt[i] = gens[i].send(r)
+                    nxt[i] = gens[i].send(res[a:a + cnt] if many else res[a])
                 except StopIteration as e:
                     out[i] = e.value
             reqs = nxt
@@ -473,16 +579,25 @@ class MCSamples:
         corr = []
         k0 = 0
         ix = None
+        nblk = 1  # blocks of 16 lags per round, growing geometrically: O(log) host round trips for long chains
         while k0 <= max_off and ix is None:
-            nk = min(16, max_off + 1 - k0)
-            sums = yield (j, 0, k0, nk, mean, 0.0)
-            for t in range(nk):
-                k = k0 + t
-                corr.append(sums[t] / (n - k) / var)
-                if not corr[k] > min_corr * corr[0]:
-                    ix = k
+            reqs = []
+            kk = k0
+            for _ in range(nblk):
+                nk = min(16, max_off + 1 - kk)
+                if nk <= 0:
                     break
-            k0 += nk
+                reqs.append((kk, nk))
+                kk += nk
+            sums = yield [(j, 0, a, nk, mean, 0.0) for a, nk in reqs]
+            for (a, nk), blk in zip(reqs, sums):
+                for t in range(nk):
+                    k = a + t
+                    corr.append(blk[t] / (n - k) / var)
+                    if ix is None and not corr[k] > min_corr * corr[0]:
+                        ix = k
+            k0 = kk
+            nblk = min(nblk * 2, 256)
         if ix is None:
             ix = 0  # np.argmin over an all-True array
         return corr[0] + 2 * sum(corr[1:ix])
@@ -542,11 +657,17 @@ class MCSamples:
         return self._lag_rounds(gens)
 
     def getCorrelationLength(self, j, weight_units=True, min_corr=0.05, corr=None):
-        """chains.py:448-466 (row units only: weight_units=False)."""
-        if weight_units or corr is not None:
-            raise NotImplementedError("only weight_units=False is on the device path")
+        """chains.py:448-466.  Weight units scale every lag of the autocorrelation by numrows / sum(w)
+        (getAutocorrelation, :443-444), so the threshold crossing is the same and the length scales likewise."""
+        if corr is not None:  # an autocorrelation array handed in: plain host arithmetic on it
+            corr = np.asarray(corr)
+            ix = np.argmin(corr > min_corr * corr[0])
+            return corr[0] + 2 * np.sum(corr[1:ix])
+        if self.needs_update:
+            self.updateBaseStatistics()
         j, _ = self._parAndNumber(j)
-        return self._lag_rounds([self._corr_length_gen(j, min_corr)])[0]
+        n = self._lag_rounds([self._corr_length_gen(j, min_corr)])[0]
+        return n * self.numrows / self.norm if weight_units else n
 
     def _get1DNeff(self, par, param):
         if par.N_eff_kde is None:
@@ -646,6 +767,10 @@ class MCSamples:
             j, par = self._parAndNumber(name)
             if par is not None:
                 density = self.density1D.get(par.name)
+                if density is None and self.auto_prefetch and self.n <= 4 * self.auto_prefetch_max_params:
+                    # first miss of a serial caller: all 1D densities in one batched launch
+                    self._densities_1d([k for k in range(self.n) if self.paramNames.names[k].name not in self.density1D])
+                    density = self.density1D.get(par.name)
                 if density is not None:
                     return density
         return self.get1DDensityGridData(name, **kwargs)
@@ -753,24 +878,59 @@ class MCSamples:
                 raise NotImplementedError("mask_function with periodic parameters is not on the device path")
             density = self._densities_2d([(j, j2)], _contours=want, _likes=bool(meanlikes), _mask_function=mask_function, **kwargs)[0]
         elif not kwargs:
-            cached = self._density2D.get((j, j2))
-            if cached is not None:
-                # a fresh object per call, as the reference returns (callers normalise in place)
-                density = Density2D(cached.x, cached.y, cached.P.copy(), view_ranges=cached.view_ranges)
-                density._gdk = cached._gdk
+            if (j, j2) not in self._density2D and self.auto_prefetch:
+                self._auto_prefetch_2d(j, j2)
+            density = self._cached_2d(j, j2)
         if density is None:
             density = self._densities_2d([(j, j2)], _contours=want, **kwargs)[0]
+            if not kwargs and not meanlikes and mask_function is None:
+                density = self._cached_2d(j, j2)  # the cache keeps a private copy; callers get a fresh object
         if get_density:
             return density
         dev = density._gdk.get("levels")
-        if dev is not None and len(dev[0]) >= len(want) and list(dev[0][:len(want)]) == want:
-            if density._gdk["status"] & _abi.ST_CONTOUR_RANGE:
-                raise DensitiesError("Contour level outside plotted ranges")
+        if (dev is not None and len(dev[0]) >= len(want) and list(dev[0][:len(want)]) == want
+                and not density._gdk["status"] & _abi.ST_CONTOUR_RANGE):
             density.contours = np.array(dev[1][:len(want)])
         else:
-            density.contours = density.getContourLevels(want)  # more than 4 contours: host numpy
+            # more than 4 contours, other fractions than the cached ones, or one of the device levels fell outside the
+            # plotted range (one status bit per density): the host evaluates exactly the requested ones and raises
+            # DensitiesError only if one of THOSE is out of range (densities.py:50-51)
+            density.contours = density.getContourLevels(want)
         density.likes = getattr(density, "_likes2d", None) if meanlikes else None
         return density
+
+    def _cached_2d(self, j, j2):
+        """a fresh Density2D (own copy of the grid) from the cache entry of the pair, or None: callers normalise in
+        place (get2DDensity(normalized=True)), the reference returns a new object per call"""
+        c = self._density2D.get((j, j2))
+        if c is None:
+            return None
+        d = Density2D(c.x, c.y, c.P.copy(), view_ranges=c.view_ranges)
+        d._gdk = c._gdk
+        return d
+
+    def _auto_prefetch_2d(self, j, j2):
+        """First 2D cache miss of a serial caller (getdist.plots.triangle_plot asks pair by pair, plots.py:2613):
+        compute a batch instead of one pair.  Few parameters: the whole triangle at once.  Many parameters: every
+        uncached pair among the parameters seen so far -- for the triangle order that is one plot row per launch."""
+        if self.n <= self.auto_prefetch_max_params:
+            idx = list(range(self.n))
+            pairs = [(a, b) for a in idx for b in idx if a != b and ((a, b) not in self._density2D) and a < b]
+            if (j, j2) not in pairs:
+                pairs.append((j, j2))
+        else:
+            for q in (j, j2):
+                if q not in self._seen_2d:
+                    self._seen_2d.append(q)
+            # same orientation as the request: x = the earlier seen parameter unless asked otherwise
+            pairs = [(j, j2)]
+            for a in self._seen_2d:
+                if a in (j, j2):
+                    continue
+                for pr in ((a, j2), (a, j)):
+                    if pr not in self._density2D and (pr[1], pr[0]) not in self._density2D and pr not in pairs and pr[0] != pr[1]:
+                        pairs.append(pr)
+        self._densities_2d(pairs)
 
     def _spec_2d(self, j, j2, kwargs):
         parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
@@ -1053,7 +1213,9 @@ class MCSamples:
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
             if not kwargs and masks is None and lbuf is None:
-                self._density2D[(j, j2)] = d
+                c = Density2D(x, y, d.P.copy(), view_ranges=d.view_ranges)  # private copy: the caller may normalise d in place
+                c._gdk = d._gdk
+                self._density2D[(j, j2)] = c
             out.append(d)
         return out
 
@@ -1101,12 +1263,190 @@ class MCSamples:
         if density1D is None:
             density1D = self.get1DDensity(par.name)
         mft = self.max_frac_twotail if max_frac_twotail is None else max_frac_twotail
-        keys = limit_fractions(self.contours)[:16]
-        fr = np.array([(1 - lf) if up else lf for lf, up in keys])
-        table = dict(zip(keys, self._ctx.weighted_quantiles([j], fr)[0]))
-        par.limits = marge_limits(density1D, par, self.contours[:4], mft, lambda lf, up: table[(lf, up)],
+        keys = limit_fractions(self.contours)
+        table = {}
+        for k0 in range(0, len(keys), 16):  # at most 16 target fractions per device call
+            part = keys[k0:k0 + 16]
+            fr = np.array([(1 - lf) if up else lf for lf, up in part])
+            table.update(zip(part, self._ctx.weighted_quantiles([j], fr)[0]))
+        par.limits = marge_limits(density1D, par, self.contours, mft, lambda lf, up: table[(lf, up)],
                                   force_twotail=self.force_twotail, credible_interval_threshold=self.credible_interval_threshold)
         return par.limits
+
+    # ------------------------------------------------------------------ raw ND densities
+    def getRawNDDensity(self, xs, normalized=False, **kwargs):
+        """mcsamples.py:2081-2096."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        density = self.getRawNDDensityGridData(xs, get_density=True, **kwargs)
+        if normalized:
+            density.normalize(in_place=True)
+        return density
+
+    def getRawNDDensityGridData(self, js, writeDataToFile=False, num_plot_contours=None, get_density=False, meanlikes=False,
+                                maxlikes=False, **kwargs):
+        """mcsamples.py:2098-2235: unsmoothed ND marginalised density.  The N-sized part (_binSamples per axis +
+        _makeNDhist, and the mean / profile likelihood histograms) is one device sweep per histogram (gdk_histnd);
+        the raw edge mask, the normalisation and the contour levels are grid-sized host arithmetic."""
+        if writeDataToFile:
+            raise NotImplementedError("plot-data files are written by the reference (file IO is out of scope)")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        jv, parv = zip(*[self._parAndNumber(j) for j in js])
+        if None in jv:
+            return None
+        ndim = len(jv)
+        self._ensure_param_ranges(list(jv))
+        bco = kwargs.get("boundary_correction_order", self.boundary_correction_order)
+        has_prior = any(par.has_limits for par in parv)
+        nbinsND = int(kwargs.get("num_bins_ND", self.num_bins_ND))
+        geo = [self._bin_geometry(par, nbinsND) for par in parv]
+        lo, hi = [g[0] for g in geo], [g[1] for g in geo]
+        nb = [nbinsND] * ndim
+        if meanlikes or maxlikes:
+            self._ensure_loglikes()
+        binsND = self._ctx.histnd(jv, nb, lo, hi, 0)
+        if has_prior and bco >= 0:
+            # _setRawEdgeMaskND (mcsamples.py:2012-2032): half weight on the boundary bins of every hard prior
+            prior_mask = np.ones(binsND.shape)
+            for ax, par in enumerate(parv[::-1]):
+                sl = [slice(None)] * ndim
+                if par.has_limits_bot:
+                    sl[ax] = 0
+                    prior_mask[tuple(sl)] /= 2
+                if par.has_limits_top:
+                    sl[ax] = binsND.shape[ax] - 1
+                    prior_mask[tuple(sl)] /= 2
+            binsND = binsND / prior_mask
+        xv = [np.linspace(lo[i], hi[i], nb[i]) for i in range(ndim)]
+        views = [(par.range_min, par.range_max) for par in parv]
+        density = DensityND(xv, binsND, view_ranges=views)
+        density.normalize("max", in_place=True)
+        if get_density:
+            return density
+        ncontours = len(self.contours)
+        if num_plot_contours:
+            ncontours = min(num_plot_contours, ncontours)
+        contours = self.contours[:ncontours]
+        density.contours = density.getContourLevels(contours)
+        if meanlikes:
+            likes = self._ctx.histnd(jv, nb, lo, hi, 1)
+            density.likes = likes / np.max(likes)
+        else:
+            density.likes = None
+        if maxlikes:
+            from .densities import getContourLevels
+
+            density.maxlikes = self._ctx.histnd(jv, nb, lo, hi, 2)
+            # getImportContourLevels(binNDmaxlikes, contours, half_edge=False) == getContourLevels(..., half_edge=False)
+            density.maxcontours = getContourLevels(density.maxlikes, contours, half_edge=False)
+        else:
+            density.maxlikes = None
+        return density
+
+    # ------------------------------------------------------------------ convergence tests (SURVEY s8f-4)
+    def getFractionIndices(self, weights=None, n=2):
+        """mcsamples.py:668-680 on the stored weights: rows that split the total weight into n equal parts."""
+        if weights is not None and weights is not self.weights:
+            raise NotImplementedError("getFractionIndices works on the stored weights")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        rows = self._ctx.weight_fraction_rows(np.linspace(0, 1, n, endpoint=False))
+        return np.append(rows, self.numrows)
+
+    def getMeanVarTest(self):
+        """'MeanVar' of getConvergeTests (mcsamples.py:964-989): per parameter sqrt(var(chain mean) / mean(chain var)),
+        from the per-chain moments of the fused device reduction."""
+        if self.chain_offsets is None:
+            raise WeightedSampleError("Samples were not combined from separate chains")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        m = self._mom
+        nch = m["chain_means"].shape[0]
+        between = np.sum((m["chain_means"] - self.means) ** 2, axis=0) / (nch - 1)
+        # in-chain variance: sum over chains of sum w (x - chain mean)^2, over the total weight
+        within = np.zeros(self.n)
+        for c in range(nch):
+            within += np.diagonal(m["chain_covs"][c]) * m["chain_norms"][c]
+        within /= self.norm
+        return np.sqrt(between / within)
+
+    def getSplitTests(self, test_confidence=0.95):
+        """'SplitTest' of getConvergeTests (mcsamples.py:1003-1034): rms change of the upper / lower quantile, in units
+        of the standard deviation, when the samples are split into 2 .. max_split_tests sets of equal weight.  Returns
+        (nparam, max_split_tests - 1, 2).  Every order statistic is a device call (gdk_weighted_quantiles[_range]),
+        batched over all parameters."""
+        if self.needs_update:
+            self.updateBaseStatistics()
+        limits = np.array([1 - (1 - test_confidence) / 2, (1 - test_confidence) / 2])
+        idx = list(range(self.n))
+        confids = self._ctx.weighted_quantiles(idx, limits)
+        out = np.zeros((self.n, self.max_split_tests - 1, 2))
+        for ix in range(self.max_split_tests - 1):
+            split_n = 2 + ix
+            frac = self.getFractionIndices(None, split_n)
+            for f1, f2 in zip(frac[:-1], frac[1:]):
+                out[:, ix, :] += (self._ctx.weighted_quantiles_range(idx, limits, f1, f2) - confids) ** 2
+            out[:, ix, :] = np.sqrt(out[:, ix, :] / split_n) / self.sddev[:, None]
+        return out
+
+    def getConvergeTests(self, test_confidence=0.95, writeDataToFile=False, what=("MeanVar", "GelmanRubin", "SplitTest"),
+                         filename=None, feedback=False):
+        """mcsamples.py:905-1034: the MeanVar, GelmanRubin and SplitTest sections, same text as the reference.
+        'RafteryLewis' and 'CorrLengths' (thinned binary chains, per-chain full-length autocorrelations) are not on
+        the device path."""
+        other = [w for w in what if w not in ("MeanVar", "GelmanRubin", "SplitTest")]
+        if other:
+            raise NotImplementedError("convergence tests %s are not on the device path" % other)
+        if writeDataToFile:
+            raise NotImplementedError("file output stays with the reference")
+        if self.needs_update:
+            self.updateBaseStatistics()
+        lines = ""
+        nparam = self.n
+        nch = 1 if self.chain_offsets is None else len(self.chain_offsets) - 1
+        parForm = self.paramNames.parFormat()
+        parNames = [parForm % self.paramNames.names[j].name for j in range(nparam)]
+        if nch > 1 and "MeanVar" in what:
+            lines += "\n"
+            lines += "mean convergence stats using remaining chains\n"
+            lines += "param sqrt(var(chain mean)/mean(chain var))\n"
+            lines += "\n"
+            mv = self.getMeanVarTest()
+            for j in range(nparam):
+                lines += parNames[j] + f"{mv[j]:10.4f}  {self.paramNames.names[j].label}\n"
+            lines += "\n"
+        nparamMC = self.paramNames.numNonDerived()
+        if nch > 1 and nparamMC > 0 and "GelmanRubin" in what:
+            D = self.getGelmanRubinEigenvalues()
+            if D is not None:
+                self.GelmanRubin = np.max(D)
+                lines += "var(mean)/mean(var) for eigenvalues of covariance of y of orthonormalized parameters\n"
+                for jj, Di in enumerate(D):
+                    lines += "%3i%13.5f\n" % (jj + 1, Di)
+                GRSummary = " var(mean)/mean(var), remaining chains, worst e-value: R-1 = %13.5F" % self.GelmanRubin
+            else:
+                self.GelmanRubin = None
+                GRSummary = "Gelman-Rubin covariance not invertible (parameter not moved?)"
+                log.warning(GRSummary)
+            if feedback:
+                print(GRSummary)
+            lines += "\n"
+        if "SplitTest" in what:
+            lines += "Split tests: rms_n([delta(upper/lower quantile)]/sd) n={2,3,4}, limit=%.0f%%:\n" % (100 * self.converge_test_limit)
+            lines += "i.e. mean sample splitting change in the quantiles in units of the st. dev.\n"
+            lines += "\n"
+            st = self.getSplitTests(test_confidence)
+            for j in range(nparam):
+                for endb, typestr in enumerate(["upper", "lower"]):
+                    lines += parNames[j]
+                    for ix in range(self.max_split_tests - 1):
+                        lines += "%9.4f" % (st[j, ix, endb])
+                    lines += " %s\n" % typestr
+            lines += "\n"
+        if feedback:
+            print(lines)
+        return lines
 
     # ------------------------------------------------------------------ batched driver
     def triangle_pairs(self, params=None):

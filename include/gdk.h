@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct gdk_ctx gdk_ctx;
 
-#define GDK_ABI_VERSION 4
+#define GDK_ABI_VERSION 5
 
 /* error codes */
 #define GDK_OK 0
@@ -128,6 +128,23 @@ int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double* cov, doub
  * ------------------------------------------------------------------------------------------- */
 int32_t gdk_weighted_quantiles(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs,
                                int32_t nf, double* out);
+
+/* Same on the row range [row_begin, row_end): confidence(paramVec, limfrac, start=, end=) (chains.py:793-838), as the
+ * split tests of getConvergeTests issue it (mcsamples.py:1013-1031).  Fractions refer to the weight of the range.   */
+int32_t gdk_weighted_quantiles_range(gdk_ctx* ctx, const int32_t* params, int32_t np, const double* fracs,
+                                     int32_t nf, int64_t row_begin, int64_t row_end, double* out);
+
+/* getFractionIndices (mcsamples.py:668-680): rows_out[i] = np.searchsorted(np.cumsum(weights), fracs[i] * sum(w)),
+ * the first row whose inclusive cumulative weight reaches the target (exact fixed-point sums).                  */
+int32_t gdk_weight_fraction_rows(gdk_ctx* ctx, const double* fracs, int32_t nf, int64_t* rows_out);
+
+/* raw (unsmoothed) ND histogram -- the N-sized part of getRawNDDensityGridData (mcsamples.py:2098-2166):
+ * _binSamples per axis (:1486-1498) + _makeNDhist (:2065-2079).  out: prod(nbins) doubles, axis 0 fastest (the
+ * reference reshapes to nbins[::-1], C order).  which: 0 = sample weights, 1 = mean-likelihood weights
+ * weights*exp(mean_loglike-loglikes) (:2155-2159), 2 = profile likelihood max(exp(-bestfit-loglike)) per bin
+ * (:2163-2169).  which != 0 needs gdk_set_loglikes.  ndim <= 8.                                                     */
+int32_t gdk_histnd(gdk_ctx* ctx, int32_t ndim, const int32_t* params, const int32_t* nbins, const double* binmin,
+                   const double* binmax, int32_t which, double* out);
 
 /* ---------------------------------------------------------------------------------------------
  * 1D densities -- replaces the body of get1DDensityGridData (mcsamples.py:1517-1686) after

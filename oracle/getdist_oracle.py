@@ -749,6 +749,84 @@ class OracleSamples:
     def get_gelman_rubin(self, nparam=None):
         return gelman_rubin(self.samples, self.weights, self.chain_offsets, nparam)
 
+    # ---- raw ND densities and the MeanVar / split convergence tests ------------------------------
+    def raw_nd_density(self, js, meanlikes=False, maxlikes=False, **kwargs):
+        """getRawNDDensityGridData (mcsamples.py:2098-2197): returns (xs, P max-normalised, likes | None, maxlikes | None)."""
+        jv = [self._num(j) for j in js]
+        parv = [self.init_param_ranges(j) for j in jv]
+        ndim = len(jv)
+        nb = int(kwargs.get("num_bins_ND", self.settings.get("num_bins_ND", 12)))
+        bco = kwargs.get("boundary_correction_order", self.settings["boundary_correction_order"])
+        ixv, xminv, xmaxv = [], [], []
+        for j, par in zip(jv, parv):
+            lo, hi, fw = bin_geometry(par, nb)  # mcsamples.py:1486-1496
+            ixv.append(bin_indices(self.samples[:, j], lo, fw))
+            xminv.append(lo)
+            xmaxv.append(hi)
+        flat = np.zeros(self.numrows, dtype=np.int64)  # _flattenValues (mcsamples.py:2034-2046): axis 0 fastest
+        stride = 1
+        for ix in ixv:
+            flat += ix * stride
+            stride *= nb
+        shape = tuple([nb] * ndim)
+        bins = np.bincount(flat, weights=self.weights, minlength=nb ** ndim).reshape(shape)  # :2077-2079
+        if any(p.has_limits_bot or p.has_limits_top for p in parv) and bco >= 0:
+            mask = np.ones(shape)  # _setRawEdgeMaskND, :2012-2032
+            for ax, par in enumerate(parv[::-1]):
+                sl = [slice(None)] * ndim
+                if par.has_limits_bot:
+                    sl[ax] = 0
+                    mask[tuple(sl)] /= 2
+                if par.has_limits_top:
+                    sl[ax] = nb - 1
+                    mask[tuple(sl)] /= 2
+            bins = bins / mask
+        P = bins / np.max(bins)
+        likes = mlk = None
+        if meanlikes:  # :2155-2159, 2200-2201
+            lw = self.weights * np.exp(self.mean_loglike - self.loglikes)
+            likes = np.bincount(flat, weights=lw, minlength=nb ** ndim).reshape(shape)
+            likes = likes / np.max(likes)
+        if maxlikes:  # :2163-2169
+            bestfit = np.max(-self.loglikes)
+            mlk = np.zeros(nb ** ndim)
+            np.maximum.at(mlk, flat, np.exp(-bestfit - self.loglikes))
+            mlk = mlk.reshape(shape)
+        xs = [np.linspace(xminv[i], xmaxv[i], nb) for i in range(ndim)]
+        return xs, P, likes, mlk
+
+    def fraction_indices(self, n):
+        """getFractionIndices (mcsamples.py:668-680)."""
+        cumsum = np.cumsum(self.weights)
+        return np.append(np.searchsorted(cumsum, np.linspace(0, 1, n, endpoint=False) * self.norm), self.numrows)
+
+    def mean_var_test(self):
+        """'MeanVar' of getConvergeTests (mcsamples.py:964-989)."""
+        offs = self.chain_offsets
+        nch = len(offs) - 1
+        between = np.zeros(self.n)
+        within = np.zeros(self.n)
+        for a, b in zip(offs[:-1], offs[1:]):
+            w = self.weights[a:b]
+            cm = w.dot(self.samples[a:b]) / np.sum(w)
+            between += (cm - self.means) ** 2
+            for j in range(self.n):
+                within[j] += np.dot(w, (self.samples[a:b, j] - cm[j]) ** 2)
+        return np.sqrt(between / (nch - 1) / (within / self.norm))
+
+    def split_tests(self, test_confidence=0.95, max_split_tests=4):
+        """'SplitTest' of getConvergeTests (mcsamples.py:1003-1034) -> (nparam, max_split_tests - 1, 2)."""
+        limits = np.array([1 - (1 - test_confidence) / 2, (1 - test_confidence) / 2])
+        out = np.zeros((self.n, max_split_tests - 1, 2))
+        fracs = [self.fraction_indices(i + 2) for i in range(max_split_tests - 1)]
+        for j in range(self.n):
+            confids = weighted_quantiles(self.samples[:, j], self.weights, limits)
+            for ix, frac in enumerate(fracs):
+                for f1, f2 in zip(frac[:-1], frac[1:]):
+                    out[j, ix] += (weighted_quantiles(self.samples[f1:f2, j], self.weights[f1:f2], limits) - confids) ** 2
+                out[j, ix] = np.sqrt(out[j, ix] / (2 + ix)) / self.sddev[j]
+        return out
+
     def init_param_ranges(self, j):
         """mcsamples.py:1421-1425; resets the limit flags from the hard ranges as _initLimits does
         once per updateBaseStatistics (the proximity test may clear them, :1463-1474)."""

@@ -138,10 +138,57 @@ def run_limits():
     print("limits ok", len(out), "arrays")
 
 
+F4_CASES = ("chains", "likes", "bounded")
+
+
+def run_f4():
+    """SURVEY s8f-4 outputs of the unmodified reference -> f4.npz: raw ND densities (getRawNDDensityGridData,
+    mcsamples.py:2098-2235) incl. mean / profile likelihoods, the fraction indices, and the MeanVar / GelmanRubin /
+    SplitTest sections of getConvergeTests (mcsamples.py:905-1034) as text plus the numbers behind them."""
+    out = {}
+    for name in F4_CASES:
+        case = CASES[name]()
+        mc = MCSamples(samples=case["samples"], weights=case["weights"], names=case["names"], ranges=case["ranges"] or None,
+                       sampler=case.get("sampler", "uncorrelated"), loglikes=case.get("loglikes"), settings=case["settings"] or None)
+        out[name + "/digest"] = np.array(input_digest(case))
+        likes = case.get("loglikes") is not None
+        for js in ([0, 1, 2], [1, 0], [0, 1, 2, 3][: len(case["names"])]):
+            tag = "_".join(str(j) for j in js)
+            d = mc.getRawNDDensityGridData(js, meanlikes=likes, maxlikes=likes)
+            out["%s/nd/%s/P" % (name, tag)] = d.P
+            out["%s/nd/%s/contours" % (name, tag)] = np.asarray(d.contours)
+            out["%s/nd/%s/x0" % (name, tag)] = np.asarray(d.xs[0])
+            if likes:
+                out["%s/nd/%s/likes" % (name, tag)] = d.likes
+                out["%s/nd/%s/maxlikes" % (name, tag)] = d.maxlikes
+                out["%s/nd/%s/maxcontours" % (name, tag)] = np.asarray(d.maxcontours)
+        for n in (2, 3, 4):
+            out["%s/frac/%d" % (name, n)] = mc.getFractionIndices(mc.weights, n)
+        if mc.chain_offsets is not None:  # getConvergeTests starts with getSeparateChains(): combined chains only
+            if mc.loglikes is None:  # getSeparateChains slices loglikes (chains.py:1519-1525)
+                mc.loglikes = np.zeros(mc.numrows)
+            out[name + "/converge_text"] = np.array(mc.getConvergeTests(what=("MeanVar", "GelmanRubin", "SplitTest")))
+        # the split-test numbers from the reference's own confidence(..., start, end) calls (mcsamples.py:1013-1029)
+        limits = np.array([1 - (1 - 0.95) / 2, (1 - 0.95) / 2])
+        st = np.zeros((mc.n, mc.max_split_tests - 1, 2))
+        for j in range(mc.n):
+            confids = mc.confidence(mc.samples[:, j], limits)
+            for ix in range(mc.max_split_tests - 1):
+                frac = mc.getFractionIndices(mc.weights, ix + 2)
+                for f1, f2 in zip(frac[:-1], frac[1:]):
+                    st[j, ix] += (mc.confidence(mc.samples[:, j], limits, start=f1, end=f2) - confids) ** 2
+                st[j, ix] = np.sqrt(st[j, ix] / (ix + 2)) / mc.sddev[j]
+        out[name + "/split_tests"] = st
+    np.savez_compressed(os.path.join(HERE, "f4.npz"), **out)
+    print("f4 ok", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES) + ["limits"]
+    names = sys.argv[1:] or list(CASES) + ["limits", "f4"]
     for nm in names:
         if nm == "limits":
             run_limits()
+        elif nm == "f4":
+            run_f4()
         else:
             run_case(nm)

@@ -28,21 +28,56 @@ class FakeContext:
         self.X = np.asarray(X, dtype=np.float64)
         self.N, self.P = self.X.shape
         self.w = np.ones(self.N) if w is None else np.asarray(w, dtype=np.float64)
-        self.nchains = 1 if chain_offsets is None else len(chain_offsets) - 1
+        self.offs = np.array([0, self.N]) if chain_offsets is None else np.asarray(chain_offsets)
+        self.nchains = len(self.offs) - 1
 
     def moments(self):
         from oracle.getdist_oracle import weighted_cov, weighted_means, weighted_vars
 
         m = weighted_means(self.X, self.w)
+        cm, cc, cn = [], [], []
+        for a, b in zip(self.offs[:-1], self.offs[1:]):
+            mm = weighted_means(self.X[a:b], self.w[a:b])
+            cm.append(mm)
+            cc.append(weighted_cov(self.X[a:b], self.w[a:b], mm))
+            cn.append(self.w[a:b].sum())
         return dict(means=m, vars=weighted_vars(self.X, self.w, m), cov=weighted_cov(self.X, self.w, m),
                     scalars=np.array([self.w.sum(), (self.w**2).sum(), self.w.max(), 0.0, self.N, self.w.min(), 0, 0]),
-                    xmin=self.X.min(axis=0), xmax=self.X.max(axis=0), chain_means=m[None, :],
-                    chain_covs=np.zeros((1, self.P, self.P)), chain_norms=np.array([self.w.sum()]))
+                    xmin=self.X.min(axis=0), xmax=self.X.max(axis=0), chain_means=np.array(cm),
+                    chain_covs=np.array(cc), chain_norms=np.array(cn))
 
     def weighted_quantiles(self, params, fracs):
         from oracle.getdist_oracle import weighted_quantiles
 
         return np.array([weighted_quantiles(self.X[:, j], self.w, np.asarray(fracs)) for j in params])
+
+    def weighted_quantiles_range(self, params, fracs, start, end):
+        from oracle.getdist_oracle import weighted_quantiles
+
+        return np.array([weighted_quantiles(self.X[start:end, j], self.w[start:end], np.asarray(fracs)) for j in params])
+
+    def weight_fraction_rows(self, fracs):
+        return np.searchsorted(np.cumsum(self.w), np.asarray(fracs) * self.w.sum())
+
+    def set_loglikes(self, ll):
+        self.ll = np.asarray(ll, dtype=np.float64)
+        return float(self.w.dot(self.ll) / self.w.sum())
+
+    def histnd(self, params, nbins, binmin, binmax, which=0):
+        from oracle.getdist_oracle import bin_indices
+
+        flat = np.zeros(self.N, dtype=np.int64)
+        stride = 1
+        for j, n, lo, hi in zip(params, nbins, binmin, binmax):
+            flat += bin_indices(self.X[:, j], lo, (hi - lo) / (n - 1)) * stride
+            stride *= n
+        shape = tuple(int(n) for n in nbins[::-1])
+        if which == 2:
+            out = np.zeros(stride)
+            np.maximum.at(out, flat, np.exp(self.ll.min() - self.ll))
+            return out.reshape(shape)
+        w = self.w if which == 0 else self.w * np.exp(self.w.dot(self.ll) / self.w.sum() - self.ll)
+        return np.bincount(flat, weights=w, minlength=stride).reshape(shape)
 
     def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
         from oracle.getdist_oracle import bin_indices
