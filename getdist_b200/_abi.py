@@ -134,6 +134,8 @@ def load():
     lib.gdk_hist1d_batch.restype = i32
     lib.gdk_hist2d_batch.argtypes = [vp, i32, vp, vp, vp]
     lib.gdk_hist2d_batch.restype = i32
+    lib.gdk_measure_peaks.argtypes = [vp, vp]
+    lib.gdk_measure_peaks.restype = i32
     lib.gdk_weighted_quantiles_range.argtypes = [vp, vp, i32, vp, i32, i64, i64, vp]
     lib.gdk_weighted_quantiles_range.restype = i32
     lib.gdk_weight_fraction_rows.argtypes = [vp, vp, i32, vp]
@@ -303,7 +305,7 @@ class Context:
                                                   C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density2d_batch")
             return None, offsets, list(res)
         if out is None:
-            out = np.empty(total)
+            out = result_buffer(total)
         self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets),
                                               C.cast(res, C.c_void_p), 0), "gdk_density2d_batch")
         return out, offsets, list(res)
@@ -362,6 +364,13 @@ class Context:
             o += int(j[3])
         return res
 
+    def measure_peaks(self):
+        """in-tree microbenchmarks: the roofline denominators of the kernels that are not HBM-bound"""
+        out = np.zeros(8)
+        self._ck(self.lib.gdk_measure_peaks(self.h, _ptr(out)), "gdk_measure_peaks")
+        return dict(fp64_tflops=out[0], smem_updates_per_s=out[1], smem_updates_random_per_s=out[2], l2_red_per_s=out[3],
+                    hbm_read_gbs=out[4])
+
     def timer_start(self):
         self._ck(self.lib.gdk_timer_start(self.h), "gdk_timer_start")
 
@@ -371,8 +380,9 @@ class Context:
     def phase_ms(self):
         return {nm: self.lib.gdk_phase_ms(self.h, i) for i, nm in enumerate(PHASES)}
 
-    KERNEL_SLOTS = ("k_bin8c", "k_bucket_records", "k_hist2d_records", "k_shear_minmax_tiled", "k_shear_hist",
-                    "k_conv2d<0>", "k_conv2d<1>")
+    KERNEL_SLOTS = ("k_bin8c", "k_bucket_records", "k_hist2d_records", "k_shear_minmax_tma", "k_shear_hist_w",
+                    "k_conv2d<0>", "k_conv2d<1>", "k_hist1d_tma", "k_kde1d", "k_qhist", "k_qscan+k_qgather+k_qselect",
+                    "k_col_sums", "k_cov_tiles", "k_xform_rows", "k_xform_cols", "k_bw2d", "k_contours2d", "k_stats_fused")
 
     def set_kernel_timing(self, on):
         self._ck(self.lib.gdk_set_kernel_timing(self.h, 1 if on else 0), "gdk_set_kernel_timing")
@@ -393,6 +403,65 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.gdk_launch_count(self.h))
+
+
+class PinnedPool:
+    """Caching allocator for page-locked host result buffers.  cudaHostAlloc of a gigabyte costs as much as computing
+    the grids that fill it, so blocks are allocated once and recycled: an array handed out here returns its block to the
+    pool when the last view of it is garbage collected (weakref.finalize on the base ndarray).  Results of the batched
+    calls larger than `threshold` bytes are placed in such blocks: device -> host copies then run at full PCIe rate and
+    asynchronously behind the kernels of the next group."""
+
+    threshold = 32 << 20
+
+    def __init__(self):
+        self.free = []  # (bytes, pointer)
+        self.outstanding = 0
+
+    def empty(self, n, dtype=np.float64):
+        import weakref
+
+        need = int(n) * np.dtype(dtype).itemsize
+        need = max((need + (2 << 20) - 1) & ~((2 << 20) - 1), 2 << 20)
+        best = None
+        for k, (sz, _) in enumerate(self.free):
+            if sz >= need and (best is None or sz < self.free[best][0]) and sz <= 2 * need:
+                best = k
+        if best is not None:
+            sz, ptr = self.free.pop(best)
+        else:
+            lib = load()
+            p = C.c_void_p()
+            if lib.gdk_alloc_pinned(need, C.byref(p)) != 0:
+                for _, q in self.free:  # release the cache and retry once
+                    lib.gdk_free_pinned(C.c_void_p(q))
+                self.free = []
+                if lib.gdk_alloc_pinned(need, C.byref(p)) != 0:
+                    raise GdkError("pinned allocation of %d bytes failed" % need)
+            sz, ptr = need, p.value
+        buf = (C.c_char * sz).from_address(ptr)
+        base = np.frombuffer(buf, dtype=np.uint8)
+        self.outstanding += 1
+        weakref.finalize(base, self._release, sz, ptr)
+        return base[: int(n) * np.dtype(dtype).itemsize].view(dtype)
+
+    def _release(self, sz, ptr):
+        self.outstanding -= 1
+        self.free.append((sz, ptr))
+
+    def trim(self):
+        lib = load()
+        for _, q in self.free:
+            lib.gdk_free_pinned(C.c_void_p(q))
+        self.free = []
+
+
+pinned_pool = PinnedPool()
+
+
+def result_buffer(n):
+    """host buffer for n float64 results: pinned (pooled) when large, plain numpy otherwise"""
+    return pinned_pool.empty(n) if n * 8 >= PinnedPool.threshold else np.empty(n)
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -20,6 +20,7 @@
 #include "kernels_stats.cuh"
 #include "gdk_ctx.h"
 #include "gdk_2d.cuh"
+#include "kernels_peak.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // helpers
@@ -114,7 +115,7 @@ extern "C" int32_t gdk_set_kernel_timing(gdk_ctx* ctx, int32_t on) {
     if (!ctx) return GDK_ERR_ARG;
     ctx->ktiming = on != 0;
     ctx->kev_used = 0;
-    while (on && ctx->kev.size() < 512) {  // event pairs are created up front, not inside the timed steps
+    while (on && ctx->kev.size() < 1024) {  // event pairs are created up front, not inside the timed steps
         gdk_ctx::KEv e{};
         if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) break;
         ctx->kev.push_back(e);
@@ -447,7 +448,10 @@ static int compute_moments(gdk_ctx* ctx) {
         const size_t np = segs.size() * (size_t)P * 4;
         if (ctx->scratch.ensure(np)) return gdk_fail(ctx, GDK_ERR_NOMEM, "moment partials");
         dim3 g((unsigned)segs.size(), (unsigned)P);
-        k_col_sums<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, ctx->scratch.p);
+        {
+            KernelTimer kt(ctx, GDK_K_COL_SUMS, (double)N * (P + 1) * 8.0, 2.0 * N * P);
+            k_col_sums<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, ctx->scratch.p);
+        }
         ctx->launches++;
         std::vector<double> part(np);
         CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -499,8 +503,11 @@ static int compute_moments(gdk_ctx* ctx) {
         CK(cudaMemcpyAsync(ctx->dmeans.p, ctx->chain_means.data(), (size_t)nch * P * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         dim3 g((unsigned)segs.size(), (unsigned)nt);
-        k_cov_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, nt, ctx->dtiles.p, ctx->dmeans.p,
-                                                ctx->scratch.p);
+        {
+            KernelTimer kt(ctx, GDK_K_COV_TILES, (double)N * (P + 1) * 8.0, (double)N * P * (P + 1));
+            k_cov_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, nt, ctx->dtiles.p, ctx->dmeans.p,
+                                                    ctx->scratch.p);
+        }
         dim3 g2((unsigned)nt, (unsigned)nch);
         k_cov_reduce<<<g2, 256, 0, ctx->stream>>>(ctx->scratch.p, ctx->segs.p, (int)segs.size(), nt, ctx->dtiles.p, P, ctx->dS.p);
         ctx->launches += 2;
@@ -664,21 +671,31 @@ static int quantiles_impl(gdk_ctx* ctx, const int32_t* params, int32_t np, const
     }
     // pass 1: shared histogram per parameter
     CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B1 * 8, ctx->stream));
-    k_qhist<<<g, 1024, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
-                                                 ctx->qhist.p, dqbase);
+    const double qrows = (double)(row_end - row_begin);
+    {
+        KernelTimer kt(ctx, GDK_K_QHIST, qrows * (np + 1) * 8.0, 0);
+        k_qhist<<<g, 1024, 2 * B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, B1, 1,
+                                                     ctx->qhist.p, dqbase);
+    }
     k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B1, 1, 0, B2_LOG2, ctx->qhist.p);
     ctx->launches += 2;
     int next_state = 2;
     for (int iter = 0; iter < 12; iter++) {
         // refinement pass: one histogram of B2 bins per refining slot
         CK(cudaMemsetAsync(ctx->qhist.p, 0, (size_t)np * QMAXF * B2 * 8, ctx->stream));
-        k_qhist<<<g, 1024, 2 * nf * B2 * 4 + B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p,
-                                                                   ctx->qslots.p, nf, B2, 0, ctx->qhist.p, dqbase);
-        k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B2, 0, next_state, B2_LOG2, ctx->qhist.p);
-        CK(cudaMemsetAsync(ctx->iscratch.p, 0, sizeof(int), ctx->stream));
-        k_qgather<<<g, 256, B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf, ctx->qcand.p,
-                                                   dqbase);
-        k_qselect<<<(unsigned)nslots, 512, 2 * QCAP * 8, ctx->stream>>>(ctx->qslots.p, nf, ctx->qcand.p, B2_LOG2, ctx->iscratch.p);
+        {
+            KernelTimer kt(ctx, GDK_K_QHIST, qrows * np * 8.0, 0);
+            k_qhist<<<g, 1024, 2 * nf * B2 * 4 + B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p,
+                                                                       ctx->qslots.p, nf, B2, 0, ctx->qhist.p, dqbase);
+        }
+        {
+            KernelTimer kt(ctx, GDK_K_QFINISH, qrows * np * 8.0, 0);
+            k_qscan<<<np, 32 * QMAXF, 0, ctx->stream>>>(ctx->qslots.p, nf, B2, 0, next_state, B2_LOG2, ctx->qhist.p);
+            CK(cudaMemsetAsync(ctx->iscratch.p, 0, sizeof(int), ctx->stream));
+            k_qgather<<<g, 256, B1 * 4, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, ctx->segs.p, ctx->qparams.p, ctx->qslots.p, nf,
+                                                       ctx->qcand.p, dqbase);
+            k_qselect<<<(unsigned)nslots, 512, 2 * QCAP * 8, ctx->stream>>>(ctx->qslots.p, nf, ctx->qcand.p, B2_LOG2, ctx->iscratch.p);
+        }
         ctx->launches += 4;
         int nover = 0;
         CK(cudaMemcpyAsync(&nover, ctx->iscratch.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -867,6 +884,7 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
             ctx->h1_tma_smem = std::max<size_t>(smem_tma, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
+        KernelTimer kt(ctx, GDK_K_HIST1D, (double)ctx->N * (n + 1) * 8.0, 0);
         k_hist1d_tma<<<g, 256, smem_tma, ctx->stream>>>(ctx->dX.p, ctx->ld, wq, ctx->segs.p, djt, gb.p, gstride);
     } else {
         if ((size_t)maxF * 8 > ctx->h1_smem) {
@@ -874,6 +892,7 @@ static int run_hist1d(gdk_ctx* ctx, int n, const gdk_spec1d* specs, int64_t* gst
             ctx->h1_smem = (size_t)std::max(maxF * 8, 48 * 1024);
         }
         pt.begin(ctx, GDK_PH_HIST1D);
+        KernelTimer kt(ctx, GDK_K_HIST1D, (double)ctx->N * (n + 1) * 8.0, 0);
         k_hist1d<<<g, 256, maxF * 8, ctx->stream>>>(ctx->dX.p, ctx->ld, wq, ctx->segs.p, ctx->jobs1d.p, gb.p, gstride);
     }
     ctx->launches++;
@@ -955,9 +974,12 @@ extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_
     const int64_t pstride = dev_out ? stride : gstride;
     PhaseTimer pt;
     pt.begin(ctx, GDK_PH_KDE1D);
-    k_kde1d<<<n, 256, use_smem ? smem_need : 0, ctx->stream>>>(ctx->specs1d.p, ctx->gbins.p, gstride, 1.0 / ctx->wscale, ctx->isj,
-                                                               ctx->tabs1d.p, dP, pstride, ctx->res1d.p, ctx->gwork.p, use_smem,
-                                                               likes ? ctx->gbins_l.p : nullptr, 1.0 / ctx->wlscale, dL);
+    {
+        KernelTimer kt(ctx, GDK_K_KDE1D, (double)n * maxF * 16.0, 0);
+        k_kde1d<<<n, 256, use_smem ? smem_need : 0, ctx->stream>>>(ctx->specs1d.p, ctx->gbins.p, gstride, 1.0 / ctx->wscale, ctx->isj,
+                                                                   ctx->tabs1d.p, dP, pstride, ctx->res1d.p, ctx->gwork.p, use_smem,
+                                                                   likes ? ctx->gbins_l.p : nullptr, 1.0 / ctx->wlscale, dL);
+    }
     ctx->launches++;
     pt.end();
     CK(cudaGetLastError());
@@ -1009,5 +1031,72 @@ extern "C" int32_t gdk_lag_sums(gdk_ctx* ctx, int32_t njobs, const gdk_lagjob* j
             for (int c = 0; c < nchunk; c++) t += part[((size_t)i * nchunk + c) * LAG_MAXK + k];
             out[o++] = t;
         }
+    return GDK_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// measured peaks (roofline denominators that MEASURED_PEAKS.json does not hold)
+// -------------------------------------------------------------------------------------------------
+extern "C" int32_t gdk_measure_peaks(gdk_ctx* ctx, double* out) {
+    if (!ctx || !out) return GDK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    auto timed = [&](auto&& launch, int reps) -> double {  // best of `reps` after one warm-up launch, in ms
+        launch();
+        double best = 1e30;
+        for (int r = 0; r < reps; r++) {
+            cudaEventRecord(e0, ctx->stream);
+            launch();
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = std::min(best, (double)ms);
+        }
+        return best;
+    };
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (ctx->scratch.ensure((size_t)ctx->num_sms * 8 * 512 + 64)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+    {  // FP64 FMA
+        const int grid = ctx->num_sms * 4, iters = 8192;
+        const double ms = timed([&] { k_peak_fp64<<<grid, 512, 0, ctx->stream>>>(ctx->scratch.p, iters, 1.0000001, 0.9999999); }, 3);
+        out[0] = 2.0 * 8 * iters * (double)grid * 512 / (ms * 1e-3) / 1e12;  // TFLOP/s
+    }
+    {  // shared-memory 64-bit fixed-point updates (ATOMS + carry + RED)
+        const int grid = ctx->num_sms, iters = 2048;
+        const size_t smem = (size_t)2 * 96 * 96 * 4;
+        CK(cudaFuncSetAttribute(k_peak_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
+        for (int mode = 0; mode < 2; mode++) {
+            const double ms = timed([&] { k_peak_atoms<<<grid, 512, smem, ctx->stream>>>(o, iters, mode); }, 3);
+            out[1 + mode] = 4.0 * iters * (double)grid * 512 / (ms * 1e-3);  // updates/s
+        }
+    }
+    {  // L2 reductions at random addresses of a 32 MB region
+        const size_t nb = (size_t)4 << 20;
+        if (ctx->gbins2.ensure(nb)) return gdk_fail(ctx, GDK_ERR_NOMEM, "peak buffer");
+        CK(cudaMemsetAsync(ctx->gbins2.p, 0, nb * 8, ctx->stream));
+        const int grid = ctx->num_sms * 16, iters = 1024;
+        const double ms = timed([&] { k_peak_l2red<<<grid, 256, 0, ctx->stream>>>(ctx->gbins2.p, (unsigned)(nb - 1), iters); }, 3);
+        out[3] = (double)iters * grid * 256 / (ms * 1e-3);  // reductions/s
+    }
+    {  // HBM read sweep over 2 GB
+        const size_t n = (size_t)1 << 28;  // doubles
+        double* buf = nullptr;
+        if (cudaMalloc(&buf, n * 8) == cudaSuccess) {
+            CK(cudaMemsetAsync(buf, 0, n * 8, ctx->stream));
+            const double ms = timed([&] { k_peak_read<<<ctx->num_sms * 8, 512, 0, ctx->stream>>>(buf, (int64_t)(n / 2), ctx->scratch.p); }, 3);
+            out[4] = (double)n * 8 / (ms * 1e-3) / 1e9;  // GB/s
+            cudaFree(buf);
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ctx->launches += 20;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
     return GDK_OK;
 }

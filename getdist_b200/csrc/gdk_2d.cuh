@@ -787,7 +787,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             dim3 g((unsigned)(g1 - g0), (unsigned)nhseg);
 #define GDK_LAUNCH_SHW(NP_, W_)                                                                                               \
     case NP_: {                                                                                                               \
-        const size_t sm_ = (size_t)NP_ * 2 * W_ * W_ * 4;                                                                     \
+        const size_t sm_ = (size_t)NP_ * 2 * (W_ * W_ + 4) * 4;                                                               \
         CK2(cudaFuncSetAttribute(k_shear_hist_w<NP_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));            \
         k_shear_hist_w<NP_, W_><<<g, 512, sm_, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dWq.p, dhsegs, dsg + g0, dgeom,        \
                                                                ctx->gbins_rot.p);                                            \
@@ -885,8 +885,21 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             CK2(cudaFuncSetAttribute(k_xform_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_r, 48 << 10)));
             CK2(cudaFuncSetAttribute(k_xform_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_c, 48 << 10)));
             dim3 g((unsigned)((G + lines - 1) / lines), (unsigned)(e - b));
-            k_xform_rows<<<g, 256, smem_r, ctx->stream>>>(dx + b, lines);
-            k_xform_cols<<<g, 256, smem_c, ctx->stream>>>(dx + b, lines);
+            {
+                int nfft = 0;
+                for (size_t q = b; q < e; q++) nfft += xjobs[q].aFFT ? 1 : 0;
+                const double G2 = (double)G * G, lg = log2((double)G);
+                // rows: read the histogram, write the real (+ complex) half-transformed lines; cols: read them, write a2 (+ aFFT)
+                KernelTimer kt(ctx, GDK_K_XFORM_ROWS, ((double)(e - b) * 16.0 + nfft * 16.0) * G2, ((double)(e - b) + nfft) * 5.0 * G2 * lg);
+                k_xform_rows<<<g, 256, smem_r, ctx->stream>>>(dx + b, lines);
+            }
+            {
+                int nfft = 0;
+                for (size_t q = b; q < e; q++) nfft += xjobs[q].aFFT ? 1 : 0;
+                const double G2 = (double)G * G, lg = log2((double)G);
+                KernelTimer kt(ctx, GDK_K_XFORM_COLS, ((double)(e - b) * 16.0 + nfft * 24.0) * G2, ((double)(e - b) + nfft) * 5.0 * G2 * lg);
+                k_xform_cols<<<g, 256, smem_c, ctx->stream>>>(dx + b, lines);
+            }
             ctx->launches += 2;
             b = e;
         }
@@ -911,7 +924,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         CK2(cudaFuncSetAttribute(k_bw2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_BW2D);
-        k_bw2d<<<n, ctx->bw2d_threads, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
+        {
+            double abytes = 0;  // a2 (+ |fft2|^2) of every optimised pair read once
+            for (int i = 0; i < n; i++)
+                if (bjobs[i].a2) abytes += (double)bjobs[i].G * bjobs[i].G * 8.0 * (bjobs[i].aFFT ? 2 : 1);
+            KernelTimer kt(ctx, GDK_K_BW2D, abytes, 0);
+            k_bw2d<<<n, ctx->bw2d_threads, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
+        }
         ctx->launches++;
         pt.end();
         CK2(cudaGetLastError());
@@ -1170,7 +1189,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             ctx->launches++;
         }
         if (any_contours) {
-            k_contours2d<<<nj, 1024, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
+            {
+                KernelTimer kt(ctx, GDK_K_CONTOURS2D, cbytes / 2, 0);  // every grid read once
+                k_contours2d<<<nj, 1024, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
+            }
             ctx->launches++;
         }
         if (!dev_out) {

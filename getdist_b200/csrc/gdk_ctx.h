@@ -73,8 +73,8 @@ struct gdk_ctx {
     };
     std::vector<KEv> kev;
     int kev_used = 0;
-    double kbytes[8] = {0}, kflops[8] = {0};
-    int klaunches[8] = {0};
+    double kbytes[24] = {0}, kflops[24] = {0};
+    int klaunches[24] = {0};
     double wall_ms[4] = {0, 0, 0, 0};  // host wall clock of the last 1D / 2D batch call, quantile call (gdk_phase_ms 10..12)
     // sample store
     int64_t N = 0, ld = 0;
@@ -140,7 +140,18 @@ enum {
     GDK_K_SHEAR_HIST = 4,
     GDK_K_CONV2D_0 = 5,
     GDK_K_CONV2D_1 = 6,
-    GDK_K_NSLOT = 8
+    GDK_K_HIST1D = 7,
+    GDK_K_KDE1D = 8,
+    GDK_K_QHIST = 9,
+    GDK_K_QFINISH = 10,  // k_qscan + k_qgather + k_qselect
+    GDK_K_COL_SUMS = 11,
+    GDK_K_COV_TILES = 12,
+    GDK_K_XFORM_ROWS = 13,
+    GDK_K_XFORM_COLS = 14,
+    GDK_K_BW2D = 15,
+    GDK_K_CONTOURS2D = 16,
+    GDK_K_STATS_FUSED = 17,
+    GDK_K_NSLOT = 24
 };
 struct KernelTimer {  // records an event pair around one launch when timing is on
     gdk_ctx* ctx;

@@ -189,7 +189,7 @@ __global__ void k_shear_geom(const double* __restrict__ part, int nseg, int njob
 // Sheared re-binning (kde.bin_samples of (p1, r0*x_i + r1*x_j), kde_bandwidth.py:76-87) with hot-window privatisation:
 // grid (ngroups, nseg) -- GROUPS are the fast grid index, so the CTAs resident at one time sweep the same row
 // segment and the columns they share (an anchor's x_i, the partners it shares with neighbouring anchors) come out
-// of L2 instead of DRAM.  512 threads, one CTA per SM, dynamic smem = NP * W*W * 8 bytes: every job of the group
+// of L2 instead of DRAM.  512 threads, one CTA per SM, dynamic smem = NP * (W*W + 4) * 8 bytes: every job of the group
 // keeps the W x W bins around the centre of its sheared cloud in shared memory (two 32-bit limbs per bin, native
 // ATOMS); the few samples outside the window go to L2 reductions.  NP = partners of the group (exactly; the host
 // launches one instantiation per group size), W = window edge for that size (3 x 96^2, 4 x 80^2, 6 x 64^2 ... fill
@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restric
                                                          const unsigned long long* __restrict__ dWq, const Seg* __restrict__ segs,
                                                          const ShearGroup* __restrict__ groups, const ShearGeom* __restrict__ geom,
                                                          unsigned long long* __restrict__ grids) {
-    extern __shared__ unsigned ssm2[];  // per job: lo[W*W], hi[W*W]
+    extern __shared__ unsigned ssm2[];  // per job: lo[WB], hi[WB], WB = W*W + 4 (bin W*W of job 0 is the trash bin)
+    constexpr unsigned WB = W * W + 4;
     __shared__ ShearGroup g;
     __shared__ ShearGeom gm[SG];
     __shared__ int s_ax0, s_by0[SG];
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restric
         int* dst = reinterpret_cast<int*>(&g);
         for (int i = threadIdx.x; i < (int)(sizeof(ShearGroup) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = threadIdx.x; i < NP * 2 * W * W; i += blockDim.x) ssm2[i] = 0;
+    for (int i = threadIdx.x; i < NP * 2 * (int)WB; i += blockDim.x) ssm2[i] = 0;
     __syncthreads();
     const int G = g.Gb;
     if (threadIdx.x < NP) {
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restric
     // Two rows (2 * NP updates) at a time, written for instruction-level parallelism: all bin indices first (branch
     // free; the exact division is a rare fix-up of the whole group), then all low-limb ATOMS back to back, then the
     // carries into the high limbs, then the few out-of-window samples as L2 reductions.
+    const unsigned trash = smem0 + W * W * 4u;  // spare bin behind window 0: target of the out-of-window samples
     auto update2 = [&](double a0, double a1, unsigned long long w0, unsigned long long w1, const double (&bx)[NP], const double (&by)[NP],
                        bool second) {
         const double d10 = __dsub_rn(a0, p1_min), d11 = __dsub_rn(a1, p1_min);
@@ -279,44 +281,52 @@ __global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restric
                 if (edge(I2[1][k])) b2[1][k] = bin_index_trunc_exact(d2[1][k], gm[k].dx);
             }
         }
+        // a row whose p1 falls outside the grid (samples beyond a hard limit) contributes nothing: weight 0, bin 0
+        if ((unsigned)b1[0] >= (unsigned)G) {
+            b1[0] = 0;
+            w0 = 0;
+        }
+        if ((unsigned)b1[1] >= (unsigned)G || !second) {
+            b1[1] = 0;
+            w1 = 0;
+        }
         const unsigned dxr[2] = {(unsigned)(b1[0] - ax0), (unsigned)(b1[1] - ax0)};
         const unsigned wl[2] = {(unsigned)w0, (unsigned)w1}, wh[2] = {(unsigned)(w0 >> 32), (unsigned)(w1 >> 32)};
-        unsigned addr[2][NP], hit[2][NP], old[2][NP];
-        unsigned miss = 0;
+        // sm_100a cannot predicate shared / global atomics (ptxas turns "@p atom" into a divergent branch with a
+        // convergence barrier per update), so every lane issues its shared-memory update unconditionally: samples
+        // outside the window are pointed at a trash bin behind the windows, and only their L2 reduction sits in a
+        // (short) divergent region: one IMAD.WIDE + REDG.
+        unsigned addr[2][NP], old[2][NP];
+        int gi[2][NP];
+        bool hit[2][NP];
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int k = 0; k < NP; k++) {
                 const unsigned dy = (unsigned)(b2[r][k] - by0[k]);
-                hit[r][k] = (max(dxr[r], dy) < wlim) & (unsigned)(r == 0 || second);
-                miss |= hit[r][k] ^ 1u;
-                addr[r][k] = smem0 + (unsigned)k * (2u * W * W * 4u) + dy * (4u * W) + (dxr[r] << 2);
-                old[r][k] = 0;
+                hit[r][k] = max(dxr[r], dy) < wlim;
+                gi[r][k] = min(max(b2[r][k], 0), G - 1) * G + b1[r];  // p2 ranges cover the samples; the clamp only guards NaNs
+                const unsigned in_win = smem0 + (unsigned)k * (2u * WB * 4u) + dy * (4u * W) + (dxr[r] << 2);
+                addr[r][k] = hit[r][k] ? in_win : trash;
             }
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int k = 0; k < NP; k++)
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
-                             : "+r"(old[r][k])
-                             : "r"(addr[r][k]), "r"(wl[r]), "r"(hit[r][k]));
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[r][k]) : "r"(addr[r][k]), "r"(wl[r]));
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int k = 0; k < NP; k++) {
                 unsigned c;
                 asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(c) : "r"(old[r][k]), "r"(wl[r]), "r"(wh[r]));
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr[r][k] + W * W * 4u),
-                             "r"(c), "r"(hit[r][k]));
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr[r][k] + WB * 4u), "r"(c));
             }
-        if (miss) {
 #pragma unroll
-            for (int r = 0; r < 2; r++)
+        for (int r = 0; r < 2; r++)
 #pragma unroll
-                for (int k = 0; k < NP; k++)
-                    if (!hit[r][k] && (r == 0 || second) && (unsigned)b1[r] < (unsigned)G && (unsigned)b2[r][k] < (unsigned)G && (r ? w1 : w0))
-                        atomicAdd(gk[k] + b2[r][k] * G + b1[r], r ? w1 : w0);
-        }
+            for (int k = 0; k < NP; k++)
+                if (!hit[r][k]) atomicAdd(gk[k] + gi[r][k], r ? w1 : w0);
     };
     // segments start on even rows (16-byte aligned pairs); an odd tail row is handled by thread 0
     const int64_t npair = (sg.r1 - sg.r0) >> 1;
@@ -365,10 +375,10 @@ __global__ void __launch_bounds__(512, 1) k_shear_hist_w(const double* __restric
     if (!wlim) return;
 #pragma unroll 1
     for (int k = 0; k < NP; k++) {
-        const unsigned* base = ssm2 + k * 2 * W * W;
+        const unsigned* base = ssm2 + k * 2 * WB;
         unsigned long long* gk = grids + g.off[k] + (long long)by0[k] * G + ax0;
         for (int t = threadIdx.x; t < W * W; t += blockDim.x) {
-            const unsigned long long v = ((unsigned long long)base[W * W + t] << 32) | base[t];
+            const unsigned long long v = ((unsigned long long)base[WB + t] << 32) | base[t];
             if (v) atomicAdd(gk + (long long)(t / W) * G + (t % W), v);
         }
     }

@@ -1213,9 +1213,11 @@ class MCSamples:
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
             if not kwargs and masks is None and lbuf is None:
-                c = Density2D(x, y, d.P.copy(), view_ranges=d.view_ranges)  # private copy: the caller may normalise d in place
-                c._gdk = d._gdk
-                self._density2D[(j, j2)] = c
+                # the cache entry is a READ-ONLY view into the batch buffer (no second copy of a gigabyte of grids);
+                # get2DDensity / get2DDensityGridData hand out private copies of it (_cached_2d), as the reference
+                # returns a fresh grid per call and callers normalise in place
+                d.P.setflags(write=False)
+                self._density2D[(j, j2)] = d
             out.append(d)
         return out
 
@@ -1468,7 +1470,8 @@ class MCSamples:
     def prefetch_triangle(self, params=None, do_1d=True, do_2d=True):
         """Compute every 1D and (lower-triangle) 2D density of a triangle plot in batched launches and seed
         the caches that get1DDensity / get2DDensity consult.  Pair (x, y) = (params[i], params[k]) for i < k,
-        as getdist.plots.triangle_plot requests them (x = column parameter, y = row parameter)."""
+        as getdist.plots.triangle_plot requests them (x = column parameter, y = row parameter).
+        Returns the cache entries themselves: the 2D grids are read-only views into one (pinned) result buffer."""
         if self.needs_update:
             self.updateBaseStatistics()
         idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]

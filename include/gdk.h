@@ -92,6 +92,12 @@ double gdk_phase_ms(gdk_ctx* ctx, int32_t phase);
 int32_t gdk_set_kernel_timing(gdk_ctx* ctx, int32_t on);
 double gdk_kernel_stat(gdk_ctx* ctx, int32_t slot, int32_t what);
 
+/* In-tree microbenchmarks (a few ms each) for the roofline denominators that are not HBM bandwidth:
+ * out[0] FP64 FMA TFLOP/s; out[1] 64-bit fixed-point shared-memory histogram updates/s (ATOMS + carry + RED), lanes on
+ * distinct banks; out[2] the same on random bins of a 96 x 96 window; out[3] L2 REDG.ADD.64 reductions/s at random
+ * addresses of a 32 MB region; out[4] HBM read GB/s of a 16-byte streaming sweep; out[5..7] reserved (0).        */
+int32_t gdk_measure_peaks(gdk_ctx* ctx, double* out);
+
 /* ---------------------------------------------------------------------------------------------
  * data residency -- replaces WeightedSamples.setSamples / Chains.makeSingle state
  * (chains.py:262-308, 1488-1503) as far as the device copy is concerned.

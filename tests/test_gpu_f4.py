@@ -88,4 +88,4 @@ def test_serial_caller_is_batched():
         # the cache keeps a private copy: normalising a returned grid in place leaves later calls untouched
         a = mc.get2DDensity(0, 1, normalized=True)
         b = mc.get2DDensityGridData(0, 1, get_density=True)
-        assert abs(b.P.max() - 1.0) < 1e-15 and a.P.max() < 1.0
+        assert abs(b.P.max() - 1.0) < 1e-15 and a.P.max() != 1.0
