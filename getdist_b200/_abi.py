@@ -10,6 +10,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgdk.so")
 
 GDK_OUT_DEVICE = 1
 GDK_BW_ONLY = 2
+GDK_OUT_PEERS = 4
+GDK_WIN_G1, GDK_WIN_G2, GDK_WIN_X, GDK_WIN_STATS = 0, 1, 2, 3
+GDK_ROW_BLOCK = 131072
 
 ST_BW_FALLBACK = 1
 ST_BW_FAILED_NONE = 2
@@ -114,6 +117,22 @@ def load():
     lib.gdk_set_samples.restype = i32
     lib.gdk_moments.argtypes = [vp] + [vp] * 9
     lib.gdk_moments.restype = i32
+    lib.gdk_moments_recompute.argtypes = [vp]
+    lib.gdk_moments_recompute.restype = i32
+    lib.gdk_peer_init.argtypes = [vp, i32, i32]
+    lib.gdk_peer_init.restype = i32
+    lib.gdk_window_export.argtypes = [vp, i32, u64, vp, vp]
+    lib.gdk_window_export.restype = i32
+    lib.gdk_window_import.argtypes = [vp, i32, i32, vp]
+    lib.gdk_window_import.restype = i32
+    lib.gdk_window_read.argtypes = [vp, i32, u64, u64, vp]
+    lib.gdk_window_read.restype = i32
+    lib.gdk_samples_prepare.argtypes = [vp, i64, i32, vp, i32]
+    lib.gdk_samples_prepare.restype = i32
+    lib.gdk_samples_upload.argtypes = [vp, vp, i64, i64, vp, i64, i64]
+    lib.gdk_samples_upload.restype = i32
+    lib.gdk_samples_finish.argtypes = [vp]
+    lib.gdk_samples_finish.restype = i32
     lib.gdk_weighted_quantiles.argtypes = [vp, vp, i32, vp, i32, vp]
     lib.gdk_weighted_quantiles.restype = i32
     lib.gdk_density1d_batch.argtypes = [vp, i32, vp, vp, i64, vp, u32]
@@ -142,7 +161,7 @@ def load():
     lib.gdk_weight_fraction_rows.restype = i32
     lib.gdk_histnd.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp]
     lib.gdk_histnd.restype = i32
-    if lib.gdk_abi_version() != 5:
+    if lib.gdk_abi_version() != 6:
         raise GdkError("libgdk.so ABI version mismatch")
     _lib = lib
     return lib
@@ -180,7 +199,7 @@ class Context:
         if rc != 0:
             raise GdkError("%s failed (code %d): %s" % (what, rc, self.lib.gdk_last_error(self.h).decode()))
 
-    def set_samples(self, X, w=None, chain_offsets=None):
+    def set_samples(self, X, w=None, chain_offsets=None, group=None):
         X = np.asarray(X)
         if X.dtype != np.float64 or X.ndim != 2:
             raise GdkError("samples must be a 2D float64 array")
@@ -197,8 +216,56 @@ class Context:
             co = np.ascontiguousarray(chain_offsets, dtype=np.int64)
             nch = co.size - 1
         self._keep = (X, w, co)
-        self._ck(self.lib.gdk_set_samples(self.h, _ptr(X), N, P, rs, cs, _ptr(w), _ptr(co), nch), "gdk_set_samples")
+        if group is None or group.world == 1:
+            self._ck(self.lib.gdk_set_samples(self.h, _ptr(X), N, P, rs, cs, _ptr(w), _ptr(co), nch), "gdk_set_samples")
+        else:
+            # sharded upload: this rank copies its row block over PCIe and stores it into every peer's column store over
+            # NVLink; the peers do the same with theirs (include/gdk.h, "multi-GPU")
+            self.peer_init(group.rank, group.world)
+            self._ck(self.lib.gdk_samples_prepare(self.h, N, P, _ptr(co), nch), "gdk_samples_prepare")
+            ld = (N + 63) & ~63
+            nblk = self.stat_block_count(N, co)
+            group.map_window(self, GDK_WIN_X, ld * P * 8)
+            group.map_window(self, GDK_WIN_STATS, nblk * (3 * P + 1 + P * P) * 8)
+            r0, r1 = group.row_range(N)
+            group.barrier()  # nobody is still reading the previous contents of the stores
+            self._ck(self.lib.gdk_samples_upload(self.h, _ptr(X), rs, cs, _ptr(w), r0, r1), "gdk_samples_upload")
+            group.barrier()  # every rank's rows and statistics records have landed
+            self._ck(self.lib.gdk_samples_finish(self.h), "gdk_samples_finish")
         self.N, self.P, self.nchains = N, P, max(nch, 1)
+
+    @staticmethod
+    def stat_block_count(N, chain_offsets=None):
+        """number of statistics blocks (GDK_ROW_BLOCK rows, cut at chain boundaries) of a data set"""
+        co = [0, N] if chain_offsets is None else [int(c) for c in chain_offsets]
+        n = 0
+        for a, b in zip(co[:-1], co[1:]):
+            n += (b - 1) // GDK_ROW_BLOCK - a // GDK_ROW_BLOCK + 1
+        return n
+
+    # -- multi-GPU windows (include/gdk.h) ------------------------------------------------------------------------
+    def peer_init(self, rank, nranks):
+        self._ck(self.lib.gdk_peer_init(self.h, rank, nranks), "gdk_peer_init")
+
+    def window_export(self, window, nbytes):
+        """(device address, 64-byte IPC handle) of a window of at least nbytes"""
+        handle = C.create_string_buffer(64)
+        addr = C.c_uint64()
+        self._ck(self.lib.gdk_window_export(self.h, window, int(nbytes), C.cast(handle, C.c_void_p), C.cast(C.byref(addr), C.c_void_p)),
+                 "gdk_window_export")
+        return int(addr.value), handle.raw
+
+    def window_import(self, window, peer, handle):
+        buf = C.create_string_buffer(handle, 64)
+        self._ck(self.lib.gdk_window_import(self.h, window, peer, C.cast(buf, C.c_void_p)), "gdk_window_import")
+
+    def window_read(self, window, offset, out):
+        """device -> host copy of out.nbytes bytes of a window starting at byte `offset`"""
+        self._ck(self.lib.gdk_window_read(self.h, window, int(offset), int(out.nbytes), _ptr(out)), "gdk_window_read")
+        return out
+
+    def moments_recompute(self):
+        self._ck(self.lib.gdk_moments_recompute(self.h), "gdk_moments_recompute")
 
     def set_loglikes(self, loglikes):
         """uploads the log-likelihoods, builds the mean-likelihood weights on the device, returns mean_loglike"""
@@ -254,10 +321,10 @@ class Context:
         self._ck(self.lib.gdk_histnd(self.h, params.size, _ptr(params), _ptr(nb), _ptr(lo), _ptr(hi), int(which), _ptr(out)), "gdk_histnd")
         return out.reshape(tuple(int(n) for n in nb[::-1]))
 
-    def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
+    def density1d_batch(self, specs, out=None, device_ptr=None, likes=False, stride=None, peers=False):
         n = len(specs)
         arr = (Spec1D * n)(*specs)
-        stride = max(s.fine_bins for s in specs)
+        stride = max(s.fine_bins for s in specs) if stride is None else int(stride)
         res = (Result1D * n)()
         if likes:  # get1DDensityGridData(meanlikes=True): (P, likes, results)
             P, L = np.empty((n, stride)), np.empty((n, stride))
@@ -266,7 +333,8 @@ class Context:
             return P, L, list(res)
         if device_ptr is not None:
             self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), stride,
-                                                  C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density1d_batch")
+                                                  C.cast(res, C.c_void_p), GDK_OUT_PEERS if peers else GDK_OUT_DEVICE),
+                     "gdk_density1d_batch")
             return None, list(res)
         P = np.empty((n, stride)) if out is None else out
         self._ck(self.lib.gdk_density1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(P), stride, C.cast(res, C.c_void_p), 0),
@@ -281,7 +349,7 @@ class Context:
         self._ck(self.lib.gdk_hist1d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), stride), "gdk_hist1d_batch")
         return out
 
-    def density2d_batch(self, specs, out=None, device_ptr=None, likes=False):
+    def density2d_batch(self, specs, out=None, device_ptr=None, likes=False, offsets=None, peers=False):
         n = len(specs)
         if isinstance(specs, np.ndarray):  # structured array with the gdk_spec2d layout (vectorised planner)
             assert specs.dtype.itemsize == C.sizeof(Spec2D) and specs.flags.c_contiguous
@@ -291,8 +359,12 @@ class Context:
         else:
             arr = (Spec2D * n)(*specs)
             sizes = np.array([s.fine_bins * s.fine_bins for s in specs], dtype=np.int64)
-        offsets = np.zeros(n, dtype=np.int64)
-        offsets[1:] = np.cumsum(sizes)[:-1]
+        if offsets is None:
+            offsets = np.zeros(n, dtype=np.int64)
+            offsets[1:] = np.cumsum(sizes)[:-1]
+        else:  # the caller's layout (gathered multi-GPU window): element offsets from device_ptr
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            assert offsets.size == n and device_ptr is not None
         total = int(sizes.sum())
         res = (Result2D * n)()
         if likes:  # get2DDensityGridData(meanlikes=True): (P, likes, offsets, results)
@@ -302,7 +374,8 @@ class Context:
             return out, lout, offsets, list(res)
         if device_ptr is not None:
             self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), _ptr(offsets),
-                                                  C.cast(res, C.c_void_p), GDK_OUT_DEVICE), "gdk_density2d_batch")
+                                                  C.cast(res, C.c_void_p), GDK_OUT_PEERS if peers else GDK_OUT_DEVICE),
+                     "gdk_density2d_batch")
             return None, offsets, list(res)
         if out is None:
             out = result_buffer(total)

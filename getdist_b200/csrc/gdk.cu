@@ -223,6 +223,9 @@ extern "C" void gdk_destroy(gdk_ctx* ctx) {
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
+    for (int w = 0; w < GDK_NWINDOW; w++)
+        for (int p = 0; p < ctx->nranks; p++)
+            if (p != ctx->rank && ctx->peer_ptr[w][p]) cudaIpcCloseMemHandle(ctx->peer_ptr[w][p]);
     delete ctx;  // DevBuf destructors free device memory
 }
 
@@ -263,10 +266,155 @@ extern "C" double gdk_phase_ms(gdk_ctx* ctx, int32_t phase) {
 // -------------------------------------------------------------------------------------------------
 // data residency
 // -------------------------------------------------------------------------------------------------
-extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
-                                   int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains) {
+// Stat blocks (kernels_stats.cuh): ST_BLOCK-row blocks cut at chain boundaries, each divided into segments at absolute
+// multiples of ST_SEG rows.  The layout depends on N and the chain offsets only.
+static int stats_layout(gdk_ctx* ctx) {
+    ctx->sblocks.clear();
+    ctx->ssegs_h.clear();
+    for (int ch = 0; ch < ctx->nchains; ch++) {
+        const int64_t a = ctx->chain_off[ch], b = ctx->chain_off[ch + 1];
+        int64_t r = a;
+        while (r < b) {
+            const int64_t e = std::min<int64_t>(b, (r / ST_BLOCK + 1) * ST_BLOCK);
+            gdk_ctx::StatBlock blk{r, e, ch, (int)ctx->ssegs_h.size(), 0};
+            int64_t q = r;
+            while (q < e) {
+                const int64_t qe = std::min<int64_t>(e, (q / ST_SEG + 1) * ST_SEG);
+                ctx->ssegs_h.push_back(Seg{q, qe, ch, 0});
+                q = qe;
+            }
+            blk.nseg = (int)ctx->ssegs_h.size() - blk.seg0;
+            ctx->sblocks.push_back(blk);
+            r = e;
+        }
+    }
+    ctx->sblock_done.assign(ctx->sblocks.size(), 0);
+    const int P = ctx->P;
+    const int T = (P + ST_T - 1) / ST_T;
+    std::vector<int2> tiles;
+    for (int x = 0; x < T; x++)
+        for (int y = x; y < T; y++) tiles.push_back(int2{x, y});
+    ctx->stT = T;
+    ctx->stNtile = (int)tiles.size();
+    std::vector<int2> blkseg(ctx->sblocks.size());
+    std::vector<int> blkout(ctx->sblocks.size());
+    for (size_t i = 0; i < ctx->sblocks.size(); i++) {
+        blkseg[i] = int2{ctx->sblocks[i].seg0, ctx->sblocks[i].nseg};
+        blkout[i] = (int)i;
+    }
+    if (ctx->ssegs.ensure(ctx->ssegs_h.size()) || ctx->sblkseg.ensure(blkseg.size()) || ctx->sblkout.ensure(blkout.size()) ||
+        ctx->stiles.ensure(tiles.size()) || ctx->dblock.ensure(ctx->sblocks.size() * (size_t)st_block_stride(P)))
+        return gdk_fail(ctx, GDK_ERR_NOMEM, "statistics buffers");
+    CK(cudaMemcpyAsync(ctx->ssegs.p, ctx->ssegs_h.data(), ctx->ssegs_h.size() * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sblkseg.p, blkseg.data(), blkseg.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->sblkout.p, blkout.data(), blkout.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->stiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// fused statistics of the stat blocks that lie inside rows [ra, rb), on stream st with partial buffer k
+static int stats_rows(gdk_ctx* ctx, int64_t ra, int64_t rb, cudaStream_t st, int k) {
+    int b0 = -1, b1 = -1;
+    for (size_t i = 0; i < ctx->sblocks.size(); i++)
+        if (ctx->sblocks[i].r0 >= ra && ctx->sblocks[i].r1 <= rb) {
+            if (b0 < 0) b0 = (int)i;
+            b1 = (int)i + 1;
+        }
+    if (b0 < 0) return 0;
+    const int P = ctx->P, T = ctx->stT, nt = ctx->stNtile;
+    const int s0 = ctx->sblocks[b0].seg0, s1 = ctx->sblocks[b1 - 1].seg0 + ctx->sblocks[b1 - 1].nseg;
+    if (ctx->spart[k].ensure((size_t)(s1 - s0) * (size_t)st_part_stride(T, nt))) return gdk_fail(ctx, GDK_ERR_NOMEM, "statistics partials");
+    double rows = 0;
+    for (int i = b0; i < b1; i++) rows += (double)(ctx->sblocks[i].r1 - ctx->sblocks[i].r0);
+    {
+        KernelTimer kt(ctx, GDK_K_STATS_FUSED, rows * (P + 1) * 8.0, rows * 2.0 * nt * ST_T * ST_T);
+        dim3 g((unsigned)(s1 - s0), (unsigned)nt);
+        k_stats_fused<<<g, 64, 0, st>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->ssegs.p + s0, P, T, nt, ctx->stiles.p, ctx->spart[k].p);
+    }
+    k_stats_merge<<<b1 - b0, 256, 3 * P * sizeof(double), st>>>(ctx->spart[k].p, ctx->ssegs.p, ctx->sblkseg.p + b0, ctx->sblkout.p + b0, s0,
+                                                                ctx->dX.p, ctx->ld, P, T, nt, ctx->dblock.p);
+    ctx->launches += 2;
+    for (int i = b0; i < b1; i++) ctx->sblock_done[i] = 1;
+    return 0;
+}
+
+extern "C" int32_t gdk_peer_init(gdk_ctx* ctx, int32_t rank, int32_t nranks) {
     if (!ctx) return GDK_ERR_ARG;
-    if (!X || N <= 0 || P <= 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_set_samples: bad shape N=%lld P=%d", (long long)N, P);
+    if (nranks < 1 || nranks > GDK_MAX_RANKS || rank < 0 || rank >= nranks) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_peer_init: rank %d of %d", rank, nranks);
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return GDK_OK;
+}
+
+static int window_buffer(gdk_ctx* ctx, int window, uint64_t bytes, void** ptr) {
+    switch (window) {
+        case GDK_WIN_G1:
+        case GDK_WIN_G2:
+            if (ctx->win[window].ensure((size_t)(bytes + 7) / 8)) return gdk_fail(ctx, GDK_ERR_NOMEM, "result window (%llu bytes)", (unsigned long long)bytes);
+            *ptr = ctx->win[window].p;
+            return 0;
+        case GDK_WIN_X:
+            if (!ctx->dX.p || ctx->dX.cap * 8 < bytes) return gdk_fail(ctx, GDK_ERR_STATE, "sample window: call gdk_samples_prepare first");
+            *ptr = ctx->dX.p;
+            return 0;
+        case GDK_WIN_STATS:
+            if (!ctx->dblock.p || ctx->dblock.cap * 8 < bytes) return gdk_fail(ctx, GDK_ERR_STATE, "statistics window: call gdk_samples_prepare first");
+            *ptr = ctx->dblock.p;
+            return 0;
+    }
+    return gdk_fail(ctx, GDK_ERR_ARG, "unknown window %d", window);
+}
+
+extern "C" int32_t gdk_window_export(gdk_ctx* ctx, int32_t window, uint64_t bytes, void* handle64, uint64_t* dptr) {
+    if (!ctx || !handle64 || !dptr) return GDK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    int rc = window_buffer(ctx, window, bytes, &p);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    *dptr = (uint64_t)(uintptr_t)p;
+    ctx->peer_ptr[window][ctx->rank] = p;
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_window_import(gdk_ctx* ctx, int32_t window, int32_t peer, const void* handle64) {
+    if (!ctx || !handle64 || window < 0 || window >= GDK_NWINDOW || peer < 0 || peer >= ctx->nranks) return GDK_ERR_ARG;
+    if (peer == ctx->rank) return GDK_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->peer_ptr[window][peer]) {
+        cudaIpcCloseMemHandle(ctx->peer_ptr[window][peer]);
+        ctx->peer_ptr[window][peer] = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gdk_fail(ctx, GDK_ERR_CUDA, "cudaIpcOpenMemHandle(window %d, peer %d): %s", window, peer, cudaGetErrorString(e));
+    }
+    ctx->peer_ptr[window][peer] = p;
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_window_read(gdk_ctx* ctx, int32_t window, uint64_t offset, uint64_t bytes, void* host_out) {
+    if (!ctx || !host_out) return GDK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    int rc = window_buffer(ctx, window, offset + bytes, &p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(host_out, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GDK_OK;
+}
+
+extern "C" int32_t gdk_samples_prepare(gdk_ctx* ctx, int64_t N, int32_t P, const int64_t* chain_offsets, int32_t nchains) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (N <= 0 || P <= 0) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_samples_prepare: bad shape N=%lld P=%d", (long long)N, P);
     CK(cudaSetDevice(ctx->device));
     ctx->have_moments = false;
     ctx->have_loglikes = false;
@@ -287,25 +435,56 @@ extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int
     }
     if (ctx->dX.ensure((size_t)ctx->ld * P) || ctx->dW.ensure((size_t)ctx->ld) || ctx->dWq.ensure((size_t)ctx->ld))
         return gdk_fail(ctx, GDK_ERR_NOMEM, "sample store (%lld x %d)", (long long)N, P);
+    return stats_layout(ctx);
+}
+
+// Rows [row_begin, row_end) of X (and all of w) from the host: chunked H2D into a row-major staging buffer, transposed
+// into the column store on the device while the next chunk is copied (two staging buffers, two streams).  Behind every
+// chunk, on the same stream: the fused statistics of its stat blocks, and -- with peers -- the push of its rows into
+// every peer's column store over NVLink.  X points at row 0 of the full matrix.
+extern "C" int32_t gdk_samples_upload(gdk_ctx* ctx, const double* X, int64_t row_stride, int64_t col_stride, const double* w,
+                                      int64_t row_begin, int64_t row_end) {
+    if (!ctx) return GDK_ERR_ARG;
+    const int64_t N = ctx->N;
+    const int P = ctx->P;
+    if (!X || N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "gdk_samples_upload: call gdk_samples_prepare first");
+    if (row_begin < 0 || row_end > N || row_begin > row_end || (row_begin % ST_BLOCK) || (row_end != N && (row_end % ST_BLOCK)))
+        return gdk_fail(ctx, GDK_ERR_ARG, "row range [%lld, %lld) must be cut at multiples of %d rows", (long long)row_begin, (long long)row_end, ST_BLOCK);
+    CK(cudaSetDevice(ctx->device));
+    ctx->row_begin = row_begin;
+    ctx->row_end = row_end;
     PhaseTimer pt;
     pt.begin(ctx, GDK_PH_UPLOAD);
+    // weights first: the statistics of the first chunk need them
+    ctx->unit_weights = (w == nullptr);
+    if (w) {
+        CK(cudaMemcpyAsync(ctx->dW.p, w, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->dW.p, N, 1.0);
+        ctx->launches++;
+    }
+    const int nb = ctx->num_sms * 4;
+    if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
+    k_wstats<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, N, ctx->scratch.p);
+    ctx->launches++;
+    std::vector<double> part((size_t)nb * 4);
+    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    const int64_t rows_all = row_end - row_begin;
     if (col_stride == 1 && row_stride >= P) {
-        // C-ordered rows: chunked H2D into a row-major staging buffer, transposed on the device while the
-        // next chunk is copied (two staging buffers, two streams)
-        int64_t chunk = std::max<int64_t>(1024, (int64_t)(128ll << 20) / ((int64_t)P * 8));
-        chunk = std::min(chunk, N);
-        if (ctx->stage[0].ensure((size_t)chunk * P) || ctx->stage[1].ensure((size_t)chunk * P))
+        // chunk = a whole number of stat blocks, about 128 MB
+        int64_t chunk = std::max<int64_t>(1, (int64_t)(128ll << 20) / ((int64_t)P * 8) / ST_BLOCK) * ST_BLOCK;
+        const int64_t stage_rows = std::min(chunk, std::max<int64_t>(rows_all, 1));
+        if (ctx->stage[0].ensure((size_t)stage_rows * P) || ctx->stage[1].ensure((size_t)stage_rows * P))
             return gdk_fail(ctx, GDK_ERR_NOMEM, "staging buffers");
         cudaEvent_t done[2];
         CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
         cudaStream_t st[2] = {ctx->stream, ctx->stream2};
-        // stream2 must not start before earlier work on stream (event chain)
-        CK(cudaEventRecord(done[0], ctx->stream));
+        CK(cudaEventRecord(done[0], ctx->stream));  // stream2 must not start before the weights are in place
         CK(cudaStreamWaitEvent(ctx->stream2, done[0], 0));
         int k = 0;
-        for (int64_t r0 = 0; r0 < N; r0 += chunk, k ^= 1) {
-            const int64_t rows = std::min(chunk, N - r0);
+        for (int64_t r0 = row_begin; r0 < row_end; r0 += chunk, k ^= 1) {
+            const int64_t rows = std::min(chunk, row_end - r0);
             if (row_stride == P)
                 CK(cudaMemcpyAsync(ctx->stage[k].p, X + r0 * row_stride, (size_t)rows * P * 8, cudaMemcpyHostToDevice, st[k]));
             else
@@ -314,36 +493,62 @@ extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int
             dim3 g((unsigned)((rows + 31) / 32), (unsigned)((P + 31) / 32));
             k_transpose_in<<<g, 256, 0, st[k]>>>(ctx->stage[k].p, rows, P, ctx->dX.p, ctx->ld, r0);
             ctx->launches++;
+            for (int p = 0; p < ctx->nranks; p++) {
+                if (p == ctx->rank) continue;
+                double* px = (double*)ctx->peer_ptr[GDK_WIN_X][p];
+                if (!px) return gdk_fail(ctx, GDK_ERR_STATE, "sample window of peer %d is not mapped", p);
+                CK(cudaMemcpy2DAsync(px + r0, (size_t)ctx->ld * 8, ctx->dX.p + r0, (size_t)ctx->ld * 8, (size_t)rows * 8, (size_t)P,
+                                     cudaMemcpyDeviceToDevice, st[k]));
+            }
+            int rc = stats_rows(ctx, r0, r0 + rows, st[k], k);
+            if (rc) return rc;
         }
         CK(cudaEventRecord(done[1], ctx->stream2));
         CK(cudaStreamWaitEvent(ctx->stream, done[1], 0));
-        CK(cudaStreamSynchronize(ctx->stream));
         cudaEventDestroy(done[0]);
         cudaEventDestroy(done[1]);
     } else if (row_stride == 1 && col_stride >= N) {
-        for (int j = 0; j < P; j++)
-            CK(cudaMemcpyAsync(ctx->dX.p + (int64_t)j * ctx->ld, X + (int64_t)j * col_stride, (size_t)N * 8, cudaMemcpyHostToDevice,
-                               ctx->stream));
+        if (rows_all > 0) {
+            CK(cudaMemcpy2DAsync(ctx->dX.p + row_begin, (size_t)ctx->ld * 8, X + row_begin, (size_t)col_stride * 8, (size_t)rows_all * 8,
+                                 (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+            for (int p = 0; p < ctx->nranks; p++) {
+                if (p == ctx->rank) continue;
+                double* px = (double*)ctx->peer_ptr[GDK_WIN_X][p];
+                if (!px) return gdk_fail(ctx, GDK_ERR_STATE, "sample window of peer %d is not mapped", p);
+                CK(cudaMemcpy2DAsync(px + row_begin, (size_t)ctx->ld * 8, ctx->dX.p + row_begin, (size_t)ctx->ld * 8, (size_t)rows_all * 8,
+                                     (size_t)P, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            const int64_t step = (int64_t)16 * ST_BLOCK;
+            for (int64_t r0 = row_begin; r0 < row_end; r0 += step) {
+                int rc = stats_rows(ctx, r0, std::min(row_end, r0 + step), ctx->stream, 0);
+                if (rc) return rc;
+            }
+        }
     } else {
         return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "samples must be C- or F-contiguous along one axis (strides %lld, %lld)",
                         (long long)row_stride, (long long)col_stride);
     }
-    // weights
-    ctx->unit_weights = (w == nullptr);
-    if (w) {
-        CK(cudaMemcpyAsync(ctx->dW.p, w, (size_t)N * 8, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->dW.p, N, 1.0);
-        ctx->launches++;
+    // this rank's stat-block records to the peers
+    if (ctx->nranks > 1) {
+        int b0 = -1, b1 = -1;
+        for (size_t i = 0; i < ctx->sblocks.size(); i++)
+            if (ctx->sblocks[i].r0 >= row_begin && ctx->sblocks[i].r1 <= row_end) {
+                if (b0 < 0) b0 = (int)i;
+                b1 = (int)i + 1;
+            }
+        const size_t bs = (size_t)st_block_stride(P);
+        for (int p = 0; p < ctx->nranks && b0 >= 0; p++) {
+            if (p == ctx->rank) continue;
+            double* pb = (double*)ctx->peer_ptr[GDK_WIN_STATS][p];
+            if (!pb) return gdk_fail(ctx, GDK_ERR_STATE, "statistics window of peer %d is not mapped", p);
+            CK(cudaMemcpyAsync(pb + (size_t)b0 * bs, ctx->dblock.p + (size_t)b0 * bs, (size_t)(b1 - b0) * bs * 8, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+        }
     }
-    // weight statistics and fixed-point weights
-    const int nb = ctx->num_sms * 4;
-    if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
-    k_wstats<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, N, ctx->scratch.p);
-    ctx->launches++;
-    std::vector<double> part((size_t)nb * 4);
-    CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    pt.end();
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    // weight statistics (every rank holds all the weights)
     double sw = 0, sw2 = 0, mx = -INFINITY, mn = INFINITY;
     for (int i = 0; i < nb; i++) {
         sw += part[i * 4 + 0];
@@ -357,24 +562,54 @@ extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int
     ctx->sum_w2 = sw2;
     ctx->max_w = mx;
     ctx->min_w = mn;
+    return GDK_OK;
+}
+
+static int combine_moments(gdk_ctx* ctx);
+
+// After every rank's rows (and stat-block records) have arrived: fixed-point weights, outlier count, and the merge of
+// the stat blocks into per-chain and total moments.
+extern "C" int32_t gdk_samples_finish(gdk_ctx* ctx) {
+    if (!ctx) return GDK_ERR_ARG;
+    const int64_t N = ctx->N;
+    if (N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "gdk_samples_finish: no samples");
+    CK(cudaSetDevice(ctx->device));
+    const int nb = ctx->num_sms * 4;
     // scale 2^k with sum(w)*2^k < 2^61 (headroom for rounding of N terms)
     int e = 0;
-    frexp(sw, &e);  // sw = m * 2^e, m in [0.5, 1)
+    frexp(ctx->sum_w, &e);  // sw = m * 2^e, m in [0.5, 1)
     ctx->wshift = 61 - e;
     ctx->wscale = ldexp(1.0, ctx->wshift);
-    const double mean_mult = sw / (double)N;
+    const double mean_mult = ctx->sum_w / (double)N;
     const double mult_max = (mean_mult * (double)N) / (double)std::min<int64_t>(N / 2, 500);  // mcsamples.py:559
+    if (ctx->scratch.ensure((size_t)nb * 4 + 16)) return gdk_fail(ctx, GDK_ERR_NOMEM, "scratch");
     unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->scratch.p);
     CK(cudaMemsetAsync(acc, 0, 16, ctx->stream));
     k_make_wq<<<nb, 256, 0, ctx->stream>>>(ctx->dW.p, N, ctx->wscale, mult_max, ctx->dWq.p, acc);
     ctx->launches++;
     unsigned long long h[2];
     CK(cudaMemcpyAsync(h, acc, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    pt.end();
+    if (ctx->nranks > 1)  // the peers' records are in place (the caller's barrier): all blocks are valid
+        for (auto& d : ctx->sblock_done) d = 1;
+    bool all = true;
+    for (char d : ctx->sblock_done) all = all && d;
+    int rc = all ? combine_moments(ctx) : 0;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->wq_total = h[0];
     ctx->n_outliers = (double)h[1];
-    return GDK_OK;
+    return rc;
+}
+
+extern "C" int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
+                                   int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (!X) return gdk_fail(ctx, GDK_ERR_ARG, "gdk_set_samples: null samples");
+    if (ctx->nranks > 1) return gdk_fail(ctx, GDK_ERR_STATE, "gdk_set_samples on a multi-rank context: use prepare / upload / finish");
+    int rc = gdk_samples_prepare(ctx, N, P, chain_offsets, nchains);
+    if (rc) return rc;
+    rc = gdk_samples_upload(ctx, X, row_stride, col_stride, w, 0, N);
+    if (rc) return rc;
+    return gdk_samples_finish(ctx);
 }
 
 extern "C" int32_t gdk_set_loglikes(gdk_ctx* ctx, const double* loglikes, int64_t n, double* mean_loglike_out) {
@@ -430,106 +665,103 @@ extern "C" int32_t gdk_set_loglikes(gdk_ctx* ctx, const double* loglikes, int64_
 // -------------------------------------------------------------------------------------------------
 // moments
 // -------------------------------------------------------------------------------------------------
+// Host merge of the stat-block records (row order, per chain) into per-chain means / centred second moments, then the
+// totals; the order is fixed by the data layout, so the result is the same on 1 and on N ranks.
+static int combine_moments(gdk_ctx* ctx) {
+    const int P = ctx->P, nch = ctx->nchains;
+    const size_t bs = (size_t)st_block_stride(P), nblk = ctx->sblocks.size();
+    std::vector<double> rec(nblk * bs);
+    CK(cudaMemcpyAsync(rec.data(), ctx->dblock.p, rec.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->chain_means.assign((size_t)nch * P, 0.0);
+    ctx->chain_norm.assign(nch, 0.0);
+    ctx->chain_S.assign((size_t)nch * P * P, 0.0);
+    ctx->xmin.assign(P, INFINITY);
+    ctx->xmax.assign(P, -INFINITY);
+    std::vector<double> D(P);
+    for (size_t b = 0; b < nblk; b++) {
+        const double* r = &rec[b * bs];
+        const int ch = ctx->sblocks[b].chain;
+        for (int j = 0; j < P; j++) {
+            ctx->xmin[j] = std::min(ctx->xmin[j], r[1 + P + j]);
+            ctx->xmax[j] = std::max(ctx->xmax[j], r[1 + 2 * P + j]);
+        }
+        const double Ab = r[0];
+        if (!(Ab > 0)) continue;
+        double& A = ctx->chain_norm[ch];
+        double* m = &ctx->chain_means[(size_t)ch * P];
+        double* S = &ctx->chain_S[(size_t)ch * P * P];
+        const double* Sb = r + 3 * P + 1;
+        if (!(A > 0)) {
+            for (int j = 0; j < P; j++) m[j] = r[1 + j];
+            for (size_t e = 0; e < (size_t)P * P; e++) S[e] = Sb[e];
+            A = Ab;
+            continue;
+        }
+        const double W = A + Ab, f = A * Ab / W;
+        for (int j = 0; j < P; j++) D[j] = r[1 + j] - m[j];
+        for (int i = 0; i < P; i++) {
+            const double fi = f * D[i];
+            for (int j = 0; j < P; j++) S[(size_t)i * P + j] += Sb[(size_t)i * P + j] + fi * D[j];
+        }
+        for (int j = 0; j < P; j++) m[j] += D[j] * (Ab / W);
+        A = W;
+    }
+    ctx->means.assign(P, 0.0);
+    double norm = 0;
+    for (int ch = 0; ch < nch; ch++) norm += ctx->chain_norm[ch];
+    ctx->norm = norm;
+    for (int j = 0; j < P; j++) {
+        // total mean as the weighted mean of the chain means about the first chain's (no cancellation)
+        const double ref = ctx->chain_means[j];
+        double t = 0;
+        for (int ch = 0; ch < nch; ch++) t += ctx->chain_norm[ch] * (ctx->chain_means[(size_t)ch * P + j] - ref);
+        ctx->means[j] = ref + t / norm;
+    }
+    // global covariance: sum_c (S_c + W_c d_c d_c^T) / W with d_c = m_c - m  (no cancellation)
+    ctx->cov.assign((size_t)P * P, 0.0);
+    for (int i = 0; i < P; i++)
+        for (int j = i; j < P; j++) {
+            double t = 0;
+            for (int ch = 0; ch < nch; ch++) {
+                const double di = ctx->chain_means[(size_t)ch * P + i] - ctx->means[i];
+                const double dj = ctx->chain_means[(size_t)ch * P + j] - ctx->means[j];
+                t += ctx->chain_S[((size_t)ch * P + i) * P + j] + ctx->chain_norm[ch] * di * dj;
+            }
+            ctx->cov[(size_t)i * P + j] = ctx->cov[(size_t)j * P + i] = t / ctx->norm;
+        }
+    ctx->have_moments = true;
+    return 0;
+}
+
 static int compute_moments(gdk_ctx* ctx) {
     if (ctx->have_moments) return 0;
     if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
     CK(cudaSetDevice(ctx->device));
-    const int P = ctx->P, nch = ctx->nchains;
-    const int64_t N = ctx->N;
     PhaseTimer pt;
     pt.begin(ctx, GDK_PH_MOMENTS);
-    // pass 1: per-chain sums
-    {
-        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 8 / std::max(1, P));
-        const int64_t seglen = std::max<int64_t>(1 << 14, (N + want - 1) / want);
-        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
-        int rc = gdk_upload_segs(ctx, segs, ctx->segs);
+    // stat blocks that were not produced during the upload: one fused sweep over their rows
+    const int64_t step = (int64_t)16 * ST_BLOCK;
+    for (int64_t r0 = 0; r0 < ctx->N; r0 += step) {
+        const int64_t r1 = std::min(ctx->N, r0 + step);
+        bool need = false;
+        for (size_t i = 0; i < ctx->sblocks.size(); i++)
+            if (ctx->sblocks[i].r0 >= r0 && ctx->sblocks[i].r1 <= r1 && !ctx->sblock_done[i]) need = true;
+        if (!need) continue;
+        int rc = stats_rows(ctx, r0, r1, ctx->stream, 0);
         if (rc) return rc;
-        const size_t np = segs.size() * (size_t)P * 4;
-        if (ctx->scratch.ensure(np)) return gdk_fail(ctx, GDK_ERR_NOMEM, "moment partials");
-        dim3 g((unsigned)segs.size(), (unsigned)P);
-        {
-            KernelTimer kt(ctx, GDK_K_COL_SUMS, (double)N * (P + 1) * 8.0, 2.0 * N * P);
-            k_col_sums<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, ctx->scratch.p);
-        }
-        ctx->launches++;
-        std::vector<double> part(np);
-        CK(cudaMemcpyAsync(part.data(), ctx->scratch.p, np * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->chain_means.assign((size_t)nch * P, 0.0);
-        ctx->chain_norm.assign(nch, 0.0);
-        ctx->xmin.assign(P, INFINITY);
-        ctx->xmax.assign(P, -INFINITY);
-        std::vector<double> swx((size_t)nch * P, 0.0);
-        for (size_t s = 0; s < segs.size(); s++) {
-            const int ch = segs[s].chain;
-            for (int j = 0; j < P; j++) {
-                const double* o = &part[(s * P + j) * 4];
-                swx[(size_t)ch * P + j] += o[0];
-                if (j == 0) ctx->chain_norm[ch] += o[1];
-                ctx->xmin[j] = std::min(ctx->xmin[j], o[2]);
-                ctx->xmax[j] = std::max(ctx->xmax[j], o[3]);
-            }
-        }
-        ctx->means.assign(P, 0.0);
-        double norm = 0;
-        for (int ch = 0; ch < nch; ch++) norm += ctx->chain_norm[ch];
-        ctx->norm = norm;
-        for (int j = 0; j < P; j++) {
-            double t = 0;
-            for (int ch = 0; ch < nch; ch++) {
-                t += swx[(size_t)ch * P + j];
-                ctx->chain_means[(size_t)ch * P + j] = swx[(size_t)ch * P + j] / ctx->chain_norm[ch];
-            }
-            ctx->means[j] = t / norm;
-        }
     }
-    // pass 2: centred second moments per chain
-    {
-        const int T = (P + COV_T - 1) / COV_T;
-        std::vector<int2> tiles;
-        for (int a = 0; a < T; a++)
-            for (int b = a; b < T; b++) tiles.push_back(int2{a, b});
-        const int nt = (int)tiles.size();
-        const int64_t want = std::max<int64_t>(1, (int64_t)ctx->num_sms * 4 / nt);
-        const int64_t seglen = std::max<int64_t>(1 << 12, (N + want - 1) / want);
-        std::vector<Seg> segs = gdk_make_segments(ctx, seglen);
-        int rc = gdk_upload_segs(ctx, segs, ctx->segs);
-        if (rc) return rc;
-        const size_t np = segs.size() * (size_t)nt * COV_T * COV_T;
-        if (ctx->scratch.ensure(np) || ctx->dS.ensure((size_t)nch * P * P) || ctx->dmeans.ensure((size_t)nch * P) ||
-            ctx->dtiles.ensure(tiles.size()))
-            return gdk_fail(ctx, GDK_ERR_NOMEM, "covariance partials");
-        CK(cudaMemcpyAsync(ctx->dmeans.p, ctx->chain_means.data(), (size_t)nch * P * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->dtiles.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        dim3 g((unsigned)segs.size(), (unsigned)nt);
-        {
-            KernelTimer kt(ctx, GDK_K_COV_TILES, (double)N * (P + 1) * 8.0, (double)N * P * (P + 1));
-            k_cov_tiles<<<g, 256, 0, ctx->stream>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->segs.p, P, nt, ctx->dtiles.p, ctx->dmeans.p,
-                                                    ctx->scratch.p);
-        }
-        dim3 g2((unsigned)nt, (unsigned)nch);
-        k_cov_reduce<<<g2, 256, 0, ctx->stream>>>(ctx->scratch.p, ctx->segs.p, (int)segs.size(), nt, ctx->dtiles.p, P, ctx->dS.p);
-        ctx->launches += 2;
-        ctx->chain_S.resize((size_t)nch * P * P);
-        CK(cudaMemcpyAsync(ctx->chain_S.data(), ctx->dS.p, ctx->chain_S.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        pt.end();
-        CK(cudaStreamSynchronize(ctx->stream));
-        // global covariance: sum_c (S_c + W_c d_c d_c^T) / W with d_c = m_c - m  (no cancellation)
-        ctx->cov.assign((size_t)P * P, 0.0);
-        for (int i = 0; i < P; i++)
-            for (int j = i; j < P; j++) {
-                double t = 0;
-                for (int ch = 0; ch < nch; ch++) {
-                    const double di = ctx->chain_means[(size_t)ch * P + i] - ctx->means[i];
-                    const double dj = ctx->chain_means[(size_t)ch * P + j] - ctx->means[j];
-                    t += ctx->chain_S[((size_t)ch * P + i) * P + j] + ctx->chain_norm[ch] * di * dj;
-                }
-                ctx->cov[(size_t)i * P + j] = ctx->cov[(size_t)j * P + i] = t / ctx->norm;
-            }
-    }
-    ctx->have_moments = true;
-    return 0;
+    pt.end();
+    return combine_moments(ctx);
+}
+
+// re-run the fused statistics sweep over the resident store (bench: the stats pass on its own)
+extern "C" int32_t gdk_moments_recompute(gdk_ctx* ctx) {
+    if (!ctx) return GDK_ERR_ARG;
+    if (ctx->N <= 0) return gdk_fail(ctx, GDK_ERR_STATE, "no samples set");
+    for (auto& d : ctx->sblock_done) d = 0;
+    ctx->have_moments = false;
+    return compute_moments(ctx);
 }
 
 int gdk_compute_moments(gdk_ctx* ctx) { return compute_moments(ctx); }
@@ -968,7 +1200,10 @@ extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_
         CK(cudaFuncSetAttribute(k_kde1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_need, 48 * 1024)));
         ctx->kde1d_smem = std::max<size_t>(smem_need, 48 * 1024);
     }
-    const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
+    const bool peers_out = (flags & GDK_OUT_PEERS) != 0 && ctx->nranks > 1;
+    const bool dev_out = (flags & (GDK_OUT_DEVICE | GDK_OUT_PEERS)) != 0;
+    if (peers_out && (likes || P_out < ctx->win[GDK_WIN_G1].p || P_out + (size_t)n * stride > ctx->win[GDK_WIN_G1].p + ctx->win[GDK_WIN_G1].cap))
+        return gdk_fail(ctx, GDK_ERR_ARG, "GDK_OUT_PEERS: P_out must lie inside the GDK_WIN_G1 window");
     double* dP = dev_out ? P_out : ctx->fbuf.p;
     double* dL = !likes ? nullptr : (dev_out ? likes_out : ctx->fbuf.p + (size_t)n * gstride);
     const int64_t pstride = dev_out ? stride : gstride;
@@ -983,6 +1218,15 @@ extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_
     ctx->launches++;
     pt.end();
     CK(cudaGetLastError());
+    if (peers_out) {  // this rank's rows of the gathered 1D window into every peer's copy (NVLink, copy engine)
+        const size_t off = (size_t)(P_out - ctx->win[GDK_WIN_G1].p);
+        for (int p = 0; p < ctx->nranks; p++) {
+            if (p == ctx->rank) continue;
+            double* pw = (double*)ctx->peer_ptr[GDK_WIN_G1][p];
+            if (!pw) return gdk_fail(ctx, GDK_ERR_STATE, "result window of peer %d is not mapped", p);
+            CK(cudaMemcpyAsync(pw + off, P_out, (size_t)n * stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
     if (!dev_out)
         for (int i = 0; i < n; i++)
             CK(cudaMemcpyAsync(P_out + (int64_t)i * stride, ctx->fbuf.p + (int64_t)i * gstride, (size_t)specs[i].fine_bins * 8,

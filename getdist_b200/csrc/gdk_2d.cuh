@@ -49,8 +49,18 @@ static int upload_vec(gdk_ctx* ctx, const std::vector<T>& v, DevBuf<unsigned cha
 static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double* P_out, const int64_t* offsets,
                            gdk_result2d* res, uint32_t flags, bool hist_only, double* likes_out = nullptr,
                            const double* masks = nullptr, const int64_t* mask_offsets = nullptr, const int32_t* mask_w = nullptr) {
-    const bool dev_out = (flags & GDK_OUT_DEVICE) != 0;
+    const bool peers_out = (flags & GDK_OUT_PEERS) != 0 && ctx->nranks > 1;
+    const bool dev_out = (flags & (GDK_OUT_DEVICE | GDK_OUT_PEERS)) != 0;
     const bool likes = likes_out != nullptr && !hist_only;
+    PeerTable ptab{};
+    if (peers_out) {
+        if (P_out != ctx->win[GDK_WIN_G2].p || likes) return gdk_fail(ctx, GDK_ERR_ARG, "GDK_OUT_PEERS: P_out must be the GDK_WIN_G2 window");
+        for (int p = 0; p < ctx->nranks; p++) {
+            if (p == ctx->rank) continue;
+            if (!ctx->peer_ptr[GDK_WIN_G2][p]) return gdk_fail(ctx, GDK_ERR_STATE, "result window of peer %d is not mapped", p);
+            ptab.base[ptab.n++] = (double*)ctx->peer_ptr[GDK_WIN_G2][p];
+        }
+    }
     // ---------------- layout of the pair grids ----------------
     std::vector<long long> goff(n);
     size_t gtot = 0;
@@ -1042,6 +1052,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     long long* doffs = nullptr;
     rc = upload_vec(ctx, offs_sorted, ctx->bytes2d_e, &doffs);
     if (rc) return rc;
+    int* dcnt = nullptr;
+    if (peers_out) {
+        std::vector<int> cnts(n);
+        for (int k = 0; k < n; k++) cnts[k] = cjs[k].G * cjs[k].G;
+        rc = upload_vec(ctx, cnts, ctx->bytes_push, &dcnt);
+        if (rc) return rc;
+    }
     // result structs in sorted order for the finalize kernel's status bit
     std::vector<gdk_result2d> res_sorted(n);
     for (int k = 0; k < n; k++) res_sorted[k] = res[order[k]];
@@ -1195,6 +1212,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             }
             ctx->launches++;
         }
+        if (peers_out) {  // this group's grids into every peer's gathered window, behind the next group's convolutions
+            cudaEvent_t ev = ctx->pipe_events[gidx];
+            CK2(cudaEventRecord(ev, ctx->stream));
+            CK2(cudaStreamWaitEvent(ctx->stream2, ev, 0));
+            k_push_peers<<<dim3((unsigned)nj, (unsigned)ptab.n), 256, 0, ctx->stream2>>>(dout, doffs + g.b, dcnt + g.b, 0, ptab);
+            ctx->launches++;
+        }
         if (!dev_out) {
             cudaEvent_t ev = ctx->pipe_events[gidx];
             CK2(cudaEventRecord(ev, ctx->stream));
@@ -1210,7 +1234,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     pt.end();
     CK2(cudaGetLastError());
     CK2(cudaMemcpyAsync(res_sorted.data(), dres, (size_t)n * sizeof(gdk_result2d), cudaMemcpyDeviceToHost, ctx->stream));
-    if (!dev_out) CK2(cudaStreamSynchronize(ctx->stream2));
+    if (!dev_out || peers_out) CK2(cudaStreamSynchronize(ctx->stream2));
     CK2(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < n; k++) {
         res[order[k]].status = res_sorted[k].status;

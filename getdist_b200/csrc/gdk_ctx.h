@@ -17,6 +17,8 @@
 #include "kernels_stats.cuh"
 
 #define GDK_NPHASE 10
+#define GDK_MAX_RANKS 16
+#define GDK_NWINDOW 4
 enum {
     GDK_PH_HIST1D = 0,
     GDK_PH_KDE1D = 1,
@@ -129,6 +131,26 @@ struct gdk_ctx {
     size_t h1_tma_smem = 0, h1_smem = 0, kde1d_smem = 0;
     DevBuf<cplx> cwork2d;
     std::vector<cudaEvent_t> pipe_events;  // group-finished events of the 2D output pipeline
+    // fused one-sweep statistics (kernels_stats.cuh): stat blocks of the whole data set in row order, their records on
+    // the device / host, and which of them hold valid data (computed here during the upload, or pushed by a peer)
+    struct StatBlock {
+        int64_t r0, r1;
+        int chain, seg0, nseg;
+    };
+    std::vector<StatBlock> sblocks;
+    std::vector<Seg> ssegs_h;
+    std::vector<char> sblock_done;
+    DevBuf<double> dblock, spart[2];
+    DevBuf<Seg> ssegs;
+    DevBuf<int2> sblkseg, stiles;
+    DevBuf<int> sblkout;
+    int stT = 0, stNtile = 0;
+    // multi-GPU (one process per GPU on one node): windows of this context mapped into the peers with CUDA IPC
+    int rank = 0, nranks = 1;
+    int64_t row_begin = 0, row_end = 0;  // rows this rank uploads itself (the rest arrives from the peers over NVLink)
+    void* peer_ptr[GDK_NWINDOW][GDK_MAX_RANKS] = {{nullptr}};
+    DevBuf<double> win[2];  // GDK_WIN_G1, GDK_WIN_G2: gathered result grids
+    DevBuf<unsigned char> bytes_push;
 };
 
 // per-kernel CUDA-event timing + algorithmic work counters for the bench's roofline figures (gdk_set_kernel_timing)

@@ -155,153 +155,203 @@ __global__ void k_fill(double* p, int64_t n, double v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// ---- per (segment, parameter): sum w x, sum w, min x, max x ----------------------------------------------
-// grid (nseg, P); partial layout part[(seg*P + j)*4 + {0..3}]
-__global__ void __launch_bounds__(256) k_col_sums(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
-                                                  const Seg* __restrict__ segs, int P, double* __restrict__ part) {
-    const Seg sg = segs[blockIdx.x];
-    const int j = blockIdx.y;
-    const double* x = dX + (int64_t)j * ld;
-    double swx = 0, sw = 0, mn = INFINITY, mx = -INFINITY;
-    // r0 is a multiple of 2 unless it is a chain boundary; handle an odd head element separately
-    int64_t r = sg.r0;
-    if ((r & 1) && r < sg.r1) {
-        if (threadIdx.x == 0) {
-            const double xv = x[r], wv = dW[r];
-            swx += wv * xv;
-            sw += wv;
-            mn = fmin(mn, xv);
-            mx = fmax(mx, xv);
-        }
-        r++;
-    }
-    const int64_t npair = (sg.r1 - r) >> 1;
-    for (int64_t i = threadIdx.x; i < npair; i += blockDim.x) {
-        const double2 xv = ldg_stream2(x + r + 2 * i);
-        const double2 wv = *reinterpret_cast<const double2*>(dW + r + 2 * i);
-        swx += wv.x * xv.x;
-        swx += wv.y * xv.y;
-        sw += wv.x + wv.y;
-        mn = fmin(mn, fmin(xv.x, xv.y));
-        mx = fmax(mx, fmax(xv.x, xv.y));
-    }
-    if (((sg.r1 - r) & 1) && threadIdx.x == 0) {
-        const double xv = x[sg.r1 - 1], wv = dW[sg.r1 - 1];
-        swx += wv * xv;
-        sw += wv;
-        mn = fmin(mn, xv);
-        mx = fmax(mx, xv);
-    }
-    __shared__ double sh[4][8];
-    swx = warp_sum(swx);
-    sw = warp_sum(sw);
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    const int wid = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-        sh[0][wid] = swx;
-        sh[1][wid] = sw;
-        sh[2][wid] = mn;
-        sh[3][wid] = mx;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a = 0, b = 0, c = INFINITY, d = -INFINITY;
-        for (int i = 0; i < 8; i++) {
-            a += sh[0][i];
-            b += sh[1][i];
-            c = fmin(c, sh[2][i]);
-            d = fmax(d, sh[3][i]);
-        }
-        double* o = part + ((int64_t)blockIdx.x * P + j) * 4;
-        o[0] = a;
-        o[1] = b;
-        o[2] = c;
-        o[3] = d;
-    }
-}
+// ---- fused one-sweep weighted statistics (chains.py:373-412, 709-733, 1446-1474; mcsamples.py:552-576) -------------
+// ONE pass over the samples gives, per row segment: sum w, sum w d, min d, max d and the P x P block sum w d d^T with
+// d = x - s, s = the segment's own first row (a shift that costs nothing to obtain, is the same whatever the number of
+// ranks or the upload chunking, and keeps the one-pass second moments free of cancellation: |d| is a few sigma).
+// Segments are cut at absolute multiples of ST_SEG rows and at chain boundaries; they are merged in a fixed order --
+// sequentially inside "stat blocks" (ST_BLOCK rows cut at chain boundaries) on the device, then sequentially over the
+// blocks on the host -- with the pairwise update of the mean and the centred second moments
+//     D = m_b - m_a,  W = A_a + A_b,  m = m_a + D A_b / W,  S = S_a + S_b + D D^T A_a A_b / W,
+// so the result does not depend on which rank or which upload chunk a block was computed in.
+//
+// k_stats_fused: grid (segments, upper-triangle 64 x 64 parameter tiles), 64 threads, 8 x 8 outputs per thread.
+// Rows are staged 32 at a time through shared memory (k-major, XOR-swizzled pairs: conflict-free 64-bit staging
+// stores and conflict-free LDS.128 operand loads, 8 LDS.128 per 64 DFMA).  Diagonal tiles also produce the column sums
+// and min/max (a row with weight 0 still counts for min/max, as in the reference), tile 0 the weight sum.
+#define ST_T 64
+#define ST_RB 32
+#define ST_SEG 8192
+#define ST_BLOCK 131072
+__device__ __forceinline__ int st_swz(int c, int k) { return ((((c >> 1) ^ (k & 15)) << 1) | (c & 1)); }
 
-// ---- centred second moments: S_c[i][j] = sum_{n in segment} w_n (x_ni - m_ci)(x_nj - m_cj) -----------------
-// 64x64 parameter tile per CTA (upper-triangle tiles only), 256 threads, 4x4 outputs per thread.
-// Rows are staged through shared memory 32 at a time, column-major with a padded leading dimension so
-// that both the staging stores (lane = row) and the inner-product loads are bank-conflict free.
-#define COV_T 64
-#define COV_RB 32
-__global__ void __launch_bounds__(256) k_cov_tiles(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
-                                                   const Seg* __restrict__ segs, int P, int ntile,
-                                                   const int2* __restrict__ tiles, const double* __restrict__ chain_means,
-                                                   double* __restrict__ part /*[nseg][ntile][64*64]*/) {
-    __shared__ double As[COV_T][COV_RB + 1];
-    __shared__ double Bs[COV_T][COV_RB + 1];
+// per-segment partial: [ntile][64*64] second-moment tiles, then B[T*64], min[T*64], max[T*64], then A (+pad to even)
+__host__ __device__ __forceinline__ int64_t st_part_stride(int T, int ntile) { return (int64_t)ntile * (ST_T * ST_T) + 3 * T * ST_T + 2; }
+
+__global__ void __launch_bounds__(64) k_stats_fused(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
+                                                    const Seg* __restrict__ segs, int P, int T, int ntile,
+                                                    const int2* __restrict__ tiles, double* __restrict__ part) {
+    __shared__ __align__(16) double As[ST_RB][ST_T];
+    __shared__ __align__(16) double Bs[ST_RB][ST_T];
+    __shared__ double shA[ST_T], shB[ST_T];
     const Seg sg = segs[blockIdx.x];
     const int2 tl = tiles[blockIdx.y];
-    const int i0 = tl.x * COV_T, j0 = tl.y * COV_T;
-    const double* mean = chain_means + (int64_t)sg.chain * P;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double acc[4][4];
+    const int i0 = tl.x * ST_T, j0 = tl.y * ST_T;
+    const bool diag = tl.x == tl.y;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int tx = t & 7, ty = t >> 3;
+    {
+        const int ci = i0 + t, cj = j0 + t;
+        shA[t] = ci < P ? dX[(int64_t)ci * ld + sg.r0] : 0.0;
+        shB[t] = cj < P ? dX[(int64_t)cj * ld + sg.r0] : 0.0;
+    }
+    __syncthreads();
+    double acc[8][8];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int e = 0; e < 8; e++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0;
-    for (int64_t rb = sg.r0; rb < sg.r1; rb += COV_RB) {
+        for (int f = 0; f < 8; f++) acc[e][f] = 0;
+    double sa = 0, mn = 0, mx = 0, sw = 0;  // d = 0 (the segment's first row) is always inside [min d, max d]
+    for (int64_t rb = sg.r0; rb < sg.r1; rb += ST_RB) {
         const int64_t r = rb + lane;
         const bool ok = r < sg.r1;
         const double wv = ok ? dW[r] : 0.0;
-        // 8 warps x 8 columns each per side
-        for (int c = wid; c < COV_T; c += 8) {
+        sw += wv;
+        // warp `wid` stages columns [32 wid, 32 wid + 32) of both sides; lane = row (coalesced along N)
+#pragma unroll 8
+        for (int cc = 0; cc < 32; cc++) {
+            const int c = 32 * wid + cc;
             const int ci = i0 + c, cj = j0 + c;
-            double a = 0, b = 0;
-            if (ok && ci < P) a = (dX[(int64_t)ci * ld + r] - mean[ci]) * wv;
-            if (ok && cj < P) b = dX[(int64_t)cj * ld + r] - mean[cj];
-            As[c][lane] = a;
-            Bs[c][lane] = b;
+            const double da = (ok && ci < P) ? ldg_stream(dX + (int64_t)ci * ld + r) - shA[c] : 0.0;
+            const double a = da * wv;
+            double b = da;
+            if (!diag) b = (ok && cj < P) ? ldg_stream(dX + (int64_t)cj * ld + r) - shB[c] : 0.0;
+            As[lane][st_swz(c, lane)] = a;
+            Bs[lane][st_swz(c, lane)] = b;
         }
         __syncthreads();
 #pragma unroll 4
-        for (int k = 0; k < COV_RB; k++) {
-            double av[4], bv[4];
+        for (int k = 0; k < ST_RB; k++) {
+            double a[8], b[8];
 #pragma unroll
-            for (int a = 0; a < 4; a++) av[a] = As[ty + 16 * a][k];
+            for (int q = 0; q < 4; q++) {
+                const double2 av = *reinterpret_cast<const double2*>(&As[k][((ty + 8 * q) ^ (k & 15)) << 1]);
+                const double2 bv = *reinterpret_cast<const double2*>(&Bs[k][((tx + 8 * q) ^ (k & 15)) << 1]);
+                a[2 * q] = av.x;
+                a[2 * q + 1] = av.y;
+                b[2 * q] = bv.x;
+                b[2 * q + 1] = bv.y;
+            }
 #pragma unroll
-            for (int b = 0; b < 4; b++) bv[b] = Bs[tx + 16 * b][k];
+            for (int e = 0; e < 8; e++)
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                for (int f = 0; f < 8; f++) acc[e][f] = fma(a[e], b[f], acc[e][f]);
+        }
+        if (diag) {  // column t: sum of w d, min / max of d over the 32 staged rows
+#pragma unroll 8
+            for (int k = 0; k < ST_RB; k++) {
+                sa += As[k][st_swz(t, k)];
+                const double d = Bs[k][st_swz(t, k)];
+                mn = fmin(mn, d);
+                mx = fmax(mx, d);
+            }
         }
         __syncthreads();
     }
-    double* o = part + ((int64_t)blockIdx.x * ntile + blockIdx.y) * (COV_T * COV_T);
+    double* o = part + (int64_t)blockIdx.x * st_part_stride(T, ntile);
+    double* oc = o + (int64_t)blockIdx.y * (ST_T * ST_T);
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int e = 0; e < 8; e++) {
+        const int i = 2 * ty + (e & 1) + 16 * (e >> 1);
 #pragma unroll
-        for (int b = 0; b < 4; b++) o[(ty + 16 * a) * COV_T + tx + 16 * b] = acc[a][b];
+        for (int q = 0; q < 4; q++) {
+            const int j = 2 * tx + 16 * q;
+            *reinterpret_cast<double2*>(&oc[i * ST_T + j]) = make_double2(acc[e][2 * q], acc[e][2 * q + 1]);
+        }
+    }
+    if (diag) {
+        double* ob = o + (int64_t)ntile * (ST_T * ST_T);
+        ob[i0 + t] = sa;
+        ob[T * ST_T + i0 + t] = mn;
+        ob[2 * T * ST_T + i0 + t] = mx;
+        if (blockIdx.y == 0 && wid == 0) {
+            sw = warp_sum(sw);
+            if (lane == 0) ob[3 * T * ST_T] = sw;
+        }
+    }
 }
 
-// deterministic reduction of the per-segment tiles into per-chain matrices S[chain][P][P] (upper tiles,
-// mirrored).  grid (ntile, nchains), 256 threads.
-__global__ void k_cov_reduce(const double* __restrict__ part, const Seg* __restrict__ segs, int nseg, int ntile,
-                             const int2* __restrict__ tiles, int P, double* __restrict__ S /*[nch][P][P]*/) {
-    const int t = blockIdx.x, ch = blockIdx.y;
-    const int2 tl = tiles[t];
-    for (int e = threadIdx.x; e < COV_T * COV_T; e += blockDim.x) {
-        double s = 0;
-        for (int sgi = 0; sgi < nseg; sgi++)
-            if (segs[sgi].chain == ch) s += part[((int64_t)sgi * ntile + t) * (COV_T * COV_T) + e];
-        const int i = tl.x * COV_T + e / COV_T, j = tl.y * COV_T + e % COV_T;
-        if (i < P && j < P) {
-            double* Sc = S + (int64_t)ch * P * P;
-            if (tl.x == tl.y) {
-                if (j >= i) {
-                    Sc[(int64_t)i * P + j] = s;
-                    Sc[(int64_t)j * P + i] = s;
-                }
-            } else {
-                Sc[(int64_t)i * P + j] = s;
-                Sc[(int64_t)j * P + i] = s;
+// Sequential merge of the segments of one stat block (grid = blocks, 256 threads, dynamic shared 3 P doubles).
+// Block record: [0] = A, [1 .. P] mean, [P+1 .. 2P] min x, [2P+1 .. 3P] max x, [3P+1 ..] S (P x P, symmetric, centred).
+__host__ __device__ __forceinline__ int64_t st_block_stride(int P) { return 3 * (int64_t)P + 1 + (int64_t)P * P; }
+__global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ part, const Seg* __restrict__ segs,
+                                                     const int2* __restrict__ blkseg /* first seg, count */,
+                                                     const int* __restrict__ blkout, int seg0, const double* __restrict__ dX, int64_t ld,
+                                                     int P, int T, int ntile, double* __restrict__ bout) {
+    extern __shared__ double shm[];
+    double* m = shm;           // running mean
+    double* dl = shm + P;      // D = m_seg - m
+    double* ds = shm + 2 * P;  // delta = B_seg / A_seg
+    const int2 bs = blkseg[blockIdx.x];
+    double* out = bout + (int64_t)blkout[blockIdx.x] * st_block_stride(P);
+    double* S = out + 3 * P + 1;
+    const int64_t pstride = st_part_stride(T, ntile);
+    for (int c = threadIdx.x; c < P; c += blockDim.x) {
+        m[c] = 0;
+        out[1 + P + c] = INFINITY;
+        out[1 + 2 * P + c] = -INFINITY;
+    }
+    for (int64_t e = threadIdx.x; e < (int64_t)P * P; e += blockDim.x) S[e] = 0;
+    double A = 0;
+    __syncthreads();
+    for (int s = bs.x; s < bs.x + bs.y; s++) {
+        const double* ps = part + (int64_t)(s - seg0) * pstride;  // the partial buffer starts at segment seg0
+        const double* pb = ps + (int64_t)ntile * (ST_T * ST_T);
+        const double As_ = pb[3 * T * ST_T];
+        const int64_t r0 = segs[s].r0;
+        for (int c = threadIdx.x; c < P; c += blockDim.x) {
+            const double sh = dX[(int64_t)c * ld + r0];
+            out[1 + P + c] = fmin(out[1 + P + c], sh + pb[T * ST_T + c]);
+            out[1 + 2 * P + c] = fmax(out[1 + 2 * P + c], sh + pb[2 * T * ST_T + c]);
+            if (As_ > 0) {
+                const double d = pb[c] / As_;
+                ds[c] = d;
+                dl[c] = (A > 0) ? (sh + d) - m[c] : 0.0;
+                if (!(A > 0)) m[c] = sh + d;
             }
         }
+        __syncthreads();
+        if (As_ > 0) {
+            const double W = A + As_;
+            const double f = (A > 0) ? A * As_ / W : 0.0;
+            for (int64_t e = threadIdx.x; e < (int64_t)P * P; e += blockDim.x) {
+                const int i = (int)(e / P), j = (int)(e % P);
+                const int a = min(i, j), b = max(i, j);
+                const int ta = a / ST_T, tb = b / ST_T;
+                const int tix = ta * T - (ta * (ta - 1)) / 2 + (tb - ta);
+                const double cv = ps[(int64_t)tix * (ST_T * ST_T) + (a % ST_T) * ST_T + (b % ST_T)];
+                S[e] += (cv - As_ * ds[i] * ds[j]) + f * dl[i] * dl[j];
+            }
+            __syncthreads();
+            if (A > 0)
+                for (int c = threadIdx.x; c < P; c += blockDim.x) m[c] += dl[c] * (As_ / W);
+            A = W;
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < P; c += blockDim.x) out[1 + c] = m[c];
+    if (threadIdx.x == 0) out[0] = A;
+}
+
+// ---- multi-GPU: finished result grids of this rank stored into every peer's gathered window over NVLink ------------
+// (peer memory mapped with CUDA IPC; launched on the second stream behind the group-finished event, so the transfer of
+// one group overlaps the convolutions of the next).  grid (densities, peers); 16-byte stores when aligned.
+struct PeerTable {
+    double* base[16];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_push_peers(const double* __restrict__ local, const long long* __restrict__ offs,
+                                                    const int* __restrict__ counts, long long fixed_count, PeerTable peers) {
+    const long long off = offs[blockIdx.x];
+    const long long cnt = counts ? counts[blockIdx.x] : fixed_count;
+    const double* src = local + off;
+    double* dst = peers.base[blockIdx.y] + off;
+    if (((off | cnt) & 1) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (long long i = threadIdx.x; i < cnt / 2; i += blockDim.x) d2[i] = s2[i];
+    } else {
+        for (long long i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
     }
 }
 

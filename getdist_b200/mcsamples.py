@@ -206,7 +206,7 @@ def _read_ini(ini):
 
 class MCSamples:
     def __init__(self, samples=None, weights=None, loglikes=None, names=None, labels=None, ranges=None, sampler=None,
-                 settings=None, label=None, device=0, name_tag=None, chain_offsets=None, **kwargs):
+                 settings=None, label=None, device=0, name_tag=None, chain_offsets=None, process_group=None, **kwargs):
         if samples is None:
             raise MCSamplesError("getdist_b200.MCSamples needs in-memory samples (file loading stays in the reference)")
         # chain_offsets: row offsets of already combined chains (chains.py:1497), as the reference object holds them
@@ -253,6 +253,9 @@ class MCSamples:
             setattr(self, k, v)
         self.contours = np.array(self.contours)
         self._ctx = _abi.Context(device)  # raises if there is no CUDA device / library: no fallback
+        # multi-GPU: a getdist_b200.parallel.PeerGroup (one process per GPU); every rank constructs the object with the
+        # same arguments, uploads 1/world of the rows and computes 1/world of the densities of prefetch_triangle
+        self.process_group = process_group
         self._device_valid = False
         self.density1D = {}
         self._density2D = {}
@@ -271,6 +274,7 @@ class MCSamples:
         d = self.__dict__.copy()
         d["_device"] = self._ctx.device
         d.pop("_ctx", None)
+        d["process_group"] = None  # a rendezvous is not part of the state
         d["_device_valid"] = False
         d["_loglikes_valid"] = False
         return d
@@ -319,7 +323,10 @@ class MCSamples:
     # ------------------------------------------------------------------ data residency / statistics
     def _upload(self):
         if not self._device_valid:
-            self._ctx.set_samples(self.samples, self.weights, self.chain_offsets)
+            pg = getattr(self, "process_group", None)
+            if pg is not None and pg.world > 1 and not pg.probe(self._ctx):
+                pg = None  # fallback transport: every rank uploads everything
+            self._ctx.set_samples(self.samples, self.weights, self.chain_offsets, **({} if pg is None else {"group": pg}))
             self._device_valid = True
             self._loglikes_valid = False
 
@@ -819,6 +826,10 @@ class MCSamples:
             P, res = self._ctx.density1d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, res  # grids stay on the device (row i at device_ptr + i * max(fine_bins))
+        return self._finish_1d(indices, specs, P, res, L, cache=not kwargs)
+
+    def _finish_1d(self, indices, specs, P, res, L=None, cache=True):
+        """Density1D objects (+ the reference's warnings / errors and ParamInfo side effects) from the rows of a 1D batch"""
         out = []
         for k, (j, sp, row, r) in enumerate(zip(indices, specs, P, res)):
             par = self.paramNames.names[j]
@@ -842,7 +853,7 @@ class MCSamples:
             d = Density1D(x, P=row[: sp.fine_bins], view_ranges=[par.range_min, par.range_max])
             d.likes = None if L is None else L[k][: sp.fine_bins]  # mcsamples.py:1672-1684
             d._gdk = dict(kde_h=r.kde_h, smooth_1D=r.smooth_1D, winw=r.winw, status=r.status, n_feval=r.n_feval)
-            if not kwargs:
+            if cache:
                 self.density1D[par.name] = d
             out.append(d)
         return out
@@ -1183,6 +1194,12 @@ class MCSamples:
             buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
         if _device_ptr is not None:
             return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
+        return self._finish_2d(pairs, specs, buf, offsets, res, conts, lbuf=lbuf, masks=masks,
+                               cache=not kwargs and masks is None and lbuf is None)
+
+    def _finish_2d(self, pairs, specs, buf, offsets, res, conts, lbuf=None, masks=None, cache=True):
+        """Density2D objects (+ the reference's warnings / errors) from the grids of a 2D batch; `buf` holds density i at
+        buf[offsets[i]:][:G*G]"""
         out = []
         for (j, j2), spr, off, r in zip(pairs, specs, offsets, res):
             sp = _SpecView(spr)
@@ -1212,7 +1229,7 @@ class MCSamples:
                           levels=(conts, [r.levels[k] for k in range(len(conts))]) if conts else None)
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
-            if not kwargs and masks is None and lbuf is None:
+            if cache:
                 # the cache entry is a READ-ONLY view into the batch buffer (no second copy of a gigabyte of grids);
                 # get2DDensity / get2DDensityGridData hand out private copies of it (_cached_2d), as the reference
                 # returns a fresh grid per call and callers normalise in place
@@ -1477,6 +1494,11 @@ class MCSamples:
         idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]
         if any(i is None for i in idx):
             raise ParamError("unknown parameter in prefetch_triangle")
+        pg = getattr(self, "process_group", None)
+        if pg is not None and pg.world > 1:
+            from .parallel import prefetch_triangle_group
+
+            return prefetch_triangle_group(self, pg, idx, do_1d, do_2d)
         d1 = self._densities_1d(idx) if do_1d else []
         pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))]
         d2 = self._densities_2d(pairs) if (do_2d and pairs) else []

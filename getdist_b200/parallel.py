@@ -110,82 +110,254 @@ def exchange_param_ranges(mc, indices, rank, world, dist=None, device="cuda"):
 
 
 class PeerGroup:
-    """One process per GPU on one node.  Holds the rendezvous (torch.distributed), this rank's id, and -- per
-    MCSamples object attached to it -- the gathered result buffers of the library, mapped into every peer.
+    """One process per GPU on one node: the rendezvous (torch.distributed: NCCL on GPUs, gloo in the CPU tests), this
+    rank's id, and the bookkeeping of which library windows are mapped into the peers.
 
-        pg = PeerGroup(dist, rank, world)                       # after dist.init_process_group("nccl")
-        d1, d2 = mc.prefetch_triangle(process_group=pg)         # every rank ends up with every density
-    """
+        dist.init_process_group("nccl", ...)
+        pg = PeerGroup(dist, rank, world)
+        mc = MCSamples(samples=X, weights=w, names=..., process_group=pg)   # sharded upload: 1/world of the rows per GPU
+        d1, d2 = mc.prefetch_triangle()                                     # every rank ends up with every density
 
-    SLOT_G1, SLOT_G2, SLOT_X, SLOT_W, SLOT_WQ = 0, 1, 2, 3, 4
+    transport: "p2p" = CUDA IPC windows (the product path); "nccl" = the loud fallback where peer mapping is not
+    available (every rank uploads everything, ONE NCCL all-gather of the result tensors after the batch)."""
 
     def __init__(self, dist, rank, world, device="cuda", use_p2p=True):
-        self.dist, self.rank, self.world, self.device = dist, rank, world, device
-        self.use_p2p = use_p2p and world > 1
-        self.transport = "single" if world == 1 else ("p2p" if self.use_p2p else "nccl")
-        self._bufs = {}  # (id(ctx), slot) -> (ptr, bytes)
-        self.last = {}
+        self.dist, self.rank, self.world, self.device = dist, int(rank), int(world), device
+        self.p2p = bool(use_p2p) and self.world > 1
+        self.transport = "single" if self.world == 1 else ("p2p" if self.p2p else "nccl")
+        self.timings = {}
 
     # -- small control collectives ----------------------------------------------------------------------------
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
 
-    def all_gather_bytes(self, payload, nbytes):
-        """fixed-size byte strings from every rank (IPC handles)"""
-        import torch
-
-        if self.world == 1:
-            return [payload]
-        t = torch.frombuffer(bytearray(payload.ljust(nbytes, b"\0")), dtype=torch.uint8).to(self.device)
-        out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=self.device)
-        self.dist.all_gather_into_tensor(out, t)
-        raw = out.cpu().numpy().tobytes()
-        return [raw[r * nbytes:(r + 1) * nbytes] for r in range(self.world)]
-
     def all_gather_array(self, arr):
-        """(n, k) float64 host array per rank (same shape everywhere) -> (world, n, k)"""
+        """host array per rank (same shape and dtype everywhere) -> (world,) + shape on every rank"""
         import torch
 
+        arr = np.ascontiguousarray(arr)
         if self.world == 1:
             return arr[None]
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        t = torch.from_numpy(arr).to(self.device)
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=self.device)
         self.dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy()
 
+    def row_range(self, N):
+        """rows this rank uploads itself: whole statistics blocks (GDK_ROW_BLOCK rows), dealt as evenly as they go"""
+        from ._abi import GDK_ROW_BLOCK
+
+        nblk = (N + GDK_ROW_BLOCK - 1) // GDK_ROW_BLOCK
+        b0 = (self.rank * nblk) // self.world
+        b1 = ((self.rank + 1) * nblk) // self.world
+        return min(N, b0 * GDK_ROW_BLOCK), min(N, b1 * GDK_ROW_BLOCK)
+
     # -- peer windows -----------------------------------------------------------------------------------------
-    def window(self, ctx, slot, nbytes):
-        """Device buffer `slot` of this context with at least nbytes, mapped into every peer (same size on every rank:
-        all ranks call this with the same arguments).  Returns the local device pointer."""
-        key = (id(ctx), slot)
-        have = self._bufs.get(key)
+    def map_window(self, ctx, window, nbytes):
+        """Window `window` of this rank's context with at least nbytes, mapped into every peer (every rank calls this
+        with the same arguments).  Returns the local device address.  The windows only grow, and every rank sees the
+        same sequence of sizes, so whether the handles must be exchanged again is decided without communication."""
+        mapped = ctx.__dict__.setdefault("_peer_windows", {})  # lives and dies with the context
+        have = mapped.get(window)
         if have is not None and have[1] >= nbytes:
             return have[0]
-        ptr, handle = ctx.peer_alloc(slot, nbytes)
-        if self.use_p2p:
-            handles = self.all_gather_bytes(handle, 64)
-            try:
-                for r, h in enumerate(handles):
-                    if r != self.rank:
-                        ctx.peer_open(slot, r, h)
-            except Exception as e:  # no peer access on this box: say so and use the collective
-                self.use_p2p = False
-                self.transport = "nccl (CUDA IPC mapping failed: %s)" % e
-            ok = self.all_gather_array(np.array([[1.0 if self.use_p2p else 0.0]]))
-            if ok.min() < 1.0 and self.use_p2p:
-                self.use_p2p = False
-                self.transport = "nccl (CUDA IPC mapping failed on a peer)"
-        self._bufs[key] = (ptr, nbytes)
-        return ptr
+        ctx.peer_init(self.rank, self.world)
+        addr, handle = ctx.window_export(window, nbytes)
+        handles = self.all_gather_array(np.frombuffer(handle, dtype=np.uint8))
+        ok = 1.0
+        try:
+            for r in range(self.world):
+                if r != self.rank:
+                    ctx.window_import(window, r, handles[r].tobytes())
+        except Exception as e:  # no peer mapping on this box: every rank must learn it
+            ok = 0.0
+            self._why = str(e)
+        if self.all_gather_array(np.array([ok])).min() < 1.0:
+            self.p2p = False
+            self.transport = "nccl (CUDA IPC peer mapping failed: %s)" % getattr(self, "_why", "on a peer")
+            raise PeerMappingError(self.transport)
+        mapped[window] = (addr, nbytes)
+        return addr
 
-    def tensor(self, ptr, shape):
-        """torch view (float64) of a library-owned device buffer"""
-        import torch
+    def probe(self, ctx):
+        """decide the transport once: try to map a small result window into the peers"""
+        if self.world == 1 or not self.p2p or getattr(self, "_probed", False):
+            return self.p2p
+        self._probed = True
+        try:
+            from ._abi import GDK_WIN_G1
 
-        n = int(np.prod(shape))
+            self.map_window(ctx, GDK_WIN_G1, 1 << 16)
+        except PeerMappingError:
+            import logging
 
-        class _Arr:
-            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+            logging.getLogger("getdist_b200").warning("multi-GPU transport: %s", self.transport)
+        return self.p2p
 
-        return torch.as_tensor(_Arr(), device=self.device).view(*shape)
+
+class PeerMappingError(RuntimeError):
+    pass
+
+
+def _res1d_table(res):
+    return np.array([[r.kde_h, r.h_raw, r.smooth_1D, r.winw, r.status, r.n_feval] for r in res], dtype=np.float64).reshape(-1, 6)
+
+
+def _res2d_table(res):
+    return np.array([[r.hx, r.hy, r.c, r.rx, r.ry, r.t_star, r.winw, r.status, r.n_brent] + list(r.levels) for r in res],
+                    dtype=np.float64).reshape(-1, 13)
+
+
+def _res1d_from(row):
+    from ._abi import Result1D
+
+    r = Result1D()
+    r.kde_h, r.h_raw, r.smooth_1D = row[0], row[1], row[2]
+    r.winw, r.status, r.n_feval = int(row[3]), int(row[4]), int(row[5])
+    return r
+
+
+def _res2d_from(row):
+    from ._abi import Result2D
+
+    r = Result2D()
+    r.hx, r.hy, r.c, r.rx, r.ry, r.t_star = row[:6]
+    r.winw, r.status, r.n_brent = int(row[6]), int(row[7]), int(row[8])
+    for k in range(4):
+        r.levels[k] = row[9 + k]
+    return r
+
+
+def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True):
+    """MCSamples.prefetch_triangle over a PeerGroup: the densities of the triangle are partitioned across the ranks
+    (1D round-robin, 2D by anchor blocks), every rank computes its share from its resident copy of the samples and the
+    library stores each finished grid into the gathered windows of ALL ranks over NVLink while the next group is
+    convolved; the per-density result records travel in one small all-gather.  After the closing barrier every rank
+    holds every density.  to_host=False leaves the grids in the device windows (returns their addresses and layout)."""
+    import time
+
+    from . import _abi
+
+    t0 = time.perf_counter()
+    rank, world = pg.rank, pg.world
+    if not pg.probe(mc._ctx):
+        return _prefetch_triangle_nccl(mc, pg, idx, do_1d, do_2d, to_host)
+    exchange_param_ranges(mc, idx, rank, world, pg.dist, pg.device)
+    if mc.smooth_scale_1D <= 0 or mc.smooth_scale_2D < 0:
+        mc._ensure_neff(idx)
+    pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))] if do_2d else []
+    my1d, my2d, max1d, per, hints = partition_triangle(idx, pairs, rank, world, with_hints=True) if pairs else (
+        idx[rank::world], [], (len(idx) + world - 1) // world, 0, None)
+    out = {"transport": pg.transport}
+    t1 = time.perf_counter()
+    # ---- 1D: window rows [r * max1d, (r + 1) * max1d) belong to rank r
+    d1 = []
+    if do_1d:
+        F = int(mc.fine_bins)
+        base1 = pg.map_window(mc._ctx, _abi.GDK_WIN_G1, world * max1d * F * 8)
+        specs_all = [mc._spec_1d(j, {}) for j in idx]
+        pos = {j: n for n, j in enumerate(idx)}
+        tab = np.zeros((max1d, 6))
+        if my1d:
+            _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d], device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
+            tab[: len(my1d)] = _res1d_table(res)
+        out["res1d"] = pg.all_gather_array(tab)
+    t2 = time.perf_counter()
+    # ---- 2D: the window holds every pair's grid in the caller's pair order
+    if pairs:
+        specs = mc._specs_2d_batch(pairs, {})
+        conts = [float(c) for c in list(mc.contours[:4])]
+        specs["n_contours"] = len(conts)
+        for k, c in enumerate(conts):
+            specs["contours"][:, k] = c
+        fb = specs["fine_bins"].astype(np.int64)
+        offs = np.zeros(len(pairs), dtype=np.int64)
+        offs[1:] = np.cumsum(fb * fb)[:-1]
+        total = int((fb * fb).sum())
+        base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
+        where = {pr: n for n, pr in enumerate(pairs)}
+        mine = np.array([where[pr] for pr in my2d], dtype=np.int64)
+        tab = np.zeros((per, 13))
+        if len(mine):
+            sp = np.ascontiguousarray(specs[mine])
+            sp["anchor_hint"] = np.asarray(hints, dtype=np.int32)
+            _, _, res = mc._ctx.density2d_batch(sp, device_ptr=base2, offsets=offs[mine], peers=True)
+            tab[: len(mine)] = _res2d_table(res)
+        out["res2d"] = pg.all_gather_array(tab)
+    t3 = time.perf_counter()
+    pg.barrier()  # every rank's stores into every window have completed (the library synchronised its streams)
+    t4 = time.perf_counter()
+    d2 = []
+    if do_1d:
+        rows1d = {}
+        for r in range(world):
+            for k, j in enumerate(idx[r::world]):
+                rows1d[j] = (r * max1d + k, out["res1d"][r][k])
+        if to_host:
+            P1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, _abi.result_buffer(world * max1d * F).reshape(world * max1d, F))
+            d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
+        else:
+            out["g1"] = dict(address=base1, stride=F, rows=[rows1d[j][0] for j in idx])
+    if pairs:
+        lists, _ = split_pairs(idx, pairs, world)
+        rows2d = {}
+        for r in range(world):
+            for k, pr in enumerate(lists[r]):
+                rows2d[pr] = out["res2d"][r][k]
+        if to_host:
+            buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total))
+            d2 = mc._finish_2d(pairs, specs, buf, offs, [_res2d_from(rows2d[pr]) for pr in pairs], conts)
+        else:
+            out["g2"] = dict(address=base2, offsets=offs, fine_bins=fb)
+    t5 = time.perf_counter()
+    pg.timings = dict(ranges_ms=(t1 - t0) * 1e3, d1_ms=(t2 - t1) * 1e3, d2_ms=(t3 - t2) * 1e3, barrier_ms=(t4 - t3) * 1e3,
+                      read_ms=(t5 - t4) * 1e3)
+    if to_host:
+        return d1, d2
+    return out
+
+
+def _prefetch_triangle_nccl(mc, pg, idx, do_1d, do_2d, to_host):
+    """fallback transport: every rank computes its share into local tensors, ONE all-gather per result tensor"""
+    import torch
+
+    rank, world = pg.rank, pg.world
+    exchange_param_ranges(mc, idx, rank, world, pg.dist, pg.device)
+    pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))] if do_2d else []
+    my1d, my2d, max1d, per, hints = partition_triangle(idx, pairs, rank, world, with_hints=True) if pairs else (
+        idx[rank::world], [], (len(idx) + world - 1) // world, 0, None)
+    rows1d, rows2d = gather_order(idx, pairs, world) if pairs else ([(n % world) * max1d + n // world for n in range(len(idx))], [])
+    d1, d2 = [], []
+    if do_1d:
+        F = int(mc.fine_bins)
+        loc = torch.zeros((max1d, F), dtype=torch.float64, device=pg.device)
+        tab = np.zeros((max1d, 6))
+        specs_all = [mc._spec_1d(j, {}) for j in idx]
+        pos = {j: n for n, j in enumerate(idx)}
+        if my1d:
+            _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d], device_ptr=loc.data_ptr(), stride=F)
+            tab[: len(my1d)] = _res1d_table(res)
+        g1 = all_gather_grids(loc, world, pg.dist).cpu().numpy()
+        t1 = pg.all_gather_array(tab).reshape(world * max1d, 6)
+        d1 = mc._finish_1d(idx, specs_all, [g1[r] for r in rows1d], [_res1d_from(t1[r]) for r in rows1d])
+    if pairs:
+        specs = mc._specs_2d_batch(pairs, {})
+        conts = [float(c) for c in list(mc.contours[:4])]
+        specs["n_contours"] = len(conts)
+        for k, c in enumerate(conts):
+            specs["contours"][:, k] = c
+        G2 = int(specs["fine_bins"].astype(np.int64).max()) ** 2  # padded slots of the largest grid
+        where = {pr: n for n, pr in enumerate(pairs)}
+        mine = np.array([where[pr] for pr in my2d], dtype=np.int64)
+        loc = torch.zeros((max(per, 1), G2), dtype=torch.float64, device=pg.device)
+        tab = np.zeros((per, 13))
+        if len(mine):
+            sp = np.ascontiguousarray(specs[mine])
+            sp["anchor_hint"] = np.asarray(hints, dtype=np.int32)
+            _, _, res = mc._ctx.density2d_batch(sp, device_ptr=loc.data_ptr(), offsets=np.arange(len(mine), dtype=np.int64) * G2)
+            tab[: len(mine)] = _res2d_table(res)
+        g2 = all_gather_grids(loc, world, pg.dist).cpu().numpy().reshape(-1)
+        t2 = pg.all_gather_array(tab).reshape(world * per, 13)
+        d2 = mc._finish_2d(pairs, specs, g2, np.array(rows2d, dtype=np.int64) * G2, [_res2d_from(t2[r]) for r in rows2d], conts)
+    return d1, d2

@@ -29,7 +29,7 @@ extern "C" {
 
 typedef struct gdk_ctx gdk_ctx;
 
-#define GDK_ABI_VERSION 5
+#define GDK_ABI_VERSION 6
 
 /* error codes */
 #define GDK_OK 0
@@ -41,6 +41,10 @@ typedef struct gdk_ctx gdk_ctx;
 
 /* flags for the batch calls */
 #define GDK_OUT_DEVICE 1u /* P_out is a device pointer */
+#define GDK_OUT_PEERS 4u  /* P_out lies in this context's gathered result window (GDK_WIN_G1 for the 1D call, the base of
+                             GDK_WIN_G2 for the 2D call): results stay on the device AND are stored at the same offset of
+                             every peer's window over NVLink (CUDA IPC peer memory), group by group behind the
+                             convolutions of the next group.  A single-rank context treats it as GDK_OUT_DEVICE.   */
 #define GDK_BW_ONLY 2u    /* 2D: stop after the bandwidth stage -- only `res` (rx, ry, c, winw, status) is written; used by
                              the mask_function path, whose prior mask needs the kernel half-width first          */
 
@@ -99,6 +103,30 @@ double gdk_kernel_stat(gdk_ctx* ctx, int32_t slot, int32_t what);
 int32_t gdk_measure_peaks(gdk_ctx* ctx, double* out);
 
 /* ---------------------------------------------------------------------------------------------
+ * multi-GPU: one process (one context) per GPU on one node -- SURVEY.md s8b/s8e.  The path shards by independent
+ * densities, so there is no data-path collective; what is exchanged moves through WINDOWS: device buffers of a context
+ * that every peer maps with CUDA IPC and writes with plain stores / copy engines over NVLink:
+ *   GDK_WIN_G1 / GDK_WIN_G2   gathered 1D / 2D result grids (every rank ends up with every density)
+ *   GDK_WIN_X                 the column store (a rank uploads 1/nranks of the rows over PCIe, the peers push the rest)
+ *   GDK_WIN_STATS             stat-block records of the fused statistics sweep (moments of rows uploaded elsewhere)
+ * The caller's rendezvous (torch.distributed in getdist_b200/parallel.py) carries the 64-byte handles and the barriers:
+ *   gdk_peer_init -> [gdk_samples_prepare] -> gdk_window_export on every rank -> all-gather of the handles ->
+ *   gdk_window_import per peer -> barrier -> the call that writes the window -> barrier -> read.
+ * ------------------------------------------------------------------------------------------- */
+#define GDK_WIN_G1 0
+#define GDK_WIN_G2 1
+#define GDK_WIN_X 2
+#define GDK_WIN_STATS 3
+int32_t gdk_peer_init(gdk_ctx* ctx, int32_t rank, int32_t nranks);
+/* make window `window` at least `bytes` large (G1/G2; X and STATS are sized by gdk_samples_prepare), return its device
+ * address and the 64-byte CUDA IPC handle of its allocation.  The address changes when the window had to grow: the
+ * handles must then be exchanged and imported again.                                                              */
+int32_t gdk_window_export(gdk_ctx* ctx, int32_t window, uint64_t bytes, void* handle64, uint64_t* device_address);
+int32_t gdk_window_import(gdk_ctx* ctx, int32_t window, int32_t peer, const void* handle64);
+/* device -> host copy of a byte range of a window (after the barrier that follows the writers)                     */
+int32_t gdk_window_read(gdk_ctx* ctx, int32_t window, uint64_t offset, uint64_t bytes, void* host_out);
+
+/* ---------------------------------------------------------------------------------------------
  * data residency -- replaces WeightedSamples.setSamples / Chains.makeSingle state
  * (chains.py:262-308, 1488-1503) as far as the device copy is concerned.
  *   X: N x P float64, element (n, j) at X[n*row_stride + j*col_stride] (strides in elements);
@@ -108,6 +136,18 @@ int32_t gdk_measure_peaks(gdk_ctx* ctx, double* out);
  * ------------------------------------------------------------------------------------------- */
 int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int64_t row_stride,
                         int64_t col_stride, const double* w, const int64_t* chain_offsets, int32_t nchains);
+/* The same in three steps (gdk_set_samples = prepare + upload(0, N) + finish), for the sharded upload of a multi-rank
+ * group: prepare allocates the store and lays out the statistics; upload copies rows [row_begin, row_end) of X (X
+ * points at row 0 of the full matrix; the range must be cut at multiples of GDK_ROW_BLOCK rows) and ALL the weights,
+ * transposes them into the column store, runs the fused statistics sweep on them chunk by chunk behind the copies, and
+ * pushes rows and statistics records into every imported peer window; finish (after the group's barrier) derives the
+ * fixed-point weights and merges the statistics records of all row blocks -- in an order fixed by the data layout, so
+ * means / covariances are bit-identical on 1 and on N ranks.                                                      */
+#define GDK_ROW_BLOCK 131072
+int32_t gdk_samples_prepare(gdk_ctx* ctx, int64_t N, int32_t P, const int64_t* chain_offsets, int32_t nchains);
+int32_t gdk_samples_upload(gdk_ctx* ctx, const double* X, int64_t row_stride, int64_t col_stride, const double* w,
+                           int64_t row_begin, int64_t row_end);
+int32_t gdk_samples_finish(gdk_ctx* ctx);
 
 /* log-likelihoods of the stored rows -- replaces the mean_loglike dot product of setMeans (chains.py:380-381)
  * and the N-sized mean-likelihood weights  weights * exp(mean_loglike - loglikes)  of the `meanlikes` option
@@ -126,6 +166,9 @@ int32_t gdk_set_loglikes(gdk_ctx* ctx, const double* loglikes, int64_t n, double
  * ------------------------------------------------------------------------------------------- */
 int32_t gdk_moments(gdk_ctx* ctx, double* means, double* vars, double* cov, double* scalars, double* xmin,
                     double* xmax, double* chain_means, double* chain_covs, double* chain_norms);
+/* run the fused statistics sweep again over the resident store (normally it rides behind the upload chunks): the
+ * stats pass on its own, for measurements                                                                          */
+int32_t gdk_moments_recompute(gdk_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * exact weighted order statistics -- replaces initParamConfidenceData + confidence
