@@ -500,7 +500,8 @@ def run_ours(args):
     gc.collect()
     e2e_s = float("nan")
     if not args.no_e2e:
-        step_e2e()  # warm
+        step_e2e()  # warm: context, device buffers
+        step_e2e()  # warm: the second pooled pinned result buffer (the previous step's grids are still referenced)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -561,7 +562,12 @@ def run_ours(args):
     # from the ncu --set full capture of exactly this workload (profiles/); other sizes have no capture -> null.
     c2 = (args.workload == "c2" and N == 10_000_000 and P == 64 and world == 1)
     ncu_traffic = {"k_bin8c": 5.96e9, "k_bucket_records": 13.49e9, "k_hist2d_records": 13.30e9, "k_hist1d_tma": 5.97e9}
-    updates = {"k_hist2d_records": lambda st: st["bytes"] / 40.0, "k_shear_hist_w": lambda st: st["flops"] / 3.0}
+    from getdist_b200.parallel import partition_triangle
+
+    n_my_pairs = len(partition_triangle(idx, pairs, rank, world)[1])
+    # histogram updates (one 64-bit fixed-point shared-memory add each): every pair of this rank bins all N rows once
+    # (k_hist2d_records); the sheared re-binning does the same for the shear-branch pairs (3 "flops" per pair-sample)
+    updates = {"k_hist2d_records": lambda st: float(N) * n_my_pairs * args.steps, "k_shear_hist_w": lambda st: st["flops"] / 3.0}
     fp64_kernels = ("k_conv2d<0>", "k_conv2d<1>", "k_stats_fused", "k_xform_rows", "k_xform_cols")
     kernels = []
     for nm, st in kstats.items():

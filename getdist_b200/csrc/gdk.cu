@@ -330,7 +330,12 @@ static int stats_rows(gdk_ctx* ctx, int64_t ra, int64_t rb, cudaStream_t st, int
     {
         KernelTimer kt(ctx, GDK_K_STATS_FUSED, rows * (P + 1) * 8.0, rows * 2.0 * nt * ST_T * ST_T);
         dim3 g((unsigned)(s1 - s0), (unsigned)nt);
-        k_stats_fused<<<g, 64, 0, st>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->ssegs.p + s0, P, T, nt, ctx->stiles.p, ctx->spart[k].p);
+        static bool attr = false;  // per process; every context of a process sits on a B200
+        if (!attr) {
+            CK(cudaFuncSetAttribute(k_stats_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+            attr = true;
+        }
+        k_stats_fused<<<g, 128, ST_SMEM, st>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->ssegs.p + s0, P, T, nt, ctx->stiles.p, ctx->spart[k].p);
     }
     k_stats_merge<<<b1 - b0, 256, 3 * P * sizeof(double), st>>>(ctx->spart[k].p, ctx->ssegs.p, ctx->sblkseg.p + b0, ctx->sblkout.p + b0, s0,
                                                                 ctx->dX.p, ctx->ld, P, T, nt, ctx->dblock.p);

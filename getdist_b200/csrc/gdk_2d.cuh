@@ -1107,6 +1107,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         CK2(cudaFuncSetAttribute(k_conv2d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
         CK2(cudaFuncSetAttribute(k_conv2d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     }
+    CK2(cudaFuncSetAttribute(k_contours2d, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
     // output
     double* dout = nullptr;
     if (dev_out) {
@@ -1208,7 +1209,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
         if (any_contours) {
             {
                 KernelTimer kt(ctx, GDK_K_CONTOURS2D, cbytes / 2, 0);  // every grid read once
-                k_contours2d<<<nj, 1024, 0, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
+                k_contours2d<<<nj, 512, CT_SMEM, ctx->stream>>>(dcj + g.b, dout, doffs + g.b, dres + g.b);
             }
             ctx->launches++;
         }

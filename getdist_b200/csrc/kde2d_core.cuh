@@ -520,6 +520,69 @@ GDK_HD double bits_dbl(unsigned long long b) {
 #endif
 }
 
+// Given, per contour, the crossing key K* (the smallest key whose inclusive cumulative sum reaches the target): the
+// cumulative weight strictly below, the halved bin of one member of the tie group, the sorted predecessor and its
+// halved bin, then the interpolation of densities.py:39-47.  Two sweeps over the grid for all contours together.
+template <class C>
+GDK_HD unsigned contour_finish(const C& co, const double* P, int G, const unsigned long long* Kc, const double* target, int nc,
+                               double* levels) {
+    const int n = G * G;
+    double below[4] = {0, 0, 0, 0}, tie_a[4] = {0, 0, 0, 0}, cnt_tie[4] = {0, 0, 0, 0};
+    unsigned long long prevk[4] = {0, 0, 0, 0};
+    bool has_prev[4] = {false, false, false, false};
+    for (int i = co.tid; i < n; i += co.nt) {
+        const double v = P[i];
+        const unsigned long long kb = dbl_bits(v);
+        const double a = v * edge_factor(i / G, i % G, G);
+        for (int c = 0; c < 4; c++) {
+            if (c >= nc) continue;
+            if (kb < Kc[c]) {
+                below[c] += a;
+                if (!has_prev[c] || kb > prevk[c]) {
+                    prevk[c] = kb;
+                    has_prev[c] = true;
+                }
+            } else if (kb == Kc[c]) {
+                tie_a[c] = fmax(tie_a[c], a);
+                cnt_tie[c] += 1;
+            }
+        }
+    }
+    double B[4], sg[4], ntie[4], pk[4];
+    unsigned long long pkb[4];
+    for (int c = 0; c < 4; c++) {
+        if (c >= nc) continue;
+        B[c] = co.sum(below[c]);
+        sg[c] = co.max(tie_a[c]);  // interior members of a tie group all carry the same halved bin
+        ntie[c] = co.sum(cnt_tie[c]);
+        pk[c] = co.max(has_prev[c] ? bits_dbl(prevk[c]) : -1.0);  // value of the sorted predecessor (or -1)
+        pkb[c] = dbl_bits(pk[c] >= 0 ? pk[c] : 0.0);
+    }
+    // the predecessor's halved bin: the largest one among the elements equal to pk
+    double pa[4] = {0, 0, 0, 0};
+    for (int i = co.tid; i < n; i += co.nt) {
+        const double v = P[i];
+        const unsigned long long kb = dbl_bits(v);
+        for (int c = 0; c < 4; c++)
+            if (c < nc && pk[c] >= 0 && kb == pkb[c]) pa[c] = fmax(pa[c], v * edge_factor(i / G, i % G, G));
+    }
+    unsigned outside = 0;
+    for (int c = 0; c < nc; c++) {
+        const double sg_prev_single = co.max(pa[c]);
+        // first member of the tie group at which the running sum reaches the target
+        double j = 1;
+        if (sg[c] > 0) j = ceil((target[c] - B[c]) / sg[c]);
+        if (j < 1) j = 1;
+        if (j > ntie[c]) j = ntie[c];
+        const double cum = B[c] + j * sg[c];
+        const double sg_prev = (j > 1) ? sg[c] : sg_prev_single;
+        if (pk[c] < 0 && j <= 1) outside |= 1u << c;  // ix == 0
+        const double d = sg[c] > 0 ? (cum - target[c]) / sg[c] : 0.0;
+        levels[c] = sg[c] * (1 - d) + d * sg_prev;
+    }
+    return outside;
+}
+
 template <class C>
 GDK_HD unsigned contour_levels_core(const C& co, const double* P, int G, const double* contours, int nc, double* levels) {
     const int n = G * G;
@@ -564,51 +627,5 @@ GDK_HD unsigned contour_levels_core(const C& co, const double* P, int G, const d
             }
         }
     }
-    // at the crossing value K*: cumulative weight strictly below, the halved bin of one member of the tie group,
-    // and the largest element strictly below (the sorted predecessor)
-    unsigned outside = 0;
-    for (int c = 0; c < nc; c++) {
-        const unsigned long long K = hi[c];
-        double below = 0, tie_a = 0, cnt_tie = 0;
-        unsigned long long prevk = 0;
-        bool has_prev = false;
-        for (int i = co.tid; i < n; i += co.nt) {
-            const double v = P[i];
-            const unsigned long long kb = dbl_bits(v);
-            const double a = v * edge_factor(i / G, i % G, G);
-            if (kb < K) {
-                below += a;
-                if (!has_prev || kb > prevk) {
-                    prevk = kb;
-                    has_prev = true;
-                }
-            } else if (kb == K) {
-                tie_a = fmax(tie_a, a);
-                cnt_tie += 1;
-            }
-        }
-        const double B = co.sum(below);
-        const double sg = co.max(tie_a);  // interior members of a tie group all carry the same halved bin
-        const double ntie = co.sum(cnt_tie);
-        const double pk = co.max(has_prev ? bits_dbl(prevk) : -1.0);  // value of the sorted predecessor (or -1)
-        // the predecessor's halved bin: the largest one among the elements equal to pk
-        double pa = 0;
-        if (pk >= 0) {
-            const unsigned long long pkb = dbl_bits(pk);
-            for (int i = co.tid; i < n; i += co.nt)
-                if (dbl_bits(P[i]) == pkb) pa = fmax(pa, P[i] * edge_factor(i / G, i % G, G));
-        }
-        const double sg_prev_single = co.max(pa);
-        // first member of the tie group at which the running sum reaches the target
-        double j = 1;
-        if (sg > 0) j = ceil((target[c] - B) / sg);
-        if (j < 1) j = 1;
-        if (j > ntie) j = ntie;
-        const double cum = B + j * sg;
-        const double sg_prev = (j > 1) ? sg : sg_prev_single;
-        if (pk < 0 && j <= 1) outside |= 1u << c;  // ix == 0
-        const double d = sg > 0 ? (cum - target[c]) / sg : 0.0;
-        levels[c] = sg * (1 - d) + d * sg_prev;
-    }
-    return outside;
+    return contour_finish(co, P, G, hi, target, nc, levels);
 }

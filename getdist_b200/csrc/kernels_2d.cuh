@@ -1019,15 +1019,159 @@ __global__ void __launch_bounds__(256) k_finalize2d(const ConvJob* __restrict__ 
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(mx != 0)) res[blockIdx.y].status |= GDK_ST_ZERO_MAX;
 }
 
-// contour levels of the normalised output grids (densities.py:19-56).  grid (njobs), 1024 threads.
-__global__ void __launch_bounds__(1024) k_contours2d(const ConvJob* __restrict__ jobs, const double* __restrict__ out,
+// contour levels of the normalised output grids (densities.py:19-56).  grid (njobs), 512 threads.
+// The reference sorts the grid and walks the cumulative sum; here the crossing value of every contour is found by a
+// multi-pass radix selection over the IEEE bit patterns (non-negative doubles order like their bits): each pass
+// histograms the halved-edge bin contents -- as 64-bit fixed point, 2^61 = the grid total, so the sums are exact
+// integers and independent of the order of the shared-memory atomics -- of the elements inside the contour's current
+// key interval by their leading CT_BITS bits, scans the histogram and narrows the interval to one digit: at most six
+// sweeps of the (L2-resident) grid instead of one per key bit.  contour_finish then interpolates as the reference does.
+#define CT_BITS 11
+#define CT_NB (1 << CT_BITS)
+#define CT_SMEM (4 * 2 * CT_NB * 4)
+__global__ void __launch_bounds__(512) k_contours2d(const ConvJob* __restrict__ jobs, const double* __restrict__ out,
                                                      const long long* __restrict__ offs, gdk_result2d* __restrict__ res) {
+    extern __shared__ unsigned ct_hist[];  // [4 contours][lo limbs CT_NB | hi limbs CT_NB]
     __shared__ double red[32];
-    const ConvJob jb = jobs[blockIdx.x];
-    if (jb.nc <= 0) return;
+    __shared__ unsigned long long s_klo[4], s_khi[4], s_below[4], s_target[4];
+    __shared__ int s_shift[4], s_done[4];
+    const ConvJob* jp = jobs + blockIdx.x;
+    const int G = jp->G, n = G * G, nc = jp->nc;
+    if (nc <= 0) return;
     CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    const double* P = out + offs[blockIdx.x];
+    double part = 0, pmx = 0;
+    for (int i = co.tid; i < n; i += co.nt) {
+        const double v = P[i];
+        part += v * edge_factor(i / G, i % G, G);
+        pmx = fmax(pmx, v);
+    }
+    const double norm = co.sum(part);
+    const double vmax = co.max(pmx);
+    double target[4];
+    for (int c = 0; c < 4; c++) target[c] = c < nc ? (1 - jp->contours[c]) * norm : 0;
+    const double scale = norm > 0 ? 2305843009213693952.0 / norm : 0.0;  // 2^61 / total
+    if (threadIdx.x < 4) {
+        const int c = threadIdx.x;
+        s_klo[c] = 0;
+        s_khi[c] = dbl_bits(vmax);
+        s_below[c] = 0;
+        const double tq = target[c] * scale;
+        s_target[c] = tq >= 1.0 ? (unsigned long long)__double2ull_ru(tq) : 1ull;
+        s_shift[c] = q_shift_for(s_khi[c], CT_BITS);
+        s_done[c] = (c >= nc || s_khi[c] == 0) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const bool shared_hist = pass == 0;  // all contours still share [0, key(max)]: one histogram
+        bool active = false;
+        for (int c = 0; c < nc; c++) active = active || !s_done[c];
+        if (!active) break;
+        for (int i = threadIdx.x; i < (shared_hist ? 1 : nc) * 2 * CT_NB; i += blockDim.x) ct_hist[i] = 0;
+        unsigned long long klo[4], khi[4];
+        int shift[4], live[4];
+        for (int c = 0; c < 4; c++) {
+            klo[c] = s_klo[c];
+            khi[c] = s_khi[c];
+            shift[c] = s_shift[c];
+            live[c] = c < nc && !s_done[c];
+        }
+        __syncthreads();
+        for (int i = co.tid; i < n; i += co.nt) {
+            const double v = P[i];
+            const unsigned long long kb = dbl_bits(v);
+            const unsigned long long q = __double2ull_rn(v * edge_factor(i / G, i % G, G) * scale);
+            if (q == 0) continue;
+            if (shared_hist) {
+                const unsigned bin = (unsigned)(kb >> shift[0]);
+                smem_add_u64(ct_hist + bin, ct_hist + CT_NB + bin, q);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (live[c] && kb >= klo[c] && kb <= khi[c]) {
+                        const unsigned bin = (unsigned)((kb - klo[c]) >> shift[c]);
+                        smem_add_u64(ct_hist + c * 2 * CT_NB + bin, ct_hist + c * 2 * CT_NB + CT_NB + bin, q);
+                    }
+            }
+        }
+        __syncthreads();
+        // warp c scans the histogram of contour c: lane l owns bins [64 l, 64 l + 64)
+        const int wc = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (wc < nc && live[wc]) {
+            const unsigned* hl = ct_hist + (shared_hist ? 0 : wc * 2 * CT_NB);
+            const unsigned* hh = hl + CT_NB;
+            const int per = CT_NB / 32;
+            unsigned long long mine = 0;
+            int last_nonempty = -1;
+            for (int k = 0; k < per; k++) {
+                const unsigned long long hv = ((unsigned long long)hh[lane * per + k] << 32) | hl[lane * per + k];
+                mine += hv;
+                if (hv) last_nonempty = lane * per + k;
+            }
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned long long before = incl - mine;  // bins of the lower lanes
+            const unsigned long long need = s_target[wc] - s_below[wc];  // > 0 by construction
+            // the lane whose range contains the crossing: first lane with inclusive sum >= need
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+            int lastbin = last_nonempty;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) lastbin = max(lastbin, __shfl_xor_sync(0xffffffffu, lastbin, o));
+            int bsel = -1;
+            unsigned long long bbelow = 0;
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                if (lane == src) {
+                    unsigned long long run = before;
+                    for (int k = 0; k < per; k++) {
+                        const unsigned long long hv = ((unsigned long long)hh[lane * per + k] << 32) | hl[lane * per + k];
+                        if (run + hv >= need) {
+                            bsel = lane * per + k;
+                            bbelow = run;
+                            break;
+                        }
+                        run += hv;
+                    }
+                }
+                bsel = __shfl_sync(0xffffffffu, bsel, src);
+                bbelow = __shfl_sync(0xffffffffu, bbelow, src);
+            } else {  // rounding left the total a hair under the target: the crossing is the largest element
+                bsel = lastbin;
+                const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+                const unsigned long long hv = bsel >= 0 ? (((unsigned long long)hh[bsel] << 32) | hl[bsel]) : 0;
+                bbelow = total - hv;
+            }
+            if (lane == 0) {
+                if (bsel < 0) {
+                    s_done[wc] = 1;  // empty interval (all-zero grid): leave klo
+                } else {
+                    const unsigned long long nlo = s_klo[wc] + ((unsigned long long)bsel << s_shift[wc]);
+                    unsigned long long nhi = nlo + ((1ull << s_shift[wc]) - 1);
+                    if (nhi > s_khi[wc]) nhi = s_khi[wc];
+                    s_below[wc] += bbelow;
+                    s_klo[wc] = nlo;
+                    s_khi[wc] = nhi;
+                    if (s_shift[wc] == 0 || nlo == nhi) {
+                        s_done[wc] = 1;
+                        s_khi[wc] = nlo;
+                    } else {
+                        s_shift[wc] = q_shift_for(nhi - nlo, CT_BITS);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // the interval of a finished contour is one digit wide: its largest member key present in the grid is the crossing
+    // key (shift 0: exactly the key).  A contour stopped by `nlo == nhi` or shift 0 has klo == the key.
+    unsigned long long Kc[4];
+    for (int c = 0; c < 4; c++) Kc[c] = s_klo[c];
     double lv[4] = {0, 0, 0, 0};
-    const unsigned outside = contour_levels_core(co, out + offs[blockIdx.x], jb.G, jb.contours, jb.nc, lv);
+    const unsigned outside = contour_finish(co, P, G, Kc, target, nc, lv);
     if (threadIdx.x == 0) {
         for (int c = 0; c < 4; c++) res[blockIdx.x].levels[c] = lv[c];
         if (outside) res[blockIdx.x].status |= GDK_ST_CONTOUR_RANGE;

@@ -156,7 +156,7 @@ __global__ void k_fill(double* p, int64_t n, double v) {
 }
 
 // ---- fused one-sweep weighted statistics (chains.py:373-412, 709-733, 1446-1474; mcsamples.py:552-576) -------------
-// ONE pass over the samples gives, per row segment: sum w, sum w d, min d, max d and the P x P block sum w d d^T with
+// ONE pass over the samples gives, per row segment: sum w, sum w d, min x, max x and the P x P block sum w d d^T with
 // d = x - s, s = the segment's own first row (a shift that costs nothing to obtain, is the same whatever the number of
 // ranks or the upload chunking, and keeps the one-pass second moments free of cancellation: |d| is a few sigma).
 // Segments are cut at absolute multiples of ST_SEG rows and at chain boundaries; they are merged in a fixed order --
@@ -165,85 +165,123 @@ __global__ void k_fill(double* p, int64_t n, double v) {
 //     D = m_b - m_a,  W = A_a + A_b,  m = m_a + D A_b / W,  S = S_a + S_b + D D^T A_a A_b / W,
 // so the result does not depend on which rank or which upload chunk a block was computed in.
 //
-// k_stats_fused: grid (segments, upper-triangle 64 x 64 parameter tiles), 64 threads, 8 x 8 outputs per thread.
+// k_stats_fused: grid (segments, upper-triangle 64 x 64 parameter tiles), 128 threads, 4 x 8 outputs per thread.
 // Rows are staged 32 at a time through shared memory (k-major, XOR-swizzled pairs: conflict-free 64-bit staging
-// stores and conflict-free LDS.128 operand loads, 8 LDS.128 per 64 DFMA).  Diagonal tiles also produce the column sums
+// stores and conflict-free LDS.128 operand loads, 6 LDS.128 per 32 DFMA).  Diagonal tiles also produce the column sums
 // and min/max (a row with weight 0 still counts for min/max, as in the reference), tile 0 the weight sum.
 #define ST_T 64
 #define ST_RB 32
-#define ST_SEG 8192
+#define ST_SEG 2048
 #define ST_BLOCK 131072
+#define ST_SMEM ((3 * ST_RB * ST_T + 2 * ST_T) * 8)
 __device__ __forceinline__ int st_swz(int c, int k) { return ((((c >> 1) ^ (k & 15)) << 1) | (c & 1)); }
 
 // per-segment partial: [ntile][64*64] second-moment tiles, then B[T*64], min[T*64], max[T*64], then A (+pad to even)
 __host__ __device__ __forceinline__ int64_t st_part_stride(int T, int ntile) { return (int64_t)ntile * (ST_T * ST_T) + 3 * T * ST_T + 2; }
 
-__global__ void __launch_bounds__(64) k_stats_fused(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
-                                                    const Seg* __restrict__ segs, int P, int T, int ntile,
-                                                    const int2* __restrict__ tiles, double* __restrict__ part) {
-    __shared__ __align__(16) double As[ST_RB][ST_T];
-    __shared__ __align__(16) double Bs[ST_RB][ST_T];
-    __shared__ double shA[ST_T], shB[ST_T];
+__global__ void __launch_bounds__(128, 3) k_stats_fused(const double* __restrict__ dX, int64_t ld, const double* __restrict__ dW,
+                                                        const Seg* __restrict__ segs, int P, int T, int ntile,
+                                                        const int2* __restrict__ tiles, double* __restrict__ part) {
+    extern __shared__ __align__(16) double st_sm[];  // ST_SMEM bytes (opt-in: more than 48 KB)
+    double(*As)[ST_T] = reinterpret_cast<double(*)[ST_T]>(st_sm);
+    double(*Bs)[ST_T] = reinterpret_cast<double(*)[ST_T]>(st_sm + ST_RB * ST_T);
+    double(*Xs)[ST_T] = reinterpret_cast<double(*)[ST_T]>(st_sm + 2 * ST_RB * ST_T);  // diagonal tiles: the raw values
+                                                            // (exact min / max: (x - s) + s need not give x back)
+    double* shA = st_sm + 3 * ST_RB * ST_T;
+    double* shB = shA + ST_T;
     const Seg sg = segs[blockIdx.x];
     const int2 tl = tiles[blockIdx.y];
     const int i0 = tl.x * ST_T, j0 = tl.y * ST_T;
     const bool diag = tl.x == tl.y;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int tx = t & 7, ty = t >> 3;
-    {
+    const int tx = t & 7, ty = t >> 3;  // 8 x 16 threads, 4 (rows) x 8 (columns) outputs each
+    if (t < ST_T) {
         const int ci = i0 + t, cj = j0 + t;
         shA[t] = ci < P ? dX[(int64_t)ci * ld + sg.r0] : 0.0;
         shB[t] = cj < P ? dX[(int64_t)cj * ld + sg.r0] : 0.0;
     }
     __syncthreads();
-    double acc[8][8];
+    double acc[4][8];
 #pragma unroll
-    for (int e = 0; e < 8; e++)
+    for (int e = 0; e < 4; e++)
 #pragma unroll
         for (int f = 0; f < 8; f++) acc[e][f] = 0;
-    double sa = 0, mn = 0, mx = 0, sw = 0;  // d = 0 (the segment's first row) is always inside [min d, max d]
+    const int ct = t & (ST_T - 1);  // threads 0..63: column ct of a diagonal tile
+    double sa = 0, mn = shA[ct], mx = shA[ct], sw = 0;
     for (int64_t rb = sg.r0; rb < sg.r1; rb += ST_RB) {
         const int64_t r = rb + lane;
         const bool ok = r < sg.r1;
+        const int64_t rr = ok ? r : sg.r1 - 1;
         const double wv = ok ? dW[r] : 0.0;
         sw += wv;
-        // warp `wid` stages columns [32 wid, 32 wid + 32) of both sides; lane = row (coalesced along N)
-#pragma unroll 8
-        for (int cc = 0; cc < 32; cc++) {
-            const int c = 32 * wid + cc;
-            const int ci = i0 + c, cj = j0 + c;
-            const double da = (ok && ci < P) ? ldg_stream(dX + (int64_t)ci * ld + r) - shA[c] : 0.0;
-            const double a = da * wv;
-            double b = da;
-            if (!diag) b = (ok && cj < P) ? ldg_stream(dX + (int64_t)cj * ld + r) - shB[c] : 0.0;
-            As[lane][st_swz(c, lane)] = a;
-            Bs[lane][st_swz(c, lane)] = b;
+        // warp `wid` stages columns [16 wid, 16 wid + 16) of both sides; lane = row (coalesced along N).  Loads are
+        // unconditional on clamped addresses and issued eight at a time before their first use (the latency of a batch
+        // is paid once); the out-of-range ones are replaced afterwards.
+        if (diag) {
+#pragma unroll
+            for (int c8 = 0; c8 < 16; c8 += 8) {
+                double xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) xv[u] = __ldcs(dX + (int64_t)min(i0 + 16 * wid + c8 + u, P - 1) * ld + rr);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int c = 16 * wid + c8 + u;
+                    const double xa = (ok && i0 + c < P) ? xv[u] : shA[c];
+                    const double da = xa - shA[c];
+                    const int sc = st_swz(c, lane);
+                    As[lane][sc] = da * wv;
+                    Bs[lane][sc] = da;
+                    Xs[lane][sc] = xa;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+                double xv[4], yv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    xv[u] = __ldcs(dX + (int64_t)min(i0 + 16 * wid + c4 + u, P - 1) * ld + rr);
+                    yv[u] = __ldcs(dX + (int64_t)min(j0 + 16 * wid + c4 + u, P - 1) * ld + rr);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = 16 * wid + c4 + u;
+                    const double da = (ok && i0 + c < P) ? xv[u] - shA[c] : 0.0;
+                    const double db = (ok && j0 + c < P) ? yv[u] - shB[c] : 0.0;
+                    const int sc = st_swz(c, lane);
+                    As[lane][sc] = da * wv;
+                    Bs[lane][sc] = db;
+                }
+            }
         }
         __syncthreads();
 #pragma unroll 4
         for (int k = 0; k < ST_RB; k++) {
-            double a[8], b[8];
+            double a[4], b[8];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const double2 av = *reinterpret_cast<const double2*>(&As[k][((ty + 8 * q) ^ (k & 15)) << 1]);
-                const double2 bv = *reinterpret_cast<const double2*>(&Bs[k][((tx + 8 * q) ^ (k & 15)) << 1]);
+            for (int q = 0; q < 2; q++) {
+                const double2 av = *reinterpret_cast<const double2*>(&As[k][((ty + 16 * q) ^ (k & 15)) << 1]);
                 a[2 * q] = av.x;
                 a[2 * q + 1] = av.y;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double2 bv = *reinterpret_cast<const double2*>(&Bs[k][((tx + 8 * q) ^ (k & 15)) << 1]);
                 b[2 * q] = bv.x;
                 b[2 * q + 1] = bv.y;
             }
 #pragma unroll
-            for (int e = 0; e < 8; e++)
+            for (int e = 0; e < 4; e++)
 #pragma unroll
                 for (int f = 0; f < 8; f++) acc[e][f] = fma(a[e], b[f], acc[e][f]);
         }
-        if (diag) {  // column t: sum of w d, min / max of d over the 32 staged rows
+        if (diag && t < ST_T) {  // column t: sum of w d, exact min / max of x over the 32 staged rows
 #pragma unroll 8
             for (int k = 0; k < ST_RB; k++) {
                 sa += As[k][st_swz(t, k)];
-                const double d = Bs[k][st_swz(t, k)];
-                mn = fmin(mn, d);
-                mx = fmax(mx, d);
+                const double xv = Xs[k][st_swz(t, k)];
+                mn = fmin(mn, xv);
+                mx = fmax(mx, xv);
             }
         }
         __syncthreads();
@@ -251,8 +289,8 @@ __global__ void __launch_bounds__(64) k_stats_fused(const double* __restrict__ d
     double* o = part + (int64_t)blockIdx.x * st_part_stride(T, ntile);
     double* oc = o + (int64_t)blockIdx.y * (ST_T * ST_T);
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const int i = 2 * ty + (e & 1) + 16 * (e >> 1);
+    for (int e = 0; e < 4; e++) {
+        const int i = 2 * ty + (e & 1) + 32 * (e >> 1);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int j = 2 * tx + 16 * q;
@@ -261,9 +299,11 @@ __global__ void __launch_bounds__(64) k_stats_fused(const double* __restrict__ d
     }
     if (diag) {
         double* ob = o + (int64_t)ntile * (ST_T * ST_T);
-        ob[i0 + t] = sa;
-        ob[T * ST_T + i0 + t] = mn;
-        ob[2 * T * ST_T + i0 + t] = mx;
+        if (t < ST_T) {
+            ob[i0 + t] = sa;
+            ob[T * ST_T + i0 + t] = mn;
+            ob[2 * T * ST_T + i0 + t] = mx;
+        }
         if (blockIdx.y == 0 && wid == 0) {
             sw = warp_sum(sw);
             if (lane == 0) ob[3 * T * ST_T] = sw;
@@ -301,8 +341,8 @@ __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ 
         const int64_t r0 = segs[s].r0;
         for (int c = threadIdx.x; c < P; c += blockDim.x) {
             const double sh = dX[(int64_t)c * ld + r0];
-            out[1 + P + c] = fmin(out[1 + P + c], sh + pb[T * ST_T + c]);
-            out[1 + 2 * P + c] = fmax(out[1 + 2 * P + c], sh + pb[2 * T * ST_T + c]);
+            out[1 + P + c] = fmin(out[1 + P + c], pb[T * ST_T + c]);
+            out[1 + 2 * P + c] = fmax(out[1 + 2 * P + c], pb[2 * T * ST_T + c]);
             if (As_ > 0) {
                 const double d = pb[c] / As_;
                 ds[c] = d;

@@ -161,15 +161,55 @@ class _LimitGrids:
 
 class Density2D(GridDensity):
     def __init__(self, x, y, P=None, view_ranges=None, mask=None):
-        self.x = x
-        self.y = y
-        self.axes = [y, x]
+        self._x = x
+        self._y = y
         self.view_ranges = view_ranges
         self.mask = mask
-        self.spacing = (self.x[1] - self.x[0]) * (self.y[1] - self.y[0])
         self.likes = None
         self.contours = None
         self.setP(P)
+
+    @classmethod
+    def on_linspace(cls, xr, yr, P, view_ranges=None):
+        """Grid on x = linspace(*xr), y = linspace(*yr) (xr = (lo, hi, n)).  The axis vectors are only built when
+        something reads them: the batched calls hand back thousands of these per launch."""
+        d = cls.__new__(cls)
+        d._x = d._y = None
+        d._xr, d._yr = xr, yr
+        d.view_ranges = view_ranges
+        d.mask = d.likes = d.contours = d.spl = None
+        if P.shape != (yr[2], xr[2]):
+            raise DensitiesError("Array size mismatch in Density arrays: P %s, axes %s" % (P.shape, (yr[2], xr[2])))
+        d.P = P
+        return d
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = np.linspace(*self._xr)
+        return self._x
+
+    @x.setter
+    def x(self, v):
+        self._x = v
+
+    @property
+    def y(self):
+        if self._y is None:
+            self._y = np.linspace(*self._yr)
+        return self._y
+
+    @y.setter
+    def y(self, v):
+        self._y = v
+
+    @property
+    def axes(self):
+        return [self.y, self.x]
+
+    @property
+    def spacing(self):
+        return (self.x[1] - self.x[0]) * (self.y[1] - self.y[0])
 
     def integrate(self, P):
         """trapezoid rule on the grid: corners weigh 1/4, edges 1/2 (reference densities.py:273-280)"""

@@ -1201,39 +1201,45 @@ class MCSamples:
         """Density2D objects (+ the reference's warnings / errors) from the grids of a 2D batch; `buf` holds density i at
         buf[offsets[i]:][:G*G]"""
         out = []
-        for (j, j2), spr, off, r in zip(pairs, specs, offsets, res):
-            sp = _SpecView(spr)
-            parx, pary = self.paramNames.names[j], self.paramNames.names[j2]
-            if r.status & _abi.ST_BIAS_NEG:
-                raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
-            if r.status & _abi.ST_BW_FALLBACK:
-                msg = "2D kernel density bandwidth optimizer failed for %s, %s. Using fallback width" % (parx.name, pary.name)
-                if self.raise_on_bandwidth_errors:
-                    raise BandwidthError(msg)
-                log.warning(msg)
-            if r.status & _abi.ST_SMALL_SMOOTH:
-                log.warning("fine_bins_2D not large enough for optimal density: %s, %s", parx.name, pary.name)
-            if r.status & _abi.ST_ZERO_MAX:
-                raise DensitiesError("no samples in bin")
-            G = sp.fine_bins
-            x = np.linspace(sp.xbinmin, sp.xbinmax, G)
-            y = np.linspace(sp.ybinmin, sp.ybinmax, G)
-            d = Density2D(x, y, buf[off: off + G * G].reshape(G, G),
-                          view_ranges=[(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
+        names = self.paramNames.names
+        # plain Python scalars of the spec columns once per batch (a field access per pair costs microseconds)
+        col = {k: specs[k].tolist() for k in ("fine_bins", "xbinmin", "xbinmax", "ybinmin", "ybinmax", "bw_mode")}
+        offsets = [int(o) for o in offsets]
+        bad = _abi.ST_BIAS_NEG | _abi.ST_BW_FALLBACK | _abi.ST_SMALL_SMOOTH | _abi.ST_ZERO_MAX
+        nc = len(conts)
+        for n, ((j, j2), off, r) in enumerate(zip(pairs, offsets, res)):
+            parx, pary = names[j], names[j2]
+            status = r.status
+            if status & bad:
+                if status & _abi.ST_BIAS_NEG:
+                    raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
+                if status & _abi.ST_BW_FALLBACK:
+                    msg = "2D kernel density bandwidth optimizer failed for %s, %s. Using fallback width" % (parx.name, pary.name)
+                    if self.raise_on_bandwidth_errors:
+                        raise BandwidthError(msg)
+                    log.warning(msg)
+                if status & _abi.ST_SMALL_SMOOTH:
+                    log.warning("fine_bins_2D not large enough for optimal density: %s, %s", parx.name, pary.name)
+                if status & _abi.ST_ZERO_MAX:
+                    raise DensitiesError("no samples in bin")
+            G = col["fine_bins"][n]
+            d = Density2D.on_linspace((col["xbinmin"][n], col["xbinmax"][n], G), (col["ybinmin"][n], col["ybinmax"][n], G),
+                                      buf[off: off + G * G].reshape(G, G),
+                                      [(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
             if masks is not None:  # bool_mask, mcsamples.py:1917, 1986
-                w = len(masks[len(out)]) - G
+                w = len(masks[n]) - G
                 w //= 2
-                d.mask = np.asarray(masks[len(out)][w: w + G, w: w + G] < 1e-8)
-            d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=r.status, t_star=r.t_star,
-                          n_brent=r.n_brent, bw_mode=sp.bw_mode, fine_bins=G,
-                          levels=(conts, [r.levels[k] for k in range(len(conts))]) if conts else None)
+                d.mask = np.asarray(masks[n][w: w + G, w: w + G] < 1e-8)
+            d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=status, t_star=r.t_star,
+                          n_brent=r.n_brent, bw_mode=col["bw_mode"][n], fine_bins=G,
+                          levels=(conts, r.levels[:nc]) if nc else None)
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
             if cache:
                 # the cache entry is a READ-ONLY view into the batch buffer (no second copy of a gigabyte of grids);
                 # get2DDensity / get2DDensityGridData hand out private copies of it (_cached_2d), as the reference
                 # returns a fresh grid per call and callers normalise in place
-                d.P.setflags(write=False)
+                d.P.flags.writeable = False
                 self._density2D[(j, j2)] = d
             out.append(d)
         return out
