@@ -38,12 +38,14 @@ struct CoopHost {
     double sum(double v) const { return v; }
     double max(double v) const { return v; }
     int any(int v) const { return v; }
+    void sumv(double* v, int n) const {}
 };
 
 #if defined(__CUDACC__)
 struct CoopBlock {
     int tid, nt;
-    double* red;  // >= 32 doubles of shared memory
+    double* red;              // >= 32 doubles of shared memory
+    double* redv = nullptr;   // optional: >= 8 * 32 doubles for the fused reduction of up to 8 values (sumv)
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
@@ -68,5 +70,28 @@ struct CoopBlock {
         return t;
     }
     __device__ __forceinline__ int any(int v) const { return __syncthreads_or(v); }
+    // sums of n <= 8 values at once (same order as `sum`): two barriers instead of 2 n
+    __device__ __forceinline__ void sumv(double* v, int n) const {
+        if (!redv) {
+            for (int k = 0; k < n; k++) v[k] = sum(v[k]);
+            return;
+        }
+        for (int k = 0; k < n; k++) {
+            double t = v[k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            v[k] = t;
+        }
+        __syncthreads();
+        if ((tid & 31) == 0)
+            for (int k = 0; k < n; k++) redv[k * 32 + (tid >> 5)] = v[k];
+        __syncthreads();
+        const int nw = (nt + 31) >> 5;
+        for (int k = 0; k < n; k++) {
+            double t = 0;
+            for (int i = 0; i < nw; i++) t += redv[k * 32 + i];
+            v[k] = t;
+        }
+    }
 };
 #endif

@@ -184,7 +184,7 @@ extern "C" int32_t gdk_create(int32_t device, gdk_ctx** out) {
         const char* ess = getenv("GDK_SHEAR_SORTED");
         ctx->shear_sorted = ess && ess[0] == '1';
         const char* ebt = getenv("GDK_BW2D_THREADS");
-        if (ebt && (atoi(ebt) == 256 || atoi(ebt) == 512 || atoi(ebt) == 768)) ctx->bw2d_threads = atoi(ebt);
+        if (ebt && (atoi(ebt) == 128 || atoi(ebt) == 256)) ctx->bw2d_threads = atoi(ebt);
         const char* enp = getenv("GDK_SHEAR_NP");
         if (enp && atoi(enp) >= 1 && atoi(enp) <= 6) ctx->shear_np = atoi(enp);
         const char* em = getenv("GDK_SORTED_MIN_N");

@@ -120,7 +120,7 @@ struct gdk_ctx {
     bool cluster_ok = false, use_bands = false, use_hot = true, use_sorted = true, shear_sorted = false;
     int64_t sorted_min_n = 1 << 15;
     int shear_np = 3;        // max jobs per group of k_shear_hist_w (GDK_SHEAR_NP: 1..6; fewer jobs = larger windows)
-    int bw2d_threads = 256;  // CTA size of k_bw2d (GDK_BW2D_THREADS: 256 = three pairs per SM, 768 = one)
+    int bw2d_threads = 256;  // CTA size of k_bw2d (GDK_BW2D_THREADS: 128 or 256)
     DevBuf<unsigned char> recs;         // bucket-sorted sweep: 32-byte records [job][position]
     DevBuf<unsigned long long> recw;    // ... and their fixed-point weights
     DevBuf<unsigned> bucket;            // bucket counts / starts / write cursors

@@ -27,30 +27,71 @@ struct Kde2dConsts {
     double twopipow[12];  // (2 pi)^k, k = 0..11
 };
 
+struct PsiEntry {
+    int s0, s1;
+    double time;
+};
+
 struct Kde2dWork {
     const double* a2;    // squared dct2d of the normalised histogram, G x G row-major [ky][kx]; row/col 0 unused
     const double* aFFT;  // |fft2|^2, G x G, or NULL when do_correlation is off
     int G;
     double* wx;  // [PSI_MAXE][G] scratch (shared memory on the device)
     double* wy;  // [PSI_MAXE][G]
+    int* cut;    // [2 * PSI_MAXE] scratch (shared memory on the device): frequency cut-offs of the current level
+    PsiEntry* ebuf;  // [PSI_MAXE] scratch (shared memory on the device): the entries of the current level -- their
+                     // plug-in times cost two pow() each and are computed by ONE thread per entry, not by every thread
 };
 
-struct PsiEntry {
-    int s0, s1;
-    double time;
-};
+// The weights of a psi functional, exp(-a i^2) i^p, fall off like a Gaussian in the frequency index: beyond
+// psi_cut(...) every weight is below 1e-30 of the largest one and the terms (|a2| <= 1) cannot reach the last bit of
+// the sum.  Returns the smallest c in [1, imax] with exp(-a i^2 + p ln i) < e^-70 * max for every i > c.
+GDK_HD double psi_ipow(double x, int s) {  // x^s, s >= 0 small, by products
+    double r = 1;
+    for (; s > 0; s >>= 1, x *= x)
+        if (s & 1) r *= x;
+    return r;
+}
+GDK_HD int psi_cut(double a, double p, int imax) {
+    if (!(a > 0) || !(a < INFINITY) || imax < 2) return imax;
+    double ipk = p > 0 ? sqrt(p / (2 * a)) : 1.0;  // maximum of -a i^2 + p ln i
+    if (!(ipk >= 1)) ipk = 1;
+    if (ipk >= imax) return imax;
+    const double thr = -a * ipk * ipk + p * log(ipk) - 70.0;
+    int lo = (int)ipk, hi = imax;
+    if (-a * (double)hi * hi + p * log((double)hi) >= thr) return imax;
+    while (hi - lo > 1) {  // the log-weight decreases beyond the maximum: L(lo) >= thr > L(hi)
+        const int mid = (lo + hi) >> 1;
+        if (-a * (double)mid * mid + p * log((double)mid) < thr)
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return lo;
+}
 
 // psi(s, time) for up to PSI_MAXE entries in one sweep over a2 (kde_bandwidth.py:182-186)
 template <class C>
 GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W, const PsiEntry* e, int n, double* out) {
     const int G = W.G;
-    for (int it = co.tid; it < n * (G - 1); it += co.nt) {
-        const int k = it / (G - 1), i = it - k * (G - 1) + 1;  // i = 1..G-1
+    for (int q = co.tid; q < 2 * n; q += co.nt) {  // one thread per (entry, axis): where the weights of this level die out
+        const int k = q >> 1;
+        W.cut[q] = psi_cut(K.pi2 * e[k].time, 2.0 * ((q & 1) ? e[k].s1 : e[k].s0), G - 1);
+    }
+    co.sync();
+    int xcut = 1, ycut = 1;
+    for (int k = 0; k < n; k++) {
+        xcut = W.cut[2 * k] > xcut ? W.cut[2 * k] : xcut;
+        ycut = W.cut[2 * k + 1] > ycut ? W.cut[2 * k + 1] : ycut;
+    }
+    // weights exp(-i^2 pi^2 t) (i^2)^s up to the cut-offs only (one exp per entry and index; integer powers by products)
+    const int fc = xcut > ycut ? xcut : ycut;
+    for (int it = co.tid; it < n * fc; it += co.nt) {
+        const int k = it / fc, i = it - k * fc + 1;  // i = 1..fc
         const double I = (double)i * (double)i;
-        const double logI = log(I);
-        const double w = -I * (K.pi2 * e[k].time);
-        W.wx[k * G + i] = exp(w + logI * e[k].s0);
-        W.wy[k * G + i] = exp(w + logI * e[k].s1);
+        const double ew = exp(-I * (K.pi2 * e[k].time));
+        W.wx[k * G + i] = ew * psi_ipow(I, e[k].s0);
+        W.wy[k * G + i] = ew * psi_ipow(I, e[k].s1);
     }
     co.sync();
     double part[PSI_MAXE];
@@ -59,29 +100,29 @@ GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W
     // coalesced loads of a2.  The row weights wy_k[y] are uniform over the group and hoisted out of the x loop.
     const int L = co.nt >= 32 ? 32 : co.nt;
     const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
-    for (int y = 1 + grp; y < G; y += ngrp) {
+    for (int y = 1 + grp; y <= ycut; y += ngrp) {
         double wyk[PSI_MAXE];
         for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
         const double* row = W.a2 + (size_t)y * G;
-        for (int x0 = 1 + lane; x0 < G; x0 += 4 * L) {
+        for (int x0 = 1 + lane; x0 <= xcut; x0 += 4 * L) {
             double v[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int x = x0 + j * L;
-                v[j] = x < G ? row[x] : 0.0;
+                v[j] = x <= xcut ? row[x] : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int x = x0 + j * L;
-                if (x < G)
+                if (x <= xcut)
                     for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + x];
             }
         }
     }
+    co.sumv(part, n);
     for (int k = 0; k < n; k++) {
-        const double s = co.sum(part[k]);
         const int ss = e[k].s0 + e[k].s1;
-        out[k] = ((ss & 1) ? -1.0 : 1.0) * s * K.pipow[ss] / 4;
+        out[k] = ((ss & 1) ? -1.0 : 1.0) * part[k] * K.pipow[ss] / 4;
     }
     co.sync();
 }
@@ -90,41 +131,58 @@ GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W
 template <class C>
 GDK_HD void psi_odd_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W, const PsiEntry* e, int n, double* out) {
     const int G = W.G;
-    for (int it = co.tid; it < n * G; it += co.nt) {
-        const int k = it / G, i = it - k * G;
-        const double f = (i < (G + 1) / 2) ? (double)i : (double)(i - G);
-        const double w = exp(-(f * f) * (4 * K.pi2 * e[k].time));
-        W.wx[k * G + i] = w * pow(f, (double)e[k].s0);
-        W.wy[k * G + i] = w * pow(f, (double)e[k].s1);
+    for (int q = co.tid; q < 2 * n; q += co.nt) {
+        const int k = q >> 1;
+        W.cut[q] = psi_cut(4 * K.pi2 * e[k].time, (double)((q & 1) ? e[k].s1 : e[k].s0), G / 2);
+    }
+    co.sync();
+    int xcut = 1, ycut = 1;
+    for (int k = 0; k < n; k++) {
+        xcut = W.cut[2 * k] > xcut ? W.cut[2 * k] : xcut;
+        ycut = W.cut[2 * k + 1] > ycut ? W.cut[2 * k + 1] : ycut;
+    }
+    // frequencies |f| <= cut: indices [0, cut] and [G - cut, G - 1] (everything when the two bands meet)
+    const int nx = (2 * xcut + 1 < G) ? 2 * xcut + 1 : G, ny = (2 * ycut + 1 < G) ? 2 * ycut + 1 : G;
+    {
+        const int fc = xcut > ycut ? xcut : ycut;
+        const int nf = (2 * fc + 1 < G) ? 2 * fc + 1 : G;
+        for (int it = co.tid; it < n * nf; it += co.nt) {
+            const int k = it / nf, ii = it - k * nf;
+            const int i = (nf == G || ii <= fc) ? ii : G - (nf - ii);
+            const double f = (i < (G + 1) / 2) ? (double)i : (double)(i - G);
+            const double w = exp(-(f * f) * (4 * K.pi2 * e[k].time));
+            W.wx[k * G + i] = w * psi_ipow(f, e[k].s0);
+            W.wy[k * G + i] = w * psi_ipow(f, e[k].s1);
+        }
     }
     co.sync();
     double part[PSI_MAXE];
     for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
     const int L = co.nt >= 32 ? 32 : co.nt;
     const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
-    for (int y = grp; y < G; y += ngrp) {
+    for (int yy = grp; yy < ny; yy += ngrp) {
+        const int y = (ny == G || yy <= ycut) ? yy : G - (ny - yy);
         double wyk[PSI_MAXE];
         for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
         const double* row = W.aFFT + (size_t)y * G;
-        for (int x0 = lane; x0 < G; x0 += 4 * L) {
+        for (int x0 = lane; x0 < nx; x0 += 4 * L) {
             double v[4];
+            int xi[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int x = x0 + j * L;
-                v[j] = x < G ? row[x] : 0.0;
+                const int xx = x0 + j * L;
+                xi[j] = (nx == G || xx <= xcut) ? xx : G - (nx - xx);
+                v[j] = xx < nx ? row[xi[j]] : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int x = x0 + j * L;
-                if (x < G)
-                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + x];
+                if (x0 + j * L < nx)
+                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + xi[j]];
             }
         }
     }
-    for (int k = 0; k < n; k++) {
-        const double s = co.sum(part[k]);
-        out[k] = s * K.twopipow[e[k].s0 + e[k].s1];
-    }
+    co.sumv(part, n);
+    for (int k = 0; k < n; k++) out[k] = part[k] * K.twopipow[e[k].s0 + e[k].s1];
     co.sync();
 }
 
@@ -138,7 +196,7 @@ GDK_HD int func2d_table(const C& co, const Kde2dConsts& K, const Kde2dWork& W, d
         PsiEntry e[PSI_MAXE];
         double out[PSI_MAXE];
         const int n = ssum + 1;
-        for (int s0 = 0; s0 <= ssum; s0++) {
+        for (int s0 = co.tid; s0 <= ssum; s0 += co.nt) {
             const int s1 = ssum - s0;
             double time = t;
             if (ssum <= 4) {
@@ -146,8 +204,12 @@ GDK_HD int func2d_table(const C& co, const Kde2dConsts& K, const Kde2dWork& W, d
                 const double cst = (1 + pow(0.5, (double)(ssum + 1))) / 3;
                 time = pow(-2 * cst * K.K[s0] * K.K[s1] / N / sum_func, 1.0 / (2 + ssum));
             }
-            e[s0] = PsiEntry{s0, s1, time};
-            if (!(time == time)) bad = 1;
+            W.ebuf[s0] = PsiEntry{s0, s1, time};
+        }
+        co.sync();
+        for (int k = 0; k < n; k++) {
+            e[k] = W.ebuf[k];
+            if (!(e[k].time == e[k].time)) bad = 1;
         }
         psi_even_level(co, K, W, e, n, out);
         for (int s0 = 0; s0 <= ssum; s0++) {
@@ -352,20 +414,25 @@ GDK_HD Bw2dOut kernel_optimizer_2d(const C& co, const Kde2dConsts& K, const Kde2
     for (int ssum = 10; ssum >= 4; ssum -= 2) {
         PsiEntry e[PSI_MAXE];
         double out[PSI_MAXE];
-        int n = 0;
-        for (int s0 = 1; s0 < ssum; s0 += 2) {
-            const int s1 = ssum - s0;
+        const int n = ssum / 2;  // s0 = 1, 3, ..., ssum - 1
+        for (int k = co.tid; k < n; k += co.nt) {
+            const int s0 = 2 * k + 1, s1 = ssum - s0;
             double time = t_star;
             if (ssum <= 8) {
                 const double sum_func = otab[s0 + 2][s1] + otab[s0][s1 + 2];
                 const double cst = 8 * (1 - pow(2.0, (double)(-ssum - 1))) / 3.0;
                 time = pow(cst * p00 * K.Kodd[s0] * K.Kodd[s1] / (N * N) / (sum_func * sum_func), 1.0 / (3 + ssum));
             }
-            e[n++] = PsiEntry{s0, s1, time};
+            W.ebuf[k] = PsiEntry{s0, s1, time};
         }
+        co.sync();
+        for (int k = 0; k < n; k++) e[k] = W.ebuf[k];
         psi_odd_level(co, K, W, e, n, out);
         for (int k = 0; k < n; k++) otab[e[k].s0][e[k].s1] = out[k];
     }
+    // the AMISE minimisation is scalar code and only the group's thread 0 hands the result on: the others are done
+    // (no barrier follows)
+    if (co.tid != 0) return o;
     Amise am{p_20, p_02, p_11, otab[3][1], otab[1][3], N};
     double AM = am(h_x, h_y, 0.0);
     if (!(AM < INFINITY)) {

@@ -510,14 +510,16 @@ struct Bw2dJob {
     int shear;    // index into ShearGeom or -1
 };
 
-// grid (npairs), 512 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
-__global__ void __launch_bounds__(768, 1) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
+// grid (npairs), 256 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
+__global__ void __launch_bounds__(256, 2) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
                                               const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res) {
     extern __shared__ __align__(16) unsigned char bsm[];
-    __shared__ double red[32];
+    __shared__ double red[32], redv[8 * 32];
+    __shared__ int cuts[2 * PSI_MAXE];
+    __shared__ PsiEntry ebuf[PSI_MAXE];
     const gdk_spec2d sp = specs[blockIdx.x];
     const Bw2dJob jb = jobs[blockIdx.x];
-    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red};
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red, redv};
     Bw2dOut o{0, 0, 0, NAN, 0u, 0, 0};
     double r2 = 0;
     if (sp.bw_mode == GDK_BW2D_PLAIN || sp.bw_mode == GDK_BW2D_SHEAR) {
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(768, 1) k_bw2d(const gdk_spec2d* __restrict__ 
         double* wy = wx + (size_t)PSI_MAXE * G;
         const bool has_limits = sp.x_has_bot || sp.x_has_top || sp.y_has_bot || sp.y_has_top;
         const int do_corr = has_limits ? 0 : 1;
-        Kde2dWork W{jb.a2, do_corr ? jb.aFFT : nullptr, G, wx, wy};
+        Kde2dWork W{jb.a2, do_corr ? jb.aFFT : nullptr, G, wx, wy, cuts, ebuf};
         if (sp.bw_mode == GDK_BW2D_PLAIN) {
             const double rangex = sp.xbinmax - sp.xbinmin, rangey = sp.ybinmax - sp.ybinmin;
             const double q = fmin(sp.y_sigma_range / rangey, sp.x_sigma_range / rangex) / pow(sp.neff, 1.0 / 6);

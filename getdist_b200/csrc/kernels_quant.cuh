@@ -149,15 +149,13 @@ __global__ void __launch_bounds__(1024) k_qhist(const double* __restrict__ dX, i
     for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
         unsigned long long key[4], wq[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int64_t r = r0 + (int64_t)k * blockDim.x;
-            key[k] = 0;
-            wq[k] = 0;
-            if (r < sg.r1) {
-                key[k] = f64_to_key(ldg_stream(x + r));
-                if (shared_first) wq[k] = dWq[r];  // first pass: every sample lands in the histogram
-            }
+        for (int k = 0; k < 4; k++) {  // unconditional loads on clamped rows: all eight are in flight before the first use
+            const int64_t r = min(r0 + (int64_t)k * blockDim.x, sg.r1 - 1);
+            key[k] = (unsigned long long)__double_as_longlong(__ldcs(x + r));
+            wq[k] = shared_first ? __ldcs(dWq + r) : 0ull;  // first pass: every sample lands in the histogram
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) key[k] = (key[k] >> 63) ? ~key[k] : (key[k] | 0x8000000000000000ull);  // f64_to_key
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int64_t r = r0 + (int64_t)k * blockDim.x;
@@ -295,10 +293,10 @@ __global__ void __launch_bounds__(256) k_qgather(const double* __restrict__ dX, 
     for (int64_t r0 = sg.r0 + threadIdx.x; r0 < sg.r1; r0 += 4 * (int64_t)blockDim.x) {
         unsigned long long key[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int64_t r = r0 + (int64_t)k * blockDim.x;
-            key[k] = (r < sg.r1) ? f64_to_key(ldg_stream(x + r)) : 0ull;
-        }
+        for (int k = 0; k < 4; k++)  // unconditional loads on clamped rows: all four in flight before the first use
+            key[k] = (unsigned long long)__double_as_longlong(__ldcs(x + min(r0 + (int64_t)k * blockDim.x, sg.r1 - 1)));
+#pragma unroll
+        for (int k = 0; k < 4; k++) key[k] = (key[k] >> 63) ? ~key[k] : (key[k] | 0x8000000000000000ull);  // f64_to_key
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int64_t r = r0 + (int64_t)k * blockDim.x;

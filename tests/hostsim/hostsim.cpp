@@ -167,7 +167,9 @@ int hs_bw2d(const double* a2, const double* aFFT, int G, double N, double corr, 
     Kde2dConsts K;
     gdk_fill_kde2d_consts(&K);
     std::vector<double> wx((size_t)PSI_MAXE * G), wy((size_t)PSI_MAXE * G);
-    Kde2dWork W{a2, do_corr ? aFFT : nullptr, G, wx.data(), wy.data()};
+    std::vector<int> cut(2 * PSI_MAXE);
+    std::vector<PsiEntry> ebuf(PSI_MAXE);
+    Kde2dWork W{a2, do_corr ? aFFT : nullptr, G, wx.data(), wy.data(), cut.data(), ebuf.data()};
     Bw2dOut o = kernel_optimizer_2d(co, K, W, N, corr, do_corr, have_ft, ft);
     out[0] = o.hx; out[1] = o.hy; out[2] = o.c; out[3] = o.t_star;
     iout[0] = (int)o.status; iout[1] = o.n_brent; iout[2] = o.failed;
