@@ -486,6 +486,8 @@ def run_ours(args):
         t2 = time.perf_counter()
         s = float(a[0].P[F // 2]) + float(b[0].P[b[0].P.shape[0] // 2, b[0].P.shape[1] // 2])
         e2e_parts.update(upload_and_moments_s=t1 - t0, prefetch_triangle_s=t2 - t1)
+        if getattr(m, "last_prefetch_ms", None):
+            e2e_parts["prefetch_ms"] = {k: (round(v, 2) if v is not None else None) for k, v in m.last_prefetch_ms.items()}
         if world > 1:
             e2e_parts["group"] = dict(pg.timings)
         holder["d"] = (a, b)

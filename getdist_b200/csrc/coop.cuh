@@ -39,13 +39,23 @@ struct CoopHost {
     double max(double v) const { return v; }
     int any(int v) const { return v; }
     void sumv(double* v, int n) const {}
+    // part[k] += sum_{y0 <= y <= y1} sum_{x0 <= x <= x1} wy[k*G + y] * A[y*G + x] * wx[k*G + x],  k < n
+    void bilinear(const double* A, int G, int y0, int y1, int x0, int x1, const double* wx, const double* wy, int n,
+                  double* part) const {
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++)
+                for (int k = 0; k < n; k++) part[k] += (wy[k * G + y] * A[(size_t)y * G + x]) * wx[k * G + x];
+    }
 };
 
 #if defined(__CUDACC__)
+#define COOP_RING_STAGES 4
 struct CoopBlock {
     int tid, nt;
     double* red;              // >= 32 doubles of shared memory
     double* redv = nullptr;   // optional: >= 8 * 32 doubles for the fused reduction of up to 8 values (sumv)
+    double* ring = nullptr;   // optional: COOP_RING_STAGES stages of ring_rows x G doubles for `bilinear`
+    int ring_rows = 0;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
@@ -70,6 +80,67 @@ struct CoopBlock {
         return t;
     }
     __device__ __forceinline__ int any(int v) const { return __syncthreads_or(v); }
+    // part[k] += sum_{y0 <= y <= y1} sum_{x0 <= x <= x1} wy[k*G + y] * A[y*G + x] * wx[k*G + x],  k < n <= 6 (per-thread
+    // partial sums).  A streams from L2 / HBM: the sweep is bound by the bytes in flight, so whole rows are copied
+    // asynchronously (cp.async, 16 bytes per thread and piece) into a ring of shared-memory stages, COOP_RING_STAGES - 1
+    // stages ahead of the one being consumed; a warp then takes one row of the stage, its lanes stride over x.
+    __device__ __forceinline__ void bilinear(const double* __restrict__ A, int G, int y0, int y1, int x0, int x1,
+                                             const double* wx, const double* wy, int n, double* part) const {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        if (!ring || (G & 1) || y1 < y0) {  // plain path: rows dealt to warps, four loads in flight per lane
+            for (int y = y0 + wid; y <= y1; y += nw) {
+                const double* row = A + (size_t)y * G;
+                for (int xb = x0 + lane; xb <= x1; xb += 128) {
+                    double v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = xb + 32 * j <= x1 ? row[xb + 32 * j] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (xb + 32 * j <= x1)
+                            for (int k = 0; k < n; k++) part[k] += (wy[k * G + y] * v[j]) * wx[k * G + xb + 32 * j];
+                }
+            }
+            return;
+        }
+        const int R = ring_rows, S = COOP_RING_STAGES;
+        const int nchunk = (y1 - y0 + R) / R;
+        auto issue = [&](int c) {
+            if (c < nchunk) {
+                const int ya = y0 + c * R;
+                const int rows = (y1 - ya + 1) < R ? (y1 - ya + 1) : R;
+                const char* src = reinterpret_cast<const char*>(A + (size_t)ya * G);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (size_t)(c % S) * R * G);
+                const int n16 = rows * (G >> 1);
+                for (int i = tid; i < n16; i += nt)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src + 16 * (size_t)i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, empty past the end
+        };
+        for (int c = 0; c < S - 1; c++) issue(c);
+        for (int c = 0; c < nchunk; c++) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(COOP_RING_STAGES - 2) : "memory");  // this thread's pieces of chunk c
+            __syncthreads();  // everybody's pieces of chunk c have landed, and everybody is done with chunk c - 1 ...
+            issue(c + S - 1);  // ... whose stage is refilled now, S - 1 chunks ahead
+            const int ya = y0 + c * R;
+            const int rows = (y1 - ya + 1) < R ? (y1 - ya + 1) : R;
+            const double* st = ring + (size_t)(c % S) * R * G;
+            for (int rr = wid; rr < rows; rr += nw) {
+                const int y = ya + rr;
+                double wyk[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) wyk[k] = k < n ? wy[k * G + y] : 0.0;
+                const double* row = st + (size_t)rr * G;
+                for (int x = x0 + lane; x <= x1; x += 32) {
+                    const double v = row[x];
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                        if (k < n) part[k] += (wyk[k] * v) * wx[k * G + x];
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // the ring is idle before the caller reuses shared memory
+    }
     // sums of n <= 8 values at once (same order as `sum`): two barriers instead of 2 n
     __device__ __forceinline__ void sumv(double* v, int n) const {
         if (!redv) {

@@ -929,8 +929,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (ctx->bytes2d_res.ensure((size_t)n * sizeof(gdk_result2d))) return gdk_fail(ctx, GDK_ERR_NOMEM, "result buffer");
     gdk_result2d* dres = reinterpret_cast<gdk_result2d*>(ctx->bytes2d_res.p);
     {
-        const size_t smem = std::max<size_t>((size_t)2 * PSI_MAXE * std::max(Gmax_opt, 8) * 8, 1024);
+        const int Gm = std::max(Gmax_opt, 8);
+        size_t smem = std::max<size_t>((size_t)2 * PSI_MAXE * Gm * 8, 1024);
         if (smem > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "optimiser grid too large");
+        // row ring of the a2 sweeps: stages of about 16 KB, as long as two CTAs still fit an SM
+        int ring_rows = std::max(1, std::min(8, 2048 / Gm));
+        if (smem + (size_t)COOP_RING_STAGES * ring_rows * Gm * 8 > (size_t)100 << 10) ring_rows = 0;
+        smem += (size_t)COOP_RING_STAGES * ring_rows * Gm * 8;
         CK2(cudaFuncSetAttribute(k_bw2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 << 10)));
         PhaseTimer pt;
         pt.begin(ctx, GDK_PH_BW2D);
@@ -939,7 +944,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             for (int i = 0; i < n; i++)
                 if (bjobs[i].a2) abytes += (double)bjobs[i].G * bjobs[i].G * 8.0 * (bjobs[i].aFFT ? 2 : 1);
             KernelTimer kt(ctx, GDK_K_BW2D, abytes, 0);
-            k_bw2d<<<n, ctx->bw2d_threads, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres);
+            k_bw2d<<<n, ctx->bw2d_threads, smem, ctx->stream>>>(dspecs, dbj, dgeom, ctx->k2d, dres, Gm, ring_rows);
         }
         ctx->launches++;
         pt.end();

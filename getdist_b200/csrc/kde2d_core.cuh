@@ -96,29 +96,7 @@ GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W
     co.sync();
     double part[PSI_MAXE];
     for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
-    // rows are dealt to groups of L threads (a warp on the device); within a row the L threads stride over x with
-    // coalesced loads of a2.  The row weights wy_k[y] are uniform over the group and hoisted out of the x loop.
-    const int L = co.nt >= 32 ? 32 : co.nt;
-    const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
-    for (int y = 1 + grp; y <= ycut; y += ngrp) {
-        double wyk[PSI_MAXE];
-        for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
-        const double* row = W.a2 + (size_t)y * G;
-        for (int x0 = 1 + lane; x0 <= xcut; x0 += 4 * L) {
-            double v[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = x0 + j * L;
-                v[j] = x <= xcut ? row[x] : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = x0 + j * L;
-                if (x <= xcut)
-                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + x];
-            }
-        }
-    }
+    co.bilinear(W.a2, G, 1, ycut, 1, xcut, W.wx, W.wy, n, part);
     co.sumv(part, n);
     for (int k = 0; k < n; k++) {
         const int ss = e[k].s0 + e[k].s1;
@@ -131,56 +109,17 @@ GDK_HD void psi_even_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W
 template <class C>
 GDK_HD void psi_odd_level(const C& co, const Kde2dConsts& K, const Kde2dWork& W, const PsiEntry* e, int n, double* out) {
     const int G = W.G;
-    for (int q = co.tid; q < 2 * n; q += co.nt) {
-        const int k = q >> 1;
-        W.cut[q] = psi_cut(4 * K.pi2 * e[k].time, (double)((q & 1) ? e[k].s1 : e[k].s0), G / 2);
-    }
-    co.sync();
-    int xcut = 1, ycut = 1;
-    for (int k = 0; k < n; k++) {
-        xcut = W.cut[2 * k] > xcut ? W.cut[2 * k] : xcut;
-        ycut = W.cut[2 * k + 1] > ycut ? W.cut[2 * k + 1] : ycut;
-    }
-    // frequencies |f| <= cut: indices [0, cut] and [G - cut, G - 1] (everything when the two bands meet)
-    const int nx = (2 * xcut + 1 < G) ? 2 * xcut + 1 : G, ny = (2 * ycut + 1 < G) ? 2 * ycut + 1 : G;
-    {
-        const int fc = xcut > ycut ? xcut : ycut;
-        const int nf = (2 * fc + 1 < G) ? 2 * fc + 1 : G;
-        for (int it = co.tid; it < n * nf; it += co.nt) {
-            const int k = it / nf, ii = it - k * nf;
-            const int i = (nf == G || ii <= fc) ? ii : G - (nf - ii);
-            const double f = (i < (G + 1) / 2) ? (double)i : (double)(i - G);
-            const double w = exp(-(f * f) * (4 * K.pi2 * e[k].time));
-            W.wx[k * G + i] = w * psi_ipow(f, e[k].s0);
-            W.wy[k * G + i] = w * psi_ipow(f, e[k].s1);
-        }
+    for (int it = co.tid; it < n * G; it += co.nt) {
+        const int k = it / G, i = it - k * G;
+        const double f = (i < (G + 1) / 2) ? (double)i : (double)(i - G);
+        const double w = exp(-(f * f) * (4 * K.pi2 * e[k].time));
+        W.wx[k * G + i] = w * psi_ipow(f, e[k].s0);
+        W.wy[k * G + i] = w * psi_ipow(f, e[k].s1);
     }
     co.sync();
     double part[PSI_MAXE];
     for (int k = 0; k < PSI_MAXE; k++) part[k] = 0;
-    const int L = co.nt >= 32 ? 32 : co.nt;
-    const int grp = co.tid / L, ngrp = co.nt / L, lane = co.tid - grp * L;
-    for (int yy = grp; yy < ny; yy += ngrp) {
-        const int y = (ny == G || yy <= ycut) ? yy : G - (ny - yy);
-        double wyk[PSI_MAXE];
-        for (int k = 0; k < PSI_MAXE; k++) wyk[k] = k < n ? W.wy[k * G + y] : 0.0;
-        const double* row = W.aFFT + (size_t)y * G;
-        for (int x0 = lane; x0 < nx; x0 += 4 * L) {
-            double v[4];
-            int xi[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int xx = x0 + j * L;
-                xi[j] = (nx == G || xx <= xcut) ? xx : G - (nx - xx);
-                v[j] = xx < nx ? row[xi[j]] : 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (x0 + j * L < nx)
-                    for (int k = 0; k < n; k++) part[k] += (wyk[k] * v[j]) * W.wx[k * G + xi[j]];
-            }
-        }
-    }
+    co.bilinear(W.aFFT, G, 0, G - 1, 0, G - 1, W.wx, W.wy, n, part);
     co.sumv(part, n);
     for (int k = 0; k < n; k++) out[k] = part[k] * K.twopipow[e[k].s0 + e[k].s1];
     co.sync();

@@ -510,16 +510,18 @@ struct Bw2dJob {
     int shear;    // index into ShearGeom or -1
 };
 
-// grid (npairs), 256 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8
+// grid (npairs), 256 threads, dynamic smem = 2 * PSI_MAXE * Gmax * 8 + the row ring (COOP_RING_STAGES * ring_rows * Gmax * 8)
 __global__ void __launch_bounds__(256, 2) k_bw2d(const gdk_spec2d* __restrict__ specs, const Bw2dJob* __restrict__ jobs,
-                                              const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res) {
+                                                 const ShearGeom* __restrict__ geom, Kde2dConsts K, gdk_result2d* __restrict__ res,
+                                                 int Gmax, int ring_rows) {
     extern __shared__ __align__(16) unsigned char bsm[];
     __shared__ double red[32], redv[8 * 32];
     __shared__ int cuts[2 * PSI_MAXE];
     __shared__ PsiEntry ebuf[PSI_MAXE];
     const gdk_spec2d sp = specs[blockIdx.x];
     const Bw2dJob jb = jobs[blockIdx.x];
-    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red, redv};
+    CoopBlock co{(int)threadIdx.x, (int)blockDim.x, red, redv,
+                 ring_rows > 0 ? reinterpret_cast<double*>(bsm) + (size_t)2 * PSI_MAXE * Gmax : nullptr, ring_rows};
     Bw2dOut o{0, 0, 0, NAN, 0u, 0, 0};
     double r2 = 0;
     if (sp.bw_mode == GDK_BW2D_PLAIN || sp.bw_mode == GDK_BW2D_SHEAR) {

@@ -1505,7 +1505,16 @@ class MCSamples:
             from .parallel import prefetch_triangle_group
 
             return prefetch_triangle_group(self, pg, idx, do_1d, do_2d)
+        import time as _time
+
+        t0 = _time.perf_counter()
         d1 = self._densities_1d(idx) if do_1d else []
+        t1 = _time.perf_counter()
         pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))]
         d2 = self._densities_2d(pairs) if (do_2d and pairs) else []
+        t2 = _time.perf_counter()
+        wl = self._ctx.wall_ms() if hasattr(self._ctx, "wall_ms") else {}
+        # host wall clock of the call: the 1D and 2D batches, of which the time inside the library's 2D call
+        self.last_prefetch_ms = dict(d1=(t1 - t0) * 1e3, d2=(t2 - t1) * 1e3, lib_2d=wl.get("call_2d"), lib_1d=wl.get("call_1d"),
+                                     lib_quantiles=wl.get("call_quantiles"))
         return d1, d2

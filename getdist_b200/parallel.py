@@ -136,13 +136,13 @@ class PeerGroup:
         """host array per rank (same shape and dtype everywhere) -> (world,) + shape on every rank"""
         import torch
 
-        arr = np.ascontiguousarray(arr)
+        arr = np.array(arr, copy=True)  # contiguous and writable (torch.from_numpy wants both)
         if self.world == 1:
             return arr[None]
-        t = torch.from_numpy(arr).to(self.device)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=self.device)
+        t = torch.from_numpy(arr.reshape(-1)).to(self.device)
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=self.device)
         self.dist.all_gather_into_tensor(out, t)
-        return out.cpu().numpy()
+        return out.cpu().numpy().reshape((self.world,) + arr.shape)
 
     def row_range(self, N):
         """rows this rank uploads itself: whole statistics blocks (GDK_ROW_BLOCK rows), dealt as evenly as they go"""

@@ -174,7 +174,41 @@ def case_likes():
                 mask_kwargs_2d=[{}, {"mult_bias_correction_order": 0, "fine_bins_2D": 128}])
 
 
+def _c1_inputs():
+    """C1 (BASELINE.json configs[0]): samples drawn by the REFERENCE's own mixture classes
+    (getdist.gaussian_mixtures, make_golden.py:make_c1_inputs) and stored as a fixture -- the reference is not importable
+    where the GPU tests run."""
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c1_inputs.npz"))
+
+
+def case_c1rand():
+    """RandomTestMixtureND(ndim=3, ncomponent=2, seed=10).MCSamples(100000, random_state=10), unit weights"""
+    z = _c1_inputs()
+    return dict(samples=np.ascontiguousarray(z["rand"]), weights=None, names=["x", "y", "z"], ranges={}, settings={},
+                pairs=[(0, 1), (0, 2), (1, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+def case_c1rand_w():
+    """the same samples with Exponential(1) weights (seed 11)"""
+    z = _c1_inputs()
+    return dict(samples=np.ascontiguousarray(z["rand"]), weights=np.ascontiguousarray(z["w"]), names=["x", "y", "z"], ranges={},
+                settings={}, pairs=[(0, 1), (0, 2), (1, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
+def case_c1wj():
+    """bimodal WJ1 mixture Mixture2D([[-1,0],[1,0]], [(2/3,2/3,0)]*2) (test_distributions.py:196-198) with a third
+    Gaussian dimension, 100000 samples, unit weights"""
+    z = _c1_inputs()
+    return dict(samples=np.ascontiguousarray(z["wj"]), weights=None, names=["x", "y", "z"], ranges={}, settings={},
+                pairs=[(0, 1), (0, 2), (1, 2)], kwargs_1d=[{}], kwargs_2d=[{}])
+
+
 CASES = {
+    "c1rand": case_c1rand,
+    "c1rand_w": case_c1rand_w,
+    "c1wj": case_c1wj,
     "mix3": case_mix3,
     "unit5": case_unit5,
     "bounded": case_bounded,

@@ -22,6 +22,20 @@ from getdist import MCSamples  # noqa: E402
 from cases import CASES, grid_stride, input_digest, kw_tag  # noqa: E402
 
 
+def make_c1_inputs():
+    """C1 samples from the reference's own generators -> c1_inputs.npz (cases.py:_c1_inputs)"""
+    from getdist.gaussian_mixtures import MixtureND, RandomTestMixtureND
+
+    names = ["x", "y", "z"]
+    rand = RandomTestMixtureND(ndim=3, ncomponent=2, seed=10, names=names).MCSamples(100000, random_state=10).samples
+    s = 2.0 / 3
+    cov = np.diag([s * s, s * s, 1.5 ** 2])
+    wj = MixtureND([[-1.0, 0.0, 0.5], [1.0, 0.0, 0.5]], [cov, cov], names=names).MCSamples(100000, random_state=10).samples
+    w = np.random.default_rng(11).exponential(1.0, 100000)
+    np.savez_compressed(os.path.join(HERE, "c1_inputs.npz"), rand=np.ascontiguousarray(rand), wj=np.ascontiguousarray(wj), w=w)
+    print("c1 inputs ok", rand.shape, wj.shape)
+
+
 def run_case(name):
     case = CASES[name]()
     out = {"digest": np.array(input_digest(case)), "getdist_version": np.array(getdist.__version__)}
@@ -185,8 +199,12 @@ def run_f4():
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES) + ["limits", "f4"]
+    if any(nm.startswith("c1") for nm in names) and not os.path.exists(os.path.join(HERE, "c1_inputs.npz")):
+        make_c1_inputs()
     for nm in names:
-        if nm == "limits":
+        if nm == "c1_inputs":
+            make_c1_inputs()
+        elif nm == "limits":
             run_limits()
         elif nm == "f4":
             run_f4()

@@ -1,0 +1,146 @@
+"""The multi-GPU product path (getdist_b200.parallel.prefetch_triangle_group behind MCSamples(process_group=...)) on the
+CPU: a world_size-2 gloo group, the library context replaced by a TEST DOUBLE whose "windows" are POSIX shared-memory
+segments (the stand-in of CUDA IPC peer memory) and whose batch calls write a recognisable pattern into every rank's
+window, as the library's peer stores do.  Checks the host logic of the path: window mapping through the rendezvous,
+the gathered layouts (1D rows per rank, 2D grids in the caller's pair order), the result-record exchange, the quantile
+exchange, and that every rank ends up with every density in the caller's order."""
+import os
+import socket
+from multiprocessing import shared_memory
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from test_host_mirror_cpu import FakeContext
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def f1(j):
+    return 0.25 + 0.001 * j
+
+
+def f2(a, b):
+    return 0.5 + 0.001 * a + 0.000001 * b
+
+
+class WinContext(FakeContext):
+    """numpy stand-in with windows: addresses are offsets into per-window shared-memory segments"""
+
+    BASE = 1 << 44
+
+    def __init__(self, device=0):
+        super().__init__(device)
+        self.own, self.peer = {}, {}
+        self.rank, self.world = 0, 1
+
+    def set_samples(self, X, w=None, chain_offsets=None, group=None):
+        self.group_seen = group
+        super().set_samples(X, w, chain_offsets)
+
+    def peer_init(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def window_export(self, window, nbytes):
+        seg = shared_memory.SharedMemory(create=True, size=int(nbytes))
+        self.own[window] = seg
+        self.peer[window] = {}
+        return self.BASE * (window + 1), seg.name.encode().ljust(64, b"\0")
+
+    def window_import(self, window, peer, handle):
+        self.peer[window][peer] = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
+
+    def _views(self, window):
+        segs = [self.own[window]] + list(self.peer[window].values())
+        return [np.ndarray((s.size // 8,), dtype=np.float64, buffer=s.buf) for s in segs]
+
+    def window_read(self, window, offset, out):
+        v = np.ndarray((self.own[window].size // 8,), dtype=np.float64, buffer=self.own[window].buf)
+        out.reshape(-1)[:] = v[offset // 8: offset // 8 + out.size]
+        return out
+
+    def density1d_batch(self, specs, out=None, device_ptr=None, likes=False, stride=None, peers=False):
+        from getdist_b200 import _abi
+
+        assert peers and device_ptr is not None
+        off = (device_ptr - self.BASE * (_abi.GDK_WIN_G1 + 1)) // 8
+        res = []
+        for i, s in enumerate(specs):
+            for v in self._views(_abi.GDK_WIN_G1):
+                v[off + i * stride: off + i * stride + s.fine_bins] = f1(s.param)
+            r = _abi.Result1D()
+            r.kde_h, r.status, r.winw = 0.1 * (s.param + 1), 0, s.param
+            res.append(r)
+        return None, res
+
+    def density2d_batch(self, specs, out=None, device_ptr=None, likes=False, offsets=None, peers=False):
+        from getdist_b200 import _abi
+
+        assert peers and device_ptr == self.BASE * (_abi.GDK_WIN_G2 + 1)
+        res = []
+        for sp, off in zip(specs, offsets):
+            G = int(sp["fine_bins"])
+            for v in self._views(_abi.GDK_WIN_G2):
+                v[off: off + G * G] = f2(int(sp["px"]), int(sp["py"]))
+            r = _abi.Result2D()
+            r.hx, r.status, r.winw = 1.0 + int(sp["px"]), 0, int(sp["py"])
+            for k in range(int(sp["n_contours"])):
+                r.levels[k] = 100 * int(sp["px"]) + int(sp["py"]) + 0.1 * k
+            res.append(r)
+        return None, np.asarray(offsets), res
+
+    def close(self):
+        for seg in self.own.values():
+            seg.close()
+            seg.unlink()
+
+
+def _worker(rank, world, port, P, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from getdist_b200 import MCSamples, _abi
+    from getdist_b200.parallel import PeerGroup
+
+    _abi.Context = WinContext
+    rng = np.random.default_rng(5)
+    N = 4000
+    X = rng.standard_normal((N, P)) * np.arange(1, P + 1) + 10.0
+    w = rng.exponential(1.0, N)
+    pg = PeerGroup(dist, rank, world, device="cpu")
+    r0, r1 = pg.row_range(10_000_000)
+    mc = MCSamples(samples=X, weights=w, names=["p%d" % i for i in range(P)], sampler="uncorrelated",
+                   settings={"fine_bins": 64, "fine_bins_2D": 16}, process_group=pg)
+    d1, d2 = mc.prefetch_triangle()
+    idx, pairs = mc.triangle_pairs()
+    ok = pg.transport == "p2p" and mc._ctx.group_seen is pg
+    ok = ok and len(d1) == P and len(d2) == len(pairs)
+    ok = ok and all(np.all(d.P == f1(j)) and d._gdk["winw"] == j for d, j in zip(d1, idx))
+    ok = ok and all(np.all(d.P == f2(a, b)) and d._gdk["winw"] == b and d._gdk["hx"] == 1.0 + a
+                    and d._gdk["levels"][1][0] == 100 * a + b for d, (a, b) in zip(d2, pairs))
+    # the ranges came through the quantile exchange: identical on both ranks (checked by the parent)
+    ret[rank] = (bool(ok), [mc.paramNames.names[j].range_min for j in idx], (r0, r1))
+    dist.barrier()
+    mc._ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [5, 8])
+def test_group_prefetch_world2(P):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), P, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][1] == ret[1][1]
+    # row blocks: whole statistics blocks, contiguous, covering [0, N)
+    (a0, a1), (b0, b1) = ret[0][2], ret[1][2]
+    assert a0 == 0 and a1 == b0 and b1 == 10_000_000 and a1 % 131072 == 0
