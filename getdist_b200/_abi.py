@@ -67,6 +67,21 @@ class Result2D(C.Structure):
                 ("pad", C.c_int32), ("levels", C.c_double * 4)]
 
 
+RES2D_DTYPE = np.dtype([("hx", "f8"), ("hy", "f8"), ("c", "f8"), ("rx", "f8"), ("ry", "f8"), ("t_star", "f8"), ("winw", "i4"),
+                        ("status", "u4"), ("n_brent", "i4"), ("pad", "i4"), ("levels", "f8", (4,))])
+assert RES2D_DTYPE.itemsize == C.sizeof(Result2D)
+
+
+def results2d_columns(res):
+    """{field: list} of a batch of Result2D records (a ctypes array from the library, or any sequence of records)"""
+    if isinstance(res, C.Array):
+        a = np.frombuffer(res, dtype=RES2D_DTYPE)
+        return {k: a[k].tolist() for k in RES2D_DTYPE.names if k != "pad"}
+    cols = {k: [getattr(r, k) for r in res] for k in RES2D_DTYPE.names if k not in ("pad", "levels")}
+    cols["levels"] = [list(r.levels) for r in res]
+    return cols
+
+
 class LagJob(C.Structure):
     _fields_ = [("param", C.c_int32), ("mode", C.c_int32), ("k0", C.c_int64), ("nk", C.c_int32), ("pad", C.c_int32),
                 ("mean", C.c_double), ("inv4s2", C.c_double)]
@@ -381,7 +396,7 @@ class Context:
             out = result_buffer(total)
         self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets),
                                               C.cast(res, C.c_void_p), 0), "gdk_density2d_batch")
-        return out, offsets, list(res)
+        return out, offsets, res  # the ctypes array of records (indexable like a list; _finish_2d reads it column-wise)
 
     def bandwidth2d_batch(self, specs):
         """bandwidth stage only (GDK_BW_ONLY): results with rx, ry, c, winw, status; no grids"""

@@ -152,6 +152,33 @@ class _SpecView:
         return v.item() if hasattr(v, "item") and np.ndim(v) == 0 else v
 
 
+class _BatchRecord:
+    """The library's result record of one density of a batch (bandwidths, status bits, contour levels ...), read like a
+    dict: `d._gdk["status"]`.  The columns of the whole batch are shared; nothing is copied per density."""
+
+    __slots__ = ("_cols", "_n", "_conts")
+
+    def __init__(self, cols, n, conts):
+        self._cols, self._n, self._conts = cols, n, conts
+
+    def __getitem__(self, key):
+        if key == "levels":
+            return (self._conts, self._cols["levels"][self._n][: len(self._conts)]) if self._conts else None
+        return self._cols[key][self._n]
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return key == "levels" or key in self._cols
+
+    def keys(self):
+        return [k for k in self._cols] + ["levels"]
+
+
 class ParamConfidenceData:
     """Handle standing in for chains.ParamConfidenceData: the device resolves order statistics directly, so
     the handle only remembers what it refers to: a stored column (index) with an optional row range, or an
@@ -1202,14 +1229,23 @@ class MCSamples:
         buf[offsets[i]:][:G*G]"""
         out = []
         names = self.paramNames.names
-        # plain Python scalars of the spec columns once per batch (a field access per pair costs microseconds)
+        # plain Python scalars of the spec and result columns once per batch (a field access per pair costs microseconds)
         col = {k: specs[k].tolist() for k in ("fine_bins", "xbinmin", "xbinmax", "ybinmin", "ybinmax", "bw_mode")}
+        rcol = _abi.results2d_columns(res)
+        rcol["bw_mode"], rcol["fine_bins"] = col["bw_mode"], col["fine_bins"]
         offsets = [int(o) for o in offsets]
         bad = _abi.ST_BIAS_NEG | _abi.ST_BW_FALLBACK | _abi.ST_SMALL_SMOOTH | _abi.ST_ZERO_MAX
-        nc = len(conts)
-        for n, ((j, j2), off, r) in enumerate(zip(pairs, offsets, res)):
+        conts = list(conts)
+        G0 = col["fine_bins"][0] if len(pairs) else 0
+        grids = None
+        if cache:
+            buf.flags.writeable = False  # cache entries are read-only views into the batch buffer, see below
+        if len(pairs) and all(g == G0 for g in col["fine_bins"]) and offsets == list(range(offsets[0], offsets[0] + len(pairs) * G0 * G0, G0 * G0)):
+            grids = buf[offsets[0]: offsets[0] + len(pairs) * G0 * G0].reshape(len(pairs), G0, G0)  # one view, indexed per pair
+        status_col = rcol["status"]
+        for n, (j, j2) in enumerate(pairs):
             parx, pary = names[j], names[j2]
-            status = r.status
+            status = status_col[n]
             if status & bad:
                 if status & _abi.ST_BIAS_NEG:
                     raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
@@ -1223,23 +1259,21 @@ class MCSamples:
                 if status & _abi.ST_ZERO_MAX:
                     raise DensitiesError("no samples in bin")
             G = col["fine_bins"][n]
+            off = offsets[n]
             d = Density2D.on_linspace((col["xbinmin"][n], col["xbinmax"][n], G), (col["ybinmin"][n], col["ybinmax"][n], G),
-                                      buf[off: off + G * G].reshape(G, G),
+                                      grids[n] if grids is not None else buf[off: off + G * G].reshape(G, G),
                                       [(parx.range_min, parx.range_max), (pary.range_min, pary.range_max)])
             if masks is not None:  # bool_mask, mcsamples.py:1917, 1986
                 w = len(masks[n]) - G
                 w //= 2
                 d.mask = np.asarray(masks[n][w: w + G, w: w + G] < 1e-8)
-            d._gdk = dict(hx=r.hx, hy=r.hy, c=r.c, rx=r.rx, ry=r.ry, winw=r.winw, status=status, t_star=r.t_star,
-                          n_brent=r.n_brent, bw_mode=col["bw_mode"][n], fine_bins=G,
-                          levels=(conts, r.levels[:nc]) if nc else None)
+            d._gdk = _BatchRecord(rcol, n, conts)
             if lbuf is not None:
                 d._likes2d = lbuf[off: off + G * G].reshape(G, G)
             if cache:
                 # the cache entry is a READ-ONLY view into the batch buffer (no second copy of a gigabyte of grids);
                 # get2DDensity / get2DDensityGridData hand out private copies of it (_cached_2d), as the reference
                 # returns a fresh grid per call and callers normalise in place
-                d.P.flags.writeable = False
                 self._density2D[(j, j2)] = d
             out.append(d)
         return out

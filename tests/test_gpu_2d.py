@@ -74,8 +74,9 @@ def test_density_2d(gpu_objs, name):
             amise = bool(info["status"] & AMISE_BITS)
             if not np.isnan(h[0]):
                 # bandwidths handed back by getAutoBandwidth2D: SURVEY s8c staged tolerance 5e-5, except where the
-                # reference's TNC step decided the value (chaotic at ~1e-4, DESIGN.md "TNC")
-                rtol = 3e-4 if amise else 5e-5
+                # reference's TNC step decided the value: TNC stops on finite-difference gradients within a few 1e-4 of
+                # the minimiser (3.5e-4 on c1rand_w (1, 2), where the grids still agree to 1e-5; DESIGN.md "TNC")
+                rtol = 5e-4 if amise else 5e-5
                 np.testing.assert_allclose([info["hx"], info["hy"]], h[:2], rtol=rtol, err_msg=str((name, tag, jx, jy)))
                 np.testing.assert_allclose(info["c"], h[2], rtol=rtol, atol=1e-12)
             tol = 1e-5 if amise else 1e-6
