@@ -1055,15 +1055,21 @@ __global__ void __launch_bounds__(512) k_contours2d(const ConvJob* __restrict__ 
     double target[4];
     for (int c = 0; c < 4; c++) target[c] = c < nc ? (1 - jp->contours[c]) * norm : 0;
     const double scale = norm > 0 ? 2305843009213693952.0 / norm : 0.0;  // 2^61 / total
+    // first interval: the top 20 octaves below the maximum (contour levels of a density normalised to its maximum sit
+    // there); what lies below is summed per thread, not histogrammed -- the tails of the grid would otherwise pile
+    // onto a handful of exponent bins.  A contour whose level is lower still falls back to [0, klo0) afterwards.
+    __shared__ unsigned long long s_below0;
+    const unsigned long long klo0 = dbl_bits(vmax * 9.5367431640625e-07);  // vmax * 2^-20 (0 if vmax is tiny)
     if (threadIdx.x < 4) {
         const int c = threadIdx.x;
-        s_klo[c] = 0;
+        s_klo[c] = klo0;
         s_khi[c] = dbl_bits(vmax);
         s_below[c] = 0;
         const double tq = target[c] * scale;
         s_target[c] = tq >= 1.0 ? (unsigned long long)__double2ull_ru(tq) : 1ull;
-        s_shift[c] = q_shift_for(s_khi[c], CT_BITS);
+        s_shift[c] = q_shift_for(s_khi[c] - klo0, CT_BITS);
         s_done[c] = (c >= nc || s_khi[c] == 0) ? 1 : 0;
+        if (c == 0) s_below0 = 0;
     }
     __syncthreads();
     for (int pass = 0; pass < 8; pass++) {
@@ -1081,14 +1087,19 @@ __global__ void __launch_bounds__(512) k_contours2d(const ConvJob* __restrict__ 
             live[c] = c < nc && !s_done[c];
         }
         __syncthreads();
+        unsigned long long qbelow = 0;
         for (int i = co.tid; i < n; i += co.nt) {
             const double v = P[i];
             const unsigned long long kb = dbl_bits(v);
             const unsigned long long q = __double2ull_rn(v * edge_factor(i / G, i % G, G) * scale);
             if (q == 0) continue;
             if (shared_hist) {
-                const unsigned bin = (unsigned)(kb >> shift[0]);
-                smem_add_u64(ct_hist + bin, ct_hist + CT_NB + bin, q);
+                if (kb < klo0) {
+                    qbelow += q;
+                } else {
+                    const unsigned bin = (unsigned)((kb - klo0) >> shift[0]);
+                    smem_add_u64(ct_hist + bin, ct_hist + CT_NB + bin, q);
+                }
             } else {
 #pragma unroll
                 for (int c = 0; c < 4; c++)
@@ -1098,10 +1109,23 @@ __global__ void __launch_bounds__(512) k_contours2d(const ConvJob* __restrict__ 
                     }
             }
         }
+        if (shared_hist) {
+            qbelow = warp_sum_u64(qbelow);
+            if ((threadIdx.x & 31) == 0 && qbelow) atomicAdd(&s_below0, qbelow);
+        }
         __syncthreads();
         // warp c scans the histogram of contour c: lane l owns bins [64 l, 64 l + 64)
         const int wc = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (wc < nc && live[wc]) {
+        if (shared_hist && wc < nc && live[wc] && s_target[wc] <= s_below0) {
+            // the level lies below the first interval: continue on [0, klo0) with the contour's own histogram
+            if (lane == 0) {
+                s_klo[wc] = 0;
+                s_khi[wc] = klo0 - 1;
+                s_shift[wc] = q_shift_for(klo0 - 1, CT_BITS);
+            }
+        } else if (wc < nc && live[wc]) {
+            if (shared_hist && lane == 0) s_below[wc] = s_below0;
+            __syncwarp();
             const unsigned* hl = ct_hist + (shared_hist ? 0 : wc * 2 * CT_NB);
             const unsigned* hh = hl + CT_NB;
             const int per = CT_NB / 32;

@@ -158,7 +158,8 @@ def _pair_inputs(o, jx, jy, G=256):
 
 
 @pytest.mark.parametrize("name,jx,jy,G", [("mix3", 0, 1, 256), ("unit5", 1, 2, 256), ("unit5", 0, 4, 256),
-                                         ("bounded", 0, 1, 256), ("bounded", 0, 2, 100), ("unit5", 3, 2, 128)])
+                                         ("bounded", 0, 1, 256), ("bounded", 0, 2, 100), ("unit5", 3, 2, 128),
+                                         ("c1rand_w", 1, 2, 256)])
 def test_bw2d_core_vs_oracle(hs, name, jx, jy, G):
     """2D transforms + KernelOptimizer2D restatement (plain branch) against the oracle's optimiser."""
     from oracle.getdist_oracle import BandwidthOptimizer2D
@@ -188,9 +189,13 @@ def test_bw2d_core_vs_oracle(hs, name, jx, jy, G):
     np.testing.assert_allclose(ref.h_closed, ref.h_closed)
     # closed-form part is tight; where the reference's TNC result is accepted, h scatters by ~1e-4
     tnc = (c != 0) or (abs(hx - ref.h_closed[0]) > 0)
-    rtol = 3e-4 if tnc else 1e-9
+    rtol = 5e-4 if tnc else 1e-9
     np.testing.assert_allclose(out[:2], [hx, hy], rtol=rtol)
     np.testing.assert_allclose(out[2], c, rtol=1e-12, atol=1e-15)
+    if tnc and c != 0:
+        # where the reference's TNC decides the widths it stops (on finite-difference gradients) short of the minimum of
+        # the AMISE; the safeguarded Newton iteration of the device code ends at or below the reference's value
+        assert ref.amise(np.array([out[0], out[1]]), c) <= ref.amise(np.array([hx, hy]), c) * (1 + 1e-12)
 
 
 def test_contour_levels_core(hs):
