@@ -86,7 +86,10 @@ def gen_c2(N, P, out_X=None, out_w=None, rho=0.85, seed=1234):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md): NVML queries
+    from a thread of this process every 50 ms.  (A polling `nvidia-smi -lms` child was measured to stall kernel launches
+    for tens of milliseconds per poll on some boxes and inflated single steps by up to 2x; it remains the fallback when
+    the NVML bindings are missing.)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -96,16 +99,43 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []  # (sm_mhz, max_mhz, reason bits)
+        self.nvml = None
+        self.first = 0
+        self._stop = False
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.samples.append((mhz, self.max_mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -113,9 +143,19 @@ class ClockSampler:
 
     def mark(self):
         """start of the timed region: only samples from here on are reported"""
-        self.first = len(self.lines)
+        self.first = len(self.samples) if self.nvml else len(self.lines)
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml:
+            self._stop = True
+            nv = self.nvml
+            masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            sel = self.samples[self.first:]
+            reasons = sorted({nm for (_, _, bits) in sel for nm, m in zip(names, masks) if bits & m})
+            return {"sm_mhz": float(np.median([x[0] for x in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(sel), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -124,8 +164,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines[getattr(self, "first", 0):]:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -138,7 +177,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------

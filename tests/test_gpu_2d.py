@@ -117,7 +117,7 @@ def test_contour_levels(gpu_objs, name):
         d = mc.get2DDensityGridData(jx, jy, num_plot_contours=3)
         ref = g["d2/default/%d_%d/contours" % (jx, jy)]
         amise = bool(d._gdk["status"] & AMISE_BITS)
-        np.testing.assert_allclose(d.contours, ref, rtol=1e-4 if amise else 1e-7, atol=1e-12)
+        np.testing.assert_allclose(d.contours, ref, rtol=5e-4 if amise else 1e-7, atol=1e-12)  # amise: see test_density_2d
         np.testing.assert_allclose(d.contours, getContourLevels(d.P, mc.contours[:3]), rtol=1e-9, atol=1e-14)
         assert d.likes is None
 
