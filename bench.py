@@ -431,7 +431,7 @@ def run_ours(args):
             mc._densities_1d(idx, _device_ptr=d1.data_ptr())
             ph = mc._ctx.phase_ms()
             phases["hist1d"], phases["kde1d"], phases["quantiles"] = ph["hist1d"], ph["kde1d"], ph["quantiles"]
-            mc._densities_2d(pairs, _device_ptr=d2.data_ptr(), _contours=[])
+            mc._densities_2d(pairs, _device_ptr=d2.data_ptr())  # with the contour levels, as the public call
             ph = mc._ctx.phase_ms()
             for k in ("hist2d", "shear", "xform2d", "bw2d", "conv2d"):
                 phases[k] = ph[k]
@@ -521,16 +521,18 @@ def run_ours(args):
             m.updateBaseStatistics()    # H2D upload of the pinned host arrays; the fused moments ride behind the chunks
         t1 = time.perf_counter()
         e2e_parts["upload_ms_events"] = m._ctx.phase_ms()["upload"]
-        a, b = m.prefetch_triangle()
+        a, b = m.prefetch_triangle() if world == 1 else m.prefetch_triangle(root=0)  # N ranks: the grids end on rank 0's host
         t2 = time.perf_counter()
-        s = float(a[0].P[F // 2]) + float(b[0].P[b[0].P.shape[0] // 2, b[0].P.shape[1] // 2])
+        s = float(a[0].P[F // 2]) + float(b[0].P[b[0].P.shape[0] // 2, b[0].P.shape[1] // 2]) if a else 0.0
         e2e_parts.update(upload_and_moments_s=t1 - t0, prefetch_triangle_s=t2 - t1)
+        e2e_parts["phases_ms"] = {k: round(v, 2) for k, v in m._ctx.phase_ms().items() if v and v > 0}
         if getattr(m, "last_prefetch_ms", None):
             e2e_parts["prefetch_ms"] = {k: (round(v, 2) if v is not None else None) for k, v in m.last_prefetch_ms.items()}
         if world > 1:
-            e2e_parts["group"] = dict(pg.timings)
+            e2e_parts["group"] = {k: round(v, 2) for k, v in pg.timings.items()}
+            e2e_parts["upload_group"] = {k: round(v, 2) for k, v in getattr(pg, "upload_timings", {}).items()}
         holder["d"] = (a, b)
-        return s, len(a) + len(b)
+        return s, ndens_total
 
     if world > 1:
         dist.barrier()
@@ -571,7 +573,7 @@ def run_ours(args):
     rows_mine = N if world == 1 or not pg.p2p else (pg.row_range(N)[1] - pg.row_range(N)[0])
     h2d = rows_mine * P * 8 + N * 8
     d2h = None
-    if "d" in holder:
+    if "d" in holder and rank == 0:
         d2h = int(sum(d.P.size for d in holder["d"][0]) + sum(d.P.size for d in holder["d"][1])) * 8
 
     # ---------------- multi-GPU: the gathered grids against a single-GPU computation (rank 0) ----------------
@@ -730,7 +732,8 @@ def run_ours(args):
                 "s_per_step": e2e_s, "checksum": checksum, "parts": e2e_parts,
                 "path": "MCSamples.setSamples(pinned host) + updateBaseStatistics() [H2D, fused moments behind the chunks] -> "
                         "prefetch_triangle() [quantiles, 1D + 2D batches with contour levels] -> host grids (pooled pinned buffers)",
-                "bytes_are": "per rank" if world > 1 else "total", "diagnostic_call": e2e_diag},
+                "bytes_are": ("h2d: rank 0's row block + all weights (every rank uploads its own block); d2h: all grids, to rank 0's "
+                              "host (prefetch_triangle(root=0))") if world > 1 else "total", "diagnostic_call": e2e_diag},
         "gpu_launches": int(launches), "phases_ms": {k: round(v, 3) for k, v in phases.items()}, "step_ms": [round(x, 3) for x in step_ms],
         "host_ms": host_log[-len(step_ms):], "group_ms": group_timings[-1] if group_timings else None,
         "clocks": clk, "roofline": roof, "measured_peaks": measured, "kernels": kernels, "hist1d": hist1d, "stats_pass": stats_pass,

@@ -136,6 +136,8 @@ def load():
     lib.gdk_moments_recompute.restype = i32
     lib.gdk_peer_init.argtypes = [vp, i32, i32]
     lib.gdk_peer_init.restype = i32
+    lib.gdk_peer_targets.argtypes = [vp, u32]
+    lib.gdk_peer_targets.restype = i32
     lib.gdk_window_export.argtypes = [vp, i32, u64, vp, vp]
     lib.gdk_window_export.restype = i32
     lib.gdk_window_import.argtypes = [vp, i32, i32, vp]
@@ -236,6 +238,9 @@ class Context:
         else:
             # sharded upload: this rank copies its row block over PCIe and stores it into every peer's column store over
             # NVLink; the peers do the same with theirs (include/gdk.h, "multi-GPU")
+            import time as _t
+
+            t0 = _t.perf_counter()
             self.peer_init(group.rank, group.world)
             self._ck(self.lib.gdk_samples_prepare(self.h, N, P, _ptr(co), nch), "gdk_samples_prepare")
             ld = (N + 63) & ~63
@@ -243,10 +248,17 @@ class Context:
             group.map_window(self, GDK_WIN_X, ld * P * 8)
             group.map_window(self, GDK_WIN_STATS, nblk * (3 * P + 1 + P * P) * 8)
             r0, r1 = group.row_range(N)
+            t1 = _t.perf_counter()
             group.barrier()  # nobody is still reading the previous contents of the stores
+            t2 = _t.perf_counter()
             self._ck(self.lib.gdk_samples_upload(self.h, _ptr(X), rs, cs, _ptr(w), r0, r1), "gdk_samples_upload")
+            t3 = _t.perf_counter()
             group.barrier()  # every rank's rows and statistics records have landed
+            t4 = _t.perf_counter()
             self._ck(self.lib.gdk_samples_finish(self.h), "gdk_samples_finish")
+            t5 = _t.perf_counter()
+            group.upload_timings = dict(prepare_map_ms=(t1 - t0) * 1e3, barrier1_ms=(t2 - t1) * 1e3, upload_ms=(t3 - t2) * 1e3,
+                                        barrier2_ms=(t4 - t3) * 1e3, finish_ms=(t5 - t4) * 1e3)
         self.N, self.P, self.nchains = N, P, max(nch, 1)
 
     @staticmethod
@@ -261,6 +273,9 @@ class Context:
     # -- multi-GPU windows (include/gdk.h) ------------------------------------------------------------------------
     def peer_init(self, rank, nranks):
         self._ck(self.lib.gdk_peer_init(self.h, rank, nranks), "gdk_peer_init")
+
+    def peer_targets(self, mask):
+        self._ck(self.lib.gdk_peer_targets(self.h, int(mask) & 0xFFFFFFFF), "gdk_peer_targets")
 
     def window_export(self, window, nbytes):
         """(device address, 64-byte IPC handle) of a window of at least nbytes"""

@@ -352,6 +352,12 @@ extern "C" int32_t gdk_peer_init(gdk_ctx* ctx, int32_t rank, int32_t nranks) {
     return GDK_OK;
 }
 
+extern "C" int32_t gdk_peer_targets(gdk_ctx* ctx, uint32_t rank_mask) {
+    if (!ctx) return GDK_ERR_ARG;
+    ctx->push_mask = rank_mask;
+    return GDK_OK;
+}
+
 static int window_buffer(gdk_ctx* ctx, int window, uint64_t bytes, void** ptr) {
     switch (window) {
         case GDK_WIN_G1:
@@ -423,6 +429,7 @@ extern "C" int32_t gdk_samples_prepare(gdk_ctx* ctx, int64_t N, int32_t P, const
     CK(cudaSetDevice(ctx->device));
     ctx->have_moments = false;
     ctx->have_loglikes = false;
+    if (ctx->N != N || ctx->P != P) ctx->mem_free = 0;  // a different store: ask the driver again
     ctx->N = N;
     ctx->P = P;
     ctx->ld = (N + 63) & ~int64_t(63);
@@ -1226,7 +1233,7 @@ extern "C" int32_t gdk_density1d_likes_batch(gdk_ctx* ctx, int32_t n, const gdk_
     if (peers_out) {  // this rank's rows of the gathered 1D window into every peer's copy (NVLink, copy engine)
         const size_t off = (size_t)(P_out - ctx->win[GDK_WIN_G1].p);
         for (int p = 0; p < ctx->nranks; p++) {
-            if (p == ctx->rank) continue;
+            if (p == ctx->rank || !((ctx->push_mask >> p) & 1u)) continue;
             double* pw = (double*)ctx->peer_ptr[GDK_WIN_G1][p];
             if (!pw) return gdk_fail(ctx, GDK_ERR_STATE, "result window of peer %d is not mapped", p);
             CK(cudaMemcpyAsync(pw + off, P_out, (size_t)n * stride * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -56,7 +56,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (peers_out) {
         if (P_out != ctx->win[GDK_WIN_G2].p || likes) return gdk_fail(ctx, GDK_ERR_ARG, "GDK_OUT_PEERS: P_out must be the GDK_WIN_G2 window");
         for (int p = 0; p < ctx->nranks; p++) {
-            if (p == ctx->rank) continue;
+            if (p == ctx->rank || !((ctx->push_mask >> p) & 1u)) continue;
             if (!ctx->peer_ptr[GDK_WIN_G2][p]) return gdk_fail(ctx, GDK_ERR_STATE, "result window of peer %d is not mapped", p);
             ptab.base[ptab.n++] = (double*)ctx->peer_ptr[GDK_WIN_G2][p];
         }
@@ -317,10 +317,9 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
                 // memory that is free or already held by it (very large N: smaller batches instead of an allocation failure)
                 int maxjobs = SRT_MAXJOBS;
                 {
-                    size_t freeb = 0, totalb = 0;
-                    cudaMemGetInfo(&freeb, &totalb);
                     const size_t have = ctx->recs.cap + ctx->recw.cap * 8;
-                    const size_t fit = ((freeb + have) / 3) / ((size_t)pld * 40);
+                    const size_t fit = have >= (size_t)SRT_MAXJOBS * pld * 40 ? (size_t)SRT_MAXJOBS
+                                                                              : ((ctx->query_free() + have) / 3) / ((size_t)pld * 40);
                     maxjobs = (int)std::max<size_t>(1, std::min<size_t>((size_t)SRT_MAXJOBS, fit));
                 }
                 const int nbatch_max = std::min(njobs, maxjobs);
@@ -1222,8 +1221,10 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             cudaEvent_t ev = ctx->pipe_events[gidx];
             CK2(cudaEventRecord(ev, ctx->stream));
             CK2(cudaStreamWaitEvent(ctx->stream2, ev, 0));
-            k_push_peers<<<dim3((unsigned)nj, (unsigned)ptab.n), 256, 0, ctx->stream2>>>(dout, doffs + g.b, dcnt + g.b, 0, ptab);
-            ctx->launches++;
+            if (ptab.n > 0) {
+                k_push_peers<<<dim3((unsigned)nj, (unsigned)ptab.n), 256, 0, ctx->stream2>>>(dout, doffs + g.b, dcnt + g.b, 0, ptab);
+                ctx->launches++;
+            }
         }
         if (!dev_out) {
             cudaEvent_t ev = ctx->pipe_events[gidx];
@@ -1277,8 +1278,7 @@ static int density2d_impl(gdk_ctx* ctx, int32_t n, const gdk_spec2d* specs, doub
         if (rcm) return rcm;
     }
     // chunks bounded by a memory budget
-    size_t freeb = 0, totalb = 0;
-    cudaMemGetInfo(&freeb, &totalb);
+    const size_t freeb = ctx->query_free();
     const size_t budget = std::max<size_t>((size_t)1 << 30, std::min<size_t>((size_t)32 << 30, (freeb + ctx->bytes_arena.cap) / 2));
     int b = 0;
     while (b < n) {

@@ -147,10 +147,21 @@ struct gdk_ctx {
     int stT = 0, stNtile = 0;
     // multi-GPU (one process per GPU on one node): windows of this context mapped into the peers with CUDA IPC
     int rank = 0, nranks = 1;
+    uint32_t push_mask = 0xffffffffu;  // ranks that receive the result grids of GDK_OUT_PEERS calls (gdk_peer_targets)
     int64_t row_begin = 0, row_end = 0;  // rows this rank uploads itself (the rest arrives from the peers over NVLink)
     void* peer_ptr[GDK_NWINDOW][GDK_MAX_RANKS] = {{nullptr}};
     DevBuf<double> win[2];  // GDK_WIN_G1, GDK_WIN_G2: gathered result grids
     DevBuf<unsigned char> bytes_push;
+    // free device memory as last queried (cudaMemGetInfo takes a driver-wide lock; asked once per sample store, the work
+    // buffers only grow afterwards)
+    size_t mem_free = 0;
+    size_t query_free() {
+        if (!mem_free) {
+            size_t t = 0;
+            if (cudaMemGetInfo(&mem_free, &t) != cudaSuccess) mem_free = (size_t)8 << 30;
+        }
+        return mem_free;
+    }
 };
 
 // per-kernel CUDA-event timing + algorithmic work counters for the bench's roofline figures (gdk_set_kernel_timing)

@@ -1524,11 +1524,13 @@ class MCSamples:
             par.N_eff_kde = None
         self._initLimits()
 
-    def prefetch_triangle(self, params=None, do_1d=True, do_2d=True):
+    def prefetch_triangle(self, params=None, do_1d=True, do_2d=True, root=None):
         """Compute every 1D and (lower-triangle) 2D density of a triangle plot in batched launches and seed
         the caches that get1DDensity / get2DDensity consult.  Pair (x, y) = (params[i], params[k]) for i < k,
         as getdist.plots.triangle_plot requests them (x = column parameter, y = row parameter).
-        Returns the cache entries themselves: the 2D grids are read-only views into one (pinned) result buffer."""
+        Returns the cache entries themselves: the 2D grids are read-only views into one (pinned) result buffer.
+        With a process group (MCSamples(process_group=...)): every rank computes its share; root=None leaves every rank
+        with every density, root=r only rank r (the others return empty lists)."""
         if self.needs_update:
             self.updateBaseStatistics()
         idx = list(range(self.n)) if params is None else [self._parAndNumber(p)[0] for p in params]
@@ -1538,7 +1540,7 @@ class MCSamples:
         if pg is not None and pg.world > 1:
             from .parallel import prefetch_triangle_group
 
-            return prefetch_triangle_group(self, pg, idx, do_1d, do_2d)
+            return prefetch_triangle_group(self, pg, idx, do_1d, do_2d, root=root)
         import time as _time
 
         t0 = _time.perf_counter()

@@ -229,12 +229,14 @@ def _res2d_from(row):
     return r
 
 
-def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True):
+def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, root=None):
     """MCSamples.prefetch_triangle over a PeerGroup: the densities of the triangle are partitioned across the ranks
     (1D round-robin, 2D by anchor blocks), every rank computes its share from its resident copy of the samples and the
     library stores each finished grid into the gathered windows of ALL ranks over NVLink while the next group is
     convolved; the per-density result records travel in one small all-gather.  After the closing barrier every rank
-    holds every density.  to_host=False leaves the grids in the device windows (returns their addresses and layout)."""
+    holds every density.  to_host=False leaves the grids in the device windows (returns their addresses and layout).
+    root=r gathers to rank r only (the process that plots): the grids are stored into its window alone and the other
+    ranks return empty lists -- N host copies of a gigabyte of grids share one host memory system."""
     import time
 
     from . import _abi
@@ -243,6 +245,9 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True):
     rank, world = pg.rank, pg.world
     if not pg.probe(mc._ctx):
         return _prefetch_triangle_nccl(mc, pg, idx, do_1d, do_2d, to_host)
+    if hasattr(mc._ctx, "peer_targets"):
+        mc._ctx.peer_targets(0xFFFFFFFF if root is None else (1 << int(root)))
+    mine_host = to_host and (root is None or int(root) == rank)
     exchange_param_ranges(mc, idx, rank, world, pg.dist, pg.device)
     if mc.smooth_scale_1D <= 0 or mc.smooth_scale_2D < 0:
         mc._ensure_neff(idx)
@@ -289,15 +294,16 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True):
     pg.barrier()  # every rank's stores into every window have completed (the library synchronised its streams)
     t4 = time.perf_counter()
     d2 = []
+    t_d2h = 0.0
     if do_1d:
         rows1d = {}
         for r in range(world):
             for k, j in enumerate(idx[r::world]):
                 rows1d[j] = (r * max1d + k, out["res1d"][r][k])
-        if to_host:
+        if mine_host:
             P1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, _abi.result_buffer(world * max1d * F).reshape(world * max1d, F))
             d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
-        else:
+        elif not to_host:
             out["g1"] = dict(address=base1, stride=F, rows=[rows1d[j][0] for j in idx])
     if pairs:
         lists, _ = split_pairs(idx, pairs, world)
@@ -305,14 +311,16 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True):
         for r in range(world):
             for k, pr in enumerate(lists[r]):
                 rows2d[pr] = out["res2d"][r][k]
-        if to_host:
+        if mine_host:
+            tr = time.perf_counter()
             buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total))
+            t_d2h = time.perf_counter() - tr
             d2 = mc._finish_2d(pairs, specs, buf, offs, [_res2d_from(rows2d[pr]) for pr in pairs], conts)
-        else:
+        elif not to_host:
             out["g2"] = dict(address=base2, offsets=offs, fine_bins=fb)
     t5 = time.perf_counter()
     pg.timings = dict(ranges_ms=(t1 - t0) * 1e3, d1_ms=(t2 - t1) * 1e3, d2_ms=(t3 - t2) * 1e3, barrier_ms=(t4 - t3) * 1e3,
-                      read_ms=(t5 - t4) * 1e3)
+                      read_ms=(t5 - t4) * 1e3, d2h_2d_ms=t_d2h * 1e3)
     if to_host:
         return d1, d2
     return out

@@ -118,6 +118,9 @@ int32_t gdk_measure_peaks(gdk_ctx* ctx, double* out);
 #define GDK_WIN_X 2
 #define GDK_WIN_STATS 3
 int32_t gdk_peer_init(gdk_ctx* ctx, int32_t rank, int32_t nranks);
+/* ranks (bit r = rank r) whose windows receive this rank's result grids in GDK_OUT_PEERS calls; default: every rank
+ * (replicated results).  One bit set = gather to that rank only (the process that plots).                          */
+int32_t gdk_peer_targets(gdk_ctx* ctx, uint32_t rank_mask);
 /* make window `window` at least `bytes` large (G1/G2; X and STATS are sized by gdk_samples_prepare), return its device
  * address and the 64-byte CUDA IPC handle of its allocation.  The address changes when the window had to grow: the
  * handles must then be exchanged and imported again.                                                              */
