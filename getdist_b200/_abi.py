@@ -74,6 +74,8 @@ assert RES2D_DTYPE.itemsize == C.sizeof(Result2D)
 
 def results2d_columns(res):
     """{field: list} of a batch of Result2D records (a ctypes array from the library, or any sequence of records)"""
+    if isinstance(res, dict):  # already columns (the multi-GPU path builds them from the gathered table)
+        return res
     if isinstance(res, C.Array):
         a = np.frombuffer(res, dtype=RES2D_DTYPE)
         return {k: a[k].tolist() for k in RES2D_DTYPE.names if k != "pad"}
@@ -144,6 +146,8 @@ def load():
     lib.gdk_window_import.restype = i32
     lib.gdk_window_read.argtypes = [vp, i32, u64, u64, vp]
     lib.gdk_window_read.restype = i32
+    lib.gdk_stream_sync.argtypes = [vp]
+    lib.gdk_stream_sync.restype = i32
     lib.gdk_samples_prepare.argtypes = [vp, i64, i32, vp, i32]
     lib.gdk_samples_prepare.restype = i32
     lib.gdk_samples_upload.argtypes = [vp, vp, i64, i64, vp, i64, i64]
@@ -289,10 +293,15 @@ class Context:
         buf = C.create_string_buffer(handle, 64)
         self._ck(self.lib.gdk_window_import(self.h, window, peer, C.cast(buf, C.c_void_p)), "gdk_window_import")
 
-    def window_read(self, window, offset, out):
-        """device -> host copy of out.nbytes bytes of a window starting at byte `offset`"""
-        self._ck(self.lib.gdk_window_read(self.h, window, int(offset), int(out.nbytes), _ptr(out)), "gdk_window_read")
+    def window_read(self, window, offset, out, sync=True):
+        """device -> host copy of out.nbytes bytes of a window starting at byte `offset`; sync=False returns with the
+        copy in flight on the library stream (stream_sync() before the data is read)"""
+        self._ck(self.lib.gdk_window_read(self.h, window, int(offset), int(out.nbytes) | (0 if sync else 1 << 63), _ptr(out)),
+                 "gdk_window_read")
         return out
+
+    def stream_sync(self):
+        self._ck(self.lib.gdk_stream_sync(self.h), "gdk_stream_sync")
 
     def moments_recompute(self):
         self._ck(self.lib.gdk_moments_recompute(self.h), "gdk_moments_recompute")

@@ -412,14 +412,23 @@ extern "C" int32_t gdk_window_import(gdk_ctx* ctx, int32_t window, int32_t peer,
     return GDK_OK;
 }
 
+extern "C" int32_t gdk_stream_sync(gdk_ctx* ctx) {
+    if (!ctx) return GDK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GDK_OK;
+}
+
 extern "C" int32_t gdk_window_read(gdk_ctx* ctx, int32_t window, uint64_t offset, uint64_t bytes, void* host_out) {
     if (!ctx || !host_out) return GDK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    const bool async = (bytes >> 63) != 0;  // top bit of `bytes`: leave the copy in flight (gdk_stream_sync)
+    bytes &= ~(1ull << 63);
     void* p = nullptr;
     int rc = window_buffer(ctx, window, offset + bytes, &p);
     if (rc) return rc;
     CK(cudaMemcpyAsync(host_out, (const char*)p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!async) CK(cudaStreamSynchronize(ctx->stream));
     return GDK_OK;
 }
 

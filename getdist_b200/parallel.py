@@ -313,9 +313,16 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
                 rows2d[pr] = out["res2d"][r][k]
         if mine_host:
             tr = time.perf_counter()
-            buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total))
+            # the copy runs while the host wraps the grids (views of the buffer: nothing reads it before the sync below)
+            buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total), sync=False)
+            tab2 = np.array([rows2d[pr] for pr in pairs])  # (pairs, 13) in the caller's order -> result columns
+            names2 = ("hx", "hy", "c", "rx", "ry", "t_star", "winw", "status", "n_brent")
+            rcol = {k: (tab2[:, i].astype(np.int64).tolist() if k in ("winw", "status", "n_brent") else tab2[:, i].tolist())
+                    for i, k in enumerate(names2)}
+            rcol["levels"] = tab2[:, 9:13].tolist()
+            d2 = mc._finish_2d(pairs, specs, buf, offs, rcol, conts)
+            mc._ctx.stream_sync()
             t_d2h = time.perf_counter() - tr
-            d2 = mc._finish_2d(pairs, specs, buf, offs, [_res2d_from(rows2d[pr]) for pr in pairs], conts)
         elif not to_host:
             out["g2"] = dict(address=base2, offsets=offs, fine_bins=fb)
     t5 = time.perf_counter()

@@ -126,8 +126,10 @@ int32_t gdk_peer_targets(gdk_ctx* ctx, uint32_t rank_mask);
  * handles must then be exchanged and imported again.                                                              */
 int32_t gdk_window_export(gdk_ctx* ctx, int32_t window, uint64_t bytes, void* handle64, uint64_t* device_address);
 int32_t gdk_window_import(gdk_ctx* ctx, int32_t window, int32_t peer, const void* handle64);
-/* device -> host copy of a byte range of a window (after the barrier that follows the writers)                     */
+/* device -> host copy of a byte range of a window (after the barrier that follows the writers).  With the top bit of
+ * `bytes` set the call returns with the copy in flight on the library stream; gdk_stream_sync waits for it.       */
 int32_t gdk_window_read(gdk_ctx* ctx, int32_t window, uint64_t offset, uint64_t bytes, void* host_out);
+int32_t gdk_stream_sync(gdk_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * data residency -- replaces WeightedSamples.setSamples / Chains.makeSingle state

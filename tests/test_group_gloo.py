@@ -62,7 +62,10 @@ class WinContext(FakeContext):
         segs = [self.own[window]] + list(self.peer[window].values())
         return [np.ndarray((s.size // 8,), dtype=np.float64, buffer=s.buf) for s in segs]
 
-    def window_read(self, window, offset, out):
+    def stream_sync(self):
+        pass
+
+    def window_read(self, window, offset, out, sync=True):
         v = np.ndarray((self.own[window].size // 8,), dtype=np.float64, buffer=self.own[window].buf)
         out.reshape(-1)[:] = v[offset // 8: offset // 8 + out.size]
         return out
