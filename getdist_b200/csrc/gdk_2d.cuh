@@ -1107,6 +1107,7 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (smem_max > (size_t)ctx->max_smem) return gdk_fail(ctx, GDK_ERR_UNSUPPORTED, "window too large for the convolution kernel");
     CK2(cudaFuncSetAttribute(k_conv2d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     CK2(cudaFuncSetAttribute(k_conv2d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
+    CK2(cudaFuncSetAttribute(k_conv2d<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
     if (likes) {
         CK2(cudaFuncSetAttribute(k_conv2d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
         CK2(cudaFuncSetAttribute(k_conv2d<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 48 << 10)));
@@ -1165,8 +1166,13 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             cbytes += 16.0 * G2;
         }
         {
+            bool any_mom = false;
+            for (int k = g.b; k < g.e; k++) any_mom = any_mom || (cjs[k].bounded && cjs[k].bco == 1);
             KernelTimer kt(ctx, GDK_K_CONV2D_0, cbytes, cflops0);
-            k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
+            if (any_mom)
+                k_conv2d<0><<<gc, 256, conv_smem(g.wmax, kc0), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc0);
+            else
+                k_conv2d<4><<<gc, 256, conv_smem(g.wmax, kc1), ctx->stream>>>(dcj + g.b, 0, g.wmax, kc1);
         }
         dim3 gcirc((unsigned)((g.Gmax * g.Gmax + 255) / 256), (unsigned)nj);
         if (any_periodic) {

@@ -617,6 +617,8 @@ __host__ __device__ __forceinline__ int cv_q(int wmax) {
 // MODE 0: in = hist                      -> P (and xP, yP when bounded with order 1); running max -> mx[0]
 // MODE 1: in = box = hist / P where P > thr (thr = mx[1+iter]*1e-8) else hist
 //                                         -> next P = P * conv / a00b; running max -> mx[2+iter]
+// MODE 4: MODE 0 compiled without the moment maps (groups with no boundary correction of order 1): 24 accumulator
+//         registers fewer, higher occupancy
 // MODE 2: in = lhist (mean-likelihood histogram) -> lP           (jobs without lhist return)
 // MODE 3: in = lbox                              -> lP2 = conv * lP where lP > 0, else conv   (jobs with lmbc only)
 // grid (tiles, njobs), 256 threads = 16 (x) x 16 (y); every thread produces 8 consecutive outputs of one row.
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     extern __shared__ __align__(16) double csm[];
     const ConvJob jb = jobs[blockIdx.y];
     if (MODE == 1 && iter >= jb.mbc) return;
-    if (MODE >= 2 && (!jb.lhist || (MODE == 3 && !jb.lmbc))) return;
+    if ((MODE == 2 || MODE == 3) && (!jb.lhist || (MODE == 3 && !jb.lmbc))) return;
     if (jb.xper | jb.yper) return;  // periodic pairs: k_conv2d_circ
     const int G = jb.G, w = jb.w, K = 2 * w + 1;
     const int Kp = (K + 7) & ~7;
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
     double* Pout = (MODE == 1) ? ((iter & 1) ? jb.P : jb.Pn) : jb.P;
     double thr = 0;
     if (MODE == 1) thr = __longlong_as_double((long long)jb.mx[1 + iter]) * 1e-8;
-    const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;
+    const bool moments = (MODE == 0) && jb.bounded && jb.bco == 1;  // MODE 4: MODE 0 for groups without moment maps
     double acc[CV_MX], accx[CV_MX], accy[CV_MX];
 #pragma unroll
     for (int m = 0; m < CV_MX; m++) acc[m] = accx[m] = accy[m] = 0;
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
         // input rows a = abase + r, r < CV_TY + kc - 1; one warp per row, lanes stride over the columns
         const int abase = oy0 - (k0 + kc - 1) + w;
         const int nrow = CV_TY + kc - 1;
-        const double* srcp = (MODE == 1) ? jb.box : (MODE == 2 ? jb.lhist : (MODE == 3 ? jb.lbox : jb.hist));
+        const double* srcp = (MODE == 1) ? jb.box : (MODE == 2 ? jb.lhist : (MODE == 3 ? jb.lbox : jb.hist));  // MODE 0, 4: hist
         for (int r = threadIdx.x >> 5; r < nrow; r += 8) {
             const int a = abase + r;
             const bool rowok = a >= 0 && a < G;
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
             const int ox = ox0 + tx * CV_MX + m;
             if (ox >= G) continue;
             const size_t o = (size_t)oy * G + ox;
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 4) {
                 jb.P[o] = acc[m];
                 if (moments) {
                     jb.xP[o] = accx[m];
@@ -747,9 +749,9 @@ __global__ void __launch_bounds__(256) k_conv2d(const ConvJob* __restrict__ jobs
             }
         }
     }
-    if (MODE >= 2) return;
+    if (MODE == 2 || MODE == 3) return;
     tmax = warp_max(tmax);
-    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 0 ? 0 : 2 + iter), tmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(jb.mx + (MODE == 1 ? 2 + iter : 0), tmax);
 }
 
 // mean likelihoods, elementwise steps (mcsamples.py:1890-1898).  grid (64, njobs).
