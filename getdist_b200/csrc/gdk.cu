@@ -337,7 +337,8 @@ static int stats_rows(gdk_ctx* ctx, int64_t ra, int64_t rb, cudaStream_t st, int
         }
         k_stats_fused<<<g, 128, ST_SMEM, st>>>(ctx->dX.p, ctx->ld, ctx->dW.p, ctx->ssegs.p + s0, P, T, nt, ctx->stiles.p, ctx->spart[k].p);
     }
-    k_stats_merge<<<b1 - b0, 256, 3 * P * sizeof(double), st>>>(ctx->spart[k].p, ctx->ssegs.p, ctx->sblkseg.p + b0, ctx->sblkout.p + b0, s0,
+    const int slices = std::max(1, std::min(16, (P * P + 255) / 256));
+    k_stats_merge<<<dim3((unsigned)(b1 - b0), (unsigned)slices), 256, 3 * P * sizeof(double), st>>>(ctx->spart[k].p, ctx->ssegs.p, ctx->sblkseg.p + b0, ctx->sblkout.p + b0, s0,
                                                                 ctx->dX.p, ctx->ld, P, T, nt, ctx->dblock.p);
     ctx->launches += 2;
     for (int i = b0; i < b1; i++) ctx->sblock_done[i] = 1;

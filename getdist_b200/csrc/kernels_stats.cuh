@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(128, 3) k_stats_fused(const double* __restrict
     }
 }
 
-// Sequential merge of the segments of one stat block (grid = blocks, 256 threads, dynamic shared 3 P doubles).
+// Sequential merge of the segments of one stat block: grid (blocks, slices), 256 threads, dynamic shared 3 P doubles.
+// Every slice repeats the (cheap) recursion of the running mean and applies it to its own share of the P x P elements.
 // Block record: [0] = A, [1 .. P] mean, [P+1 .. 2P] min x, [2P+1 .. 3P] max x, [3P+1 ..] S (P x P, symmetric, centred).
 __host__ __device__ __forceinline__ int64_t st_block_stride(int P) { return 3 * (int64_t)P + 1 + (int64_t)P * P; }
 __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ part, const Seg* __restrict__ segs,
@@ -326,12 +327,16 @@ __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ 
     double* out = bout + (int64_t)blkout[blockIdx.x] * st_block_stride(P);
     double* S = out + 3 * P + 1;
     const int64_t pstride = st_part_stride(T, ntile);
+    const bool first = blockIdx.y == 0;  // slice 0 also writes the vectors
     for (int c = threadIdx.x; c < P; c += blockDim.x) {
         m[c] = 0;
-        out[1 + P + c] = INFINITY;
-        out[1 + 2 * P + c] = -INFINITY;
+        if (first) {
+            out[1 + P + c] = INFINITY;
+            out[1 + 2 * P + c] = -INFINITY;
+        }
     }
-    for (int64_t e = threadIdx.x; e < (int64_t)P * P; e += blockDim.x) S[e] = 0;
+    const int64_t e0 = (int64_t)blockIdx.y * blockDim.x + threadIdx.x, estep = (int64_t)gridDim.y * blockDim.x;
+    for (int64_t e = e0; e < (int64_t)P * P; e += estep) S[e] = 0;
     double A = 0;
     __syncthreads();
     for (int s = bs.x; s < bs.x + bs.y; s++) {
@@ -341,8 +346,10 @@ __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ 
         const int64_t r0 = segs[s].r0;
         for (int c = threadIdx.x; c < P; c += blockDim.x) {
             const double sh = dX[(int64_t)c * ld + r0];
-            out[1 + P + c] = fmin(out[1 + P + c], pb[T * ST_T + c]);
-            out[1 + 2 * P + c] = fmax(out[1 + 2 * P + c], pb[2 * T * ST_T + c]);
+            if (first) {
+                out[1 + P + c] = fmin(out[1 + P + c], pb[T * ST_T + c]);
+                out[1 + 2 * P + c] = fmax(out[1 + 2 * P + c], pb[2 * T * ST_T + c]);
+            }
             if (As_ > 0) {
                 const double d = pb[c] / As_;
                 ds[c] = d;
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ 
         if (As_ > 0) {
             const double W = A + As_;
             const double f = (A > 0) ? A * As_ / W : 0.0;
-            for (int64_t e = threadIdx.x; e < (int64_t)P * P; e += blockDim.x) {
+            for (int64_t e = e0; e < (int64_t)P * P; e += estep) {
                 const int i = (int)(e / P), j = (int)(e % P);
                 const int a = min(i, j), b = max(i, j);
                 const int ta = a / ST_T, tb = b / ST_T;
@@ -369,8 +376,10 @@ __global__ void __launch_bounds__(256) k_stats_merge(const double* __restrict__ 
         }
         __syncthreads();
     }
-    for (int c = threadIdx.x; c < P; c += blockDim.x) out[1 + c] = m[c];
-    if (threadIdx.x == 0) out[0] = A;
+    if (first) {
+        for (int c = threadIdx.x; c < P; c += blockDim.x) out[1 + c] = m[c];
+        if (threadIdx.x == 0) out[0] = A;
+    }
 }
 
 // ---- multi-GPU: finished result grids of this rank stored into every peer's gathered window over NVLink ------------
