@@ -385,10 +385,13 @@ def run_ours(args):
     torch.cuda.set_device(dev)
 
     from getdist_b200 import MCSamples, _abi
-    from getdist_b200.parallel import PeerGroup, prefetch_triangle_group
+    from getdist_b200.parallel import PeerGroup, bind_to_gpu_numa, prefetch_triangle_group
 
+    numa_cpus = None
     if world > 1:
         pg = PeerGroup(dist, rank, world, use_p2p=not args.nccl_gather)
+        if not args.no_numa:
+            numa_cpus = bind_to_gpu_numa(dev)  # before the pinned input buffers are allocated
 
     N, P = args.n, args.p
     # pinned host inputs (e2e path copies from here every step)
@@ -731,7 +734,8 @@ def run_ours(args):
                                  "over PCIe and stores them into the peers' column stores over NVLink; finished grids are stored into every "
                                  "rank's gathered window (transport: %s)" % (world, world, pg.transport)),
                    "l2": "inputs (%.1f GB) are larger than L2; no flush needed between steps" % ((N * P * 8 + N * 8) / 1e9),
-                   "datagen_s": round(t_gen, 2), "extra_untimed_settle_steps": extra_warm},
+                   "datagen_s": round(t_gen, 2), "extra_untimed_settle_steps": extra_warm,
+                   "rank0_cpu_affinity": (None if numa_cpus is None else "%d CPUs next to GPU %d (NVML ideal affinity)" % (len(numa_cpus), dev))},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_step": e2e_s, "checksum": checksum, "parts": e2e_parts,
                 "path": "MCSamples.setSamples(pinned host) + updateBaseStatistics() [H2D, fused moments behind the chunks] -> "
@@ -764,6 +768,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU vs single-GPU comparison")
     ap.add_argument("--parity-1d", type=int, default=None, help="debug: limit the CPU parity leg to this many 1D and 2D densities")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the ranks to the CPUs next to their GPUs")
     ap.add_argument("--nccl-gather", action="store_true", help="force the fallback transport (NCCL all-gather after the batch)")
     args = ap.parse_args()
     if args.n is None:

@@ -118,6 +118,10 @@ def load():
     lib.gdk_alloc_pinned.restype = i32
     lib.gdk_free_pinned.argtypes = [vp]
     lib.gdk_free_pinned.restype = i32
+    lib.gdk_host_register.argtypes = [vp, u64]
+    lib.gdk_host_register.restype = i32
+    lib.gdk_host_unregister.argtypes = [vp]
+    lib.gdk_host_unregister.restype = i32
     lib.gdk_launch_count.argtypes = [vp]
     lib.gdk_launch_count.restype = i64
     lib.gdk_timer_start.argtypes = [vp]
@@ -401,9 +405,9 @@ class Context:
         if offsets is None:
             offsets = np.zeros(n, dtype=np.int64)
             offsets[1:] = np.cumsum(sizes)[:-1]
-        else:  # the caller's layout (gathered multi-GPU window): element offsets from device_ptr
+        else:  # the caller's layout (gathered multi-GPU results): element offsets from device_ptr / from `out`
             offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-            assert offsets.size == n and device_ptr is not None
+            assert offsets.size == n and (device_ptr is not None or out is not None)
         total = int(sizes.sum())
         res = (Result2D * n)()
         if likes:  # get2DDensityGridData(meanlikes=True): (P, likes, offsets, results)
@@ -574,6 +578,16 @@ pinned_pool = PinnedPool()
 def result_buffer(n):
     """host buffer for n float64 results: pinned (pooled) when large, plain numpy otherwise"""
     return pinned_pool.empty(n) if n * 8 >= PinnedPool.threshold else np.empty(n)
+
+
+def host_register(arr):
+    """page-lock the memory of a numpy array this process owns or maps (full-rate, asynchronous device copies)"""
+    if load().gdk_host_register(C.c_void_p(arr.ctypes.data), int(arr.nbytes)) != 0:
+        raise GdkError("cudaHostRegister of %d bytes failed" % arr.nbytes)
+
+
+def host_unregister(arr):
+    load().gdk_host_unregister(C.c_void_p(arr.ctypes.data))
 
 
 def pinned_empty(shape, dtype=np.float64):

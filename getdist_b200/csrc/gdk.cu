@@ -235,6 +235,16 @@ extern "C" int32_t gdk_alloc_pinned(uint64_t bytes, void** out) {
     if (!out) return GDK_ERR_ARG;
     return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? GDK_OK : GDK_ERR_NOMEM;
 }
+extern "C" int32_t gdk_host_register(void* p, uint64_t bytes) {
+    if (!p || !bytes) return GDK_ERR_ARG;
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return GDK_ERR_CUDA;
+    }
+    return GDK_OK;
+}
+extern "C" int32_t gdk_host_unregister(void* p) { return (p && cudaHostUnregister(p) == cudaSuccess) ? GDK_OK : GDK_ERR_CUDA; }
 extern "C" int32_t gdk_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? GDK_OK : GDK_ERR_CUDA; }
 extern "C" int64_t gdk_launch_count(gdk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int32_t gdk_timer_start(gdk_ctx* ctx) {

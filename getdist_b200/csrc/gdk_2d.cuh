@@ -1045,16 +1045,22 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     for (int i = 0; i < n; i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](int a, int b) { return cj[a].w < cj[b].w; });
     std::vector<ConvJob> cjs(n);
-    std::vector<long long> offs_sorted(n);
+    // offs_sorted: where the caller wants density k (elements from P_out: any layout, e.g. the gathered layout of a
+    // multi-rank call); devo_sorted: where it sits on the device -- the same for device output, packed in launch order
+    // in the staging buffer for host output
+    std::vector<long long> offs_sorted(n), devo_sorted(n);
+    size_t otot = 0;
     for (int k = 0; k < n; k++) {
         cjs[k] = cj[order[k]];
         offs_sorted[k] = offsets[order[k]];
+        devo_sorted[k] = dev_out ? offs_sorted[k] : (long long)otot;
+        otot += (size_t)cjs[k].G * cjs[k].G;
     }
     ConvJob* dcj = nullptr;
     rc = upload_vec(ctx, cjs, ctx->bytes2d_c, &dcj);
     if (rc) return rc;
     long long* doffs = nullptr;
-    rc = upload_vec(ctx, offs_sorted, ctx->bytes2d_e, &doffs);
+    rc = upload_vec(ctx, devo_sorted, ctx->bytes2d_e, &doffs);
     if (rc) return rc;
     int* dcnt = nullptr;
     if (peers_out) {
@@ -1118,20 +1124,16 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
     if (dev_out) {
         dout = P_out;
     } else {
-        size_t otot = 0;
-        for (int i = 0; i < n; i++) otot = std::max(otot, (size_t)(offsets[i] - offsets[0]) + (size_t)specs[i].fine_bins * specs[i].fine_bins);
         if (ctx->f2.ensure(otot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D output buffer");
-        dout = ctx->f2.p - offsets[0];  // offsets are relative to P_out; the chunk's first density sits at f2[0]
+        dout = ctx->f2.p;
     }
     double* dlout = nullptr;
     if (likes) {
         if (dev_out) {
             dlout = likes_out;
         } else {
-            size_t otot = 0;
-            for (int i = 0; i < n; i++) otot = std::max(otot, (size_t)(offsets[i] - offsets[0]) + (size_t)specs[i].fine_bins * specs[i].fine_bins);
             if (ctx->f2l.ensure(otot)) return gdk_fail(ctx, GDK_ERR_NOMEM, "2D mean-likelihood output buffer");
-            dlout = ctx->f2l.p - offsets[0];
+            dlout = ctx->f2l.p;
         }
     }
     bool any_contours = false;
@@ -1238,8 +1240,8 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             CK2(cudaStreamWaitEvent(ctx->stream2, ev, 0));
             for (int k = g.b; k < g.e; k++) {
                 const size_t cnt = (size_t)cjs[k].G * cjs[k].G * 8;
-                CK2(cudaMemcpyAsync(P_out + offs_sorted[k], dout + offs_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
-                if (likes) CK2(cudaMemcpyAsync(likes_out + offs_sorted[k], dlout + offs_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+                CK2(cudaMemcpyAsync(P_out + offs_sorted[k], dout + devo_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+                if (likes) CK2(cudaMemcpyAsync(likes_out + offs_sorted[k], dlout + devo_sorted[k], cnt, cudaMemcpyDeviceToHost, ctx->stream2));
             }
         }
         gidx++;

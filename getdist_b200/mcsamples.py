@@ -1175,6 +1175,20 @@ class MCSamples:
                 sp["ry_fixed"] = smooth * fine / nbin2D
         return sp
 
+    def _fine_bins_2d_all(self, pairs):
+        """fine_bins of every pair (mcsamples.py:1811-1818: scaled up for strongly correlated pairs): from the correlation
+        matrix and the settings alone"""
+        jx = np.array([p[0] for p in pairs], dtype=np.int64)
+        jy = np.array([p[1] for p in pairs], dtype=np.int64)
+        base = int(self.fine_bins_2D)
+        corr = self.getCorrelationMatrix()[jy, jx].copy()
+        one = np.abs(np.abs(corr) - 1.0) <= 1e-8
+        corr[one] = np.sign(corr[one]) * self.max_corr_2D
+        corr[np.abs(corr) < 0.1] = 0.0
+        angle = np.maximum(0.2, np.sqrt(1 - np.minimum(self.max_corr_2D, np.abs(corr)) ** 2))
+        scaled = 192 * (3 / angle).astype(np.int64) // 3
+        return np.where((corr != 0) & (base < scaled) & ((1 / angle).astype(np.int64) > 1), scaled, base).astype(np.int64)
+
     def _densities_2d(self, pairs, _out=None, _device_ptr=None, _contours=None, _likes=False, _anchor_hints=None,
                       _mask_function=None, **kwargs):
         if _likes:

@@ -109,6 +109,29 @@ def exchange_param_ranges(mc, indices, rank, world, dist=None, device="cuda"):
             mc._finish_param(mc.paramNames.names[j], j, table[r * per + k])
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) before it allocates page-locked buffers: with
+    N ranks uploading at once, host buffers on the far socket halve the aggregate PCIe rate.  Returns the CPU list, or
+    None where NVML or the affinity call is not available."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 class PeerGroup:
     """One process per GPU on one node: the rendezvous (torch.distributed: NCCL on GPUs, gloo in the CPU tests), this
     rank's id, and the bookkeeping of which library windows are mapped into the peers.
@@ -180,6 +203,61 @@ class PeerGroup:
         mapped[window] = (addr, nbytes)
         return addr
 
+    # -- shared host result buffer (gather to one rank) ---------------------------------------------------------
+    def shared_results(self, nbytes, root):
+        """A host buffer of at least nbytes that EVERY rank of the node maps (a /dev/shm file, unlinked once all have it
+        open) and page-locks: each rank's batch call copies its grids straight into it over its own PCIe link, and the
+        root rank reads them in place.  Collective.  The root reuses a segment once nothing refers to the arrays it
+        handed out from it.  Returns a float64 array over the segment (the root's carries the reference that keeps the
+        segment busy)."""
+        import mmap
+        import os
+        import uuid
+        import weakref
+
+        from . import _abi
+
+        segs = self.__dict__.setdefault("_segs", {})
+        msg = np.zeros(72, dtype=np.uint8)
+        if self.rank == root:
+            seg = None
+            for sg in segs.values():
+                if sg["owner"] and not sg["busy"] and sg["size"] >= nbytes and (seg is None or sg["size"] < seg["size"]):
+                    seg = sg
+            if seg is None:
+                size = ((int(nbytes * 1.05) + (2 << 20) - 1) // (2 << 20)) * (2 << 20)
+                name = "gdk_%s" % uuid.uuid4().hex
+                fd = os.open("/dev/shm/" + name, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, size)
+                seg = dict(name=name, size=size, fd=fd, owner=True, busy=False, mm=None)
+            nm = seg["name"].encode()
+            msg[: len(nm)] = np.frombuffer(nm, dtype=np.uint8)
+            msg[64:72] = np.frombuffer(np.int64(seg["size"]).tobytes(), dtype=np.uint8)
+        row = self.all_gather_array(msg)[root]
+        name = bytes(row[:64]).rstrip(b"\0").decode()
+        size = int(np.frombuffer(bytes(row[64:72]), dtype=np.int64)[0])
+        sg = segs.get(name)
+        fresh = sg is None or sg["mm"] is None
+        if fresh:
+            if self.rank == root:
+                sg = seg
+            else:
+                sg = dict(name=name, size=size, fd=os.open("/dev/shm/" + name, os.O_RDWR), owner=False, busy=False, mm=None)
+            sg["mm"] = mmap.mmap(sg["fd"], size)
+            os.close(sg["fd"])
+            sg["arr"] = np.frombuffer(sg["mm"], dtype=np.float64)
+            _abi.host_register(sg["arr"])
+            segs[name] = sg
+            self.barrier()  # everybody has it open: the name can go
+            if self.rank == root:
+                os.unlink("/dev/shm/" + name)
+        if self.rank != root:
+            return sg["arr"]
+        sg["busy"] = True
+        base = np.frombuffer(sg["mm"], dtype=np.float64)  # a fresh base object per call: its death frees the segment
+        weakref.finalize(base, sg.__setitem__, "busy", False)
+        return base
+
     def probe(self, ctx):
         """decide the transport once: try to map a small result window into the peers"""
         if self.world == 1 or not self.p2p or getattr(self, "_probed", False):
@@ -248,6 +326,7 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     if hasattr(mc._ctx, "peer_targets"):
         mc._ctx.peer_targets(0xFFFFFFFF if root is None else (1 << int(root)))
     mine_host = to_host and (root is None or int(root) == rank)
+    host_gather = to_host and root is not None and hasattr(pg, "shared_results") and getattr(pg, "host_gather", True)
     exchange_param_ranges(mc, idx, rank, world, pg.dist, pg.device)
     if mc.smooth_scale_1D <= 0 or mc.smooth_scale_2D < 0:
         mc._ensure_neff(idx)
@@ -260,13 +339,24 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     d1 = []
     if do_1d:
         F = int(mc.fine_bins)
-        base1 = pg.map_window(mc._ctx, _abi.GDK_WIN_G1, world * max1d * F * 8)
         specs_all = [mc._spec_1d(j, {}) for j in idx]
         pos = {j: n for n, j in enumerate(idx)}
         tab = np.zeros((max1d, 6))
-        if my1d:
-            _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d], device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
-            tab[: len(my1d)] = _res1d_table(res)
+        n1 = world * max1d * F
+        shared = None
+        if host_gather:
+            # one host buffer for the node: [1D rows per rank | 2D grids in the caller's pair order]
+            fbq = mc._fine_bins_2d_all(pairs) if pairs else np.zeros(0, dtype=np.int64)
+            shared = pg.shared_results((n1 + int((fbq * fbq).sum())) * 8, int(root))
+            if my1d:
+                _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d],
+                                                 out=shared[rank * max1d * F: (rank * max1d + len(my1d)) * F].reshape(len(my1d), F), stride=F)
+                tab[: len(my1d)] = _res1d_table(res)
+        else:
+            base1 = pg.map_window(mc._ctx, _abi.GDK_WIN_G1, n1 * 8)
+            if my1d:
+                _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d], device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
+                tab[: len(my1d)] = _res1d_table(res)
         out["res1d"] = pg.all_gather_array(tab)
     t2 = time.perf_counter()
     # ---- 2D: the window holds every pair's grid in the caller's pair order
@@ -280,15 +370,25 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
         offs = np.zeros(len(pairs), dtype=np.int64)
         offs[1:] = np.cumsum(fb * fb)[:-1]
         total = int((fb * fb).sum())
-        base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
         where = {pr: n for n, pr in enumerate(pairs)}
         mine = np.array([where[pr] for pr in my2d], dtype=np.int64)
         tab = np.zeros((per, 13))
+        if host_gather and shared is None:
+            shared = pg.shared_results(total * 8, int(root))
+        if host_gather and shared.size < (world * max1d * int(mc.fine_bins) if do_1d else 0) + total:
+            raise RuntimeError("shared result buffer smaller than the gathered layout")
+        n1 = world * max1d * int(mc.fine_bins) if do_1d else 0
         if len(mine):
             sp = np.ascontiguousarray(specs[mine])
             sp["anchor_hint"] = np.asarray(hints, dtype=np.int32)
-            _, _, res = mc._ctx.density2d_batch(sp, device_ptr=base2, offsets=offs[mine], peers=True)
+            if host_gather:  # every rank copies its grids into the node's shared host buffer over its own PCIe link
+                _, _, res = mc._ctx.density2d_batch(sp, out=shared[n1: n1 + total], offsets=offs[mine])
+            else:
+                base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
+                _, _, res = mc._ctx.density2d_batch(sp, device_ptr=base2, offsets=offs[mine], peers=True)
             tab[: len(mine)] = _res2d_table(res)
+        elif not host_gather:
+            base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
         out["res2d"] = pg.all_gather_array(tab)
     t3 = time.perf_counter()
     pg.barrier()  # every rank's stores into every window have completed (the library synchronised its streams)
@@ -300,7 +400,10 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
         for r in range(world):
             for k, j in enumerate(idx[r::world]):
                 rows1d[j] = (r * max1d + k, out["res1d"][r][k])
-        if mine_host:
+        if mine_host and host_gather:
+            P1 = shared[:n1].reshape(world * max1d, F)
+            d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
+        elif mine_host:
             P1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, _abi.result_buffer(world * max1d * F).reshape(world * max1d, F))
             d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
         elif not to_host:
@@ -313,15 +416,19 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
                 rows2d[pr] = out["res2d"][r][k]
         if mine_host:
             tr = time.perf_counter()
-            # the copy runs while the host wraps the grids (views of the buffer: nothing reads it before the sync below)
-            buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total), sync=False)
+            if host_gather:
+                buf = shared[n1: n1 + total]  # already on this host: every rank copied its share
+            else:
+                # the copy runs while the host wraps the grids (views of the buffer: nothing reads it before the sync below)
+                buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total), sync=False)
             tab2 = np.array([rows2d[pr] for pr in pairs])  # (pairs, 13) in the caller's order -> result columns
             names2 = ("hx", "hy", "c", "rx", "ry", "t_star", "winw", "status", "n_brent")
             rcol = {k: (tab2[:, i].astype(np.int64).tolist() if k in ("winw", "status", "n_brent") else tab2[:, i].tolist())
                     for i, k in enumerate(names2)}
             rcol["levels"] = tab2[:, 9:13].tolist()
             d2 = mc._finish_2d(pairs, specs, buf, offs, rcol, conts)
-            mc._ctx.stream_sync()
+            if not host_gather:
+                mc._ctx.stream_sync()
             t_d2h = time.perf_counter() - tr
         elif not to_host:
             out["g2"] = dict(address=base2, offsets=offs, fine_bins=fb)

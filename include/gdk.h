@@ -78,6 +78,10 @@ const char* gdk_last_error(gdk_ctx* ctx);
 /* pinned host staging buffers for callers that want full-rate H2D (bench e2e path) */
 int32_t gdk_alloc_pinned(uint64_t bytes, void** out);
 int32_t gdk_free_pinned(void* p);
+/* page-lock / release host memory the caller owns (e.g. a shared-memory segment that the ranks of a node all map: each
+ * rank's batch call then copies its grids straight into the one host buffer the plotting process reads)           */
+int32_t gdk_host_register(void* p, uint64_t bytes);
+int32_t gdk_host_unregister(void* p);
 /* number of kernel launches issued by this context since creation (bench `gpu_launches`) */
 int64_t gdk_launch_count(gdk_ctx* ctx);
 /* CUDA-event stopwatch on the library's stream: start records an event, stop records another, waits for it

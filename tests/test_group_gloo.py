@@ -73,11 +73,14 @@ class WinContext(FakeContext):
     def density1d_batch(self, specs, out=None, device_ptr=None, likes=False, stride=None, peers=False):
         from getdist_b200 import _abi
 
-        assert peers and device_ptr is not None
-        off = (device_ptr - self.BASE * (_abi.GDK_WIN_G1 + 1)) // 8
         res = []
+        if out is not None:  # host output (the node's shared result buffer)
+            views, off = [out.reshape(-1)], 0
+        else:
+            assert peers and device_ptr is not None
+            views, off = self._views(_abi.GDK_WIN_G1), (device_ptr - self.BASE * (_abi.GDK_WIN_G1 + 1)) // 8
         for i, s in enumerate(specs):
-            for v in self._views(_abi.GDK_WIN_G1):
+            for v in views:
                 v[off + i * stride: off + i * stride + s.fine_bins] = f1(s.param)
             r = _abi.Result1D()
             r.kde_h, r.status, r.winw = 0.1 * (s.param + 1), 0, s.param
@@ -87,11 +90,15 @@ class WinContext(FakeContext):
     def density2d_batch(self, specs, out=None, device_ptr=None, likes=False, offsets=None, peers=False):
         from getdist_b200 import _abi
 
-        assert peers and device_ptr == self.BASE * (_abi.GDK_WIN_G2 + 1)
+        if out is not None:
+            views = [out]
+        else:
+            assert peers and device_ptr == self.BASE * (_abi.GDK_WIN_G2 + 1)
+            views = self._views(_abi.GDK_WIN_G2)
         res = []
         for sp, off in zip(specs, offsets):
             G = int(sp["fine_bins"])
-            for v in self._views(_abi.GDK_WIN_G2):
+            for v in views:
                 v[off: off + G * G] = f2(int(sp["px"]), int(sp["py"]))
             r = _abi.Result2D()
             r.hx, r.status, r.winw = 1.0 + int(sp["px"]), 0, int(sp["py"])
@@ -106,7 +113,7 @@ class WinContext(FakeContext):
             seg.unlink()
 
 
-def _worker(rank, world, port, P, ret):
+def _worker(rank, world, port, P, root, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -114,6 +121,7 @@ def _worker(rank, world, port, P, ret):
     from getdist_b200.parallel import PeerGroup
 
     _abi.Context = WinContext
+    _abi.host_register = lambda arr: None  # no CUDA here: the shared segment stays pageable
     rng = np.random.default_rng(5)
     N = 4000
     X = rng.standard_normal((N, P)) * np.arange(1, P + 1) + 10.0
@@ -122,9 +130,15 @@ def _worker(rank, world, port, P, ret):
     r0, r1 = pg.row_range(10_000_000)
     mc = MCSamples(samples=X, weights=w, names=["p%d" % i for i in range(P)], sampler="uncorrelated",
                    settings={"fine_bins": 64, "fine_bins_2D": 16}, process_group=pg)
-    d1, d2 = mc.prefetch_triangle()
+    d1, d2 = mc.prefetch_triangle(root=root)
     idx, pairs = mc.triangle_pairs()
     ok = pg.transport == "p2p" and mc._ctx.group_seen is pg
+    if root is not None and rank != root:  # gather to one rank: the others hold nothing
+        ret[rank] = (len(d1) == 0 and len(d2) == 0, [mc.paramNames.names[j].range_min for j in idx], (r0, r1))
+        dist.barrier()
+        mc._ctx.close()
+        dist.destroy_process_group()
+        return
     ok = ok and len(d1) == P and len(d2) == len(pairs)
     ok = ok and all(np.all(d.P == f1(j)) and d._gdk["winw"] == j for d, j in zip(d1, idx))
     ok = ok and all(np.all(d.P == f2(a, b)) and d._gdk["winw"] == b and d._gdk["hx"] == 1.0 + a
@@ -136,12 +150,14 @@ def _worker(rank, world, port, P, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("P", [5, 8])
-def test_group_prefetch_world2(P):
+@pytest.mark.parametrize("P,root", [(5, None), (8, None), (6, 0), (7, 1)])
+def test_group_prefetch_world2(P, root):
+    """root=None: every rank gets every density through the peer windows; root=r: the ranks copy their grids into the
+    node's shared host buffer and only rank r wraps them"""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), P, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), P, root, ret), nprocs=world, join=True)
     assert ret[0][0] and ret[1][0]
     assert ret[0][1] == ret[1][1]
     # row blocks: whole statistics blocks, contiguous, covering [0, N)
