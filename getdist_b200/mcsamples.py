@@ -152,6 +152,30 @@ class _SpecView:
         return v.item() if hasattr(v, "item") and np.ndim(v) == 0 else v
 
 
+def _overlapped(device_call, host_work):
+    """Run `device_call` (a ctypes call into the library: it releases the GIL) in a worker thread while this thread does
+    `host_work`; returns both results.  An exception of either side is re-raised here after both have ended."""
+    import threading
+
+    box = {}
+
+    def run():
+        try:
+            box["r"] = device_call()
+        except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
+            box["e"] = e
+
+    th = threading.Thread(target=run)
+    th.start()
+    try:
+        w = host_work()
+    finally:
+        th.join()
+    if "e" in box:
+        raise box["e"]
+    return box["r"], w
+
+
 class _BatchRecord:
     """The library's result record of one density of a batch (bandwidths, status bits, contour levels ...), read like a
     dict: `d._gdk["status"]`.  The columns of the whole batch are shared; nothing is copied per density."""
@@ -1231,24 +1255,47 @@ class MCSamples:
                 r2.hx, r2.hy, r2.t_star, r2.n_brent = r.hx, r.hy, r.t_star, r.n_brent
         elif _likes:
             buf, lbuf, offsets, res = self._ctx.density2d_batch(specs, likes=True)
-        else:
-            buf, offsets, res = self._ctx.density2d_batch(specs, out=_out, device_ptr=_device_ptr)
-        if _device_ptr is not None:
+        elif _device_ptr is not None:
+            buf, offsets, res = self._ctx.density2d_batch(specs, device_ptr=_device_ptr)
             return specs, offsets, res  # grids stay on the device (density i at device_ptr + offsets[i])
+        elif len(pairs) >= 64 and hasattr(_abi, "result_buffer"):
+            # large batch: the host wraps the grids (views of the result buffer) while the library call is in flight
+            fb = specs["fine_bins"].astype(np.int64)
+            offsets = np.zeros(len(pairs), dtype=np.int64)
+            offsets[1:] = np.cumsum(fb * fb)[:-1]
+            buf = _out if _out is not None else _abi.result_buffer(int((fb * fb).sum()))
+            try:
+                (_, _, res), (out, rcol) = _overlapped(
+                    lambda: self._ctx.density2d_batch(specs, out=buf),
+                    lambda: self._wrap_2d(pairs, specs, buf, offsets, conts, cache=not kwargs))
+            except Exception:
+                for pr in pairs:  # nothing of a failed batch stays in the cache
+                    self._density2D.pop(tuple(pr), None)
+                raise
+            self._records_2d(pairs, rcol, res, cache=not kwargs)
+            return out
+        else:
+            buf, offsets, res = self._ctx.density2d_batch(specs, out=_out)
         return self._finish_2d(pairs, specs, buf, offsets, res, conts, lbuf=lbuf, masks=masks,
                                cache=not kwargs and masks is None and lbuf is None)
 
     def _finish_2d(self, pairs, specs, buf, offsets, res, conts, lbuf=None, masks=None, cache=True):
         """Density2D objects (+ the reference's warnings / errors) from the grids of a 2D batch; `buf` holds density i at
         buf[offsets[i]:][:G*G]"""
+        out, rcol = self._wrap_2d(pairs, specs, buf, offsets, conts, lbuf=lbuf, masks=masks, cache=cache)
+        self._records_2d(pairs, rcol, res, cache=cache)
+        return out
+
+    def _wrap_2d(self, pairs, specs, buf, offsets, conts, lbuf=None, masks=None, cache=True):
+        """The Density2D objects of a batch over (views of) its result buffer.  Needs nothing the device computes, so it
+        can run while the library call is still in flight; the result records are attached by _records_2d afterwards.
+        Returns (objects, the shared column dict their `_gdk` records read from)."""
         out = []
         names = self.paramNames.names
-        # plain Python scalars of the spec and result columns once per batch (a field access per pair costs microseconds)
+        # plain Python scalars of the spec columns once per batch (a field access per pair costs microseconds)
         col = {k: specs[k].tolist() for k in ("fine_bins", "xbinmin", "xbinmax", "ybinmin", "ybinmax", "bw_mode")}
-        rcol = _abi.results2d_columns(res)
-        rcol["bw_mode"], rcol["fine_bins"] = col["bw_mode"], col["fine_bins"]
+        rcol = {"bw_mode": col["bw_mode"], "fine_bins": col["fine_bins"]}
         offsets = [int(o) for o in offsets]
-        bad = _abi.ST_BIAS_NEG | _abi.ST_BW_FALLBACK | _abi.ST_SMALL_SMOOTH | _abi.ST_ZERO_MAX
         conts = list(conts)
         G0 = col["fine_bins"][0] if len(pairs) else 0
         grids = None
@@ -1256,22 +1303,8 @@ class MCSamples:
             buf.flags.writeable = False  # cache entries are read-only views into the batch buffer, see below
         if len(pairs) and all(g == G0 for g in col["fine_bins"]) and offsets == list(range(offsets[0], offsets[0] + len(pairs) * G0 * G0, G0 * G0)):
             grids = buf[offsets[0]: offsets[0] + len(pairs) * G0 * G0].reshape(len(pairs), G0, G0)  # one view, indexed per pair
-        status_col = rcol["status"]
         for n, (j, j2) in enumerate(pairs):
             parx, pary = names[j], names[j2]
-            status = status_col[n]
-            if status & bad:
-                if status & _abi.ST_BIAS_NEG:
-                    raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
-                if status & _abi.ST_BW_FALLBACK:
-                    msg = "2D kernel density bandwidth optimizer failed for %s, %s. Using fallback width" % (parx.name, pary.name)
-                    if self.raise_on_bandwidth_errors:
-                        raise BandwidthError(msg)
-                    log.warning(msg)
-                if status & _abi.ST_SMALL_SMOOTH:
-                    log.warning("fine_bins_2D not large enough for optimal density: %s, %s", parx.name, pary.name)
-                if status & _abi.ST_ZERO_MAX:
-                    raise DensitiesError("no samples in bin")
             G = col["fine_bins"][n]
             off = offsets[n]
             d = Density2D.on_linspace((col["xbinmin"][n], col["xbinmax"][n], G), (col["ybinmin"][n], col["ybinmax"][n], G),
@@ -1290,7 +1323,34 @@ class MCSamples:
                 # returns a fresh grid per call and callers normalise in place
                 self._density2D[(j, j2)] = d
             out.append(d)
-        return out
+        return out, rcol
+
+    def _records_2d(self, pairs, rcol, res, cache=True):
+        """attach the library's result records to the objects of _wrap_2d and raise / warn as the reference does"""
+        rcol.update(_abi.results2d_columns(res))
+        bad = _abi.ST_BIAS_NEG | _abi.ST_BW_FALLBACK | _abi.ST_SMALL_SMOOTH | _abi.ST_ZERO_MAX
+        names = self.paramNames.names
+        try:
+            for n, status in enumerate(rcol["status"]):
+                if not status & bad:
+                    continue
+                parx, pary = names[pairs[n][0]], names[pairs[n][1]]
+                if status & _abi.ST_BIAS_NEG:
+                    raise Exception("bias not positive definite")  # kde_bandwidth.py:230-231 (propagates in the reference)
+                if status & _abi.ST_BW_FALLBACK:
+                    msg = "2D kernel density bandwidth optimizer failed for %s, %s. Using fallback width" % (parx.name, pary.name)
+                    if self.raise_on_bandwidth_errors:
+                        raise BandwidthError(msg)
+                    log.warning(msg)
+                if status & _abi.ST_SMALL_SMOOTH:
+                    log.warning("fine_bins_2D not large enough for optimal density: %s, %s", parx.name, pary.name)
+                if status & _abi.ST_ZERO_MAX:
+                    raise DensitiesError("no samples in bin")
+        except Exception:
+            if cache:  # nothing of a failed batch stays behind
+                for pr in pairs:
+                    self._density2D.pop(tuple(pr), None)
+            raise
 
     # ------------------------------------------------------------------ marginalised limits (SURVEY s8f-2)
     def setMargeLimits(self, params=None, max_frac_twotail=None):

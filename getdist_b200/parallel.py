@@ -283,6 +283,17 @@ def _res1d_table(res):
 
 
 def _res2d_table(res):
+    import ctypes
+
+    from ._abi import RES2D_DTYPE
+
+    if isinstance(res, ctypes.Array):  # the library's record array: column-wise, no Python loop
+        a = np.frombuffer(res, dtype=RES2D_DTYPE)
+        out = np.empty((a.size, 13))
+        for i, k in enumerate(("hx", "hy", "c", "rx", "ry", "t_star", "winw", "status", "n_brent")):
+            out[:, i] = a[k]
+        out[:, 9:13] = a["levels"]
+        return out
     return np.array([[r.hx, r.hy, r.c, r.rx, r.ry, r.t_star, r.winw, r.status, r.n_brent] + list(r.levels) for r in res],
                     dtype=np.float64).reshape(-1, 13)
 
@@ -359,36 +370,53 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
                 tab[: len(my1d)] = _res1d_table(res)
         out["res1d"] = pg.all_gather_array(tab)
     t2 = time.perf_counter()
-    # ---- 2D: the window holds every pair's grid in the caller's pair order
+    # ---- 2D: the gathered buffer holds every pair's grid in the caller's pair order
+    wrapped = None
     if pairs:
-        specs = mc._specs_2d_batch(pairs, {})
         conts = [float(c) for c in list(mc.contours[:4])]
-        specs["n_contours"] = len(conts)
-        for k, c in enumerate(conts):
-            specs["contours"][:, k] = c
-        fb = specs["fine_bins"].astype(np.int64)
+        fb = mc._fine_bins_2d_all(pairs)
         offs = np.zeros(len(pairs), dtype=np.int64)
         offs[1:] = np.cumsum(fb * fb)[:-1]
         total = int((fb * fb).sum())
         where = {pr: n for n, pr in enumerate(pairs)}
         mine = np.array([where[pr] for pr in my2d], dtype=np.int64)
-        tab = np.zeros((per, 13))
+        tab = np.zeros((per, 14))
+        n1 = world * max1d * int(mc.fine_bins) if do_1d else 0
         if host_gather and shared is None:
             shared = pg.shared_results(total * 8, int(root))
-        if host_gather and shared.size < (world * max1d * int(mc.fine_bins) if do_1d else 0) + total:
+        if host_gather and shared.size < n1 + total:
             raise RuntimeError("shared result buffer smaller than the gathered layout")
-        n1 = world * max1d * int(mc.fine_bins) if do_1d else 0
+        if not host_gather:
+            base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
+
+        def full_specs():
+            sp_all = mc._specs_2d_batch(pairs, {})
+            assert np.array_equal(sp_all["fine_bins"].astype(np.int64), fb)
+            return sp_all
+
+        def wrap_all():  # host side of the wrapping rank: runs while this rank's library call is in flight
+            return mc._wrap_2d(pairs, full_specs(), shared[n1: n1 + total], offs, conts)
+
         if len(mine):
-            sp = np.ascontiguousarray(specs[mine])
+            sp = mc._specs_2d_batch(my2d, {})  # only this rank's pairs on the critical path
+            sp["n_contours"] = len(conts)
+            for k, c in enumerate(conts):
+                sp["contours"][:, k] = c
             sp["anchor_hint"] = np.asarray(hints, dtype=np.int32)
             if host_gather:  # every rank copies its grids into the node's shared host buffer over its own PCIe link
-                _, _, res = mc._ctx.density2d_batch(sp, out=shared[n1: n1 + total], offsets=offs[mine])
+                call = lambda: mc._ctx.density2d_batch(sp, out=shared[n1: n1 + total], offsets=offs[mine])  # noqa: E731
+                if mine_host:
+                    from .mcsamples import _overlapped
+
+                    (_, _, res), wrapped = _overlapped(call, wrap_all)
+                else:
+                    _, _, res = call()
             else:
-                base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
                 _, _, res = mc._ctx.density2d_batch(sp, device_ptr=base2, offsets=offs[mine], peers=True)
-            tab[: len(mine)] = _res2d_table(res)
-        elif not host_gather:
-            base2 = pg.map_window(mc._ctx, _abi.GDK_WIN_G2, total * 8)
+            tab[: len(mine), :13] = _res2d_table(res)
+            tab[: len(mine), 13] = sp["bw_mode"]
+        elif host_gather and mine_host:
+            wrapped = wrap_all()
         out["res2d"] = pg.all_gather_array(tab)
     t3 = time.perf_counter()
     pg.barrier()  # every rank's stores into every window have completed (the library synchronised its streams)
@@ -416,18 +444,18 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
                 rows2d[pr] = out["res2d"][r][k]
         if mine_host:
             tr = time.perf_counter()
-            if host_gather:
-                buf = shared[n1: n1 + total]  # already on this host: every rank copied its share
-            else:
-                # the copy runs while the host wraps the grids (views of the buffer: nothing reads it before the sync below)
-                buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total), sync=False)
-            tab2 = np.array([rows2d[pr] for pr in pairs])  # (pairs, 13) in the caller's order -> result columns
+            tab2 = np.array([rows2d[pr] for pr in pairs])  # (pairs, 14) in the caller's order -> result columns
             names2 = ("hx", "hy", "c", "rx", "ry", "t_star", "winw", "status", "n_brent")
             rcol = {k: (tab2[:, i].astype(np.int64).tolist() if k in ("winw", "status", "n_brent") else tab2[:, i].tolist())
                     for i, k in enumerate(names2)}
             rcol["levels"] = tab2[:, 9:13].tolist()
-            d2 = mc._finish_2d(pairs, specs, buf, offs, rcol, conts)
-            if not host_gather:
+            if host_gather:  # the grids are already on this host (every rank copied its share) and wrapped
+                d2, cols = wrapped
+                mc._records_2d(pairs, cols, rcol)
+            else:
+                # the copy runs while the host wraps the grids (views of the buffer: nothing reads it before the sync below)
+                buf = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, _abi.result_buffer(total), sync=False)
+                d2 = mc._finish_2d(pairs, full_specs(), buf, offs, rcol, conts)
                 mc._ctx.stream_sync()
             t_d2h = time.perf_counter() - tr
         elif not to_host:
