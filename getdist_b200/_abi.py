@@ -12,7 +12,7 @@ GDK_OUT_DEVICE = 1
 GDK_BW_ONLY = 2
 GDK_OUT_PEERS = 4
 GDK_WIN_G1, GDK_WIN_G2, GDK_WIN_X, GDK_WIN_STATS = 0, 1, 2, 3
-GDK_ROW_BLOCK = 131072
+GDK_ROW_BLOCK = 65536
 
 ST_BW_FALLBACK = 1
 ST_BW_FAILED_NONE = 2

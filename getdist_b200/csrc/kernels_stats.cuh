@@ -172,7 +172,7 @@ __global__ void k_fill(double* p, int64_t n, double v) {
 #define ST_T 64
 #define ST_RB 32
 #define ST_SEG 2048
-#define ST_BLOCK 131072
+#define ST_BLOCK 65536
 #define ST_SMEM ((3 * ST_RB * ST_T + 2 * ST_T) * 8)
 __device__ __forceinline__ int st_swz(int c, int k) { return ((((c >> 1) ^ (k & 15)) << 1) | (c & 1)); }
 

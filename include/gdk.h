@@ -152,7 +152,7 @@ int32_t gdk_set_samples(gdk_ctx* ctx, const double* X, int64_t N, int32_t P, int
  * pushes rows and statistics records into every imported peer window; finish (after the group's barrier) derives the
  * fixed-point weights and merges the statistics records of all row blocks -- in an order fixed by the data layout, so
  * means / covariances are bit-identical on 1 and on N ranks.                                                      */
-#define GDK_ROW_BLOCK 131072
+#define GDK_ROW_BLOCK 65536
 int32_t gdk_samples_prepare(gdk_ctx* ctx, int64_t N, int32_t P, const int64_t* chain_offsets, int32_t nchains);
 int32_t gdk_samples_upload(gdk_ctx* ctx, const double* X, int64_t row_stride, int64_t col_stride, const double* w,
                            int64_t row_begin, int64_t row_end);

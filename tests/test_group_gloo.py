@@ -162,4 +162,4 @@ def test_group_prefetch_world2(P, root):
     assert ret[0][1] == ret[1][1]
     # row blocks: whole statistics blocks, contiguous, covering [0, N)
     (a0, a1), (b0, b1) = ret[0][2], ret[1][2]
-    assert a0 == 0 and a1 == b0 and b1 == 10_000_000 and a1 % 131072 == 0
+    assert a0 == 0 and a1 == b0 and b1 == 10_000_000 and a1 % 65536 == 0
