@@ -246,11 +246,23 @@ class PeerGroup:
             sg["mm"] = mmap.mmap(sg["fd"], size)
             os.close(sg["fd"])
             sg["arr"] = np.frombuffer(sg["mm"], dtype=np.float64)
-            _abi.host_register(sg["arr"])
+            ok = 1.0
+            try:
+                _abi.host_register(sg["arr"])
+            except Exception:  # page-locking refused (limits on locked memory): every rank must learn it
+                ok = 0.0
             segs[name] = sg
-            self.barrier()  # everybody has it open: the name can go
+            allok = self.all_gather_array(np.array([ok]))  # also the rendezvous after which the name can go
             if self.rank == root:
                 os.unlink("/dev/shm/" + name)
+            if allok.min() < 1.0:
+                if ok:
+                    _abi.host_unregister(sg["arr"])
+                sg["arr"] = None
+                sg["mm"].close()
+                sg["mm"] = None
+                self.host_gather = False  # from now on: gather through the root's device window
+                return None
         if self.rank != root:
             return sg["arr"]
         sg["busy"] = True
@@ -359,6 +371,9 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
             # one host buffer for the node: [1D rows per rank | 2D grids in the caller's pair order]
             fbq = mc._fine_bins_2d_all(pairs) if pairs else np.zeros(0, dtype=np.int64)
             shared = pg.shared_results((n1 + int((fbq * fbq).sum())) * 8, int(root))
+            if shared is None:
+                host_gather = False
+        if host_gather:
             if my1d:
                 _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d],
                                                  out=shared[rank * max1d * F: (rank * max1d + len(my1d)) * F].reshape(len(my1d), F), stride=F)
@@ -384,6 +399,8 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
         n1 = world * max1d * int(mc.fine_bins) if do_1d else 0
         if host_gather and shared is None:
             shared = pg.shared_results(total * 8, int(root))
+            if shared is None:
+                host_gather = False
         if host_gather and shared.size < n1 + total:
             raise RuntimeError("shared result buffer smaller than the gathered layout")
         if not host_gather:
