@@ -622,7 +622,11 @@ def run_ours(args):
     # states the per-unit figures).  achieved = work per launch / average launch time.  `traffic` = dram bytes per launch
     # from the ncu --set full capture of exactly this workload (profiles/); other sizes have no capture -> null.
     c2 = (args.workload == "c2" and N == 10_000_000 and P == 64 and world == 1)
-    ncu_traffic = {"k_bin8c": 5.96e9, "k_bucket_records": 13.49e9, "k_hist2d_records": 13.30e9, "k_hist1d_tma": 5.97e9}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r4u_ncu_full_summary.csv (ncu --set full, this workload)
+    ncu_traffic = {"k_bin8c": 5.96e9, "k_bucket_records": 13.49e9, "k_hist2d_records": 13.30e9, "k_hist1d_tma": 5.83e9,
+                   "k_qhist": 6.14e9, "k_shear_minmax_tma": 9.45e9, "k_shear_hist_w": 8.70e9,  # average over the step's three launches (25.04 + 0.82 + 0.24 GB)
+                    "k_bw2d": 27.37e9,
+                   "k_xform_rows": 4.17e9, "k_xform_cols": 5.26e9, "k_conv2d<0>": 0.36e9, "k_conv2d<1>": 0.79e9, "k_contours2d": 1.49e9}
     from getdist_b200.parallel import partition_triangle
 
     n_my_pairs = len(partition_triangle(idx, pairs, rank, world)[1])
@@ -640,6 +644,8 @@ def run_ours(args):
         gbs = st["bytes"] / (st["ms"] * 1e-3) / 1e9
         ent.update({"hbm_GBs": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "algorithmic_bytes_per_launch": st["bytes"] / st["launches"],
                     "traffic": ncu_traffic.get(nm) if c2 else None})
+        if c2 and nm in ncu_traffic and st["bytes"] > 0:
+            ent["traffic_over_algorithmic"] = round(ncu_traffic[nm] / (st["bytes"] / st["launches"]), 2)
         if nm in fp64_kernels and st["flops"] > 0:
             tf = st["flops"] / (st["ms"] * 1e-3) / 1e12
             ent.update({"bound": "fp64", "achieved": round(tf, 3), "peak": round(fp64_peak, 2), "unit": "TFLOP/s", "frac": round(tf / fp64_peak, 4),
@@ -671,7 +677,7 @@ def run_ours(args):
     if k1 and k1["ms"] > 0:
         a1 = k1["bytes"] / (k1["ms"] * 1e-3) / 1e9
         hist1d = {"kernel": "k_hist1d_tma", "bound": "hbm", "achieved": round(a1, 1), "peak": peak, "unit": "GB/s", "frac": round(a1 / peak, 4),
-                  "algorithmic_bytes": k1["bytes"] / k1["launches"], "kernel_ms": k1["ms"] / k1["launches"], "traffic": 5.97e9 if c2 else None}
+                  "algorithmic_bytes": k1["bytes"] / k1["launches"], "kernel_ms": k1["ms"] / k1["launches"], "traffic": 5.83e9 if c2 else None}
     stats_pass = None
     if stats_line:
         gbs = stats_line["bytes"] / (stats_line["ms"] * 1e-3) / 1e9

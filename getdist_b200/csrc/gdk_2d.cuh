@@ -790,9 +790,16 @@ static int density2d_chunk(gdk_ctx* ctx, int n, const gdk_spec2d* specs, double*
             int g1 = g0;
             while (g1 < ngroups && sgroups[g1].nj == sgroups[g0].nj) g1++;
             const int nj = sgroups[g0].nj;
-            double colsum = 0;  // per group: x_i + nj partner columns + the weights
-            for (int q = g0; q < g1; q++) colsum += 2.0 + sgroups[q].nj;
-            KernelTimer kt(ctx, GDK_K_SHEAR_HIST, (double)ctx->N * colsum * 8.0, (double)ctx->N * (g1 - g0) * nj * 3.0);
+            // algorithmic bytes of the launch: the MINIMUM sweep -- every distinct column its groups touch once, plus the
+            // weights (not what the grouping happens to re-read: groups share columns, the rest comes out of L2)
+            std::vector<char> seen(ctx->P, 0);
+            double ncols = 1.0;
+            for (int q = g0; q < g1; q++) {
+                if (!seen[sgroups[q].pi]) seen[sgroups[q].pi] = 1, ncols += 1.0;
+                for (int k = 0; k < sgroups[q].nj; k++)
+                    if (!seen[sgroups[q].pj[k]]) seen[sgroups[q].pj[k]] = 1, ncols += 1.0;
+            }
+            KernelTimer kt(ctx, GDK_K_SHEAR_HIST, (double)ctx->N * ncols * 8.0, (double)ctx->N * (g1 - g0) * nj * 3.0);
             dim3 g((unsigned)(g1 - g0), (unsigned)nhseg);
 #define GDK_LAUNCH_SHW(NP_, W_)                                                                                               \
     case NP_: {                                                                                                               \
