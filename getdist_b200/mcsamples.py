@@ -1300,6 +1300,7 @@ class MCSamples:
         G0 = col["fine_bins"][0] if len(pairs) else 0
         grids = None
         if cache:
+            buf = buf.view()
             buf.flags.writeable = False  # cache entries are read-only views into the batch buffer, see below
         if len(pairs) and all(g == G0 for g in col["fine_bins"]) and offsets == list(range(offsets[0], offsets[0] + len(pairs) * G0 * G0, G0 * G0)):
             grids = buf[offsets[0]: offsets[0] + len(pairs) * G0 * G0].reshape(len(pairs), G0, G0)  # one view, indexed per pair

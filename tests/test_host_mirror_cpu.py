@@ -201,3 +201,42 @@ def test_use_effective_samples_2D_is_inert(fake_ctx):
     for (j, j2) in pairs:
         x, y = a._spec_2d(j, j2, {}), b._spec_2d(j, j2, {})
         assert all(getattr(x, f) == getattr(y, f) for f, _ in _abi.Spec2D._fields_ if f != "contours")
+
+
+def test_fine_bins_all_matches_the_planner(fake_ctx):
+    """the light fine_bins_2D rule used for the gathered multi-GPU layout == the planner's column, on strongly
+    correlated data where the grids are scaled up (mcsamples.py:1811-1818)"""
+    from getdist_b200 import MCSamples
+
+    rng = np.random.default_rng(3)
+    P, N = 10, 4000
+    L = np.linalg.cholesky(0.95 ** np.abs(np.subtract.outer(np.arange(P), np.arange(P))))
+    X = rng.standard_normal((N, P)).dot(L.T)
+    mc = MCSamples(samples=X, names=["p%d" % i for i in range(P)], sampler="uncorrelated", settings={"fine_bins_2D": 256})
+    idx, pairs = mc.triangle_pairs()
+    mc._ensure_param_ranges(idx)
+    fb = mc._fine_bins_2d_all(pairs)
+    assert np.array_equal(fb, mc._specs_2d_batch(pairs, {})["fine_bins"].astype(np.int64))
+    assert fb.max() > 256 and fb.min() == 256
+
+
+def test_batch_record_and_overlap_helper():
+    from getdist_b200.mcsamples import _BatchRecord, _overlapped
+
+    cols = {"status": [0, 4], "hx": [0.1, 0.2], "levels": [[1.0, 2.0, 3.0, 0.0], [4.0, 5.0, 6.0, 0.0]]}
+    r = _BatchRecord(cols, 1, [0.68, 0.95, 0.99])
+    assert r["status"] == 4 and r["hx"] == 0.2 and r["levels"] == ([0.68, 0.95, 0.99], [4.0, 5.0, 6.0])
+    assert "levels" in r and "hx" in r and "nope" not in r and r.get("nope", 7) == 7
+    assert _BatchRecord(cols, 0, [])["levels"] is None
+    cols["late"] = [10, 11]  # records attached after the wrapping (the library call was still in flight)
+    assert r["late"] == 11
+    # both sides run; results come back in order; an exception of the device side surfaces after the host work ended
+    done = []
+    assert _overlapped(lambda: "dev", lambda: done.append(1) or "host") == ("dev", "host") and done == [1]
+
+    def boom():
+        raise ValueError("device side failed")
+
+    with pytest.raises(ValueError):
+        _overlapped(boom, lambda: done.append(2))
+    assert done == [1, 2]

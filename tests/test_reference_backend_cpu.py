@@ -28,7 +28,7 @@ class FakeContext2D(FakeContext):
         fb = specs["fine_bins"].astype(np.int64)
         offsets = np.zeros(len(specs), dtype=np.int64)
         offsets[1:] = np.cumsum(fb * fb)[:-1]
-        buf = np.empty(int((fb * fb).sum()))
+        buf = np.empty(int((fb * fb).sum())) if out is None else out  # large batches hand in the buffer they wrap
         res = []
         for sp, off in zip(specs, offsets):
             d = type(self).oracle.density_2d(int(sp["px"]), int(sp["py"]))
@@ -156,3 +156,29 @@ def test_pickle_and_copy(backend, getdist_ref):
     g = mc._gpu()
     mc.reweightAddingLogLikes(np.zeros(mc.numrows)) if mc.loglikes is not None else mc.setSamples(mc.samples, mc.weights * 2.0)
     assert mc._gpu() is not g
+
+
+def test_large_batch_is_wrapped_while_the_call_is_in_flight(hs, monkeypatch):  # noqa: F811
+    """>= 64 pairs: the mirror allocates the result buffer, wraps views of it in the calling thread while the library
+    call runs in a worker thread, and attaches the result records afterwards (mcsamples._overlapped)"""
+    from getdist_b200 import MCSamples, _abi
+    from oracle.getdist_oracle import OracleSamples
+
+    FakeContext2D.hs = hs
+    monkeypatch.setattr(_abi, "Context", FakeContext2D)
+    rng = np.random.default_rng(8)
+    P, N = 12, 2500
+    X = rng.standard_normal((N, P)) * np.arange(1, P + 1)
+    names = ["p%d" % i for i in range(P)]
+    FakeContext2D.oracle = OracleSamples(X, None, names=names, sampler="uncorrelated", settings={"fine_bins_2D": 64})
+    mc = MCSamples(samples=X, names=names, sampler="uncorrelated", settings={"fine_bins_2D": 64})
+    idx, pairs = mc.triangle_pairs()
+    assert len(pairs) >= 64
+    d2 = mc._densities_2d(pairs)
+    for (a, b), d in zip(pairs[::7], d2[::7]):
+        ref = FakeContext2D.oracle.density_2d(a, b)
+        assert np.array_equal(d.P, ref.P) and not d.P.flags.writeable
+        assert d._gdk["status"] == 0 and len(d._gdk["levels"][1]) == 3
+        assert mc._density2D[(a, b)] is d
+    fresh = mc.get2DDensityGridData(pairs[3][0], pairs[3][1], num_plot_contours=2)
+    assert fresh.P.flags.writeable and len(fresh.contours) == 2
