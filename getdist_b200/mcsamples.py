@@ -21,6 +21,10 @@ caches that the serial ``get1DDensity`` / ``get2DDensity`` calls (as issued by g
 caller that never calls it still gets batches: the first cache miss of ``get1DDensity`` / ``get2DDensityGridData``
 triggers a batched launch for the analysis' parameter set (``auto_prefetch``).
 
+Multi-GPU (one process per GPU): ``MCSamples(..., process_group=PeerGroup(...))`` uploads 1/world of the rows per rank
+(the peers receive them over NVLink) and ``prefetch_triangle(root=...)`` computes 1/world of the densities per rank;
+see getdist_b200/parallel.py and DESIGN.md s6.
+
 Also here: ``getRawNDDensityGridData`` (mcsamples.py:2098-2235) on the histogram kernels and the
 MeanVar / Gelman-Rubin / split-quantile parts of ``getConvergeTests`` (mcsamples.py:964-1034) on the per-chain
 moment and order-statistics kernels.
