@@ -70,6 +70,7 @@ class Result2D(C.Structure):
 RES2D_DTYPE = np.dtype([("hx", "f8"), ("hy", "f8"), ("c", "f8"), ("rx", "f8"), ("ry", "f8"), ("t_star", "f8"), ("winw", "i4"),
                         ("status", "u4"), ("n_brent", "i4"), ("pad", "i4"), ("levels", "f8", (4,))])
 assert RES2D_DTYPE.itemsize == C.sizeof(Result2D)
+SPEC2D_DTYPE = np.dtype(Spec2D)  # the structured-array layout of gdk_spec2d (converted once: the planner builds one per batch)
 
 
 def results2d_columns(res):
@@ -419,7 +420,7 @@ class Context:
             self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(device_ptr), _ptr(offsets),
                                                   C.cast(res, C.c_void_p), GDK_OUT_PEERS if peers else GDK_OUT_DEVICE),
                      "gdk_density2d_batch")
-            return None, offsets, list(res)
+            return None, offsets, res  # the ctypes array of records (read column-wise by the callers)
         if out is None:
             out = result_buffer(total)
         self._ck(self.lib.gdk_density2d_batch(self.h, n, C.cast(arr, C.c_void_p), _ptr(out), _ptr(offsets),

@@ -761,47 +761,45 @@ class MCSamples:
         if not todo:
             return
         fr = self._range_fracs()
-        q = self._ctx.weighted_quantiles(todo, fr)
-        for row, j in zip(q, todo):
-            self._finish_param(self.paramNames.names[j], j, row)
+        self._finish_params(todo, self._ctx.weighted_quantiles(todo, fr))
 
     def _finish_param(self, par, j, confids):
-        par.err = self.sddev[j]
-        par.mean = self.means[j]
-        par.param_min = self._xmin[j]
-        par.param_max = self._xmax[j]
-        confids = np.array(confids, dtype=np.float64)
-        par.range_min, par.range_max = confids[0:2]
-        confids[1:-1] = confids[2:]
-        confids[0] = par.param_min
-        confids[-1] = par.param_max
-        diffs = confids[4:] - confids[:-4]
-        scale = np.min(diffs) / 1.049
-        if np.all(diffs > par.err * 1.049) and np.all(diffs < scale * 1.5):
-            par.sigma_range = scale
-        else:
-            par.sigma_range = min(par.err, scale)
+        self._finish_params([j], [confids])
+
+    def _finish_params(self, js, table):
+        """The scalar range / limit logic of _initParam (mcsamples.py:1438-1484) for a set of parameters at once:
+        row k of `table` holds the 11 order statistics of parameter js[k] (_range_fracs).  Written as array
+        expressions over the parameters -- the same IEEE operations per element as the per-parameter statements of
+        the reference -- because a 64-parameter triangle pays for 64 x a dozen tiny numpy calls otherwise."""
         if self.range_ND_contour >= 0 and self.likeStats:
             raise NotImplementedError("range_ND_contour needs likeStats (mcsamples.py:1455-1459): use the reference")
-        smooth_1D = par.sigma_range * 0.4
-        par.has_limits_bot = par.limmin is not None
-        par.has_limits_top = par.limmax is not None
-        if par.has_limits_bot:
-            if par.range_min - par.limmin > 2 * smooth_1D and par.param_min - par.limmin > smooth_1D:
-                par.has_limits_bot = False
-            else:
-                par.range_min = par.limmin
-        if par.has_limits_top:
-            if par.limmax - par.range_max > 2 * smooth_1D and par.limmax - par.param_max > smooth_1D:
-                par.has_limits_top = False
-            else:
-                par.range_max = par.limmax
-        if not par.has_limits_bot:
-            par.range_min -= smooth_1D * 2
-        if not par.has_limits_top:
-            par.range_max += smooth_1D * 2
-        par.has_limits = par.has_limits_top or par.has_limits_bot
-        par._ranges_ready = True
+        js = np.asarray(js, dtype=np.int64)
+        pars = [self.paramNames.names[j] for j in js]
+        q = np.asarray(table, dtype=np.float64).reshape(len(pars), -1)
+        err, mean, pmin, pmax = self.sddev[js], self.means[js], self._xmin[js], self._xmax[js]
+        rmin, rmax = q[:, 0], q[:, 1]
+        conf = np.empty((len(pars), q.shape[1]))  # [param_min, the tail quantiles, param_max]
+        conf[:, 0], conf[:, 1:-1], conf[:, -1] = pmin, q[:, 2:], pmax
+        diffs = conf[:, 4:] - conf[:, :-4]
+        scale = diffs.min(axis=1) / 1.049
+        regular = np.all(diffs > (err * 1.049)[:, None], axis=1) & np.all(diffs < (scale * 1.5)[:, None], axis=1)
+        sigma = np.where(regular, scale, np.minimum(err, scale))
+        smooth = sigma * 0.4
+        lo = np.array([np.nan if p.limmin is None else p.limmin for p in pars], dtype=np.float64)
+        hi = np.array([np.nan if p.limmax is None else p.limmax for p in pars], dtype=np.float64)
+        with np.errstate(invalid="ignore"):
+            # a hard limit far outside the samples is dropped (mcsamples.py:1465-1476), otherwise the range snaps to it
+            bot = ~np.isnan(lo) & ~((rmin - lo > 2 * smooth) & (pmin - lo > smooth))
+            top = ~np.isnan(hi) & ~((hi - rmax > 2 * smooth) & (hi - pmax > smooth))
+        rmin = np.where(bot, lo, rmin - smooth * 2)
+        rmax = np.where(top, hi, rmax + smooth * 2)
+        for k, par in enumerate(pars):
+            par.err, par.mean, par.param_min, par.param_max = err[k], mean[k], pmin[k], pmax[k]
+            par.sigma_range = sigma[k]
+            par.range_min, par.range_max = rmin[k], rmax[k]
+            par.has_limits_bot, par.has_limits_top = bool(bot[k]), bool(top[k])
+            par.has_limits = par.has_limits_bot or par.has_limits_top
+            par._ranges_ready = True
 
     def _initParamRanges(self, j, paramConfid=None):
         j, par = self._parAndNumber(j)
@@ -1147,7 +1145,7 @@ class MCSamples:
         ylo, yhi = geom(jy)
         fwx = (xhi - xlo) / (fine - 1)
         fwy = (yhi - ylo) / (fine - 1)
-        sp = np.zeros(n, dtype=np.dtype(_abi.Spec2D))
+        sp = np.zeros(n, dtype=_abi.SPEC2D_DTYPE)
         sp["px"], sp["py"] = jx, jy
         sp["fine_bins"], sp["base_fine_bins"] = fine, base
         sp["xbinmin"], sp["xbinmax"], sp["ybinmin"], sp["ybinmax"] = xlo, xhi, ylo, yhi
@@ -1203,11 +1201,12 @@ class MCSamples:
                 sp["ry_fixed"] = smooth * fine / nbin2D
         return sp
 
-    def _fine_bins_2d_all(self, pairs):
+    def _fine_bins_2d_all(self, pairs, jx=None, jy=None):
         """fine_bins of every pair (mcsamples.py:1811-1818: scaled up for strongly correlated pairs): from the correlation
-        matrix and the settings alone"""
-        jx = np.array([p[0] for p in pairs], dtype=np.int64)
-        jy = np.array([p[1] for p in pairs], dtype=np.int64)
+        matrix and the settings alone (jx / jy: the pairs' columns as index arrays, where the caller keeps them)"""
+        if jx is None:
+            jx = np.array([p[0] for p in pairs], dtype=np.int64)
+            jy = np.array([p[1] for p in pairs], dtype=np.int64)
         base = int(self.fine_bins_2D)
         corr = self.getCorrelationMatrix()[jy, jx].copy()
         one = np.abs(np.abs(corr) - 1.0) <= 1e-8

@@ -27,17 +27,73 @@ def split_pairs(idx, pairs, world):
     """Pairs grouped by rank so that every anchor's pairs stay on one rank (each rank then sweeps P/world full
     32-lane jobs instead of P partly filled ones).  Returns (lists, hints): hints[r][k] = 1 if the anchor of
     lists[r][k] is its x parameter, 2 if it is its y parameter (gdk_spec2d.anchor_hint)."""
-    P = len(idx)
-    pos = {p: n for n, p in enumerate(idx)}
-    blk = (P + world - 1) // world
-    lists = [[] for _ in range(world)]
-    hints = [[] for _ in range(world)]
-    for (a, b) in pairs:
-        ap = _anchor_position(pos[a], pos[b], P)
-        r = min(ap // blk, world - 1)
-        lists[r].append((a, b))
-        hints[r].append(1 if ap == pos[a] else 2)
+    owner, hint = _pair_owners(idx, pairs, world)
+    lists, hints = [], []
+    for r in range(world):
+        sel = np.nonzero(owner == r)[0].tolist()
+        lists.append([pairs[n] for n in sel])
+        hints.append(hint[sel].tolist())
     return lists, hints
+
+
+def _pair_owners(idx, pairs, world):
+    """(owner rank, anchor hint) of every pair, as arrays in the caller's pair order: _anchor_position and the block
+    rule of split_pairs for all pairs at once (a P = 256 triangle has 32 640 of them)"""
+    P = len(idx)
+    if not len(pairs):
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    lut = {p: n for n, p in enumerate(idx)}
+    pa = np.fromiter((lut[a] for a, _ in pairs), dtype=np.int64, count=len(pairs))
+    pb = np.fromiter((lut[b] for _, b in pairs), dtype=np.int64, count=len(pairs))
+    d = (pb - pa) % P
+    first = (2 * d < P) | ((2 * d == P) & (pa < pb))
+    anchor = np.where(first, pa, pb)
+    blk = (P + world - 1) // world
+    return np.minimum(anchor // blk, world - 1), np.where(first, 1, 2)
+
+
+class TrianglePlan:
+    """Everything about the partition of a triangle over the ranks that depends only on the parameter list and the world
+    size: the pairs in the caller's order, their owners, each rank's list with its anchor hints, the padded per-rank
+    counts and, for every density, its (rank, slot) in the gathered tables.  Built once per (parameter list, world) and
+    kept (`triangle_plan`): a step of a 64-parameter triangle on 8 ranks is 20 ms, the Python loops over its 2016 pairs
+    were 3 of them."""
+
+    def __init__(self, idx, world, do_2d=True):
+        self.idx, self.world = list(idx), int(world)
+        n = len(self.idx)
+        self.pairs = [(self.idx[i], self.idx[k]) for i in range(n) for k in range(i + 1, n)] if do_2d else []
+        self.max1d = (n + world - 1) // world
+        # 1D: round-robin; density n of the list is row (n % world) * max1d + n // world of the gathered rows
+        pos = np.arange(n)
+        self.rank1d, self.slot1d = pos % world, pos // world
+        self.row1d = self.rank1d * self.max1d + self.slot1d
+        self.jx = np.array([p[0] for p in self.pairs], dtype=np.int64)
+        self.jy = np.array([p[1] for p in self.pairs], dtype=np.int64)
+        owner, hint = _pair_owners(self.idx, self.pairs, world)
+        self.rank2d = owner
+        self.slot2d = np.zeros(len(self.pairs), dtype=np.int64)
+        self.mine, self.hints, self.lists = [], [], []
+        for r in range(world):
+            sel = np.nonzero(owner == r)[0]
+            self.slot2d[sel] = np.arange(sel.size)
+            self.mine.append(sel)
+            self.hints.append(hint[sel].astype(np.int32))
+            self.lists.append([self.pairs[k] for k in sel.tolist()])
+        self.per = max((m.size for m in self.mine), default=0)
+
+
+_PLANS = {}
+
+
+def triangle_plan(idx, world, do_2d=True):
+    key = (tuple(idx), int(world), bool(do_2d))
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) >= 16:
+            _PLANS.clear()
+        plan = _PLANS[key] = TrianglePlan(idx, world, do_2d)
+    return plan
 
 
 def partition_triangle(idx, pairs, rank, world, with_hints=False):
@@ -104,9 +160,13 @@ def exchange_param_ranges(mc, indices, rank, world, dist=None, device="cuda"):
     recv = torch.empty((world * per, fr.size), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(recv, send)
     table = recv.cpu().numpy()  # the host planner needs the values: the one synchronisation of this step
-    for r in range(world):
-        for k, j in enumerate(todo[r::world]):
-            mc._finish_param(mc.paramNames.names[j], j, table[r * per + k])
+    order = [j for r in range(world) for j in todo[r::world]]
+    rows = [r * per + k for r in range(world) for k in range(len(todo[r::world]))]
+    if hasattr(mc, "_finish_params"):
+        mc._finish_params(order, table[rows])
+    else:
+        for j, row in zip(order, rows):
+            mc._finish_param(mc.paramNames.names[j], j, table[row])
 
 
 def bind_to_gpu_numa(device_index):
@@ -353,35 +413,37 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     exchange_param_ranges(mc, idx, rank, world, pg.dist, pg.device)
     if mc.smooth_scale_1D <= 0 or mc.smooth_scale_2D < 0:
         mc._ensure_neff(idx)
-    pairs = [(idx[i], idx[k]) for i in range(len(idx)) for k in range(i + 1, len(idx))] if do_2d else []
-    my1d, my2d, max1d, per, hints = partition_triangle(idx, pairs, rank, world, with_hints=True) if pairs else (
-        idx[rank::world], [], (len(idx) + world - 1) // world, 0, None)
+    plan = triangle_plan(idx, world, do_2d)  # the partition: depends on the parameter list and the world size only
+    pairs, max1d, per = plan.pairs, plan.max1d, plan.per
+    my1d = idx[rank::world]
     out = {"transport": pg.transport}
     t1 = time.perf_counter()
     # ---- 1D: window rows [r * max1d, (r + 1) * max1d) belong to rank r
     d1 = []
+    specs_all = None
     if do_1d:
         F = int(mc.fine_bins)
-        specs_all = [mc._spec_1d(j, {}) for j in idx]
-        pos = {j: n for n, j in enumerate(idx)}
+        # the wrapping rank needs every spec (Density1D axes and ranges), the others only their own
+        specs_all = [mc._spec_1d(j, {}) for j in idx] if mine_host else None
+        my_specs = specs_all[rank::world] if mine_host else [mc._spec_1d(j, {}) for j in my1d]
         tab = np.zeros((max1d, 6))
         n1 = world * max1d * F
         shared = None
         if host_gather:
             # one host buffer for the node: [1D rows per rank | 2D grids in the caller's pair order]
-            fbq = mc._fine_bins_2d_all(pairs) if pairs else np.zeros(0, dtype=np.int64)
+            fbq = mc._fine_bins_2d_all(pairs, plan.jx, plan.jy) if pairs else np.zeros(0, dtype=np.int64)
             shared = pg.shared_results((n1 + int((fbq * fbq).sum())) * 8, int(root))
             if shared is None:
                 host_gather = False
         if host_gather:
             if my1d:
-                _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d],
-                                                 out=shared[rank * max1d * F: (rank * max1d + len(my1d)) * F].reshape(len(my1d), F), stride=F)
+                _, res = mc._ctx.density1d_batch(my_specs, out=shared[rank * max1d * F: (rank * max1d + len(my1d)) * F].reshape(len(my1d), F),
+                                                 stride=F)
                 tab[: len(my1d)] = _res1d_table(res)
         else:
             base1 = pg.map_window(mc._ctx, _abi.GDK_WIN_G1, n1 * 8)
             if my1d:
-                _, res = mc._ctx.density1d_batch([specs_all[pos[j]] for j in my1d], device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
+                _, res = mc._ctx.density1d_batch(my_specs, device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
                 tab[: len(my1d)] = _res1d_table(res)
         out["res1d"] = pg.all_gather_array(tab)
     t2 = time.perf_counter()
@@ -389,12 +451,11 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     wrapped = None
     if pairs:
         conts = [float(c) for c in list(mc.contours[:4])]
-        fb = mc._fine_bins_2d_all(pairs)
+        fb = mc._fine_bins_2d_all(pairs, plan.jx, plan.jy)
         offs = np.zeros(len(pairs), dtype=np.int64)
         offs[1:] = np.cumsum(fb * fb)[:-1]
         total = int((fb * fb).sum())
-        where = {pr: n for n, pr in enumerate(pairs)}
-        mine = np.array([where[pr] for pr in my2d], dtype=np.int64)
+        my2d, mine, hints = plan.lists[rank], plan.mine[rank], plan.hints[rank]
         tab = np.zeros((per, 14))
         n1 = world * max1d * int(mc.fine_bins) if do_1d else 0
         if host_gather and shared is None:
@@ -419,7 +480,7 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
             sp["n_contours"] = len(conts)
             for k, c in enumerate(conts):
                 sp["contours"][:, k] = c
-            sp["anchor_hint"] = np.asarray(hints, dtype=np.int32)
+            sp["anchor_hint"] = hints
             if host_gather:  # every rank copies its grids into the node's shared host buffer over its own PCIe link
                 call = lambda: mc._ctx.density2d_batch(sp, out=shared[n1: n1 + total], offsets=offs[mine])  # noqa: E731
                 if mine_host:
@@ -441,27 +502,19 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     d2 = []
     t_d2h = 0.0
     if do_1d:
-        rows1d = {}
-        for r in range(world):
-            for k, j in enumerate(idx[r::world]):
-                rows1d[j] = (r * max1d + k, out["res1d"][r][k])
-        if mine_host and host_gather:
-            P1 = shared[:n1].reshape(world * max1d, F)
-            d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
-        elif mine_host:
-            P1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, _abi.result_buffer(world * max1d * F).reshape(world * max1d, F))
-            d1 = mc._finish_1d(idx, specs_all, [P1[rows1d[j][0]] for j in idx], [_res1d_from(rows1d[j][1]) for j in idx])
+        if mine_host:
+            rec1 = out["res1d"][plan.rank1d, plan.slot1d]  # (len(idx), 6) in the caller's order
+            if host_gather:
+                P1 = shared[:n1].reshape(world * max1d, F)
+            else:
+                P1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, _abi.result_buffer(world * max1d * F).reshape(world * max1d, F))
+            d1 = mc._finish_1d(idx, specs_all, [P1[r] for r in plan.row1d.tolist()], [_res1d_from(row) for row in rec1])
         elif not to_host:
-            out["g1"] = dict(address=base1, stride=F, rows=[rows1d[j][0] for j in idx])
+            out["g1"] = dict(address=base1, stride=F, rows=plan.row1d.tolist())
     if pairs:
-        lists, _ = split_pairs(idx, pairs, world)
-        rows2d = {}
-        for r in range(world):
-            for k, pr in enumerate(lists[r]):
-                rows2d[pr] = out["res2d"][r][k]
         if mine_host:
             tr = time.perf_counter()
-            tab2 = np.array([rows2d[pr] for pr in pairs])  # (pairs, 14) in the caller's order -> result columns
+            tab2 = out["res2d"][plan.rank2d, plan.slot2d]  # (pairs, 14) in the caller's order -> result columns
             names2 = ("hx", "hy", "c", "rx", "ry", "t_star", "winw", "status", "n_brent")
             rcol = {k: (tab2[:, i].astype(np.int64).tolist() if k in ("winw", "status", "n_brent") else tab2[:, i].tolist())
                     for i, k in enumerate(names2)}

@@ -163,3 +163,48 @@ def test_group_prefetch_world2(P, root):
     # row blocks: whole statistics blocks, contiguous, covering [0, N)
     (a0, a1), (b0, b1) = ret[0][2], ret[1][2]
     assert a0 == 0 and a1 == b0 and b1 == 10_000_000 and a1 % 65536 == 0
+
+
+def _worker_resident(rank, world, port, P, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from getdist_b200 import MCSamples, _abi
+    from getdist_b200.parallel import PeerGroup, prefetch_triangle_group
+
+    _abi.Context = WinContext
+    rng = np.random.default_rng(7)
+    N = 3000
+    X = rng.standard_normal((N, P)) * np.arange(1, P + 1) - 3.0
+    pg = PeerGroup(dist, rank, world, device="cpu")
+    mc = MCSamples(samples=X, names=["p%d" % i for i in range(P)], sampler="uncorrelated",
+                   settings={"fine_bins": 32, "fine_bins_2D": 8}, process_group=pg)
+    idx, pairs = mc.triangle_pairs()
+    ok = True
+    for _ in range(2):  # the second call reuses the kept partition plan and the mapped windows
+        mc.invalidate_density_caches()
+        out = prefetch_triangle_group(mc, pg, idx, to_host=False)
+        F = out["g1"]["stride"]
+        g1 = mc._ctx.window_read(_abi.GDK_WIN_G1, 0, np.empty(world * ((P + world - 1) // world) * F))
+        for j, row in zip(idx, out["g1"]["rows"]):
+            ok = ok and bool(np.all(g1[row * F: (row + 1) * F] == f1(j)))
+        offs, fb = out["g2"]["offsets"], out["g2"]["fine_bins"]
+        g2 = mc._ctx.window_read(_abi.GDK_WIN_G2, 0, np.empty(int((fb * fb).sum())))
+        for (a, b), o, G in zip(pairs, offs, fb):
+            ok = ok and bool(np.all(g2[o: o + G * G] == f2(a, b)))
+        # records of every rank's densities, in rank-major padded tables
+        ok = ok and out["res1d"].shape[0] == world and out["res2d"].shape[:1] == (world,)
+    ret[rank] = bool(ok)
+    dist.barrier()
+    mc._ctx.close()
+    dist.destroy_process_group()
+
+
+def test_group_resident_results_world2():
+    """to_host=False (the bench's resident step): every rank's windows hold every grid at the rows / offsets the call
+    reports"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_resident, args=(world, _free_port(), 7, ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]

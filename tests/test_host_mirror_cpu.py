@@ -240,3 +240,50 @@ def test_batch_record_and_overlap_helper():
     with pytest.raises(ValueError):
         _overlapped(boom, lambda: done.append(2))
     assert done == [1, 2]
+
+
+def test_vectorised_param_ranges_equal_the_scalar_logic(fake_ctx):
+    """MCSamples._finish_params (all parameters of a batch as array expressions) against the oracle's per-parameter
+    restatement of _initParam's range / limit logic (mcsamples.py:1444-1484), bit for bit, over hard limits that are
+    kept, dropped (far outside the samples) and one-sided"""
+    from getdist_b200 import MCSamples
+    from oracle.getdist_oracle import ParamState, finish_param_ranges
+
+    rng = np.random.default_rng(11)
+    N, P = 3000, 24
+    X = rng.standard_normal((N, P)) * 10.0 ** rng.uniform(-3, 2, P) + rng.uniform(-5, 5, P)
+    X[:, 3] = np.abs(X[:, 3])  # piles up at a boundary
+    X[:, 4] = rng.exponential(1.0, N) ** 3  # irregular tails: the min(err, scale) branch
+    w = rng.exponential(1.0, N)
+    names = ["p%d" % i for i in range(P)]
+    ranges = {}
+    for i in range(P):
+        lo, hi = X[:, i].min(), X[:, i].max()
+        d = hi - lo
+        kind = i % 6
+        if kind == 1:
+            ranges[names[i]] = (lo - 1e-3 * d, None)  # kept
+        elif kind == 2:
+            ranges[names[i]] = (lo - 5 * d, hi + 5 * d)  # both dropped
+        elif kind == 3:
+            ranges[names[i]] = (None, hi)  # kept, at the sample maximum
+        elif kind == 4:
+            ranges[names[i]] = (lo - 1e-3 * d, hi + 5 * d)  # one kept, one dropped
+    mc = MCSamples(samples=X, weights=w, names=names, ranges=ranges, sampler="uncorrelated")
+    fr = mc._range_fracs()
+    table = mc._ctx.weighted_quantiles(list(range(P)), fr)
+    mc._finish_params(list(range(P)), table)
+    kept = 0
+    for j, par in enumerate(mc.paramNames.names):
+        ref = ParamState(name=par.name)
+        ref.limmin, ref.limmax = mc.ranges.getLower(par.name), mc.ranges.getUpper(par.name)
+        ref.err, ref.mean, ref.param_min, ref.param_max = mc.sddev[j], mc.means[j], X[:, j].min(), X[:, j].max()
+        finish_param_ranges(ref, table[j])
+        for a in ("range_min", "range_max", "sigma_range", "has_limits_bot", "has_limits_top", "has_limits", "param_min", "param_max", "err"):
+            assert getattr(par, a) == getattr(ref, a), (j, a, getattr(par, a), getattr(ref, a))
+        kept += par.has_limits
+    assert 0 < kept < P
+    # one parameter through the single-parameter entry point: same numbers
+    one = MCSamples(samples=X, weights=w, names=names, ranges=ranges, sampler="uncorrelated")
+    p5 = one._initParamRanges(4)
+    assert p5.range_min == mc.paramNames.names[4].range_min and p5.sigma_range == mc.paramNames.names[4].sigma_range
