@@ -162,19 +162,31 @@ def _overlapped(device_call, host_work):
     import threading
 
     box = {}
+    running = threading.Event()
 
     def run():
+        running.set()
         try:
             box["r"] = device_call()
         except BaseException as e:  # noqa: BLE001 - handed to the caller's thread
             box["e"] = e
 
     th = threading.Thread(target=run)
-    th.start()
+    # The worker must be inside the library call before this thread's Python work takes the interpreter lock: a thread
+    # that has to ask for the lock waits a whole switch interval (5 ms by default) each time, and the worker gives the
+    # lock up a few times on its way into the call (numpy releases it around array operations) -- measured: 1-11 ms
+    # in front of the device work.  So: the worker runs first (event), and hand-overs cost 50 us while both run.
+    import sys
+
+    interval = sys.getswitchinterval()
+    sys.setswitchinterval(5e-5)
     try:
+        th.start()
+        running.wait()
         w = host_work()
     finally:
         th.join()
+        sys.setswitchinterval(interval)
     if "e" in box:
         raise box["e"]
     return box["r"], w
