@@ -246,3 +246,42 @@ def test_kde1d_core_meanlikes(hs):
             assert np.max(np.abs(P - d.P)) < 1e-7
             assert np.max(np.abs(L - d.likes)) < 1e-6, (tag, j, np.max(np.abs(L - d.likes)))
             assert np.max(np.abs(L - g["l1/%s/%d/likes" % (tag, j)])) < 1e-6, (tag, j)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# barrier structure of the grid-stage device code: the same headers on REAL host threads under ThreadSanitizer
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="session")
+def race_check(tmp_path_factory):
+    src = os.path.join(HERE, "hostsim", "race_check.cpp")
+    exe = str(tmp_path_factory.mktemp("race") / "race_check")
+    probe = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-o", exe, src],
+                           capture_output=True, text=True, cwd=os.path.join(HERE, "hostsim"))
+    if probe.returncode != 0:
+        if "tsan" in probe.stderr.lower() or "sanitize" in probe.stderr.lower():
+            pytest.skip("no ThreadSanitizer runtime for this g++")
+        raise RuntimeError(probe.stderr[-2000:])
+    return exe
+
+
+def _run_tsan(exe, *args):
+    env = dict(os.environ, TSAN_OPTIONS="exitcode=66 halt_on_error=0")
+    return subprocess.run([exe, *args], capture_output=True, text=True, env=env, timeout=600)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128])
+def test_device_code_barriers_under_thread_sanitizer(race_check, threads):
+    """fft / dct lines, the whole 1D grid stage (k_kde1d's body: every boundary / bias / periodic / likes variant), the
+    2D bandwidth optimiser (k_bw2d's body) and the contour selection (k_contours2d's body), instantiated with a group
+    of real threads whose co.sync() is a pthread barrier: no data race (a missing barrier between a shared-scratch
+    write and another thread's read would be one), and the same numbers as the one-thread instantiation"""
+    r = _run_tsan(race_check, str(threads))
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:3000]
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "all cases agree" in r.stdout and "MISMATCH" not in r.stdout
+
+
+def test_thread_sanitizer_sees_a_missing_barrier(race_check):
+    """the checker checks itself: with the barriers turned into no-ops the FFT stages race and ThreadSanitizer says so"""
+    r = _run_tsan(race_check, "64", "--break-barriers")
+    assert r.returncode == 66 and "data race" in r.stderr and "fft.cuh" in r.stderr
