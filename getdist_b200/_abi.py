@@ -25,6 +25,7 @@ ST_AMISE_FULL = 128
 ST_BIAS_NEG = 256
 ST_NONFINITE = 512
 ST_CONTOUR_RANGE = 1024
+ST_AMISE_ABORT = 2048
 
 BW2D_FIXED, BW2D_PLAIN, BW2D_SHEAR, BW2D_RULE = 0, 1, 2, 3
 

@@ -205,6 +205,28 @@ struct Amise {
     }
 };
 
+// True if the bias term of the AMISE is negative somewhere on the faces c = +-0.99 of the search box for a width ratio
+// hx / hy between those of (ax, ay) and (bx, by), widened by a factor 1.5 either way (at fixed c the sign of the bias
+// depends on the ratio only: it is a quartic form in the widths).  Used to predict where the reference's TNC run ends in
+// its bare except (see kernel_optimizer_2d); any widening factor between 1.1 and 3 decides the measured cases alike.
+GDK_HD bool amise_bias_negative_near(const Amise& f, double ax, double ay, double bx, double by) {
+    const double ra = ax / ay, rb = bx / by;
+    const double rlo = fmin(ra, rb) / 1.5, rhi = fmax(ra, rb) * 1.5;
+    const int n = 96;
+    const double step = pow(rhi / rlo, 1.0 / (n - 1));
+    const double cb = 0.99, q = 2 * cb * cb + 1;
+    double r = rlo;
+    for (int i = 0; i < n + 2; i++) {
+        const double rr = i < n ? r : (i == n ? ra : rb);  // the two ratios themselves, whatever the spacing
+        const double r2 = rr * rr;
+        const double even = f.p40 * r2 * r2 + f.p04 + 2 * f.p22 * q * r2;
+        const double odd = 4 * cb * (f.p31 * r2 * rr + f.p13 * rr);
+        if (even + odd < 0 || even - odd < 0) return true;
+        r *= step;
+    }
+    return false;
+}
+
 // Safeguarded Newton minimisation of the AMISE over a box (nv = 2: c fixed; nv = 3: c free).
 // Variables at a bound whose gradient points outwards are frozen (active set); the Hessian of the free
 // block is shifted until positive definite; steps are backtracked on the function value.
@@ -401,7 +423,17 @@ GDK_HD Bw2dOut kernel_optimizer_2d(const C& co, const Kde2dConsts& K, const Kde2
         for (int i = 0; i < 3; i++) x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
         if (amise_minimise(am, 3, x, lo, hi)) {
             const double A3 = am(x[0], x[1], x[2]);
-            if (A3 < AM * 0.9) {
+            // The reference runs this search with scipy's TNC inside a bare try/except (kde_bandwidth.py:292-304): an
+            // exception raised by AMISE ("bias not positive definite", :230-231) at ANY trial point ends it and the result
+            // so far stands.  TNC's line searches run onto the correlation bound, so it dies there whenever the bias is
+            // negative on that face of the box near its path; a Newton iteration never leaves the region where the AMISE
+            // is finite and would hand back a minimum the reference never reports (small samples with hard edges: widths
+            // off by up to 3x, |c| up to 0.99).  amise_bias_negative_near() is that test; against the unmodified reference
+            // on random distributions it decides the 37 cases where the two used to differ and the 23 minima
+            // the reference accepted like the reference (5 260 cases), and 1 700 fresh cases without a mismatch.
+            const bool ref_aborts = amise_bias_negative_near(am, h_x, h_y, x[0], x[1]);
+            if (ref_aborts) o.status |= GDK_ST_AMISE_ABORT;
+            if (A3 < AM * 0.9 && !ref_aborts) {
                 h_x = x[0];
                 h_y = x[1];
                 c = x[2];

@@ -61,6 +61,8 @@ typedef struct gdk_ctx gdk_ctx;
 #define GDK_ST_BIAS_NEG 256u     /* 2D: AMISE bias term negative at the closed-form h (reference raises)         */
 #define GDK_ST_NONFINITE 512u    /* a non-finite intermediate was met; treated as optimiser failure              */
 #define GDK_ST_CONTOUR_RANGE 1024u /* 2D: a contour level lies outside the plotted range (densities.py:50-51)     */
+#define GDK_ST_AMISE_ABORT 2048u  /* 2D: 3-parameter AMISE search not run: bias negative at the correlation bound,
+                                     where the reference's TNC run ends in its bare except (kde_bandwidth.py:292-304) */
 
 /* 2D bandwidth branch (mcsamples.py:1347-1409) */
 #define GDK_BW2D_FIXED 0 /* smooth_scale_2D >= 0: rx, ry given in bins by the host       */
