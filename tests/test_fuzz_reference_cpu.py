@@ -208,3 +208,48 @@ def test_three_parameter_search_aborted_and_accepted_like_the_reference(hs, getd
     cases plus 22881 (minimum on the bound), and two where both sides accept the 3-parameter minimum."""
     ab, fu = _check_2d(hs, [20699, 21434, 21491, 22481, 22749, 23127, 22881, 20074, 23084])
     assert ab >= 6 and fu == 2, (ab, fu)
+
+
+def _grid_2d(rng, G, kind):
+    y, x = np.mgrid[0:G, 0:G] / (G - 1.0)
+
+    def blob(cx, cy, sx, sy, r):
+        dx, dy = (x - cx) / sx, (y - cy) / sy
+        return np.exp(-(dx * dx - 2 * r * dx * dy + dy * dy) / (2 * (1 - r * r)))
+
+    if kind == 0:
+        P = blob(rng.uniform(.3, .7), rng.uniform(.3, .7), rng.uniform(.03, .2), rng.uniform(.03, .2), rng.uniform(-.9, .9))
+    elif kind == 1:
+        P = blob(.3, .4, .05, .08, .3) + rng.uniform(.1, 1) * blob(.7, .6, .1, .04, -.5)
+    elif kind == 2:
+        P = blob(rng.uniform(-.1, .1), .5, .2, .2, 0)  # cut by the edge of the grid
+    elif kind == 3:
+        P = np.floor(blob(.5, .5, .15, .15, 0) * 8) / 8  # plateaus: thousands of exactly equal cells
+    elif kind == 4:
+        P = blob(.5, .5, .1, .1, .2) * (rng.random((G, G)) < 0.3)  # sparse, many exact zeros
+    else:
+        P = blob(.5, .5, rng.uniform(.3, 2), rng.uniform(.3, 2), 0)  # wider than the grid: levels outside the plotted range
+    return np.ascontiguousarray(P / P.max())
+
+
+def test_random_contour_levels_match_the_reference(hs, getdist_ref):  # noqa: F811
+    """contour_levels_core (the body of k_contours2d: radix selection over the bit patterns + the reference's
+    interpolation) against getdist.densities.getContourLevels on random grids -- ties, zeros, multi-modal, cut by the
+    edge; 'Contour level outside plotted ranges' must be flagged for exactly the grids where the reference raises"""
+    from getdist.densities import DensitiesError, getContourLevels
+
+    for seed in range(7000, 7060):
+        rng = np.random.default_rng(seed)
+        G = int(rng.choice([256, 384, 100, 64]))
+        P = _grid_2d(rng, G, int(rng.integers(0, 6)))
+        nc = int(rng.integers(1, 5))
+        conts = np.ascontiguousarray(np.sort(rng.choice([0.5, 0.68, 0.9, 0.95, 0.99, 0.997], size=nc, replace=False)))
+        lv = np.zeros(4)
+        status = hs.hs_contours(dptr(P), G, dptr(conts), nc, dptr(lv))
+        try:
+            want = getContourLevels(P, conts)
+        except DensitiesError:
+            assert status != 0, seed
+            continue
+        assert status == 0, seed
+        np.testing.assert_allclose(lv[:nc], want, rtol=1e-9, atol=1e-300, err_msg=str(seed))
