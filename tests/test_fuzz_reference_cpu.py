@@ -253,3 +253,85 @@ def test_random_contour_levels_match_the_reference(hs, getdist_ref):  # noqa: F8
             continue
         assert status == 0, seed
         np.testing.assert_allclose(lv[:nc], want, rtol=1e-9, atol=1e-300, err_msg=str(seed))
+
+
+def test_random_marginalised_limits_match_the_reference(fake_ctx, getdist_ref):  # noqa: F811
+    """setMargeLimits (batched _setDensitiesandMarge1D: 1D densities + one quantile call + getdist_b200/limits.py)
+    against getMargeStats of the reference on random 1D distributions, contour sets (1-4 contours) and
+    credible_interval_threshold: limit tags (two-tail / one-tail / none) identical, values to 1e-6"""
+    from getdist_b200 import MCSamples
+
+    logging.disable(logging.WARNING)
+    try:
+        for seed in range(8000, 8024):
+            rng = np.random.default_rng(seed)
+            kw = _case_1d(seed)
+            kw["settings"] = dict(fine_bins=int(rng.choice([256, 1024])),
+                                  contours=[[0.68, 0.95, 0.99], [0.68, 0.95], [0.5, 0.9, 0.99, 0.999], [0.95]][int(rng.integers(0, 4))],
+                                  credible_interval_threshold=float(rng.choice([0.05, 0.05, 0.2])))
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = getdist_ref.MCSamples(**kw)
+                want = ref.getMargeStats().parWithName("x").limits
+            mc = MCSamples(**kw)
+            have = mc.setMargeLimits()["x"]
+            assert len(have) == len(want), seed
+            for a, b in zip(want, have):
+                assert a.limitTag() == b.limitTag(), (seed, a.limitTag(), b.limitTag())
+                for u, v in ((a.lower, b.lower), (a.upper, b.upper)):
+                    assert (u is None) == (v is None), seed
+                    if u is not None:
+                        assert abs(u - v) <= 1e-6 * max(abs(u), mc.sddev[0]), (seed, u, v)
+    finally:
+        logging.disable(logging.NOTSET)
+
+
+def _lag_sums_numpy(self, jobs):
+    """numpy stand-in of gdk_lag_sums (include/gdk.h): mode 0 lag products of d = (x - mean) w, mode 1 kernel-weighted pairs"""
+    out = []
+    for (j, mode, k0, nk, mean, inv4) in jobs:
+        x, w, N = self.X[:, j], self.w, self.N
+        res = np.zeros(nk)
+        for t in range(nk):
+            k = k0 + t
+            if k >= N:
+                continue
+            if mode == 0:
+                d = (x - mean) * w
+                res[t] = np.dot(d[:N - k], d[k:])
+            else:
+                res[t] = np.dot(np.exp(-((x[:N - k] - x[k:]) ** 2) * inv4) * w[:N - k], w[k:])
+        out.append(res)
+    return out
+
+
+def test_random_mcmc_chains_neff_and_correlation_length(fake_ctx, getdist_ref, monkeypatch):  # noqa: F811
+    """the host control flow of the MCMC effective-sample estimate (threshold search, coarse steps, correlation length
+    in row and weight units; chains.py:448-466, 477-574) on random AR(1) chains with unit / integer / geometric
+    weights against the reference: the lag sums come from a numpy stand-in of the device call, everything that decides
+    WHICH lags are asked for is the product's host code"""
+    from getdist_b200 import MCSamples
+
+    monkeypatch.setattr(fake_ctx, "lag_sums", _lag_sums_numpy, raising=False)
+    for seed in range(9000, 9010):
+        rng = np.random.default_rng(seed)
+        N = int(10 ** rng.uniform(2.8, 4.0))
+        phi = float(rng.choice([0.0, 0.3, 0.7, 0.9, 0.97, 0.995]))
+        e = rng.normal(size=N)
+        x = np.empty(N)
+        x[0] = e[0]
+        for i in range(1, N):
+            x[i] = phi * x[i - 1] + np.sqrt(1 - phi * phi) * e[i]
+        wk = int(rng.integers(0, 3))
+        w = None if wk == 0 else (rng.integers(1, 8, N).astype(float) if wk == 1 else rng.geometric(0.3, N).astype(float))
+        kw = dict(samples=np.column_stack([x, rng.normal(size=N)]), weights=w, names=["x", "y"], sampler="mcmc")
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = getdist_ref.MCSamples(**kw)
+        mc = MCSamples(**kw)
+        for wu in (True, False):
+            np.testing.assert_allclose(mc.getCorrelationLength(0, weight_units=wu), ref.getCorrelationLength(0, weight_units=wu),
+                                       rtol=1e-12, err_msg=str(seed))
+        np.testing.assert_allclose(mc.getEffectiveSamplesGaussianKDE(0), ref.getEffectiveSamplesGaussianKDE(0), rtol=1e-12,
+                                   err_msg=str(seed))
+        ref.get1DDensityGridData(0)
+        mc.get1DDensityGridData(0)
+        np.testing.assert_allclose(mc.paramNames.names[0].N_eff_kde, ref.paramNames.names[0].N_eff_kde, rtol=1e-12, err_msg=str(seed))
