@@ -100,8 +100,9 @@ def test_random_1d_densities_match_the_reference(fake_ctx, getdist_ref, block): 
 
 
 def _case_2d(seed):
-    """a random weighted 2D histogram with the correlations the plain branch of getAutoBandwidth2D hands to the optimiser
-    (0, or 0.1 < |corr| <= 0.2: larger ones go through the shear branch, which calls it with 0; mcsamples.py:1347-1409)"""
+    """a random weighted 2D histogram with the correlations getAutoBandwidth2D hands to the optimiser: the sample
+    correlation itself (|corr| <= 0.2, not zeroed below 0.1) in the plain branch, exactly 0 in the shear branch
+    (mcsamples.py:1347-1409)"""
     rng = np.random.default_rng(seed)
     G = int(rng.choice([256, 256, 128, 100, 384]))
     N = int(10 ** rng.uniform(3, 5.3))
@@ -143,8 +144,8 @@ def _case_2d(seed):
     corr = float(np.corrcoef(x, y)[0, 1])
     if abs(corr) > 0.2:
         return None  # the shear branch takes such a pair
-    if abs(corr) < 0.1:
-        corr = 0.0
+    if seed % 3 == 0:
+        corr = 0.0  # what the shear branch passes for its de-correlated histogram
     do_corr = bool(rng.random() < 0.8)
     have_ft = bool(rng.random() < 0.5)
     ft = float((0.05 / neff ** (1 / 6.0)) ** 2 * rng.uniform(0.3, 3))
@@ -335,3 +336,135 @@ def test_random_mcmc_chains_neff_and_correlation_length(fake_ctx, getdist_ref, m
         ref.get1DDensityGridData(0)
         mc.get1DDensityGridData(0)
         np.testing.assert_allclose(mc.paramNames.names[0].N_eff_kde, ref.paramNames.names[0].N_eff_kde, rtol=1e-12, err_msg=str(seed))
+
+
+def _case_pair(seed):
+    """a random correlated pair (|rho| from 0 to 1) with optional hard priors the samples obey"""
+    rng = np.random.default_rng(seed)
+    N = int(10 ** rng.uniform(3, 4.3))
+    rho = float(rng.choice([0.0, 0.05, 0.15, 0.25, 0.5, 0.8, 0.93, 0.985, 0.995, -0.3, -0.9, -0.999, 1.0]))
+    u, v = rng.normal(size=N), rng.normal(size=N)
+    x = u * 10 ** rng.uniform(-2, 2) + rng.uniform(-50, 50)
+    y = (rho * u + np.sqrt(max(0.0, 1 - rho * rho)) * v) * 10 ** rng.uniform(-2, 2) + rng.uniform(-50, 50)
+    ranges = {}
+    lk = int(rng.integers(0, 6))
+    if lk == 1:
+        ranges["x"] = (float(np.quantile(x, 0.2)), None)
+    elif lk == 2:
+        ranges["y"] = (None, float(np.quantile(y, 0.7)))
+    elif lk == 3:
+        ranges["x"] = (float(np.quantile(x, 0.1)), float(np.quantile(x, 0.9)))
+        ranges["y"] = (float(np.quantile(y, 0.3)), None)
+    elif lk == 4:
+        ranges["y"] = (float(np.quantile(y, 0.1)), float(np.quantile(y, 0.95)))
+    keep = np.ones(N, bool)
+    for nm, z in (("x", x), ("y", y)):
+        lo, hi = ranges.get(nm, (None, None))
+        if lo is not None:
+            keep &= z >= lo
+        if hi is not None:
+            keep &= z <= hi
+    x, y = x[keep], y[keep]
+    w = None if rng.random() < 0.3 else rng.exponential(1.0, x.size)
+    settings = dict(fine_bins_2D=int(rng.choice([256, 256, 128, 512])), mult_bias_correction_order=int(rng.choice([0, 1, 1, 2])),
+                    max_corr_2D=float(rng.choice([0.99, 0.99, 0.95])), boundary_correction_order=int(rng.choice([0, 1])),
+                    smooth_scale_2D=float(rng.choice([-1.0, -1.0, -1.0, -0.6, 0.3, 1.5])))
+    return dict(samples=np.column_stack([x, y]), weights=w, names=["x", "y"], ranges=ranges, sampler="uncorrelated", settings=settings)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_2d_planner_and_bandwidth_tail_match_the_reference(fake_ctx, hs, getdist_ref, monkeypatch, block):  # noqa: F811
+    """The host planner (`_specs_2d_batch`: grid scaling for tight degeneracies, bin geometry, the plain / shear / rule
+    / fixed branch of getAutoBandwidth2D, the 2x2 Cholesky algebra of the shear, the kde.bin_samples range of p1) and the
+    device's `finish_bandwidth_2d` (rescaling, de-rotation of the sheared kernel, swap, bias-order rescale) against the
+    reference, with the optimiser replaced by the same dummy answer on both sides: the reference's own
+    get2DDensityGridData runs with spies on _binSamples / kde.bin_samples / KernelOptimizer2D / getAutoBandwidth2D."""
+    from getdist import mcsamples as refmod
+
+    from getdist_b200 import MCSamples, _abi
+
+    dummy = (0.043, 0.057, 0.31)
+    rec = {}
+
+    class SpyOptimizer:
+        def __init__(self, data, Neff, correlation, do_correlation=True, fallback_t=None):
+            rec["opt"] = dict(neff=Neff, corr=correlation, do_corr=do_correlation, ft=fallback_t)
+
+        def get_h(self):
+            return dummy
+
+    real_bin_samples = refmod.kde.bin_samples
+
+    def spy_bin_samples(samples, range_min=None, range_max=None, nbins=2046, edge_fac=0.1):
+        out = real_bin_samples(samples, range_min, range_max, nbins, edge_fac)
+        mx, mn = np.max(samples), np.min(samples)
+        rec.setdefault("bins", []).append(dict(rmin=range_min if range_min is not None else mn - (mx - mn) * edge_fac, R=out[1],
+                                               samples=np.array(samples)))
+        return out
+
+    monkeypatch.setattr(refmod.kde, "KernelOptimizer2D", SpyOptimizer)
+    monkeypatch.setattr(refmod.kde, "bin_samples", spy_bin_samples)
+    logging.disable(logging.WARNING)
+    try:
+        modes = set()
+        for seed in range(11000 + 10 * block, 11010 + 10 * block):
+            kw = _case_pair(seed)
+            rec.clear()
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = getdist_ref.MCSamples(**kw)
+            seen = {"bs": []}
+            real_bs, real_auto = ref._binSamples, ref.getAutoBandwidth2D
+
+            def bs(vec, par, nfine, borderfrac=0.1, _f=real_bs):
+                r = _f(vec, par, nfine, borderfrac)
+                seen["bs"].append((nfine, r[2], r[3]))
+                return r
+
+            def auto(*a, _f=real_auto, **k):
+                seen["auto"] = _f(*a, **k)
+                return seen["auto"]
+
+            ref._binSamples, ref.getAutoBandwidth2D = bs, auto
+            ref.get2DDensityGridData(0, 1, get_density=True)
+            mc = MCSamples(**kw)
+            mc._ensure_param_ranges([0, 1])
+            mc._ensure_neff([0, 1])
+            sp = mc._specs_2d_batch([(0, 1)], {})
+            s = sp[0]
+            (fx, xmin, xmax), (_, ymin, ymax) = seen["bs"][0], seen["bs"][1]
+            assert int(s["fine_bins"]) == fx, seed
+            # (the stand-in context's moments differ from the reference's in the last bit, so may the bin range)
+            np.testing.assert_allclose([s["xbinmin"], s["xbinmax"], s["ybinmin"], s["ybinmax"]], [xmin, xmax, ymin, ymax], rtol=1e-14)
+            mode = int(s["bw_mode"])
+            if kw["settings"]["smooth_scale_2D"] >= 0:
+                assert mode == _abi.BW2D_FIXED and "opt" not in rec, seed
+                continue
+            want = _abi.BW2D_RULE if "opt" not in rec else (_abi.BW2D_SHEAR if "bins" in rec else _abi.BW2D_PLAIN)
+            assert mode == want, (seed, mode, want)
+            modes.add(mode)
+            has_lim = bool(s["x_has_bot"] or s["x_has_top"] or s["y_has_bot"] or s["y_has_top"])
+            r2 = 0.0
+            if mode != _abi.BW2D_RULE:
+                assert rec["opt"]["do_corr"] == (not has_lim), seed
+                np.testing.assert_allclose(float(s["neff"]), rec["opt"]["neff"], rtol=1e-12)
+            if mode == _abi.BW2D_PLAIN:
+                # the optimiser gets the sample correlation itself (not the kernel correlation, which is zeroed below 0.1)
+                np.testing.assert_allclose(float(s["corr"]), rec["opt"]["corr"], rtol=1e-11, atol=1e-15, err_msg=str(seed))
+            if mode == _abi.BW2D_SHEAR:
+                b1, b2 = rec["bins"]
+                X = kw["samples"]
+                assert np.array_equal(X[:, int(s["shear_i"])], b1["samples"]), seed
+                p2 = float(s["r0"]) * X[:, int(s["shear_i"])] + float(s["r1"]) * X[:, int(s["shear_j"])]
+                assert np.max(np.abs(p2 - b2["samples"])) <= 1e-12 * np.max(np.abs(b2["samples"])), seed
+                np.testing.assert_allclose([float(s["p1_min"]), float(s["p1_max"]) - float(s["p1_min"])], [b1["rmin"], b1["R"]], rtol=1e-13)
+                assert rec["opt"]["corr"] == 0, seed
+                r2 = b2["R"]
+            optv = np.array([dummy[0], dummy[1], dummy[2], 0.001])
+            opti = np.zeros(3, dtype=np.int32)
+            res = _abi.Result2D()
+            spec = _abi.Spec2D.from_buffer_copy(sp[0:1].tobytes())
+            hs.hs_finish_bw2d(C.byref(spec), dptr(optv), opti.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(r2), C.byref(res))
+            np.testing.assert_allclose([res.hx, res.hy, res.c], seen["auto"], rtol=1e-11, err_msg=str((seed, mode)))
+        assert len(modes) >= 2
+    finally:
+        logging.disable(logging.NOTSET)
