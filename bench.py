@@ -724,6 +724,7 @@ def run_ours(args):
                       "pass": bool(e1 < 1e-6 and e2p < 1e-6 and e2t < 1e-5),
                       "triangle_status": {"pairs": len(pairs), "amise_corr_accepted": int(np.count_nonzero(st2 & 64)),
                                           "amise_full_accepted": int(np.count_nonzero(st2 & 128)),
+                                          "amise_full_refused_like_the_reference": int(np.count_nonzero((st2 & 2048) != 0)),
                                           "bandwidth_fallback": int(np.count_nonzero(st2 & 1)),
                                           "fallback_t": int(np.count_nonzero(st2 & 32))}}
             cpu = {"value": len(tasks) / wall, "unit": UNIT, "cores": nw, "kind": cpu_backend_kind(),
