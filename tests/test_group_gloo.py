@@ -208,3 +208,13 @@ def test_group_resident_results_world2():
     ret = mgr.dict()
     mp.spawn(_worker_resident, args=(world, _free_port(), 7, ret), nprocs=world, join=True)
     assert ret[0] and ret[1]
+
+
+def test_group_prefetch_world3_odd_sizes():
+    """three ranks, parameter counts that do not divide: padded 1D rows, anchor blocks of unequal size, gather to rank 1"""
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), 8, 1, ret), nprocs=world, join=True)
+    assert all(ret[r][0] for r in range(world))
+    assert ret[0][1] == ret[1][1] == ret[2][1]
