@@ -468,3 +468,33 @@ def test_random_2d_planner_and_bandwidth_tail_match_the_reference(fake_ctx, hs, 
         assert len(modes) >= 2
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_random_1d_mean_likelihoods_and_periodic_match_the_reference(fake_ctx, getdist_ref):  # noqa: F811
+    """get1DDensityGridData(meanlikes=True) (second weighted histogram, raw / bias-corrected ratio: mcsamples.py:1556-1561,
+    1597-1598, 1672-1684) and periodic parameters (circular convolution, :1663-1666) on random inputs"""
+    from getdist_b200 import MCSamples
+
+    logging.disable(logging.WARNING)
+    try:
+        for seed in range(12000, 12024):
+            rng = np.random.default_rng(seed)
+            kw = _case_1d(seed)
+            x = kw["samples"][:, 0]
+            periodic = seed % 3 == 0
+            if periodic:
+                x = (x - x.min()) / (x.max() - x.min()) * 2 * np.pi * (1 - 1e-9)
+                kw["samples"] = np.column_stack([x, kw["samples"][:, 1]])
+                kw["ranges"] = {"x": (0.0, 2 * np.pi, True)}
+                kw["settings"]["boundary_correction_order"] = 1
+            kw["loglikes"] = 0.5 * ((x - np.median(x)) / np.std(x)) ** 2 * rng.uniform(0.2, 2) + rng.gamma(1.5, 1.0, x.size)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = getdist_ref.MCSamples(**kw)
+            mc = MCSamples(**kw)
+            want = ref.get1DDensityGridData(0, meanlikes=not periodic)
+            have = mc.get1DDensityGridData(0, meanlikes=not periodic)
+            assert np.max(np.abs(have.P - want.P)) < 1e-6, (seed, periodic)
+            if not periodic:
+                assert np.max(np.abs(have.likes - want.likes)) < 1e-6, seed
+    finally:
+        logging.disable(logging.NOTSET)

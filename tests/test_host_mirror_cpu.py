@@ -82,20 +82,27 @@ class FakeContext:
     def density1d_batch(self, specs, out=None, device_ptr=None, likes=False):
         from oracle.getdist_oracle import bin_indices
 
-        assert device_ptr is None and not likes
+        assert device_ptr is None
         stride = max(s.fine_bins for s in specs)
-        P = np.zeros((len(specs), stride))
+        P, L = np.zeros((len(specs), stride)), np.zeros((len(specs), stride))
         res = []
         for i, s in enumerate(specs):
             F = s.fine_bins
             fw = (s.binmax - s.binmin) / (F - 1)
-            bins = np.bincount(bin_indices(self.X[:, s.param], s.binmin, fw), weights=self.w, minlength=F)
+            ix = bin_indices(self.X[:, s.param], s.binmin, fw)
+            bins = np.bincount(ix, weights=self.w, minlength=F)
             sp = Spec1D(*[getattr(s, f) for f, _ in Spec1D._fields_])
             r, row = Res1D(), np.empty(F)
-            self.hs.hs_kde1d(C.byref(sp), dptr(bins), dptr(row), C.byref(r))
+            if likes:  # second histogram with weights * exp(mean_loglike - loglikes), as gdk_set_loglikes builds it
+                lw = self.w * np.exp(self.w.dot(self.ll) / self.w.sum() - self.ll)
+                lbins, lrow = np.bincount(ix, weights=lw, minlength=F), np.empty(F)
+                self.hs.hs_kde1d_likes(C.byref(sp), dptr(bins), dptr(lbins), dptr(row), dptr(lrow), C.byref(r))
+                L[i, :F] = lrow
+            else:
+                self.hs.hs_kde1d(C.byref(sp), dptr(bins), dptr(row), C.byref(r))
             P[i, :F] = row
             res.append(r)
-        return P, res
+        return (P, L, res) if likes else (P, res)
 
 
 @pytest.fixture()
