@@ -394,7 +394,8 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
     """MCSamples.prefetch_triangle over a PeerGroup: the densities of the triangle are partitioned across the ranks
     (1D round-robin, 2D by anchor blocks), every rank computes its share from its resident copy of the samples and the
     library stores each finished grid into the gathered windows of ALL ranks over NVLink while the next group is
-    convolved; the per-density result records travel in one small all-gather.  After the closing barrier every rank
+    convolved; the per-density result records of both batches travel in ONE small all-gather, which is also the closing
+    rendezvous (a rank contributes after its library calls have returned).  After it every rank
     holds every density.  to_host=False leaves the grids in the device windows (returns their addresses and layout).
     root=r gathers to rank r only (the process that plots): the grids are stored into its window alone and the other
     ranks return empty lists -- N host copies of a gigabyte of grids share one host memory system."""
@@ -445,7 +446,9 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
             if my1d:
                 _, res = mc._ctx.density1d_batch(my_specs, device_ptr=base1 + rank * max1d * F * 8, stride=F, peers=True)
                 tab[: len(my1d)] = _res1d_table(res)
-        out["res1d"] = pg.all_gather_array(tab)
+        tab1 = tab
+        if not pairs:
+            out["res1d"] = pg.all_gather_array(tab1)
     t2 = time.perf_counter()
     # ---- 2D: the gathered buffer holds every pair's grid in the caller's pair order
     wrapped = None
@@ -495,10 +498,17 @@ def prefetch_triangle_group(mc, pg, idx, do_1d=True, do_2d=True, to_host=True, r
             tab[: len(mine), 13] = sp["bw_mode"]
         elif host_gather and mine_host:
             wrapped = wrap_all()
-        out["res2d"] = pg.all_gather_array(tab)
+        # ONE exchange for the result records of both batches.  It is also the closing rendezvous: a rank contributes after
+        # its library calls have returned (streams synchronised, its stores into every window and into the shared host
+        # segment complete), so once the gathered table is here every rank's grids are where the readers expect them
+        if do_1d:
+            both = pg.all_gather_array(np.concatenate([tab1.ravel(), tab.ravel()]))
+            out["res1d"] = both[:, : tab1.size].reshape((world,) + tab1.shape)
+            out["res2d"] = both[:, tab1.size:].reshape((world,) + tab.shape)
+        else:
+            out["res2d"] = pg.all_gather_array(tab)
     t3 = time.perf_counter()
-    pg.barrier()  # every rank's stores into every window have completed (the library synchronised its streams)
-    t4 = time.perf_counter()
+    t4 = t3
     d2 = []
     t_d2h = 0.0
     if do_1d:
