@@ -335,3 +335,30 @@ def test_mask_function():
     ref = o.density_2d(0, 1, mask_function=case["mask_function"], meanlikes=True)
     assert np.max(np.abs(d.P - ref.P)) < 1e-6 and np.max(np.abs(d.likes - ref.likes)) < 1e-5
     assert d.contours is not None and len(d.contours) == len(mc.contours)
+
+
+def test_aborted_three_parameter_search_is_decided_like_the_reference():
+    """A small sample with a hard edge that no prior declares (x = |u|): the reference's 3-parameter TNC search dies on
+    "bias not positive definite" inside its bare except and the fixed-correlation result stands (kde_bandwidth.py:292-304;
+    the oracle runs the same scipy call).  The device predicts that (GDK_ST_AMISE_ABORT) instead of handing back the
+    3-parameter minimum its Newton iteration finds there (c = 0.78, widths +50 %: found on the CPU with the device code
+    compiled for the host)."""
+    from getdist_b200 import MCSamples, _abi
+    from oracle.getdist_oracle import OracleSamples
+
+    rng = np.random.default_rng(18)
+    N = 2500
+    u, v, t = rng.normal(size=N), rng.normal(size=N), rng.normal(size=N)
+    X = np.column_stack([np.abs(u), v, 0.6 * t + 0.1 * np.abs(u)])
+    names = ["a", "b", "c"]
+    mc = MCSamples(samples=X, names=names, sampler="uncorrelated")
+    o = OracleSamples(X, None, names=names, sampler="uncorrelated")
+    d = mc.get2DDensity(0, 2)
+    want = o.density_2d(0, 2)
+    st = int(d._gdk["status"])
+    assert st & _abi.ST_AMISE_ABORT and st & _abi.ST_AMISE_CORR and not st & _abi.ST_AMISE_FULL, st
+    corr = mc.getCorrelationMatrix()[2][0]
+    assert abs(d._gdk["c"] - corr) < 1e-12 and abs(want.corr - corr) < 1e-9
+    np.testing.assert_allclose([d._gdk["rx"], d._gdk["ry"]], [want.rx, want.ry], rtol=1e-3)
+    assert d._gdk["winw"] == want.winw
+    assert np.max(np.abs(d.P - want.P)) < 1e-4  # the refused minimum would differ by ~0.1
