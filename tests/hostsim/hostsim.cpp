@@ -187,3 +187,54 @@ int hs_contours(const double* P, int G, const double* contours, int nc, double* 
     return (int)contour_levels_core(co, P, G, contours, nc, levels);
 }
 }
+
+// ---- trace of the ISJ fixed-point solve (the fsolve stage of kde1d_core) on a given histogram: evaluation points and
+// values of hybrd1_port, for side-by-side comparison with scipy.optimize.fsolve on the same function
+extern "C" int hs_isj_trace(const double* bins, int F, double neff, double* xs, double* fs, int* nfev, double* xout) {
+    CoopHost co;
+    IsjConsts K;
+    gdk_fill_isj_consts(&K);
+    std::vector<double> aux(F), aux2(F), a2(F), logI(F);
+    std::vector<cplx> ca(F), cb(F), tw, tw4;
+    std::vector<double> c4;
+    double total = 0;
+    for (int i = 0; i < F; i++) total += bins[i];
+    for (int i = 0; i < F; i++) aux[i] = bins[i] / total;
+    if (is_pow2(F)) {
+        tw.resize(F);
+        tw4.resize(F);
+        gdk_fill_roots(tw.data(), F, F);
+        gdk_fill_roots(tw4.data(), 4 * F, F);
+        dct2_lines_pow2(co, aux.data(), aux2.data(), ca.data(), cb.data(), F, 1, tw.data(), tw4.data());
+    } else {
+        c4.resize(4 * (size_t)F);
+        gdk_fill_cos(c4.data(), 4 * F);
+        dct2_lines_direct(co, aux.data(), aux2.data(), F, 1, c4.data());
+    }
+    for (int k = 1; k < F; k++) {
+        const double a = aux2[k] / 2;
+        a2[k - 1] = a * a;
+        logI[k - 1] = log((double)k * (double)k);
+    }
+    IsjFixedPoint<CoopHost> fp{co, K, a2.data(), logI.data(), F, neff};
+    struct Traced {
+        IsjFixedPoint<CoopHost>& f;
+        double* xs;
+        double* fs;
+        int n;
+        double operator()(double h, int& fail) {
+            const double v = f(h, fail);
+            if (n < 512) {
+                xs[n] = h;
+                fs[n] = v;
+            }
+            n++;
+            return v;
+        }
+    } tr{fp, xs, fs, 0};
+    const double h0 = 0.53 * pow(neff, -1.0 / 5);
+    RootResult rr = hybrd1_port(tr, h0, h0 / 20, 1.0, 400);
+    *nfev = tr.n;
+    *xout = rr.x;
+    return rr.status;
+}
